@@ -1,0 +1,359 @@
+"""ctypes binding of libvr.so (include/vr.h) — the Python view of the C-ABI used by tests/ and bench.py.
+
+The product is the CUDA library; this module only marshals numpy buffers into it.  There is no CPU fallback:
+if libvr.so is missing, or no B200 is visible, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvr.so")
+
+VR_TF_USE_GRADIENT = 1
+VR_TF_THRESHOLD = 2
+VR_TF_MAX_RECTS = 16
+
+
+class VrError(RuntimeError):
+    pass
+
+
+class TfRect(C.Structure):
+    _fields_ = [("min_v", C.c_float), ("max_v", C.c_float), ("min_g", C.c_float), ("max_g", C.c_float),
+                ("flags", C.c_int32), ("rgba", C.c_int32 * 4)]
+
+    def as_dict(self):
+        return {"min_v": self.min_v, "max_v": self.max_v, "min_g": self.min_g, "max_g": self.max_g,
+                "flags": self.flags, "rgba": tuple(self.rgba)}
+
+
+# every symbol include/vr.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "vr_last_error": (C.c_char_p, []),
+    "vr_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "vr_ctx_destroy": (None, [_P]),
+    "vr_ctx_synchronize": (C.c_int, [_P]),
+    "vr_ctx_stream": (_P, [_P]),
+    "vr_ctx_launch_count": (C.c_uint64, [_P]),
+    "vr_tf_parse": (C.c_int, [C.c_char_p, C.POINTER(TfRect), C.c_int, C.POINTER(C.c_int)]),
+    "vr_tf_format": (C.c_int, [C.POINTER(TfRect), C.c_int, C.c_char_p, C.c_size_t]),
+    "vr_volume_upload": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vr_volume_destroy": (None, [_P]),
+    "vr_volume_stats": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "vr_volume_set_value_clip": (C.c_int, [_P, C.c_int, C.c_int]),
+    "vr_volume_set_gradient_clip": (C.c_int, [_P, C.c_int, C.c_int]),
+    "vr_volume_clipped_stats": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "vr_volume_dims": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "vr_volume_clip": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "vr_volume_filter": (C.c_int, [_P]),
+    "vr_volume_download": (C.c_int, [_P, _P]),
+    "vr_histogram": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), _P]),
+    "vr_envmap_bind": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vr_envmap_destroy": (None, [_P]),
+    "vr_sdf_build": (C.c_int, [_P, _P, C.POINTER(TfRect), C.c_int, C.POINTER(_P)]),
+    "vr_sdf_destroy": (None, [_P]),
+    "vr_sdf_download": (C.c_int, [_P, _P]),
+    "vr_sdf_levels": (C.c_int, [_P]),
+    "vr_renderer_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vr_renderer_destroy": (None, [_P]),
+    "vr_renderer_set_scene": (C.c_int, [_P, _P, _P]),
+    "vr_renderer_set_tf": (C.c_int, [_P, C.POINTER(TfRect), C.c_int]),
+    "vr_renderer_set_tf_code": (C.c_int, [_P, C.c_char_p]),
+    "vr_renderer_flush": (C.c_int, [_P]),
+    "vr_renderer_reset_cache": (C.c_int, [_P]),
+    "vr_render_frame": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, _P]),
+    "vr_render_frames": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int, _P]),
+    "vr_render_tf": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "vr_renderer_host_frame": (_P, [_P]),
+    "vr_cache_download": (C.c_int, [_P, _P]),
+    "vr_renderer_sdf": (_P, [_P]),
+    "vr_renderer_set_token_cap": (C.c_int, [_P, C.c_int]),
+    "vr_renderer_set_rows": (C.c_int, [_P, C.c_int, C.c_int]),
+    "vr_renderer_cache_device_ptr": (_P, [_P]),
+    "vr_renderer_cache_bytes": (C.c_size_t, [_P]),
+    "vr_renderer_frame_device_ptr": (_P, [_P]),
+    "vr_renderer_resolve": (C.c_int, [_P, _P]),
+    "vr_renderer_enable_counters": (C.c_int, [_P, C.c_int]),
+    "vr_renderer_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads libvr.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VrError(f"{LIB_PATH} is missing: build it with `make` (there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _check(status):
+    if status != 0:
+        raise VrError(f"vr status {status}: {lib().vr_last_error().decode(errors='replace')}")
+
+
+def make_rects(specs):
+    arr = (TfRect * max(len(specs), 1))()
+    for i, s in enumerate(specs):
+        arr[i].min_v = s.get("min_v", 0.0)
+        arr[i].max_v = s.get("max_v", 0.0)
+        arr[i].min_g = s.get("min_g", 0.0)
+        arr[i].max_g = s.get("max_g", 0.0)
+        arr[i].flags = s.get("flags", 0)
+        col = s.get("rgba", (0, 0, 0, 0))
+        for k in range(4):
+            arr[i].rgba[k] = col[k]
+    return arr, len(specs)
+
+
+def tf_parse(src):
+    out = (TfRect * VR_TF_MAX_RECTS)()
+    n = C.c_int(0)
+    _check(lib().vr_tf_parse(src.encode(), out, VR_TF_MAX_RECTS, C.byref(n)))
+    return [out[i].as_dict() for i in range(n.value)]
+
+
+def tf_format(specs):
+    arr, n = make_rects(specs)
+    buf = C.create_string_buffer(8192)
+    _check(lib().vr_tf_format(arr, n, buf, 8192))
+    return buf.value.decode()
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class Context:
+    def __init__(self, device=0):
+        self.h = _P()
+        _check(lib().vr_ctx_create(device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().vr_ctx_destroy(self.h)
+            self.h = _P()
+
+    def synchronize(self):
+        _check(lib().vr_ctx_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return lib().vr_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(lib().vr_ctx_launch_count(self.h))
+
+
+class Volume:
+    """reference_volume (app/reference_volume.hpp:27-63)"""
+
+    def __init__(self, ctx, voxels):
+        voxels = np.ascontiguousarray(voxels, dtype=np.int16)
+        assert voxels.ndim == 3, "volume must be [nz, ny, nx]"
+        nz, ny, nx = voxels.shape
+        self.ctx = ctx
+        self.h = _P()
+        _check(lib().vr_volume_upload(ctx.h, _vp(voxels), nx, ny, nz, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().vr_volume_destroy(self.h)
+            self.h = _P()
+
+    def stats(self):
+        s = (C.c_int32 * 4)()
+        _check(lib().vr_volume_stats(self.h, s))
+        return list(s)
+
+    def set_value_clip(self, lo, hi):
+        _check(lib().vr_volume_set_value_clip(self.h, lo, hi))
+
+    def set_gradient_clip(self, lo, hi):
+        _check(lib().vr_volume_set_gradient_clip(self.h, lo, hi))
+
+    def clipped_stats(self):
+        s = (C.c_float * 4)()
+        _check(lib().vr_volume_clipped_stats(self.h, s))
+        return list(s)
+
+    def dims(self):
+        d = (C.c_int * 3)()
+        _check(lib().vr_volume_dims(self.h, d))
+        return list(d)
+
+    def clip(self, mn, mx):
+        _check(lib().vr_volume_clip(self.h, (C.c_uint32 * 3)(*mn), (C.c_uint32 * 3)(*mx)))
+
+    def filter(self):
+        _check(lib().vr_volume_filter(self.h))
+
+    def download(self):
+        nx, ny, nz = self.dims()
+        out = np.empty((nz, ny, nx), dtype=np.int16)
+        _check(lib().vr_volume_download(self.h, _vp(out)))
+        return out
+
+    def histogram(self, width, height, rng):
+        bins = np.empty(width * height, dtype=np.uint32)
+        _check(lib().vr_histogram(self.h, width, height, (C.c_float * 4)(*rng), _vp(bins)))
+        return bins
+
+
+class EnvMap:
+    def __init__(self, ctx, rgba):
+        rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+        assert rgba.ndim == 3 and rgba.shape[2] == 4
+        self.h = _P()
+        _check(lib().vr_envmap_bind(ctx.h, _vp(rgba), rgba.shape[1], rgba.shape[0], C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().vr_envmap_destroy(self.h)
+            self.h = _P()
+
+
+class Sdf:
+    """signed_distance_field (app/signed_distance_field.hpp:5-12)"""
+
+    def __init__(self, ctx, volume, tf_specs):
+        arr, n = make_rects(tf_specs)
+        self.h = _P()
+        self.dims = volume.dims()
+        _check(lib().vr_sdf_build(ctx.h, volume.h, arr, n, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().vr_sdf_destroy(self.h)
+            self.h = _P()
+
+    def download(self):
+        nx, ny, nz = self.dims
+        out = np.empty((nz, ny, nx), dtype=np.int8)
+        _check(lib().vr_sdf_download(self.h, _vp(out)))
+        return out
+
+    @property
+    def levels(self):
+        return lib().vr_sdf_levels(self.h)
+
+
+class Renderer:
+    """renderer : frame_emitter (app/renderer.hpp:10-29)"""
+
+    def __init__(self, ctx, width, height):
+        self.ctx = ctx
+        self.W, self.H = width, height
+        self.h = _P()
+        self.volume = None
+        _check(lib().vr_renderer_create(ctx.h, width, height, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().vr_renderer_destroy(self.h)
+            self.h = _P()
+
+    def image_set(self, volume, env):
+        self.volume = volume
+        self.env = env
+        _check(lib().vr_renderer_set_scene(self.h, volume.h, env.h))
+
+    def set_tf(self, tf_specs):
+        arr, n = make_rects(tf_specs)
+        _check(lib().vr_renderer_set_tf(self.h, arr, n))
+
+    def next_event_code_set(self, cl_code):
+        _check(lib().vr_renderer_set_tf_code(self.h, cl_code.encode()))
+
+    def flush_changes(self):
+        _check(lib().vr_renderer_flush(self.h))
+
+    def reset_cache(self):
+        _check(lib().vr_renderer_reset_cache(self.h))
+
+    def host_frame(self):
+        """numpy view of the renderer-owned pinned frame buffer"""
+        p = lib().vr_renderer_host_frame(self.h)
+        buf = (C.c_uint8 * (self.W * self.H * 4)).from_address(p)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(self.H, self.W, 4)
+
+    def render_frame(self, pos, direction, seed, readback=True, out=None):
+        if readback:
+            if out is None:
+                out = np.empty((self.H, self.W, 4), dtype=np.uint8)
+            _check(lib().vr_render_frame(self.h, _f3(pos), _f3(direction), C.c_int32(seed), _vp(out)))
+            return out
+        _check(lib().vr_render_frame(self.h, _f3(pos), _f3(direction), C.c_int32(seed), None))
+        return None
+
+    def render_frames(self, pos, direction, seeds, readback=True, out=None):
+        seeds = (C.c_int32 * len(seeds))(*[int(s) for s in seeds])
+        if readback and out is None:
+            out = np.empty((self.H, self.W, 4), dtype=np.uint8)
+        _check(lib().vr_render_frames(self.h, _f3(pos), _f3(direction), seeds, len(seeds),
+                                      _vp(out) if readback else None))
+        return out if readback else None
+
+    def resolve(self, readback=True):
+        out = np.empty((self.H, self.W, 4), dtype=np.uint8) if readback else None
+        _check(lib().vr_renderer_resolve(self.h, _vp(out) if readback else None))
+        return out
+
+    def render_tf(self, width, height):
+        out = np.empty((height, width, 4), dtype=np.uint8)
+        _check(lib().vr_render_tf(self.h, width, height, _vp(out)))
+        return out
+
+    def cache_download(self):
+        n = lib().vr_renderer_cache_bytes(self.h) // 2
+        out = np.empty(n, dtype=np.uint16)
+        _check(lib().vr_cache_download(self.h, _vp(out)))
+        return out
+
+    def sdf_download(self):
+        nx, ny, nz = self.volume.dims()
+        out = np.empty((nz, ny, nx), dtype=np.int8)
+        _check(lib().vr_sdf_download(lib().vr_renderer_sdf(self.h), _vp(out)))
+        return out
+
+    def set_token_cap(self, cap):
+        _check(lib().vr_renderer_set_token_cap(self.h, cap))
+
+    def set_rows(self, y0, y1):
+        _check(lib().vr_renderer_set_rows(self.h, y0, y1))
+
+    @property
+    def cache_device_ptr(self):
+        return lib().vr_renderer_cache_device_ptr(self.h)
+
+    @property
+    def cache_bytes(self):
+        return int(lib().vr_renderer_cache_bytes(self.h))
+
+    @property
+    def frame_device_ptr(self):
+        return lib().vr_renderer_frame_device_ptr(self.h)
+
+    def enable_counters(self, on=True):
+        _check(lib().vr_renderer_enable_counters(self.h, 1 if on else 0))
+
+    def counters(self, reset=False):
+        c = (C.c_uint64 * 6)()
+        _check(lib().vr_renderer_counters(self.h, c, 1 if reset else 0))
+        return dict(zip(["steps", "normals", "env", "primary_hits", "admitted", "samples"], [int(v) for v in c]))

@@ -1,0 +1,474 @@
+// vr_api.cu — the extern "C" surface of include/vr.h: handle lifetime, uploads/downloads and the host-side
+// sequencing of the reference's renderer / reference_volume / signed_distance_field classes.
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include <set>
+#include "vr_internal.h"
+
+static thread_local char g_err[1024] = "";
+
+void vr_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* vr_last_error(void) { return g_err; }
+
+// ---- context -------------------------------------------------------------------------------------------------
+extern "C" int vr_ctx_create(int device_ordinal, vr_ctx** out) {
+  VR_REQUIRE(out, "vr_ctx_create: null out");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    vr_set_error("vr_ctx_create: no usable CUDA device (%s) — this library has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return VR_ERR_CUDA;
+  }
+  VR_REQUIRE(device_ordinal >= 0 && device_ordinal < count, "vr_ctx_create: device ordinal out of range");
+  VR_CUDA(cudaSetDevice(device_ordinal));
+  cudaDeviceProp prop;
+  VR_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+  if (prop.major != 10) {
+    vr_set_error("vr_ctx_create: device %d is sm_%d%d; this build contains sm_100a code only", device_ordinal,
+                 prop.major, prop.minor);
+    return VR_ERR_CUDA;
+  }
+  vr_ctx* c = new (std::nothrow) vr_ctx();
+  if (!c) return VR_ERR_NOMEM;
+  c->device = device_ordinal;
+  c->sm_count = prop.multiProcessorCount;
+  VR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  VR_CUDA(cudaMalloc(&c->scratch, 4096));
+  VR_CUDA(cudaMallocHost(&c->scratch_host, 4096));
+  *out = c;
+  return VR_OK;
+}
+
+extern "C" void vr_ctx_destroy(vr_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->scratch);
+  cudaFreeHost(c->scratch_host);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int vr_ctx_synchronize(vr_ctx* c) {
+  VR_REQUIRE(c, "vr_ctx_synchronize: null ctx");
+  VR_CUDA(cudaStreamSynchronize(c->stream));
+  return VR_OK;
+}
+
+extern "C" void* vr_ctx_stream(vr_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" uint64_t vr_ctx_launch_count(const vr_ctx* c) { return c ? c->launches : 0; }
+
+// ---- volume --------------------------------------------------------------------------------------------------
+extern "C" int vr_volume_upload(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz, vr_volume** out) {
+  VR_REQUIRE(ctx && voxels && out, "vr_volume_upload: null argument");
+  VR_REQUIRE(nx > 0 && ny > 0 && nz > 0, "vr_volume_upload: dimensions must be positive");
+  VR_REQUIRE((size_t)nx * ny * nz < ((size_t)1 << 32) - 1, "vr_volume_upload: more than 2^32-2 voxels");
+  VR_CUDA(cudaSetDevice(ctx->device));
+  vr_volume* v = new (std::nothrow) vr_volume();
+  if (!v) return VR_ERR_NOMEM;
+  v->ctx = ctx;
+  v->onx = v->nx = nx; v->ony = v->ny = ny; v->onz = v->nz = nz;
+  const size_t bytes = v->count() * sizeof(int16_t);
+  VR_CUDA(cudaMalloc(&v->original, bytes));
+  VR_CUDA(cudaMemcpyAsync(v->original, voxels, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int s = vrk_fetch_stats(ctx, v->original, nx, ny, nz, v->stats);  // reference_volume.cpp:22-41
+  if (s != VR_OK) { cudaFree(v->original); delete v; return s; }
+  *out = v;
+  return VR_OK;
+}
+
+extern "C" void vr_volume_destroy(vr_volume* v) {
+  if (!v) return;
+  cudaSetDevice(v->ctx->device);
+  cudaStreamSynchronize(v->ctx->stream);
+  cudaFree(v->original);
+  cudaFree(v->cropped);
+  delete v;
+}
+
+extern "C" int vr_volume_stats(const vr_volume* v, int32_t out[4]) {
+  VR_REQUIRE(v && out, "vr_volume_stats: null argument");
+  memcpy(out, v->stats, sizeof(v->stats));
+  return VR_OK;
+}
+
+extern "C" int vr_volume_dims(const vr_volume* v, int out[3]) {
+  VR_REQUIRE(v && out, "vr_volume_dims: null argument");
+  out[0] = v->nx; out[1] = v->ny; out[2] = v->nz;
+  return VR_OK;
+}
+
+extern "C" int vr_volume_clip(vr_volume* v, const uint32_t mn[3], const uint32_t mx[3]) {
+  VR_REQUIRE(v && mn && mx, "vr_volume_clip: null argument");
+  // reference_volume.cpp:57-59 asserts min < max; reads beyond the original are border reads (0)
+  VR_REQUIRE(mn[0] < mx[0] && mn[1] < mx[1] && mn[2] < mx[2], "vr_volume_clip: min must be < max on every axis");
+  VR_CUDA(cudaSetDevice(v->ctx->device));
+  const int nx = (int)(mx[0] - mn[0]), ny = (int)(mx[1] - mn[1]), nz = (int)(mx[2] - mn[2]);
+  int16_t* dst = nullptr;
+  VR_CUDA(cudaMalloc(&dst, (size_t)nx * ny * nz * sizeof(int16_t)));
+  int s = vrk_clip(v->ctx, v->original, v->onx, v->ony, v->onz, mn, dst, nx, ny, nz);
+  if (s != VR_OK) { cudaFree(dst); return s; }
+  VR_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  cudaFree(v->cropped);
+  v->cropped = dst;
+  v->nx = nx; v->ny = ny; v->nz = nz;
+  return VR_OK;
+}
+
+extern "C" int vr_volume_filter(vr_volume* v) {
+  VR_REQUIRE(v, "vr_volume_filter: null argument");
+  VR_CUDA(cudaSetDevice(v->ctx->device));
+  int16_t* dst = nullptr;
+  VR_CUDA(cudaMalloc(&dst, v->count() * sizeof(int16_t)));
+  int s = vrk_bilateral(v->ctx, v->current(), dst, v->nx, v->ny, v->nz);
+  if (s != VR_OK) { cudaFree(dst); return s; }
+  VR_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  // `ref = std::move(buffer)` (reference_volume.cpp:77): the filtered data replaces the current volume
+  if (v->cropped) { cudaFree(v->cropped); v->cropped = dst; }
+  else { cudaFree(v->original); v->original = dst; }
+  return VR_OK;
+}
+
+extern "C" int vr_volume_download(const vr_volume* v, int16_t* out) {
+  VR_REQUIRE(v && out, "vr_volume_download: null argument");
+  VR_CUDA(cudaSetDevice(v->ctx->device));
+  VR_CUDA(cudaMemcpyAsync(out, v->current(), v->count() * sizeof(int16_t), cudaMemcpyDeviceToHost, v->ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return VR_OK;
+}
+
+extern "C" int vr_histogram(const vr_volume* v, int width, int height, const float range[4], uint32_t* bins_out) {
+  VR_REQUIRE(v && range && bins_out, "vr_histogram: null argument");
+  VR_REQUIRE(width > 0 && height > 0 && (size_t)width * height < ((size_t)1 << 31), "vr_histogram: bad bin grid");
+  VR_CUDA(cudaSetDevice(v->ctx->device));
+  uint32_t* bins = nullptr;
+  const size_t bytes = sizeof(uint32_t) * (size_t)width * height;
+  VR_CUDA(cudaMalloc(&bins, bytes));
+  int s = vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins);
+  if (s == VR_OK) {
+    cudaError_t e = cudaMemcpyAsync(bins_out, bins, bytes, cudaMemcpyDeviceToHost, v->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(v->ctx->stream);
+    if (e != cudaSuccess) { vr_set_error("vr_histogram: %s", cudaGetErrorString(e)); s = VR_ERR_CUDA; }
+  }
+  cudaFree(bins);
+  return s;
+}
+
+// ---- environment map -------------------------------------------------------------------------------------------
+extern "C" int vr_envmap_bind(vr_ctx* ctx, const uint8_t* rgba8, int w, int h, vr_envmap** out) {
+  VR_REQUIRE(ctx && rgba8 && out, "vr_envmap_bind: null argument");
+  VR_REQUIRE(w > 0 && h > 0, "vr_envmap_bind: dimensions must be positive");
+  VR_CUDA(cudaSetDevice(ctx->device));
+  vr_envmap* e = new (std::nothrow) vr_envmap();
+  if (!e) return VR_ERR_NOMEM;
+  e->ctx = ctx; e->w = w; e->h = h;
+  VR_CUDA(cudaMalloc(&e->texels, (size_t)w * h * 4));
+  VR_CUDA(cudaMemcpyAsync(e->texels, rgba8, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = e;
+  return VR_OK;
+}
+
+extern "C" void vr_envmap_destroy(vr_envmap* e) {
+  if (!e) return;
+  cudaSetDevice(e->ctx->device);
+  cudaStreamSynchronize(e->ctx->stream);
+  cudaFree(e->texels);
+  delete e;
+}
+
+// ---- SDF -----------------------------------------------------------------------------------------------------
+static int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, vr_sdf** out) {
+  VR_CUDA(cudaSetDevice(ctx->device));
+  vr_sdf* s = new (std::nothrow) vr_sdf();
+  if (!s) return VR_ERR_NOMEM;
+  s->ctx = ctx; s->nx = vol->nx; s->ny = vol->ny; s->nz = vol->nz;
+  cudaError_t e = cudaMalloc(&s->field, vol->count());
+  if (e != cudaSuccess) { delete s; vr_set_error("vr_sdf_build: %s", cudaGetErrorString(e)); return VR_ERR_CUDA; }
+  int st = vrk_sdf_build(ctx, vol->current(), vol->nx, vol->ny, vol->nz, tf, s->field, &s->levels, &s->max_it);
+  if (st != VR_OK) { cudaFree(s->field); delete s; return st; }
+  *out = s;
+  return VR_OK;
+}
+
+extern "C" int vr_sdf_build(vr_ctx* ctx, const vr_volume* vol, const vr_tf_rect* rects, int n_rects, vr_sdf** out) {
+  VR_REQUIRE(ctx && vol && out && (rects || n_rects == 0), "vr_sdf_build: null argument");
+  VR_REQUIRE(n_rects >= 0 && n_rects <= VR_TF_MAX_RECTS, "vr_sdf_build: too many TF clauses");
+  return sdf_build_impl(ctx, vol, vr_make_tf_table(rects, n_rects), out);
+}
+
+extern "C" void vr_sdf_destroy(vr_sdf* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->field);
+  delete s;
+}
+
+extern "C" int vr_sdf_download(const vr_sdf* s, int8_t* out) {
+  VR_REQUIRE(s && out, "vr_sdf_download: null argument");
+  VR_CUDA(cudaSetDevice(s->ctx->device));
+  VR_CUDA(cudaMemcpyAsync(out, s->field, (size_t)s->nx * s->ny * s->nz, cudaMemcpyDeviceToHost, s->ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  return VR_OK;
+}
+
+extern "C" int vr_sdf_levels(const vr_sdf* s) { return s ? s->levels : 0; }
+
+// ---- renderer --------------------------------------------------------------------------------------------------
+extern "C" int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_renderer** out) {
+  VR_REQUIRE(ctx && out, "vr_renderer_create: null argument");
+  VR_REQUIRE(width > 0 && height > 0, "vr_renderer_create: frame size must be positive");
+  VR_CUDA(cudaSetDevice(ctx->device));
+  vr_renderer* r = new (std::nothrow) vr_renderer();
+  if (!r) return VR_ERR_NOMEM;
+  r->ctx = ctx; r->W = width; r->H = height; r->row0 = 0; r->row1 = height;
+  const size_t px = (size_t)width * height;
+  VR_CUDA(cudaMalloc(&r->frame, px * 4));
+  VR_CUDA(cudaMalloc(&r->hit, px * 4));
+  VR_CUDA(cudaMalloc(&r->counters, 6 * sizeof(unsigned long long)));
+  VR_CUDA(cudaMallocHost(&r->frame_host, px * 4));
+  VR_CUDA(cudaMemsetAsync(r->frame, 0, px * 4, ctx->stream));
+  VR_CUDA(cudaMemsetAsync(r->hit, 0xFF, px * 4, ctx->stream));
+  VR_CUDA(cudaMemsetAsync(r->counters, 0, 6 * sizeof(unsigned long long), ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = r;
+  return VR_OK;
+}
+
+extern "C" void vr_renderer_destroy(vr_renderer* r) {
+  if (!r) return;
+  cudaSetDevice(r->ctx->device);
+  cudaStreamSynchronize(r->ctx->stream);
+  vr_sdf_destroy(r->sdf);
+  cudaFree(r->cache);
+  cudaFree(r->hit);
+  cudaFree(r->frame);
+  cudaFree(r->counters);
+  cudaFreeHost(r->frame_host);
+  delete r;
+}
+
+extern "C" int vr_renderer_set_scene(vr_renderer* r, const vr_volume* vol, const vr_envmap* env) {
+  VR_REQUIRE(r && vol && env, "vr_renderer_set_scene: null argument");
+  VR_REQUIRE(vol->ctx == r->ctx && env->ctx == r->ctx, "vr_renderer_set_scene: objects belong to another context");
+  r->vol = vol;
+  r->env = env;
+  return VR_OK;
+}
+
+extern "C" int vr_renderer_set_tf(vr_renderer* r, const vr_tf_rect* rects, int n_rects) {
+  VR_REQUIRE(r && (rects || n_rects == 0), "vr_renderer_set_tf: null argument");
+  VR_REQUIRE(n_rects >= 0 && n_rects <= VR_TF_MAX_RECTS, "vr_renderer_set_tf: too many TF clauses");
+  r->tf_pending = vr_make_tf_table(rects, n_rects);
+  r->have_tf = true;
+  return VR_OK;
+}
+
+extern "C" int vr_renderer_set_tf_code(vr_renderer* r, const char* src) {
+  VR_REQUIRE(r && src, "vr_renderer_set_tf_code: null argument");
+  vr_tf_rect rects[VR_TF_MAX_RECTS];
+  int n = 0;
+  VR_TRY(vr_tf_parse(src, rects, VR_TF_MAX_RECTS, &n));
+  return vr_renderer_set_tf(r, rects, n);
+}
+
+extern "C" int vr_renderer_reset_cache(vr_renderer* r) {
+  VR_REQUIRE(r && r->cache, "vr_renderer_reset_cache: no cache (call vr_renderer_flush first)");
+  VR_CUDA(cudaSetDevice(r->ctx->device));
+  return vrk_cache_reset(r->ctx, r->cache, r->cache_voxels);
+}
+
+extern "C" int vr_renderer_flush(vr_renderer* r) {
+  VR_REQUIRE(r && r->vol && r->env, "vr_renderer_flush: no scene bound (vr_renderer_set_scene)");
+  VR_REQUIRE(r->have_tf, "vr_renderer_flush: no transfer function set");
+  VR_CUDA(cudaSetDevice(r->ctx->device));
+  // renderer.cpp:29-30 — reallocate the cache only when the volume size changed
+  const size_t voxels = r->vol->count();
+  if (voxels != r->cache_voxels) {
+    VR_CUDA(cudaStreamSynchronize(r->ctx->stream));
+    cudaFree(r->cache);
+    r->cache = nullptr;
+    r->cache_voxels = 0;
+    VR_CUDA(cudaMalloc(&r->cache, voxels * 8));
+    r->cache_voxels = voxels;
+  }
+  VR_TRY(vrk_cache_reset(r->ctx, r->cache, r->cache_voxels));  // renderer.cpp:32-35
+  r->tf_active = r->tf_pending;                                  // renderer.cpp:39
+  vr_sdf* fresh = nullptr;                                       // renderer.cpp:42
+  VR_TRY(sdf_build_impl(r->ctx, r->vol, r->tf_active, &fresh));
+  vr_sdf_destroy(r->sdf);
+  r->sdf = fresh;
+  VR_CUDA(cudaMemsetAsync(r->hit, 0xFF, (size_t)r->W * r->H * 4, r->ctx->stream));
+  return VR_OK;
+}
+
+static int read_frame(vr_renderer* r, uint8_t* host_rgba) {
+  if (!host_rgba) return VR_OK;
+  VR_CUDA(cudaMemcpyAsync(host_rgba, r->frame, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost, r->ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(r->ctx->stream));  // blocking pull, renderer.cpp:150
+  return VR_OK;
+}
+
+extern "C" int vr_render_frame(vr_renderer* r, const float pos[3], const float dir[3], int32_t seed,
+                               uint8_t* host_rgba) {
+  VR_REQUIRE(r && pos && dir, "vr_render_frame: null argument");
+  VR_REQUIRE(r->sdf && r->cache, "vr_render_frame: call vr_renderer_flush first");
+  VR_CUDA(cudaSetDevice(r->ctx->device));
+  VR_TRY(vrk_render(r, pos, dir, seed, true, true));
+  return read_frame(r, host_rgba);
+}
+
+extern "C" int vr_render_frames(vr_renderer* r, const float pos[3], const float dir[3], const int32_t* seeds,
+                                int n_frames, uint8_t* host_rgba) {
+  VR_REQUIRE(r && pos && dir && seeds && n_frames > 0, "vr_render_frames: bad argument");
+  VR_REQUIRE(r->sdf && r->cache, "vr_render_frames: call vr_renderer_flush first");
+  VR_CUDA(cudaSetDevice(r->ctx->device));
+  for (int k = 0; k < n_frames; ++k) VR_TRY(vrk_render(r, pos, dir, seeds[k], true, true));
+  return read_frame(r, host_rgba);
+}
+
+extern "C" int vr_renderer_resolve(vr_renderer* r, uint8_t* host_rgba) {
+  VR_REQUIRE(r && r->sdf && r->cache, "vr_renderer_resolve: call vr_renderer_flush first");
+  VR_CUDA(cudaSetDevice(r->ctx->device));
+  const float z[3] = {0, 0, 0};
+  VR_TRY(vrk_render(r, z, z, 0, false, true));
+  return read_frame(r, host_rgba);
+}
+
+extern "C" uint8_t* vr_renderer_host_frame(vr_renderer* r) { return r ? r->frame_host : nullptr; }
+
+extern "C" int vr_cache_download(const vr_renderer* r, uint16_t* out) {
+  VR_REQUIRE(r && out && r->cache, "vr_cache_download: no cache");
+  VR_CUDA(cudaSetDevice(r->ctx->device));
+  VR_CUDA(cudaMemcpyAsync(out, r->cache, r->cache_voxels * 8, cudaMemcpyDeviceToHost, r->ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(r->ctx->stream));
+  return VR_OK;
+}
+
+extern "C" const vr_sdf* vr_renderer_sdf(const vr_renderer* r) { return r ? r->sdf : nullptr; }
+
+extern "C" int vr_renderer_set_token_cap(vr_renderer* r, int cap) {
+  VR_REQUIRE(r && cap >= 1 && cap <= 256, "vr_renderer_set_token_cap: cap must be in [1,256]");
+  r->token_cap = cap;
+  return VR_OK;
+}
+
+extern "C" int vr_renderer_set_rows(vr_renderer* r, int y0, int y1) {
+  VR_REQUIRE(r && y0 >= 0 && y1 <= r->H && y0 <= y1, "vr_renderer_set_rows: rows out of range");
+  r->row0 = y0; r->row1 = y1;
+  return VR_OK;
+}
+
+extern "C" void* vr_renderer_cache_device_ptr(const vr_renderer* r) { return r ? (void*)r->cache : nullptr; }
+extern "C" size_t vr_renderer_cache_bytes(const vr_renderer* r) { return r ? r->cache_voxels * 8 : 0; }
+extern "C" void* vr_renderer_frame_device_ptr(const vr_renderer* r) { return r ? (void*)r->frame : nullptr; }
+
+extern "C" int vr_renderer_enable_counters(vr_renderer* r, int enable) {
+  VR_REQUIRE(r, "vr_renderer_enable_counters: null argument");
+  r->count = enable != 0;
+  return VR_OK;
+}
+
+extern "C" int vr_renderer_counters(const vr_renderer* r, uint64_t out[6], int reset) {
+  VR_REQUIRE(r && out, "vr_renderer_counters: null argument");
+  VR_CUDA(cudaSetDevice(r->ctx->device));
+  VR_CUDA(cudaMemcpyAsync(out, r->counters, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, r->ctx->stream));
+  if (reset) VR_CUDA(cudaMemsetAsync(r->counters, 0, 6 * sizeof(uint64_t), r->ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(r->ctx->stream));
+  return VR_OK;
+}
+
+// ---- render_tf: renderer.cpp:45-124 ---------------------------------------------------------------------------------
+extern "C" int vr_volume_set_value_clip(vr_volume* v, int lo, int hi) {
+  VR_REQUIRE(v, "vr_volume_set_value_clip: null argument");
+  v->value_clip[0] = lo; v->value_clip[1] = hi;
+  return VR_OK;
+}
+extern "C" int vr_volume_set_gradient_clip(vr_volume* v, int lo, int hi) {
+  VR_REQUIRE(v, "vr_volume_set_gradient_clip: null argument");
+  v->gradient_clip[0] = lo; v->gradient_clip[1] = hi;
+  return VR_OK;
+}
+// get_volume_stats(), reference_volume.cpp:82-88,110-112
+extern "C" int vr_volume_clipped_stats(const vr_volume* v, float out[4]) {
+  VR_REQUIRE(v && out, "vr_volume_clipped_stats: null argument");
+  out[0] = (float)std::max(v->value_clip[0], v->stats[0]);
+  out[1] = (float)std::min(v->value_clip[1], v->stats[1]);
+  out[2] = (float)std::max(v->gradient_clip[0], v->stats[2]);
+  out[3] = (float)std::min(v->gradient_clip[1], v->stats[3]);
+  return VR_OK;
+}
+
+extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba_out) {
+  VR_REQUIRE(r && r->vol && rgba_out, "vr_render_tf: no scene bound");
+  VR_REQUIRE(width > 0 && height > 0 && (size_t)width * height < ((size_t)1 << 31), "vr_render_tf: bad size");
+  vr_ctx* ctx = r->ctx;
+  VR_CUDA(cudaSetDevice(ctx->device));
+  const size_t nb = (size_t)width * height;
+  float range[4];
+  VR_TRY(vr_volume_clipped_stats(r->vol, range));
+  uint32_t* bins = nullptr;
+  int32_t* lookup = nullptr;
+  uchar4* img = nullptr;
+  std::vector<uint32_t> h(nb);
+  int status = VR_OK;
+  cudaError_t e = cudaMalloc(&bins, nb * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&img, nb * 4);
+  if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
+  if (status == VR_OK)
+    status = vrk_histogram(ctx, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height, range, bins);
+  if (status == VR_OK) {
+    e = cudaMemcpyAsync(h.data(), bins, nb * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
+  }
+  std::vector<int32_t> lut;
+  if (status == VR_OK) {
+    // renderer.cpp:65-79: round every non-zero count down to two significant digits, collect the distinct values
+    std::set<int> hist;
+    for (int y = 0; y < height; ++y)
+      for (int x = 0; x < width; ++x) {
+        int value = (int)h[(size_t)x * height + y];
+        if (value != 0) {
+          int roundingpart = std::max((int)(pow(10, (std::floor(std::log10(value))) - 1)), (int)1);
+          int corrected = (int)(floor(value / roundingpart) * roundingpart);
+          h[(size_t)x * height + y] = (uint32_t)corrected;
+          hist.insert(corrected);
+        }
+      }
+    lut.assign(hist.begin(), hist.end());
+    if (lut.empty()) {
+      // renderer.cpp:84-86: the colour kernel is skipped, the frame keeps its zero initialisation
+      memset(rgba_out, 0, nb * 4);
+    } else {
+      e = cudaMalloc(&lookup, lut.size() * 4);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(bins, h.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(lookup, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
+      if (status == VR_OK)
+        status = vrk_tf_color_frame(ctx, reinterpret_cast<const int32_t*>(bins), lookup, (int)lut.size(), width, height,
+                                    img);
+      if (status == VR_OK) {
+        e = cudaMemcpyAsync(rgba_out, img, nb * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
+      }
+    }
+  }
+  cudaFree(bins);
+  cudaFree(lookup);
+  cudaFree(img);
+  return status;
+}

@@ -1,0 +1,112 @@
+// vr_internal.h — host-side object model behind the opaque handles of include/vr.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/vr.h"
+
+void vr_set_error(const char* fmt, ...);
+
+#define VR_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      vr_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return VR_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+#define VR_REQUIRE(cond, msg)                                     \
+  do {                                                            \
+    if (!(cond)) {                                                \
+      vr_set_error("%s:%d: %s", __FILE__, __LINE__, msg);         \
+      return VR_ERR_INVALID;                                      \
+    }                                                             \
+  } while (0)
+
+#define VR_TRY(call)          \
+  do {                        \
+    int s__ = (call);         \
+    if (s__ != VR_OK) return s__; \
+  } while (0)
+
+struct vr_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  int32_t* scratch = nullptr;  // small device scratch (counters, stats), 4 KiB
+  int32_t* scratch_host = nullptr;  // pinned mirror
+};
+
+// Device-side TF table, passed to kernels by value.
+struct TfTable {
+  vr_tf_rect r[VR_TF_MAX_RECTS];
+  int n;
+  int needs_gradient;  // any clause carries a gradient test
+};
+
+struct vr_volume {
+  vr_ctx* ctx = nullptr;
+  int16_t* original = nullptr;  // device, x fastest
+  int onx = 0, ony = 0, onz = 0;
+  int16_t* cropped = nullptr;  // device, non-null once clipped (reference_volume.hpp:31-33)
+  int nx = 0, ny = 0, nz = 0;  // dims of the current volume
+  int32_t stats[4] = {0, 0, 0, 0};
+  int value_clip[2] = {INT32_MIN, INT32_MAX};     // reference_volume.hpp:35-36
+  int gradient_clip[2] = {INT32_MIN, INT32_MAX};
+  const int16_t* current() const { return cropped ? cropped : original; }
+  size_t count() const { return (size_t)nx * ny * nz; }
+};
+
+struct vr_envmap {
+  vr_ctx* ctx = nullptr;
+  uchar4* texels = nullptr;
+  int w = 0, h = 0;
+};
+
+struct vr_sdf {
+  vr_ctx* ctx = nullptr;
+  int8_t* field = nullptr;  // device, x fastest (API order)
+  int nx = 0, ny = 0, nz = 0;
+  int levels = 0;
+  int max_it = 0;
+};
+
+struct vr_renderer {
+  vr_ctx* ctx = nullptr;
+  int W = 0, H = 0;
+  int row0 = 0, row1 = 0;
+  const vr_volume* vol = nullptr;
+  const vr_envmap* env = nullptr;
+  TfTable tf_pending{};
+  TfTable tf_active{};
+  bool have_tf = false;
+  vr_sdf* sdf = nullptr;
+  uint32_t* cache = nullptr;  // 2 x uint32 per voxel: lo = R | G<<16, hi = B | tokens<<16 (utility.cl:39-54)
+  size_t cache_voxels = 0;
+  uint32_t* hit = nullptr;    // per pixel: voxel number of the primary hit, 0xFFFFFFFF = env pixel
+  uchar4* frame = nullptr;    // device RGBA8
+  uint8_t* frame_host = nullptr;  // pinned staging (used when the caller's buffer is pageable)
+  int token_cap = 256;
+  bool count = false;
+  unsigned long long* counters = nullptr;  // 6 x u64 on device
+};
+
+// ---- kernel launchers (defined in the .cu files) -----------------------------------------------------
+int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int32_t out[4]);
+int vrk_clip(vr_ctx* ctx, const int16_t* src, int snx, int sny, int snz, const uint32_t start[3], int16_t* dst, int nx,
+             int ny, int nz);
+int vrk_bilateral(vr_ctx* ctx, const int16_t* src, int16_t* dst, int nx, int ny, int nz);
+int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4],
+                  uint32_t* bins_dev);
+int vrk_tf_color_frame(vr_ctx* ctx, const int32_t* bins_dev, const int32_t* lookup_dev, int lookup_len, int width,
+                       int height, uchar4* out_dev);
+int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field,
+                  int* levels_out, int* max_it_out);
+int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels);
+int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], int32_t seed, bool trace, bool resolve);
+
+TfTable vr_make_tf_table(const vr_tf_rect* rects, int n);

@@ -1,0 +1,231 @@
+// vr_volume_ops.cu — streaming kernels over the whole volume: fetch_stats, apply_clip, bilateral_filter,
+// tf_sort_values, tf_flush_color_frame, buffer_reset.  All are HBM- (or, for the bilateral filter, SFU-) bound;
+// none is a contraction, so no tensor cores.
+#include "vr_device.cuh"
+
+// 3-D tile of a block: 32 voxels along x (one warp = one 64-byte row segment), 4 rows, 4 slices.  The y±1 and
+// z±1 gradient taps of a voxel are the centre taps of other warps of the same block, so they hit in L1.
+#define TX 32
+#define TY 4
+#define TZ 4
+
+// ---- fetch_stats: reference_volume_figures.cl:10-26 -----------------------------------------------------------
+// The reference issues four global atomics per voxel; here: per-thread -> warp shuffle -> block -> 4 atomics/block.
+__global__ void __launch_bounds__(TX* TY* TZ) k_fetch_stats(VolView vol, int32_t* __restrict__ stats) {
+  const int x = blockIdx.x * TX + threadIdx.x;
+  const int y = blockIdx.y * TY + threadIdx.y;
+  const int z = blockIdx.z * TZ + threadIdx.z;
+  int mnv = INT32_MAX, mxv = INT32_MIN, mng = INT32_MAX, mxg = INT32_MIN;
+  if (x < vol.nx && y < vol.ny && z < vol.nz) {
+    int v = vol.at(x, y, z);
+    int g = f2i(length3(gradient_voxel(vol, x, y, z)));  // implicit float->int of atomic_min/max(int*, float)
+    mnv = mxv = v;
+    mng = mxg = g;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mnv = min(mnv, __shfl_xor_sync(0xffffffffu, mnv, o));
+    mxv = max(mxv, __shfl_xor_sync(0xffffffffu, mxv, o));
+    mng = min(mng, __shfl_xor_sync(0xffffffffu, mng, o));
+    mxg = max(mxg, __shfl_xor_sync(0xffffffffu, mxg, o));
+  }
+  __shared__ int s[4][TY * TZ];
+  const int warp = threadIdx.y + TY * threadIdx.z;
+  if (threadIdx.x == 0) {
+    s[0][warp] = mnv; s[1][warp] = mxv; s[2][warp] = mng; s[3][warp] = mxg;
+  }
+  __syncthreads();
+  if (warp == 0 && threadIdx.x < TY * TZ) {
+    mnv = s[0][threadIdx.x]; mxv = s[1][threadIdx.x]; mng = s[2][threadIdx.x]; mxg = s[3][threadIdx.x];
+    for (int o = TY * TZ / 2; o > 0; o >>= 1) {
+      mnv = min(mnv, __shfl_xor_sync(0x0000ffffu, mnv, o));
+      mxv = max(mxv, __shfl_xor_sync(0x0000ffffu, mxv, o));
+      mng = min(mng, __shfl_xor_sync(0x0000ffffu, mng, o));
+      mxg = max(mxg, __shfl_xor_sync(0x0000ffffu, mxg, o));
+    }
+    if (threadIdx.x == 0) {
+      atomicMin(stats + 0, mnv); atomicMax(stats + 1, mxv);
+      atomicMin(stats + 2, mng); atomicMax(stats + 3, mxg);
+    }
+  }
+}
+
+int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int32_t out[4]) {
+  int32_t init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};  // reference_volume.cpp:22-28
+  memcpy(ctx->scratch_host, init, sizeof(init));
+  VR_CUDA(cudaMemcpyAsync(ctx->scratch, ctx->scratch_host, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  VolView v{vol, nx, ny, nz};
+  dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
+  k_fetch_stats<<<grid, block, 0, ctx->stream>>>(v, ctx->scratch);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  VR_CUDA(cudaMemcpyAsync(ctx->scratch_host, ctx->scratch, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->scratch_host, sizeof(init));
+  return VR_OK;
+}
+
+// ---- apply_clip: reference_volume_clip.cl:4-15 ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_clip(VolView src, int sx, int sy, int sz, int16_t* __restrict__ dst, int nx,
+                                              int ny, int nz) {
+  const size_t n = (size_t)nx * ny * nz;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % nx);
+    size_t t = i / nx;
+    int y = (int)(t % ny);
+    int z = (int)(t / ny);
+    dst[i] = (int16_t)src.at(sx + x, sy + y, sz + z);
+  }
+}
+
+int vrk_clip(vr_ctx* ctx, const int16_t* src, int snx, int sny, int snz, const uint32_t start[3], int16_t* dst, int nx,
+             int ny, int nz) {
+  VolView v{src, snx, sny, snz};
+  size_t n = (size_t)nx * ny * nz;
+  unsigned blocks = (unsigned)std::min<size_t>(div_up(n, 256), (size_t)ctx->sm_count * 16);
+  k_clip<<<blocks, 256, 0, ctx->stream>>>(v, (int)start[0], (int)start[1], (int)start[2], dst, nx, ny, nz);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}
+
+// ---- bilateral_filter: volume_filter.cl:5-11 + utility_filter.cl:38-62 ---------------------------------------
+// 125 taps per voxel, one exp per tap: bound by the SFU/FP32 pipes, not by HBM.  The block stages its
+// (TX+4)x(TY+4)x(TZ+4) neighbourhood in shared memory once so every tap is an LDS.
+// pow(d, 2.0f) is evaluated as d*d.
+__global__ void __launch_bounds__(TX* TY* TZ) k_bilateral(VolView vol, int16_t* __restrict__ dst) {
+  __shared__ float tile[TZ + 4][TY + 4][TX + 4];
+  const int bx = blockIdx.x * TX, by = blockIdx.y * TY, bz = blockIdx.z * TZ;
+  const int tid = threadIdx.x + TX * (threadIdx.y + TY * threadIdx.z);
+  for (int i = tid; i < (TZ + 4) * (TY + 4) * (TX + 4); i += TX * TY * TZ) {
+    int lx = i % (TX + 4);
+    int t = i / (TX + 4);
+    int ly = t % (TY + 4);
+    int lz = t / (TY + 4);
+    tile[lz][ly][lx] = (float)vol.at(bx + lx - 2, by + ly - 2, bz + lz - 2);
+  }
+  __syncthreads();
+  const int x = bx + threadIdx.x, y = by + threadIdx.y, z = bz + threadIdx.z;
+  if (x >= vol.nx || y >= vol.ny || z >= vol.nz) return;
+  const float sigmas = 0.6f, sigmar = 1.0f;
+  const float mid = tile[threadIdx.z + 2][threadIdx.y + 2][threadIdx.x + 2];
+  float out_colour = 0.0f, wp = 0.0f;
+#pragma unroll
+  for (int dz = -2; dz <= 2; ++dz)
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+      for (int dx = -2; dx <= 2; ++dx) {
+        float local = tile[threadIdx.z + 2 + dz][threadIdx.y + 2 + dy][threadIdx.x + 2 + dx];
+        float posd = ((float)(dx * dx + dy * dy + dz * dz)) / (2 * sigmas * sigmas);
+        float diff = mid - local;
+        float cold = (diff * diff) / (2 * sigmar * sigmar);
+        float w = expf(-posd - cold);
+        wp += w;
+        out_colour += local * w;
+      }
+  dst[(size_t)x + (size_t)vol.nx * ((size_t)y + (size_t)vol.ny * (size_t)z)] = (int16_t)f2s(out_colour / wp);
+}
+
+int vrk_bilateral(vr_ctx* ctx, const int16_t* src, int16_t* dst, int nx, int ny, int nz) {
+  VolView v{src, nx, ny, nz};
+  dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
+  k_bilateral<<<grid, block, 0, ctx->stream>>>(v, dst);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}
+
+// ---- tf_sort_values: histogram.cl:4-32 ------------------------------------------------------------------------
+// Flat index x*height + y computed exactly as written; indices outside [0, W*H) are dropped (the reference
+// writes out of bounds there); the y==H aliasing into the next column is kept.
+// Lanes of a warp that land in the same bin are merged with __match_any_sync so a hot bin costs one atomic
+// per warp instead of 32.
+__global__ void __launch_bounds__(TX* TY* TZ) k_histogram(VolView vol, uint32_t* __restrict__ bins, int width,
+                                                          int height, float min_v, float max_v, float min_g,
+                                                          float max_g) {
+  const int x = blockIdx.x * TX + threadIdx.x;
+  const int y = blockIdx.y * TY + threadIdx.y;
+  const int z = blockIdx.z * TZ + threadIdx.z;
+  long long flat = -1;
+  if (x < vol.nx && y < vol.ny && z < vol.nz) {
+    int ref_value = vol.at(x, y, z);
+    float g = length3(gradient_voxel(vol, x, y, z));
+    if (!(g > max_g) && !((float)ref_value > max_v)) {
+      float value_range = max_v - min_v;
+      float gradient_range = max_g - min_g;
+      int px = f2i(roundf((((float)ref_value - min_v) / value_range) * (float)width));
+      int py = f2i(roundf(((g - min_g) / gradient_range) * (float)height));
+      flat = (long long)px * height + py;
+      if (flat < 0 || flat >= (long long)width * height) flat = -1;
+    }
+  }
+  const unsigned active = __ballot_sync(0xffffffffu, flat >= 0);
+  if (flat >= 0) {
+    const unsigned peers = __match_any_sync(active, (int)flat);
+    const int leader = __ffs(peers) - 1;
+    if ((int)(threadIdx.x & 31) == leader) atomicAdd(bins + flat, (uint32_t)__popc(peers));
+  }
+}
+
+int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4],
+                  uint32_t* bins_dev) {
+  VR_CUDA(cudaMemsetAsync(bins_dev, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
+  VolView v{vol, nx, ny, nz};
+  dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
+  k_histogram<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3]);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}
+
+// ---- tf_flush_color_frame: histogram.cl:34-69 -------------------------------------------------------------------
+// The reference searches the sorted lookup linearly per pixel; the lookup is sorted ascending (std::set,
+// renderer.cpp:65-89) so a binary search returns the same rank.
+__global__ void __launch_bounds__(256) k_tf_color_frame(const int32_t* __restrict__ bins,
+                                                        const int32_t* __restrict__ lookup, int lookup_len, int width,
+                                                        int height, uchar4* __restrict__ out) {
+  const int px = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int py = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (px >= width || py >= height) return;
+  const int value = bins[(size_t)px * height + (height - py - 1)];
+  int lo = 0, hi = lookup_len - 1, local_value = -1;
+  while (lo <= hi) {
+    int mid = (lo + hi) >> 1;
+    int lv = __ldg(lookup + mid);
+    if (lv == value) { local_value = mid; break; }
+    if (lv < value) lo = mid + 1; else hi = mid - 1;
+  }
+  int result = 0;
+  if (local_value > -1) result = f2i(20.0f + (((float)local_value) / (float)lookup_len) * (255.0f - 20.0f));
+  unsigned char c = (unsigned char)max(0, min(255, result));
+  out[(size_t)py * width + px] = make_uchar4(c, c, c, 255);
+}
+
+int vrk_tf_color_frame(vr_ctx* ctx, const int32_t* bins_dev, const int32_t* lookup_dev, int lookup_len, int width,
+                       int height, uchar4* out_dev) {
+  dim3 grid(div_up(width, 16), div_up(height, 16));
+  k_tf_color_frame<<<grid, 256, 0, ctx->stream>>>(bins_dev, lookup_dev, lookup_len, width, height, out_dev);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}
+
+// ---- buffer_reset: buffer_reset.cl:3-13 — 8 bytes per voxel, pure store bandwidth ------------------------------
+__global__ void __launch_bounds__(256) k_cache_reset(uint4* __restrict__ p, size_t n16, uint32_t* __restrict__ tail,
+                                                     int ntail) {
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = z;
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
+}
+
+int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels) {
+  const size_t words = voxels * 2;
+  const size_t n16 = words / 4;
+  const int ntail = (int)(words - n16 * 4);
+  unsigned blocks = (unsigned)std::min<size_t>(std::max<size_t>(div_up(n16, 256), 1), (size_t)ctx->sm_count * 8);
+  k_cache_reset<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(cache), n16, cache + n16 * 4, ntail);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}

@@ -1,0 +1,170 @@
+/* vr.h — C-ABI of the B200-native volume path tracer (libvr.so).
+ *
+ * This is the layer that replaces cl-volume-renderer's `opencl_wrapper` (clw_context / clw_vector /
+ * clw_image / clw_function, opencl_wrapper/include/clw_*.hpp) for the renderer hot path.  Every entry
+ * point cites the reference call site(s) it replaces; paths are relative to the reference checkout.
+ *
+ * Conventions
+ *   - plain C: opaque handles, pointers and sizes only; no C++ types, no exceptions, no torch types.
+ *   - every function returning `int` returns VR_OK (0) or a negative vr_status; the message of the
+ *     last failure on the calling thread is vr_last_error().  (The reference prints and exit(1)s:
+ *     opencl_wrapper/include/clw_helper.hpp:293-309 — the C++ shim in host/ keeps that behaviour.)
+ *   - host pointers are caller-owned; device memory is owned by the library behind the handles.
+ *   - volumes are `short`, x fastest: voxel (x,y,z) at x + nx*(y + ny*z)   (app/volume_block.hpp:6-34,
+ *     app/nrrd_loader.cpp:126-151).  Frames and env maps are RGBA8, row-major.
+ *   - one CUDA stream per context; calls are not re-entrant on one context (same as the reference's
+ *     single in-order queue, opencl_wrapper/src/clw_context.cpp:38-48).
+ *   - there is NO CPU fallback: without a usable CUDA device vr_ctx_create fails with VR_ERR_CUDA.
+ */
+#ifndef VR_H
+#define VR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum vr_status {
+  VR_OK = 0,
+  VR_ERR_INVALID = -1, /* bad argument / bad state */
+  VR_ERR_CUDA = -2,    /* CUDA runtime failure (message carries the CUDA error string) */
+  VR_ERR_PARSE = -3,   /* transfer-function source not in one of the generated forms */
+  VR_ERR_NOMEM = -4
+} vr_status;
+
+typedef struct vr_ctx vr_ctx;
+typedef struct vr_volume vr_volume;
+typedef struct vr_envmap vr_envmap;
+typedef struct vr_sdf vr_sdf;
+typedef struct vr_renderer vr_renderer;
+
+/* One clause of the run-time generated `is_event_gen` (app/ui.cpp:160-168 + app/tf_part.cpp:55-79).
+ * Clauses are tested in order, first match wins.
+ *   flags & VR_TF_USE_GRADIENT : the `&& gradient > min_g && gradient < max_g` part is present
+ *   flags & VR_TF_THRESHOLD    : the test/bench form `return (value > min_v);` (tests/sdf/sdf_test.cpp:22,
+ *                                app/sdf_benchmark.cpp:18) — terminal, does not write a colour
+ * rgba = the `int4 tmp_color` of the clause, each (int)(c*255). */
+enum { VR_TF_USE_GRADIENT = 1, VR_TF_THRESHOLD = 2 };
+typedef struct vr_tf_rect {
+  float min_v, max_v, min_g, max_g;
+  int32_t flags;
+  int32_t rgba[4];
+} vr_tf_rect;
+#define VR_TF_MAX_RECTS 16
+
+const char* vr_last_error(void);
+
+/* ---- context: replaces clw_context (clw_context.hpp:5-28; main.cpp:13, sdf_test.cpp:14) ------------ */
+int vr_ctx_create(int device_ordinal, vr_ctx** out);
+void vr_ctx_destroy(vr_ctx* ctx);
+int vr_ctx_synchronize(vr_ctx* ctx);
+/* cudaStream_t of the context (for CUDA-event timing by the caller). */
+void* vr_ctx_stream(vr_ctx* ctx);
+/* number of kernels this context has launched so far */
+uint64_t vr_ctx_launch_count(const vr_ctx* ctx);
+
+/* ---- transfer function ---------------------------------------------------------------------------- */
+/* Strict parser for the two generated forms of `is_event_gen` (host only, needs no GPU).
+ * Writes at most `cap` clauses, *n = number of clauses found. */
+int vr_tf_parse(const char* is_event_gen_src, vr_tf_rect* out, int cap, int* n);
+/* Inverse: renders clauses as the text app/ui.cpp:160-168 would have generated (for round-trip tests). */
+int vr_tf_format(const vr_tf_rect* rects, int n, char* out, size_t cap);
+
+/* ---- reference_volume (app/reference_volume.cpp) ---------------------------------------------------- */
+/* ctor reference_volume.cpp:11-44: upload (clw_image<short> push) + fetch_stats
+ * (opencl_kernels/reference_volume_figures.cl:10-26). */
+int vr_volume_upload(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz, vr_volume** out);
+void vr_volume_destroy(vr_volume* vol);
+/* {min value, max value, min (int)|grad|, max (int)|grad|} over the ORIGINAL volume, unclamped
+ * (reference_volume.cpp:33-37).  The clip getters (reference_volume.cpp:82-88) live in the C++ shim. */
+int vr_volume_stats(const vr_volume* vol, int32_t out[4]);
+/* set_value_clip / set_gradient_clip (reference_volume.cpp:46-52) and get_volume_stats()
+ * (reference_volume.cpp:82-88,110-112): out = {max(clip,min_v), min(clip,max_v), max(clip,min_g), min(clip,max_g)} */
+int vr_volume_set_value_clip(vr_volume* vol, int lo, int hi);
+int vr_volume_set_gradient_clip(vr_volume* vol, int lo, int hi);
+int vr_volume_clipped_stats(const vr_volume* vol, float out[4]);
+/* dims of the volume the renderer sees (cropped if vr_volume_clip was called) */
+int vr_volume_dims(const vr_volume* vol, int out[3]);
+/* set_clipping, reference_volume.cpp:54-68 + reference_volume_clip.cl:4-15.  max is exclusive. */
+int vr_volume_clip(vr_volume* vol, const uint32_t min[3], const uint32_t max[3]);
+/* filter, reference_volume.cpp:70-80 + volume_filter.cl:5-11 + utility_filter.cl:38-62 (5^3 bilateral);
+ * replaces the current (cropped or original) volume. */
+int vr_volume_filter(vr_volume* vol);
+/* current volume back to the host (parity tests) */
+int vr_volume_download(const vr_volume* vol, int16_t* out);
+/* tf_sort_values, histogram.cl:4-32 as launched by renderer.cpp:57-61.
+ * range = {min_v, max_v, min_g, max_g}; bins_out = width*height uint32, index x*height + y. */
+int vr_histogram(const vr_volume* vol, int width, int height, const float range[4], uint32_t* bins_out);
+
+/* ---- env_map (app/env_map.hpp:10) ------------------------------------------------------------------- */
+int vr_envmap_bind(vr_ctx* ctx, const uint8_t* rgba8, int w, int h, vr_envmap** out);
+void vr_envmap_destroy(vr_envmap* env);
+
+/* ---- signed_distance_field (app/signed_distance_field.cpp:7-35 + signed_distance_field.cl) ---------- */
+int vr_sdf_build(vr_ctx* ctx, const vr_volume* vol, const vr_tf_rect* rects, int n_rects, vr_sdf** out);
+void vr_sdf_destroy(vr_sdf* sdf);
+/* x-fastest int8, same order as clw_image<char>::pull() (tests/sdf/sdf_test.cpp:24-31) */
+int vr_sdf_download(const vr_sdf* sdf, int8_t* out);
+/* number of wavefront levels the build ran (diagnostics) */
+int vr_sdf_levels(const vr_sdf* sdf);
+
+/* ---- renderer : frame_emitter (app/ui.hpp:29-37, app/renderer.cpp) ---------------------------------- */
+/* renderer(ctx), renderer.cpp:8-17 — the reference fixes the frame at SCREEN_WIDTH x SCREEN_HEIGHT
+ * (common_defines.hpp:3-4); here the size is a constructor argument. */
+int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_renderer** out);
+void vr_renderer_destroy(vr_renderer* r);
+/* image_set, renderer.cpp:19-23 */
+int vr_renderer_set_scene(vr_renderer* r, const vr_volume* vol, const vr_envmap* env);
+/* next_event_code_set, renderer.cpp:126-129 — either the clause table or the generated source text */
+int vr_renderer_set_tf(vr_renderer* r, const vr_tf_rect* rects, int n_rects);
+int vr_renderer_set_tf_code(vr_renderer* r, const char* is_event_gen_src);
+/* flush_changes, renderer.cpp:25-43: (re)allocate + zero the voxel cache (buffer_reset.cl:3-13),
+ * adopt the pending TF, rebuild the SDF. */
+int vr_renderer_flush(vr_renderer* r);
+/* buffer_reset only (renderer.cpp:32-35) */
+int vr_renderer_reset_cache(vr_renderer* r);
+/* render_frame, renderer.cpp:131-158 + ray_marching.cl:152-199: one sample per pixel accumulated into the
+ * voxel cache, then every pixel resolved from the cache.  dir = Position3D(look0, look1, 0, {1,0,0})
+ * (renderer.cpp:140), seed = the value std::rand() would have returned (renderer.cpp:142).
+ * host_rgba (W*H*4) may be NULL: the frame then stays on the device (no readback, no sync). */
+int vr_render_frame(vr_renderer* r, const float pos[3], const float dir[3], int32_t seed, uint8_t* host_rgba);
+/* n_frames calls of vr_render_frame with seeds[0..n), reading back only the last frame. */
+int vr_render_frames(vr_renderer* r, const float pos[3], const float dir[3], const int32_t* seeds, int n_frames,
+                     uint8_t* host_rgba);
+/* render_tf, renderer.cpp:45-124 + histogram.cl:34-69; rgba_out = width*height*4.  Histogram ranges are
+ * vr_volume_clipped_stats of the bound volume, as in renderer.cpp:57-61. */
+int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba_out);
+/* renderer-owned pinned host frame (W*H*4): the pointer render_frame() returns in the reference
+ * (renderer.cpp:157); passing it as host_rgba makes the readback a single DMA. */
+uint8_t* vr_renderer_host_frame(vr_renderer* r);
+/* packed voxel cache, 4 ushort per voxel at (nx*nz*y + nx*z + x)*4 (utility.cl:21) — parity tests */
+int vr_cache_download(const vr_renderer* r, uint16_t* out);
+/* the SDF the renderer built at the last flush (renderer.hpp:19) */
+const vr_sdf* vr_renderer_sdf(const vr_renderer* r);
+
+/* ---- multi-GPU hooks (no reference counterpart: the reference is single-device) ---------------------- */
+/* per-rank token cap for the spp split: 256/R keeps the summed cache under the reference's cap of 256
+ * (ray_marching.cl:39) and every 16-bit lane below overflow. Default 256. */
+int vr_renderer_set_token_cap(vr_renderer* r, int cap);
+/* restrict tracing to the pixel rows [y0,y1) (image-tile split); default whole frame */
+int vr_renderer_set_rows(vr_renderer* r, int y0, int y1);
+/* device pointers for collectives done by the caller (NCCL / torch.distributed): the packed cache viewed as
+ * uint32[2*N] (sum-reducible without cross-lane carries), and the RGBA8 frame. */
+void* vr_renderer_cache_device_ptr(const vr_renderer* r);
+size_t vr_renderer_cache_bytes(const vr_renderer* r);
+void* vr_renderer_frame_device_ptr(const vr_renderer* r);
+/* re-run only the resolve pass (after an external cache all-reduce) and optionally read the frame back */
+int vr_renderer_resolve(vr_renderer* r, uint8_t* host_rgba);
+
+/* ---- instrumentation ---------------------------------------------------------------------------------- */
+/* When enabled the trace kernel also accumulates the per-sample counters of SURVEY.md §8(d):
+ * {march steps, shading normals, env fetches, primary hits, admitted samples, samples}. */
+int vr_renderer_enable_counters(vr_renderer* r, int enable);
+int vr_renderer_counters(const vr_renderer* r, uint64_t out[6], int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VR_H */
