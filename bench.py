@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the volume path tracer (BASELINE.json: path Msamples/s @1080p 512^3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One STEP = one pass of the hot path over one batch: cache reset (buffer_reset) + 64 render_frame calls (64 spp,
+trace + resolve per frame) at 1920x1080 on the 512^3 synthetic CT volume, starting from a freshly reset voxel cache.
+N > 1: spp split (BASELINE config 3, weak scaling): every rank holds the whole scene, renders its own 64 frames with its
+own seeds and a token cap of 256/N, then the packed voxel caches are summed with one NCCL all-reduce and every rank
+resolves the frame.  value = N * W*H*64 / max-over-ranks device time.
+
+Keys beyond the base contract: `roofline` (dominant kernel k_trace, algorithmic bytes of SURVEY.md §8d over its
+CUDA-event time), `cpu_baseline` (the CPU oracle on a bounded sample of the same workload), `e2e` (the same metric
+through the C-ABI with host buffers: volume upload, env bind, flush incl. SDF build, 64 frames each read back).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+VOL_N = 512
+W, H = 1920, 1080
+SPP = 64
+ENV_W, ENV_H = 2048, 1024
+WORKLOAD = (f"{VOL_N}^3 short synthetic CT (synth_ct), {W}x{H}, {SPP} spp from a reset voxel cache, default TF rect(500,1200), "
+            f"synthetic env {ENV_W}x{ENV_H}, camera (-400,400,-400) look (0.9,6.183)")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception as e:  # nvidia-smi missing: report it, do not fail the bench
+            log("clock sampler unavailable:", e)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene():
+    from cl_volume_renderer_b200 import synth
+    t = time.time()
+    vol = synth.synth_ct(VOL_N)
+    env = synth.synth_env(ENV_W, ENV_H)
+    pos, d = synth.default_camera(VOL_N)
+    log(f"scene generated in {time.time() - t:.1f}s")
+    return vol, env, pos, d
+
+
+def alg_bytes_per_sample(c, trace_only):
+    """B = 15*S + 12*Hn + 4*E + 18*Hp + 16*A + 4 bytes per sample.  For the trace kernel alone the
+    8-byte resolve read per hit pixel belongs to k_resolve: 10*Hp instead of 18*Hp."""
+    S = float(c["samples"])
+    hp = 10 if trace_only else 18
+    return (15 * c["steps"] + 12 * c["normals"] + 4 * c["env"] + hp * c["primary_hits"] + 16 * c["admitted"]) / S + 4
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path.  The reference has no CPU implementation of its own and its OpenCL
+    kernels cannot run here (no OpenCL runtime in the image), so this arm times the CPU oracle — the
+    restatement of the reference kernels (oracle/oracle.cpp, OpenMP over pixels) — on the box's host cores.
+    Each step = a bounded sample of the workload: ONE frame (1 spp) of the same 1920x1080 / 512^3 scene."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as o
+    from cl_volume_renderer_b200 import synth
+    vol, env, pos, d = make_scene()
+    t = time.time()
+    sdf, iters = o.sdf_build(vol, synth.default_tf())
+    sdf_s = time.time() - t
+    log(f"oracle SDF build {VOL_N}^3: {sdf_s:.1f}s ({iters} iterations, {o.num_threads()} threads)")
+    r = o.Renderer(vol, env, synth.default_tf(), W, H, sdf=sdf)
+    seeds = synth.glibc_rand(args.steps + args.warmup)
+    for k in range(args.warmup):
+        r.render_frame(pos, d, seeds[k])
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        r.render_frame(pos, d, seeds[args.warmup + k])
+    dt = time.perf_counter() - t0
+    value = W * H * args.steps / dt / 1e6
+    sample = f"{args.steps} x 1 spp frame of the workload (SDF built once beforehand by the oracle in {sdf_s:.1f}s, untimed)"
+    print(json.dumps({
+        "impl": "reference", "metric": "path_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": o.num_threads(), "kind": "port", "sample": sample,
+                         "sdf_build_ms": 1e3 * sdf_s},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from cl_volume_renderer_b200 import api, synth
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = api.Context(local_rank)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+    vol_np, env_np, pos, d = make_scene()
+    # pinned host copies: the e2e leg uploads from these
+    vol_pin = torch.empty(vol_np.shape, dtype=torch.int16, pin_memory=True)
+    vol_pin.numpy()[...] = vol_np
+    env_pin = torch.empty(env_np.shape, dtype=torch.uint8, pin_memory=True)
+    env_pin.numpy()[...] = env_np
+    tf_code = api.tf_format(synth.default_tf())
+    all_seeds = synth.glibc_rand(SPP * max(world, 1))
+    seeds = all_seeds[SPP * rank: SPP * (rank + 1)]
+
+    vol = api.Volume(ctx, vol_pin.numpy())
+    env = api.EnvMap(ctx, env_pin.numpy())
+    r = api.Renderer(ctx, W, H)
+    r.image_set(vol, env)
+    r.next_event_code_set(tf_code)
+    r.set_token_cap(max(256 // world, 1))
+    r.flush_changes()
+    ctx.synchronize()
+    cache_t = None
+    if world > 1:
+        cache_t = torch.as_tensor(_DevArray(r.cache_device_ptr, r.cache_bytes // 4, "<i4"), device=f"cuda:{local_rank}")
+
+    def step():
+        r.reset_cache()
+        r.render_frames(pos, d, seeds, readback=False)
+        if world > 1:
+            with torch.cuda.stream(ext):
+                dist.all_reduce(cache_t)  # int32 view of the packed lanes: sums cannot carry across lanes (cap 256/N)
+            r.resolve(readback=False)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- SDF build time (second half of BASELINE's metric) ----
+    sdf_ms = []
+    for _ in range(3):
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        s = api.Sdf(ctx, vol, synth.default_tf())
+        sdf_ms.append(1e3 * (time.perf_counter() - t0))
+        levels = s.levels
+        s.close()
+
+    # ---- algorithmic counters of one step (same scene, same seeds) ----
+    r.enable_counters(True)
+    r.reset_cache()
+    r.render_frames(pos, d, seeds, readback=False)
+    counters = r.counters(reset=True)
+    r.enable_counters(False)
+
+    # ---- warm-up, then the timed region ----
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = ctx.launches
+    r.enable_timing(True)
+    r.kernel_times(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        step()
+    e1.record(ext)
+    e1.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    trace_ms, resolve_ms, nframes = r.kernel_times(reset=True)
+    r.enable_timing(False)
+    launches = ctx.launches - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    samples_per_step = W * H * SPP * world
+    value = samples_per_step * args.steps / ms_max / 1e3  # Msamples/s
+
+    # ---- e2e: the same metric through the C-ABI with host buffers ----
+    e2e_steps = 2
+    host_frame = r.host_frame()
+
+    def e2e_step():
+        v2 = api.Volume(ctx, vol_pin.numpy())          # H2D 256 MiB + fetch_stats
+        en2 = api.EnvMap(ctx, env_pin.numpy())         # H2D 8 MiB
+        r2 = api.Renderer(ctx, W, H)
+        r2.image_set(v2, en2)
+        r2.next_event_code_set(tf_code)
+        r2.set_token_cap(max(256 // world, 1))
+        r2.flush_changes()                             # cache alloc + reset + SDF build
+        hf = r2.host_frame()
+        for k in range(SPP):
+            if world > 1 and k == SPP - 1:
+                r2.render_frame(pos, d, seeds[k], readback=False)
+                c2 = torch.as_tensor(_DevArray(r2.cache_device_ptr, r2.cache_bytes // 4, "<i4"),
+                                     device=f"cuda:{local_rank}")
+                with torch.cuda.stream(ext):
+                    dist.all_reduce(c2)
+                api._check(api.lib().vr_renderer_resolve(r2.h, hf.ctypes.data_as(api.C.c_void_p)))
+            else:
+                r2.render_frame(pos, d, seeds[k], out=hf)  # D2H W*H*4 per frame (renderer.cpp:150)
+        checksum = int(hf[::97, ::89].sum())
+        r2.close(); en2.close(); v2.close()
+        return checksum
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = samples_per_step * e2e_steps / float(t.item()) / 1e6
+    del host_frame
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as o
+        sdf_np = r.sdf_download()  # bit-identical to the oracle's (tests/test_parity_gpu.py); saves minutes of CPU SDF build
+        ref = o.Renderer(vol_np, env_np, synth.default_tf(), W, H, sdf=sdf_np)
+        ref.render_frame(pos, d, seeds[0], want_frame=False)
+        t0 = time.perf_counter()
+        nfr = 0
+        while nfr < 8 and (time.perf_counter() - t0) < 10.0:
+            ref.render_frame(pos, d, seeds[1 + nfr])
+            nfr += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": W * H * nfr / dt / 1e6, "unit": "Msamples/s", "cores": o.num_threads(), "kind": "port",
+               "sample": f"{nfr} x 1 spp frame of the same 1920x1080/512^3 scene (oracle/oracle.cpp, OpenMP; SDF taken from the "
+                         f"GPU build, which the parity tests pin bit-exact)"}
+
+    if rank == 0:
+        hbm, peak_src = peaks()
+        b_trace = alg_bytes_per_sample(counters, trace_only=True)
+        trace_launch_ms = trace_ms / max(nframes, 1)
+        achieved = b_trace * W * H / (trace_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_k_trace.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        S = float(counters["samples"])
+        out = {
+            "metric": "path_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": f"spp-split x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (cache 1 GiB + volume 256 MiB + SDF 128 MiB), no flush"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s",
+                    "h2d_bytes_per_step": int(vol_np.nbytes + env_np.nbytes), "d2h_bytes_per_step": int(W * H * 4 * SPP),
+                    "steps": e2e_steps,
+                    "what": "per step: vr_volume_upload + vr_envmap_bind from pinned host memory, vr_renderer_flush (cache "
+                            "alloc/reset + SDF build), 64 x vr_render_frame each read back to the host"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                         "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
+                         "alg_bytes_per_sample": b_trace, "samples_per_launch": W * H,
+                         "launch_ms": trace_launch_ms, "resolve_launch_ms": resolve_ms / max(nframes, 1),
+                         "trace_share_of_step": trace_ms / ms if ms > 0 else None,
+                         "per_sample": {"steps": counters["steps"] / S, "normals": counters["normals"] / S,
+                                        "env": counters["env"] / S, "primary_hits": counters["primary_hits"] / S,
+                                        "admitted": counters["admitted"] / S}},
+            "cpu_baseline": cpu,
+            "sdf_build_ms": {"value": float(np.median(sdf_ms)), "levels": levels, "volume": f"{VOL_N}^3",
+                             "note": "vr_sdf_build wall time incl. allocation, excl. upload (app/sdf_benchmark.cpp:15-20)"},
+        }
+        print(json.dumps(out), flush=True)
+    r.close(); env.close(); vol.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        assert args.warmup >= 3 or os.environ.get("VR_BENCH_ALLOW_SHORT"), "timing rules: at least 3 warm-up steps"
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

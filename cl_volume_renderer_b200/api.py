@@ -78,6 +78,8 @@ SYMBOLS = {
     "vr_renderer_resolve": (C.c_int, [_P, _P]),
     "vr_renderer_enable_counters": (C.c_int, [_P, C.c_int]),
     "vr_renderer_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int]),
+    "vr_renderer_enable_timing": (C.c_int, [_P, C.c_int]),
+    "vr_renderer_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }
 
 _lib = None
@@ -357,3 +359,13 @@ class Renderer:
         c = (C.c_uint64 * 6)()
         _check(lib().vr_renderer_counters(self.h, c, 1 if reset else 0))
         return dict(zip(["steps", "normals", "env", "primary_hits", "admitted", "samples"], [int(v) for v in c]))
+
+    def enable_timing(self, on=True):
+        _check(lib().vr_renderer_enable_timing(self.h, 1 if on else 0))
+
+    def kernel_times(self, reset=True):
+        """(trace_ms_total, resolve_ms_total, frames) measured with CUDA events on the launching stream"""
+        ms = (C.c_double * 2)()
+        n = C.c_int(0)
+        _check(lib().vr_renderer_kernel_times(self.h, ms, C.byref(n), 1 if reset else 0))
+        return ms[0], ms[1], n.value

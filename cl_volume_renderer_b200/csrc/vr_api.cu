@@ -255,6 +255,7 @@ extern "C" void vr_renderer_destroy(vr_renderer* r) {
   cudaFree(r->hit);
   cudaFree(r->frame);
   cudaFree(r->counters);
+  for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
   cudaFreeHost(r->frame_host);
   delete r;
 }
@@ -386,6 +387,29 @@ extern "C" int vr_renderer_counters(const vr_renderer* r, uint64_t out[6], int r
   VR_CUDA(cudaMemcpyAsync(out, r->counters, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, r->ctx->stream));
   if (reset) VR_CUDA(cudaMemsetAsync(r->counters, 0, 6 * sizeof(uint64_t), r->ctx->stream));
   VR_CUDA(cudaStreamSynchronize(r->ctx->stream));
+  return VR_OK;
+}
+
+extern "C" int vr_renderer_enable_timing(vr_renderer* r, int enable) {
+  VR_REQUIRE(r, "vr_renderer_enable_timing: null argument");
+  r->timing = enable != 0;
+  return VR_OK;
+}
+
+extern "C" int vr_renderer_kernel_times(vr_renderer* r, double out_ms[2], int* n_frames, int reset) {
+  VR_REQUIRE(r && out_ms && n_frames, "vr_renderer_kernel_times: null argument");
+  VR_CUDA(cudaSetDevice(r->ctx->device));
+  VR_CUDA(cudaStreamSynchronize(r->ctx->stream));
+  out_ms[0] = out_ms[1] = 0.0;
+  for (size_t i = 0; i + 3 <= r->ev_used; i += 3) {
+    float a = 0.f, b = 0.f;
+    VR_CUDA(cudaEventElapsedTime(&a, r->ev[i], r->ev[i + 1]));
+    VR_CUDA(cudaEventElapsedTime(&b, r->ev[i + 1], r->ev[i + 2]));
+    out_ms[0] += a;
+    out_ms[1] += b;
+  }
+  *n_frames = (int)(r->ev_used / 3);
+  if (reset) r->ev_used = 0;
   return VR_OK;
 }
 

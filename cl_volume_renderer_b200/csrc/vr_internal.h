@@ -93,6 +93,9 @@ struct vr_renderer {
   int token_cap = 256;
   bool count = false;
   unsigned long long* counters = nullptr;  // 6 x u64 on device
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;  // 3 events per timed frame: before trace, between, after resolve
+  size_t ev_used = 0;
 };
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------------

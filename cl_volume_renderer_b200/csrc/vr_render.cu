@@ -291,6 +291,17 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], int32_t s
   vr_ctx* ctx = r->ctx;
   const int rows = r->row1 - r->row0;
   if (rows <= 0) return VR_OK;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  if (r->timing && trace && resolve) {
+    while (r->ev.size() < r->ev_used + 3) {
+      cudaEvent_t e;
+      VR_CUDA(cudaEventCreate(&e));
+      r->ev.push_back(e);
+    }
+    e0 = r->ev[r->ev_used]; e1 = r->ev[r->ev_used + 1]; e2 = r->ev[r->ev_used + 2];
+    r->ev_used += 3;
+    VR_CUDA(cudaEventRecord(e0, ctx->stream));
+  }
   if (trace) {
     RenderParams p;
     p.vol = VolView{r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz};
@@ -313,12 +324,14 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], int32_t s
     else k_trace<false><<<grid, 128, 0, ctx->stream>>>(p);
     ctx->launches++;
   }
+  if (e1) VR_CUDA(cudaEventRecord(e1, ctx->stream));
   if (resolve) {
     const size_t n = (size_t)r->W * rows;
     k_resolve<<<div_up(n, 256), 256, 0, ctx->stream>>>(r->hit, reinterpret_cast<const uint2*>(r->cache), r->frame, r->W,
                                                        r->row0, r->row1);
     ctx->launches++;
   }
+  if (e2) VR_CUDA(cudaEventRecord(e2, ctx->stream));
   VR_CUDA(cudaGetLastError());
   return VR_OK;
 }

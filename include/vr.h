@@ -163,6 +163,11 @@ int vr_renderer_resolve(vr_renderer* r, uint8_t* host_rgba);
  * {march steps, shading normals, env fetches, primary hits, admitted samples, samples}. */
 int vr_renderer_enable_counters(vr_renderer* r, int enable);
 int vr_renderer_counters(const vr_renderer* r, uint64_t out[6], int reset);
+/* When enabled, every trace / resolve launch is bracketed by CUDA events on the context's stream;
+ * vr_renderer_kernel_times synchronises and returns the summed device time of the trace kernel (out_ms[0]) and of
+ * the resolve kernel (out_ms[1]) and the number of frames measured since the last reset. */
+int vr_renderer_enable_timing(vr_renderer* r, int enable);
+int vr_renderer_kernel_times(vr_renderer* r, double out_ms[2], int* n_frames, int reset);
 
 #ifdef __cplusplus
 }
