@@ -18,6 +18,17 @@ void vr_set_error(const char* fmt, ...) {
 
 extern "C" const char* vr_last_error(void) { return g_err; }
 
+// Device memory comes from the device's default stream-ordered pool, whose release threshold is raised to "never" in
+// vr_ctx_create: scene objects that are destroyed and re-created (volume upload, TF flush, SDF rebuild) then recycle
+// their blocks without a driver round trip.  Frees are ordered on the context's stream.
+template <typename T>
+static cudaError_t pool_alloc(vr_ctx* ctx, T** p, size_t bytes) {
+  return cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 1, ctx->stream);
+}
+static void pool_free(vr_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
 // ---- context -------------------------------------------------------------------------------------------------
 extern "C" int vr_ctx_create(int device_ordinal, vr_ctx** out) {
   VR_REQUIRE(out, "vr_ctx_create: null out");
@@ -43,6 +54,10 @@ extern "C" int vr_ctx_create(int device_ordinal, vr_ctx** out) {
   c->device = device_ordinal;
   c->sm_count = prop.multiProcessorCount;
   VR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  VR_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
+  uint64_t keep = UINT64_MAX;
+  VR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   VR_CUDA(cudaMalloc(&c->scratch, 4096));
   VR_CUDA(cudaMallocHost(&c->scratch_host, 4096));
   *out = c;
@@ -79,10 +94,10 @@ extern "C" int vr_volume_upload(vr_ctx* ctx, const int16_t* voxels, int nx, int 
   v->ctx = ctx;
   v->onx = v->nx = nx; v->ony = v->ny = ny; v->onz = v->nz = nz;
   const size_t bytes = v->count() * sizeof(int16_t);
-  VR_CUDA(cudaMalloc(&v->original, bytes));
+  VR_CUDA(pool_alloc(ctx, &v->original, bytes));
   VR_CUDA(cudaMemcpyAsync(v->original, voxels, bytes, cudaMemcpyHostToDevice, ctx->stream));
   int s = vrk_fetch_stats(ctx, v->original, nx, ny, nz, v->stats);  // reference_volume.cpp:22-41
-  if (s != VR_OK) { cudaFree(v->original); delete v; return s; }
+  if (s != VR_OK) { pool_free(ctx, v->original); delete v; return s; }
   *out = v;
   return VR_OK;
 }
@@ -91,8 +106,9 @@ extern "C" void vr_volume_destroy(vr_volume* v) {
   if (!v) return;
   cudaSetDevice(v->ctx->device);
   cudaStreamSynchronize(v->ctx->stream);
-  cudaFree(v->original);
-  cudaFree(v->cropped);
+  pool_free(v->ctx, v->original);
+  pool_free(v->ctx, v->cropped);
+  cudaStreamSynchronize(v->ctx->stream);
   delete v;
 }
 
@@ -115,11 +131,11 @@ extern "C" int vr_volume_clip(vr_volume* v, const uint32_t mn[3], const uint32_t
   VR_CUDA(cudaSetDevice(v->ctx->device));
   const int nx = (int)(mx[0] - mn[0]), ny = (int)(mx[1] - mn[1]), nz = (int)(mx[2] - mn[2]);
   int16_t* dst = nullptr;
-  VR_CUDA(cudaMalloc(&dst, (size_t)nx * ny * nz * sizeof(int16_t)));
+  VR_CUDA(pool_alloc(v->ctx, &dst, (size_t)nx * ny * nz * sizeof(int16_t)));
   int s = vrk_clip(v->ctx, v->original, v->onx, v->ony, v->onz, mn, dst, nx, ny, nz);
-  if (s != VR_OK) { cudaFree(dst); return s; }
+  if (s != VR_OK) { pool_free(v->ctx, dst); return s; }
   VR_CUDA(cudaStreamSynchronize(v->ctx->stream));
-  cudaFree(v->cropped);
+  pool_free(v->ctx, v->cropped);
   v->cropped = dst;
   v->nx = nx; v->ny = ny; v->nz = nz;
   return VR_OK;
@@ -129,13 +145,13 @@ extern "C" int vr_volume_filter(vr_volume* v) {
   VR_REQUIRE(v, "vr_volume_filter: null argument");
   VR_CUDA(cudaSetDevice(v->ctx->device));
   int16_t* dst = nullptr;
-  VR_CUDA(cudaMalloc(&dst, v->count() * sizeof(int16_t)));
+  VR_CUDA(pool_alloc(v->ctx, &dst, v->count() * sizeof(int16_t)));
   int s = vrk_bilateral(v->ctx, v->current(), dst, v->nx, v->ny, v->nz);
-  if (s != VR_OK) { cudaFree(dst); return s; }
+  if (s != VR_OK) { pool_free(v->ctx, dst); return s; }
   VR_CUDA(cudaStreamSynchronize(v->ctx->stream));
   // `ref = std::move(buffer)` (reference_volume.cpp:77): the filtered data replaces the current volume
-  if (v->cropped) { cudaFree(v->cropped); v->cropped = dst; }
-  else { cudaFree(v->original); v->original = dst; }
+  if (v->cropped) { pool_free(v->ctx, v->cropped); v->cropped = dst; }
+  else { pool_free(v->ctx, v->original); v->original = dst; }
   return VR_OK;
 }
 
@@ -153,14 +169,14 @@ extern "C" int vr_histogram(const vr_volume* v, int width, int height, const flo
   VR_CUDA(cudaSetDevice(v->ctx->device));
   uint32_t* bins = nullptr;
   const size_t bytes = sizeof(uint32_t) * (size_t)width * height;
-  VR_CUDA(cudaMalloc(&bins, bytes));
+  VR_CUDA(pool_alloc(v->ctx, &bins, bytes));
   int s = vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins);
   if (s == VR_OK) {
     cudaError_t e = cudaMemcpyAsync(bins_out, bins, bytes, cudaMemcpyDeviceToHost, v->ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(v->ctx->stream);
     if (e != cudaSuccess) { vr_set_error("vr_histogram: %s", cudaGetErrorString(e)); s = VR_ERR_CUDA; }
   }
-  cudaFree(bins);
+  pool_free(v->ctx, bins);
   return s;
 }
 
@@ -172,7 +188,7 @@ extern "C" int vr_envmap_bind(vr_ctx* ctx, const uint8_t* rgba8, int w, int h, v
   vr_envmap* e = new (std::nothrow) vr_envmap();
   if (!e) return VR_ERR_NOMEM;
   e->ctx = ctx; e->w = w; e->h = h;
-  VR_CUDA(cudaMalloc(&e->texels, (size_t)w * h * 4));
+  VR_CUDA(pool_alloc(ctx, &e->texels, (size_t)w * h * 4));
   VR_CUDA(cudaMemcpyAsync(e->texels, rgba8, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
   VR_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = e;
@@ -183,7 +199,8 @@ extern "C" void vr_envmap_destroy(vr_envmap* e) {
   if (!e) return;
   cudaSetDevice(e->ctx->device);
   cudaStreamSynchronize(e->ctx->stream);
-  cudaFree(e->texels);
+  pool_free(e->ctx, e->texels);
+  cudaStreamSynchronize(e->ctx->stream);
   delete e;
 }
 
@@ -193,10 +210,10 @@ static int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, 
   vr_sdf* s = new (std::nothrow) vr_sdf();
   if (!s) return VR_ERR_NOMEM;
   s->ctx = ctx; s->nx = vol->nx; s->ny = vol->ny; s->nz = vol->nz;
-  cudaError_t e = cudaMalloc(&s->field, vol->count());
+  cudaError_t e = pool_alloc(ctx, &s->field, vrk_sdf_field_bytes(vol->nx, vol->ny, vol->nz));
   if (e != cudaSuccess) { delete s; vr_set_error("vr_sdf_build: %s", cudaGetErrorString(e)); return VR_ERR_CUDA; }
   int st = vrk_sdf_build(ctx, vol->current(), vol->nx, vol->ny, vol->nz, tf, s->field, &s->levels, &s->max_it);
-  if (st != VR_OK) { cudaFree(s->field); delete s; return st; }
+  if (st != VR_OK) { pool_free(ctx, s->field); delete s; return st; }
   *out = s;
   return VR_OK;
 }
@@ -211,16 +228,25 @@ extern "C" void vr_sdf_destroy(vr_sdf* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
-  cudaFree(s->field);
+  pool_free(s->ctx, s->field);
+  cudaStreamSynchronize(s->ctx->stream);
   delete s;
 }
 
 extern "C" int vr_sdf_download(const vr_sdf* s, int8_t* out) {
   VR_REQUIRE(s && out, "vr_sdf_download: null argument");
   VR_CUDA(cudaSetDevice(s->ctx->device));
-  VR_CUDA(cudaMemcpyAsync(out, s->field, (size_t)s->nx * s->ny * s->nz, cudaMemcpyDeviceToHost, s->ctx->stream));
-  VR_CUDA(cudaStreamSynchronize(s->ctx->stream));
-  return VR_OK;
+  const size_t n = (size_t)s->nx * s->ny * s->nz;
+  int8_t* linear = nullptr;
+  VR_CUDA(pool_alloc(s->ctx, &linear, n));
+  int st = vrk_sdf_unbrick(s->ctx, s->field, s->nx, s->ny, s->nz, linear);
+  if (st == VR_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, linear, n, cudaMemcpyDeviceToHost, s->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->ctx->stream);
+    if (e != cudaSuccess) { vr_set_error("vr_sdf_download: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  }
+  pool_free(s->ctx, linear);
+  return st;
 }
 
 extern "C" int vr_sdf_levels(const vr_sdf* s) { return s ? s->levels : 0; }
@@ -234,9 +260,9 @@ extern "C" int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_rendere
   if (!r) return VR_ERR_NOMEM;
   r->ctx = ctx; r->W = width; r->H = height; r->row0 = 0; r->row1 = height;
   const size_t px = (size_t)width * height;
-  VR_CUDA(cudaMalloc(&r->frame, px * 4));
-  VR_CUDA(cudaMalloc(&r->hit, px * 4));
-  VR_CUDA(cudaMalloc(&r->counters, 6 * sizeof(unsigned long long)));
+  VR_CUDA(pool_alloc(ctx, &r->frame, px * 4));
+  VR_CUDA(pool_alloc(ctx, &r->hit, px * 4));
+  VR_CUDA(pool_alloc(ctx, &r->counters, 6 * sizeof(unsigned long long)));
   VR_CUDA(cudaMallocHost(&r->frame_host, px * 4));
   VR_CUDA(cudaMemsetAsync(r->frame, 0, px * 4, ctx->stream));
   VR_CUDA(cudaMemsetAsync(r->hit, 0xFF, px * 4, ctx->stream));
@@ -251,10 +277,11 @@ extern "C" void vr_renderer_destroy(vr_renderer* r) {
   cudaSetDevice(r->ctx->device);
   cudaStreamSynchronize(r->ctx->stream);
   vr_sdf_destroy(r->sdf);
-  cudaFree(r->cache);
-  cudaFree(r->hit);
-  cudaFree(r->frame);
-  cudaFree(r->counters);
+  pool_free(r->ctx, r->cache);
+  pool_free(r->ctx, r->hit);
+  pool_free(r->ctx, r->frame);
+  pool_free(r->ctx, r->counters);
+  cudaStreamSynchronize(r->ctx->stream);
   for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
   cudaFreeHost(r->frame_host);
   delete r;
@@ -298,10 +325,10 @@ extern "C" int vr_renderer_flush(vr_renderer* r) {
   const size_t voxels = r->vol->count();
   if (voxels != r->cache_voxels) {
     VR_CUDA(cudaStreamSynchronize(r->ctx->stream));
-    cudaFree(r->cache);
+    pool_free(r->ctx, r->cache);
     r->cache = nullptr;
     r->cache_voxels = 0;
-    VR_CUDA(cudaMalloc(&r->cache, voxels * 8));
+    VR_CUDA(pool_alloc(r->ctx, &r->cache, voxels * 8));
     r->cache_voxels = voxels;
   }
   VR_TRY(vrk_cache_reset(r->ctx, r->cache, r->cache_voxels));  // renderer.cpp:32-35
@@ -447,8 +474,8 @@ extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba
   uchar4* img = nullptr;
   std::vector<uint32_t> h(nb);
   int status = VR_OK;
-  cudaError_t e = cudaMalloc(&bins, nb * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&img, nb * 4);
+  cudaError_t e = pool_alloc(ctx, &bins, nb * 4);
+  if (e == cudaSuccess) e = pool_alloc(ctx, &img, nb * 4);
   if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
   if (status == VR_OK)
     status = vrk_histogram(ctx, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height, range, bins);
@@ -476,7 +503,7 @@ extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba
       // renderer.cpp:84-86: the colour kernel is skipped, the frame keeps its zero initialisation
       memset(rgba_out, 0, nb * 4);
     } else {
-      e = cudaMalloc(&lookup, lut.size() * 4);
+      e = pool_alloc(ctx, &lookup, lut.size() * 4);
       if (e == cudaSuccess) e = cudaMemcpyAsync(bins, h.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream);
       if (e == cudaSuccess)
         e = cudaMemcpyAsync(lookup, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
@@ -491,8 +518,8 @@ extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba
       }
     }
   }
-  cudaFree(bins);
-  cudaFree(lookup);
-  cudaFree(img);
+  pool_free(ctx, bins);
+  pool_free(ctx, lookup);
+  pool_free(ctx, img);
   return status;
 }

@@ -69,7 +69,7 @@ struct vr_envmap {
 
 struct vr_sdf {
   vr_ctx* ctx = nullptr;
-  int8_t* field = nullptr;  // device, x fastest (API order)
+  int8_t* field = nullptr;  // device, 8x8x8 bricks of 512 contiguous bytes, dims padded up to multiples of 8
   int nx = 0, ny = 0, nz = 0;
   int levels = 0;
   int max_it = 0;
@@ -109,6 +109,8 @@ int vrk_tf_color_frame(vr_ctx* ctx, const int32_t* bins_dev, const int32_t* look
                        int height, uchar4* out_dev);
 int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field,
                   int* levels_out, int* max_it_out);
+size_t vrk_sdf_field_bytes(int nx, int ny, int nz);
+int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear);
 int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels);
 int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], int32_t seed, bool trace, bool resolve);
 

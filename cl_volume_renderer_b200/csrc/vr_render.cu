@@ -20,7 +20,7 @@
 
 struct RenderParams {
   VolView vol;
-  const int8_t* __restrict__ sdf;
+  SdfView sdf;
   const uchar4* __restrict__ env;
   int env_w, env_h;
   uint32_t* __restrict__ cache;
@@ -114,13 +114,7 @@ __device__ __forceinline__ int march_to_next_event(const RenderParams& p, Ray& r
                                                    unsigned& steps) {
   const int nx = p.vol.nx, ny = p.vol.ny, nz = p.vol.nz;
   // SDF value at trunc(origin); border (any coordinate outside the field) reads 0
-  int d;
-  {
-    const int x = f2i(r.o.x), y = f2i(r.o.y), z = f2i(r.o.z);
-    d = 0;
-    if ((unsigned)x < (unsigned)nx && (unsigned)y < (unsigned)ny && (unsigned)z < (unsigned)nz)
-      d = __ldg(p.sdf + ((size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * (size_t)z)));
-  }
+  int d = p.sdf.at(f2i(r.o.x), f2i(r.o.y), f2i(r.o.z));
   for (int i = 0; i < 70; ++i) {
     const float step_size = max_cl((float)d, 0.5f);
     r.o = r.o + step_size * r.d;
@@ -134,7 +128,7 @@ __device__ __forceinline__ int march_to_next_event(const RenderParams& p, Ray& r
     const bool inside = (x < nx) & (y < ny) & (z < nz);
     int clause;
     if (inside) {
-      d = __ldg(p.sdf + ((size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * (size_t)z)));
+      d = __ldg(p.sdf.f + p.sdf.addr(x, y, z));
       if (d > 0) continue;  // sign(sdf) > 0  <=>  no event at this voxel
       const int value = p.vol.at(x, y, z);
       grad = gradient_voxel(p.vol, x, y, z);
@@ -305,7 +299,7 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], int32_t s
   if (trace) {
     RenderParams p;
     p.vol = VolView{r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz};
-    p.sdf = r->sdf->field;
+    p.sdf = SdfView{r->sdf->field, r->sdf->nx, r->sdf->ny, r->sdf->nz, (r->sdf->nx + 7) / 8, (r->sdf->ny + 7) / 8};
     p.env = r->env->texels;
     p.env_w = r->env->w;
     p.env_h = r->env->h;
