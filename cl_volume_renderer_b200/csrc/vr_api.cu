@@ -353,7 +353,7 @@ extern "C" int vr_render_frame(vr_renderer* r, const float pos[3], const float d
   VR_REQUIRE(r && pos && dir, "vr_render_frame: null argument");
   VR_REQUIRE(r->sdf && r->cache, "vr_render_frame: call vr_renderer_flush first");
   VR_CUDA(cudaSetDevice(r->ctx->device));
-  VR_TRY(vrk_render(r, pos, dir, seed, true, true));
+  VR_TRY(vrk_render(r, pos, dir, &seed, 1, true, true));
   return read_frame(r, host_rgba);
 }
 
@@ -362,7 +362,13 @@ extern "C" int vr_render_frames(vr_renderer* r, const float pos[3], const float 
   VR_REQUIRE(r && pos && dir && seeds && n_frames > 0, "vr_render_frames: bad argument");
   VR_REQUIRE(r->sdf && r->cache, "vr_render_frames: call vr_renderer_flush first");
   VR_CUDA(cudaSetDevice(r->ctx->device));
-  for (int k = 0; k < n_frames; ++k) VR_TRY(vrk_render(r, pos, dir, seeds[k], true, true));
+  // Only the last frame is observable, so the traces of a batch share one launch (their samples commute: integer
+  // atomics) and the cache is resolved once at the end.  Which samples a voxel admits once it reaches the token cap
+  // mid-batch is scheduling dependent — the same class of nondeterminism the reference has inside a single frame.
+  for (int k = 0; k < n_frames; k += VR_MAX_BATCH) {
+    const int nb = std::min(VR_MAX_BATCH, n_frames - k);
+    VR_TRY(vrk_render(r, pos, dir, seeds + k, nb, true, k + nb == n_frames));
+  }
   return read_frame(r, host_rgba);
 }
 
@@ -370,7 +376,8 @@ extern "C" int vr_renderer_resolve(vr_renderer* r, uint8_t* host_rgba) {
   VR_REQUIRE(r && r->sdf && r->cache, "vr_renderer_resolve: call vr_renderer_flush first");
   VR_CUDA(cudaSetDevice(r->ctx->device));
   const float z[3] = {0, 0, 0};
-  VR_TRY(vrk_render(r, z, z, 0, false, true));
+  const int32_t zero = 0;
+  VR_TRY(vrk_render(r, z, z, &zero, 1, false, true));
   return read_frame(r, host_rgba);
 }
 
@@ -435,8 +442,9 @@ extern "C" int vr_renderer_kernel_times(vr_renderer* r, double out_ms[2], int* n
     out_ms[0] += a;
     out_ms[1] += b;
   }
-  *n_frames = (int)(r->ev_used / 3);
-  if (reset) r->ev_used = 0;
+  *n_frames = 0;
+  for (int f : r->ev_frames) *n_frames += f;
+  if (reset) { r->ev_used = 0; r->ev_frames.clear(); }
   return VR_OK;
 }
 

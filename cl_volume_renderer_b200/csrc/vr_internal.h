@@ -94,8 +94,9 @@ struct vr_renderer {
   bool count = false;
   unsigned long long* counters = nullptr;  // 6 x u64 on device
   bool timing = false;
-  std::vector<cudaEvent_t> ev;  // 3 events per timed frame: before trace, between, after resolve
+  std::vector<cudaEvent_t> ev;  // 3 events per timed launch: before trace, between, after resolve
   size_t ev_used = 0;
+  std::vector<int> ev_frames;   // frames traced by each timed launch
 };
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------------
@@ -112,6 +113,9 @@ int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const
 size_t vrk_sdf_field_bytes(int nx, int ny, int nz);
 int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear);
 int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels);
-int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], int32_t seed, bool trace, bool resolve);
+#define VR_MAX_BATCH 64
+// trace `nframes` frames (seeds[0..nframes)) in ONE launch (gridDim.z = frame), then optionally resolve once
+int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int32_t* seeds, int nframes, bool trace,
+               bool resolve);
 
 TfTable vr_make_tf_table(const vr_tf_rect* rects, int n);

@@ -28,8 +28,10 @@ struct RenderParams {
   uchar4* __restrict__ frame;
   int W, H, row0, row1;
   f3 cam_pos, cam_dir;
-  int seed;
+  f3 cam_side, cam_up;  // camera basis of generate_ray, evaluated once on the host in the same fp32 op order
   int token_cap;
+  int nframes;          // frames in this launch: blockIdx.z selects the seed
+  int seeds[VR_MAX_BATCH];
   unsigned long long* counters;
   TfTable tf;
 };
@@ -40,12 +42,10 @@ struct Ray {
 
 enum { EV_NONE = 0, EV_HIT = 1, EV_EXIT = 2 };
 
-// generate_ray, utility_ray.cl:69-89
-__device__ __forceinline__ Ray generate_ray(f3 cam_pos, f3 cam_dir, int x, int y, int x_total, int y_total) {
-  const f3 up = {0.0f, 1.0f, 0.0f};
-  f3 cam_side = normalize3(cross3(up, cam_dir));
-  f3 cam_up = normalize3(cross3(cam_dir, cam_side));
-  if (cam_up.y < 0) cam_up = -cam_up;
+// generate_ray, utility_ray.cl:69-89.  cam_side / cam_up (utility_ray.cl:70-76) depend only on the camera, so the
+// host evaluates them once per frame (camera_basis below) instead of once per pixel.
+__device__ __forceinline__ Ray generate_ray(f3 cam_pos, f3 cam_dir, f3 cam_side, f3 cam_up, int x, int y, int x_total,
+                                            int y_total) {
   const float x_f = (float)(x - x_total / 2);
   const float y_f = (float)(y - y_total / 2);
   const float aspect_ratio = (float)x_total / (float)y_total;
@@ -119,24 +119,21 @@ __device__ __forceinline__ int march_to_next_event(const RenderParams& p, Ray& r
     const float step_size = max_cl((float)d, 0.5f);
     r.o = r.o + step_size * r.d;
     if (COUNT) steps++;
-    // exited_volume, utility_ray.cl:112-117 (strict)
-    const bool exited = ((float)nx < r.o.x) | ((float)ny < r.o.y) | ((float)nz < r.o.z) | (r.o.x < 0) | (r.o.y < 0) |
-                        (r.o.z < 0);
+    // exited_volume, utility_ray.cl:112-117 (strict).  floor() of a coordinate in (-1,0) is -1, so "any coordinate
+    // < 0" is one sign test on the OR of the three floored coordinates; inside [0,dim] floor == trunc.
+    const int x = ifloor(r.o.x), y = ifloor(r.o.y), z = ifloor(r.o.z);
+    const bool exited = ((x | y | z) < 0) | ((float)nx < r.o.x) | ((float)ny < r.o.y) | ((float)nz < r.o.z);
     if (exited) return EV_EXIT;
-    // inside [0,dim]: floor == trunc.  x == dim (exactly on the far face) is outside the field.
-    const int x = f2i(r.o.x), y = f2i(r.o.y), z = f2i(r.o.z);
-    const bool inside = (x < nx) & (y < ny) & (z < nz);
+    // One gather: the field has an apron at x == nx / y == ny / z == nz (a coordinate exactly on the far face) that
+    // holds 0 — the border colour the reference's SDF read returns there — and real voxels are never 0.
+    d = __ldg(p.sdf.f + p.sdf.addr(x, y, z));
+    if (d > 0) continue;  // sign(sdf) > 0  <=>  no event at this voxel
     int clause;
-    if (inside) {
-      d = __ldg(p.sdf.f + p.sdf.addr(x, y, z));
-      if (d > 0) continue;  // sign(sdf) > 0  <=>  no event at this voxel
-      const int value = p.vol.at(x, y, z);
-      grad = gradient_voxel(p.vol, x, y, z);
-      clause = tf_match(p.tf, value, f2s(length3(grad)));
+    grad = gradient_voxel(p.vol, x, y, z);
+    if (d < 0) {
+      clause = tf_match(p.tf, p.vol.at(x, y, z), f2s(length3(grad)));
     } else {
-      // far-face voxel: value reads the border (0), gradient taps are read as the reference would
-      d = 0;
-      grad = gradient_voxel(p.vol, x, y, z);
+      // far-face position: the value reads the border (0), the gradient taps are read as the reference would
       clause = tf_match(p.tf, 0, f2s(length3(grad)));
       if (clause == 0) continue;
     }
@@ -160,7 +157,8 @@ __global__ void __launch_bounds__(128) k_trace(const RenderParams p) {
   if (x < p.W && y < p.row1) {
     c_samples = 1;
     const size_t pix = (size_t)y * p.W + x;
-    Ray vray = generate_ray(p.cam_pos, p.cam_dir, x, y, p.W, p.H);
+    const int seed = p.seeds[blockIdx.z];
+    Ray vray = generate_ray(p.cam_pos, p.cam_dir, p.cam_side, p.cam_up, x, y, p.W, p.H);
     // in_volume / cut, ray_marching.cl:165-170
     bool is_cut;
     f3 cut_point;
@@ -212,7 +210,7 @@ __global__ void __launch_bounds__(128) k_trace(const RenderParams p) {
         for (int o = 1; o <= 2; ++o) {
           // ray_bounce_fake_reflectance, utility_ray.cl:106-109; ray_marching.cl:48-50
           cur.o = hit_information.o + hit_information.d;
-          cur.d = hemisphere_reflective(normal, p.seed + o, (float)color[3] / 255.0f, (unsigned)x, (unsigned)y);
+          cur.d = hemisphere_reflective(normal, seed + o, (float)color[3] / 255.0f, (unsigned)x, (unsigned)y);
           cur.o = cur.o + normal * 2.0f;
           float atten = fabsf(dot3(cur.d, normal));
           for (int i = 8; i <= 10; ++i) {
@@ -230,7 +228,7 @@ __global__ void __launch_bounds__(128) k_trace(const RenderParams p) {
               const f3 n2 = -normalize3(grad);
               c_normals++;
               cur.o = cur.o + cur.d;
-              cur.d = hemisphere_reflective(n2, p.seed + o + i, (float)color[3] / 255.0f, (unsigned)x, (unsigned)y);
+              cur.d = hemisphere_reflective(n2, seed + o + i, (float)color[3] / 255.0f, (unsigned)x, (unsigned)y);
               cur.o = cur.o + n2 * 2.0f;
               atten *= fabsf(dot3(cur.d, n2));
               r_energy *= (float)color[0] / 255.0f;
@@ -281,12 +279,44 @@ __global__ void __launch_bounds__(256) k_resolve(const uint32_t* __restrict__ hi
                            (unsigned char)min(f2u(fb), 255u), 1);
 }
 
-int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], int32_t seed, bool trace, bool resolve) {
+// Host evaluation of utility_ray.cl:70-76 in fp32, same operation order as the device helpers (dot3/length3/normalize3).
+// volatile keeps every intermediate in fp32 and forbids contraction, so the result is bit-identical to the per-pixel
+// evaluation the reference does.
+namespace {
+struct h3 { float x, y, z; };
+inline h3 h_cross(h3 a, h3 b) {
+  volatile float x0 = a.y * b.z, x1 = a.z * b.y, y0 = a.z * b.x, y1 = a.x * b.z, z0 = a.x * b.y, z1 = a.y * b.x;
+  volatile float x = x0 - x1, y = y0 - y1, z = z0 - z1;
+  return {x, y, z};
+}
+inline h3 h_normalize(h3 a) {
+  volatile float xx = a.x * a.x, yy = a.y * a.y, zz = a.z * a.z;
+  volatile float s0 = xx + yy;
+  volatile float s1 = s0 + zz;
+  volatile float l = sqrtf(s1);
+  if (l == 0.0f) return {0.0f, 0.0f, 0.0f};
+  volatile float x = a.x / l, y = a.y / l, z = a.z / l;
+  return {x, y, z};
+}
+void camera_basis(const float dir[3], f3* side, f3* up) {
+  const h3 upv = {0.0f, 1.0f, 0.0f};
+  const h3 d = {dir[0], dir[1], dir[2]};
+  h3 s = h_normalize(h_cross(upv, d));
+  h3 u = h_normalize(h_cross(d, s));
+  if (u.y < 0) { u.x = -u.x; u.y = -u.y; u.z = -u.z; }
+  *side = {s.x, s.y, s.z};
+  *up = {u.x, u.y, u.z};
+}
+}  // namespace
+
+int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int32_t* seeds, int nframes, bool trace,
+               bool resolve) {
   vr_ctx* ctx = r->ctx;
   const int rows = r->row1 - r->row0;
   if (rows <= 0) return VR_OK;
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-  if (r->timing && trace && resolve) {
+  if (nframes < 1 || nframes > VR_MAX_BATCH) { vr_set_error("vrk_render: bad batch size"); return VR_ERR_INVALID; }
+  if (r->timing && trace) {
     while (r->ev.size() < r->ev_used + 3) {
       cudaEvent_t e;
       VR_CUDA(cudaEventCreate(&e));
@@ -294,12 +324,13 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], int32_t s
     }
     e0 = r->ev[r->ev_used]; e1 = r->ev[r->ev_used + 1]; e2 = r->ev[r->ev_used + 2];
     r->ev_used += 3;
+    r->ev_frames.push_back(nframes);
     VR_CUDA(cudaEventRecord(e0, ctx->stream));
   }
   if (trace) {
     RenderParams p;
     p.vol = VolView{r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz};
-    p.sdf = SdfView{r->sdf->field, r->sdf->nx, r->sdf->ny, r->sdf->nz, (r->sdf->nx + 7) / 8, (r->sdf->ny + 7) / 8};
+    p.sdf = SdfView{r->sdf->field, r->sdf->nx, r->sdf->ny, r->sdf->nz, r->sdf->nx / 8 + 1, r->sdf->ny / 8 + 1};
     p.env = r->env->texels;
     p.env_w = r->env->w;
     p.env_h = r->env->h;
@@ -309,11 +340,13 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], int32_t s
     p.W = r->W; p.H = r->H; p.row0 = r->row0; p.row1 = r->row1;
     p.cam_pos = {pos[0], pos[1], pos[2]};
     p.cam_dir = {dir[0], dir[1], dir[2]};
-    p.seed = seed;
+    camera_basis(dir, &p.cam_side, &p.cam_up);
+    p.nframes = nframes;
+    for (int k = 0; k < nframes; ++k) p.seeds[k] = seeds[k];
     p.token_cap = r->token_cap;
     p.counters = r->counters;
     p.tf = r->tf_active;
-    dim3 grid(div_up(r->W, 8), div_up(rows, 16));
+    dim3 grid(div_up(r->W, 8), div_up(rows, 16), nframes);
     if (r->count) k_trace<true><<<grid, 128, 0, ctx->stream>>>(p);
     else k_trace<false><<<grid, 128, 0, ctx->stream>>>(p);
     ctx->launches++;

@@ -15,7 +15,7 @@
 // B200 formulation:
 //   * A value written during level i is i+1 > i, so it can neither satisfy nor break another voxel's `min == i` test in
 //     the same level: the update is hazard-free IN PLACE — one int8 field, no ping-pong.
-//   * The field lives in 8x8x8 bricks (512 contiguous bytes): a 32-byte sector is an 8x4x1 patch and a 128-byte line an
+//   * The field lives in 8x8x8 bricks (512 contiguous bytes) covering coordinates 0..n inclusive (apron of zeros): a 32-byte sector is an 8x4x1 patch and a 128-byte line an
 //     8x8x2 slab, which is also what the ray marcher's gathers want (vr_render.cu).
 //   * Only bricks next to the wavefront are visited: a brick that finalised a voxel at level i enqueues itself and its
 //     26 neighbours (deduplicated with an atomicExch stamp) for level i+1.  Each visit stages the brick's 10^3 halo
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(SDF_THREADS) k_sdf_base(VolView vol, TfTable t
     const int v = threadIdx.x + k * SDF_THREADS;
     const int lx = v & 7, ly = (v >> 3) & 7, lz = v >> 6;
     const int x = bx * BR + lx, y = by * BR + ly, z = bz * BR + lz;
-    int val = max_it;  // padding voxels beyond the volume are never read
+    int val = 0;  // apron / padding cells: the border colour 0 (vr_device.cuh SdfView)
     if (x < g.nx && y < g.ny && z < g.nz) {
       const int c = (lz + 1) * HALO * HALO + (ly + 1) * HALO + (lx + 1);
       const int e = ev[c];
@@ -193,13 +193,13 @@ __global__ void __launch_bounds__(256) k_sdf_unbrick(BrickDims g, const int8_t* 
 }
 
 size_t vrk_sdf_field_bytes(int nx, int ny, int nz) {
-  return (size_t)div_up(nx, BR) * div_up(ny, BR) * div_up(nz, BR) * BRV;
+  return (size_t)(nx / BR + 1) * (ny / BR + 1) * (nz / BR + 1) * BRV;
 }
 
 int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field,
                   int* levels_out, int* max_it_out) {
   const int max_it = std::min(std::max(nx, std::max(ny, nz)) / 2, 127);  // signed_distance_field.cpp:11
-  BrickDims g{nx, ny, nz, (int)div_up(nx, BR), (int)div_up(ny, BR), (int)div_up(nz, BR)};
+  BrickDims g{nx, ny, nz, nx / BR + 1, ny / BR + 1, nz / BR + 1};
   const size_t nbricks = (size_t)g.bx * g.by * g.bz;
   // scratch: stamp[nbricks] | list A[nbricks] | list B[nbricks] | counts[130]
   uint32_t* scratch = nullptr;
@@ -233,7 +233,7 @@ int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const
 }
 
 int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear) {
-  BrickDims g{nx, ny, nz, (int)div_up(nx, BR), (int)div_up(ny, BR), (int)div_up(nz, BR)};
+  BrickDims g{nx, ny, nz, nx / BR + 1, ny / BR + 1, nz / BR + 1};
   const size_t n = (size_t)nx * ny * nz;
   const unsigned blocks = (unsigned)std::min<size_t>(div_up(n, 256), (size_t)ctx->sm_count * 16);
   k_sdf_unbrick<<<blocks, 256, 0, ctx->stream>>>(g, field, linear);

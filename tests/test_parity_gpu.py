@@ -230,3 +230,42 @@ def test_tf_code_entry_point_equals_table(vr_ctx):
     b = r.render_frame(pos, d, 3)
     assert np.array_equal(a, b)
     r.close(); [k.close() for k in keep]
+
+
+def test_render_frames_batch_equals_sequential_oracle(vr_ctx):
+    # vr_render_frames traces the whole batch in one launch (gridDim.z = frame) and resolves once; below the token cap
+    # the samples commute (integer atomics), so cache and final frame must equal the oracle's frame-by-frame result.
+    r, ref, keep = _scene(vr_ctx, 64, 128, 96)
+    pos, d = synth.default_camera(64)
+    seeds = synth.glibc_rand(10)
+    got = r.render_frames(pos, d, seeds)
+    for s in seeds:
+        want = ref.render_frame(pos, d, s)
+    gc, wc = r.cache_download().astype(np.int32), ref.cache.astype(np.int32)
+    assert gc.reshape(-1, 4)[:, 3].max() < 256
+    assert np.array_equal(gc.reshape(-1, 4)[:, 3], wc.reshape(-1, 4)[:, 3])
+    assert (gc == wc).mean() >= 0.999
+    assert np.array_equal(got[..., 3], want[..., 3])
+    assert _psnr(got[..., :3], want[..., :3]) >= 45.0
+    r.close(); [k.close() for k in keep]
+
+
+def test_render_far_face_positions(vr_ctx):
+    # rays that land exactly on the far faces (coordinate == dim): axis-aligned steps of 0.5 from integer origins.
+    # The SDF apron must behave like the reference's border read (0 -> step 0.5) and the TF must see value 0.
+    n = 16
+    v = np.zeros((n, n, n), dtype=np.int16)
+    v[:, :, n - 1] = 900  # a slab touching the far x face, so the gradient tap at x == n sees it
+    envimg = synth.synth_env(64, 32)
+    tf = [{"min_v": -10.0, "max_v": 10.0, "min_g": 500.0, "max_g": 2000.0, "flags": 1, "rgba": (200, 100, 50, 255)},
+          {"min_v": 500.0, "max_v": 1200.0, "min_g": 0.0, "max_g": 0.0, "flags": 0, "rgba": (255, 255, 255, 255)}]
+    vol = api.Volume(vr_ctx, v); env = api.EnvMap(vr_ctx, envimg)
+    r = api.Renderer(vr_ctx, 32, 32); r.image_set(vol, env); r.set_tf(tf); r.flush_changes()
+    ref = o.Renderer(v, envimg, tf, 32, 32)
+    assert np.array_equal(r.sdf_download(), ref.sdf)
+    for pos, d in [((-4.0, 8.0, 8.0), (1.0, 0.0, 0.0)), ((8.0, 8.0, -4.0), (0.0, 0.0, 1.0)), ((20.0, 8.0, 8.0), (-1.0, 0.0, 0.0))]:
+        r.reset_cache(); ref.reset()
+        got = r.render_frame(pos, d, 5); want = ref.render_frame(pos, d, 5)
+        assert np.array_equal(got[..., 3], want[..., 3])
+        assert np.array_equal(r.cache_download().reshape(-1, 4)[:, 3], ref.cache.reshape(-1, 4)[:, 3])
+    r.close(); env.close(); vol.close()
