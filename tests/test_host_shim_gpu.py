@@ -1,0 +1,47 @@
+"""GPU suite: the C++ host shim (cl_volume_renderer_b200/host/vr_host.hpp) driven like the reference's app
+(ui::run start-up, render loop, render_tf, and the reference's SDF test) against the CPU oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as o
+from cl_volume_renderer_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "tests", "cpp", "frame_emitter_driver")
+
+
+def test_frame_emitter_flow_matches_oracle(tmp_path):
+    assert os.path.exists(DRIVER), "build the driver: make host"
+    n, W, H, frames = 64, 160, 120, 4
+    v = synth.synth_ct(n)
+    env = synth.synth_env(128, 64)
+    v.tofile(tmp_path / "vol.raw")
+    env.tofile(tmp_path / "env.raw")
+    out = subprocess.run([DRIVER, str(tmp_path / "vol.raw"), str(n), str(n), str(n), str(tmp_path / "env.raw"), "128", "64",
+                          str(W), str(H), str(frames), str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert "EVERYTHING FINE" in out.stdout
+    # oracle: same flow — default TF, seeds = glibc rand() stream, camera (-200,200,-200)*n/256, look (0.9, 6.183)
+    tf = synth.default_tf()
+    ref = o.Renderer(v, env, tf, W, H)
+    pos, d = synth.default_camera(n)
+    for s in synth.glibc_rand(frames):
+        want = ref.render_frame(pos, d, s)
+    got = np.fromfile(tmp_path / "frame.bin", dtype=np.uint8).reshape(H, W, 4)
+    assert np.array_equal(got[..., 3], want[..., 3])
+    mse = np.mean((got[..., :3].astype(np.float64) - want[..., :3].astype(np.float64)) ** 2)
+    assert mse == 0 or 10 * np.log10(255.0 ** 2 / mse) >= 45.0
+    # render_tf with the UI's clips (value [-2000,3000], gradient [0,4000])
+    st = o.fetch_stats(v)
+    rng = [float(max(-2000, st[0])), float(min(3000, st[1])), float(max(0, st[2])), float(min(4000, st[3]))]
+    want_tf, _, _ = o.tf_color_frame(o.histogram(v, 100, 80, rng), 100, 80)
+    got_tf = np.fromfile(tmp_path / "tf.bin", dtype=np.uint8).reshape(80, 100, 4)
+    assert np.array_equal(got_tf, want_tf)
+    # the reference's SDF test flow (`value > 800`)
+    got_sdf = np.fromfile(tmp_path / "sdf.bin", dtype=np.int8).reshape(n, n, n)
+    assert np.array_equal(got_sdf, o.sdf_build(v, o.tf_threshold(800))[0])
+    assert f"stats {rng[0]:g} {rng[1]:g} {rng[2]:g} {rng[3]:g}" in out.stdout
