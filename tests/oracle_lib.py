@@ -194,5 +194,16 @@ class Renderer:
         return frame
 
 
+def render_frame_immediate(r, cam_pos, cam_dir, seed, window=None):
+    """single-phase, row-major sequential execution (see orc_render_frame_immediate) on Renderer r's state"""
+    frame = np.zeros((r.H, r.W, 4), dtype=np.uint8)
+    x0, y0, x1, y1 = window if window else (0, 0, r.W, r.H)
+    lib().orc_render_frame_immediate(_p(r.vol), r.nx, r.ny, r.nz, _p(r.sdf), _p(r.env), r.env.shape[1], r.env.shape[0],
+                                     r.tf, r.ntf, _p(r.cache), r.token_cap, r.W, r.H, x0, y0, x1, y1,
+                                     (C.c_float * 3)(*[float(v) for v in cam_pos]),
+                                     (C.c_float * 3)(*[float(v) for v in cam_dir]), C.c_int32(seed), _p(frame))
+    return frame
+
+
 def num_threads():
     return lib().orc_num_threads()
