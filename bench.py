@@ -116,29 +116,42 @@ def run_reference(args, rank, world):
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as o
+    import ref_lib as R
     from cl_volume_renderer_b200 import synth
     vol, env, pos, d = make_scene()
     t = time.time()
+    # SDF for the 512^3 scene: built by the oracle (bit-identical to the reference kernels' result — tests/
+    # test_ref_pinning_cpu.py — but minutes faster than their 9-TF-evaluations-per-voxel base pass); untimed set-up
     sdf, iters = o.sdf_build(vol, synth.default_tf())
     sdf_s = time.time() - t
     log(f"oracle SDF build {VOL_N}^3: {sdf_s:.1f}s ({iters} iterations, {o.num_threads()} threads)")
-    r = o.Renderer(vol, env, synth.default_tf(), W, H, sdf=sdf)
     seeds = synth.glibc_rand(args.steps + args.warmup)
+    if R.available():
+        kind, cores = "reference", R.num_threads()
+        r = R.Renderer(vol, env, synth.default_tf(), W, H, sdf)
+        frame_fn = lambda s: r.render_frame(pos, d, s, threads=0)  # noqa: E731
+        what = "the reference's own ray_marching.cl `render` kernel compiled for the host (oracle/_ref), OpenMP over rows"
+    else:
+        kind, cores = "port", o.num_threads()
+        r = o.Renderer(vol, env, synth.default_tf(), W, H, sdf=sdf)
+        frame_fn = lambda s: r.render_frame(pos, d, s)  # noqa: E731
+        what = "CPU restatement of the reference kernels (oracle/oracle.cpp), OpenMP over rows"
     for k in range(args.warmup):
-        r.render_frame(pos, d, seeds[k])
+        frame_fn(seeds[k])
     t0 = time.perf_counter()
     for k in range(args.steps):
-        r.render_frame(pos, d, seeds[args.warmup + k])
+        frame_fn(seeds[args.warmup + k])
     dt = time.perf_counter() - t0
     value = W * H * args.steps / dt / 1e6
-    sample = f"{args.steps} x 1 spp frame of the workload (SDF built once beforehand by the oracle in {sdf_s:.1f}s, untimed)"
+    sample = (f"{args.steps} x 1 spp frame of the workload; {what}; SDF built once beforehand on the CPU in {sdf_s:.1f}s, "
+              f"untimed")
     print(json.dumps({
         "impl": "reference", "metric": "path_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": o.num_threads(), "kind": "port", "sample": sample,
-                         "sdf_build_ms": 1e3 * sdf_s},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample,
+                         "sdf_build_ms_oracle": 1e3 * sdf_s},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -287,18 +300,28 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as o
+        import ref_lib as R
         sdf_np = r.sdf_download()  # bit-identical to the oracle's (tests/test_parity_gpu.py); saves minutes of CPU SDF build
-        ref = o.Renderer(vol_np, env_np, synth.default_tf(), W, H, sdf=sdf_np)
-        ref.render_frame(pos, d, seeds[0], want_frame=False)
+        if R.available():
+            kind, cores = "reference", R.num_threads()
+            ref = R.Renderer(vol_np, env_np, synth.default_tf(), W, H, sdf_np)
+            frame_fn = lambda s: ref.render_frame(pos, d, s, threads=0)  # noqa: E731
+            what = "the reference's own `render` kernel compiled for the host (oracle/_ref), OpenMP over rows"
+        else:
+            kind, cores = "port", o.num_threads()
+            ref = o.Renderer(vol_np, env_np, synth.default_tf(), W, H, sdf=sdf_np)
+            frame_fn = lambda s: ref.render_frame(pos, d, s)  # noqa: E731
+            what = "oracle/oracle.cpp, OpenMP over rows"
+        frame_fn(seeds[0])
         t0 = time.perf_counter()
         nfr = 0
-        while nfr < 8 and (time.perf_counter() - t0) < 10.0:
-            ref.render_frame(pos, d, seeds[1 + nfr])
+        while nfr < 16 and (time.perf_counter() - t0) < 12.0:
+            frame_fn(seeds[1 + nfr])
             nfr += 1
         dt = time.perf_counter() - t0
-        cpu = {"value": W * H * nfr / dt / 1e6, "unit": "Msamples/s", "cores": o.num_threads(), "kind": "port",
-               "sample": f"{nfr} x 1 spp frame of the same 1920x1080/512^3 scene (oracle/oracle.cpp, OpenMP; SDF taken from the "
-                         f"GPU build, which the parity tests pin bit-exact)"}
+        cpu = {"value": W * H * nfr / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind,
+               "sample": f"{nfr} x 1 spp frame of the same 1920x1080/512^3 scene ({what}; SDF taken from the GPU build, which "
+                         f"the parity tests pin bit-exact)"}
 
     if rank == 0:
         hbm, peak_src = peaks()
