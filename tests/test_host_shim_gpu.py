@@ -38,8 +38,10 @@ def test_frame_emitter_flow_matches_oracle(tmp_path):
     # render_tf with the UI's clips (value [-2000,3000], gradient [0,4000])
     st = o.fetch_stats(v)
     rng = [float(max(-2000, st[0])), float(min(3000, st[1])), float(max(0, st[2])), float(min(4000, st[3]))]
-    want_tf, _, _ = o.tf_color_frame(o.histogram(v, 100, 80, rng), 100, 80)
-    got_tf = np.fromfile(tmp_path / "tf.bin", dtype=np.uint8).reshape(80, 100, 4)
+    # the driver calls render_tf(100, 80); the implementation names its parameters (height, width) (renderer.cpp:45 vs
+    # renderer.hpp:26), so the image is 80 wide and 100 tall
+    want_tf, _, _ = o.tf_color_frame(o.histogram(v, 80, 100, rng), 80, 100)
+    got_tf = np.fromfile(tmp_path / "tf.bin", dtype=np.uint8).reshape(100, 80, 4)
     assert np.array_equal(got_tf, want_tf)
     # the reference's SDF test flow (`value > 800`)
     got_sdf = np.fromfile(tmp_path / "sdf.bin", dtype=np.int8).reshape(n, n, n)
