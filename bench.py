@@ -7,8 +7,8 @@
 One STEP = one pass of the hot path over one batch: cache reset (buffer_reset) + 64 render_frame calls (64 spp,
 trace + resolve per frame) at 1920x1080 on the 512^3 synthetic CT volume, starting from a freshly reset voxel cache.
 N > 1: spp split (BASELINE config 3, weak scaling): every rank holds the whole scene, renders its own 64 frames with its
-own seeds and a token cap of 256/N, then the packed voxel caches are summed with one NCCL all-reduce and every rank
-resolves the frame.  value = N * W*H*64 / max-over-ranks device time.
+own seeds and a token cap of 256/N, then the touched cache entries (one per pixel: all ranks trace the same camera and
+therefore hit the same voxels) are summed with one NCCL all-reduce and every rank resolves the frame.  value = N * W*H*64 / max-over-ranks device time.
 
 Keys beyond the base contract: `roofline` (dominant kernel k_trace, algorithmic bytes of SURVEY.md §8d over its
 CUDA-event time), `cpu_baseline` (the CPU oracle on a bounded sample of the same workload), `e2e` (the same metric
@@ -191,16 +191,19 @@ def run_ours(args, rank, world, local_rank):
     r.set_token_cap(max(256 // world, 1))
     r.flush_changes()
     ctx.synchronize()
-    cache_t = None
+    xchg_t = None
     if world > 1:
-        cache_t = torch.as_tensor(_DevArray(r.cache_device_ptr, r.cache_bytes // 4, "<i4"), device=f"cuda:{local_rank}")
+        # compact exchange buffer: one 8-byte cache entry per pixel (all ranks trace the same camera, hence the same voxels)
+        xchg_t = torch.as_tensor(_DevArray(r.xchg_device_ptr, r.xchg_bytes // 4, "<i4"), device=f"cuda:{local_rank}")
 
     def step():
         r.reset_cache()
         r.render_frames(pos, d, seeds, readback=False)
         if world > 1:
+            r.xchg_gather()
             with torch.cuda.stream(ext):
-                dist.all_reduce(cache_t)  # int32 view of the packed lanes: sums cannot carry across lanes (cap 256/N)
+                dist.all_reduce(xchg_t)  # int32 view of the packed lanes: sums cannot carry across lanes (cap 256/N)
+            r.xchg_scatter()
             r.resolve(readback=False)
 
     def barrier():
@@ -304,9 +307,11 @@ def run_ours(args, rank, world, local_rank):
             r2.render_frames(pos, d, seeds, out=hf)        # one D2H of the final frame
         else:
             r2.render_frames(pos, d, seeds, readback=False)
-            c2 = torch.as_tensor(_DevArray(r2.cache_device_ptr, r2.cache_bytes // 4, "<i4"), device=f"cuda:{local_rank}")
+            r2.xchg_gather()
+            c2 = torch.as_tensor(_DevArray(r2.xchg_device_ptr, r2.xchg_bytes // 4, "<i4"), device=f"cuda:{local_rank}")
             with torch.cuda.stream(ext):
                 dist.all_reduce(c2)
+            r2.xchg_scatter()
             api._check(api.lib().vr_renderer_resolve(r2.h, hf.ctypes.data_as(api.C.c_void_p)))
         checksum = int(hf[::97, ::89].sum())
         r2.close(); en2.close(); v2.close()
@@ -324,6 +329,30 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return samples_per_step * e2e_steps / float(tt.item()) / 1e6
 
+    if os.environ.get("VR_E2E_BREAKDOWN"):
+        for it in range(2):
+            marks = []
+            def m(name):
+                ctx.synchronize(); marks.append((name, time.perf_counter()))
+            m("start")
+            v2 = api.Volume(ctx, vol_pin.numpy()); m("volume_upload+stats")
+            en2 = api.EnvMap(ctx, env_pin.numpy()); m("env")
+            r2 = api.Renderer(ctx, W, H); m("renderer_create")
+            r2.image_set(v2, en2); r2.next_event_code_set(tf_code); r2.set_token_cap(max(256 // world, 1))
+            r2.flush_changes(); m("flush")
+            hf = r2.host_frame()
+            r2.render_frames(pos, d, seeds, readback=False); m("render_frames")
+            if world > 1:
+                r2.xchg_gather(); m("gather")
+                c2 = torch.as_tensor(_DevArray(r2.xchg_device_ptr, r2.xchg_bytes // 4, "<i4"), device=f"cuda:{local_rank}")
+                m("as_tensor")
+                with torch.cuda.stream(ext):
+                    dist.all_reduce(c2)
+                m("all_reduce")
+                r2.xchg_scatter(); m("scatter")
+            api._check(api.lib().vr_renderer_resolve(r2.h, hf.ctypes.data_as(api.C.c_void_p))); m("resolve+readback")
+            r2.close(); m("renderer_close"); en2.close(); v2.close(); m("scene_close")
+            log(f"[rank {rank}] e2e breakdown: " + ", ".join(f"{n} {1e3*(t-marks[i][1]):.2f}ms" for i, (n, t) in enumerate(marks[1:])))
     e2e_value = time_e2e(False)
     e2e_interactive = time_e2e(True) if world == 1 else None
 

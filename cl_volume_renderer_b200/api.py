@@ -76,6 +76,10 @@ SYMBOLS = {
     "vr_renderer_cache_bytes": (C.c_size_t, [_P]),
     "vr_renderer_frame_device_ptr": (_P, [_P]),
     "vr_renderer_resolve": (C.c_int, [_P, _P]),
+    "vr_renderer_xchg_gather": (C.c_int, [_P]),
+    "vr_renderer_xchg_scatter": (C.c_int, [_P]),
+    "vr_renderer_xchg_device_ptr": (_P, [_P]),
+    "vr_renderer_xchg_bytes": (C.c_size_t, [_P]),
     "vr_renderer_enable_counters": (C.c_int, [_P, C.c_int]),
     "vr_renderer_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int]),
     "vr_renderer_enable_timing": (C.c_int, [_P, C.c_int]),
@@ -369,3 +373,17 @@ class Renderer:
         n = C.c_int(0)
         _check(lib().vr_renderer_kernel_times(self.h, ms, C.byref(n), 1 if reset else 0))
         return ms[0], ms[1], n.value
+
+    def xchg_gather(self):
+        _check(lib().vr_renderer_xchg_gather(self.h))
+
+    def xchg_scatter(self):
+        _check(lib().vr_renderer_xchg_scatter(self.h))
+
+    @property
+    def xchg_device_ptr(self):
+        return lib().vr_renderer_xchg_device_ptr(self.h)
+
+    @property
+    def xchg_bytes(self):
+        return int(lib().vr_renderer_xchg_bytes(self.h))

@@ -29,6 +29,18 @@ static void pool_free(vr_ctx* ctx, void* p) {
   if (p) cudaFreeAsync(p, ctx->stream);
 }
 
+static cudaError_t pinned_acquire(vr_ctx* ctx, void** p, size_t bytes) {
+  for (auto& b : ctx->pinned)
+    if (!b.in_use && b.bytes == bytes) { b.in_use = true; *p = b.p; return cudaSuccess; }
+  cudaError_t e = cudaMallocHost(p, bytes);
+  if (e == cudaSuccess) ctx->pinned.push_back({*p, bytes, true});
+  return e;
+}
+static void pinned_release(vr_ctx* ctx, void* p) {
+  for (auto& b : ctx->pinned)
+    if (b.p == p) b.in_use = false;
+}
+
 // ---- context -------------------------------------------------------------------------------------------------
 extern "C" int vr_ctx_create(int device_ordinal, vr_ctx** out) {
   VR_REQUIRE(out, "vr_ctx_create: null out");
@@ -70,6 +82,7 @@ extern "C" void vr_ctx_destroy(vr_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->scratch);
   cudaFreeHost(c->scratch_host);
+  for (auto& b : c->pinned) cudaFreeHost(b.p);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -263,7 +276,7 @@ extern "C" int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_rendere
   VR_CUDA(pool_alloc(ctx, &r->frame, px * 4));
   VR_CUDA(pool_alloc(ctx, &r->hit, px * 4));
   VR_CUDA(pool_alloc(ctx, &r->counters, 6 * sizeof(unsigned long long)));
-  VR_CUDA(cudaMallocHost(&r->frame_host, px * 4));
+  VR_CUDA(pinned_acquire(ctx, reinterpret_cast<void**>(&r->frame_host), px * 4));
   VR_CUDA(cudaMemsetAsync(r->frame, 0, px * 4, ctx->stream));
   VR_CUDA(cudaMemsetAsync(r->hit, 0xFF, px * 4, ctx->stream));
   VR_CUDA(cudaMemsetAsync(r->counters, 0, 6 * sizeof(unsigned long long), ctx->stream));
@@ -281,9 +294,10 @@ extern "C" void vr_renderer_destroy(vr_renderer* r) {
   pool_free(r->ctx, r->hit);
   pool_free(r->ctx, r->frame);
   pool_free(r->ctx, r->counters);
+  pool_free(r->ctx, r->xchg);
   cudaStreamSynchronize(r->ctx->stream);
   for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
-  cudaFreeHost(r->frame_host);
+  pinned_release(r->ctx, r->frame_host);
   delete r;
 }
 
@@ -423,6 +437,29 @@ extern "C" int vr_renderer_counters(const vr_renderer* r, uint64_t out[6], int r
   VR_CUDA(cudaStreamSynchronize(r->ctx->stream));
   return VR_OK;
 }
+
+static int ensure_xchg(vr_renderer* r) {
+  if (!r->xchg) VR_CUDA(pool_alloc(r->ctx, &r->xchg, (size_t)r->W * r->H * sizeof(uint2)));
+  return VR_OK;
+}
+extern "C" int vr_renderer_xchg_gather(vr_renderer* r) {
+  VR_REQUIRE(r && r->cache, "vr_renderer_xchg_gather: call vr_renderer_flush first");
+  VR_CUDA(cudaSetDevice(r->ctx->device));
+  VR_TRY(ensure_xchg(r));
+  return vrk_xchg(r, r->xchg, false);
+}
+extern "C" int vr_renderer_xchg_scatter(vr_renderer* r) {
+  VR_REQUIRE(r && r->cache && r->xchg, "vr_renderer_xchg_scatter: nothing gathered");
+  VR_CUDA(cudaSetDevice(r->ctx->device));
+  return vrk_xchg(r, r->xchg, true);
+}
+extern "C" void* vr_renderer_xchg_device_ptr(vr_renderer* r) {
+  if (!r) return nullptr;
+  cudaSetDevice(r->ctx->device);
+  if (ensure_xchg(r) != VR_OK) return nullptr;
+  return r->xchg;
+}
+extern "C" size_t vr_renderer_xchg_bytes(const vr_renderer* r) { return r ? (size_t)r->W * r->H * sizeof(uint2) : 0; }
 
 extern "C" int vr_renderer_enable_timing(vr_renderer* r, int enable) {
   VR_REQUIRE(r, "vr_renderer_enable_timing: null argument");

@@ -39,6 +39,9 @@ struct vr_ctx {
   uint64_t launches = 0;
   int32_t* scratch = nullptr;  // small device scratch (counters, stats), 4 KiB
   int32_t* scratch_host = nullptr;  // pinned mirror
+  // pinned host frame buffers are recycled across renderers: cudaMallocHost / cudaFreeHost cost milliseconds each
+  struct PinnedBuf { void* p; size_t bytes; bool in_use; };
+  std::vector<PinnedBuf> pinned;
 };
 
 // Device-side TF table, passed to kernels by value.
@@ -93,6 +96,7 @@ struct vr_renderer {
   int token_cap = 256;
   bool count = false;
   unsigned long long* counters = nullptr;  // 6 x u64 on device
+  uint2* xchg = nullptr;  // W*H compact cache entries for the spp-split exchange (allocated on first use)
   bool timing = false;
   std::vector<cudaEvent_t> ev;  // 3 events per timed launch: before trace, between, after resolve
   size_t ev_used = 0;
@@ -118,4 +122,5 @@ int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels);
 int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int32_t* seeds, int nframes, bool trace,
                bool resolve);
 
+int vrk_xchg(vr_renderer* r, uint2* xchg, bool scatter);
 TfTable vr_make_tf_table(const vr_tf_rect* rects, int n);

@@ -362,3 +362,36 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
   VR_CUDA(cudaGetLastError());
   return VR_OK;
 }
+
+// ---- compact cache exchange for the spp split (multi-GPU hook, no reference counterpart) -----------------------------
+// Every rank of an spp split traces the SAME camera, so the primary hit voxel of a pixel — and therefore the set of
+// cache entries touched since the last reset — is identical on all ranks.  Instead of all-reducing the dense cache
+// (8 bytes x voxels: 1 GiB at 512^3) the ranks exchange one 8-byte entry per pixel (16 MB at 1080p):
+//   gather : xchg[pix] = cache[hit[pix]]  (0 for environment pixels)
+//   (caller: sum-all-reduce xchg as int32 words — 16-bit lanes cannot carry with a per-rank token cap of 256/N)
+//   scatter: cache[hit[pix]] = xchg[pix]  (pixels sharing a voxel write the same global sum)
+__global__ void __launch_bounds__(256) k_xchg_gather(const uint32_t* __restrict__ hit, const uint2* __restrict__ cache,
+                                                     uint2* __restrict__ xchg, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t voxel = hit[i];
+  xchg[i] = voxel == VR_MISS ? make_uint2(0u, 0u) : cache[voxel];
+}
+__global__ void __launch_bounds__(256) k_xchg_scatter(const uint32_t* __restrict__ hit, uint2* __restrict__ cache,
+                                                      const uint2* __restrict__ xchg, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t voxel = hit[i];
+  if (voxel != VR_MISS) cache[voxel] = xchg[i];
+}
+
+int vrk_xchg(vr_renderer* r, uint2* xchg, bool scatter) {
+  const size_t n = (size_t)r->W * r->H;
+  if (scatter)
+    k_xchg_scatter<<<div_up(n, 256), 256, 0, r->ctx->stream>>>(r->hit, reinterpret_cast<uint2*>(r->cache), xchg, n);
+  else
+    k_xchg_gather<<<div_up(n, 256), 256, 0, r->ctx->stream>>>(r->hit, reinterpret_cast<const uint2*>(r->cache), xchg, n);
+  r->ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}

@@ -155,6 +155,14 @@ int vr_renderer_set_rows(vr_renderer* r, int y0, int y1);
 void* vr_renderer_cache_device_ptr(const vr_renderer* r);
 size_t vr_renderer_cache_bytes(const vr_renderer* r);
 void* vr_renderer_frame_device_ptr(const vr_renderer* r);
+/* Compact cache exchange for the spp split: all ranks trace the same camera, so they touch the same voxels (the
+ * pixels' primary hit voxels).  gather copies cache[hit[pix]] into a W*H*8-byte device buffer (pointer returned by
+ * vr_renderer_xchg_device_ptr), the caller sum-reduces that buffer across ranks as int32 words, scatter writes the sums
+ * back.  Valid when every rank has traced only this camera since the last vr_renderer_reset_cache / exchange. */
+int vr_renderer_xchg_gather(vr_renderer* r);
+int vr_renderer_xchg_scatter(vr_renderer* r);
+void* vr_renderer_xchg_device_ptr(vr_renderer* r);
+size_t vr_renderer_xchg_bytes(const vr_renderer* r);
 /* re-run only the resolve pass (after an external cache all-reduce) and optionally read the frame back */
 int vr_renderer_resolve(vr_renderer* r, uint8_t* host_rgba);
 
