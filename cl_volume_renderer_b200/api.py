@@ -82,6 +82,7 @@ SYMBOLS = {
     "vr_renderer_xchg_bytes": (C.c_size_t, [_P]),
     "vr_renderer_enable_counters": (C.c_int, [_P, C.c_int]),
     "vr_renderer_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int]),
+    "vr_renderer_set_trace_mode": (C.c_int, [_P, C.c_int]),
     "vr_renderer_enable_timing": (C.c_int, [_P, C.c_int]),
     "vr_renderer_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }
@@ -387,3 +388,6 @@ class Renderer:
     @property
     def xchg_bytes(self):
         return int(lib().vr_renderer_xchg_bytes(self.h))
+
+    def set_trace_mode(self, mode):
+        _check(lib().vr_renderer_set_trace_mode(self.h, mode))

@@ -275,11 +275,12 @@ extern "C" int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_rendere
   const size_t px = (size_t)width * height;
   VR_CUDA(pool_alloc(ctx, &r->frame, px * 4));
   VR_CUDA(pool_alloc(ctx, &r->hit, px * 4));
-  VR_CUDA(pool_alloc(ctx, &r->counters, 6 * sizeof(unsigned long long)));
+  VR_CUDA(pool_alloc(ctx, &r->counters, 8 * sizeof(unsigned long long)));
+  if (const char* m = getenv("VR_TRACE_MODE")) r->trace_mode = atoi(m) ? 1 : 0;
   VR_CUDA(pinned_acquire(ctx, reinterpret_cast<void**>(&r->frame_host), px * 4));
   VR_CUDA(cudaMemsetAsync(r->frame, 0, px * 4, ctx->stream));
   VR_CUDA(cudaMemsetAsync(r->hit, 0xFF, px * 4, ctx->stream));
-  VR_CUDA(cudaMemsetAsync(r->counters, 0, 6 * sizeof(unsigned long long), ctx->stream));
+  VR_CUDA(cudaMemsetAsync(r->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
   VR_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = r;
   return VR_OK;
@@ -295,6 +296,7 @@ extern "C" void vr_renderer_destroy(vr_renderer* r) {
   pool_free(r->ctx, r->frame);
   pool_free(r->ctx, r->counters);
   pool_free(r->ctx, r->xchg);
+  pool_free(r->ctx, r->queue);
   cudaStreamSynchronize(r->ctx->stream);
   for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
   pinned_release(r->ctx, r->frame_host);
@@ -410,6 +412,12 @@ extern "C" const vr_sdf* vr_renderer_sdf(const vr_renderer* r) { return r ? r->s
 extern "C" int vr_renderer_set_token_cap(vr_renderer* r, int cap) {
   VR_REQUIRE(r && cap >= 1 && cap <= 256, "vr_renderer_set_token_cap: cap must be in [1,256]");
   r->token_cap = cap;
+  return VR_OK;
+}
+
+extern "C" int vr_renderer_set_trace_mode(vr_renderer* r, int mode) {
+  VR_REQUIRE(r && (mode == 0 || mode == 1), "vr_renderer_set_trace_mode: mode must be 0 or 1");
+  r->trace_mode = mode;
   return VR_OK;
 }
 

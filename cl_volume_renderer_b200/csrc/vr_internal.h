@@ -95,7 +95,10 @@ struct vr_renderer {
   uint8_t* frame_host = nullptr;  // pinned staging (used when the caller's buffer is pageable)
   int token_cap = 256;
   bool count = false;
-  unsigned long long* counters = nullptr;  // 6 x u64 on device
+  unsigned long long* counters = nullptr;  // 6 x u64 on device (+ 2 spare words: [6] is k_trace_pt's work counter)
+  int trace_mode = 1;  // 0: k_trace alone (a thread per pixel for its whole life), 1: hybrid k_trace + k_trace_pt (default)
+  uint4* queue = nullptr;  // hybrid schedule: admitted primary hits (3 x uint4 each)
+  size_t queue_cap = 0;
   uint2* xchg = nullptr;  // W*H compact cache entries for the spp-split exchange (allocated on first use)
   bool timing = false;
   std::vector<cudaEvent_t> ev;  // 3 events per timed launch: before trace, between, after resolve

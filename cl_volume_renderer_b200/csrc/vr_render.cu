@@ -33,8 +33,35 @@ struct RenderParams {
   int nframes;          // frames in this launch: blockIdx.z selects the seed
   int seeds[VR_MAX_BATCH];
   unsigned long long* counters;
+  // hybrid schedule: k_trace<QUEUE> appends admitted primary hits here, k_trace_pt<FROM_QUEUE> runs their secondary paths
+  uint4* queue;       // 3 x uint4 per record (HitRecord)
+  unsigned* qcount;   // [0] records appended, [1] records consumed
+  unsigned qcap;
   TfTable tf;
 };
+
+// An admitted primary hit, everything ray_marching.cl:42-76 needs: pixel (RNG), seed, cache voxel, the clause whose colour
+// is current, hit_information.origin + hit_information.direction, and the shading normal.
+struct HitRecord {
+  int xy, seed;
+  unsigned voxel;
+  int clause;
+  f3 base, normal;
+};
+__device__ __forceinline__ void store_record(uint4* q, unsigned slot, const HitRecord& h) {
+  q[3 * (size_t)slot + 0] = make_uint4((unsigned)h.xy, (unsigned)h.seed, h.voxel, (unsigned)h.clause);
+  q[3 * (size_t)slot + 1] = make_uint4(__float_as_uint(h.base.x), __float_as_uint(h.base.y), __float_as_uint(h.base.z),
+                                       __float_as_uint(h.normal.x));
+  q[3 * (size_t)slot + 2] = make_uint4(__float_as_uint(h.normal.y), __float_as_uint(h.normal.z), 0u, 0u);
+}
+__device__ __forceinline__ HitRecord load_record(const uint4* q, unsigned slot) {
+  const uint4 a = q[3 * (size_t)slot + 0], b = q[3 * (size_t)slot + 1], c = q[3 * (size_t)slot + 2];
+  HitRecord h;
+  h.xy = (int)a.x; h.seed = (int)a.y; h.voxel = a.z; h.clause = (int)a.w;
+  h.base = {__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)};
+  h.normal = {__uint_as_float(b.w), __uint_as_float(c.x), __uint_as_float(c.y)};
+  return h;
+}
 
 struct Ray {
   f3 o, d;
@@ -111,7 +138,7 @@ __device__ __forceinline__ f3 hemisphere_reflective(f3 normal, int seed, float r
 //   color    in/out: written only when a TF clause with a colour matched (like `*color = tmp_color`)
 template <bool COUNT>
 __device__ __forceinline__ int march_to_next_event(const RenderParams& p, Ray& r, f3& grad, int color[4],
-                                                   unsigned& steps) {
+                                                   int& colour_clause, unsigned& steps) {
   const int nx = p.vol.nx, ny = p.vol.ny, nz = p.vol.nz;
   // SDF value at trunc(origin); border (any coordinate outside the field) reads 0
   int d = p.sdf.at(f2i(r.o.x), f2i(r.o.y), f2i(r.o.z));
@@ -141,6 +168,7 @@ __device__ __forceinline__ int march_to_next_event(const RenderParams& p, Ray& r
       const vr_tf_rect& q = p.tf.r[clause - 1];
       if (!(q.flags & VR_TF_THRESHOLD)) {
         color[0] = q.rgba[0]; color[1] = q.rgba[1]; color[2] = q.rgba[2]; color[3] = q.rgba[3];
+        colour_clause = clause;
       }
     }
     return EV_HIT;
@@ -148,8 +176,8 @@ __device__ __forceinline__ int march_to_next_event(const RenderParams& p, Ray& r
   return EV_NONE;
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(const RenderParams p) {
+template <bool COUNT, bool QUEUE>
+__global__ void __launch_bounds__(128, 12) k_trace(const RenderParams p) {
   // one warp = an 8x4 pixel tile: neighbouring primary rays walk neighbouring voxels
   const int x = blockIdx.x * 8 + (threadIdx.x & 7);
   const int y = p.row0 + blockIdx.y * 16 + (threadIdx.x >> 3);
@@ -170,7 +198,8 @@ __global__ void __launch_bounds__(128) k_trace(const RenderParams p) {
     Ray cur = {cut_point, vray.d};
     f3 grad = {0.0f, 0.0f, 0.0f};
     int color[4] = {0, 0, 0, 0};
-    if (is_cut) ev = march_to_next_event<COUNT>(p, cur, grad, color, c_steps);
+    int colour_clause = 0;
+    if (is_cut) ev = march_to_next_event<COUNT>(p, cur, grad, color, colour_clause, c_steps);
 
     if (ev != EV_HIT) {
       // ray_marching.cl:172-178,188-194: environment colour, alpha 200
@@ -198,6 +227,25 @@ __global__ void __launch_bounds__(128) k_trace(const RenderParams p) {
           else atomicSub(hi, 0x00010000u);
         }
       }
+      // hybrid schedule: hand the secondary paths to k_trace_pt; when the queue is full they run inline below
+      if (QUEUE && admitted) {
+        const unsigned m = __activemask();
+        unsigned first = 0;
+        const unsigned lane = threadIdx.x & 31;
+        if (lane == (unsigned)(__ffs(m) - 1)) first = atomicAdd(p.qcount, (unsigned)__popc(m));
+        first = __shfl_sync(m, first, __ffs(m) - 1);
+        const unsigned slot = first + (unsigned)__popc(m & ((1u << lane) - 1u));
+        if (slot < p.qcap) {
+          HitRecord h;
+          h.xy = x | (y << 16); h.seed = seed; h.voxel = (unsigned)voxel; h.clause = colour_clause;
+          h.base = cur.o + cur.d;
+          h.normal = -normalize3(grad);
+          store_record(p.queue, slot, h);
+          c_adm++;
+          c_normals++;
+          admitted = false;
+        }
+      }
       if (admitted) {
         c_adm++;
         c_normals++;
@@ -214,7 +262,7 @@ __global__ void __launch_bounds__(128) k_trace(const RenderParams p) {
           cur.o = cur.o + normal * 2.0f;
           float atten = fabsf(dot3(cur.d, normal));
           for (int i = 8; i <= 10; ++i) {
-            ev = march_to_next_event<COUNT>(p, cur, grad, color, c_steps);
+            ev = march_to_next_event<COUNT>(p, cur, grad, color, colour_clause, c_steps);
             if (ev == EV_EXIT) {
               const float factor = 8.0f / (float)i;
               const uchar4 lm = env_sample(p, cur.d);
@@ -253,6 +301,181 @@ __global__ void __launch_bounds__(128) k_trace(const RenderParams p) {
       unsigned s = v[k];
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if ((threadIdx.x & 31) == 0 && s) atomicAdd(p.counters + k, (unsigned long long)s);
+    }
+  }
+}
+
+// ---- k_trace_pt: the secondary paths (ray_marching.cl:47-76) of the queued primary hits, on persistent warps ------------
+// k_trace gives every pixel a thread for its whole life; with the secondary paths inline a warp runs until its LAST lane
+// is done and ncu shows 12-17 of 32 lanes active per instruction (only the lanes whose primary ray hit do secondary work,
+// 1..3 segments of 1..70 steps each, twice).  In the hybrid schedule k_trace<QUEUE> stops at the admitted primary hit and
+// appends a HitRecord; here a lane is a SLOT: warps pull records from the queue, all lanes with a segment in flight step
+// together, and finished segments are processed in batches.  Event processing costs more than stepping (normalisations,
+// the RNG bounce, the env lookup), so (a) the warp leaves the step loop as soon as more lanes wait than march, and
+// (b) every lane that needs a bounce — new record, secondary hit, start of o = 2 — goes through ONE bounce site.
+// What is computed per sample, every fp32 operation and its order, is unchanged; only the schedule differs.
+enum { M_IDLE = 0, M_SECOND = 2 };
+enum { EVP_NONE = 0, EVP_HIT = 1, EVP_EXIT = 2, EVP_SDF_NEG = 3, EVP_FARFACE = 4 };
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128, 12) k_trace_pt(const RenderParams p, unsigned* __restrict__ work_counter) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int nx = p.vol.nx, ny = p.vol.ny, nz = p.vol.nz;
+  const unsigned total = min(__ldcv(p.qcount), p.qcap);
+
+  // slot state
+  int mode = M_IDLE;
+  bool marching = false;
+  int ev = EVP_NONE;
+  int x = 0, y = 0, seed = 0;
+  f3 o = {0, 0, 0}, dv = {0, 0, 0};  // current ray
+  int d = 0, steps_left = 0;
+  f3 base = {0, 0, 0}, normal = {0, 0, 0};
+  float atten = 0, er = 0, eg = 0, eb = 0;
+  unsigned bv0 = 0, bv1 = 0, bv2 = 0, voxel = 0;
+  int clause_col = 0;  // 1-based index of the clause that last wrote the colour (0: colour still {0,0,0,0})
+  int po = 0, pi = 0;  // the loop variables o (1..2) and i (8..10) of ray_marching.cl:47,52
+  bool exhausted = false;
+  unsigned c_steps = 0, c_normals = 0, c_env = 0;
+
+  auto colour = [&](int k) -> int { return clause_col ? p.tf.r[clause_col - 1].rgba[k] : 0; };
+
+  for (;;) {
+    bool need_bounce = false, reset_atten = false, need_start = false;
+    f3 bn = {0, 0, 0};
+    int bseed = 0;
+
+    // ---- events of the slots whose segment ended ---------------------------------------------------------------------------
+    if (mode != M_IDLE && !marching) {
+      f3 grad = {0.0f, 0.0f, 0.0f};
+      if (ev == EVP_SDF_NEG || ev == EVP_FARFACE) {
+        const int vx = ifloor(o.x), vy = ifloor(o.y), vz = ifloor(o.z);
+        grad = gradient_voxel(p.vol, vx, vy, vz);
+        const int value = ev == EVP_SDF_NEG ? p.vol.at(vx, vy, vz) : 0;
+        const int clause = tf_match(p.tf, value, f2s(length3(grad)));
+        if (ev == EVP_FARFACE && clause == 0) {
+          // no event on the far face: `continue` in march_to_next_event
+          ev = EVP_NONE;
+          if (steps_left > 0) marching = true;
+        } else {
+          if (clause > 0 && !(p.tf.r[clause - 1].flags & VR_TF_THRESHOLD)) clause_col = clause;
+          ev = EVP_HIT;
+        }
+      }
+      if (!marching) {  // body of the i-loop, ray_marching.cl:53-72
+        bool next_o = false;
+        if (ev == EVP_EXIT) {
+          const float factor = 8.0f / (float)pi;
+          const uchar4 lm = env_sample(p, dv);
+          if (COUNT) c_env++;
+          bv0 = f2u((float)bv0 + atten * er * (float)lm.x * factor / 1.0f);
+          bv1 = f2u((float)bv1 + atten * eg * (float)lm.y * factor / 1.0f);
+          bv2 = f2u((float)bv2 + atten * eb * (float)lm.z * factor / 1.0f);
+          next_o = true;  // break
+        } else {
+          const bool more = pi < 10;
+          if (ev == EVP_HIT) {
+            if (COUNT) c_normals++;
+            er *= (float)colour(0) / 255.0f; eg *= (float)colour(1) / 255.0f; eb *= (float)colour(2) / 255.0f;
+            if (more) {  // at i == 10 the new ray (ray_marching.cl:64-67) is never marched and atten is reset next
+              bn = -normalize3(grad);
+              o = o + dv;
+              bseed = seed + po + pi;
+              need_bounce = true;
+            }
+          }
+          ++pi;
+          if (more) need_start = true;
+          else next_o = true;
+        }
+        if (next_o) {
+          if (po == 1) {
+            po = 2; pi = 8;
+            o = base;
+            bn = normal; bseed = seed + po;
+            need_bounce = true; reset_atten = true; need_start = true;
+          } else {
+            bv0 /= 2u; bv1 /= 2u; bv2 /= 2u;
+            const uint32_t low = (bv0 & 0xFFFFu) + ((bv1 & 0xFFFFu) << 16);
+            const uint32_t high = (bv2 & 0xFFFFu);
+            if (low) atomicAdd(p.cache + 2 * (size_t)voxel, low);
+            if (high) atomicAdd(p.cache + 2 * (size_t)voxel + 1, high);
+            mode = M_IDLE;
+          }
+        }
+      }
+    }
+
+    // ---- refill free slots from the queue --------------------------------------------------------------------------------------
+    {
+      const unsigned idle = __ballot_sync(0xffffffffu, mode == M_IDLE);
+      if (idle && !exhausted) {
+        unsigned first = 0;
+        if (lane == 0) first = atomicAdd(work_counter, (unsigned)__popc(idle));
+        first = __shfl_sync(0xffffffffu, first, 0);
+        exhausted = first + (unsigned)__popc(idle) >= total;
+        const unsigned idx = first + (unsigned)__popc(idle & lt_mask);
+        if (mode == M_IDLE && idx < total) {  // ray_marching.cl:42-50 for o = 1
+          const HitRecord h = load_record(p.queue, idx);
+          x = h.xy & 0xFFFF; y = h.xy >> 16; seed = h.seed; voxel = h.voxel; clause_col = h.clause;
+          base = h.base; normal = h.normal;
+          er = (float)colour(0) / 255.0f; eg = (float)colour(1) / 255.0f; eb = (float)colour(2) / 255.0f;
+          bv0 = bv1 = bv2 = 0;
+          po = 1; pi = 8;
+          o = base;
+          bn = normal; bseed = seed + po;
+          need_bounce = true; reset_atten = true; need_start = true;
+          mode = M_SECOND;
+        }
+      }
+    }
+
+    // ---- the one bounce site: ray_bounce_fake_reflectance + `origin += normal*2` + attenuation ------------------------------------
+    if (need_bounce) {
+      dv = hemisphere_reflective(bn, bseed, (float)colour(3) / 255.0f, (unsigned)x, (unsigned)y);
+      o = o + bn * 2.0f;
+      const float a = fabsf(dot3(dv, bn));
+      atten = reset_atten ? a : atten * a;
+    }
+    if (need_start) {  // first half of march(), utility_ray.cl:148-150
+      d = p.sdf.at(f2i(o.x), f2i(o.y), f2i(o.z));
+      steps_left = 70;
+      marching = true;
+      ev = EVP_NONE;
+    }
+    if (!__ballot_sync(0xffffffffu, mode != M_IDLE)) break;  // queue empty and every slot free
+
+    // ---- step loop: march (second half) + get_event_and_value with the SDF-sign shortcut -------------------------------------------
+    for (;;) {
+      if (marching) {
+        const float step_size = max_cl((float)d, 0.5f);
+        o = o + step_size * dv;
+        if (COUNT) c_steps++;
+        steps_left--;
+        const int vx = ifloor(o.x), vy = ifloor(o.y), vz = ifloor(o.z);
+        const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
+        if (exited) { marching = false; ev = EVP_EXIT; }
+        else {
+          d = __ldg(p.sdf.f + p.sdf.addr(vx, vy, vz));
+          if (d <= 0) { marching = false; ev = d < 0 ? EVP_SDF_NEG : EVP_FARFACE; }
+          else if (steps_left == 0) { marching = false; ev = EVP_NONE; }
+        }
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, marching);
+      if (!act) break;
+      // majority rule: leave as soon as more lanes wait for event processing (or a refill) than are marching
+      const unsigned waiting = __ballot_sync(0xffffffffu, !marching && (mode != M_IDLE || !exhausted));
+      if (__popc(act) < __popc(waiting)) break;
+    }
+  }
+  if (COUNT) {
+    unsigned v[3] = {c_steps, c_normals, c_env};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      unsigned s = v[k];
+      for (int q = 16; q > 0; q >>= 1) s += __shfl_xor_sync(0xffffffffu, s, q);
+      if (lane == 0 && s) atomicAdd(p.counters + k, (unsigned long long)s);
     }
   }
 }
@@ -345,10 +568,38 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     for (int k = 0; k < nframes; ++k) p.seeds[k] = seeds[k];
     p.token_cap = r->token_cap;
     p.counters = r->counters;
+    p.queue = nullptr; p.qcount = nullptr; p.qcap = 0;
     p.tf = r->tf_active;
+    static int per_sm[2] = {0, 0};  // resident CTAs per SM of the two k_trace_pt instantiations
+    if (!per_sm[0]) {
+      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_trace_pt<false>, 128, 0));
+      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_trace_pt<true>, 128, 0));
+    }
+    const size_t pixels = (size_t)r->W * rows * nframes;
     dim3 grid(div_up(r->W, 8), div_up(rows, 16), nframes);
-    if (r->count) k_trace<true><<<grid, 128, 0, ctx->stream>>>(p);
-    else k_trace<false><<<grid, 128, 0, ctx->stream>>>(p);
+    if (r->trace_mode == 1) {
+      // hybrid: dense thread-per-pixel primary phase, persistent warps for the queued secondary paths
+      const size_t cap = std::min<size_t>(pixels, (size_t)32 << 20);
+      if (r->queue_cap < cap) {
+        if (r->queue) VR_CUDA(cudaFreeAsync(r->queue, ctx->stream));
+        r->queue = nullptr; r->queue_cap = 0;
+        VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&r->queue), cap * 3 * sizeof(uint4), ctx->stream));
+        r->queue_cap = cap;
+      }
+      p.queue = r->queue;
+      p.qcap = (unsigned)r->queue_cap;
+      p.qcount = reinterpret_cast<unsigned*>(r->counters + 6);
+      VR_CUDA(cudaMemsetAsync(p.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
+      if (r->count) k_trace<true, true><<<grid, 128, 0, ctx->stream>>>(p);
+      else k_trace<false, true><<<grid, 128, 0, ctx->stream>>>(p);
+      const unsigned blocks = (unsigned)ctx->sm_count * std::max(1, per_sm[r->count ? 1 : 0]);
+      if (r->count) k_trace_pt<true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+      else k_trace_pt<false><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+      ctx->launches++;
+    } else {
+      if (r->count) k_trace<true, false><<<grid, 128, 0, ctx->stream>>>(p);
+      else k_trace<false, false><<<grid, 128, 0, ctx->stream>>>(p);
+    }
     ctx->launches++;
   }
   if (e1) VR_CUDA(cudaEventRecord(e1, ctx->stream));

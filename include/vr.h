@@ -171,6 +171,11 @@ int vr_renderer_resolve(vr_renderer* r, uint8_t* host_rgba);
  * {march steps, shading normals, env fetches, primary hits, admitted samples, samples}. */
 int vr_renderer_enable_counters(vr_renderer* r, int enable);
 int vr_renderer_counters(const vr_renderer* r, uint64_t out[6], int reset);
+/* Scheduling of the trace phase — same per-sample computation and results in both modes:
+ *   1 (default) hybrid: the dense thread-per-pixel primary phase (k_trace) queues the admitted hits, persistent warps
+ *               (k_trace_pt) run their secondary paths in refilled lanes
+ *   0 one thread per pixel for its whole life (k_trace alone) */
+int vr_renderer_set_trace_mode(vr_renderer* r, int mode);
 /* When enabled, every trace / resolve launch is bracketed by CUDA events on the context's stream;
  * vr_renderer_kernel_times synchronises and returns the summed device time of the trace kernel (out_ms[0]) and of
  * the resolve kernel (out_ms[1]) and the number of frames measured since the last reset. */

@@ -113,6 +113,16 @@ def test_render_tf_image(vr_ctx):
 
 
 # ---- render ------------------------------------------------------------------------------------------------------
+TRACE_MODE = [1]  # 1: hybrid k_trace + k_trace_pt (default), 0: k_trace alone; tests using `both` run each
+
+
+@pytest.fixture(params=[1, 0], ids=["hybrid", "k_trace"])
+def both(request):
+    TRACE_MODE[0] = request.param
+    yield request.param
+    TRACE_MODE[0] = 1
+
+
 def _scene(vr_ctx, n, W, H, tf=None, token_cap=256):
     v = synth.synth_ct(n)
     envimg = synth.synth_env(256, 128)
@@ -123,6 +133,7 @@ def _scene(vr_ctx, n, W, H, tf=None, token_cap=256):
     r.image_set(vol, env)
     r.set_tf(tf)
     r.set_token_cap(token_cap)
+    r.set_trace_mode(TRACE_MODE[0])
     r.flush_changes()
     ref = o.Renderer(v, envimg, tf, W, H, token_cap=token_cap)
     return r, ref, (vol, env)
@@ -140,7 +151,7 @@ def test_render_sdf_built_by_flush_matches(vr_ctx):
 
 
 @pytest.mark.parametrize("n,W,H,frames", [(64, 160, 120, 6), (96, 200, 136, 3)])
-def test_render_cache_and_image_parity(vr_ctx, n, W, H, frames):
+def test_render_cache_and_image_parity(vr_ctx, both, n, W, H, frames):
     # Ray positions are bit-identical by construction (no FMA, IEEE div/sqrt); the only sources of difference are
     # atan2f/asinf ulps at environment-texel boundaries and powf in the tone map.
     # Stated tolerance: voxel cache >= 99.9% of entries identical and max |diff| <= 64 per 16-bit lane;
@@ -167,7 +178,7 @@ def test_render_cache_and_image_parity(vr_ctx, n, W, H, frames):
     r.close(); [k.close() for k in keep]
 
 
-def test_render_token_cap_saturates(vr_ctx):
+def test_render_token_cap_saturates(vr_ctx, both):
     r, ref, keep = _scene(vr_ctx, 32, 96, 72, token_cap=3)
     pos, d = synth.default_camera(32)
     for k in range(6):
@@ -177,7 +188,7 @@ def test_render_token_cap_saturates(vr_ctx):
     r.close(); [k.close() for k in keep]
 
 
-def test_render_camera_inside_and_axis_aligned(vr_ctx):
+def test_render_camera_inside_and_axis_aligned(vr_ctx, both):
     # camera inside the volume, looking along +x exactly: zero direction components exercise the inf/NaN paths of
     # cut() and positions that land exactly on integer coordinates
     r, ref, keep = _scene(vr_ctx, 48, 64, 64)
@@ -191,7 +202,7 @@ def test_render_camera_inside_and_axis_aligned(vr_ctx):
     r.close(); [k.close() for k in keep]
 
 
-def test_render_threshold_tf_and_multi_clause_tf(vr_ctx):
+def test_render_threshold_tf_and_multi_clause_tf(vr_ctx, both):
     tf2 = [{"min_v": 900.0, "max_v": 1200.0, "min_g": 0.0, "max_g": 0.0, "flags": 0, "rgba": (255, 64, 32, 128)},
            {"min_v": 500.0, "max_v": 1500.0, "min_g": 100.0, "max_g": 2000.0, "flags": 1, "rgba": (40, 200, 255, 255)}]
     for tf in (synth.threshold_tf(700), tf2):
@@ -208,7 +219,7 @@ def test_render_threshold_tf_and_multi_clause_tf(vr_ctx):
         r.close(); [k.close() for k in keep]
 
 
-def test_render_rows_window_and_resolve(vr_ctx):
+def test_render_rows_window_and_resolve(vr_ctx, both):
     # image-tile split hook: tracing rows [y0,y1) only touches those pixels
     r, ref, keep = _scene(vr_ctx, 48, 64, 48)
     pos, d = synth.default_camera(48)
@@ -232,7 +243,7 @@ def test_tf_code_entry_point_equals_table(vr_ctx):
     r.close(); [k.close() for k in keep]
 
 
-def test_render_frames_batch_equals_sequential_oracle(vr_ctx):
+def test_render_frames_batch_equals_sequential_oracle(vr_ctx, both):
     # vr_render_frames traces the whole batch in one launch (gridDim.z = frame) and resolves once; below the token cap
     # the samples commute (integer atomics), so cache and final frame must equal the oracle's frame-by-frame result.
     r, ref, keep = _scene(vr_ctx, 64, 128, 96)
@@ -250,7 +261,8 @@ def test_render_frames_batch_equals_sequential_oracle(vr_ctx):
     r.close(); [k.close() for k in keep]
 
 
-def test_render_far_face_positions(vr_ctx):
+@pytest.mark.parametrize("mode", [1, 0])
+def test_render_far_face_positions(vr_ctx, mode):
     # rays that land exactly on the far faces (coordinate == dim): axis-aligned steps of 0.5 from integer origins.
     # The SDF apron must behave like the reference's border read (0 -> step 0.5) and the TF must see value 0.
     n = 16
@@ -260,7 +272,7 @@ def test_render_far_face_positions(vr_ctx):
     tf = [{"min_v": -10.0, "max_v": 10.0, "min_g": 500.0, "max_g": 2000.0, "flags": 1, "rgba": (200, 100, 50, 255)},
           {"min_v": 500.0, "max_v": 1200.0, "min_g": 0.0, "max_g": 0.0, "flags": 0, "rgba": (255, 255, 255, 255)}]
     vol = api.Volume(vr_ctx, v); env = api.EnvMap(vr_ctx, envimg)
-    r = api.Renderer(vr_ctx, 32, 32); r.image_set(vol, env); r.set_tf(tf); r.flush_changes()
+    r = api.Renderer(vr_ctx, 32, 32); r.image_set(vol, env); r.set_tf(tf); r.set_trace_mode(mode); r.flush_changes()
     ref = o.Renderer(v, envimg, tf, 32, 32)
     assert np.array_equal(r.sdf_download(), ref.sdf)
     for pos, d in [((-4.0, 8.0, 8.0), (1.0, 0.0, 0.0)), ((8.0, 8.0, -4.0), (0.0, 0.0, 1.0)), ((20.0, 8.0, 8.0), (-1.0, 0.0, 0.0))]:
