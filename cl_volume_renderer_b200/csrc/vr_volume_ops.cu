@@ -49,13 +49,99 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_fetch_stats(VolView vol, int32_t
   }
 }
 
+// ---- vectorised stencil front end for fetch_stats / tf_sort_values (nx % 8 == 0) ------------------------------------------
+// A thread owns 8 consecutive voxels of a row: the centre row and its y+-1 / z+-1 rows are five 16-byte loads, the two x
+// neighbours beyond the octet two scalar loads — 7 load instructions per 8 voxels instead of 56.  Rows that fall outside
+// the volume read the border colour 0 (CLK_ADDRESS_CLAMP).
+struct Octet {
+  int c[8];                // centre values
+  int dx[8], dy[8], dz[8]; // central differences (not halved), utility_filter.cl:2-35
+};
+__device__ __forceinline__ void unpack8(const uint4 q, int v[8]) {
+  v[0] = (short)(q.x & 0xFFFF); v[1] = (short)(q.x >> 16); v[2] = (short)(q.y & 0xFFFF); v[3] = (short)(q.y >> 16);
+  v[4] = (short)(q.z & 0xFFFF); v[5] = (short)(q.z >> 16); v[6] = (short)(q.w & 0xFFFF); v[7] = (short)(q.w >> 16);
+}
+__device__ __forceinline__ Octet load_octet(const VolView& vol, int x0, int y, int z) {
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const size_t row = ((size_t)z * vol.ny + y) * vol.nx + x0;
+  const size_t sy = vol.nx, sz = (size_t)vol.nx * vol.ny;
+  const uint4* base = reinterpret_cast<const uint4*>(vol.v + row);
+  const uint4 qc = __ldg(base);
+  const uint4 qym = y > 0 ? __ldg(reinterpret_cast<const uint4*>(vol.v + row - sy)) : zero;
+  const uint4 qyp = y + 1 < vol.ny ? __ldg(reinterpret_cast<const uint4*>(vol.v + row + sy)) : zero;
+  const uint4 qzm = z > 0 ? __ldg(reinterpret_cast<const uint4*>(vol.v + row - sz)) : zero;
+  const uint4 qzp = z + 1 < vol.nz ? __ldg(reinterpret_cast<const uint4*>(vol.v + row + sz)) : zero;
+  const int xl = x0 > 0 ? (int)__ldg(vol.v + row - 1) : 0;
+  const int xr = x0 + 8 < vol.nx ? (int)__ldg(vol.v + row + 8) : 0;
+  Octet o;
+  int ym[8], yp[8], zm[8], zp[8];
+  unpack8(qc, o.c); unpack8(qym, ym); unpack8(qyp, yp); unpack8(qzm, zm); unpack8(qzp, zp);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int l = k == 0 ? xl : o.c[k - 1], r = k == 7 ? xr : o.c[k + 1];
+    o.dx[k] = r - l; o.dy[k] = yp[k] - ym[k]; o.dz[k] = zp[k] - zm[k];
+  }
+  return o;
+}
+// squared gradient length in the evaluation order of length(): (dx*dx + dy*dy) + dz*dz in fp32
+__device__ __forceinline__ float grad_sq(const Octet& o, int k) {
+  const float fx = (float)o.dx[k], fy = (float)o.dy[k], fz = (float)o.dz[k];
+  return (fx * fx + fy * fy) + fz * fz;
+}
+
+#define VX 16  // threads along x (128 voxels)
+#define VY 8
+#define VZ 2
+// fetch_stats, vectorised.  sqrt and float->int are monotonic, so min/max of (int)sqrt(s) = (int)sqrt(min/max s): the
+// square root is taken once per thread instead of once per voxel — bit-identical.
+__global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8(VolView vol, int32_t* __restrict__ stats) {
+  const int x0 = (blockIdx.x * VX + threadIdx.x) * 8;
+  const int y = blockIdx.y * VY + threadIdx.y;
+  const int z = blockIdx.z * VZ + threadIdx.z;
+  int mnv = INT32_MAX, mxv = INT32_MIN, mng = INT32_MAX, mxg = INT32_MIN;
+  if (x0 < vol.nx && y < vol.ny && z < vol.nz) {
+    const Octet o = load_octet(vol, x0, y, z);
+    float smin = grad_sq(o, 0), smax = smin;
+    mnv = mxv = o.c[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float s = grad_sq(o, k);
+      smin = fminf(smin, s); smax = fmaxf(smax, s);
+      mnv = min(mnv, o.c[k]); mxv = max(mxv, o.c[k]);
+    }
+    mng = f2i(sqrtf(smin)); mxg = f2i(sqrtf(smax));
+  }
+  for (int q = 16; q > 0; q >>= 1) {
+    mnv = min(mnv, __shfl_xor_sync(0xffffffffu, mnv, q));
+    mxv = max(mxv, __shfl_xor_sync(0xffffffffu, mxv, q));
+    mng = min(mng, __shfl_xor_sync(0xffffffffu, mng, q));
+    mxg = max(mxg, __shfl_xor_sync(0xffffffffu, mxg, q));
+  }
+  __shared__ int s4[4][VX * VY * VZ / 32];
+  const int tid = threadIdx.x + VX * (threadIdx.y + VY * threadIdx.z);
+  if ((tid & 31) == 0) { s4[0][tid >> 5] = mnv; s4[1][tid >> 5] = mxv; s4[2][tid >> 5] = mng; s4[3][tid >> 5] = mxg; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < VX * VY * VZ / 32; ++w) {
+      mnv = min(mnv, s4[0][w]); mxv = max(mxv, s4[1][w]); mng = min(mng, s4[2][w]); mxg = max(mxg, s4[3][w]);
+    }
+    atomicMin(stats + 0, mnv); atomicMax(stats + 1, mxv);
+    atomicMin(stats + 2, mng); atomicMax(stats + 3, mxg);
+  }
+}
+
 int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int32_t out[4]) {
   int32_t init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};  // reference_volume.cpp:22-28
   memcpy(ctx->scratch_host, init, sizeof(init));
   VR_CUDA(cudaMemcpyAsync(ctx->scratch, ctx->scratch_host, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   VolView v{vol, nx, ny, nz};
-  dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
-  k_fetch_stats<<<grid, block, 0, ctx->stream>>>(v, ctx->scratch);
+  if (nx % 8 == 0) {
+    dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
+    k_fetch_stats_v8<<<grid, block, 0, ctx->stream>>>(v, ctx->scratch);
+  } else {
+    dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
+    k_fetch_stats<<<grid, block, 0, ctx->stream>>>(v, ctx->scratch);
+  }
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
   VR_CUDA(cudaMemcpyAsync(ctx->scratch_host, ctx->scratch, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
@@ -167,12 +253,48 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_histogram(VolView vol, uint32_t*
   }
 }
 
+// tf_sort_values, vectorised front end (nx % 8 == 0): same binning arithmetic per voxel, 8 voxels per thread
+__global__ void __launch_bounds__(VX* VY* VZ) k_histogram_v8(VolView vol, uint32_t* __restrict__ bins, int width, int height,
+                                                             float min_v, float max_v, float min_g, float max_g) {
+  const int x0 = (blockIdx.x * VX + threadIdx.x) * 8;
+  const int y = blockIdx.y * VY + threadIdx.y;
+  const int z = blockIdx.z * VZ + threadIdx.z;
+  const bool in = x0 < vol.nx && y < vol.ny && z < vol.nz;
+  Octet o;
+  if (in) o = load_octet(vol, x0, y, z);
+  const float value_range = max_v - min_v, gradient_range = max_g - min_g;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    long long flat = -1;
+    if (in) {
+      const float g = sqrtf(grad_sq(o, k));
+      if (!(g > max_g) && !((float)o.c[k] > max_v)) {
+        const int px = f2i(roundf((((float)o.c[k] - min_v) / value_range) * (float)width));
+        const int py = f2i(roundf(((g - min_g) / gradient_range) * (float)height));
+        flat = (long long)px * height + py;
+        if (flat < 0 || flat >= (long long)width * height) flat = -1;
+      }
+    }
+    const unsigned active = __ballot_sync(0xffffffffu, flat >= 0);
+    if (flat >= 0) {
+      const unsigned peers = __match_any_sync(active, (int)flat);
+      if ((int)((threadIdx.x + VX * (threadIdx.y + VY * threadIdx.z)) & 31) == __ffs(peers) - 1)
+        atomicAdd(bins + flat, (uint32_t)__popc(peers));
+    }
+  }
+}
+
 int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4],
                   uint32_t* bins_dev) {
   VR_CUDA(cudaMemsetAsync(bins_dev, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
   VolView v{vol, nx, ny, nz};
-  dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
-  k_histogram<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3]);
+  if (nx % 8 == 0) {
+    dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
+    k_histogram_v8<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3]);
+  } else {
+    dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
+    k_histogram<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3]);
+  }
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
   return VR_OK;

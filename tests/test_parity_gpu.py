@@ -62,8 +62,9 @@ def test_fetch_stats_bit_exact(vr_ctx):
         vol.close()
 
 
-def test_histogram_bit_exact(vr_ctx):
-    v = _ragged()
+@pytest.mark.parametrize("which", ["ragged", "x8"])  # nx % 8 == 0 takes the vectorised kernels
+def test_histogram_bit_exact(vr_ctx, which):
+    v = _ragged() if which == "ragged" else synth.synth_ct(0, dims=(72, 37, 29))
     st = o.fetch_stats(v)
     vol = api.Volume(vr_ctx, v)
     for (w, h, rng) in [(50, 40, st), (500, 500, st), (64, 64, [-2000, 3000, 0, 4000]), (17, 9, [0, 100, 5, 50])]:
