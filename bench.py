@@ -387,8 +387,9 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         hbm, peak_src = peaks()
         b_trace = alg_bytes_per_sample(counters, trace_only=True)
-        trace_launch_ms = trace_ms / max(nframes, 1)
-        achieved = b_trace * W * H / (trace_launch_ms * 1e-3) / 1e9
+        n_launches = max(nframes // SPP, 1)             # one trace launch (k_trace + k_trace_pt) covers the 64 frames of a step
+        trace_launch_ms = trace_ms / n_launches
+        achieved = b_trace * W * H * SPP / (trace_launch_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic_k_trace.json")
         if os.path.exists(tp):
@@ -410,10 +411,15 @@ def run_ours(args, rank, world, local_rank):
                                     "what": "same, but 64 x vr_render_frame with every frame read back (the reference UI's "
                                             "usage, renderer.cpp:131-158)"}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "trace phase = k_trace (primary rays, queues admitted hits) + k_trace_pt "
+                                                   "(secondary paths), one launch pair per 64-frame step",
+                         "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
-                         "alg_bytes_per_sample": b_trace, "samples_per_launch": W * H,
-                         "launch_ms": trace_launch_ms, "resolve_launch_ms": resolve_ms / max(nframes, 1),
+                         "alg_bytes_per_sample": b_trace, "samples_per_launch": W * H * SPP,
+                         "launch_ms": trace_launch_ms, "resolve_launch_ms": resolve_ms / n_launches,
+                         "note": "scattered 1-byte gathers: issue-bound (ncu: 88 % / 74 % issue-active), not HBM-bound; traffic "
+                                 "(measured DRAM bytes) is below the algorithmic bytes because one SDF byte per step replaces "
+                                 "the reference's 15 bytes (DESIGN.md 4.1)",
                          "trace_share_of_step": trace_ms / ms if ms > 0 else None,
                          "per_sample": {"steps": counters["steps"] / S, "normals": counters["normals"] / S,
                                         "env": counters["env"] / S, "primary_hits": counters["primary_hits"] / S,

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_fetch_stats(VolView vol, int32_t
 // A thread owns 8 consecutive voxels of a row: the centre row and its y+-1 / z+-1 rows are five 16-byte loads, the two x
 // neighbours beyond the octet two scalar loads — 7 load instructions per 8 voxels instead of 56.  Rows that fall outside
 // the volume read the border colour 0 (CLK_ADDRESS_CLAMP).
+__device__ __forceinline__ unsigned div_up_dev(int a, int b) { return (unsigned)((a + b - 1) / b); }
 struct Octet {
   int c[8];                // centre values
   int dx[8], dy[8], dz[8]; // central differences (not halved), utility_filter.cl:2-35
@@ -253,35 +254,61 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_histogram(VolView vol, uint32_t*
   }
 }
 
-// tf_sort_values, vectorised front end (nx % 8 == 0): same binning arithmetic per voxel, 8 voxels per thread
+// tf_sort_values, vectorised front end (nx % 8 == 0): same binning arithmetic per voxel, 8 voxels per thread.
+// CT-like volumes put most voxels into a handful of bins (air, soft tissue), and same-address atomics serialise in L2
+// (the first version spent 3.2 ms at 512^3 on them).  Counts are therefore aggregated three times before they reach
+// global memory: lanes of a warp that hit the same bin merge (__match_any_sync), persistent CTAs accumulate in a
+// shared-memory hash table (HKEYS slots, linear probing, overflow goes straight to global), and each CTA flushes its
+// table once at the end.
+#define HKEYS 4096
 __global__ void __launch_bounds__(VX* VY* VZ) k_histogram_v8(VolView vol, uint32_t* __restrict__ bins, int width, int height,
                                                              float min_v, float max_v, float min_g, float max_g) {
-  const int x0 = (blockIdx.x * VX + threadIdx.x) * 8;
-  const int y = blockIdx.y * VY + threadIdx.y;
-  const int z = blockIdx.z * VZ + threadIdx.z;
-  const bool in = x0 < vol.nx && y < vol.ny && z < vol.nz;
-  Octet o;
-  if (in) o = load_octet(vol, x0, y, z);
+  __shared__ int hkey[HKEYS];
+  __shared__ unsigned hcnt[HKEYS];
+  const int tid = threadIdx.x + VX * (threadIdx.y + VY * threadIdx.z);
+  for (int i = tid; i < HKEYS; i += VX * VY * VZ) { hkey[i] = -1; hcnt[i] = 0; }
+  __syncthreads();
+  const unsigned tx = div_up_dev(vol.nx, VX * 8), ty = div_up_dev(vol.ny, VY), tz = div_up_dev(vol.nz, VZ);
   const float value_range = max_v - min_v, gradient_range = max_g - min_g;
+  for (unsigned t = blockIdx.x; t < tx * ty * tz; t += gridDim.x) {
+    const int x0 = (int)(((t % tx) * VX + threadIdx.x) * 8);
+    const int y = (int)(((t / tx) % ty) * VY + threadIdx.y);
+    const int z = (int)((t / (tx * ty)) * VZ + threadIdx.z);
+    const bool in = x0 < vol.nx && y < vol.ny && z < vol.nz;
+    Octet o;
+    if (in) o = load_octet(vol, x0, y, z);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    long long flat = -1;
-    if (in) {
-      const float g = sqrtf(grad_sq(o, k));
-      if (!(g > max_g) && !((float)o.c[k] > max_v)) {
-        const int px = f2i(roundf((((float)o.c[k] - min_v) / value_range) * (float)width));
-        const int py = f2i(roundf(((g - min_g) / gradient_range) * (float)height));
-        flat = (long long)px * height + py;
-        if (flat < 0 || flat >= (long long)width * height) flat = -1;
+    for (int k = 0; k < 8; ++k) {
+      long long flat = -1;
+      if (in) {
+        const float g = sqrtf(grad_sq(o, k));
+        if (!(g > max_g) && !((float)o.c[k] > max_v)) {
+          const int px = f2i(roundf((((float)o.c[k] - min_v) / value_range) * (float)width));
+          const int py = f2i(roundf(((g - min_g) / gradient_range) * (float)height));
+          flat = (long long)px * height + py;
+          if (flat < 0 || flat >= (long long)width * height) flat = -1;
+        }
+      }
+      const unsigned active = __ballot_sync(0xffffffffu, flat >= 0);
+      if (flat >= 0) {
+        const unsigned peers = __match_any_sync(active, (int)flat);
+        if ((tid & 31) == __ffs(peers) - 1) {
+          const int key = (int)flat;
+          const unsigned c = (unsigned)__popc(peers);
+          unsigned slot = ((unsigned)key * 2654435761u) >> 20;  // 12 bits
+          bool done = false;
+          for (int probe = 0; probe < 8 && !done; ++probe, slot = (slot + 1) & (HKEYS - 1)) {
+            const int old = atomicCAS(&hkey[slot], -1, key);
+            if (old == -1 || old == key) { atomicAdd(&hcnt[slot], c); done = true; }
+          }
+          if (!done) atomicAdd(bins + key, c);
+        }
       }
     }
-    const unsigned active = __ballot_sync(0xffffffffu, flat >= 0);
-    if (flat >= 0) {
-      const unsigned peers = __match_any_sync(active, (int)flat);
-      if ((int)((threadIdx.x + VX * (threadIdx.y + VY * threadIdx.z)) & 31) == __ffs(peers) - 1)
-        atomicAdd(bins + flat, (uint32_t)__popc(peers));
-    }
   }
+  __syncthreads();
+  for (int i = tid; i < HKEYS; i += VX * VY * VZ)
+    if (hkey[i] >= 0 && hcnt[i]) atomicAdd(bins + hkey[i], hcnt[i]);
 }
 
 int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4],
@@ -289,7 +316,8 @@ int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int w
   VR_CUDA(cudaMemsetAsync(bins_dev, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
   VolView v{vol, nx, ny, nz};
   if (nx % 8 == 0) {
-    dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
+    const size_t tiles = (size_t)div_up(nx, VX * 8) * div_up(ny, VY) * div_up(nz, VZ);
+    dim3 grid((unsigned)std::min<size_t>(tiles, (size_t)ctx->sm_count * 6)), block(VX, VY, VZ);
     k_histogram_v8<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3]);
   } else {
     dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
