@@ -61,3 +61,13 @@ finally:
         for p in gen:
             os.remove(p)
 print("built", os.path.join(out, "libref.so"))
+
+# The reference's own loaders (NRRD, env map through the vendored stb_image) compile as they are: a small main() around
+# them gives tests/test_io_cpu.py the reference's behaviour for the ingest row.
+app = os.path.join(ref, "app")
+cmd = [cxx, "-std=c++17", "-O2", "-w", "-I", app, "-I", os.path.join(ref, "subprojects", "stb"),
+       os.path.join(here, "ref_loaders.cpp")] + [os.path.join(app, f) for f in
+                                                 ("nrrd_loader.cpp", "volume_block.cpp", "hdre_loader.cpp", "image.cpp")] + \
+      ["-lz", "-o", os.path.join(out, "ref_loaders")]
+subprocess.check_call(cmd)
+print("built", os.path.join(out, "ref_loaders"))

@@ -47,3 +47,36 @@ def test_frame_emitter_flow_matches_oracle(tmp_path):
     got_sdf = np.fromfile(tmp_path / "sdf.bin", dtype=np.int8).reshape(n, n, n)
     assert np.array_equal(got_sdf, o.sdf_build(v, o.tf_threshold(800))[0])
     assert f"stats {rng[0]:g} {rng[1]:g} {rng[2]:g} {rng[3]:g}" in out.stdout
+
+
+def test_headless_cli_matches_oracle(tmp_path):
+    """vr_headless = app/main.cpp + ui::run without the window (SURVEY 8f, f1): NRRD (gzip) + Radiance .hdr from disk, the
+    UI's start-up sequence, `--spp` frames with the std::rand() seeds, frame written upright as PPM and raw RGBA."""
+    from test_io_cpu import hdr_to_ldr, write_hdr, write_nrrd, _rgbe
+    cli = os.path.join(ROOT, "cl_volume_renderer_b200", "host", "vr_headless")
+    assert os.path.exists(cli), "build first: make host"
+    n, W, H, spp = 64, 160, 120, 3
+    v = synth.synth_ct(n)
+    write_nrrd(tmp_path / "vol.nrrd", v, "gzip")
+    rgbe = _rgbe(synth.synth_env(128, 64)[..., :3].astype(np.float64) / 255.0 * 1.5)
+    write_hdr(tmp_path / "env.hdr", rgbe, rle=True)
+    env = hdr_to_ldr(rgbe)
+    out = subprocess.run([cli, str(tmp_path / "vol.nrrd"), str(tmp_path / "env.hdr"), "--w", str(W), "--h", str(H), "--spp", str(spp),
+                          "--out", str(tmp_path / "f.ppm"), "--raw", str(tmp_path / "f.rgba"), "--tf-image", str(tmp_path / "tf.ppm")],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr + out.stdout
+    ref = o.Renderer(v, env, synth.default_tf(), W, H)
+    pos, d = synth.default_camera(n)
+    for s in synth.glibc_rand(spp):
+        want = ref.render_frame(pos, d, s)
+    got = np.fromfile(tmp_path / "f.rgba", dtype=np.uint8).reshape(H, W, 4)
+    assert np.array_equal(got[..., 3], want[..., 3])
+    mse = np.mean((got[..., :3].astype(np.float64) - want[..., :3].astype(np.float64)) ** 2)
+    assert mse == 0 or 10 * np.log10(255.0 ** 2 / mse) >= 45.0
+    ppm = open(tmp_path / "f.ppm", "rb").read()
+    head = f"P6\n{W} {H}\n255\n".encode()
+    assert ppm.startswith(head)
+    img = np.frombuffer(ppm[len(head):], dtype=np.uint8).reshape(H, W, 3)
+    assert np.array_equal(img, got[::-1, :, :3])  # the frame's row 0 is the bottom of the view
+    tf = open(tmp_path / "tf.ppm", "rb").read()
+    assert tf.startswith(b"P6\n500 500\n255\n") and len(tf) == 15 + 500 * 500 * 3
