@@ -258,6 +258,25 @@ def run_ours(args, rank, world, local_rank):
     samples_per_step = W * H * SPP * world
     value = samples_per_step * args.steps / ms_max / 1e3  # Msamples/s
 
+    # ---- A/B: the per-frame schedule (mode 1: every frame re-marches its primary rays, as 64 launches of the reference would) ----
+    per_frame = None
+    if world == 1:
+        r.set_trace_mode(1)
+        for _ in range(2):
+            step()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(ext)
+        for _ in range(3):
+            step()
+        p1.record(ext)
+        p1.synchronize()
+        pms = p0.elapsed_time(p1) / 3
+        r.set_trace_mode(2)
+        per_frame = {"value": W * H * SPP / pms / 1e3, "unit": "Msamples/s", "ms_per_step": pms,
+                     "what": "same step with vr_renderer_set_trace_mode(1): k_trace re-marches the primary ray of every pixel in "
+                             "each of the 64 frames (no reuse of the seed-independent part)"}
+
     # ---- saturated-cache rate: once a voxel holds 256 tokens its samples stop at the token check ----
     saturated = None
     if world == 1:
@@ -318,6 +337,7 @@ def run_ours(args, rank, world, local_rank):
         r2.flush_changes()                             # cache alloc + reset + SDF build
         hf = r2.host_frame()
         if interactive:
+            r2.set_primary_reuse(2)                    # camera unchanged between the calls: primary records are kept
             for k in range(SPP):
                 r2.render_frame(pos, d, seeds[k], out=hf)  # D2H W*H*4 per frame
         elif world == 1:
@@ -430,23 +450,27 @@ def run_ours(args, rank, world, local_rank):
                             "alloc/reset + SDF build), vr_render_frames(64 seeds), final frame read back to the host",
                     "interactive": {"value": e2e_interactive, "unit": "Msamples/s", "d2h_bytes_per_step": int(W * H * 4 * SPP),
                                     "what": "same, but 64 x vr_render_frame with every frame read back (the reference UI's "
-                                            "usage, renderer.cpp:131-158)"}},
+                                            "usage, renderer.cpp:131-158), vr_renderer_set_primary_reuse(2)"}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "trace phase = k_trace (primary rays, queues admitted hits) + k_trace_pt "
-                                                   "(secondary paths), one launch pair per 64-frame step",
+            "roofline": {"bound": "hbm", "kernel": "trace phase = k_primary (seed-independent part of the 64 samples of a pixel: ray, "
+                                                   "box cut, primary march, env colour / hit voxel + normal; once per pixel and "
+                                                   "step) + k_trace_pt (token admission + secondary paths per pixel and frame), "
+                                                   "one launch pair per 64-frame step",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
                          "alg_bytes_per_sample": b_trace, "samples_per_launch": W * H * SPP,
                          "launch_ms": trace_launch_ms, "resolve_launch_ms": resolve_ms / n_launches,
-                         "note": "scattered 1-byte gathers: issue-bound (ncu: 88 % / 74 % issue-active), not HBM-bound; traffic "
-                                 "(measured DRAM bytes) is below the algorithmic bytes because one SDF byte per step replaces "
-                                 "the reference's 15 bytes (DESIGN.md 4.1)",
+                         "note": "achieved = the reference algorithm's bytes (SURVEY 8d: 15 B per march step, ...) for the 64 samples "
+                                 "per pixel over the measured trace time; the kernels move fewer bytes: one SDF byte per step "
+                                 "instead of 15 and the primary segment once per pixel instead of 64 times (DESIGN.md 4.1). "
+                                 "Scattered 1-byte gathers: issue-bound, not HBM-bound (profiles/)",
                          "trace_share_of_step": trace_ms / ms if ms > 0 else None,
                          "per_sample": {"steps": counters["steps"] / S, "normals": counters["normals"] / S,
                                         "env": counters["env"] / S, "primary_hits": counters["primary_hits"] / S,
                                         "admitted": counters["admitted"] / S}},
             "cpu_baseline": cpu,
             "closeup": closeup,
+            "per_frame_schedule": per_frame,
             "saturated_cache": saturated,
             "sdf_build_ms": {"value": float(np.median(sdf_ms)), "levels": levels, "volume": f"{VOL_N}^3",
                              "note": "vr_sdf_build wall time incl. allocation, excl. upload (app/sdf_benchmark.cpp:15-20)"},

@@ -83,6 +83,7 @@ SYMBOLS = {
     "vr_renderer_enable_counters": (C.c_int, [_P, C.c_int]),
     "vr_renderer_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int]),
     "vr_renderer_set_trace_mode": (C.c_int, [_P, C.c_int]),
+    "vr_renderer_set_primary_reuse": (C.c_int, [_P, C.c_int]),
     "vr_renderer_enable_timing": (C.c_int, [_P, C.c_int]),
     "vr_renderer_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }
@@ -391,3 +392,6 @@ class Renderer:
 
     def set_trace_mode(self, mode):
         _check(lib().vr_renderer_set_trace_mode(self.h, mode))
+
+    def set_primary_reuse(self, level):
+        _check(lib().vr_renderer_set_primary_reuse(self.h, level))

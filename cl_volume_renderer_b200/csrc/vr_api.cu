@@ -276,7 +276,7 @@ extern "C" int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_rendere
   VR_CUDA(pool_alloc(ctx, &r->frame, px * 4));
   VR_CUDA(pool_alloc(ctx, &r->hit, px * 4));
   VR_CUDA(pool_alloc(ctx, &r->counters, 8 * sizeof(unsigned long long)));
-  if (const char* m = getenv("VR_TRACE_MODE")) r->trace_mode = atoi(m) ? 1 : 0;
+  if (const char* m = getenv("VR_TRACE_MODE")) r->trace_mode = std::min(std::max(atoi(m), 0), 2);
   VR_CUDA(pinned_acquire(ctx, reinterpret_cast<void**>(&r->frame_host), px * 4));
   VR_CUDA(cudaMemsetAsync(r->frame, 0, px * 4, ctx->stream));
   VR_CUDA(cudaMemsetAsync(r->hit, 0xFF, px * 4, ctx->stream));
@@ -308,6 +308,7 @@ extern "C" int vr_renderer_set_scene(vr_renderer* r, const vr_volume* vol, const
   VR_REQUIRE(vol->ctx == r->ctx && env->ctx == r->ctx, "vr_renderer_set_scene: objects belong to another context");
   r->vol = vol;
   r->env = env;
+  r->primary_valid = false;
   return VR_OK;
 }
 
@@ -347,6 +348,7 @@ extern "C" int vr_renderer_flush(vr_renderer* r) {
     VR_CUDA(pool_alloc(r->ctx, &r->cache, voxels * 8));
     r->cache_voxels = voxels;
   }
+  r->primary_valid = false;
   VR_TRY(vrk_cache_reset(r->ctx, r->cache, r->cache_voxels));  // renderer.cpp:32-35
   r->tf_active = r->tf_pending;                                  // renderer.cpp:39
   vr_sdf* fresh = nullptr;                                       // renderer.cpp:42
@@ -383,7 +385,7 @@ extern "C" int vr_render_frames(vr_renderer* r, const float pos[3], const float 
   // mid-batch is scheduling dependent — the same class of nondeterminism the reference has inside a single frame.
   for (int k = 0; k < n_frames; k += VR_MAX_BATCH) {
     const int nb = std::min(VR_MAX_BATCH, n_frames - k);
-    VR_TRY(vrk_render(r, pos, dir, seeds + k, nb, true, k + nb == n_frames));
+    VR_TRY(vrk_render(r, pos, dir, seeds + k, nb, true, k + nb == n_frames, k == 0));
   }
   return read_frame(r, host_rgba);
 }
@@ -416,8 +418,16 @@ extern "C" int vr_renderer_set_token_cap(vr_renderer* r, int cap) {
 }
 
 extern "C" int vr_renderer_set_trace_mode(vr_renderer* r, int mode) {
-  VR_REQUIRE(r && (mode == 0 || mode == 1), "vr_renderer_set_trace_mode: mode must be 0 or 1");
+  VR_REQUIRE(r && mode >= 0 && mode <= 2, "vr_renderer_set_trace_mode: mode must be 0, 1 or 2");
   r->trace_mode = mode;
+  r->primary_valid = false;
+  return VR_OK;
+}
+
+extern "C" int vr_renderer_set_primary_reuse(vr_renderer* r, int level) {
+  VR_REQUIRE(r && (level == 1 || level == 2), "vr_renderer_set_primary_reuse: level must be 1 or 2");
+  r->primary_across_calls = level == 2;
+  r->primary_valid = false;
   return VR_OK;
 }
 

@@ -96,7 +96,13 @@ struct vr_renderer {
   int token_cap = 256;
   bool count = false;
   unsigned long long* counters = nullptr;  // 6 x u64 on device (+ 2 spare words: [6] is k_trace_pt's work counter)
-  int trace_mode = 1;  // 0: k_trace alone (a thread per pixel for its whole life), 1: hybrid k_trace + k_trace_pt (default)
+  // 0: k_trace alone (a thread per pixel for its whole life), 1: hybrid k_trace + k_trace_pt per frame,
+  // 2 (default): k_primary once per pixel and call + k_trace_pt per (pixel, frame)
+  int trace_mode = 2;
+  bool primary_valid = false;         // r->queue holds the primary records of (primary_pos, primary_dir, primary_rows)
+  bool primary_across_calls = false;  // vr_renderer_set_primary_reuse(r, 2)
+  float primary_pos[3] = {0, 0, 0}, primary_dir[3] = {0, 0, 0};
+  int primary_rows[2] = {0, 0};
   uint4* queue = nullptr;  // hybrid schedule: admitted primary hits (3 x uint4 each)
   size_t queue_cap = 0;
   uint2* xchg = nullptr;  // W*H compact cache entries for the spp-split exchange (allocated on first use)
@@ -123,7 +129,7 @@ int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels);
 #define VR_MAX_BATCH 64
 // trace `nframes` frames (seeds[0..nframes)) in ONE launch (gridDim.z = frame), then optionally resolve once
 int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int32_t* seeds, int nframes, bool trace,
-               bool resolve);
+               bool resolve, bool first_of_call = true);
 
 int vrk_xchg(vr_renderer* r, uint2* xchg, bool scatter);
 TfTable vr_make_tf_table(const vr_tf_rect* rects, int n);

@@ -16,6 +16,8 @@
 //   the very voxel the next `march` reads its step length from.  So one int8 gather per step carries both the
 //   event test and the next step size; the 7 volume texels are fetched only at the <=7 hits per sample, where
 //   the gradient is needed for the shading normal anyway.  Same positions, same events, 1/15 of the bytes.
+#include <cstring>
+
 #include "vr_device.cuh"
 
 struct RenderParams {
@@ -33,7 +35,9 @@ struct RenderParams {
   int nframes;          // frames in this launch: blockIdx.z selects the seed
   int seeds[VR_MAX_BATCH];
   unsigned long long* counters;
-  // hybrid schedule: k_trace<QUEUE> appends admitted primary hits here, k_trace_pt<FROM_QUEUE> runs their secondary paths
+  // hybrid schedule: k_trace<QUEUE> appends admitted primary hits here, k_trace_pt runs their secondary paths.
+  // primary-reuse schedule: k_primary appends ONE record per shaded pixel, k_trace_pt<.., true> runs token admission and the
+  // secondary paths for every (record, frame) pair.
   uint4* queue;       // 3 x uint4 per record (HitRecord)
   unsigned* qcount;   // [0] records appended, [1] records consumed
   unsigned qcap;
@@ -305,6 +309,70 @@ __global__ void __launch_bounds__(128, 12) k_trace(const RenderParams p) {
   }
 }
 
+// ---- k_primary: the seed-independent part of a sample, once per pixel and call ------------------------------------------------
+// Everything ray_marching.cl does before the first use of random_seed — generate_ray, cut, the primary march_to_next_event
+// (:162-170, :21-33), the environment colour of a pixel whose ray leaves the volume (:172-178,188-194), the hit voxel and
+// the shading normal (:42) — depends on the camera only.  A progressive batch (vr_render_frames: n seeds, one camera)
+// therefore evaluates it ONCE per pixel; the n samples of the pixel differ from the token admission (:39) onwards, which
+// k_trace_pt<.., true> runs per (pixel, frame).  Same values as n executions of the reference kernel, 1/n of the work.
+template <bool COUNT>
+__global__ void __launch_bounds__(128, 12) k_primary(const RenderParams p) {
+  const int x = blockIdx.x * 8 + (threadIdx.x & 7);
+  const int y = p.row0 + blockIdx.y * 16 + (threadIdx.x >> 3);
+  unsigned c_steps = 0, c_env = 0, c_hits = 0, c_samples = 0;
+  if (x < p.W && y < p.row1) {
+    c_samples = 1;
+    const size_t pix = (size_t)y * p.W + x;
+    Ray vray = generate_ray(p.cam_pos, p.cam_dir, p.cam_side, p.cam_up, x, y, p.W, p.H);
+    bool is_cut;
+    f3 cut_point;
+    if (!(lim(vray.o.x, p.vol.nx) && lim(vray.o.y, p.vol.ny) && lim(vray.o.z, p.vol.nz)))
+      is_cut = cut_box(p.vol, vray, &cut_point);
+    else { is_cut = true; cut_point = vray.o; }
+    int ev = EV_NONE;
+    Ray cur = {cut_point, vray.d};
+    f3 grad = {0.0f, 0.0f, 0.0f};
+    int color[4] = {0, 0, 0, 0};
+    int colour_clause = 0;
+    if (is_cut) ev = march_to_next_event<COUNT>(p, cur, grad, color, colour_clause, c_steps);
+    if (ev != EV_HIT) {
+      uchar4 e = env_sample(p, vray.d);
+      e.w = 200;
+      p.frame[pix] = e;
+      p.hit[pix] = VR_MISS;
+      c_env++;
+    } else {
+      const int vx = min(max(f2i(cur.o.x), 0), p.vol.nx - 1);
+      const int vy = min(max(f2i(cur.o.y), 0), p.vol.ny - 1);
+      const int vz = min(max(f2i(cur.o.z), 0), p.vol.nz - 1);
+      const size_t voxel = (size_t)p.vol.nx * p.vol.nz * vy + (size_t)p.vol.nx * vz + vx;
+      p.hit[pix] = (uint32_t)voxel;
+      c_hits++;
+      const unsigned m = __activemask();
+      unsigned first = 0;
+      const unsigned lane = threadIdx.x & 31;
+      if (lane == (unsigned)(__ffs(m) - 1)) first = atomicAdd(p.qcount, (unsigned)__popc(m));
+      first = __shfl_sync(m, first, __ffs(m) - 1);
+      const unsigned slot = first + (unsigned)__popc(m & ((1u << lane) - 1u));  // < W*rows <= qcap
+      HitRecord h;
+      h.xy = x | (y << 16); h.seed = 0; h.voxel = (unsigned)voxel; h.clause = colour_clause;
+      h.base = cur.o + cur.d;
+      h.normal = -normalize3(grad);
+      store_record(p.queue, slot, h);
+    }
+  }
+  if (COUNT) {  // per-sample counters: the n samples of the pixel each own this primary segment
+    const unsigned n = (unsigned)p.nframes;
+    unsigned v[6] = {c_steps * n, 0u, c_env * n, c_hits * n, 0u, c_samples * n};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      unsigned s = v[k];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if ((threadIdx.x & 31) == 0 && s) atomicAdd(p.counters + k, (unsigned long long)s);
+    }
+  }
+}
+
 // ---- k_trace_pt: the secondary paths (ray_marching.cl:47-76) of the queued primary hits, on persistent warps ------------
 // k_trace gives every pixel a thread for its whole life; with the secondary paths inline a warp runs until its LAST lane
 // is done and ncu shows 12-17 of 32 lanes active per instruction (only the lanes whose primary ray hit do secondary work,
@@ -317,12 +385,14 @@ __global__ void __launch_bounds__(128, 12) k_trace(const RenderParams p) {
 enum { M_IDLE = 0, M_SECOND = 2 };
 enum { EVP_NONE = 0, EVP_HIT = 1, EVP_EXIT = 2, EVP_SDF_NEG = 3, EVP_FARFACE = 4 };
 
-template <bool COUNT>
+template <bool COUNT, bool REUSE>
 __global__ void __launch_bounds__(128, 12) k_trace_pt(const RenderParams p, unsigned* __restrict__ work_counter) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int nx = p.vol.nx, ny = p.vol.ny, nz = p.vol.nz;
-  const unsigned total = min(__ldcv(p.qcount), p.qcap);
+  // REUSE: the queue holds one record per shaded pixel (k_primary); work item = frame * records + record
+  const unsigned records = min(__ldcv(p.qcount), p.qcap);
+  const unsigned total = REUSE ? records * (unsigned)p.nframes : records;
 
   // slot state
   int mode = M_IDLE;
@@ -337,7 +407,7 @@ __global__ void __launch_bounds__(128, 12) k_trace_pt(const RenderParams p, unsi
   int clause_col = 0;  // 1-based index of the clause that last wrote the colour (0: colour still {0,0,0,0})
   int po = 0, pi = 0;  // the loop variables o (1..2) and i (8..10) of ray_marching.cl:47,52
   bool exhausted = false;
-  unsigned c_steps = 0, c_normals = 0, c_env = 0;
+  unsigned c_steps = 0, c_normals = 0, c_env = 0, c_adm = 0;
 
   auto colour = [&](int k) -> int { return clause_col ? p.tf.r[clause_col - 1].rgba[k] : 0; };
 
@@ -408,16 +478,37 @@ __global__ void __launch_bounds__(128, 12) k_trace_pt(const RenderParams p, unsi
     }
 
     // ---- refill free slots from the queue --------------------------------------------------------------------------------------
-    {
+    for (;;) {
       const unsigned idle = __ballot_sync(0xffffffffu, mode == M_IDLE);
-      if (idle && !exhausted) {
+      if (!idle || exhausted) break;
+      {
         unsigned first = 0;
         if (lane == 0) first = atomicAdd(work_counter, (unsigned)__popc(idle));
         first = __shfl_sync(0xffffffffu, first, 0);
         exhausted = first + (unsigned)__popc(idle) >= total;
         const unsigned idx = first + (unsigned)__popc(idle & lt_mask);
-        if (mode == M_IDLE && idx < total) {  // ray_marching.cl:42-50 for o = 1
-          const HitRecord h = load_record(p.queue, idx);
+        bool take = mode == M_IDLE && idx < total;
+        HitRecord h;
+        if (take) {
+          if (REUSE) {
+            const unsigned f = idx / records;
+            h = load_record(p.queue, idx - f * records);
+            h.seed = p.seeds[f];
+            // atomic_allow_write_max, utility.cl:20-31 (ray_marching.cl:39)
+            uint32_t* hi = p.cache + 2 * (size_t)h.voxel + 1;
+            const int w = (int)(short)(__ldcv(hi) >> 16);
+            take = false;
+            if (!((unsigned)w > (unsigned)p.token_cap)) {
+              const int t = (int)atomicAdd(hi, 0x00010000u);
+              if ((unsigned)(t >> 16) < (unsigned)p.token_cap) take = true;
+              else atomicSub(hi, 0x00010000u);
+            }
+            if (COUNT && take) { c_adm++; c_normals++; }
+          } else {
+            h = load_record(p.queue, idx);
+          }
+        }
+        if (take) {  // ray_marching.cl:42-50 for o = 1
           x = h.xy & 0xFFFF; y = h.xy >> 16; seed = h.seed; voxel = h.voxel; clause_col = h.clause;
           base = h.base; normal = h.normal;
           er = (float)colour(0) / 255.0f; eg = (float)colour(1) / 255.0f; eb = (float)colour(2) / 255.0f;
@@ -429,6 +520,8 @@ __global__ void __launch_bounds__(128, 12) k_trace_pt(const RenderParams p, unsi
           mode = M_SECOND;
         }
       }
+      // rejected samples (voxel at the token cap) leave their slot free: draw again while at least half of the warp is idle
+      if (!REUSE || __popc(__ballot_sync(0xffffffffu, mode == M_IDLE)) < 16) break;
     }
 
     // ---- the one bounce site: ray_bounce_fake_reflectance + `origin += normal*2` + attenuation ------------------------------------
@@ -470,9 +563,9 @@ __global__ void __launch_bounds__(128, 12) k_trace_pt(const RenderParams p, unsi
     }
   }
   if (COUNT) {
-    unsigned v[3] = {c_steps, c_normals, c_env};
+    unsigned v[5] = {c_steps, c_normals, c_env, 0u, c_adm};
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 5; ++k) {
       unsigned s = v[k];
       for (int q = 16; q > 0; q >>= 1) s += __shfl_xor_sync(0xffffffffu, s, q);
       if (lane == 0 && s) atomicAdd(p.counters + k, (unsigned long long)s);
@@ -533,7 +626,7 @@ void camera_basis(const float dir[3], f3* side, f3* up) {
 }  // namespace
 
 int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int32_t* seeds, int nframes, bool trace,
-               bool resolve) {
+               bool resolve, bool first_of_call) {
   vr_ctx* ctx = r->ctx;
   const int rows = r->row1 - r->row0;
   if (rows <= 0) return VR_OK;
@@ -570,33 +663,63 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     p.counters = r->counters;
     p.queue = nullptr; p.qcount = nullptr; p.qcap = 0;
     p.tf = r->tf_active;
-    static int per_sm[2] = {0, 0};  // resident CTAs per SM of the two k_trace_pt instantiations
+    static int per_sm[4] = {0, 0, 0, 0};  // resident CTAs per SM of the k_trace_pt instantiations
     if (!per_sm[0]) {
-      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_trace_pt<false>, 128, 0));
-      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_trace_pt<true>, 128, 0));
+      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_trace_pt<false, false>, 128, 0));
+      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_trace_pt<true, false>, 128, 0));
+      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_trace_pt<false, true>, 128, 0));
+      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_trace_pt<true, true>, 128, 0));
     }
     const size_t pixels = (size_t)r->W * rows * nframes;
     dim3 grid(div_up(r->W, 8), div_up(rows, 16), nframes);
-    if (r->trace_mode == 1) {
-      // hybrid: dense thread-per-pixel primary phase, persistent warps for the queued secondary paths
-      const size_t cap = std::min<size_t>(pixels, (size_t)32 << 20);
+    if (r->trace_mode >= 1) {
+      // mode 1 (hybrid): dense thread-per-pixel k_trace per frame queues admitted hits, persistent warps run their secondary paths
+      // mode 2 (primary reuse, default): k_primary once per pixel, persistent warps run admission + secondary paths per (pixel, frame)
+      const bool reuse = r->trace_mode == 2;
+      const size_t cap = reuse ? (size_t)r->W * rows : std::min<size_t>(pixels, (size_t)32 << 20);
       if (r->queue_cap < cap) {
         if (r->queue) VR_CUDA(cudaFreeAsync(r->queue, ctx->stream));
         r->queue = nullptr; r->queue_cap = 0;
+        r->primary_valid = false;
         VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&r->queue), cap * 3 * sizeof(uint4), ctx->stream));
         r->queue_cap = cap;
       }
       p.queue = r->queue;
       p.qcap = (unsigned)r->queue_cap;
       p.qcount = reinterpret_cast<unsigned*>(r->counters + 6);
-      VR_CUDA(cudaMemsetAsync(p.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
-      if (r->count) k_trace<true, true><<<grid, 128, 0, ctx->stream>>>(p);
-      else k_trace<false, true><<<grid, 128, 0, ctx->stream>>>(p);
-      const unsigned blocks = (unsigned)ctx->sm_count * std::max(1, per_sm[r->count ? 1 : 0]);
-      if (r->count) k_trace_pt<true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-      else k_trace_pt<false><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-      ctx->launches++;
+      if (reuse) {
+        // The records stay valid while camera, rows and scene are unchanged.  Within one call they are always reused; across
+        // calls only on request (vr_renderer_set_primary_reuse(r, 2): the frame_emitter loop calls render_frame once per
+        // sample).  With the per-sample counters on, every batch re-marches (k_primary adds its share for the batch).
+        const bool same = r->primary_valid && !memcmp(r->primary_pos, pos, 12) && !memcmp(r->primary_dir, dir, 12) &&
+                          r->primary_rows[0] == r->row0 && r->primary_rows[1] == r->row1;
+        if (!same || r->count || (first_of_call && !r->primary_across_calls)) {
+          VR_CUDA(cudaMemsetAsync(p.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
+          dim3 g1(div_up(r->W, 8), div_up(rows, 16), 1);
+          if (r->count) k_primary<true><<<g1, 128, 0, ctx->stream>>>(p);
+          else k_primary<false><<<g1, 128, 0, ctx->stream>>>(p);
+          ctx->launches++;
+          memcpy(r->primary_pos, pos, 12); memcpy(r->primary_dir, dir, 12);
+          r->primary_rows[0] = r->row0; r->primary_rows[1] = r->row1;
+          r->primary_valid = true;
+        }
+        VR_CUDA(cudaMemsetAsync(p.qcount + 1, 0, sizeof(unsigned), ctx->stream));
+        const int v = r->count ? 3 : 2;
+        const unsigned blocks = (unsigned)ctx->sm_count * std::max(1, per_sm[v]);
+        if (r->count) k_trace_pt<true, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        else k_trace_pt<false, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+      } else {
+        r->primary_valid = false;
+        VR_CUDA(cudaMemsetAsync(p.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
+        if (r->count) k_trace<true, true><<<grid, 128, 0, ctx->stream>>>(p);
+        else k_trace<false, true><<<grid, 128, 0, ctx->stream>>>(p);
+        const unsigned blocks = (unsigned)ctx->sm_count * std::max(1, per_sm[r->count ? 1 : 0]);
+        if (r->count) k_trace_pt<true, false><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        else k_trace_pt<false, false><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        ctx->launches++;
+      }
     } else {
+      r->primary_valid = false;
       if (r->count) k_trace<true, false><<<grid, 128, 0, ctx->stream>>>(p);
       else k_trace<false, false><<<grid, 128, 0, ctx->stream>>>(p);
     }

@@ -171,11 +171,19 @@ int vr_renderer_resolve(vr_renderer* r, uint8_t* host_rgba);
  * {march steps, shading normals, env fetches, primary hits, admitted samples, samples}. */
 int vr_renderer_enable_counters(vr_renderer* r, int enable);
 int vr_renderer_counters(const vr_renderer* r, uint64_t out[6], int reset);
-/* Scheduling of the trace phase — same per-sample computation and results in both modes:
- *   1 (default) hybrid: the dense thread-per-pixel primary phase (k_trace) queues the admitted hits, persistent warps
+/* Scheduling of the trace phase — same per-sample computation and results in all modes:
+ *   2 (default) primary reuse: everything ray_marching.cl does before it first uses random_seed (ray generation, box cut,
+ *               primary march, environment colour of escaping rays, hit voxel, shading normal — :162-170, :21-33, :42)
+ *               depends on the camera only and is evaluated once per pixel and call (k_primary); token admission and the
+ *               secondary paths run per (pixel, frame) on persistent warps (k_trace_pt)
+ *   1 hybrid:   a dense thread-per-pixel primary phase per frame (k_trace) queues the admitted hits, persistent warps
  *               (k_trace_pt) run their secondary paths in refilled lanes
- *   0 one thread per pixel for its whole life (k_trace alone) */
+ *   0 one thread per pixel and frame for its whole life (k_trace alone) */
 int vr_renderer_set_trace_mode(vr_renderer* r, int mode);
+/* Primary reuse across calls (mode 2 only): 1 (default) = within one vr_render_frames call only; 2 = also across calls
+ * while camera, rows and scene are unchanged — for the reference's usage, one render_frame call per sample
+ * (renderer.cpp:131-158).  Flush, scene, row-range or camera changes always re-march. */
+int vr_renderer_set_primary_reuse(vr_renderer* r, int level);
 /* When enabled, every trace / resolve launch is bracketed by CUDA events on the context's stream;
  * vr_renderer_kernel_times synchronises and returns the summed device time of the trace kernel (out_ms[0]) and of
  * the resolve kernel (out_ms[1]) and the number of frames measured since the last reset. */

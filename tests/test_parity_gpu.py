@@ -114,14 +114,16 @@ def test_render_tf_image(vr_ctx):
 
 
 # ---- render ------------------------------------------------------------------------------------------------------
-TRACE_MODE = [1]  # 1: hybrid k_trace + k_trace_pt (default), 0: k_trace alone; tests using `both` run each
+# 2: k_primary once per pixel + k_trace_pt per (pixel, frame) (default), 1: hybrid k_trace + k_trace_pt per frame,
+# 0: k_trace alone; tests using `both` run each
+TRACE_MODE = [2]
 
 
-@pytest.fixture(params=[1, 0], ids=["hybrid", "k_trace"])
+@pytest.fixture(params=[2, 1, 0], ids=["primary_reuse", "hybrid", "k_trace"])
 def both(request):
     TRACE_MODE[0] = request.param
     yield request.param
-    TRACE_MODE[0] = 1
+    TRACE_MODE[0] = 2
 
 
 def _scene(vr_ctx, n, W, H, tf=None, token_cap=256):
@@ -262,7 +264,35 @@ def test_render_frames_batch_equals_sequential_oracle(vr_ctx, both):
     r.close(); [k.close() for k in keep]
 
 
-@pytest.mark.parametrize("mode", [1, 0])
+def test_primary_reuse_across_calls_and_invalidation(vr_ctx):
+    """vr_renderer_set_primary_reuse(2): per-frame calls with an unchanged camera reuse the primary records; a camera move, a
+    row-range change or a flush re-marches.  Results equal the oracle frame by frame."""
+    r, ref, keep = _scene(vr_ctx, 64, 128, 96)
+    r.set_primary_reuse(2)
+    pos, d = synth.default_camera(64)
+    pos2 = pos + np.array([6.0, -3.0, 2.0], dtype=np.float32)
+    seeds = synth.glibc_rand(9)
+    l0 = vr_ctx.launches
+    for k, s in enumerate(seeds):
+        cam = pos if k < 4 or k >= 7 else pos2   # 4 frames, move, 3 frames, move back, 2 frames
+        got = r.render_frame(cam, d, s)
+        want = ref.render_frame(cam, d, s)
+        assert np.array_equal(got[..., 3], want[..., 3]), k
+        assert _psnr(got[..., :3], want[..., :3]) >= 45.0
+    assert vr_ctx.launches - l0 == 9 * 2 + 3   # trace + resolve per frame, k_primary only after the three camera changes
+    gc, wc = r.cache_download().astype(np.int32), ref.cache.astype(np.int32)
+    assert np.array_equal(gc.reshape(-1, 4)[:, 3], wc.reshape(-1, 4)[:, 3])
+    assert (gc == wc).mean() >= 0.999
+    r.flush_changes(); ref.reset()
+    l0 = vr_ctx.launches
+    got = r.render_frames(pos, d, seeds[:3]); [ref.render_frame(pos, d, s) for s in seeds[:2]]
+    want = ref.render_frame(pos, d, seeds[2])
+    assert vr_ctx.launches - l0 == 3   # k_primary (flush invalidated the records), one k_trace_pt, one k_resolve
+    assert np.array_equal(got[..., 3], want[..., 3]) and _psnr(got[..., :3], want[..., :3]) >= 45.0
+    r.close(); [k.close() for k in keep]
+
+
+@pytest.mark.parametrize("mode", [2, 1, 0])
 def test_render_far_face_positions(vr_ctx, mode):
     # rays that land exactly on the far faces (coordinate == dim): axis-aligned steps of 0.5 from integer origins.
     # The SDF apron must behave like the reference's border read (0 -> step 0.5) and the TF must see value 0.
