@@ -392,6 +392,908 @@ __global__ void __launch_bounds__(RELAX_WARPS * 32) k_sdf_relax(BrickDims g, int
   }
 }
 
+// ---- bit-parallel wavefront (default build) ---------------------------------------------------------------------------------
+// The level-synchronous iteration is a breadth-first search (see the header): |F(v)| = 1 on the band, else
+// min(max_it, 1 + length of the shortest clamped-corner-step walk from v to the band), sign = -1 inside an event.  A voxel's
+// level is the first k at which it belongs to R_k, where R_0 = band and R_k = R_{k-1} | dilate(R_{k-1}); dilate takes the
+// union over the 8 clamped corner offsets and is separable per axis.  With one BIT per voxel (32 voxels along x per word)
+// a level is a handful of shifts and ORs per word, the whole working set (two 16 MiB bit volumes at 512^3) lives in L2, and
+// each int8 of the field is written exactly twice: by the base pass and when its bit first appears.
+//   k_sdf_events : E = event bit of every voxel (is_event_gen evaluated once per voxel; the reference does it 9x)
+//   k_sdf_band   : R_0 = voxels with a clamped corner of the other event state (signed_distance_field.cl:22-48), field =
+//                  +-1 on the band, +-max_it elsewhere, 0 on the apron
+//   k_sdf_wave   : one launch per level; tiles of 4 x 4 rows whose 3x3x3 tile neighbourhood did not change in the previous
+//                  level are skipped (both bit volumes already agree there)
+#define WT_XW 4   // tile = 4 words (128 voxels) x 8 rows x 8 slices: one thread per word
+#define WT_Y 8
+#define WT_Z 8
+#define WAVE_THREADS (WT_XW * WT_Y * WT_Z)
+
+struct WaveDims {
+  int nx, ny, nz;
+  int nxw;         // words per row
+  int bx, by, bz;  // bricks per axis of the field
+  int tx, ty, tz;  // tiles per axis
+  unsigned lastbit;  // bit of x == nx-1 in the last word of a row
+};
+
+__device__ __forceinline__ uint32_t shl_clamped(uint32_t c, uint32_t l, bool first) {  // bit i <- x-1 (x == 0 sees itself)
+  return first ? ((c << 1) | (c & 1u)) : __funnelshift_l(l, c, 1);
+}
+__device__ __forceinline__ uint32_t shr_clamped(uint32_t c, uint32_t r, bool last, unsigned lastbit) {  // bit i <- x+1
+  return last ? ((c >> 1) | (c & (1u << lastbit))) : __funnelshift_r(c, r, 1);
+}
+__device__ __forceinline__ uint32_t valid_mask(const WaveDims& g, int xw) {
+  if (xw != g.nxw - 1 || g.lastbit == 31u) return 0xFFFFFFFFu;
+  return (2u << g.lastbit) - 1u;
+}
+
+// E = event bit of every voxel.  Vector path (nx % 8 == 0, no gradient clause): a warp covers 256 voxels of a row with one
+// 16-byte load per lane (512 contiguous bytes), each lane evaluates its 8 voxels, two shuffles assemble the words.
+__global__ void __launch_bounds__(256) k_sdf_events_v8(VolView vol, TfTable tf, int nxw, uint32_t* __restrict__ E,
+                                                       unsigned chunks_per_row, unsigned nitems) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned it = warp; it < nitems; it += nwarps) {
+    const unsigned row = it / chunks_per_row, chunk = it - row * chunks_per_row;
+    const int x = (int)(chunk * 256 + lane * 8);
+    unsigned bits = 0;
+    if (x < vol.nx) {
+      const int4 q = __ldg(reinterpret_cast<const int4*>(vol.v + (size_t)row * vol.nx + x));
+      const int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int v = (int)(short)((unsigned)w[k >> 1] >> (16 * (k & 1)));
+        bits |= (tf_match(tf, v, 0) != 0 ? 1u : 0u) << k;
+      }
+    }
+    unsigned word = bits << (8 * (lane & 3));
+    word |= __shfl_xor_sync(0xffffffffu, word, 1);
+    word |= __shfl_xor_sync(0xffffffffu, word, 2);
+    const int xw = (int)(chunk * 8 + (lane >> 2));
+    if ((lane & 3) == 0 && xw < nxw) E[(size_t)row * nxw + xw] = word;
+  }
+}
+
+// general path: any nx, TFs with a gradient clause (6 more taps per voxel through L1/L2)
+template <bool GRAD>
+__global__ void __launch_bounds__(256) k_sdf_events(VolView vol, TfTable tf, int nxw, uint32_t* __restrict__ E,
+                                                    unsigned nwords) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned w = warp; w < nwords; w += nwarps) {
+    const unsigned row = w / (unsigned)nxw, xw = w - row * (unsigned)nxw;
+    const int z = (int)(row / (unsigned)vol.ny), y = (int)(row - (unsigned)z * (unsigned)vol.ny);
+    const int x = (int)(xw * 32 + lane);
+    bool e = false;
+    if (x < vol.nx) {
+      if (GRAD) e = voxel_event(vol, tf, x, y, z) != 0;
+      else e = tf_match(tf, __ldg(vol.v + (size_t)row * vol.nx + x), 0) != 0;
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, e);
+    if (lane == 0) E[w] = bits;
+  }
+}
+
+// spread the low 4 bits of b to 4 bytes 0x00/0x01
+__device__ __forceinline__ uint32_t bits4_to_bytes(uint32_t b) { return ((b & 0xFu) * 0x00204081u) & 0x01010101u; }
+
+// One warp per (word column, 8 rows of one z): lane = (8-bit piece of the word) * 8 + row, so that the 8 lanes of a piece
+// write the 64 contiguous bytes of one z-slice of a brick.
+__global__ void __launch_bounds__(256) k_sdf_band(WaveDims g, int max_it, const uint32_t* __restrict__ E,
+                                                  uint32_t* __restrict__ Ra, uint32_t* __restrict__ Rb,
+                                                  int8_t* __restrict__ field, unsigned nxwf, unsigned items) {
+  const unsigned lane = threadIdx.x & 31;
+  const int yr = lane & 7, piece = lane >> 3;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned it = warp; it < items; it += nwarps) {
+    const unsigned t = it / nxwf;
+    const int xw = (int)(it - t * nxwf);
+    const int z = (int)(t / (unsigned)g.by), yg = (int)(t - (unsigned)z * (unsigned)g.by);
+    const int y = yg * 8 + yr;
+    uint32_t own = 0, band = 0, valid = 0;
+    if (xw < g.nxw && y < g.ny && z < g.nz) {
+      valid = valid_mask(g, xw);
+      const bool first = xw == 0, last = xw == g.nxw - 1;
+      own = __ldg(E + ((size_t)z * g.ny + y) * g.nxw + xw);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int yy = min(max(y + ((q & 1) ? 1 : -1), 0), g.ny - 1), zz = min(max(z + ((q & 2) ? 1 : -1), 0), g.nz - 1);
+        const uint32_t* row = E + ((size_t)zz * g.ny + yy) * g.nxw;
+        const uint32_t c = __ldg(row + xw);
+        const uint32_t l = first ? 0u : __ldg(row + xw - 1), r = last ? 0u : __ldg(row + xw + 1);
+        band |= (shl_clamped(c, l, first) ^ own) | (shr_clamped(c, r, last, g.lastbit) ^ own);
+      }
+      band &= valid;
+      if (piece == 0) {
+        const size_t w = ((size_t)z * g.ny + y) * g.nxw + xw;
+        Ra[w] = band;
+        Rb[w] = band;
+      }
+    }
+    const int brick_x = xw * 4 + piece;
+    if (brick_x < g.bx) {
+      const uint32_t e8 = (own >> (8 * piece)) & 0xFFu, b8 = (band >> (8 * piece)) & 0xFFu, v8 = (valid >> (8 * piece)) & 0xFFu;
+      // per byte: valid ? (event ? -1 : 1) * (band ? 1 : max_it) : 0
+      uint32_t out[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t ev = bits4_to_bytes(e8 >> (4 * h)), bd = bits4_to_bytes(b8 >> (4 * h)), vd = bits4_to_bytes(v8 >> (4 * h));
+        const uint32_t mag = bd + (0x01010101u - bd) * (uint32_t)max_it;  // per byte 1 or max_it (<= 127: no carries)
+        const uint32_t val = (mag ^ (ev * 0xFFu)) + ev;                    // per byte -m = ~m + 1 (m >= 1: no carry out)
+        out[h] = val & (vd * 0xFFu);
+      }
+      const size_t brick = ((size_t)(z >> 3) * g.by + yg) * g.bx + brick_x;
+      *reinterpret_cast<uint2*>(field + brick * BRV + ((z & 7) << 6) + (yr << 3)) = make_uint2(out[0], out[1]);
+    }
+  }
+}
+
+// One level: R_out = R_in | dilate(R_in) on the active tiles; the voxels whose bit appears get +-(level+1).
+// Thread = one word: lane = lx + 4*ly (4 words x 8 rows), warp = lz.  The x-neighbour words of the 4 corner rows come from
+// the neighbouring lanes by shuffle; only the lanes at the tile's x edges load them.
+__global__ void __launch_bounds__(WAVE_THREADS) k_sdf_wave(WaveDims g, int level, const uint32_t* __restrict__ Rin,
+                                                           uint32_t* __restrict__ Rout, const uint32_t* __restrict__ E,
+                                                           int8_t* __restrict__ field, const int* __restrict__ stamp_in,
+                                                           int* __restrict__ stamp_out, unsigned* __restrict__ changed_tiles) {
+  const int ntiles = g.tx * g.ty * g.tz;
+  const int lx = threadIdx.x & (WT_XW - 1), ly = (threadIdx.x >> 2) & (WT_Y - 1), lz = threadIdx.x >> 5;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (level != 1 && stamp_in[tile] != level) continue;  // uniform per CTA
+    const int ttx = tile % g.tx, tq = tile / g.tx;
+    const int tty = tq % g.ty, ttz = tq / g.ty;
+    const int xw = ttx * WT_XW + lx, y = tty * WT_Y + ly, z = ttz * WT_Z + lz;
+    const bool inside = xw < g.nxw && y < g.ny && z < g.nz;
+    const bool first = xw == 0, last = xw == g.nxw - 1;
+    const int yc = min(y, g.ny - 1), zc = min(z, g.nz - 1);
+    uint32_t dil = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = min(max(yc + ((q & 1) ? 1 : -1), 0), g.ny - 1), zz = min(max(zc + ((q & 2) ? 1 : -1), 0), g.nz - 1);
+      const uint32_t* row = Rin + ((unsigned)zz * (unsigned)g.ny + (unsigned)yy) * (unsigned)g.nxw;
+      const uint32_t c = xw < g.nxw ? row[xw] : 0u;
+      uint32_t l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
+      if (lx == 0) l = (xw > 0 && xw <= g.nxw) ? row[xw - 1] : 0u;
+      if (lx == WT_XW - 1) r = (xw + 1 < g.nxw) ? row[xw + 1] : 0u;
+      dil |= shl_clamped(c, l, first) | shr_clamped(c, r, last, g.lastbit);
+    }
+    bool changed = false;
+    if (inside) {
+      const unsigned w = ((unsigned)z * (unsigned)g.ny + (unsigned)y) * (unsigned)g.nxw + (unsigned)xw;
+      const uint32_t old = Rin[w];
+      const uint32_t now = (old | dil) & valid_mask(g, xw);
+      Rout[w] = now;
+      const uint32_t diff = now & ~old;
+      if (diff) {
+        changed = true;
+        const uint32_t e = __ldg(E + w);
+        int8_t* rowbase = field + (((size_t)(z >> 3) * g.by + (y >> 3)) * g.bx + (size_t)xw * 4) * BRV + ((z & 7) << 6) + ((y & 7) << 3);
+        const uint32_t mag = 0x01010101u * (uint32_t)(level + 1);
+#pragma unroll
+        for (int piece = 0; piece < 4; ++piece) {
+          const uint32_t d8 = (diff >> (8 * piece)) & 0xFFu;
+          if (!d8) continue;
+          const uint32_t e8 = (e >> (8 * piece)) & 0xFFu;
+          uint2* ptr = reinterpret_cast<uint2*>(rowbase + piece * BRV);
+          uint2 cur = *ptr;
+          const uint32_t m0 = bits4_to_bytes(d8) * 0xFFu, m1 = bits4_to_bytes(d8 >> 4) * 0xFFu;
+          const uint32_t ev0 = bits4_to_bytes(e8), ev1 = bits4_to_bytes(e8 >> 4);
+          cur.x = (cur.x & ~m0) | (((mag ^ (ev0 * 0xFFu)) + ev0) & m0);
+          cur.y = (cur.y & ~m1) | (((mag ^ (ev1 * 0xFFu)) + ev1) & m1);
+          *ptr = cur;
+        }
+      }
+    }
+    if (__syncthreads_or(changed)) {
+      if (threadIdx.x < 27) {
+        const int ox = threadIdx.x % 3 - 1, oy = (threadIdx.x / 3) % 3 - 1, oz = threadIdx.x / 9 - 1;
+        const int ax = ttx + ox, ay = tty + oy, az = ttz + oz;
+        if ((unsigned)ax < (unsigned)g.tx && (unsigned)ay < (unsigned)g.ty && (unsigned)az < (unsigned)g.tz)
+          stamp_out[(az * g.ty + ay) * g.tx + ax] = level + 1;
+      }
+      if (threadIdx.x == 32) atomicAdd(changed_tiles + level, 1u);
+    }
+  }
+}
+
+// ---- dense per-level kernel with bit-sliced level planes (default) -------------------------------------------------------------
+// ncu on the variants below: whatever moves the bits (per-level tiles, shared-memory or register tiles, frontier lists), the
+// time goes into writing one field BYTE per newly reached voxel from inside the wave (divergent per-bit loops or 8-byte
+// read-modify-writes with a dependent load).  Here the wave never touches the field: the level at which a voxel's bit
+// appears is recorded in 7 bit planes L_0..L_6 (L_j[w] |= diff for every set bit j of level+1 — RED.OR, no return value, no
+// divergence), and one coalesced pass at the end (k_sdf_assemble) turns planes + event bits into the bricked int8 field,
+// which is thereby written exactly once.  The band is value 1 (plane 0), voxels that were never reached read 0 -> max_it.
+__global__ void __launch_bounds__(WAVE_THREADS) k_sdf_wave3(WaveDims g, int level, const uint32_t* __restrict__ Rin,
+                                                            uint32_t* __restrict__ Rout, uint32_t* __restrict__ planes,
+                                                            unsigned nwords, const int* __restrict__ stamp_in,
+                                                            int* __restrict__ stamp_out, unsigned* __restrict__ changed_tiles) {
+  const int ntiles = g.tx * g.ty * g.tz;
+  const int lx = threadIdx.x & (WT_XW - 1), ly = (threadIdx.x >> 2) & (WT_Y - 1), lz = threadIdx.x >> 5;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (level != 1 && stamp_in[tile] != level) continue;  // uniform per CTA
+    const int ttx = tile % g.tx, tq = tile / g.tx;
+    const int tty = tq % g.ty, ttz = tq / g.ty;
+    const int xw = ttx * WT_XW + lx, y = tty * WT_Y + ly, z = ttz * WT_Z + lz;
+    const bool inside = xw < g.nxw && y < g.ny && z < g.nz;
+    const bool first = xw == 0, last = xw == g.nxw - 1;
+    const int yc = min(y, g.ny - 1), zc = min(z, g.nz - 1);
+    const unsigned w = ((unsigned)zc * (unsigned)g.ny + (unsigned)yc) * (unsigned)g.nxw + (unsigned)min(xw, g.nxw - 1);
+    const uint32_t old = Rin[w];
+    uint32_t dil = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = min(max(yc + ((q & 1) ? 1 : -1), 0), g.ny - 1), zz = min(max(zc + ((q & 2) ? 1 : -1), 0), g.nz - 1);
+      const uint32_t* row = Rin + ((unsigned)zz * (unsigned)g.ny + (unsigned)yy) * (unsigned)g.nxw;
+      const uint32_t c = xw < g.nxw ? row[xw] : 0u;
+      uint32_t l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
+      if (lx == 0) l = (xw > 0 && xw <= g.nxw) ? row[xw - 1] : 0u;
+      if (lx == WT_XW - 1) r = (xw + 1 < g.nxw) ? row[xw + 1] : 0u;
+      dil |= shl_clamped(c, l, first) | shr_clamped(c, r, last, g.lastbit);
+    }
+    bool changed = false;
+    if (inside) {
+      const uint32_t now = (old | dil) & valid_mask(g, xw);
+      Rout[w] = now;
+      const uint32_t diff = now & ~old;
+      if (diff) {
+        changed = true;
+        const unsigned lv = (unsigned)level + 1u;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+          if ((lv >> j) & 1u) atomicOr(planes + (size_t)j * nwords + w, diff);  // result unused: RED.OR
+      }
+    }
+    if (__syncthreads_or(changed)) {
+      if (threadIdx.x < 27) {
+        const int ox = threadIdx.x % 3 - 1, oy = (threadIdx.x / 3) % 3 - 1, oz = threadIdx.x / 9 - 1;
+        const int ax = ttx + ox, ay = tty + oy, az = ttz + oz;
+        if ((unsigned)ax < (unsigned)g.tx && (unsigned)ay < (unsigned)g.ty && (unsigned)az < (unsigned)g.tz)
+          stamp_out[(az * g.ty + ay) * g.tx + ax] = level + 1;
+      }
+      if (threadIdx.x == 32) changed_tiles[level] = 1u;
+    }
+  }
+}
+
+// Same level semantics, one WARP per tile (4 words x 8 rows x 8 planes): lane = lx + 4*ly, the warp walks the planes.  The
+// y- and x-dilated rows yd(z') are computed once per plane (10 per tile) and reused by the planes z'-1 and z'+1, and all the
+// per-word index arithmetic of k_sdf_wave3 (ncu: ~250 instructions per word, issue-bound) is shared by the 8 words of a
+// thread's column: ~40 instructions per word.  No block-level synchronisation.
+template <int XW>  // words per tile row: lane = lx + XW*ly, tile = XW words x (32/XW) rows x WT_Z planes
+__global__ void __launch_bounds__(128) k_sdf_wave5(WaveDims g, int tx, int ty, int tz, int level,
+                                                   const uint32_t* __restrict__ Rin, uint32_t* __restrict__ Rout,
+                                                   uint32_t* __restrict__ planes, unsigned nwords, const int* __restrict__ stamp_in,
+                                                   int* __restrict__ stamp_out, unsigned* __restrict__ changed_tiles) {
+  constexpr int YR = 32 / XW;
+  const int ntiles = tx * ty * tz;
+  const unsigned lane = threadIdx.x & 31;
+  const int lx = lane & (XW - 1), ly = lane / XW;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles; tile += nwarps) {
+    if (level != 1 && stamp_in[tile] != level) continue;  // warp-uniform
+    const int ttx = tile % tx, tq = tile / tx;
+    const int tty = tq % ty, ttz = tq / ty;
+    const int xw = ttx * XW + lx, y = tty * YR + ly, z0 = ttz * WT_Z;
+    const bool xin = xw < g.nxw;
+    const bool first = xw == 0, last = xw == g.nxw - 1;
+    const uint32_t lm = last ? (1u << g.lastbit) : 0u;  // x == nx-1 is its own +1 neighbour
+    const int yc = min(y, g.ny - 1);
+    const unsigned plane_stride = (unsigned)g.ny * (unsigned)g.nxw;
+    const uint32_t* pm = Rin + (unsigned)max(yc - 1, 0) * (unsigned)g.nxw + (unsigned)min(xw, g.nxw - 1);
+    const uint32_t* pp = Rin + (unsigned)min(yc + 1, g.ny - 1) * (unsigned)g.nxw + (unsigned)min(xw, g.nxw - 1);
+    const bool lload = lx == 0 && xw > 0 && xin, rload = lx == XW - 1 && xw + 1 < g.nxw;
+    uint32_t ydz[WT_Z + 2];
+#pragma unroll
+    for (int k = 0; k < WT_Z + 2; ++k) {
+      const unsigned zo = (unsigned)min(max(z0 - 1 + k, 0), g.nz - 1) * plane_stride;
+      const uint32_t c0 = xin ? pm[zo] : 0u, c1 = xin ? pp[zo] : 0u;
+      uint32_t l0 = __shfl_up_sync(0xffffffffu, c0, 1), r0 = __shfl_down_sync(0xffffffffu, c0, 1);
+      uint32_t l1 = __shfl_up_sync(0xffffffffu, c1, 1), r1 = __shfl_down_sync(0xffffffffu, c1, 1);
+      if (lx == 0) { l0 = 0u; l1 = 0u; }
+      if (lx == XW - 1) { r0 = 0u; r1 = 0u; }
+      if (lload) { l0 = (pm - 1)[zo]; l1 = (pp - 1)[zo]; }
+      if (rload) { r0 = (pm + 1)[zo]; r1 = (pp + 1)[zo]; }
+      if (first) { l0 = c0 << 31; l1 = c1 << 31; }  // x == 0 is its own -1 neighbour
+      ydz[k] = __funnelshift_l(l0, c0, 1) | __funnelshift_r(c0, r0, 1) | __funnelshift_l(l1, c1, 1) | __funnelshift_r(c1, r1, 1) |
+               ((c0 | c1) & lm);
+    }
+    bool changed = false;
+    if (xin && y < g.ny) {
+      const uint32_t vm = valid_mask(g, xw);
+      const unsigned lv = (unsigned)level + 1u;
+#pragma unroll
+      for (int j = 0; j < WT_Z; ++j) {
+        const int z = z0 + j;
+        if (z >= g.nz) break;
+        const unsigned w = (unsigned)z * plane_stride + (unsigned)y * (unsigned)g.nxw + (unsigned)xw;
+        const uint32_t old = Rin[w];
+        const uint32_t now = (old | ydz[j] | ydz[j + 2]) & vm;
+        Rout[w] = now;
+        const uint32_t diff = now & ~old;
+        if (diff) {
+          changed = true;
+#pragma unroll
+          for (int b = 0; b < 7; ++b)
+            if ((lv >> b) & 1u) atomicOr(planes + (size_t)b * nwords + w, diff);  // result unused: RED.OR
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, changed)) {
+      if (lane < 27) {
+        const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
+        const int ax = ttx + ox, ay = tty + oy, az = ttz + oz;
+        if ((unsigned)ax < (unsigned)tx && (unsigned)ay < (unsigned)ty && (unsigned)az < (unsigned)tz)
+          stamp_out[(az * ty + ay) * tx + ax] = level + 1;
+      }
+      if (lane == 31) changed_tiles[level] = 1u;
+    }
+  }
+}
+
+// band bits only (R_0 into both bit volumes and into plane 0 = value 1); the field is written by k_sdf_assemble
+__global__ void __launch_bounds__(256) k_sdf_band_bits(WaveDims g, const uint32_t* __restrict__ E, uint32_t* __restrict__ Ra,
+                                                       uint32_t* __restrict__ Rb, uint32_t* __restrict__ plane0, unsigned nwords) {
+  for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
+    const unsigned row = w / (unsigned)g.nxw;
+    const int xw = (int)(w - row * (unsigned)g.nxw);
+    const int z = (int)(row / (unsigned)g.ny), y = (int)(row - (unsigned)z * (unsigned)g.ny);
+    const bool first = xw == 0, last = xw == g.nxw - 1;
+    const uint32_t own = __ldg(E + w);
+    uint32_t band = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = min(max(y + ((q & 1) ? 1 : -1), 0), g.ny - 1), zz = min(max(z + ((q & 2) ? 1 : -1), 0), g.nz - 1);
+      const uint32_t* r = E + ((size_t)zz * g.ny + yy) * g.nxw;
+      const uint32_t c = __ldg(r + xw);
+      const uint32_t l = first ? 0u : __ldg(r + xw - 1), rr = last ? 0u : __ldg(r + xw + 1);
+      band |= (shl_clamped(c, l, first) ^ own) | (shr_clamped(c, rr, last, g.lastbit) ^ own);
+    }
+    band &= valid_mask(g, xw);
+    Ra[w] = band;
+    Rb[w] = band;
+    plane0[w] = band;
+  }
+}
+
+// planes + event bits -> bricked int8 field.  Same mapping as k_sdf_band: warp = word column x 8 rows of one z,
+// lane = (8-bit piece) * 8 + row, so the 8 lanes of a piece write the 64 contiguous bytes of one z-slice of a brick.
+__global__ void __launch_bounds__(256) k_sdf_assemble(WaveDims g, int max_it, const uint32_t* __restrict__ E,
+                                                      const uint32_t* __restrict__ planes, unsigned nwords,
+                                                      int8_t* __restrict__ field, unsigned nxwf, unsigned items) {
+  const unsigned lane = threadIdx.x & 31;
+  const int yr = lane & 7, piece = lane >> 3;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned it = warp; it < items; it += nwarps) {
+    const unsigned t = it / nxwf;
+    const int xw = (int)(it - t * nxwf);
+    const int z = (int)(t / (unsigned)g.by), yg = (int)(t - (unsigned)z * (unsigned)g.by);
+    const int y = yg * 8 + yr;
+    const int brick_x = xw * 4 + piece;
+    if (brick_x >= g.bx) continue;
+    uint32_t out[2] = {0u, 0u};
+    if (xw < g.nxw && y < g.ny && z < g.nz) {
+      const unsigned w = ((unsigned)z * (unsigned)g.ny + (unsigned)y) * (unsigned)g.nxw + (unsigned)xw;
+      const int sh = 8 * piece;
+      const uint32_t e8 = (__ldg(E + w) >> sh) & 0xFFu, v8 = (valid_mask(g, xw) >> sh) & 0xFFu;
+      uint32_t m0 = 0, m1 = 0;  // per byte: the 7-bit level
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const uint32_t p8 = (__ldg(planes + (size_t)j * nwords + w) >> sh) & 0xFFu;
+        m0 |= bits4_to_bytes(p8) << j;
+        m1 |= bits4_to_bytes(p8 >> 4) << j;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t mag = h ? m1 : m0;
+        // bytes that are 0 (never reached) become max_it: (mag | 0x80808080) - 0x01010101 has bit 7 clear exactly in zero bytes
+        const uint32_t nz = (((mag | 0x80808080u) - 0x01010101u) >> 7) & 0x01010101u;  // 1 where the byte is non-zero
+        mag |= (0x01010101u - nz) * (uint32_t)max_it;
+        const uint32_t ev = bits4_to_bytes(e8 >> (4 * h)), vd = bits4_to_bytes(v8 >> (4 * h));
+        out[h] = ((mag ^ (ev * 0xFFu)) + ev) & (vd * 0xFFu);
+      }
+    }
+    const size_t brick = ((size_t)(z >> 3) * g.by + yg) * g.bx + brick_x;
+    *reinterpret_cast<uint2*>(field + brick * BRV + ((z & 7) << 6) + (yr << 3)) = make_uint2(out[0], out[1]);
+  }
+}
+
+// ---- dense per-level kernel, latency-optimised (default) ------------------------------------------------------------------
+// ncu on k_sdf_wave: ~20 % issue-active; a tile visit is a chain of dependent L2 round trips (stamp -> words -> event word ->
+// field bytes -> barrier).  Here every load of a visit (stamp, the 4 corner-row words, the x-edge words, the word itself, the
+// event word) is issued at once and one visit ahead (software pipelining over the CTA's tiles), the field bytes are plain
+// byte stores (no read-modify-write), and the warps of a CTA never synchronise: each warp owns one z-plane of the tile and
+// raises the neighbour stamps itself.
+struct WaveTileData {
+  int stamp;
+  uint32_t c[4], edge[4], old, e;
+};
+
+__device__ __forceinline__ void wave2_load(const WaveDims& g, int tile, int level, int lx, int ly, int lz,
+                                           const uint32_t* __restrict__ Rin, const uint32_t* __restrict__ E,
+                                           const int* __restrict__ stamp_in, WaveTileData& d) {
+  d.stamp = level == 1 ? level : stamp_in[tile];
+  const int ttx = tile % g.tx, tq = tile / g.tx;
+  const int tty = tq % g.ty, ttz = tq / g.ty;
+  const int xw = ttx * WT_XW + lx, y = tty * WT_Y + ly, z = ttz * WT_Z + lz;
+  const int yc = min(y, g.ny - 1), zc = min(z, g.nz - 1);
+  const bool xin = xw < g.nxw;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int yy = min(max(yc + ((q & 1) ? 1 : -1), 0), g.ny - 1), zz = min(max(zc + ((q & 2) ? 1 : -1), 0), g.nz - 1);
+    const uint32_t* row = Rin + ((unsigned)zz * (unsigned)g.ny + (unsigned)yy) * (unsigned)g.nxw;
+    d.c[q] = xin ? row[xw] : 0u;
+    d.edge[q] = 0u;
+    if (lx == 0 && xw > 0 && xw <= g.nxw) d.edge[q] = row[xw - 1];
+    if (lx == WT_XW - 1 && xw + 1 < g.nxw) d.edge[q] = row[xw + 1];
+  }
+  const unsigned w = ((unsigned)zc * (unsigned)g.ny + (unsigned)yc) * (unsigned)g.nxw + (unsigned)min(xw, g.nxw - 1);
+  d.old = Rin[w];
+  d.e = __ldg(E + w);
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS) k_sdf_wave2(WaveDims g, int level, const uint32_t* __restrict__ Rin,
+                                                            uint32_t* __restrict__ Rout, const uint32_t* __restrict__ E,
+                                                            int8_t* __restrict__ field, const int* __restrict__ stamp_in,
+                                                            int* __restrict__ stamp_out, unsigned* __restrict__ changed_levels) {
+  const int ntiles = g.tx * g.ty * g.tz;
+  const int lx = threadIdx.x & (WT_XW - 1), ly = (threadIdx.x >> 2) & (WT_Y - 1), lz = threadIdx.x >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  WaveTileData cur, nxt;
+  wave2_load(g, tile, level, lx, ly, lz, Rin, E, stamp_in, cur);
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int next = tile + gridDim.x;
+    if (next < ntiles) wave2_load(g, next, level, lx, ly, lz, Rin, E, stamp_in, nxt);
+    if (cur.stamp == level) {  // uniform per CTA
+      const int ttx = tile % g.tx, tq = tile / g.tx;
+      const int tty = tq % g.ty, ttz = tq / g.ty;
+      const int xw = ttx * WT_XW + lx, y = tty * WT_Y + ly, z = ttz * WT_Z + lz;
+      const bool inside = xw < g.nxw && y < g.ny && z < g.nz;
+      const bool first = xw == 0, last = xw == g.nxw - 1;
+      uint32_t dil = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t c = cur.c[q];
+        uint32_t l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
+        if (lx == 0) l = cur.edge[q];
+        if (lx == WT_XW - 1) r = cur.edge[q];
+        dil |= shl_clamped(c, l, first) | shr_clamped(c, r, last, g.lastbit);
+      }
+      uint32_t diff = 0;
+      if (inside) {
+        const uint32_t now = (cur.old | dil) & valid_mask(g, xw);
+        Rout[((unsigned)z * (unsigned)g.ny + (unsigned)y) * (unsigned)g.nxw + (unsigned)xw] = now;
+        diff = now & ~cur.old;
+        if (diff) {
+          int8_t* rowbase = field + (((size_t)(z >> 3) * g.by + (y >> 3)) * g.bx + (size_t)xw * 4) * BRV + ((z & 7) << 6) + ((y & 7) << 3);
+          uint32_t bits = diff;
+          do {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            rowbase[(b >> 3) * BRV + (b & 7)] = (int8_t)(((cur.e >> b) & 1u) ? -(level + 1) : (level + 1));
+          } while (bits);
+        }
+      }
+      if (__any_sync(0xffffffffu, diff != 0)) {  // this warp's plane changed: wake the tile and its neighbours for the next level
+        if (lane < 27) {
+          const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
+          const int ax = ttx + ox, ay = tty + oy, az = ttz + oz;
+          if ((unsigned)ax < (unsigned)g.tx && (unsigned)ay < (unsigned)g.ty && (unsigned)az < (unsigned)g.tz)
+            stamp_out[(az * g.ty + ay) * g.tx + ax] = level + 1;
+        }
+        if (lane == 31) changed_levels[level] = 1u;
+      }
+    }
+    cur = nxt;
+  }
+}
+
+// ---- temporally blocked wavefront (default): W4_H levels per launch, the tile's bits in shared memory ------------------------
+// k_sdf_wave is latency-bound: a level touches every word once with a handful of dependent L2 round trips.  Here a CTA loads
+// a (4+2) x (32+2H) x (32+2H)-word region of R into shared memory, runs H levels on it (the region's rim goes stale by one
+// cell per level, the 4 x 32 x 32 interior stays exact), writes the interior back and the field bytes of the bits that
+// appeared.  Per level: pass 1  B = dilate_y(dilate_x(A)), pass 2  A |= B[z-1] | B[z+1]  (clamped at the volume faces).
+#define W4_VX 4
+#define W4_VY 32
+#define W4_VZ 32
+#define W4_H 4
+#define W4_THREADS 512
+template <int H>
+__global__ void __launch_bounds__(W4_THREADS, 2) k_sdf_wave_tb(WaveDims g, int tx4, int ty4, int tz4, int launch_idx, int level0,
+                                                               int nlev, const uint32_t* __restrict__ Rin,
+                                                               uint32_t* __restrict__ Rout, const uint32_t* __restrict__ E,
+                                                               int8_t* __restrict__ field, const int* __restrict__ stamp_in,
+                                                               int* __restrict__ stamp_out, unsigned* __restrict__ diag) {
+  constexpr int RX = W4_VX + 2, RY = W4_VY + 2 * H, RZ = W4_VZ + 2 * H;
+  constexpr int PLANE = RX * RY;
+  extern __shared__ uint32_t sm[];
+  uint32_t* A = sm;
+  uint32_t* B = sm + PLANE * RZ;
+  uint32_t* Es = B + PLANE * RZ;  // event bits of the interior: W4_VX x W4_VY x W4_VZ
+  const int tile = blockIdx.x;
+  if (launch_idx != 0 && stamp_in[tile] != launch_idx) return;
+  const int ttx = tile % tx4, tq = tile / tx4;
+  const int tty = tq % ty4, ttz = tq / ty4;
+  const int xwb = ttx * W4_VX - 1, yb = tty * W4_VY - H, zb = ttz * W4_VZ - H;
+  for (int i = threadIdx.x; i < PLANE * RZ; i += W4_THREADS) {
+    const int rx = i % RX, r = i / RX;
+    const int ry = r % RY, rz = r / RY;
+    const int xw = xwb + rx, y = yb + ry, z = zb + rz;
+    uint32_t v = 0;
+    if ((unsigned)xw < (unsigned)g.nxw && (unsigned)y < (unsigned)g.ny && (unsigned)z < (unsigned)g.nz)
+      v = Rin[((unsigned)z * (unsigned)g.ny + (unsigned)y) * (unsigned)g.nxw + (unsigned)xw];
+    A[i] = v;
+  }
+  for (int i = threadIdx.x; i < W4_VX * W4_VY * W4_VZ; i += W4_THREADS) {
+    const int xw = xwb + 1 + (i & (W4_VX - 1)), y = yb + H + ((i / W4_VX) & (W4_VY - 1)), z = zb + H + i / (W4_VX * W4_VY);
+    uint32_t v = 0;
+    if (xw < g.nxw && y < g.ny && z < g.nz) v = __ldg(E + ((unsigned)z * (unsigned)g.ny + (unsigned)y) * (unsigned)g.nxw + (unsigned)xw);
+    Es[i] = v;
+  }
+  __syncthreads();
+  // this thread's column (rx, ry) and half of the planes
+  const int col = threadIdx.x % PLANE, zhalf = threadIdx.x / PLANE;
+  const int rx = col % RX, ry = col / RX;
+  const int xw = xwb + rx, y = yb + ry;
+  const bool active = zhalf < 2 && (unsigned)xw < (unsigned)g.nxw && (unsigned)y < (unsigned)g.ny;
+  const bool first = xw == 0, last = xw == g.nxw - 1;
+  const int offc = ry * RX + rx;
+  const int offm = max(min(max(y - 1, 0), g.ny - 1) - yb, 0) * RX + rx;
+  const int offp = min(min(max(y + 1, 0), g.ny - 1) - yb, RY - 1) * RX + rx;
+  const int rz0 = zhalf * (RZ / 2), rz1 = rz0 + RZ / 2;
+  const bool owner = active && rx >= 1 && rx <= W4_VX && ry >= H && ry < H + W4_VY;
+  const uint32_t vmask = active ? valid_mask(g, xw) : 0u;
+  bool changed = false;
+  int maxlev = 0;
+  for (int l = 0; l < nlev; ++l) {
+    const int lev = level0 + l;
+    if (active) {
+      for (int rz = rz0; rz < rz1; ++rz) {
+        if ((unsigned)(zb + rz) >= (unsigned)g.nz) continue;
+        const int p = rz * PLANE;
+        const uint32_t c0 = A[p + offm], c1 = A[p + offp];
+        const uint32_t l0 = rx > 0 ? A[p + offm - 1] : 0u, r0 = rx < RX - 1 ? A[p + offm + 1] : 0u;
+        const uint32_t l1 = rx > 0 ? A[p + offp - 1] : 0u, r1 = rx < RX - 1 ? A[p + offp + 1] : 0u;
+        B[p + offc] = shl_clamped(c0, l0, first) | shr_clamped(c0, r0, last, g.lastbit) | shl_clamped(c1, l1, first) |
+                      shr_clamped(c1, r1, last, g.lastbit);
+      }
+    }
+    __syncthreads();
+    if (active) {
+      for (int rz = rz0; rz < rz1; ++rz) {
+        const int z = zb + rz;
+        if ((unsigned)z >= (unsigned)g.nz) continue;
+        const int p = rz * PLANE + offc;
+        const int pm = max(min(max(z - 1, 0), g.nz - 1) - zb, 0) * PLANE + offc;
+        const int pp = min(min(max(z + 1, 0), g.nz - 1) - zb, RZ - 1) * PLANE + offc;
+        const uint32_t old = A[p];
+        const uint32_t now = (old | B[pm] | B[pp]) & vmask;
+        A[p] = now;
+        if (owner && rz >= H && rz < H + W4_VZ) {
+          uint32_t diff = now & ~old;
+          if (diff) {
+            changed = true;
+            maxlev = lev;
+            const uint32_t e = Es[((rz - H) * W4_VY + (ry - H)) * W4_VX + (rx - 1)];
+            int8_t* rowbase = field + (((size_t)(z >> 3) * g.by + (y >> 3)) * g.bx + (size_t)xw * 4) * BRV + ((z & 7) << 6) + ((y & 7) << 3);
+            do {
+              const int b = __ffs(diff) - 1;
+              diff &= diff - 1;
+              rowbase[(b >> 3) * BRV + (b & 7)] = (int8_t)(((e >> b) & 1u) ? -(lev + 1) : (lev + 1));
+            } while (diff);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (owner) {
+    for (int rz = max(rz0, H); rz < min(rz1, H + W4_VZ); ++rz) {
+      const int z = zb + rz;
+      if (z >= g.nz) break;
+      Rout[((unsigned)z * (unsigned)g.ny + (unsigned)y) * (unsigned)g.nxw + (unsigned)xw] = A[rz * PLANE + offc];
+    }
+  }
+  if (__syncthreads_or(changed)) {
+    if (threadIdx.x < 27) {
+      const int ox = threadIdx.x % 3 - 1, oy = (threadIdx.x / 3) % 3 - 1, oz = threadIdx.x / 9 - 1;
+      const int ax = ttx + ox, ay = tty + oy, az = ttz + oz;
+      if ((unsigned)ax < (unsigned)tx4 && (unsigned)ay < (unsigned)ty4 && (unsigned)az < (unsigned)tz4)
+        stamp_out[(az * ty4 + ay) * tx4 + ax] = launch_idx + 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) maxlev = max(maxlev, __shfl_xor_sync(0xffffffffu, maxlev, o));
+    if ((threadIdx.x & 31) == 0 && maxlev) atomicMax(diag, (unsigned)maxlev);
+  }
+}
+
+// ---- frontier wavefront (default): only the words that gain bits are touched -------------------------------------------------
+// R_k = R_{k-1} | dilate(F_{k-1}) with F_{k-1} = R_{k-1} \ R_{k-2}: bits older than the frontier were dilated in earlier levels.
+// A level works on a list of UNIQUE words that have pending bits (P): the owner of a word takes  new = P[w] & ~R[w],  sets
+// R[w] |= new, writes the field bytes +-(level+1) of the new bits (the whole warp writes one word's 32 bytes at a time), and
+// scatters dilate(new) into the pending words of the <= 12 target words (4 clamped corner rows x {left, centre, right})
+// with atomicOr — the clamped corner relation is symmetric, so scattering from the source equals gathering at the target.
+// The thread whose atomicOr finds a pending word empty appends it to the next list.  Work is proportional to the voxels
+// finalised (~1 % of the volume per level at 512^3), not to the volume.  P is double buffered (a level clears the words it
+// owns while it fills the next level's).  If a list overflows the build restarts with the dense per-level kernel.
+#define FRONT_THREADS 256
+struct FrontCtx {
+  WaveDims g;
+  uint32_t* R;
+  uint32_t* Pnext;
+  uint2* out;
+  unsigned* count_out;
+  unsigned cap;
+  unsigned* overflow;
+};
+
+// scatter dilate(nb) of word (xw,y,z) into Pnext, append the words that had nothing pending; warp-synchronous
+__device__ __forceinline__ void front_scatter(const FrontCtx& f, bool have, uint32_t nb, int xw, int y, int z, unsigned lane) {
+  const WaveDims& g = f.g;
+  uint32_t tws[4] = {0, 0, 0, 0};
+  uint32_t tyz[4] = {0, 0, 0, 0};
+  unsigned app = 0;  // bit 3q+k: append target k (0 centre, 1 left, 2 right) of row q
+  if (have) {
+    const bool first = xw == 0, last = xw == g.nxw - 1;
+    const uint32_t c = (shl_clamped(nb, 0u, first) | shr_clamped(nb, 0u, last, g.lastbit)) & valid_mask(g, xw);
+    const bool lbit = !first && (nb & 1u), rbit = !last && (nb >> 31);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = (q & 1) ? min(y + 1, g.ny - 1) : max(y - 1, 0), zz = (q & 2) ? min(z + 1, g.nz - 1) : max(z - 1, 0);
+      const uint32_t tw = ((unsigned)zz * (unsigned)g.ny + (unsigned)yy) * (unsigned)g.nxw + (unsigned)xw;
+      tws[q] = tw;
+      tyz[q] = (unsigned)yy | ((unsigned)zz << 16);
+      // filter with the (possibly stale) R: bits already reached need no pending entry
+      const uint32_t t = c & ~f.R[tw];
+      if (t && atomicOr(f.Pnext + tw, t) == 0u) app |= 1u << (3 * q);
+      if (lbit && !(f.R[tw - 1] >> 31) && atomicOr(f.Pnext + tw - 1, 0x80000000u) == 0u) app |= 2u << (3 * q);
+      if (rbit && !(f.R[tw + 1] & 1u) && atomicOr(f.Pnext + tw + 1, 1u) == 0u) app |= 4u << (3 * q);
+    }
+  }
+  const unsigned cnt = (unsigned)__popc(app);
+  unsigned incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (unsigned)o) incl += t;
+  }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  unsigned base = 0;
+  if (lane == 31) base = atomicAdd(f.count_out, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  unsigned slot = base + incl - cnt;
+  while (app) {
+    const int k = __ffs(app) - 1;
+    app &= app - 1;
+    const int q = k / 3, side = k - 3 * q;
+    const uint32_t tw = tws[q] + (side == 1 ? 0xFFFFFFFFu : (side == 2 ? 1u : 0u));
+    if (slot < f.cap) f.out[slot] = make_uint2(tw, tyz[q]);
+    else *f.overflow = 1u;
+    ++slot;
+  }
+}
+
+__global__ void __launch_bounds__(FRONT_THREADS) k_sdf_front(FrontCtx f, int level, uint32_t* __restrict__ Pcur,
+                                                             const uint32_t* __restrict__ E, int8_t* __restrict__ field,
+                                                             const uint2* __restrict__ in, const unsigned* __restrict__ count_in) {
+  const WaveDims& g = f.g;
+  const unsigned n = min(*count_in, f.cap);
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n; i0 += stride) {  // warp-uniform trip count
+    const unsigned i = i0 + lane;
+    uint32_t nb = 0, e = 0;
+    int xw = 0, y = 0, z = 0;
+    unsigned long long rowbase = 0;
+    if (i < n) {
+      const uint2 ent = in[i];
+      const uint32_t w = ent.x;
+      y = (int)(ent.y & 0xFFFFu); z = (int)(ent.y >> 16);
+      xw = (int)(w - ((unsigned)z * (unsigned)g.ny + (unsigned)y) * (unsigned)g.nxw);
+      const uint32_t pend = Pcur[w], old = f.R[w];
+      Pcur[w] = 0u;
+      nb = pend & ~old;
+      if (nb) {
+        f.R[w] = old | nb;
+        e = __ldg(E + w);
+        rowbase = (unsigned long long)(field + (((size_t)(z >> 3) * g.by + (y >> 3)) * g.bx + (size_t)xw * 4) * BRV + ((z & 7) << 6) + ((y & 7) << 3));
+      }
+    }
+    // field bytes: one word (32 voxels along x = 4 brick rows of 8 bytes) per step, lane b writes voxel b
+    unsigned m = __ballot_sync(0xffffffffu, nb != 0);
+    const unsigned lane_off = (lane >> 3) * BRV + (lane & 7);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t bits = __shfl_sync(0xffffffffu, nb, src), ev = __shfl_sync(0xffffffffu, e, src);
+      const unsigned long long rb = __shfl_sync(0xffffffffu, rowbase, src);
+      if ((bits >> lane) & 1u) reinterpret_cast<int8_t*>(rb)[lane_off] = (int8_t)(((ev >> lane) & 1u) ? -(level + 1) : (level + 1));
+    }
+    front_scatter(f, nb != 0, nb, xw, y, z, lane);
+  }
+}
+
+// level 0: every band word scatters its bits (nothing to finalise: the band got +-1 from k_sdf_band)
+__global__ void __launch_bounds__(FRONT_THREADS) k_sdf_front_seed(FrontCtx f, unsigned nrows) {
+  const WaveDims& g = f.g;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  // a warp walks whole rows, 32 words at a time
+  for (unsigned row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrows; row += nwarps) {
+    const int z = (int)(row / (unsigned)g.ny), y = (int)(row - (unsigned)z * (unsigned)g.ny);
+    for (int x0 = 0; x0 < g.nxw; x0 += 32) {
+      const int xw = x0 + (int)lane;
+      const uint32_t bits = xw < g.nxw ? f.R[row * (unsigned)g.nxw + (unsigned)xw] : 0u;
+      front_scatter(f, bits != 0, bits, xw, y, z, lane);
+    }
+  }
+}
+
+// ---- register-resident wavefront (default): H levels per launch, a warp's tile of bits lives in registers --------------------
+// The dense per-level kernel is latency-bound (every level is a handful of dependent L2 round trips per word), the shared-
+// memory tile pays 2.3x halo redundancy in instructions, the frontier lists pay atomics per word.  Here a WARP owns a tile
+// of one 32-voxel word (x) x 32 rows (y, one per lane) x RG_Z planes (z, in registers).  Each cell is a 64-bit value
+// [low 16 bits of the right word | the word | high 16 bits of the left word], so x-dilation is two 64-bit shifts, y-dilation
+// two warp shuffles, z-dilation an OR of the neighbouring planes' registers: a level touches no memory at all.  The tile's
+// rim goes stale by one cell per level; after H levels the (32-2H) x (RG_Z-2H) interior is written back.  The bit volumes
+// of this mode are stored [z][xw][y] (y fastest) so that the lanes' loads coalesce.
+#define RG_Z 24
+#define RG_H 4
+#define RG_WARPS 4
+
+__device__ __noinline__ void sdf_emit_bits(int8_t* __restrict__ field, int bx, int by, int xw, int y, int z, uint32_t diff,
+                                           uint32_t e, int mag) {
+  int8_t* rowbase = field + (((size_t)(z >> 3) * by + (y >> 3)) * bx + (size_t)xw * 4) * BRV + ((z & 7) << 6) + ((y & 7) << 3);
+  do {
+    const int b = __ffs(diff) - 1;
+    diff &= diff - 1;
+    rowbase[(b >> 3) * BRV + (b & 7)] = (int8_t)(((e >> b) & 1u) ? -mag : mag);
+  } while (diff);
+}
+
+template <int H, bool BORDER>
+__device__ __forceinline__ void wave_reg_body(const WaveDims& g, int xw, int y0, int z0, int level0, int nlev,
+                                              const uint32_t* __restrict__ Rin, uint32_t* __restrict__ Rout,
+                                              const uint32_t* __restrict__ Et, int8_t* __restrict__ field,
+                                              unsigned* __restrict__ diag) {
+  const unsigned lane = threadIdx.x & 31;
+  const int y = y0 + (int)lane;
+  const bool yin = (unsigned)y < (unsigned)g.ny;
+  const bool first = xw == 0, last = xw == g.nxw - 1;
+  uint32_t lo[RG_Z], hi[RG_Z];
+#pragma unroll
+  for (int k = 0; k < RG_Z; ++k) {
+    const int z = z0 + k;
+    lo[k] = 0; hi[k] = 0;
+    if (yin && (unsigned)z < (unsigned)g.nz) {
+      const uint32_t* p = Rin + ((unsigned)z * (unsigned)g.nxw + (unsigned)xw) * (unsigned)g.ny + (unsigned)y;
+      const uint32_t C = p[0];
+      const uint32_t L = first ? 0u : p[-g.ny];
+      const uint32_t Rr = last ? 0u : p[g.ny];
+      lo[k] = (C << 16) | (L >> 16);
+      hi[k] = (Rr << 16) | (C >> 16);
+    }
+  }
+  // x clamps and the valid-bit mask in the 64-bit cell: word bit b sits at cell bit 16 + b
+  uint32_t fm_lo = 0, lm_lo = 0, lm_hi = 0, vm_lo = 0xFFFFFFFFu, vm_hi = 0xFFFFFFFFu;
+  if (BORDER) {
+    if (first) { fm_lo = 0x10000u; vm_lo = 0xFFFF0000u; }
+    if (last) {
+      const unsigned pb = 16u + g.lastbit;  // cell bit of x == nx-1
+      if (pb < 32u) { lm_lo = 1u << pb; vm_lo &= (2u << pb) - 1u; vm_hi = 0u; }
+      else { lm_hi = 1u << (pb - 32u); vm_hi = (pb - 32u == 31u) ? 0xFFFFFFFFu : ((2u << (pb - 32u)) - 1u); }
+    }
+    if (!yin) { vm_lo = 0u; vm_hi = 0u; }
+  }
+  const bool ytop = BORDER && y == 0, ybot = BORDER && y == g.ny - 1;
+  const bool lane_valid = lane >= (unsigned)H && lane < 32u - (unsigned)H && yin;
+  int maxlev = 0;
+  // event bits of the interior cells (the sign of the field bytes), loaded up front: a load inside the level loop would stall
+  // the warp for a memory round trip at every plane the wavefront crosses
+  uint32_t ev[RG_Z - 2 * H];
+#pragma unroll
+  for (int k = H; k < RG_Z - H; ++k) {
+    const int z = z0 + k;
+    ev[k - H] = 0;
+    if (lane_valid && (unsigned)z < (unsigned)g.nz)
+      ev[k - H] = __ldg(Et + ((unsigned)z * (unsigned)g.nxw + (unsigned)xw) * (unsigned)g.ny + (unsigned)y);
+  }
+
+  auto ydil = [&](uint32_t vlo, uint32_t vhi, uint32_t& olo, uint32_t& ohi) {
+    // x: (V << 1) | (V >> 1) on the 64-bit cell, plus the clamped self-neighbours of x == 0 / x == nx-1
+    uint32_t xlo = (vlo << 1) | __funnelshift_r(vlo, vhi, 1);
+    uint32_t xhi = __funnelshift_l(vlo, vhi, 1) | (vhi >> 1);
+    if (BORDER) { xlo |= vlo & (fm_lo | lm_lo); xhi |= vhi & lm_hi; }
+    // y: rows y-1 and y+1 live in the neighbouring lanes (clamped at the volume faces)
+    uint32_t ulo = __shfl_up_sync(0xffffffffu, xlo, 1), uhi = __shfl_up_sync(0xffffffffu, xhi, 1);
+    uint32_t dlo = __shfl_down_sync(0xffffffffu, xlo, 1), dhi = __shfl_down_sync(0xffffffffu, xhi, 1);
+    if (BORDER) {
+      if (ytop) { ulo = xlo; uhi = xhi; }
+      if (ybot) { dlo = xlo; dhi = xhi; }
+    }
+    olo = ulo | dlo;
+    ohi = uhi | dhi;
+  };
+
+  for (int l = 0; l < nlev; ++l) {
+    const int lev = level0 + l;
+    uint32_t mlo, mhi, clo, chi, plo, phi;  // y-dilated planes k-1, k, k+1 (all from the values before this level)
+    ydil(lo[0], hi[0], clo, chi);
+    mlo = clo; mhi = chi;
+#pragma unroll
+    for (int k = 0; k < RG_Z; ++k) {
+      const int z = z0 + k;
+      if (k + 1 < RG_Z) ydil(lo[k + 1], hi[k + 1], plo, phi);
+      else { plo = clo; phi = chi; }
+      uint32_t nlo, nhi;
+      if (BORDER) {
+        const bool zlo_face = z == 0, zhi_face = z == g.nz - 1;
+        nlo = (zlo_face ? clo : mlo) | (zhi_face ? clo : plo);
+        nhi = (zlo_face ? chi : mhi) | (zhi_face ? chi : phi);
+        if ((unsigned)z >= (unsigned)g.nz) { nlo = 0u; nhi = 0u; }
+        nlo &= vm_lo; nhi &= vm_hi;
+      } else {
+        nlo = mlo | plo;
+        nhi = mhi | phi;
+      }
+      const uint32_t olo = lo[k], ohi = hi[k];
+      lo[k] = olo | nlo;
+      hi[k] = ohi | nhi;
+      if (k >= H && k < RG_Z - H) {  // interior plane: record the voxels whose bit appeared
+        const uint32_t cold = __funnelshift_r(olo, ohi, 16), cnew = __funnelshift_r(lo[k], hi[k], 16);
+        const uint32_t diff = cnew & ~cold;
+        if (lane_valid && diff && (!BORDER || (unsigned)z < (unsigned)g.nz)) {
+          maxlev = lev;
+          sdf_emit_bits(field, g.bx, g.by, xw, y, z, diff, ev[k - H], lev + 1);
+        }
+      }
+      mlo = clo; mhi = chi;
+      clo = plo; chi = phi;
+    }
+  }
+  if (lane_valid) {
+#pragma unroll
+    for (int k = H; k < RG_Z - H; ++k) {
+      const int z = z0 + k;
+      if ((unsigned)z < (unsigned)g.nz)
+        Rout[((unsigned)z * (unsigned)g.nxw + (unsigned)xw) * (unsigned)g.ny + (unsigned)y] = __funnelshift_r(lo[k], hi[k], 16);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) maxlev = max(maxlev, __shfl_xor_sync(0xffffffffu, maxlev, o));
+  if (lane == 0 && maxlev) atomicMax(diag, (unsigned)maxlev);
+}
+
+template <int H>
+__global__ void __launch_bounds__(RG_WARPS * 32) k_sdf_wave_reg(WaveDims g, int nty, int ntz, int level0, int nlev,
+                                                                const uint32_t* __restrict__ Rin, uint32_t* __restrict__ Rout,
+                                                                const uint32_t* __restrict__ Et, int8_t* __restrict__ field,
+                                                                unsigned* __restrict__ diag) {
+  const unsigned tile = blockIdx.x * RG_WARPS + (threadIdx.x >> 5);
+  if (tile >= (unsigned)g.nxw * (unsigned)nty * (unsigned)ntz) return;  // warp-uniform
+  const int xw = (int)(tile % (unsigned)g.nxw);
+  const unsigned t = tile / (unsigned)g.nxw;
+  const int ty = (int)(t % (unsigned)nty), tz = (int)(t / (unsigned)nty);
+  const int y0 = ty * (32 - 2 * H) - H, z0 = tz * (RG_Z - 2 * H) - H;
+  const bool border = xw == 0 || xw == g.nxw - 1 || y0 < 0 || y0 + 32 > g.ny || z0 < 0 || z0 + RG_Z > g.nz;
+  if (border) wave_reg_body<H, true>(g, xw, y0, z0, level0, nlev, Rin, Rout, Et, field, diag);
+  else wave_reg_body<H, false>(g, xw, y0, z0, level0, nlev, Rin, Rout, Et, field, diag);
+}
+
+// [z][y][xw] -> [z][xw][y]
+__global__ void __launch_bounds__(256) k_bits_transpose(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int nxw, int ny,
+                                                        unsigned nwords) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) {
+    const unsigned row = i / (unsigned)nxw, xw = i - row * (unsigned)nxw;
+    const unsigned z = row / (unsigned)ny, y = row - z * (unsigned)ny;
+    out[(z * (unsigned)nxw + xw) * (unsigned)ny + y] = in[i];
+  }
+}
+
 // bricked -> x-fastest linear (vr_sdf_download; tests/sdf/sdf_test.cpp:24-31 order)
 __global__ void __launch_bounds__(256) k_sdf_unbrick(BrickDims g, const int8_t* __restrict__ field,
                                                      int8_t* __restrict__ linear) {
@@ -413,6 +1315,230 @@ int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const
   const int max_it = std::min(std::max(nx, std::max(ny, nz)) / 2, 127);  // signed_distance_field.cpp:11
   BrickDims g{nx, ny, nz, nx / BR + 1, ny / BR + 1, nz / BR + 1};
   const size_t nbricks = (size_t)g.bx * g.by * g.bz;
+  static const char* mode_env = getenv("VR_SDF_MODE");
+  static const bool level_sync = mode_env && !strcmp(mode_env, "level");
+  static const bool async_relax = mode_env && !strcmp(mode_env, "async");
+  static const bool brick_bfs = mode_env && !strcmp(mode_env, "warp");
+  if (!level_sync && !async_relax && !brick_bfs) {
+    // default: bit-parallel wavefront
+    WaveDims w{};
+    w.nx = nx; w.ny = ny; w.nz = nz;
+    w.nxw = (nx + 31) / 32;
+    w.bx = g.bx; w.by = g.by; w.bz = g.bz;
+    w.tx = (w.nxw + WT_XW - 1) / WT_XW; w.ty = (ny + WT_Y - 1) / WT_Y; w.tz = (nz + WT_Z - 1) / WT_Z;
+    w.lastbit = (unsigned)((nx - 1) & 31);
+    const size_t nwords = (size_t)w.nxw * ny * nz;
+    const size_t ntiles = (size_t)w.tx * w.ty * w.tz;
+    // scratch: E | Ra | Rb | stamps[2][ntiles] | changed[130]
+    uint32_t* scratch = nullptr;
+    const size_t words = 3 * nwords + 2 * ntiles + 130;
+    VR_CUDA(cudaMallocAsync(&scratch, words * 4, ctx->stream));
+    uint32_t *E = scratch, *R[2] = {scratch + nwords, scratch + 2 * nwords};
+    int* stamps[2] = {reinterpret_cast<int*>(scratch + 3 * nwords), reinterpret_cast<int*>(scratch + 3 * nwords + ntiles)};
+    unsigned* changed = scratch + 3 * nwords + 2 * ntiles;
+    VR_CUDA(cudaMemsetAsync(stamps[0], 0, (2 * ntiles + 130) * 4, ctx->stream));
+    VolView v{vol, nx, ny, nz};
+    if (!tf.needs_gradient && nx % 8 == 0) {
+      const unsigned chunks = (unsigned)div_up(nx, 256);
+      const unsigned nitems = chunks * (unsigned)ny * (unsigned)nz;
+      const unsigned eg = (unsigned)std::min<size_t>(div_up(nitems, 8), (size_t)ctx->sm_count * 16);
+      k_sdf_events_v8<<<eg, 256, 0, ctx->stream>>>(v, tf, w.nxw, E, chunks, nitems);
+    } else {
+      const unsigned eg = (unsigned)std::min<size_t>(div_up(nwords, 8), (size_t)ctx->sm_count * 16);
+      if (tf.needs_gradient) k_sdf_events<true><<<eg, 256, 0, ctx->stream>>>(v, tf, w.nxw, E, (unsigned)nwords);
+      else k_sdf_events<false><<<eg, 256, 0, ctx->stream>>>(v, tf, w.nxw, E, (unsigned)nwords);
+    }
+    const unsigned nxwf = (unsigned)((8 * w.bx + 31) / 32);
+    const unsigned band_items = nxwf * (unsigned)w.by * (8u * (unsigned)w.bz);
+    const unsigned bg = (unsigned)std::min<size_t>(div_up(band_items, 8), (size_t)ctx->sm_count * 16);
+    static const bool planes_mode = !mode_env || !(!strcmp(mode_env, "wave1") || !strcmp(mode_env, "wave2") || !strcmp(mode_env, "wave4") ||
+                                                   !strcmp(mode_env, "front") || !strcmp(mode_env, "reg"));
+    if (!planes_mode) k_sdf_band<<<bg, 256, 0, ctx->stream>>>(w, max_it, E, R[0], R[1], field, nxwf, band_items);
+    ctx->launches += 2;
+    static const bool per_level = mode_env && !strcmp(mode_env, "wave1");
+    static const bool blocked = mode_env && !strcmp(mode_env, "wave4");
+    static const bool frontier = mode_env && !strcmp(mode_env, "front");
+    static const bool regtile = mode_env && !strcmp(mode_env, "reg");
+    static const bool pipelined = mode_env && !strcmp(mode_env, "wave2");
+    if (!per_level && !blocked && !frontier && !regtile && !pipelined) {
+      // default: dense per-level kernel, levels recorded in bit planes, field assembled once at the end
+      uint32_t* planes = nullptr;
+      VR_CUDA(cudaMallocAsync(&planes, 7 * nwords * 4, ctx->stream));
+      VR_CUDA(cudaMemsetAsync(planes + nwords, 0, 6 * nwords * 4, ctx->stream));
+      const unsigned bb = (unsigned)std::min<size_t>(div_up(nwords, 256), (size_t)ctx->sm_count * 16);
+      k_sdf_band_bits<<<bb, 256, 0, ctx->stream>>>(w, E, R[0], R[1], planes, (unsigned)nwords);
+      ctx->launches++;
+      static const bool cta_tiles = mode_env && !strcmp(mode_env, "wave3");
+      const unsigned wg = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * 8);
+      // warp tiles: as many words of a row as fit (power of two up to 32), 32/XW rows, WT_Z planes
+      // measured at 512^3: XW = 4 (compact 128 x 8 x 8 voxel tiles, better tile skipping) 3.99 ms, XW = 16 4.42 ms
+      static const int xw_env = getenv("VR_SDF_TILE_XW") ? atoi(getenv("VR_SDF_TILE_XW")) : 4;
+      const int XW = (xw_env == 32 || xw_env == 16 || xw_env == 8) ? xw_env : 4;
+      const int tx5 = (w.nxw + XW - 1) / XW, ty5 = (ny + 32 / XW - 1) / (32 / XW), tz5 = (nz + WT_Z - 1) / WT_Z;
+      const size_t ntiles5 = (size_t)tx5 * ty5 * tz5;  // <= ntiles: the stamp arrays are large enough
+      const unsigned wg5 = (unsigned)std::min<size_t>(div_up(ntiles5, 4), (size_t)ctx->sm_count * 16);
+      for (int it = 1; it + 1 < max_it; ++it) {
+        const uint32_t* rin = R[(it + 1) & 1];
+        uint32_t* rout = R[it & 1];
+        const int* si = stamps[it & 1];
+        int* so = stamps[(it + 1) & 1];
+        if (cta_tiles)
+          k_sdf_wave3<<<wg, WAVE_THREADS, 0, ctx->stream>>>(w, it, rin, rout, planes, (unsigned)nwords, si, so, changed);
+        else if (XW == 32)
+          k_sdf_wave5<32><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed);
+        else if (XW == 16)
+          k_sdf_wave5<16><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed);
+        else if (XW == 8)
+          k_sdf_wave5<8><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed);
+        else
+          k_sdf_wave5<4><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed);
+        ctx->launches++;
+      }
+      k_sdf_assemble<<<bg, 256, 0, ctx->stream>>>(w, max_it, E, planes, (unsigned)nwords, field, nxwf, band_items);
+      ctx->launches++;
+      VR_CUDA(cudaGetLastError());
+      unsigned* hc = reinterpret_cast<unsigned*>(ctx->scratch_host);
+      VR_CUDA(cudaMemcpyAsync(hc, changed, sizeof(unsigned) * 130, cudaMemcpyDeviceToHost, ctx->stream));
+      VR_CUDA(cudaFreeAsync(planes, ctx->stream));
+      VR_CUDA(cudaFreeAsync(scratch, ctx->stream));
+      VR_CUDA(cudaStreamSynchronize(ctx->stream));
+      int levels = 0;
+      for (int it = 1; it + 1 < max_it; ++it)
+        if (hc[it] != 0) levels = it;
+      *levels_out = levels;
+      *max_it_out = max_it;
+      return VR_OK;
+    }
+    if (pipelined) {
+      // default: dense per-level kernel with pipelined loads
+      const unsigned wg = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * 8);
+      for (int it = 1; it + 1 < max_it; ++it) {
+        k_sdf_wave2<<<wg, WAVE_THREADS, 0, ctx->stream>>>(w, it, R[(it + 1) & 1], R[it & 1], E, field, stamps[it & 1],
+                                                         stamps[(it + 1) & 1], changed);
+        ctx->launches++;
+      }
+      VR_CUDA(cudaGetLastError());
+      unsigned* hc = reinterpret_cast<unsigned*>(ctx->scratch_host);
+      VR_CUDA(cudaMemcpyAsync(hc, changed, sizeof(unsigned) * 130, cudaMemcpyDeviceToHost, ctx->stream));
+      VR_CUDA(cudaFreeAsync(scratch, ctx->stream));
+      VR_CUDA(cudaStreamSynchronize(ctx->stream));
+      int levels = 0;
+      for (int it = 1; it + 1 < max_it; ++it)
+        if (hc[it] != 0) levels = it;
+      *levels_out = levels;
+      *max_it_out = max_it;
+      return VR_OK;
+    }
+    if (regtile) {
+      // default: register-resident tiles, RG_H levels per launch, bit volumes transposed to [z][xw][y]
+      constexpr int H = RG_H;
+      uint32_t* extra = nullptr;
+      VR_CUDA(cudaMallocAsync(&extra, 2 * nwords * 4, ctx->stream));
+      uint32_t* T[2] = {R[1], extra};   // R[1] (a copy of the band) is free in this mode
+      uint32_t* Et = extra + nwords;
+      const unsigned tg = (unsigned)std::min<size_t>(div_up(nwords, 256), (size_t)ctx->sm_count * 16);
+      k_bits_transpose<<<tg, 256, 0, ctx->stream>>>(R[0], T[0], w.nxw, ny, (unsigned)nwords);
+      k_bits_transpose<<<tg, 256, 0, ctx->stream>>>(E, Et, w.nxw, ny, (unsigned)nwords);
+      ctx->launches += 2;
+      const int nty = (ny + (32 - 2 * H) - 1) / (32 - 2 * H), ntz = (nz + (RG_Z - 2 * H) - 1) / (RG_Z - 2 * H);
+      const unsigned tiles = (unsigned)w.nxw * (unsigned)nty * (unsigned)ntz;
+      int launch = 0;
+      for (int it = 1; it + 1 < max_it; it += H, ++launch) {
+        const int nlev = std::min(H, max_it - 1 - it);
+        k_sdf_wave_reg<H><<<div_up(tiles, RG_WARPS), RG_WARPS * 32, 0, ctx->stream>>>(w, nty, ntz, it, nlev, T[launch & 1],
+                                                                                   T[(launch + 1) & 1], Et, field, changed);
+        ctx->launches++;
+      }
+      VR_CUDA(cudaGetLastError());
+      unsigned* hc = reinterpret_cast<unsigned*>(ctx->scratch_host);
+      VR_CUDA(cudaMemcpyAsync(hc, changed, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+      VR_CUDA(cudaFreeAsync(extra, ctx->stream));
+      VR_CUDA(cudaFreeAsync(scratch, ctx->stream));
+      VR_CUDA(cudaStreamSynchronize(ctx->stream));
+      *levels_out = (int)hc[0];
+      *max_it_out = max_it;
+      return VR_OK;
+    }
+    if (frontier && max_it > 2) {
+      // frontier lists: 2 x cap entries of (word, y | z << 16) | counts[130] | overflow; pending bits: R[1] and E-sized P2
+      static const char* cap_env = getenv("VR_SDF_FRONT_CAP");  // tests force the overflow fallback with a tiny capacity
+      const size_t cap = cap_env ? (size_t)atol(cap_env) : nwords + 1024;
+      uint32_t* fs = nullptr;
+      VR_CUDA(cudaMallocAsync(&fs, (4 * cap + 132 + nwords) * 4, ctx->stream));
+      uint2* lists[2] = {reinterpret_cast<uint2*>(fs), reinterpret_cast<uint2*>(fs + 2 * cap)};
+      unsigned* counts = fs + 4 * cap;
+      unsigned* overflow = counts + 130;
+      uint32_t* P[2] = {R[1], fs + 4 * cap + 132};  // R[1] is free in this mode
+      VR_CUDA(cudaMemsetAsync(counts, 0, (132 + nwords) * 4, ctx->stream));
+      VR_CUDA(cudaMemsetAsync(P[0], 0, nwords * 4, ctx->stream));
+      FrontCtx f{w, R[0], P[1], lists[1], counts + 1, (unsigned)cap, overflow};
+      const unsigned nrows = (unsigned)ny * (unsigned)nz;
+      const unsigned sg = (unsigned)std::min<size_t>(div_up(nrows, FRONT_THREADS / 32), (size_t)ctx->sm_count * 8);
+      k_sdf_front_seed<<<sg, FRONT_THREADS, 0, ctx->stream>>>(f, nrows);
+      ctx->launches++;
+      const unsigned fg = (unsigned)ctx->sm_count * 8;
+      for (int it = 1; it + 1 < max_it; ++it) {
+        f.Pnext = P[(it + 1) & 1];
+        f.out = lists[(it + 1) & 1];
+        f.count_out = counts + it + 1;
+        k_sdf_front<<<fg, FRONT_THREADS, 0, ctx->stream>>>(f, it, P[it & 1], E, field, lists[it & 1], counts + it);
+        ctx->launches++;
+      }
+      VR_CUDA(cudaGetLastError());
+      unsigned* hc = reinterpret_cast<unsigned*>(ctx->scratch_host);
+      VR_CUDA(cudaMemcpyAsync(hc, counts, sizeof(unsigned) * 132, cudaMemcpyDeviceToHost, ctx->stream));
+      VR_CUDA(cudaFreeAsync(fs, ctx->stream));
+      VR_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (hc[130] == 0) {
+        int levels = 0;
+        for (int it = 1; it + 1 < max_it; ++it)
+          if (hc[it] != 0) levels = it;  // words with pending bits at level it
+        VR_CUDA(cudaFreeAsync(scratch, ctx->stream));
+        *levels_out = levels;
+        *max_it_out = max_it;
+        return VR_OK;
+      }
+      // overflow: rebuild R_0 and the field, then run the dense per-level kernel below
+      k_sdf_band<<<bg, 256, 0, ctx->stream>>>(w, max_it, E, R[0], R[1], field, nxwf, band_items);
+      ctx->launches++;
+    }
+    if (!blocked) {
+      const unsigned wg = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * 8);
+      for (int it = 1; it + 1 < max_it; ++it) {  // level it finalises magnitude it+1, stored only when it+1 < max_it
+        k_sdf_wave<<<wg, WAVE_THREADS, 0, ctx->stream>>>(w, it, R[(it + 1) & 1], R[it & 1], E, field, stamps[it & 1],
+                                                        stamps[(it + 1) & 1], changed);
+        ctx->launches++;
+      }
+    } else {
+      constexpr int H = W4_H;
+      const int tx4 = (w.nxw + W4_VX - 1) / W4_VX, ty4 = (ny + W4_VY - 1) / W4_VY, tz4 = (nz + W4_VZ - 1) / W4_VZ;
+      const size_t smem = ((size_t)2 * (W4_VX + 2) * (W4_VY + 2 * H) * (W4_VZ + 2 * H) + W4_VX * W4_VY * W4_VZ) * 4;
+      static bool attr_set = false;
+      if (!attr_set) {
+        VR_CUDA(cudaFuncSetAttribute(k_sdf_wave_tb<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      int launch = 0;
+      for (int it = 1; it + 1 < max_it; it += H, ++launch) {
+        const int nlev = std::min(H, max_it - 1 - it);
+        k_sdf_wave_tb<H><<<tx4 * ty4 * tz4, W4_THREADS, smem, ctx->stream>>>(w, tx4, ty4, tz4, launch, it, nlev, R[launch & 1],
+                                                                          R[(launch + 1) & 1], E, field, stamps[launch & 1],
+                                                                          stamps[(launch + 1) & 1], changed);
+        ctx->launches++;
+      }
+    }
+    VR_CUDA(cudaGetLastError());
+    unsigned* hc = reinterpret_cast<unsigned*>(ctx->scratch_host);
+    VR_CUDA(cudaMemcpyAsync(hc, changed, sizeof(unsigned) * 130, cudaMemcpyDeviceToHost, ctx->stream));
+    VR_CUDA(cudaFreeAsync(scratch, ctx->stream));
+    VR_CUDA(cudaStreamSynchronize(ctx->stream));
+    int levels = (int)hc[0];  // temporally blocked build: atomicMax of the last level that set a bit
+    for (int it = 1; it + 1 < max_it; ++it)
+      if (hc[it] != 0) levels = it;
+    *levels_out = levels;
+    *max_it_out = max_it;
+    return VR_OK;
+  }
   // scratch: stamp[nbricks] | list A[nbricks] | list B[nbricks] | counts[130]
   uint32_t* scratch = nullptr;
   const size_t words = nbricks * 3 + 130;
@@ -424,9 +1550,6 @@ int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const
   VolView v{vol, nx, ny, nz};
   k_sdf_base<<<dim3(g.bx, g.by, g.bz), SDF_THREADS, 0, ctx->stream>>>(v, tf, g, max_it, field, stamp, lists[1], counts + 1);
   ctx->launches++;
-  static const char* mode_env = getenv("VR_SDF_MODE");
-  static const bool level_sync = mode_env && !strcmp(mode_env, "level");
-  static const bool async_relax = mode_env && !strcmp(mode_env, "async");
   unsigned* hc = reinterpret_cast<unsigned*>(ctx->scratch_host);
   int levels = 0;
   if (level_sync) {

@@ -312,3 +312,34 @@ def test_render_far_face_positions(vr_ctx, mode):
         assert np.array_equal(got[..., 3], want[..., 3])
         assert np.array_equal(r.cache_download().reshape(-1, 4)[:, 3], ref.cache.reshape(-1, 4)[:, 3])
     r.close(); env.close(); vol.close()
+
+
+@pytest.mark.parametrize("mode", ["front_overflow", "front", "reg", "wave1", "wave2", "wave3", "wave4", "warp"])
+def test_sdf_alternative_builds_bit_exact(mode):
+    """The SDF build has one default path (frontier lists) and fallbacks / A-B variants selected by VR_SDF_MODE; a frontier
+    list that overflows restarts with the dense per-level kernel.  All must reproduce the reference's golden vector and
+    the oracle on a synthetic volume (own process: the mode is read once per process)."""
+    import subprocess, sys, os
+    env = dict(os.environ)
+    if mode == "front_overflow":
+        env["VR_SDF_MODE"] = "front"
+        env["VR_SDF_FRONT_CAP"] = "64"
+    else:
+        env["VR_SDF_MODE"] = mode
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, 'tests')\n"
+        "import oracle_lib as o\n"
+        "from cl_volume_renderer_b200 import api, synth\n"
+        "ctx = api.Context(0)\n"
+        "G = np.load('tests/golden/sdf_ref.npz')\n"
+        "vol = api.Volume(ctx, G['volume']); s = api.Sdf(ctx, vol, synth.threshold_tf(int(G['threshold'])))\n"
+        "assert np.array_equal(s.download(), G['sdf'])\n"
+        "v = synth.synth_ct(72, dims=(70, 45, 96)); vol2 = api.Volume(ctx, v)\n"
+        "for tf in (synth.default_tf(), synth.threshold_tf(700)):\n"
+        "    s2 = api.Sdf(ctx, vol2, tf)\n"
+        "    assert np.array_equal(s2.download(), o.sdf_build(v, tf)[0])\n"
+        "print('OK')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr

@@ -45,7 +45,7 @@ def report(path, n):
         out[k] = {"launches": cnt, "total_us": round(us, 1), "alg_bytes": b, "alg_GBps": round(gbs, 1) if gbs else None,
                   "frac_of_6461.5": round(gbs / 6461.5, 3) if gbs else None}
         print(f"{k:28s} n={cnt:4d} total={us:10.1f} us  alg={'%.0f MB' % (b/1e6) if b else '-':>10s}  {('%.0f GB/s' % gbs) if gbs else '':>10s} {('%.1f%%' % (100*gbs/6461.5)) if gbs else ''}")
-    sdf = sum(v["total_us"] for k, v in out.items() if k.startswith('k_sdf_base') or k.startswith('k_sdf_level'))
+    sdf = sum(v["total_us"] for k, v in out.items() if k.startswith("k_sdf_") and not k.startswith("k_sdf_unbrick"))
     print(f"SDF build (base + levels): {sdf:.0f} us -> 3N/t = {3*N/(sdf*1e-6)/1e9:.0f} GB/s")
     return out
 
