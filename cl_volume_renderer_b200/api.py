@@ -51,6 +51,16 @@ SYMBOLS = {
     "vr_volume_filter": (C.c_int, [_P]),
     "vr_volume_download": (C.c_int, [_P, _P]),
     "vr_histogram": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), _P]),
+    "vr_volume_upload_slab": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vr_volume_download_planes": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "vr_sdf_slab_create": (C.c_int, [_P, _P, C.POINTER(TfRect), C.c_int, C.c_int, C.POINTER(_P)]),
+    "vr_sdf_slab_advance": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
+    "vr_sdf_slab_bits": (_P, [_P]),
+    "vr_sdf_slab_plane_words": (C.c_size_t, [_P]),
+    "vr_sdf_slab_mark_imported": (C.c_int, [_P]),
+    "vr_sdf_slab_finished": (C.c_int, [_P]),
+    "vr_sdf_slab_download": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vr_sdf_slab_destroy": (None, [_P]),
     "vr_envmap_bind": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
     "vr_envmap_destroy": (None, [_P]),
     "vr_sdf_build": (C.c_int, [_P, _P, C.POINTER(TfRect), C.c_int, C.POINTER(_P)]),
@@ -172,13 +182,23 @@ class Context:
 class Volume:
     """reference_volume (app/reference_volume.hpp:27-63)"""
 
-    def __init__(self, ctx, voxels):
+    def __init__(self, ctx, voxels, interior=None):
+        """interior=(z_lo, z_hi): `voxels` is a z-slab with halo planes; stats / histogram cover planes [z_lo, z_hi) only"""
         voxels = np.ascontiguousarray(voxels, dtype=np.int16)
         assert voxels.ndim == 3, "volume must be [nz, ny, nx]"
         nz, ny, nx = voxels.shape
         self.ctx = ctx
         self.h = _P()
-        _check(lib().vr_volume_upload(ctx.h, _vp(voxels), nx, ny, nz, C.byref(self.h)))
+        if interior is None:
+            _check(lib().vr_volume_upload(ctx.h, _vp(voxels), nx, ny, nz, C.byref(self.h)))
+        else:
+            _check(lib().vr_volume_upload_slab(ctx.h, _vp(voxels), nx, ny, nz, interior[0], interior[1], C.byref(self.h)))
+
+    def download_planes(self, z0, nplanes):
+        nx, ny, _ = self.dims()
+        out = np.empty((nplanes, ny, nx), dtype=np.int16)
+        _check(lib().vr_volume_download_planes(self.h, z0, nplanes, _vp(out)))
+        return out
 
     def close(self):
         if self.h:
@@ -260,6 +280,48 @@ class Sdf:
     @property
     def levels(self):
         return lib().vr_sdf_levels(self.h)
+
+
+class SdfSlab:
+    """SDF of a z-slab with halo planes, advanced level by level (include/vr.h, z-slab sharding); driver: parallel.py"""
+
+    def __init__(self, ctx, ext_volume, tf_specs, max_it_global):
+        arr, n = make_rects(tf_specs)
+        self.ctx = ctx
+        self.h = _P()
+        self.dims = ext_volume.dims()
+        _check(lib().vr_sdf_slab_create(ctx.h, ext_volume.h, arr, n, max_it_global, C.byref(self.h)))
+
+    def advance(self, nlevels):
+        done = C.c_int(0)
+        _check(lib().vr_sdf_slab_advance(self.h, nlevels, C.byref(done)))
+        return done.value
+
+    @property
+    def finished(self):
+        return bool(lib().vr_sdf_slab_finished(self.h))
+
+    @property
+    def bits_ptr(self):
+        return lib().vr_sdf_slab_bits(self.h)
+
+    @property
+    def plane_words(self):
+        return int(lib().vr_sdf_slab_plane_words(self.h))
+
+    def mark_imported(self):
+        _check(lib().vr_sdf_slab_mark_imported(self.h))
+
+    def download(self, z0, nplanes):
+        nx, ny, nz = self.dims
+        out = np.empty((nplanes, ny, nx), dtype=np.int8)
+        _check(lib().vr_sdf_slab_download(self.h, self.ctx.h, nx, ny, nz, z0, nplanes, _vp(out)))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().vr_sdf_slab_destroy(self.h)
+            self.h = _P()
 
 
 class Renderer:

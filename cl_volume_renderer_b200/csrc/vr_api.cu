@@ -97,10 +97,11 @@ extern "C" void* vr_ctx_stream(vr_ctx* c) { return c ? (void*)c->stream : nullpt
 extern "C" uint64_t vr_ctx_launch_count(const vr_ctx* c) { return c ? c->launches : 0; }
 
 // ---- volume --------------------------------------------------------------------------------------------------
-extern "C" int vr_volume_upload(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz, vr_volume** out) {
+static int volume_upload_impl(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz, int zlo, int zhi, vr_volume** out) {
   VR_REQUIRE(ctx && voxels && out, "vr_volume_upload: null argument");
   VR_REQUIRE(nx > 0 && ny > 0 && nz > 0, "vr_volume_upload: dimensions must be positive");
   VR_REQUIRE((size_t)nx * ny * nz < ((size_t)1 << 32) - 1, "vr_volume_upload: more than 2^32-2 voxels");
+  VR_REQUIRE(zlo >= 0 && zlo < zhi && zhi <= nz, "vr_volume_upload_slab: bad interior plane range");
   VR_CUDA(cudaSetDevice(ctx->device));
   vr_volume* v = new (std::nothrow) vr_volume();
   if (!v) return VR_ERR_NOMEM;
@@ -109,9 +110,31 @@ extern "C" int vr_volume_upload(vr_ctx* ctx, const int16_t* voxels, int nx, int 
   const size_t bytes = v->count() * sizeof(int16_t);
   VR_CUDA(pool_alloc(ctx, &v->original, bytes));
   VR_CUDA(cudaMemcpyAsync(v->original, voxels, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  int s = vrk_fetch_stats(ctx, v->original, nx, ny, nz, v->stats);  // reference_volume.cpp:22-41
+  v->zlo = zlo; v->zhi = zhi;
+  int s = vrk_fetch_stats(ctx, v->original, nx, ny, nz, v->stats, zlo, zhi);  // reference_volume.cpp:22-41
   if (s != VR_OK) { pool_free(ctx, v->original); delete v; return s; }
   *out = v;
+  return VR_OK;
+}
+
+extern "C" int vr_volume_upload(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz, vr_volume** out) {
+  return volume_upload_impl(ctx, voxels, nx, ny, nz, 0, nz, out);
+}
+
+// z-slab of a larger volume (multi-GPU sharding, no reference counterpart): planes [z_lo, z_hi) are this rank's, the planes
+// around them are halo — read by gradient taps, filter taps and the SDF wave, not counted by stats / histogram
+extern "C" int vr_volume_upload_slab(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz_ext, int z_lo, int z_hi,
+                                     vr_volume** out) {
+  return volume_upload_impl(ctx, voxels, nx, ny, nz_ext, z_lo, z_hi, out);
+}
+
+extern "C" int vr_volume_download_planes(const vr_volume* v, int z0, int nplanes, int16_t* out) {
+  VR_REQUIRE(v && out && z0 >= 0 && nplanes > 0 && z0 + nplanes <= v->nz, "vr_volume_download_planes: bad argument");
+  VR_CUDA(cudaSetDevice(v->ctx->device));
+  const size_t plane = (size_t)v->nx * v->ny;
+  VR_CUDA(cudaMemcpyAsync(out, v->current() + plane * z0, plane * nplanes * sizeof(int16_t), cudaMemcpyDeviceToHost,
+                          v->ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(v->ctx->stream));
   return VR_OK;
 }
 
@@ -151,6 +174,7 @@ extern "C" int vr_volume_clip(vr_volume* v, const uint32_t mn[3], const uint32_t
   pool_free(v->ctx, v->cropped);
   v->cropped = dst;
   v->nx = nx; v->ny = ny; v->nz = nz;
+  v->zlo = 0; v->zhi = nz;
   return VR_OK;
 }
 
@@ -183,7 +207,7 @@ extern "C" int vr_histogram(const vr_volume* v, int width, int height, const flo
   uint32_t* bins = nullptr;
   const size_t bytes = sizeof(uint32_t) * (size_t)width * height;
   VR_CUDA(pool_alloc(v->ctx, &bins, bytes));
-  int s = vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins);
+  int s = vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi);
   if (s == VR_OK) {
     cudaError_t e = cudaMemcpyAsync(bins_out, bins, bytes, cudaMemcpyDeviceToHost, v->ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(v->ctx->stream);
@@ -263,6 +287,49 @@ extern "C" int vr_sdf_download(const vr_sdf* s, int8_t* out) {
 }
 
 extern "C" int vr_sdf_levels(const vr_sdf* s) { return s ? s->levels : 0; }
+
+// ---- z-slab SDF build (multi-GPU sharding; driver: cl_volume_renderer_b200/parallel.py) -------------------------------------
+extern "C" int vr_sdf_slab_create(vr_ctx* ctx, const vr_volume* ext_slab, const vr_tf_rect* rects, int n_rects, int max_it_global,
+                                  vr_sdf_slab** out) {
+  VR_REQUIRE(ctx && ext_slab && out && (rects || n_rects == 0), "vr_sdf_slab_create: null argument");
+  VR_REQUIRE(n_rects >= 0 && n_rects <= VR_TF_MAX_RECTS, "vr_sdf_slab_create: too many TF clauses");
+  VR_REQUIRE(max_it_global >= 1 && max_it_global <= 127, "vr_sdf_slab_create: max_it must be in [1,127]");
+  VR_CUDA(cudaSetDevice(ctx->device));
+  return vrk_sdf_slab_create(ctx, ext_slab->current(), ext_slab->nx, ext_slab->ny, ext_slab->nz, vr_make_tf_table(rects, n_rects),
+                             max_it_global, out);
+}
+extern "C" int vr_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* levels_done) {
+  VR_REQUIRE(s && nlevels >= 0, "vr_sdf_slab_advance: bad argument");
+  return vrk_sdf_slab_advance(s, nlevels, levels_done);
+}
+extern "C" void* vr_sdf_slab_bits(vr_sdf_slab* s) { return s ? (void*)vrk_sdf_slab_bits(s) : nullptr; }
+extern "C" size_t vr_sdf_slab_plane_words(const vr_sdf_slab* s) { return s ? vrk_sdf_slab_plane_words(s) : 0; }
+extern "C" int vr_sdf_slab_mark_imported(vr_sdf_slab* s) {
+  VR_REQUIRE(s, "vr_sdf_slab_mark_imported: null argument");
+  vrk_sdf_slab_mark_imported(s);
+  return VR_OK;
+}
+extern "C" int vr_sdf_slab_finished(const vr_sdf_slab* s) { return s ? (vrk_sdf_slab_finished(s) ? 1 : 0) : 1; }
+extern "C" int vr_sdf_slab_download(vr_sdf_slab* s, vr_ctx* ctx, int nx, int ny, int nz_ext, int z0, int nplanes, int8_t* out) {
+  VR_REQUIRE(s && ctx && out && z0 >= 0 && nplanes > 0 && z0 + nplanes <= nz_ext, "vr_sdf_slab_download: bad argument");
+  VR_CUDA(cudaSetDevice(ctx->device));
+  int8_t *field = nullptr, *linear = nullptr;
+  const size_t n = (size_t)nx * ny * nz_ext;
+  VR_CUDA(pool_alloc(ctx, &field, vrk_sdf_field_bytes(nx, ny, nz_ext)));
+  VR_CUDA(pool_alloc(ctx, &linear, n));
+  int st = vrk_sdf_slab_assemble(s, field);
+  if (st == VR_OK) st = vrk_sdf_unbrick(ctx, field, nx, ny, nz_ext, linear);
+  if (st == VR_OK) {
+    const size_t plane = (size_t)nx * ny;
+    cudaError_t e = cudaMemcpyAsync(out, linear + plane * z0, plane * nplanes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { vr_set_error("vr_sdf_slab_download: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  }
+  pool_free(ctx, linear);
+  pool_free(ctx, field);
+  return st;
+}
+extern "C" void vr_sdf_slab_destroy(vr_sdf_slab* s) { vrk_sdf_slab_destroy(s); }
 
 // ---- renderer --------------------------------------------------------------------------------------------------
 extern "C" int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_renderer** out) {
@@ -541,7 +608,8 @@ extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba
   if (e == cudaSuccess) e = pool_alloc(ctx, &img, nb * 4);
   if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
   if (status == VR_OK)
-    status = vrk_histogram(ctx, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height, range, bins);
+    status = vrk_histogram(ctx, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height, range, bins, r->vol->zlo,
+                           r->vol->zhi);
   if (status == VR_OK) {
     e = cudaMemcpyAsync(h.data(), bins, nb * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -58,6 +58,7 @@ struct vr_volume {
   int16_t* cropped = nullptr;  // device, non-null once clipped (reference_volume.hpp:31-33)
   int nx = 0, ny = 0, nz = 0;  // dims of the current volume
   int32_t stats[4] = {0, 0, 0, 0};
+  int zlo = 0, zhi = 0;  // planes the stats / histogram cover (whole volume unless uploaded as a z-slab with halo planes)
   int value_clip[2] = {INT32_MIN, INT32_MAX};     // reference_volume.hpp:35-36
   int gradient_clip[2] = {INT32_MIN, INT32_MAX};
   const int16_t* current() const { return cropped ? cropped : original; }
@@ -113,12 +114,23 @@ struct vr_renderer {
 };
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------------
-int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int32_t out[4]);
+// stats / histogram over the planes [zlo, zhi) only (z-slab sharding: the other planes are halo for the gradient taps)
+int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int32_t out[4], int zlo, int zhi);
 int vrk_clip(vr_ctx* ctx, const int16_t* src, int snx, int sny, int snz, const uint32_t start[3], int16_t* dst, int nx,
              int ny, int nz);
 int vrk_bilateral(vr_ctx* ctx, const int16_t* src, int16_t* dst, int nx, int ny, int nz);
 int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4],
-                  uint32_t* bins_dev);
+                  uint32_t* bins_dev, int zlo, int zhi);
+struct vr_sdf_slab;
+int vrk_sdf_slab_create(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int max_it, vr_sdf_slab** out);
+int vrk_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* done);
+uint32_t* vrk_sdf_slab_bits(vr_sdf_slab* s);
+size_t vrk_sdf_slab_plane_words(const vr_sdf_slab* s);
+void vrk_sdf_slab_mark_imported(vr_sdf_slab* s);
+int vrk_sdf_slab_level(const vr_sdf_slab* s);
+bool vrk_sdf_slab_finished(const vr_sdf_slab* s);
+int vrk_sdf_slab_assemble(vr_sdf_slab* s, int8_t* field);
+void vrk_sdf_slab_destroy(vr_sdf_slab* s);
 int vrk_tf_color_frame(vr_ctx* ctx, const int32_t* bins_dev, const int32_t* lookup_dev, int lookup_len, int width,
                        int height, uchar4* out_dev);
 int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field,

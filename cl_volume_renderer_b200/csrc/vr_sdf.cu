@@ -666,14 +666,15 @@ template <int XW>  // words per tile row: lane = lx + XW*ly, tile = XW words x (
 __global__ void __launch_bounds__(128) k_sdf_wave5(WaveDims g, int tx, int ty, int tz, int level,
                                                    const uint32_t* __restrict__ Rin, uint32_t* __restrict__ Rout,
                                                    uint32_t* __restrict__ planes, unsigned nwords, const int* __restrict__ stamp_in,
-                                                   int* __restrict__ stamp_out, unsigned* __restrict__ changed_tiles) {
+                                                   int* __restrict__ stamp_out, unsigned* __restrict__ changed_tiles,
+                                                   int all_active) {
   constexpr int YR = 32 / XW;
   const int ntiles = tx * ty * tz;
   const unsigned lane = threadIdx.x & 31;
   const int lx = lane & (XW - 1), ly = lane / XW;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles; tile += nwarps) {
-    if (level != 1 && stamp_in[tile] != level) continue;  // warp-uniform
+    if (level != 1 && !all_active && stamp_in[tile] != level) continue;  // warp-uniform
     const int ttx = tile % tx, tq = tile / tx;
     const int tty = tq % ty, ttz = tq / ty;
     const int xw = ttx * XW + lx, y = tty * YR + ly, z0 = ttz * WT_Z;
@@ -1385,13 +1386,13 @@ int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const
         if (cta_tiles)
           k_sdf_wave3<<<wg, WAVE_THREADS, 0, ctx->stream>>>(w, it, rin, rout, planes, (unsigned)nwords, si, so, changed);
         else if (XW == 32)
-          k_sdf_wave5<32><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed);
+          k_sdf_wave5<32><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed, 0);
         else if (XW == 16)
-          k_sdf_wave5<16><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed);
+          k_sdf_wave5<16><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed, 0);
         else if (XW == 8)
-          k_sdf_wave5<8><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed);
+          k_sdf_wave5<8><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed, 0);
         else
-          k_sdf_wave5<4><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed);
+          k_sdf_wave5<4><<<wg5, 128, 0, ctx->stream>>>(w, tx5, ty5, tz5, it, rin, rout, planes, (unsigned)nwords, si, so, changed, 0);
         ctx->launches++;
       }
       k_sdf_assemble<<<bg, 256, 0, ctx->stream>>>(w, max_it, E, planes, (unsigned)nwords, field, nxwf, band_items);
@@ -1607,6 +1608,107 @@ int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const
   *levels_out = levels;
   *max_it_out = max_it;
   return VR_OK;
+}
+
+// ---- z-slab build (multi-GPU): the same kernels on a rank's slab + halo planes, driven level by level ------------
+// A rank holds the planes [z0 - h_lo, z1 + h_hi) of the volume (h = 0 at the global faces).  Everything the wave computes for
+// a plane depends on the planes within one step per level, so results go stale from the slab's artificial ends inwards by
+// one plane per level (two more at the start: gradient taps of the event test and the band test).  The driver
+// (cl_volume_renderer_b200/parallel.py) therefore runs K levels, lets the neighbours overwrite the halo planes of the
+// current bit volume with their exact interior planes, marks the import (all tiles active for one level) and continues.
+struct vr_sdf_slab {
+  vr_ctx* ctx = nullptr;
+  WaveDims w{};
+  int max_it = 0;      // of the GLOBAL volume (signed_distance_field.cpp:11)
+  int level = 1;       // next level to run
+  size_t nwords = 0, ntiles = 0;
+  uint32_t* scratch = nullptr;  // E | R0 | R1 | stamps[2][ntiles] | changed[130]
+  uint32_t* planes = nullptr;
+  bool all_active = false;
+  uint32_t* E() const { return scratch; }
+  uint32_t* R(int i) const { return scratch + (1 + i) * nwords; }
+  int* stamps(int i) const { return reinterpret_cast<int*>(scratch + 3 * nwords + (size_t)i * ntiles); }
+  unsigned* changed() const { return scratch + 3 * nwords + 2 * ntiles; }
+};
+
+int vrk_sdf_slab_create(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int max_it, vr_sdf_slab** out) {
+  vr_sdf_slab* s = new (std::nothrow) vr_sdf_slab();
+  if (!s) return VR_ERR_NOMEM;
+  s->ctx = ctx; s->max_it = max_it;
+  WaveDims& w = s->w;
+  w.nx = nx; w.ny = ny; w.nz = nz;
+  w.nxw = (nx + 31) / 32;
+  w.bx = nx / BR + 1; w.by = ny / BR + 1; w.bz = nz / BR + 1;
+  w.tx = (w.nxw + WT_XW - 1) / WT_XW; w.ty = (ny + WT_Y - 1) / WT_Y; w.tz = (nz + WT_Z - 1) / WT_Z;
+  w.lastbit = (unsigned)((nx - 1) & 31);
+  s->nwords = (size_t)w.nxw * ny * nz;
+  s->ntiles = (size_t)w.tx * w.ty * w.tz;
+  const size_t nwords = s->nwords;
+  cudaError_t e = cudaMallocAsync(&s->scratch, (3 * nwords + 2 * s->ntiles + 130) * 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&s->planes, 7 * nwords * 4, ctx->stream);
+  if (e != cudaSuccess) { vr_set_error("vr_sdf_slab_create: %s", cudaGetErrorString(e)); delete s; return VR_ERR_CUDA; }
+  VR_CUDA(cudaMemsetAsync(s->stamps(0), 0, (2 * s->ntiles + 130) * 4, ctx->stream));
+  VR_CUDA(cudaMemsetAsync(s->planes + nwords, 0, 6 * nwords * 4, ctx->stream));
+  VolView v{vol, nx, ny, nz};
+  if (!tf.needs_gradient && nx % 8 == 0) {
+    const unsigned chunks = (unsigned)div_up(nx, 256);
+    const unsigned nitems = chunks * (unsigned)ny * (unsigned)nz;
+    k_sdf_events_v8<<<(unsigned)std::min<size_t>(div_up(nitems, 8), (size_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+        v, tf, w.nxw, s->E(), chunks, nitems);
+  } else {
+    const unsigned eg = (unsigned)std::min<size_t>(div_up(nwords, 8), (size_t)ctx->sm_count * 16);
+    if (tf.needs_gradient) k_sdf_events<true><<<eg, 256, 0, ctx->stream>>>(v, tf, w.nxw, s->E(), (unsigned)nwords);
+    else k_sdf_events<false><<<eg, 256, 0, ctx->stream>>>(v, tf, w.nxw, s->E(), (unsigned)nwords);
+  }
+  const unsigned bb = (unsigned)std::min<size_t>(div_up(nwords, 256), (size_t)ctx->sm_count * 16);
+  k_sdf_band_bits<<<bb, 256, 0, ctx->stream>>>(w, s->E(), s->R(0), s->R(1), s->planes, (unsigned)nwords);
+  ctx->launches += 2;
+  VR_CUDA(cudaGetLastError());
+  *out = s;
+  return VR_OK;
+}
+
+int vrk_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* done) {
+  vr_ctx* ctx = s->ctx;
+  const WaveDims& w = s->w;
+  const unsigned wg5 = (unsigned)std::min<size_t>(div_up(s->ntiles, 4), (size_t)ctx->sm_count * 16);
+  int n = 0;
+  for (; n < nlevels && s->level + 1 < s->max_it; ++n, ++s->level) {
+    const int it = s->level;
+    k_sdf_wave5<4><<<wg5, 128, 0, ctx->stream>>>(w, w.tx, w.ty, w.tz, it, s->R((it + 1) & 1), s->R(it & 1), s->planes,
+                                                (unsigned)s->nwords, s->stamps(it & 1), s->stamps((it + 1) & 1), s->changed(),
+                                                s->all_active ? 1 : 0);
+    s->all_active = false;
+    ctx->launches++;
+  }
+  VR_CUDA(cudaGetLastError());
+  if (done) *done = n;
+  return VR_OK;
+}
+
+uint32_t* vrk_sdf_slab_bits(vr_sdf_slab* s) { return s->R((s->level + 1) & 1); }  // the volume level `s->level` will read
+size_t vrk_sdf_slab_plane_words(const vr_sdf_slab* s) { return (size_t)s->w.nxw * s->w.ny; }
+void vrk_sdf_slab_mark_imported(vr_sdf_slab* s) { s->all_active = true; }
+int vrk_sdf_slab_level(const vr_sdf_slab* s) { return s->level; }
+bool vrk_sdf_slab_finished(const vr_sdf_slab* s) { return s->level + 1 >= s->max_it; }
+
+int vrk_sdf_slab_assemble(vr_sdf_slab* s, int8_t* field) {
+  const WaveDims& w = s->w;
+  const unsigned nxwf = (unsigned)((8 * w.bx + 31) / 32);
+  const unsigned items = nxwf * (unsigned)w.by * (8u * (unsigned)w.bz);
+  const unsigned bg = (unsigned)std::min<size_t>(div_up(items, 8), (size_t)s->ctx->sm_count * 16);
+  k_sdf_assemble<<<bg, 256, 0, s->ctx->stream>>>(w, s->max_it, s->E(), s->planes, (unsigned)s->nwords, field, nxwf, items);
+  s->ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}
+
+void vrk_sdf_slab_destroy(vr_sdf_slab* s) {
+  if (!s) return;
+  cudaFreeAsync(s->scratch, s->ctx->stream);
+  cudaFreeAsync(s->planes, s->ctx->stream);
+  cudaStreamSynchronize(s->ctx->stream);
+  delete s;
 }
 
 int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear) {

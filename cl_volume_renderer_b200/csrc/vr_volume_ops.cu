@@ -11,12 +11,12 @@
 
 // ---- fetch_stats: reference_volume_figures.cl:10-26 -----------------------------------------------------------
 // The reference issues four global atomics per voxel; here: per-thread -> warp shuffle -> block -> 4 atomics/block.
-__global__ void __launch_bounds__(TX* TY* TZ) k_fetch_stats(VolView vol, int32_t* __restrict__ stats) {
+__global__ void __launch_bounds__(TX* TY* TZ) k_fetch_stats(VolView vol, int32_t* __restrict__ stats, int zlo, int zhi) {
   const int x = blockIdx.x * TX + threadIdx.x;
   const int y = blockIdx.y * TY + threadIdx.y;
   const int z = blockIdx.z * TZ + threadIdx.z;
   int mnv = INT32_MAX, mxv = INT32_MIN, mng = INT32_MAX, mxg = INT32_MIN;
-  if (x < vol.nx && y < vol.ny && z < vol.nz) {
+  if (x < vol.nx && y < vol.ny && z >= zlo && z < zhi) {
     int v = vol.at(x, y, z);
     int g = f2i(length3(gradient_voxel(vol, x, y, z)));  // implicit float->int of atomic_min/max(int*, float)
     mnv = mxv = v;
@@ -95,12 +95,12 @@ __device__ __forceinline__ float grad_sq(const Octet& o, int k) {
 #define VZ 2
 // fetch_stats, vectorised.  sqrt and float->int are monotonic, so min/max of (int)sqrt(s) = (int)sqrt(min/max s): the
 // square root is taken once per thread instead of once per voxel — bit-identical.
-__global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8(VolView vol, int32_t* __restrict__ stats) {
+__global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8(VolView vol, int32_t* __restrict__ stats, int zlo, int zhi) {
   const int x0 = (blockIdx.x * VX + threadIdx.x) * 8;
   const int y = blockIdx.y * VY + threadIdx.y;
   const int z = blockIdx.z * VZ + threadIdx.z;
   int mnv = INT32_MAX, mxv = INT32_MIN, mng = INT32_MAX, mxg = INT32_MIN;
-  if (x0 < vol.nx && y < vol.ny && z < vol.nz) {
+  if (x0 < vol.nx && y < vol.ny && z >= zlo && z < zhi) {
     const Octet o = load_octet(vol, x0, y, z);
     float smin = grad_sq(o, 0), smax = smin;
     mnv = mxv = o.c[0];
@@ -131,17 +131,17 @@ __global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8(VolView vol, int3
   }
 }
 
-int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int32_t out[4]) {
+int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int32_t out[4], int zlo, int zhi) {
   int32_t init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};  // reference_volume.cpp:22-28
   memcpy(ctx->scratch_host, init, sizeof(init));
   VR_CUDA(cudaMemcpyAsync(ctx->scratch, ctx->scratch_host, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   VolView v{vol, nx, ny, nz};
   if (nx % 8 == 0) {
     dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
-    k_fetch_stats_v8<<<grid, block, 0, ctx->stream>>>(v, ctx->scratch);
+    k_fetch_stats_v8<<<grid, block, 0, ctx->stream>>>(v, ctx->scratch, zlo, zhi);
   } else {
     dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
-    k_fetch_stats<<<grid, block, 0, ctx->stream>>>(v, ctx->scratch);
+    k_fetch_stats<<<grid, block, 0, ctx->stream>>>(v, ctx->scratch, zlo, zhi);
   }
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
@@ -229,12 +229,12 @@ int vrk_bilateral(vr_ctx* ctx, const int16_t* src, int16_t* dst, int nx, int ny,
 // per warp instead of 32.
 __global__ void __launch_bounds__(TX* TY* TZ) k_histogram(VolView vol, uint32_t* __restrict__ bins, int width,
                                                           int height, float min_v, float max_v, float min_g,
-                                                          float max_g) {
+                                                          float max_g, int zlo, int zhi) {
   const int x = blockIdx.x * TX + threadIdx.x;
   const int y = blockIdx.y * TY + threadIdx.y;
   const int z = blockIdx.z * TZ + threadIdx.z;
   long long flat = -1;
-  if (x < vol.nx && y < vol.ny && z < vol.nz) {
+  if (x < vol.nx && y < vol.ny && z >= zlo && z < zhi) {
     int ref_value = vol.at(x, y, z);
     float g = length3(gradient_voxel(vol, x, y, z));
     if (!(g > max_g) && !((float)ref_value > max_v)) {
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_histogram(VolView vol, uint32_t*
 // table once at the end.
 #define HKEYS 4096
 __global__ void __launch_bounds__(VX* VY* VZ) k_histogram_v8(VolView vol, uint32_t* __restrict__ bins, int width, int height,
-                                                             float min_v, float max_v, float min_g, float max_g) {
+                                                             float min_v, float max_v, float min_g, float max_g, int zlo, int zhi) {
   __shared__ int hkey[HKEYS];
   __shared__ unsigned hcnt[HKEYS];
   const int tid = threadIdx.x + VX * (threadIdx.y + VY * threadIdx.z);
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(VX* VY* VZ) k_histogram_v8(VolView vol, uint32
     const int x0 = (int)(((t % tx) * VX + threadIdx.x) * 8);
     const int y = (int)(((t / tx) % ty) * VY + threadIdx.y);
     const int z = (int)((t / (tx * ty)) * VZ + threadIdx.z);
-    const bool in = x0 < vol.nx && y < vol.ny && z < vol.nz;
+    const bool in = x0 < vol.nx && y < vol.ny && z >= zlo && z < zhi;
     Octet o;
     if (in) o = load_octet(vol, x0, y, z);
 #pragma unroll
@@ -312,16 +312,16 @@ __global__ void __launch_bounds__(VX* VY* VZ) k_histogram_v8(VolView vol, uint32
 }
 
 int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4],
-                  uint32_t* bins_dev) {
+                  uint32_t* bins_dev, int zlo, int zhi) {
   VR_CUDA(cudaMemsetAsync(bins_dev, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
   VolView v{vol, nx, ny, nz};
   if (nx % 8 == 0) {
     const size_t tiles = (size_t)div_up(nx, VX * 8) * div_up(ny, VY) * div_up(nz, VZ);
     dim3 grid((unsigned)std::min<size_t>(tiles, (size_t)ctx->sm_count * 6)), block(VX, VY, VZ);
-    k_histogram_v8<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3]);
+    k_histogram_v8<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3], zlo, zhi);
   } else {
     dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
-    k_histogram<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3]);
+    k_histogram<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3], zlo, zhi);
   }
   ctx->launches++;
   VR_CUDA(cudaGetLastError());

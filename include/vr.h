@@ -166,6 +166,27 @@ size_t vr_renderer_xchg_bytes(const vr_renderer* r);
 /* re-run only the resolve pass (after an external cache all-reduce) and optionally read the frame back */
 int vr_renderer_resolve(vr_renderer* r, uint8_t* host_rgba);
 
+/* ---- z-slab sharding (multi-GPU; no reference counterpart — SURVEY.md 8e).  A rank holds planes [z0-h, z1+h) of the volume:
+ * vr_volume_upload_slab marks [z_lo, z_hi) (indices into the slab) as its own; stats and histogram count only those, the
+ * other planes serve gradient / filter taps and the SDF wave.  Partial results combine with MIN/MAX (stats) and SUM (bins). */
+int vr_volume_upload_slab(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz_ext, int z_lo, int z_hi, vr_volume** out);
+int vr_volume_download_planes(const vr_volume* vol, int z0, int nplanes, int16_t* out);
+/* SDF of a slab, level by level.  The wave's results go stale from the slab's artificial ends inwards by one plane per
+ * level (plus two at the start), so the caller runs K levels (vr_sdf_slab_advance), overwrites the halo planes of the
+ * CURRENT bit volume (vr_sdf_slab_bits: uint32 [nz_ext][ny][ceil(nx/32)], one bit per voxel already reached) with the
+ * neighbours' interior planes, calls vr_sdf_slab_mark_imported and continues until vr_sdf_slab_finished.
+ * max_it_global = min(max(global dims)/2, 127) (signed_distance_field.cpp:11). */
+typedef struct vr_sdf_slab vr_sdf_slab;
+int vr_sdf_slab_create(vr_ctx* ctx, const vr_volume* ext_slab, const vr_tf_rect* rects, int n_rects, int max_it_global,
+                       vr_sdf_slab** out);
+int vr_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* levels_done);
+void* vr_sdf_slab_bits(vr_sdf_slab* s);
+size_t vr_sdf_slab_plane_words(const vr_sdf_slab* s);
+int vr_sdf_slab_mark_imported(vr_sdf_slab* s);
+int vr_sdf_slab_finished(const vr_sdf_slab* s);
+int vr_sdf_slab_download(vr_sdf_slab* s, vr_ctx* ctx, int nx, int ny, int nz_ext, int z0, int nplanes, int8_t* out);
+void vr_sdf_slab_destroy(vr_sdf_slab* s);
+
 /* ---- instrumentation ---------------------------------------------------------------------------------- */
 /* When enabled the trace kernel also accumulates the per-sample counters of SURVEY.md §8(d):
  * {march steps, shading normals, env fetches, primary hits, admitted samples, samples}. */
