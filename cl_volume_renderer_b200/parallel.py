@@ -13,7 +13,7 @@ import numpy as np
 
 from . import api
 
-SDF_EXCHANGE_LEVELS = 6          # K: levels between two halo exchanges
+SDF_EXCHANGE_LEVELS = 14         # K: levels between two halo exchanges (9 swaps for the 125 levels of a >= 254^3 volume)
 SDF_HALO = SDF_EXCHANGE_LEVELS + 2
 
 

@@ -72,11 +72,10 @@ def main():
         def exchange(s):
             if world == 1:
                 return
-            ctx.synchronize()
             t = parallel.bits_tensor(s, dev)
             down, up = s.boundary_planes()
-            parallel.exchange_planes(t, down, up, rank, dist)
-            torch.cuda.synchronize()
+            with torch.cuda.stream(ext):   # stream-ordered after the wave kernels, no host synchronisation
+                parallel.exchange_planes(t, down, up, rank, dist)
 
         sdf_ms = []
         for rep in range(3):
