@@ -4,7 +4,6 @@
 #include <cstdarg>
 #include <cstring>
 #include <new>
-#include <set>
 #include "vr_internal.h"
 
 static thread_local char g_err[1024] = "";
@@ -207,7 +206,7 @@ extern "C" int vr_histogram(const vr_volume* v, int width, int height, const flo
   uint32_t* bins = nullptr;
   const size_t bytes = sizeof(uint32_t) * (size_t)width * height;
   VR_CUDA(pool_alloc(v->ctx, &bins, bytes));
-  int s = vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi);
+  int s = vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi, v->stats[0]);
   if (s == VR_OK) {
     cudaError_t e = cudaMemcpyAsync(bins_out, bins, bytes, cudaMemcpyDeviceToHost, v->ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(v->ctx->stream);
@@ -600,57 +599,25 @@ extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba
   float range[4];
   VR_TRY(vr_volume_clipped_stats(r->vol, range));
   uint32_t* bins = nullptr;
-  int32_t* lookup = nullptr;
+  int* scratch = nullptr;
   uchar4* img = nullptr;
-  std::vector<uint32_t> h(nb);
   int status = VR_OK;
   cudaError_t e = pool_alloc(ctx, &bins, nb * 4);
   if (e == cudaSuccess) e = pool_alloc(ctx, &img, nb * 4);
+  if (e == cudaSuccess) e = pool_alloc(ctx, &scratch, 2049 * sizeof(int));
   if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
   if (status == VR_OK)
     status = vrk_histogram(ctx, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height, range, bins, r->vol->zlo,
-                           r->vol->zhi);
+                           r->vol->zhi, r->vol->stats[0]);
+  // renderer.cpp:65-96 without the host round trip: rounding, distinct-value ranking and colouring stay on the device
+  if (status == VR_OK) status = vrk_tf_image(ctx, reinterpret_cast<int32_t*>(bins), scratch, width, height, img);
   if (status == VR_OK) {
-    e = cudaMemcpyAsync(h.data(), bins, nb * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaMemcpyAsync(rgba_out, img, nb * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
   }
-  std::vector<int32_t> lut;
-  if (status == VR_OK) {
-    // renderer.cpp:65-79: round every non-zero count down to two significant digits, collect the distinct values
-    std::set<int> hist;
-    for (int y = 0; y < height; ++y)
-      for (int x = 0; x < width; ++x) {
-        int value = (int)h[(size_t)x * height + y];
-        if (value != 0) {
-          int roundingpart = std::max((int)(pow(10, (std::floor(std::log10(value))) - 1)), (int)1);
-          int corrected = (int)(floor(value / roundingpart) * roundingpart);
-          h[(size_t)x * height + y] = (uint32_t)corrected;
-          hist.insert(corrected);
-        }
-      }
-    lut.assign(hist.begin(), hist.end());
-    if (lut.empty()) {
-      // renderer.cpp:84-86: the colour kernel is skipped, the frame keeps its zero initialisation
-      memset(rgba_out, 0, nb * 4);
-    } else {
-      e = pool_alloc(ctx, &lookup, lut.size() * 4);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(bins, h.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(lookup, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
-      if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
-      if (status == VR_OK)
-        status = vrk_tf_color_frame(ctx, reinterpret_cast<const int32_t*>(bins), lookup, (int)lut.size(), width, height,
-                                    img);
-      if (status == VR_OK) {
-        e = cudaMemcpyAsync(rgba_out, img, nb * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
-      }
-    }
-  }
+  pool_free(ctx, scratch);
   pool_free(ctx, bins);
-  pool_free(ctx, lookup);
   pool_free(ctx, img);
   return status;
 }

@@ -47,6 +47,7 @@ struct vr_ctx {
 // Device-side TF table, passed to kernels by value.
 struct TfTable {
   vr_tf_rect r[VR_TF_MAX_RECTS];
+  float e[VR_TF_MAX_RECTS][4];  // rgba / 255.0f (IEEE, evaluated on the host)
   int n;
   int needs_gradient;  // any clause carries a gradient test
 };
@@ -120,7 +121,7 @@ int vrk_clip(vr_ctx* ctx, const int16_t* src, int snx, int sny, int snz, const u
              int ny, int nz);
 int vrk_bilateral(vr_ctx* ctx, const int16_t* src, int16_t* dst, int nx, int ny, int nz);
 int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4],
-                  uint32_t* bins_dev, int zlo, int zhi);
+                  uint32_t* bins_dev, int zlo, int zhi, int vol_min_value = 0);
 struct vr_sdf_slab;
 int vrk_sdf_slab_create(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int max_it, vr_sdf_slab** out);
 int vrk_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* done);
@@ -131,8 +132,7 @@ int vrk_sdf_slab_level(const vr_sdf_slab* s);
 bool vrk_sdf_slab_finished(const vr_sdf_slab* s);
 int vrk_sdf_slab_assemble(vr_sdf_slab* s, int8_t* field);
 void vrk_sdf_slab_destroy(vr_sdf_slab* s);
-int vrk_tf_color_frame(vr_ctx* ctx, const int32_t* bins_dev, const int32_t* lookup_dev, int lookup_len, int width,
-                       int height, uchar4* out_dev);
+int vrk_tf_image(vr_ctx* ctx, int32_t* bins_dev, int* scratch_dev, int width, int height, uchar4* out_dev);
 int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field,
                   int* levels_out, int* max_it_out);
 size_t vrk_sdf_field_bytes(int nx, int ny, int nz);

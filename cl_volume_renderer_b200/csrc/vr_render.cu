@@ -385,8 +385,8 @@ __global__ void __launch_bounds__(128, 12) k_primary(const RenderParams p) {
 enum { M_IDLE = 0, M_SECOND = 2 };
 enum { EVP_NONE = 0, EVP_HIT = 1, EVP_EXIT = 2, EVP_SDF_NEG = 3, EVP_FARFACE = 4 };
 
-template <bool COUNT, bool REUSE>
-__global__ void __launch_bounds__(128, 12) k_trace_pt(const RenderParams p, unsigned* __restrict__ work_counter) {
+template <bool COUNT, bool REUSE, int CTAS>
+__global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, unsigned* __restrict__ work_counter) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int nx = p.vol.nx, ny = p.vol.ny, nz = p.vol.nz;
@@ -409,7 +409,8 @@ __global__ void __launch_bounds__(128, 12) k_trace_pt(const RenderParams p, unsi
   bool exhausted = false;
   unsigned c_steps = 0, c_normals = 0, c_env = 0, c_adm = 0;
 
-  auto colour = [&](int k) -> int { return clause_col ? p.tf.r[clause_col - 1].rgba[k] : 0; };
+  // colour(k) / 255.0f of the clause whose colour is current ({0,0,0,0} before any clause wrote it)
+  auto energy = [&](int k) -> float { return clause_col ? p.tf.e[clause_col - 1][k] : 0.0f; };
 
   for (;;) {
     bool need_bounce = false, reset_atten = false, need_start = false;
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(128, 12) k_trace_pt(const RenderParams p, unsi
           const bool more = pi < 10;
           if (ev == EVP_HIT) {
             if (COUNT) c_normals++;
-            er *= (float)colour(0) / 255.0f; eg *= (float)colour(1) / 255.0f; eb *= (float)colour(2) / 255.0f;
+            er *= energy(0); eg *= energy(1); eb *= energy(2);
             if (more) {  // at i == 10 the new ray (ray_marching.cl:64-67) is never marched and atten is reset next
               bn = -normalize3(grad);
               o = o + dv;
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(128, 12) k_trace_pt(const RenderParams p, unsi
         if (take) {  // ray_marching.cl:42-50 for o = 1
           x = h.xy & 0xFFFF; y = h.xy >> 16; seed = h.seed; voxel = h.voxel; clause_col = h.clause;
           base = h.base; normal = h.normal;
-          er = (float)colour(0) / 255.0f; eg = (float)colour(1) / 255.0f; eb = (float)colour(2) / 255.0f;
+          er = energy(0); eg = energy(1); eb = energy(2);
           bv0 = bv1 = bv2 = 0;
           po = 1; pi = 8;
           o = base;
@@ -526,7 +527,7 @@ __global__ void __launch_bounds__(128, 12) k_trace_pt(const RenderParams p, unsi
 
     // ---- the one bounce site: ray_bounce_fake_reflectance + `origin += normal*2` + attenuation ------------------------------------
     if (need_bounce) {
-      dv = hemisphere_reflective(bn, bseed, (float)colour(3) / 255.0f, (unsigned)x, (unsigned)y);
+      dv = hemisphere_reflective(bn, bseed, energy(3), (unsigned)x, (unsigned)y);
       o = o + bn * 2.0f;
       const float a = fabsf(dot3(dv, bn));
       atten = reset_atten ? a : atten * a;
@@ -664,11 +665,15 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     p.queue = nullptr; p.qcount = nullptr; p.qcap = 0;
     p.tf = r->tf_active;
     static int per_sm[4] = {0, 0, 0, 0};  // resident CTAs per SM of the k_trace_pt instantiations
+    static int pt_ctas = 12;              // VR_PT_CTAS: register budget of the production variant (8: 64 regs, 10: 48, 12: 40)
     if (!per_sm[0]) {
-      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_trace_pt<false, false>, 128, 0));
-      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_trace_pt<true, false>, 128, 0));
-      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_trace_pt<false, true>, 128, 0));
-      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_trace_pt<true, true>, 128, 0));
+      if (const char* e = getenv("VR_PT_CTAS")) pt_ctas = atoi(e) == 8 ? 8 : (atoi(e) == 10 ? 10 : 12);
+      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_trace_pt<false, false, 12>, 128, 0));
+      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_trace_pt<true, false, 12>, 128, 0));
+      if (pt_ctas == 8) VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_trace_pt<false, true, 8>, 128, 0));
+      else if (pt_ctas == 10) VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_trace_pt<false, true, 10>, 128, 0));
+      else VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_trace_pt<false, true, 12>, 128, 0));
+      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_trace_pt<true, true, 12>, 128, 0));
     }
     const size_t pixels = (size_t)r->W * rows * nframes;
     dim3 grid(div_up(r->W, 8), div_up(rows, 16), nframes);
@@ -706,16 +711,18 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
         VR_CUDA(cudaMemsetAsync(p.qcount + 1, 0, sizeof(unsigned), ctx->stream));
         const int v = r->count ? 3 : 2;
         const unsigned blocks = (unsigned)ctx->sm_count * std::max(1, per_sm[v]);
-        if (r->count) k_trace_pt<true, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else k_trace_pt<false, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        if (r->count) k_trace_pt<true, true, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        else if (pt_ctas == 8) k_trace_pt<false, true, 8><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        else if (pt_ctas == 10) k_trace_pt<false, true, 10><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        else k_trace_pt<false, true, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
       } else {
         r->primary_valid = false;
         VR_CUDA(cudaMemsetAsync(p.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
         if (r->count) k_trace<true, true><<<grid, 128, 0, ctx->stream>>>(p);
         else k_trace<false, true><<<grid, 128, 0, ctx->stream>>>(p);
         const unsigned blocks = (unsigned)ctx->sm_count * std::max(1, per_sm[r->count ? 1 : 0]);
-        if (r->count) k_trace_pt<true, false><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else k_trace_pt<false, false><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        if (r->count) k_trace_pt<true, false, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        else k_trace_pt<false, false, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         ctx->launches++;
       }
     } else {

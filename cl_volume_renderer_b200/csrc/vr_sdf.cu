@@ -442,10 +442,21 @@ __global__ void __launch_bounds__(256) k_sdf_events_v8(VolView vol, TfTable tf, 
     if (x < vol.nx) {
       const int4 q = __ldg(reinterpret_cast<const int4*>(vol.v + (size_t)row * vol.nx + x));
       const int w[4] = {q.x, q.y, q.z, q.w};
+      if (tf.n == 1) {  // the two forms the UI / the tests generate most: one rectangle or one threshold (warp-uniform branch)
+        const bool thr = tf.r[0].flags & VR_TF_THRESHOLD;
+        const float lo = tf.r[0].min_v, hi = tf.r[0].max_v;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int v = (int)(short)((unsigned)w[k >> 1] >> (16 * (k & 1)));
-        bits |= (tf_match(tf, v, 0) != 0 ? 1u : 0u) << k;
+        for (int k = 0; k < 8; ++k) {
+          const float fv = (float)(int)(short)((unsigned)w[k >> 1] >> (16 * (k & 1)));
+          const bool e = thr ? fv > lo : (fv >= lo && fv <= hi);
+          bits |= (e ? 1u : 0u) << k;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int v = (int)(short)((unsigned)w[k >> 1] >> (16 * (k & 1)));
+          bits |= (tf_match(tf, v, 0) != 0 ? 1u : 0u) << k;
+        }
       }
     }
     unsigned word = bits << (8 * (lane & 3));

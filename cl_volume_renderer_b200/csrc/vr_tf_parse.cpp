@@ -163,6 +163,12 @@ TfTable vr_make_tf_table(const vr_tf_rect* rects, int n) {
   for (int i = 0; i < n; ++i) {
     t.r[i] = rects[i];
     if (rects[i].flags & VR_TF_USE_GRADIENT) t.needs_gradient = 1;
+    // (float)colour / 255.0f as ray_marching.cl:43-45,53,69-71 evaluate it per sample: one IEEE division, done once here
+    for (int k = 0; k < 4; ++k) {
+      volatile float c = (float)rects[i].rgba[k];
+      volatile float q = c / 255.0f;
+      t.e[i][k] = q;
+    }
   }
   return t;
 }

@@ -255,70 +255,85 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_histogram(VolView vol, uint32_t*
 }
 
 // tf_sort_values, vectorised front end (nx % 8 == 0): same binning arithmetic per voxel, 8 voxels per thread.
-// CT-like volumes put most voxels into a handful of bins (air, soft tissue), and same-address atomics serialise in L2
-// (the first version spent 3.2 ms at 512^3 on them).  Counts are therefore aggregated three times before they reach
-// global memory: lanes of a warp that hit the same bin merge (__match_any_sync), persistent CTAs accumulate in a
-// shared-memory hash table (HKEYS slots, linear probing, overflow goes straight to global), and each CTA flushes its
-// table once at the end.
-#define HKEYS 4096
+// CT-like volumes put most voxels into a few hundred neighbouring bins (air / soft tissue, small gradients), and same-address
+// atomics serialise in L2 (the first version spent 3.2 ms at 512^3 on them; a shared-memory hash table with __match_any
+// merging 2.2 ms).  Persistent CTAs now count into a direct-mapped WINDOW of HWX x HWY bins in shared memory (plain shared
+// atomics, no matching, no probing) placed at the bin of (smallest value, gradient 0); voxels that fall outside the window
+// go to global memory directly; every CTA flushes its window once at the end.  Bit-identical counts: integer adds commute.
+#define HWX 64
+#define HWY 128
 __global__ void __launch_bounds__(VX* VY* VZ) k_histogram_v8(VolView vol, uint32_t* __restrict__ bins, int width, int height,
-                                                             float min_v, float max_v, float min_g, float max_g, int zlo, int zhi) {
-  __shared__ int hkey[HKEYS];
-  __shared__ unsigned hcnt[HKEYS];
+                                                             float min_v, float max_v, float min_g, float max_g, int zlo, int zhi,
+                                                             int wx0, int wy0) {
+  __shared__ unsigned win[HWX * HWY];
   const int tid = threadIdx.x + VX * (threadIdx.y + VY * threadIdx.z);
-  for (int i = tid; i < HKEYS; i += VX * VY * VZ) { hkey[i] = -1; hcnt[i] = 0; }
+  for (int i = tid; i < HWX * HWY; i += VX * VY * VZ) win[i] = 0;
   __syncthreads();
   const unsigned tx = div_up_dev(vol.nx, VX * 8), ty = div_up_dev(vol.ny, VY), tz = div_up_dev(vol.nz, VZ);
   const float value_range = max_v - min_v, gradient_range = max_g - min_g;
+  const long long nbins = (long long)width * height;
   for (unsigned t = blockIdx.x; t < tx * ty * tz; t += gridDim.x) {
     const int x0 = (int)(((t % tx) * VX + threadIdx.x) * 8);
     const int y = (int)(((t / tx) % ty) * VY + threadIdx.y);
     const int z = (int)((t / (tx * ty)) * VZ + threadIdx.z);
-    const bool in = x0 < vol.nx && y < vol.ny && z >= zlo && z < zhi;
-    Octet o;
-    if (in) o = load_octet(vol, x0, y, z);
+    if (!(x0 < vol.nx && y < vol.ny && z >= zlo && z < zhi)) continue;
+    const Octet o = load_octet(vol, x0, y, z);
+    // a thread's 8 voxels often share a bin (air, the inside of a homogeneous object): run-length encode them, and merge
+    // equal out-of-window bins across the warp, so that a hot bin anywhere in the grid costs one global atomic per warp
+    long long run = -1;
+    unsigned run_n = 0;
+    int run_w = -1;
+    auto flush = [&]() {
+      if (!run_n) return;
+      if (run_w >= 0) atomicAdd(&win[run_w], run_n);
+      else {
+        const unsigned peers = __match_any_sync(__activemask(), run);
+        const unsigned total = __reduce_add_sync(peers, run_n);
+        if ((tid & 31) == __ffs(peers) - 1) atomicAdd(bins + run, total);
+      }
+    };
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
+      const float g = sqrtf(grad_sq(o, k));
       long long flat = -1;
-      if (in) {
-        const float g = sqrtf(grad_sq(o, k));
-        if (!(g > max_g) && !((float)o.c[k] > max_v)) {
-          const int px = f2i(roundf((((float)o.c[k] - min_v) / value_range) * (float)width));
-          const int py = f2i(roundf(((g - min_g) / gradient_range) * (float)height));
-          flat = (long long)px * height + py;
-          if (flat < 0 || flat >= (long long)width * height) flat = -1;
-        }
+      int w = -1;
+      if (!(g > max_g || (float)o.c[k] > max_v)) {
+        const int px = f2i(roundf((((float)o.c[k] - min_v) / value_range) * (float)width));
+        const int py = f2i(roundf(((g - min_g) / gradient_range) * (float)height));
+        flat = (long long)px * height + py;
+        if (flat < 0 || flat >= nbins) flat = -1;
+        const unsigned wx = (unsigned)(px - wx0), wy = (unsigned)(py - wy0);
+        if (flat >= 0 && wx < HWX && wy < HWY && py < height) w = (int)(wx * HWY + wy);
       }
-      const unsigned active = __ballot_sync(0xffffffffu, flat >= 0);
-      if (flat >= 0) {
-        const unsigned peers = __match_any_sync(active, (int)flat);
-        if ((tid & 31) == __ffs(peers) - 1) {
-          const int key = (int)flat;
-          const unsigned c = (unsigned)__popc(peers);
-          unsigned slot = ((unsigned)key * 2654435761u) >> 20;  // 12 bits
-          bool done = false;
-          for (int probe = 0; probe < 8 && !done; ++probe, slot = (slot + 1) & (HKEYS - 1)) {
-            const int old = atomicCAS(&hkey[slot], -1, key);
-            if (old == -1 || old == key) { atomicAdd(&hcnt[slot], c); done = true; }
-          }
-          if (!done) atomicAdd(bins + key, c);
-        }
+      if (flat != run) {
+        flush();
+        run = flat; run_w = w; run_n = 0;
       }
+      if (flat >= 0) ++run_n;
     }
+    flush();
   }
   __syncthreads();
-  for (int i = tid; i < HKEYS; i += VX * VY * VZ)
-    if (hkey[i] >= 0 && hcnt[i]) atomicAdd(bins + hkey[i], hcnt[i]);
+  for (int i = tid; i < HWX * HWY; i += VX * VY * VZ) {
+    const unsigned c = win[i];
+    if (c) atomicAdd(bins + (long long)(wx0 + i / HWY) * height + (wy0 + i % HWY), c);  // non-zero only for bins inside the grid
+  }
 }
 
 int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4],
-                  uint32_t* bins_dev, int zlo, int zhi) {
+                  uint32_t* bins_dev, int zlo, int zhi, int vol_min_value) {
   VR_CUDA(cudaMemsetAsync(bins_dev, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
   VolView v{vol, nx, ny, nz};
   if (nx % 8 == 0) {
     const size_t tiles = (size_t)div_up(nx, VX * 8) * div_up(ny, VY) * div_up(nz, VZ);
     dim3 grid((unsigned)std::min<size_t>(tiles, (size_t)ctx->sm_count * 6)), block(VX, VY, VZ);
-    k_histogram_v8<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3], zlo, zhi);
+    // window origin: the bin of the smallest value at gradient 0 (same arithmetic as the kernel), clamped into the grid
+    const float vr = range[1] - range[0], gr = range[3] - range[2];
+    int wx0 = 0, wy0 = 0;
+    if (vr > 0.0f) wx0 = std::max(0, std::min(width - 1, (int)roundf(((float)vol_min_value - range[0]) / vr * (float)width)));
+    if (gr > 0.0f) wy0 = std::max(0, std::min(height - 1, (int)roundf((0.0f - range[2]) / gr * (float)height)));
+    k_histogram_v8<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3], zlo, zhi, wx0,
+                                                   wy0);
   } else {
     dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
     k_histogram<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3], zlo, zhi);
@@ -328,34 +343,76 @@ int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int w
   return VR_OK;
 }
 
-// ---- tf_flush_color_frame: histogram.cl:34-69 -------------------------------------------------------------------
-// The reference searches the sorted lookup linearly per pixel; the lookup is sorted ascending (std::set,
-// renderer.cpp:65-89) so a binary search returns the same rank.
-__global__ void __launch_bounds__(256) k_tf_color_frame(const int32_t* __restrict__ bins,
-                                                        const int32_t* __restrict__ lookup, int lookup_len, int width,
-                                                        int height, uchar4* __restrict__ out) {
+// ---- tf_flush_color_frame: histogram.cl:34-69 — see k_tf_color_frame_ranked below ----------------------------------------------
+// ---- render_tf on the device -------------------------------------------------------------------------
+// renderer.cpp:65-96 pulls the bins to the host, rounds every non-zero count down to two significant digits, collects the
+// distinct values in a std::set, pushes bins + set back and lets the colour kernel search the set.  A rounded count is
+// (leading one or two digits) x 10^d, so it has a CODE d*100 + digits < 1000 that orders like the value: mark the codes that
+// occur, prefix-sum the marks into ranks, colour by rank.  No host round trip, no search.  The integer rounding equals the
+// reference's double pow/log10/floor expression for every count < 2^31 (tests/test_oracle_cpu.py checks it).
+__device__ __forceinline__ int tf_round_code(int v, int* corrected) {
+  int p = 1, d = 0;
+  while (v / p >= 100) { p *= 10; ++d; }   // p = max(10^(floor(log10 v) - 1), 1)
+  const int lead = v / p;
+  *corrected = lead * p;
+  return d * 100 + lead;
+}
+__global__ void __launch_bounds__(256) k_tf_round_mark(int32_t* __restrict__ bins, size_t n, int* __restrict__ flags) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = bins[i];
+    if (v != 0) {
+      int c;
+      flags[tf_round_code(v, &c)] = 1;
+      bins[i] = c;
+    }
+  }
+}
+// one block of 1024 threads: rank[code] = number of marked codes below it; rank[1024] = number of marked codes
+__global__ void __launch_bounds__(1024) k_tf_rank(const int* __restrict__ flags, int* __restrict__ rank) {
+  __shared__ int s[1024];
+  const int t = threadIdx.x;
+  const int f = flags[t];
+  s[t] = f;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = t >= o ? s[t - o] : 0;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  rank[t] = s[t] - f;
+  if (t == 1023) rank[1024] = s[t];
+}
+__global__ void __launch_bounds__(256) k_tf_color_frame_ranked(const int32_t* __restrict__ bins, const int* __restrict__ rank,
+                                                               int width, int height, uchar4* __restrict__ out) {
   const int px = blockIdx.x * 16 + (threadIdx.x & 15);
   const int py = blockIdx.y * 16 + (threadIdx.x >> 4);
   if (px >= width || py >= height) return;
-  const int value = bins[(size_t)px * height + (height - py - 1)];
-  int lo = 0, hi = lookup_len - 1, local_value = -1;
-  while (lo <= hi) {
-    int mid = (lo + hi) >> 1;
-    int lv = __ldg(lookup + mid);
-    if (lv == value) { local_value = mid; break; }
-    if (lv < value) lo = mid + 1; else hi = mid - 1;
+  const int len = rank[1024];
+  if (len == 0) {  // renderer.cpp:84-86: the colour kernel is skipped, the frame keeps its zero initialisation
+    out[(size_t)py * width + px] = make_uchar4(0, 0, 0, 0);
+    return;
   }
+  const int value = bins[(size_t)px * height + (height - py - 1)];
   int result = 0;
-  if (local_value > -1) result = f2i(20.0f + (((float)local_value) / (float)lookup_len) * (255.0f - 20.0f));
-  unsigned char c = (unsigned char)max(0, min(255, result));
-  out[(size_t)py * width + px] = make_uchar4(c, c, c, 255);
+  if (value != 0) {
+    int c;
+    const int local_value = rank[tf_round_code(value, &c)];
+    result = f2i(20.0f + (((float)local_value) / (float)len) * (255.0f - 20.0f));
+  }
+  const unsigned char g = (unsigned char)max(0, min(255, result));
+  out[(size_t)py * width + px] = make_uchar4(g, g, g, 255);
 }
 
-int vrk_tf_color_frame(vr_ctx* ctx, const int32_t* bins_dev, const int32_t* lookup_dev, int lookup_len, int width,
-                       int height, uchar4* out_dev) {
+// bins (counts) -> RGBA image, all on the device; scratch = 2049 ints
+int vrk_tf_image(vr_ctx* ctx, int32_t* bins_dev, int* scratch_dev, int width, int height, uchar4* out_dev) {
+  const size_t n = (size_t)width * height;
+  VR_CUDA(cudaMemsetAsync(scratch_dev, 0, 1024 * sizeof(int), ctx->stream));
+  k_tf_round_mark<<<(unsigned)std::min<size_t>(div_up(n, 256), (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(bins_dev, n, scratch_dev);
+  k_tf_rank<<<1, 1024, 0, ctx->stream>>>(scratch_dev, scratch_dev + 1024);
   dim3 grid(div_up(width, 16), div_up(height, 16));
-  k_tf_color_frame<<<grid, 256, 0, ctx->stream>>>(bins_dev, lookup_dev, lookup_len, width, height, out_dev);
-  ctx->launches++;
+  k_tf_color_frame_ranked<<<grid, 256, 0, ctx->stream>>>(bins_dev, scratch_dev + 1024, width, height, out_dev);
+  ctx->launches += 3;
   VR_CUDA(cudaGetLastError());
   return VR_OK;
 }

@@ -101,3 +101,24 @@ def test_render_accumulates_tokens_and_caps():
     tokens = r.cache.reshape(-1, 4)[:, 3]
     assert tokens.max() == 4  # cap honoured (utility.cl:20-31)
     assert (f[..., 3] == 1).any() and (f[..., 3] == 200).any()
+
+
+def test_tf_count_rounding_integer_form_equals_reference_expression():
+    """vr_render_tf rounds the bin counts on the device with integer arithmetic (k_tf_round_mark); the reference does
+    max((int)pow(10, floor(log10(v)) - 1), 1) and floor(v / r) * r in double (renderer.cpp:73-74).  Equal for every count around
+    the powers of ten and on a dense + random sample of [1, 2^31)."""
+    import math
+
+    def ref(v):
+        r = max(int(math.pow(10, math.floor(math.log10(v)) - 1)), 1)
+        return int(math.floor(v // r) * r)
+
+    def dev(v):
+        p = 1
+        while v // p >= 100:
+            p *= 10
+        return (v // p) * p
+
+    vals = [10 ** k + d for k in range(10) for d in range(-3, 4) if 1 <= 10 ** k + d < 2 ** 31]
+    vals += list(range(1, 30000)) + [int(x) for x in np.random.default_rng(0).integers(1, 2 ** 31 - 1, 50000)]
+    assert all(ref(v) == dev(v) for v in vals)

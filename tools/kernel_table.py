@@ -36,7 +36,7 @@ def report(path, n):
         a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v
     N = n ** 3; Nc = (n - 16) ** 3
     alg = {'k_fetch_stats_v8': 2 * N, 'k_fetch_stats': 2 * N, 'k_cache_reset': 8 * N, 'k_sdf_base': 3 * N, 'k_histogram_v8': 2 * N + 4 * 250000,
-           'k_histogram': 2 * N + 4 * 250000, 'k_sdf_unbrick': 2 * N, 'k_clip': 4 * Nc, 'k_bilateral': 4 * N, 'k_tf_color_frame': 8 * 250000}
+           'k_histogram': 2 * N + 4 * 250000, 'k_sdf_unbrick': 2 * N, 'k_clip': 4 * Nc, 'k_bilateral': 4 * N, 'k_tf_color_frame_ranked': 8 * 250000}
     out = {}
     for k, (cnt, us) in agg.items():
         b = alg.get(k)
