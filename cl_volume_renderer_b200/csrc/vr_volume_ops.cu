@@ -176,13 +176,30 @@ int vrk_clip(vr_ctx* ctx, const int16_t* src, int snx, int sny, int snz, const u
 }
 
 // ---- bilateral_filter: volume_filter.cl:5-11 + utility_filter.cl:38-62 ---------------------------------------
-// 125 taps per voxel, one exp per tap: bound by the SFU/FP32 pipes, not by HBM.  The block stages its
-// (TX+4)x(TY+4)x(TZ+4) neighbourhood in shared memory once so every tap is an LDS.
-// pow(d, 2.0f) is evaluated as d*d.
+// 125 taps per voxel, one exp per tap in the reference.  The block stages its (TX+4)x(TY+4)x(TZ+4) neighbourhood in shared
+// memory once so every tap is an LDS.  pow(d, 2.0f) is evaluated as d*d.
+// The weight exp(-posd - cold) takes few distinct values: posd depends on dx^2+dy^2+dz^2 (10 classes for a radius of 2), and the
+// voxels are integers, so cold = a*a/2 with a = |mid - local|; for a >= 16 the argument is <= -128 and expf underflows to
+// exactly 0.  Every block evaluates the 10 x 17 weights once with the SAME fp32 expression and the taps look them up:
+// bit-identical output, 125 LDS instead of 125 expf per voxel (9.2 -> see profiles/ at 512^3).
+#define BIL_A 17
+__device__ __forceinline__ int bil_class(int d2) {  // 0,1,2,3,4,5,6,8,9,12 -> 0..9
+  return d2 <= 6 ? d2 : (d2 == 8 ? 7 : (d2 == 9 ? 8 : 9));
+}
 __global__ void __launch_bounds__(TX* TY* TZ) k_bilateral(VolView vol, int16_t* __restrict__ dst) {
   __shared__ float tile[TZ + 4][TY + 4][TX + 4];
+  __shared__ float wtab[10 * BIL_A];
   const int bx = blockIdx.x * TX, by = blockIdx.y * TY, bz = blockIdx.z * TZ;
   const int tid = threadIdx.x + TX * (threadIdx.y + TY * threadIdx.z);
+  const float sigmas = 0.6f, sigmar = 1.0f;
+  if (tid < 10 * BIL_A) {
+    const int cls = tid / BIL_A, a = tid % BIL_A;
+    const int d2 = cls <= 6 ? cls : (cls == 7 ? 8 : (cls == 8 ? 9 : 12));
+    const float posd = ((float)d2) / (2 * sigmas * sigmas);
+    const float diff = (float)a;
+    const float cold = (diff * diff) / (2 * sigmar * sigmar);
+    wtab[tid] = a == BIL_A - 1 ? 0.0f : expf(-posd - cold);  // a >= 16: expf(<= -128) == 0
+  }
   for (int i = tid; i < (TZ + 4) * (TY + 4) * (TX + 4); i += TX * TY * TZ) {
     int lx = i % (TX + 4);
     int t = i / (TX + 4);
@@ -193,7 +210,6 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_bilateral(VolView vol, int16_t* 
   __syncthreads();
   const int x = bx + threadIdx.x, y = by + threadIdx.y, z = bz + threadIdx.z;
   if (x >= vol.nx || y >= vol.ny || z >= vol.nz) return;
-  const float sigmas = 0.6f, sigmar = 1.0f;
   const float mid = tile[threadIdx.z + 2][threadIdx.y + 2][threadIdx.x + 2];
   float out_colour = 0.0f, wp = 0.0f;
 #pragma unroll
@@ -202,11 +218,9 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_bilateral(VolView vol, int16_t* 
     for (int dy = -2; dy <= 2; ++dy)
 #pragma unroll
       for (int dx = -2; dx <= 2; ++dx) {
-        float local = tile[threadIdx.z + 2 + dz][threadIdx.y + 2 + dy][threadIdx.x + 2 + dx];
-        float posd = ((float)(dx * dx + dy * dy + dz * dz)) / (2 * sigmas * sigmas);
-        float diff = mid - local;
-        float cold = (diff * diff) / (2 * sigmar * sigmar);
-        float w = expf(-posd - cold);
+        const float local = tile[threadIdx.z + 2 + dz][threadIdx.y + 2 + dy][threadIdx.x + 2 + dx];
+        const int a = min(__float2int_rn(fabsf(mid - local)), BIL_A - 1);  // exact: both are integers of |value| < 2^15
+        const float w = wtab[bil_class(dx * dx + dy * dy + dz * dz) * BIL_A + a];
         wp += w;
         out_colour += local * w;
       }
