@@ -250,6 +250,20 @@ static int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, 
   if (e != cudaSuccess) { delete s; vr_set_error("vr_sdf_build: %s", cudaGetErrorString(e)); return VR_ERR_CUDA; }
   int st = vrk_sdf_build(ctx, vol->current(), vol->nx, vol->ny, vol->nz, tf, s->field, &s->levels, &s->max_it);
   if (st != VR_OK) { pool_free(ctx, s->field); delete s; return st; }
+  static const bool use_surf = getenv("VR_SDF_SURF") && atoi(getenv("VR_SDF_SURF"));
+  if (use_surf) {
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindSigned);
+    e = cudaMalloc3DArray(&s->arr, &desc, make_cudaExtent(vol->nx, vol->ny, vol->nz), cudaArraySurfaceLoadStore);
+    if (e == cudaSuccess) {
+      cudaResourceDesc rd{};
+      rd.resType = cudaResourceTypeArray;
+      rd.res.array.array = s->arr;
+      e = cudaCreateSurfaceObject(&s->surf, &rd);
+    }
+    if (e != cudaSuccess) { vr_set_error("vr_sdf_build: surface: %s", cudaGetErrorString(e)); vr_sdf_destroy(s); return VR_ERR_CUDA; }
+    st = vrk_sdf_to_surface(ctx, s->field, vol->nx, vol->ny, vol->nz, s->surf);
+    if (st != VR_OK) { vr_sdf_destroy(s); return st; }
+  }
   *out = s;
   return VR_OK;
 }
@@ -266,6 +280,8 @@ extern "C" void vr_sdf_destroy(vr_sdf* s) {
   cudaStreamSynchronize(s->ctx->stream);
   pool_free(s->ctx, s->field);
   cudaStreamSynchronize(s->ctx->stream);
+  if (s->surf) cudaDestroySurfaceObject(s->surf);
+  if (s->arr) cudaFreeArray(s->arr);
   delete s;
 }
 

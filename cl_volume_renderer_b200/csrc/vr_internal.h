@@ -78,6 +78,10 @@ struct vr_sdf {
   int nx = 0, ny = 0, nz = 0;
   int levels = 0;
   int max_it = 0;
+  // experiment (VR_SDF_SURF=1): the same int8 values in a 3-D CUDA array behind a surface object — hardware addressing and
+  // zero border for the marcher's per-step gather
+  cudaArray_t arr = nullptr;
+  cudaSurfaceObject_t surf = 0;
 };
 
 struct vr_renderer {
@@ -137,6 +141,7 @@ int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const
                   int* levels_out, int* max_it_out);
 size_t vrk_sdf_field_bytes(int nx, int ny, int nz);
 int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear);
+int vrk_sdf_to_surface(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, cudaSurfaceObject_t surf);
 int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels);
 #define VR_MAX_BATCH 64
 // trace `nframes` frames (seeds[0..nframes)) in ONE launch (gridDim.z = frame), then optionally resolve once

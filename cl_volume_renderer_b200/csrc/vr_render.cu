@@ -23,6 +23,7 @@
 struct RenderParams {
   VolView vol;
   SdfView sdf;
+  cudaSurfaceObject_t sdf_surf;  // VR_SDF_SURF=1: the field behind a surface object (k_trace_pt<.., SURF>)
   const uchar4* __restrict__ env;
   int env_w, env_h;
   uint32_t* __restrict__ cache;
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(128, 12) k_primary(const RenderParams p) {
 enum { M_IDLE = 0, M_SECOND = 2 };
 enum { EVP_NONE = 0, EVP_HIT = 1, EVP_EXIT = 2, EVP_SDF_NEG = 3, EVP_FARFACE = 4 };
 
-template <bool COUNT, bool REUSE, int CTAS>
+template <bool COUNT, bool REUSE, int CTAS, bool SURF = false>
 __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, unsigned* __restrict__ work_counter) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -533,7 +534,8 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
       atten = reset_atten ? a : atten * a;
     }
     if (need_start) {  // first half of march(), utility_ray.cl:148-150
-      d = p.sdf.at(f2i(o.x), f2i(o.y), f2i(o.z));
+      if (SURF) d = surf3Dread<signed char>(p.sdf_surf, f2i(o.x), f2i(o.y), f2i(o.z), cudaBoundaryModeZero);
+      else d = p.sdf.at(f2i(o.x), f2i(o.y), f2i(o.z));
       steps_left = 70;
       marching = true;
       ev = EVP_NONE;
@@ -548,12 +550,22 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
         if (COUNT) c_steps++;
         steps_left--;
         const int vx = ifloor(o.x), vy = ifloor(o.y), vz = ifloor(o.z);
-        const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
-        if (exited) { marching = false; ev = EVP_EXIT; }
-        else {
-          d = __ldg(p.sdf.f + p.sdf.addr(vx, vy, vz));
-          if (d <= 0) { marching = false; ev = d < 0 ? EVP_SDF_NEG : EVP_FARFACE; }
-          else if (steps_left == 0) { marching = false; ev = EVP_NONE; }
+        if (SURF) {
+          // the surface returns 0 outside the field (and real voxels are never 0): bounds only matter when the step ends
+          d = surf3Dread<signed char>(p.sdf_surf, vx, vy, vz, cudaBoundaryModeZero);
+          if (d <= 0) {
+            const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
+            marching = false;
+            ev = exited ? EVP_EXIT : (d < 0 ? EVP_SDF_NEG : EVP_FARFACE);
+          } else if (steps_left == 0) { marching = false; ev = EVP_NONE; }
+        } else {
+          const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
+          if (exited) { marching = false; ev = EVP_EXIT; }
+          else {
+            d = __ldg(p.sdf.f + p.sdf.addr(vx, vy, vz));
+            if (d <= 0) { marching = false; ev = d < 0 ? EVP_SDF_NEG : EVP_FARFACE; }
+            else if (steps_left == 0) { marching = false; ev = EVP_NONE; }
+          }
         }
       }
       const unsigned act = __ballot_sync(0xffffffffu, marching);
@@ -648,6 +660,7 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     RenderParams p;
     p.vol = VolView{r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz};
     p.sdf = SdfView{r->sdf->field, r->sdf->nx, r->sdf->ny, r->sdf->nz, r->sdf->nx / 8 + 1, r->sdf->ny / 8 + 1};
+    p.sdf_surf = r->sdf->surf;
     p.env = r->env->texels;
     p.env_w = r->env->w;
     p.env_h = r->env->h;
@@ -713,6 +726,7 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
         const unsigned blocks = (unsigned)ctx->sm_count * std::max(1, per_sm[v]);
         if (r->count) k_trace_pt<true, true, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else if (pt_ctas == 8) k_trace_pt<false, true, 8><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        else if (r->sdf->surf) k_trace_pt<false, true, 12, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else if (pt_ctas == 10) k_trace_pt<false, true, 10><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else k_trace_pt<false, true, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
       } else {

@@ -1053,17 +1053,34 @@ __device__ __forceinline__ void front_scatter(const FrontCtx& f, bool have, uint
     const bool first = xw == 0, last = xw == g.nxw - 1;
     const uint32_t c = (shl_clamped(nb, 0u, first) | shr_clamped(nb, 0u, last, g.lastbit)) & valid_mask(g, xw);
     const bool lbit = !first && (nb & 1u), rbit = !last && (nb >> 31);
+    // three batches of independent memory operations instead of a dependent chain per target (ncu: the chained version
+    // spent 64 % of its stall samples on long-scoreboard waits, 11 % issue-active): addresses, R filters, atomicOrs
+    uint32_t tc[4], tl[4], tr[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int yy = (q & 1) ? min(y + 1, g.ny - 1) : max(y - 1, 0), zz = (q & 2) ? min(z + 1, g.nz - 1) : max(z - 1, 0);
       const uint32_t tw = ((unsigned)zz * (unsigned)g.ny + (unsigned)yy) * (unsigned)g.nxw + (unsigned)xw;
       tws[q] = tw;
       tyz[q] = (unsigned)yy | ((unsigned)zz << 16);
-      // filter with the (possibly stale) R: bits already reached need no pending entry
-      const uint32_t t = c & ~f.R[tw];
-      if (t && atomicOr(f.Pnext + tw, t) == 0u) app |= 1u << (3 * q);
-      if (lbit && !(f.R[tw - 1] >> 31) && atomicOr(f.Pnext + tw - 1, 0x80000000u) == 0u) app |= 2u << (3 * q);
-      if (rbit && !(f.R[tw + 1] & 1u) && atomicOr(f.Pnext + tw + 1, 1u) == 0u) app |= 4u << (3 * q);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // filter with the (possibly stale) R: bits already reached need no pending entry
+      tc[q] = c ? (c & ~f.R[tws[q]]) : 0u;
+      tl[q] = lbit ? (0x80000000u & ~f.R[tws[q] - 1]) : 0u;
+      tr[q] = rbit ? (1u & ~f.R[tws[q] + 1]) : 0u;
+    }
+    uint32_t oc[4], ol[4], orr[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      oc[q] = tc[q] ? atomicOr(f.Pnext + tws[q], tc[q]) : 1u;
+      ol[q] = tl[q] ? atomicOr(f.Pnext + tws[q] - 1, tl[q]) : 1u;
+      orr[q] = tr[q] ? atomicOr(f.Pnext + tws[q] + 1, tr[q]) : 1u;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // whoever finds the pending word empty lists it
+      if (oc[q] == 0u) app |= 1u << (3 * q);
+      if (ol[q] == 0u) app |= 2u << (3 * q);
+      if (orr[q] == 0u) app |= 4u << (3 * q);
     }
   }
   const unsigned cnt = (unsigned)__popc(app);
@@ -1108,11 +1125,11 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_sdf_front(FrontCtx f, int lev
       y = (int)(ent.y & 0xFFFFu); z = (int)(ent.y >> 16);
       xw = (int)(w - ((unsigned)z * (unsigned)g.ny + (unsigned)y) * (unsigned)g.nxw);
       const uint32_t pend = Pcur[w], old = f.R[w];
+      e = __ldg(E + w);  // unconditionally: one round trip together with the two loads above
       Pcur[w] = 0u;
       nb = pend & ~old;
       if (nb) {
         f.R[w] = old | nb;
-        e = __ldg(E + w);
         rowbase = (unsigned long long)(field + (((size_t)(z >> 3) * g.by + (y >> 3)) * g.bx + (size_t)xw * 4) * BRV + ((z & 7) << 6) + ((y & 7) << 3));
       }
     }
@@ -1720,6 +1737,32 @@ void vrk_sdf_slab_destroy(vr_sdf_slab* s) {
   cudaFreeAsync(s->planes, s->ctx->stream);
   cudaStreamSynchronize(s->ctx->stream);
   delete s;
+}
+
+// bricked field -> 3-D array behind a surface object: one 8-byte brick row per thread
+__global__ void __launch_bounds__(256) k_sdf_to_surface(BrickDims g, const int8_t* __restrict__ field, cudaSurfaceObject_t surf) {
+  const size_t rows = (size_t)g.bx * g.by * g.bz * 64;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i >> 6;
+    const int in = (int)(i & 63);
+    const int bx = (int)(b % g.bx), by = (int)((b / g.bx) % g.by), bz = (int)(b / ((size_t)g.bx * g.by));
+    const int x0 = bx * 8, y = by * 8 + (in & 7), z = bz * 8 + (in >> 3);
+    if (x0 >= g.nx || y >= g.ny || z >= g.nz) continue;
+    const uint2 v = *reinterpret_cast<const uint2*>(field + i * 8);
+    if (x0 + 8 <= g.nx) surf3Dwrite(v, surf, x0, y, z);
+    else
+      for (int k = 0; x0 + k < g.nx; ++k)
+        surf3Dwrite((signed char)(((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 0xFF), surf, x0 + k, y, z);
+  }
+}
+
+int vrk_sdf_to_surface(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, cudaSurfaceObject_t surf) {
+  BrickDims g{nx, ny, nz, nx / BR + 1, ny / BR + 1, nz / BR + 1};
+  const size_t rows = (size_t)g.bx * g.by * g.bz * 64;
+  k_sdf_to_surface<<<(unsigned)std::min<size_t>(div_up(rows, 256), (size_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(g, field, surf);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
 }
 
 int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear) {
