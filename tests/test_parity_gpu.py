@@ -343,3 +343,32 @@ def test_sdf_alternative_builds_bit_exact(mode):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_render_odd_shapes_and_empty_tf(vr_ctx, both):
+    """Edge cases the reference leaves to luck: a frame that is not a multiple of its 8x8 work-groups (render has no bounds guard,
+    clw_function.hpp:235-237 asserts instead), a volume whose dims are not multiples of the brick / word sizes, an empty transfer
+    function (every pixel is environment), and a 1-voxel-thin volume."""
+    env = synth.synth_env(96, 48)
+    cases = [((45, 37, 29), 50, 37, synth.default_tf()), ((33, 70, 20), 61, 43, synth.threshold_tf(400)),
+             ((24, 24, 24), 40, 24, []), ((40, 1, 40), 48, 32, synth.threshold_tf(200))]
+    for dims, W, H, tf in cases:
+        v = synth.synth_ct(0, dims=dims)
+        vol = api.Volume(vr_ctx, v); e = api.EnvMap(vr_ctx, env)
+        r = api.Renderer(vr_ctx, W, H); r.image_set(vol, e); r.set_tf(tf); r.set_trace_mode(TRACE_MODE[0]); r.flush_changes()
+        ref = o.Renderer(v, env, tf, W, H)
+        assert np.array_equal(r.sdf_download(), ref.sdf)
+        m = float(max(dims))
+        pos = np.array([-0.8 * m, 0.9 * m, -0.7 * m], dtype=np.float32)
+        d = synth.camera_dir(0.9, 6.183)
+        seeds = synth.glibc_rand(3)
+        got = r.render_frames(pos, d, seeds)
+        for s in seeds:
+            want = ref.render_frame(pos, d, s)
+        assert np.array_equal(got[..., 3], want[..., 3])
+        if not tf:
+            assert (got[..., 3] == 200).all()
+        assert _psnr(got[..., :3], want[..., :3]) >= 45.0
+        gc, wc = r.cache_download().astype(np.int32), ref.cache.astype(np.int32)
+        assert np.array_equal(gc.reshape(-1, 4)[:, 3], wc.reshape(-1, 4)[:, 3])
+        r.close(); e.close(); vol.close()
