@@ -366,6 +366,45 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return samples_per_step * e2e_steps / float(tt.item()) / 1e6
 
+    # pipelined headless jobs: the volume of job k+1 is uploaded (vr_volume_upload_async, copy stream) while job k builds its
+    # SDF, renders its 64 spp and reads its frame back.  Every job still pays its own H2D + D2H inside the timed region;
+    # the copy simply no longer waits for the compute stream.
+    def time_e2e_pipelined(nsteps):
+        def job(v_ready, start_next):
+            en2 = api.EnvMap(ctx, env_pin.numpy())         # first: H2D copies are served in issue order by one copy engine
+            nxt = api.Volume(ctx, vol_pin.numpy(), async_upload=True) if start_next else None   # H2D 256 MiB + fetch_stats, async
+            r2 = api.Renderer(ctx, W, H)
+            r2.image_set(v_ready, en2)
+            r2.next_event_code_set(tf_code)
+            r2.set_token_cap(max(256 // world, 1))
+            r2.flush_changes()
+            hf = r2.host_frame()
+            if world == 1:
+                r2.render_frames(pos, d, seeds, out=hf)
+            else:
+                r2.render_frames(pos, d, seeds, readback=False)
+                r2.xchg_gather()
+                c2 = torch.as_tensor(_DevArray(r2.xchg_device_ptr, r2.xchg_bytes // 4, "<i4"), device=f"cuda:{local_rank}")
+                with torch.cuda.stream(ext):
+                    dist.all_reduce(c2)
+                r2.xchg_scatter()
+                api._check(api.lib().vr_renderer_resolve(r2.h, hf.ctypes.data_as(api.C.c_void_p)))
+            chk = int(hf[::97, ::89].sum())
+            r2.close(); en2.close(); v_ready.close()
+            return nxt, chk
+        v = api.Volume(ctx, vol_pin.numpy(), async_upload=True)
+        v, _ = job(v, True)                       # warm-up job; leaves the next volume in flight
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(nsteps):
+            v, _ = job(v, True)                   # nsteps uploads are issued inside the timed region
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
+        v.close()
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return samples_per_step * nsteps / float(tt.item()) / 1e6
+
     if os.environ.get("VR_E2E_BREAKDOWN"):
         for it in range(2):
             marks = []
@@ -390,7 +429,8 @@ def run_ours(args, rank, world, local_rank):
             api._check(api.lib().vr_renderer_resolve(r2.h, hf.ctypes.data_as(api.C.c_void_p))); m("resolve+readback")
             r2.close(); m("renderer_close"); en2.close(); v2.close(); m("scene_close")
             log(f"[rank {rank}] e2e breakdown: " + ", ".join(f"{n} {1e3*(t-marks[i][1]):.2f}ms" for i, (n, t) in enumerate(marks[1:])))
-    e2e_value = time_e2e(False)
+    e2e_sequential = time_e2e(False)
+    e2e_value = time_e2e_pipelined(2 * e2e_steps)
     e2e_interactive = time_e2e(True) if world == 1 else None
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ----
@@ -445,9 +485,13 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Msamples/s",
                     "h2d_bytes_per_step": int(vol_np.nbytes + env_np.nbytes), "d2h_bytes_per_step": int(W * H * 4),
-                    "steps": e2e_steps,
-                    "what": "per step: vr_volume_upload + vr_envmap_bind from pinned host memory, vr_renderer_flush (cache "
-                            "alloc/reset + SDF build), vr_render_frames(64 seeds), final frame read back to the host",
+                    "steps": 2 * e2e_steps,
+                    "what": "per step (one headless job): volume + env map uploaded from pinned host memory, vr_renderer_flush "
+                            "(cache alloc/reset + SDF build), vr_render_frames(64 seeds), final frame read back to the host; "
+                            "jobs are pipelined: vr_volume_upload_async copies job k+1's volume on the copy stream while job k "
+                            "computes (every job's H2D and D2H are inside the timed region)",
+                    "sequential": {"value": e2e_sequential, "unit": "Msamples/s", "steps": e2e_steps,
+                                   "what": "the same jobs one after the other with the blocking vr_volume_upload"},
                     "interactive": {"value": e2e_interactive, "unit": "Msamples/s", "d2h_bytes_per_step": int(W * H * 4 * SPP),
                                     "what": "same, but 64 x vr_render_frame with every frame read back (the reference UI's "
                                             "usage, renderer.cpp:131-158), vr_renderer_set_primary_reuse(2)"}},

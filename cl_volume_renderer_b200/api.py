@@ -41,6 +41,8 @@ SYMBOLS = {
     "vr_tf_parse": (C.c_int, [C.c_char_p, C.POINTER(TfRect), C.c_int, C.POINTER(C.c_int)]),
     "vr_tf_format": (C.c_int, [C.POINTER(TfRect), C.c_int, C.c_char_p, C.c_size_t]),
     "vr_volume_upload": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vr_volume_upload_async": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vr_volume_wait": (C.c_int, [_P]),
     "vr_volume_destroy": (None, [_P]),
     "vr_volume_stats": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "vr_volume_set_value_clip": (C.c_int, [_P, C.c_int, C.c_int]),
@@ -182,17 +184,26 @@ class Context:
 class Volume:
     """reference_volume (app/reference_volume.hpp:27-63)"""
 
-    def __init__(self, ctx, voxels, interior=None):
-        """interior=(z_lo, z_hi): `voxels` is a z-slab with halo planes; stats / histogram cover planes [z_lo, z_hi) only"""
+    def __init__(self, ctx, voxels, interior=None, async_upload=False):
+        """interior=(z_lo, z_hi): `voxels` is a z-slab with halo planes; stats / histogram cover planes [z_lo, z_hi) only.
+        async_upload: return at once (vr_volume_upload_async); `voxels` must not change until wait() / first use."""
         voxels = np.ascontiguousarray(voxels, dtype=np.int16)
         assert voxels.ndim == 3, "volume must be [nz, ny, nx]"
         nz, ny, nx = voxels.shape
         self.ctx = ctx
         self.h = _P()
-        if interior is None:
+        self._keep = voxels
+        if async_upload:
+            assert interior is None
+            _check(lib().vr_volume_upload_async(ctx.h, _vp(voxels), nx, ny, nz, C.byref(self.h)))
+        elif interior is None:
             _check(lib().vr_volume_upload(ctx.h, _vp(voxels), nx, ny, nz, C.byref(self.h)))
         else:
             _check(lib().vr_volume_upload_slab(ctx.h, _vp(voxels), nx, ny, nz, interior[0], interior[1], C.byref(self.h)))
+
+    def wait(self):
+        _check(lib().vr_volume_wait(self.h))
+        self._keep = None
 
     def download_planes(self, z0, nplanes):
         nx, ny, _ = self.dims()

@@ -65,6 +65,7 @@ extern "C" int vr_ctx_create(int device_ordinal, vr_ctx** out) {
   c->device = device_ordinal;
   c->sm_count = prop.multiProcessorCount;
   VR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  VR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   cudaMemPool_t pool;
   VR_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
   uint64_t keep = UINT64_MAX;
@@ -82,6 +83,7 @@ extern "C" void vr_ctx_destroy(vr_ctx* c) {
   cudaFree(c->scratch);
   cudaFreeHost(c->scratch_host);
   for (auto& b : c->pinned) cudaFreeHost(b.p);
+  cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -96,6 +98,22 @@ extern "C" void* vr_ctx_stream(vr_ctx* c) { return c ? (void*)c->stream : nullpt
 extern "C" uint64_t vr_ctx_launch_count(const vr_ctx* c) { return c ? c->launches : 0; }
 
 // ---- volume --------------------------------------------------------------------------------------------------
+// completes a vr_volume_upload_async: waits for the copy stream's event, takes the stats, releases the staging objects
+static int volume_finish(const vr_volume* cv) {
+  vr_volume* v = const_cast<vr_volume*>(cv);
+  if (!v || !v->pending) return VR_OK;
+  VR_CUDA(cudaEventSynchronize(v->ready));
+  memcpy(v->stats, v->stats_pin, sizeof(v->stats));
+  v->pending = false;
+  pinned_release(v->ctx, v->stats_pin);
+  v->stats_pin = nullptr;
+  pool_free(v->ctx, v->stats_dev);
+  v->stats_dev = nullptr;
+  cudaEventDestroy(v->ready);
+  v->ready = nullptr;
+  return VR_OK;
+}
+
 static int volume_upload_impl(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz, int zlo, int zhi, vr_volume** out) {
   VR_REQUIRE(ctx && voxels && out, "vr_volume_upload: null argument");
   VR_REQUIRE(nx > 0 && ny > 0 && nz > 0, "vr_volume_upload: dimensions must be positive");
@@ -120,6 +138,40 @@ extern "C" int vr_volume_upload(vr_ctx* ctx, const int16_t* voxels, int nx, int 
   return volume_upload_impl(ctx, voxels, nx, ny, nz, 0, nz, out);
 }
 
+// Asynchronous ingest (no reference counterpart: clw_image pushes are blocking, clw_image.hpp:206).  Returns at once; the copy
+// from (preferably pinned) host memory and fetch_stats run on the context's copy stream beside whatever the compute stream
+// is doing, e.g. the previous job's SDF build and frames.  `voxels` must stay valid and unchanged until vr_volume_wait (or
+// any other call that uses the volume, which waits implicitly) returns.
+extern "C" int vr_volume_upload_async(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz, vr_volume** out) {
+  VR_REQUIRE(ctx && voxels && out, "vr_volume_upload_async: null argument");
+  VR_REQUIRE(nx > 0 && ny > 0 && nz > 0, "vr_volume_upload_async: dimensions must be positive");
+  VR_REQUIRE((size_t)nx * ny * nz < ((size_t)1 << 32) - 1, "vr_volume_upload_async: more than 2^32-2 voxels");
+  VR_CUDA(cudaSetDevice(ctx->device));
+  vr_volume* v = new (std::nothrow) vr_volume();
+  if (!v) return VR_ERR_NOMEM;
+  v->ctx = ctx;
+  v->onx = v->nx = nx; v->ony = v->ny = ny; v->onz = v->nz = nz;
+  v->zlo = 0; v->zhi = nz;
+  const size_t bytes = v->count() * sizeof(int16_t);
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&v->original), bytes, ctx->copy_stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&v->stats_dev), 4 * sizeof(int32_t), ctx->copy_stream);
+  if (e == cudaSuccess) e = pinned_acquire(ctx, reinterpret_cast<void**>(&v->stats_pin), 64);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(v->original, voxels, bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+  if (e != cudaSuccess) { vr_set_error("vr_volume_upload_async: %s", cudaGetErrorString(e)); delete v; return VR_ERR_CUDA; }
+  int s = vrk_fetch_stats_enqueue(ctx, ctx->copy_stream, v->original, nx, ny, nz, 0, nz, v->stats_dev, v->stats_pin);
+  if (s != VR_OK) { delete v; return s; }
+  VR_CUDA(cudaEventRecord(v->ready, ctx->copy_stream));
+  v->pending = true;
+  *out = v;
+  return VR_OK;
+}
+
+extern "C" int vr_volume_wait(vr_volume* v) {
+  VR_REQUIRE(v, "vr_volume_wait: null argument");
+  return volume_finish(v);
+}
+
 // z-slab of a larger volume (multi-GPU sharding, no reference counterpart): planes [z_lo, z_hi) are this rank's, the planes
 // around them are halo — read by gradient taps, filter taps and the SDF wave, not counted by stats / histogram
 extern "C" int vr_volume_upload_slab(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz_ext, int z_lo, int z_hi,
@@ -129,6 +181,7 @@ extern "C" int vr_volume_upload_slab(vr_ctx* ctx, const int16_t* voxels, int nx,
 
 extern "C" int vr_volume_download_planes(const vr_volume* v, int z0, int nplanes, int16_t* out) {
   VR_REQUIRE(v && out && z0 >= 0 && nplanes > 0 && z0 + nplanes <= v->nz, "vr_volume_download_planes: bad argument");
+  VR_TRY(volume_finish(v));
   VR_CUDA(cudaSetDevice(v->ctx->device));
   const size_t plane = (size_t)v->nx * v->ny;
   VR_CUDA(cudaMemcpyAsync(out, v->current() + plane * z0, plane * nplanes * sizeof(int16_t), cudaMemcpyDeviceToHost,
@@ -140,6 +193,7 @@ extern "C" int vr_volume_download_planes(const vr_volume* v, int z0, int nplanes
 extern "C" void vr_volume_destroy(vr_volume* v) {
   if (!v) return;
   cudaSetDevice(v->ctx->device);
+  volume_finish(v);
   cudaStreamSynchronize(v->ctx->stream);
   pool_free(v->ctx, v->original);
   pool_free(v->ctx, v->cropped);
@@ -149,6 +203,7 @@ extern "C" void vr_volume_destroy(vr_volume* v) {
 
 extern "C" int vr_volume_stats(const vr_volume* v, int32_t out[4]) {
   VR_REQUIRE(v && out, "vr_volume_stats: null argument");
+  VR_TRY(volume_finish(v));
   memcpy(out, v->stats, sizeof(v->stats));
   return VR_OK;
 }
@@ -161,6 +216,7 @@ extern "C" int vr_volume_dims(const vr_volume* v, int out[3]) {
 
 extern "C" int vr_volume_clip(vr_volume* v, const uint32_t mn[3], const uint32_t mx[3]) {
   VR_REQUIRE(v && mn && mx, "vr_volume_clip: null argument");
+  VR_TRY(volume_finish(v));
   // reference_volume.cpp:57-59 asserts min < max; reads beyond the original are border reads (0)
   VR_REQUIRE(mn[0] < mx[0] && mn[1] < mx[1] && mn[2] < mx[2], "vr_volume_clip: min must be < max on every axis");
   VR_CUDA(cudaSetDevice(v->ctx->device));
@@ -179,6 +235,7 @@ extern "C" int vr_volume_clip(vr_volume* v, const uint32_t mn[3], const uint32_t
 
 extern "C" int vr_volume_filter(vr_volume* v) {
   VR_REQUIRE(v, "vr_volume_filter: null argument");
+  VR_TRY(volume_finish(v));
   VR_CUDA(cudaSetDevice(v->ctx->device));
   int16_t* dst = nullptr;
   VR_CUDA(pool_alloc(v->ctx, &dst, v->count() * sizeof(int16_t)));
@@ -193,6 +250,7 @@ extern "C" int vr_volume_filter(vr_volume* v) {
 
 extern "C" int vr_volume_download(const vr_volume* v, int16_t* out) {
   VR_REQUIRE(v && out, "vr_volume_download: null argument");
+  VR_TRY(volume_finish(v));
   VR_CUDA(cudaSetDevice(v->ctx->device));
   VR_CUDA(cudaMemcpyAsync(out, v->current(), v->count() * sizeof(int16_t), cudaMemcpyDeviceToHost, v->ctx->stream));
   VR_CUDA(cudaStreamSynchronize(v->ctx->stream));
@@ -201,6 +259,7 @@ extern "C" int vr_volume_download(const vr_volume* v, int16_t* out) {
 
 extern "C" int vr_histogram(const vr_volume* v, int width, int height, const float range[4], uint32_t* bins_out) {
   VR_REQUIRE(v && range && bins_out, "vr_histogram: null argument");
+  VR_TRY(volume_finish(v));
   VR_REQUIRE(width > 0 && height > 0 && (size_t)width * height < ((size_t)1 << 31), "vr_histogram: bad bin grid");
   VR_CUDA(cudaSetDevice(v->ctx->device));
   uint32_t* bins = nullptr;
@@ -270,6 +329,7 @@ static int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, 
 
 extern "C" int vr_sdf_build(vr_ctx* ctx, const vr_volume* vol, const vr_tf_rect* rects, int n_rects, vr_sdf** out) {
   VR_REQUIRE(ctx && vol && out && (rects || n_rects == 0), "vr_sdf_build: null argument");
+  VR_TRY(volume_finish(vol));
   VR_REQUIRE(n_rects >= 0 && n_rects <= VR_TF_MAX_RECTS, "vr_sdf_build: too many TF clauses");
   return sdf_build_impl(ctx, vol, vr_make_tf_table(rects, n_rects), out);
 }
@@ -307,6 +367,7 @@ extern "C" int vr_sdf_levels(const vr_sdf* s) { return s ? s->levels : 0; }
 extern "C" int vr_sdf_slab_create(vr_ctx* ctx, const vr_volume* ext_slab, const vr_tf_rect* rects, int n_rects, int max_it_global,
                                   vr_sdf_slab** out) {
   VR_REQUIRE(ctx && ext_slab && out && (rects || n_rects == 0), "vr_sdf_slab_create: null argument");
+  VR_TRY(volume_finish(ext_slab));
   VR_REQUIRE(n_rects >= 0 && n_rects <= VR_TF_MAX_RECTS, "vr_sdf_slab_create: too many TF clauses");
   VR_REQUIRE(max_it_global >= 1 && max_it_global <= 127, "vr_sdf_slab_create: max_it must be in [1,127]");
   VR_CUDA(cudaSetDevice(ctx->device));
@@ -418,6 +479,7 @@ extern "C" int vr_renderer_reset_cache(vr_renderer* r) {
 
 extern "C" int vr_renderer_flush(vr_renderer* r) {
   VR_REQUIRE(r && r->vol && r->env, "vr_renderer_flush: no scene bound (vr_renderer_set_scene)");
+  VR_TRY(volume_finish(r->vol));
   VR_REQUIRE(r->have_tf, "vr_renderer_flush: no transfer function set");
   VR_CUDA(cudaSetDevice(r->ctx->device));
   // renderer.cpp:29-30 — reallocate the cache only when the volume size changed
@@ -451,6 +513,7 @@ static int read_frame(vr_renderer* r, uint8_t* host_rgba) {
 extern "C" int vr_render_frame(vr_renderer* r, const float pos[3], const float dir[3], int32_t seed,
                                uint8_t* host_rgba) {
   VR_REQUIRE(r && pos && dir, "vr_render_frame: null argument");
+  VR_TRY(volume_finish(r->vol));
   VR_REQUIRE(r->sdf && r->cache, "vr_render_frame: call vr_renderer_flush first");
   VR_CUDA(cudaSetDevice(r->ctx->device));
   VR_TRY(vrk_render(r, pos, dir, &seed, 1, true, true));
@@ -460,6 +523,7 @@ extern "C" int vr_render_frame(vr_renderer* r, const float pos[3], const float d
 extern "C" int vr_render_frames(vr_renderer* r, const float pos[3], const float dir[3], const int32_t* seeds,
                                 int n_frames, uint8_t* host_rgba) {
   VR_REQUIRE(r && pos && dir && seeds && n_frames > 0, "vr_render_frames: bad argument");
+  VR_TRY(volume_finish(r->vol));
   VR_REQUIRE(r->sdf && r->cache, "vr_render_frames: call vr_renderer_flush first");
   VR_CUDA(cudaSetDevice(r->ctx->device));
   // Only the last frame is observable, so the traces of a batch share one launch (their samples commute: integer
@@ -599,6 +663,7 @@ extern "C" int vr_volume_set_gradient_clip(vr_volume* v, int lo, int hi) {
 // get_volume_stats(), reference_volume.cpp:82-88,110-112
 extern "C" int vr_volume_clipped_stats(const vr_volume* v, float out[4]) {
   VR_REQUIRE(v && out, "vr_volume_clipped_stats: null argument");
+  VR_TRY(volume_finish(v));
   out[0] = (float)std::max(v->value_clip[0], v->stats[0]);
   out[1] = (float)std::min(v->value_clip[1], v->stats[1]);
   out[2] = (float)std::max(v->gradient_clip[0], v->stats[2]);
@@ -608,6 +673,7 @@ extern "C" int vr_volume_clipped_stats(const vr_volume* v, float out[4]) {
 
 extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba_out) {
   VR_REQUIRE(r && r->vol && rgba_out, "vr_render_tf: no scene bound");
+  VR_TRY(volume_finish(r->vol));
   VR_REQUIRE(width > 0 && height > 0 && (size_t)width * height < ((size_t)1 << 31), "vr_render_tf: bad size");
   vr_ctx* ctx = r->ctx;
   VR_CUDA(cudaSetDevice(ctx->device));

@@ -36,6 +36,7 @@ struct vr_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // vr_volume_upload_async: host->device copy + fetch_stats beside the compute stream
   uint64_t launches = 0;
   int32_t* scratch = nullptr;  // small device scratch (counters, stats), 4 KiB
   int32_t* scratch_host = nullptr;  // pinned mirror
@@ -59,6 +60,12 @@ struct vr_volume {
   int16_t* cropped = nullptr;  // device, non-null once clipped (reference_volume.hpp:31-33)
   int nx = 0, ny = 0, nz = 0;  // dims of the current volume
   int32_t stats[4] = {0, 0, 0, 0};
+  // vr_volume_upload_async: copy + stats are in flight on ctx->copy_stream until `ready`; every API call that uses the
+  // volume finishes the upload first (volume_finish in vr_api.cu)
+  cudaEvent_t ready = nullptr;
+  bool pending = false;
+  int32_t* stats_dev = nullptr;
+  int32_t* stats_pin = nullptr;
   int zlo = 0, zhi = 0;  // planes the stats / histogram cover (whole volume unless uploaded as a z-slab with halo planes)
   int value_clip[2] = {INT32_MIN, INT32_MAX};     // reference_volume.hpp:35-36
   int gradient_clip[2] = {INT32_MIN, INT32_MAX};
@@ -121,6 +128,9 @@ struct vr_renderer {
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------------
 // stats / histogram over the planes [zlo, zhi) only (z-slab sharding: the other planes are halo for the gradient taps)
 int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int32_t out[4], int zlo, int zhi);
+// the same on any stream, without waiting: dev4 / pin4 = 4 ints of device scratch / pinned host memory that receive the result
+int vrk_fetch_stats_enqueue(vr_ctx* ctx, cudaStream_t stream, const int16_t* vol, int nx, int ny, int nz, int zlo, int zhi,
+                            int32_t* dev4, int32_t* pin4);
 int vrk_clip(vr_ctx* ctx, const int16_t* src, int snx, int sny, int snz, const uint32_t start[3], int16_t* dst, int nx,
              int ny, int nz);
 int vrk_bilateral(vr_ctx* ctx, const int16_t* src, int16_t* dst, int nx, int ny, int nz);

@@ -131,23 +131,29 @@ __global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8(VolView vol, int3
   }
 }
 
-int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int32_t out[4], int zlo, int zhi) {
-  int32_t init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};  // reference_volume.cpp:22-28
-  memcpy(ctx->scratch_host, init, sizeof(init));
-  VR_CUDA(cudaMemcpyAsync(ctx->scratch, ctx->scratch_host, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+int vrk_fetch_stats_enqueue(vr_ctx* ctx, cudaStream_t stream, const int16_t* vol, int nx, int ny, int nz, int zlo, int zhi,
+                            int32_t* dev4, int32_t* pin4) {
+  const int32_t init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};  // reference_volume.cpp:22-28
+  memcpy(pin4, init, sizeof(init));
+  VR_CUDA(cudaMemcpyAsync(dev4, pin4, sizeof(init), cudaMemcpyHostToDevice, stream));
   VolView v{vol, nx, ny, nz};
   if (nx % 8 == 0) {
     dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
-    k_fetch_stats_v8<<<grid, block, 0, ctx->stream>>>(v, ctx->scratch, zlo, zhi);
+    k_fetch_stats_v8<<<grid, block, 0, stream>>>(v, dev4, zlo, zhi);
   } else {
     dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
-    k_fetch_stats<<<grid, block, 0, ctx->stream>>>(v, ctx->scratch, zlo, zhi);
+    k_fetch_stats<<<grid, block, 0, stream>>>(v, dev4, zlo, zhi);
   }
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
-  VR_CUDA(cudaMemcpyAsync(ctx->scratch_host, ctx->scratch, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
+  VR_CUDA(cudaMemcpyAsync(pin4, dev4, sizeof(init), cudaMemcpyDeviceToHost, stream));
+  return VR_OK;
+}
+
+int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int32_t out[4], int zlo, int zhi) {
+  VR_TRY(vrk_fetch_stats_enqueue(ctx, ctx->stream, vol, nx, ny, nz, zlo, zhi, ctx->scratch, ctx->scratch_host));
   VR_CUDA(cudaStreamSynchronize(ctx->stream));
-  memcpy(out, ctx->scratch_host, sizeof(init));
+  memcpy(out, ctx->scratch_host, 4 * sizeof(int32_t));
   return VR_OK;
 }
 

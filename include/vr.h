@@ -76,6 +76,11 @@ int vr_tf_format(const vr_tf_rect* rects, int n, char* out, size_t cap);
 /* ctor reference_volume.cpp:11-44: upload (clw_image<short> push) + fetch_stats
  * (opencl_kernels/reference_volume_figures.cl:10-26). */
 int vr_volume_upload(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz, vr_volume** out);
+/* Asynchronous ingest: returns at once, the copy and fetch_stats run on a copy stream beside the compute stream (upload job
+ * k+1 while job k builds its SDF and renders).  `voxels` (pinned memory for a true overlap) must stay valid and unchanged
+ * until vr_volume_wait — or any other call that uses the volume, which waits implicitly — returns. */
+int vr_volume_upload_async(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz, vr_volume** out);
+int vr_volume_wait(vr_volume* vol);
 void vr_volume_destroy(vr_volume* vol);
 /* {min value, max value, min (int)|grad|, max (int)|grad|} over the ORIGINAL volume, unclamped
  * (reference_volume.cpp:33-37).  The clip getters (reference_volume.cpp:82-88) live in the C++ shim. */

@@ -372,3 +372,28 @@ def test_render_odd_shapes_and_empty_tf(vr_ctx, both):
         gc, wc = r.cache_download().astype(np.int32), ref.cache.astype(np.int32)
         assert np.array_equal(gc.reshape(-1, 4)[:, 3], wc.reshape(-1, 4)[:, 3])
         r.close(); e.close(); vol.close()
+
+
+def test_async_volume_upload_equals_blocking(vr_ctx):
+    """vr_volume_upload_async: copy + fetch_stats on the copy stream; results (stats, SDF, frame) equal the blocking upload, also
+    when a second upload is in flight while the first volume renders."""
+    import torch
+    v1, v2 = synth.synth_ct(64), synth.synth_ct(48, seed=3)
+    p1 = torch.empty(v1.shape, dtype=torch.int16, pin_memory=True); p1.numpy()[...] = v1
+    p2 = torch.empty(v2.shape, dtype=torch.int16, pin_memory=True); p2.numpy()[...] = v2
+    env = api.EnvMap(vr_ctx, synth.synth_env(128, 64))
+    a = api.Volume(vr_ctx, p1.numpy(), async_upload=True)
+    b = api.Volume(vr_ctx, p2.numpy(), async_upload=True)     # in flight while `a` is used
+    r = api.Renderer(vr_ctx, 96, 64); r.image_set(a, env); r.set_tf(synth.default_tf()); r.flush_changes()
+    pos, d = synth.default_camera(64)
+    fa = r.render_frames(pos, d, synth.glibc_rand(3))
+    sa = r.sdf_download()
+    ref = api.Volume(vr_ctx, v1)
+    r2 = api.Renderer(vr_ctx, 96, 64); r2.image_set(ref, env); r2.set_tf(synth.default_tf()); r2.flush_changes()
+    assert a.stats() == ref.stats() == o.fetch_stats(v1)
+    assert np.array_equal(sa, r2.sdf_download())
+    assert np.array_equal(fa, r2.render_frames(pos, d, synth.glibc_rand(3)))
+    b.wait()
+    assert b.stats() == o.fetch_stats(v2)
+    assert np.array_equal(b.download(), v2)
+    [x.close() for x in (r, r2, a, b, ref, env)]
