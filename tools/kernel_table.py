@@ -41,7 +41,7 @@ def report(path, n):
     for k, (cnt, us) in agg.items():
         b = alg.get(k)
         if k.startswith('k_sdf_level'): b = None
-        gbs = b / (us * 1e-6) / 1e9 if b else None
+        gbs = b * cnt / (us * 1e-6) / 1e9 if b else None  # alg bytes per launch x launches / total time
         out[k] = {"launches": cnt, "total_us": round(us, 1), "alg_bytes": b, "alg_GBps": round(gbs, 1) if gbs else None,
                   "frac_of_6461.5": round(gbs / 6461.5, 3) if gbs else None}
         print(f"{k:28s} n={cnt:4d} total={us:10.1f} us  alg={'%.0f MB' % (b/1e6) if b else '-':>10s}  {('%.0f GB/s' % gbs) if gbs else '':>10s} {('%.1f%%' % (100*gbs/6461.5)) if gbs else ''}")
