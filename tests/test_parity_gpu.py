@@ -397,3 +397,32 @@ def test_async_volume_upload_equals_blocking(vr_ctx):
     assert b.stats() == o.fetch_stats(v2)
     assert np.array_equal(b.download(), v2)
     [x.close() for x in (r, r2, a, b, ref, env)]
+
+
+def test_config1_256_uint8_volume_8spp_640x480(vr_ctx):
+    """BASELINE config 1 — the reference's CPU-runnable case: 256^3 "uint8" volume (values 0..255 stored as short, the only
+    type the loader accepts), SDF build + 8 spp at 640x480.  Full-size parity against the oracle."""
+    n, W, H = 256, 640, 480
+    v = synth.synth_ct(n, scale_to_u8=True)
+    assert v.min() >= 0 and v.max() <= 255
+    tf = [{"min_v": 85.0, "max_v": 204.0, "min_g": 0.0, "max_g": 4000.0, "flags": 0, "rgba": (255, 255, 255, 255)}]  # rect(500,1200) * 255/1500
+    envimg = synth.synth_env(512, 256)
+    vol = api.Volume(vr_ctx, v); env = api.EnvMap(vr_ctx, envimg)
+    r = api.Renderer(vr_ctx, W, H); r.image_set(vol, env); r.set_tf(tf); r.flush_changes()
+    ref = o.Renderer(v, envimg, tf, W, H)
+    assert np.array_equal(r.sdf_download(), ref.sdf)
+    assert vol.stats() == o.fetch_stats(v)
+    pos, d = synth.default_camera(n)
+    seeds = synth.glibc_rand(8)
+    r.enable_counters(True)
+    got = r.render_frames(pos, d, seeds)
+    for s in seeds:
+        want = ref.render_frame(pos, d, s)
+    c = r.counters()
+    assert c == dict(zip(["steps", "normals", "env", "primary_hits", "admitted", "samples"], [int(x) for x in ref.counters]))
+    gc, wc = r.cache_download().astype(np.int32), ref.cache.astype(np.int32)
+    assert np.array_equal(gc.reshape(-1, 4)[:, 3], wc.reshape(-1, 4)[:, 3])
+    assert (gc == wc).mean() >= 0.999 and np.abs(gc - wc).max() <= 64
+    assert np.array_equal(got[..., 3], want[..., 3]) and (got[..., 3] == 1).mean() > 0.03
+    assert _psnr(got[..., :3], want[..., :3]) >= 45.0
+    r.close(); env.close(); vol.close()
