@@ -474,7 +474,13 @@ extern "C" int vr_renderer_set_tf_code(vr_renderer* r, const char* src) {
 extern "C" int vr_renderer_reset_cache(vr_renderer* r) {
   VR_REQUIRE(r && r->cache, "vr_renderer_reset_cache: no cache (call vr_renderer_flush first)");
   VR_CUDA(cudaSetDevice(r->ctx->device));
-  return vrk_cache_reset(r->ctx, r->cache, r->cache_voxels);
+  static const bool always_full = getenv("VR_FULL_RESET") && atoi(getenv("VR_FULL_RESET"));
+  if (r->cache_exposed || always_full) r->cache_dirty = 2;
+  int st = VR_OK;
+  if (r->cache_dirty == 1) st = vrk_cache_reset_hits(r->ctx, r->cache, r->hit, (size_t)r->W * r->H);
+  else if (r->cache_dirty == 2) st = vrk_cache_reset(r->ctx, r->cache, r->cache_voxels);
+  if (st == VR_OK) r->cache_dirty = 0;
+  return st;
 }
 
 extern "C" int vr_renderer_flush(vr_renderer* r) {
@@ -494,6 +500,7 @@ extern "C" int vr_renderer_flush(vr_renderer* r) {
   }
   r->primary_valid = false;
   VR_TRY(vrk_cache_reset(r->ctx, r->cache, r->cache_voxels));  // renderer.cpp:32-35
+  r->cache_dirty = 0;
   r->tf_active = r->tf_pending;                                  // renderer.cpp:39
   vr_sdf* fresh = nullptr;                                       // renderer.cpp:42
   VR_TRY(sdf_build_impl(r->ctx, r->vol, r->tf_active, &fresh));
@@ -583,7 +590,10 @@ extern "C" int vr_renderer_set_rows(vr_renderer* r, int y0, int y1) {
   return VR_OK;
 }
 
-extern "C" void* vr_renderer_cache_device_ptr(const vr_renderer* r) { return r ? (void*)r->cache : nullptr; }
+extern "C" void* vr_renderer_cache_device_ptr(const vr_renderer* r) {
+  if (r) const_cast<vr_renderer*>(r)->cache_exposed = true;  // the caller may write anywhere: frame resets clear everything from now on
+  return r ? (void*)r->cache : nullptr;
+}
 extern "C" size_t vr_renderer_cache_bytes(const vr_renderer* r) { return r ? r->cache_voxels * 8 : 0; }
 extern "C" void* vr_renderer_frame_device_ptr(const vr_renderer* r) { return r ? (void*)r->frame : nullptr; }
 

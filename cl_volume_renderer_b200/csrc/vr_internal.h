@@ -107,6 +107,13 @@ struct vr_renderer {
   uchar4* frame = nullptr;    // device RGBA8
   uint8_t* frame_host = nullptr;  // pinned staging (used when the caller's buffer is pageable)
   int token_cap = 256;
+  // Which cache entries can be non-zero: 0 none (just reset), 1 only cache[hit[pix]] of the current `hit` buffer (every trace
+  // since the last reset used the camera / rows in dirty_pos.. below), 2 unknown (full reset needed).  A frame reset then
+  // clears W*H entries instead of 8 bytes x voxels (vr_renderer_reset_cache).
+  int cache_dirty = 2;
+  bool cache_exposed = false;  // vr_renderer_cache_device_ptr handed the raw pointer out: writes can no longer be tracked
+  float dirty_pos[3] = {0, 0, 0}, dirty_dir[3] = {0, 0, 0};
+  int dirty_rows[2] = {0, 0};
   bool count = false;
   unsigned long long* counters = nullptr;  // 6 x u64 on device (+ 2 spare words: [6] is k_trace_pt's work counter)
   // 0: k_trace alone (a thread per pixel for its whole life), 1: hybrid k_trace + k_trace_pt per frame,
@@ -153,6 +160,7 @@ size_t vrk_sdf_field_bytes(int nx, int ny, int nz);
 int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear);
 int vrk_sdf_to_surface(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, cudaSurfaceObject_t surf);
 int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels);
+int vrk_cache_reset_hits(vr_ctx* ctx, uint32_t* cache, const uint32_t* hit, size_t pixels);
 #define VR_MAX_BATCH 64
 // trace `nframes` frames (seeds[0..nframes)) in ONE launch (gridDim.z = frame), then optionally resolve once
 int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int32_t* seeds, int nframes, bool trace,

@@ -657,6 +657,15 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     VR_CUDA(cudaEventRecord(e0, ctx->stream));
   }
   if (trace) {
+    // cache dirtiness for the sparse frame reset: one camera / row window since the last reset -> only cache[hit[]] is touched
+    if (r->cache_dirty == 0) {
+      r->cache_dirty = 1;
+      memcpy(r->dirty_pos, pos, 12); memcpy(r->dirty_dir, dir, 12);
+      r->dirty_rows[0] = r->row0; r->dirty_rows[1] = r->row1;
+    } else if (r->cache_dirty == 1 && (memcmp(r->dirty_pos, pos, 12) || memcmp(r->dirty_dir, dir, 12) || r->dirty_rows[0] != r->row0 ||
+                                       r->dirty_rows[1] != r->row1)) {
+      r->cache_dirty = 2;
+    }
     RenderParams p;
     p.vol = VolView{r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz};
     p.sdf = SdfView{r->sdf->field, r->sdf->nx, r->sdf->ny, r->sdf->nz, r->sdf->nx / 8 + 1, r->sdf->ny / 8 + 1};

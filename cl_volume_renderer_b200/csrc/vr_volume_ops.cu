@@ -446,6 +446,21 @@ __global__ void __launch_bounds__(256) k_cache_reset(uint4* __restrict__ p, size
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
 }
 
+// frame reset when only the primary-hit voxels of the current hit buffer can be non-zero (the path tracer writes the cache at
+// primary hits only, ray_marching.cl:39,76): W*H scattered 8-byte stores instead of 8 bytes x voxels
+__global__ void __launch_bounds__(256) k_cache_reset_hits(uint2* __restrict__ cache, const uint32_t* __restrict__ hit, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t v = hit[i];
+  if (v != 0xFFFFFFFFu) cache[v] = make_uint2(0u, 0u);
+}
+int vrk_cache_reset_hits(vr_ctx* ctx, uint32_t* cache, const uint32_t* hit, size_t pixels) {
+  k_cache_reset_hits<<<div_up(pixels, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint2*>(cache), hit, pixels);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}
+
 int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels) {
   const size_t words = voxels * 2;
   const size_t n16 = words / 4;

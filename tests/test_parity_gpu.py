@@ -426,3 +426,31 @@ def test_config1_256_uint8_volume_8spp_640x480(vr_ctx):
     assert np.array_equal(got[..., 3], want[..., 3]) and (got[..., 3] == 1).mean() > 0.03
     assert _psnr(got[..., :3], want[..., :3]) >= 45.0
     r.close(); env.close(); vol.close()
+
+
+def test_frame_reset_clears_everything_sparse_or_full(vr_ctx, both):
+    """vr_renderer_reset_cache zeroes only cache[hit[pix]] when every trace since the last reset used one camera / row window,
+    and the whole cache otherwise: after a reset the cache must be all zero in every case, and results after it must equal a
+    fresh renderer's."""
+    r, ref, keep = _scene(vr_ctx, 48, 96, 64)
+    pos, d = synth.default_camera(48)
+    pos2 = pos + np.array([5.0, 2.0, -3.0], dtype=np.float32)
+    seeds = synth.glibc_rand(4)
+    r.render_frames(pos, d, seeds)                      # one camera -> sparse reset
+    assert r.cache_download().any()
+    r.reset_cache()
+    assert not r.cache_download().any()
+    r.reset_cache()                                     # nothing touched since: no-op, still zero
+    assert not r.cache_download().any()
+    r.render_frame(pos, d, 1); r.render_frame(pos2, d, 2)   # two cameras -> full reset
+    r.reset_cache()
+    assert not r.cache_download().any()
+    r.set_rows(8, 40); r.render_frame(pos, d, 3); r.set_rows(0, 64); r.render_frame(pos, d, 4)   # two row windows -> full reset
+    r.reset_cache()
+    assert not r.cache_download().any()
+    got = r.render_frames(pos, d, seeds)
+    for s in seeds:
+        want = ref.render_frame(pos, d, s)
+    assert np.array_equal(r.cache_download().reshape(-1, 4)[:, 3], ref.cache.reshape(-1, 4)[:, 3])
+    assert np.array_equal(got[..., 3], want[..., 3]) and _psnr(got[..., :3], want[..., :3]) >= 45.0
+    r.close(); [k.close() for k in keep]
