@@ -166,6 +166,9 @@ def run_reference(args, rank, world):
     Each step = a bounded sample of the workload: ONE frame (1 spp) of the same 1920x1080 / 512^3 scene."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it is allowed to (libgomp reads the variable
+    # when the library is loaded, which happens below)
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as o
     import ref_lib as R
@@ -488,6 +491,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as o
         import ref_lib as R
