@@ -6,12 +6,12 @@ CSRC := $(PKG)/csrc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 # --fmad=false: the numeric contract — no contraction, so ray positions match the oracle bit for bit
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo --fmad=false -Xcompiler -fPIC -ccbin $(CXX) -Xptxas -v
-CU_SRCS := $(CSRC)/vr_api.cu $(CSRC)/vr_volume_ops.cu $(CSRC)/vr_sdf.cu $(CSRC)/vr_render.cu
+CU_SRCS := $(CSRC)/vr_api.cu $(CSRC)/vr_volume_ops.cu $(CSRC)/vr_sdf.cu $(CSRC)/vr_sdf_variants.cu $(CSRC)/vr_render.cu
 CU_OBJS := $(CU_SRCS:.cu=.o)
 
 all: $(PKG)/libvr.so host oracle
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/vr_internal.h $(CSRC)/vr_device.cuh include/vr.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/vr_internal.h $(CSRC)/vr_device.cuh $(CSRC)/vr_sdf_common.cuh include/vr.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
 
 $(CSRC)/vr_tf_parse.o: $(CSRC)/vr_tf_parse.cpp $(CSRC)/vr_internal.h include/vr.h
