@@ -66,6 +66,9 @@ extern "C" int vr_ctx_create(int device_ordinal, vr_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   VR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   VR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  VR_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+  VR_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  VR_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   cudaMemPool_t pool;
   VR_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
   uint64_t keep = UINT64_MAX;
@@ -83,6 +86,9 @@ extern "C" void vr_ctx_destroy(vr_ctx* c) {
   cudaFree(c->scratch);
   cudaFreeHost(c->scratch_host);
   for (auto& b : c->pinned) cudaFreeHost(b.p);
+  cudaEventDestroy(c->ev_fork);
+  cudaEventDestroy(c->ev_join);
+  cudaStreamDestroy(c->aux_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -158,10 +164,22 @@ extern "C" int vr_volume_upload_async(vr_ctx* ctx, const int16_t* voxels, int nx
   if (e == cudaSuccess) e = pinned_acquire(ctx, reinterpret_cast<void**>(&v->stats_pin), 64);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ready, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMemcpyAsync(v->original, voxels, bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
-  if (e != cudaSuccess) { vr_set_error("vr_volume_upload_async: %s", cudaGetErrorString(e)); delete v; return VR_ERR_CUDA; }
-  int s = vrk_fetch_stats_enqueue(ctx, ctx->copy_stream, v->original, nx, ny, nz, 0, nz, v->stats_dev, v->stats_pin);
-  if (s != VR_OK) { delete v; return s; }
-  VR_CUDA(cudaEventRecord(v->ready, ctx->copy_stream));
+  int s = VR_OK;
+  if (e != cudaSuccess) { vr_set_error("vr_volume_upload_async: %s", cudaGetErrorString(e)); s = VR_ERR_CUDA; }
+  if (s == VR_OK) s = vrk_fetch_stats_enqueue(ctx, ctx->copy_stream, v->original, nx, ny, nz, 0, nz, v->stats_dev, v->stats_pin);
+  if (s == VR_OK && (e = cudaEventRecord(v->ready, ctx->copy_stream)) != cudaSuccess) {
+    vr_set_error("vr_volume_upload_async: %s", cudaGetErrorString(e));
+    s = VR_ERR_CUDA;
+  }
+  if (s != VR_OK) {  // undo whatever was set up; the copy stream may still hold work that touches the buffers
+    cudaStreamSynchronize(ctx->copy_stream);
+    if (v->original) cudaFreeAsync(v->original, ctx->copy_stream);
+    if (v->stats_dev) cudaFreeAsync(v->stats_dev, ctx->copy_stream);
+    if (v->stats_pin) pinned_release(ctx, v->stats_pin);
+    if (v->ready) cudaEventDestroy(v->ready);
+    delete v;
+    return s;
+  }
   v->pending = true;
   *out = v;
   return VR_OK;
@@ -490,7 +508,9 @@ extern "C" int vr_renderer_flush(vr_renderer* r) {
   VR_CUDA(cudaSetDevice(r->ctx->device));
   // renderer.cpp:29-30 — reallocate the cache only when the volume size changed
   const size_t voxels = r->vol->count();
+  bool fresh_cache = false, forked = false;
   if (voxels != r->cache_voxels) {
+    fresh_cache = true;
     VR_CUDA(cudaStreamSynchronize(r->ctx->stream));
     pool_free(r->ctx, r->cache);
     r->cache = nullptr;
@@ -499,11 +519,25 @@ extern "C" int vr_renderer_flush(vr_renderer* r) {
     r->cache_voxels = voxels;
   }
   r->primary_valid = false;
-  VR_TRY(vrk_cache_reset(r->ctx, r->cache, r->cache_voxels));  // renderer.cpp:32-35
+  // renderer.cpp:32-35 (buffer_reset) and :42 (new signed_distance_field) do not depend on each other: the reset is pure store
+  // bandwidth, the SDF build a chain of 125 latency-bound levels, so the reset runs on a second stream beside the build.
+  // A cache that was not reallocated and has seen one camera only is cleared through the hit buffer (vr_renderer_reset_cache).
+  vr_ctx* ctx = r->ctx;
+  if (!fresh_cache && !r->cache_exposed && r->cache_dirty <= 1) {
+    if (r->cache_dirty == 1) VR_TRY(vrk_cache_reset_hits(ctx, r->cache, r->hit, (size_t)r->W * r->H));
+  } else {
+    VR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    VR_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    VR_TRY(vrk_cache_reset(ctx, r->cache, r->cache_voxels, ctx->aux_stream));
+    VR_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    forked = true;
+  }
   r->cache_dirty = 0;
   r->tf_active = r->tf_pending;                                  // renderer.cpp:39
   vr_sdf* fresh = nullptr;                                       // renderer.cpp:42
-  VR_TRY(sdf_build_impl(r->ctx, r->vol, r->tf_active, &fresh));
+  int st = sdf_build_impl(ctx, r->vol, r->tf_active, &fresh);
+  if (forked) VR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // later work on the compute stream sees the reset cache
+  VR_TRY(st);
   vr_sdf_destroy(r->sdf);
   r->sdf = fresh;
   VR_CUDA(cudaMemsetAsync(r->hit, 0xFF, (size_t)r->W * r->H * 4, r->ctx->stream));

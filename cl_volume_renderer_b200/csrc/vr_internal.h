@@ -37,6 +37,8 @@ struct vr_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // vr_volume_upload_async: host->device copy + fetch_stats beside the compute stream
+  cudaStream_t aux_stream = nullptr;   // vr_renderer_flush: the (bandwidth-bound) cache reset beside the (latency-bound) SDF build
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint64_t launches = 0;
   int32_t* scratch = nullptr;  // small device scratch (counters, stats), 4 KiB
   int32_t* scratch_host = nullptr;  // pinned mirror
@@ -159,7 +161,7 @@ int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const
 size_t vrk_sdf_field_bytes(int nx, int ny, int nz);
 int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear);
 int vrk_sdf_to_surface(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, cudaSurfaceObject_t surf);
-int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels);
+int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels, cudaStream_t stream = nullptr);  // nullptr: the context's stream
 int vrk_cache_reset_hits(vr_ctx* ctx, uint32_t* cache, const uint32_t* hit, size_t pixels);
 #define VR_MAX_BATCH 64
 // trace `nframes` frames (seeds[0..nframes)) in ONE launch (gridDim.z = frame), then optionally resolve once

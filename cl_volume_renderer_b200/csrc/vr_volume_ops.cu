@@ -461,12 +461,13 @@ int vrk_cache_reset_hits(vr_ctx* ctx, uint32_t* cache, const uint32_t* hit, size
   return VR_OK;
 }
 
-int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels) {
+int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels, cudaStream_t stream) {
+  if (!stream) stream = ctx->stream;
   const size_t words = voxels * 2;
   const size_t n16 = words / 4;
   const int ntail = (int)(words - n16 * 4);
   unsigned blocks = (unsigned)std::min<size_t>(std::max<size_t>(div_up(n16, 256), 1), (size_t)ctx->sm_count * 8);
-  k_cache_reset<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(cache), n16, cache + n16 * 4, ntail);
+  k_cache_reset<<<blocks, 256, 0, stream>>>(reinterpret_cast<uint4*>(cache), n16, cache + n16 * 4, ntail);
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
   return VR_OK;
