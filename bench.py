@@ -90,7 +90,7 @@ class ClockSampler:
                     self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
                 except Exception:
                     pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def start(self):
         if self.nvml:
