@@ -48,7 +48,7 @@ def peaks():
 
 class ClockSampler:
     """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region of the default run is
-    ~15 ms, shorter than one `nvidia-smi -lms` period, so the clocks are polled through NVML in a thread (every ~2 ms);
+    ~15 ms, shorter than one `nvidia-smi -lms` period, so the clocks are polled through NVML in a thread (every ~1 ms);
     `nvidia-smi --query-gpu` is the fallback when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -122,7 +122,7 @@ class ClockSampler:
             names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
             reasons = sorted(k for k, bit in names.items() if self.reason_bits & bit)
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": mx, "reasons": reasons,
-                    "samples": len(self.sm), "source": "NVML polled every 2 ms during the timed region"}
+                    "samples": len(self.sm), "source": "NVML polled every 1 ms during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)

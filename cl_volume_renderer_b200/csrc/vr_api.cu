@@ -86,6 +86,7 @@ extern "C" void vr_ctx_destroy(vr_ctx* c) {
   cudaFree(c->scratch);
   cudaFreeHost(c->scratch_host);
   for (auto& b : c->pinned) cudaFreeHost(b.p);
+  for (auto& a : c->sdf_arrays) { cudaDestroySurfaceObject(a.surf); cudaFreeArray(a.arr); }
   cudaEventDestroy(c->ev_fork);
   cudaEventDestroy(c->ev_join);
   cudaStreamDestroy(c->aux_stream);
@@ -325,22 +326,31 @@ static int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, 
   s->ctx = ctx; s->nx = vol->nx; s->ny = vol->ny; s->nz = vol->nz;
   cudaError_t e = pool_alloc(ctx, &s->field, vrk_sdf_field_bytes(vol->nx, vol->ny, vol->nz));
   if (e != cudaSuccess) { delete s; vr_set_error("vr_sdf_build: %s", cudaGetErrorString(e)); return VR_ERR_CUDA; }
-  int st = vrk_sdf_build(ctx, vol->current(), vol->nx, vol->ny, vol->nz, tf, s->field, &s->levels, &s->max_it);
-  if (st != VR_OK) { pool_free(ctx, s->field); delete s; return st; }
-  static const bool use_surf = getenv("VR_SDF_SURF") && atoi(getenv("VR_SDF_SURF"));
+  static const bool use_surf = !(getenv("VR_SDF_SURF") && !atoi(getenv("VR_SDF_SURF")));
   if (use_surf) {
-    cudaChannelFormatDesc desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindSigned);
-    e = cudaMalloc3DArray(&s->arr, &desc, make_cudaExtent(vol->nx, vol->ny, vol->nz), cudaArraySurfaceLoadStore);
-    if (e == cudaSuccess) {
-      cudaResourceDesc rd{};
-      rd.resType = cudaResourceTypeArray;
-      rd.res.array.array = s->arr;
-      e = cudaCreateSurfaceObject(&s->surf, &rd);
+    for (auto& a : ctx->sdf_arrays)
+      if (!a.in_use && a.nx == vol->nx && a.ny == vol->ny && a.nz == vol->nz) { a.in_use = true; s->arr = a.arr; s->surf = a.surf; break; }
+    if (!s->arr) {
+      cudaChannelFormatDesc desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindSigned);
+      e = cudaMalloc3DArray(&s->arr, &desc, make_cudaExtent(vol->nx, vol->ny, vol->nz), cudaArraySurfaceLoadStore);
+      if (e == cudaSuccess) {
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = s->arr;
+        e = cudaCreateSurfaceObject(&s->surf, &rd);
+      }
+      if (e != cudaSuccess) {
+        if (s->arr) cudaFreeArray(s->arr);
+        pool_free(ctx, s->field);
+        delete s;
+        vr_set_error("vr_sdf_build: surface: %s", cudaGetErrorString(e));
+        return VR_ERR_CUDA;
+      }
+      ctx->sdf_arrays.push_back({s->arr, s->surf, vol->nx, vol->ny, vol->nz, true});
     }
-    if (e != cudaSuccess) { vr_set_error("vr_sdf_build: surface: %s", cudaGetErrorString(e)); vr_sdf_destroy(s); return VR_ERR_CUDA; }
-    st = vrk_sdf_to_surface(ctx, s->field, vol->nx, vol->ny, vol->nz, s->surf);
-    if (st != VR_OK) { vr_sdf_destroy(s); return st; }
   }
+  int st = vrk_sdf_build(ctx, vol->current(), vol->nx, vol->ny, vol->nz, tf, s->field, &s->levels, &s->max_it, s->surf);
+  if (st != VR_OK) { vr_sdf_destroy(s); return st; }
   *out = s;
   return VR_OK;
 }
@@ -358,8 +368,8 @@ extern "C" void vr_sdf_destroy(vr_sdf* s) {
   cudaStreamSynchronize(s->ctx->stream);
   pool_free(s->ctx, s->field);
   cudaStreamSynchronize(s->ctx->stream);
-  if (s->surf) cudaDestroySurfaceObject(s->surf);
-  if (s->arr) cudaFreeArray(s->arr);
+  for (auto& a : s->ctx->sdf_arrays)   // the array goes back to the context's cache
+    if (a.arr == s->arr) a.in_use = false;
   delete s;
 }
 

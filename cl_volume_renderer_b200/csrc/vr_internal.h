@@ -45,6 +45,9 @@ struct vr_ctx {
   // pinned host frame buffers are recycled across renderers: cudaMallocHost / cudaFreeHost cost milliseconds each
   struct PinnedBuf { void* p; size_t bytes; bool in_use; };
   std::vector<PinnedBuf> pinned;
+  // 3-D arrays (+ surface objects) of the SDF are recycled by size as well: cudaMalloc3DArray / cudaFreeArray synchronise
+  struct SdfArray { cudaArray_t arr; cudaSurfaceObject_t surf; int nx, ny, nz; bool in_use; };
+  std::vector<SdfArray> sdf_arrays;
 };
 
 // Device-side TF table, passed to kernels by value.
@@ -87,8 +90,8 @@ struct vr_sdf {
   int nx = 0, ny = 0, nz = 0;
   int levels = 0;
   int max_it = 0;
-  // experiment (VR_SDF_SURF=1): the same int8 values in a 3-D CUDA array behind a surface object — hardware addressing and
-  // zero border for the marcher's per-step gather
+  // the same int8 values in a 3-D CUDA array behind a surface object: hardware addressing and zero border for the per-step
+  // gather of k_trace_pt (VR_SDF_SURF=0 turns it off; the bricked field stays the source for everything else)
   cudaArray_t arr = nullptr;
   cudaSurfaceObject_t surf = 0;
 };
@@ -153,11 +156,12 @@ size_t vrk_sdf_slab_plane_words(const vr_sdf_slab* s);
 void vrk_sdf_slab_mark_imported(vr_sdf_slab* s);
 int vrk_sdf_slab_level(const vr_sdf_slab* s);
 bool vrk_sdf_slab_finished(const vr_sdf_slab* s);
-int vrk_sdf_slab_assemble(vr_sdf_slab* s, int8_t* field);
+int vrk_sdf_slab_assemble(vr_sdf_slab* s, int8_t* field, cudaSurfaceObject_t surf = 0);
 void vrk_sdf_slab_destroy(vr_sdf_slab* s);
 int vrk_tf_image(vr_ctx* ctx, int32_t* bins_dev, int* scratch_dev, int width, int height, uchar4* out_dev);
+// surf != 0: the field is also written into that surface (the production schedule does it in its assembly pass)
 int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field,
-                  int* levels_out, int* max_it_out);
+                  int* levels_out, int* max_it_out, cudaSurfaceObject_t surf = 0);
 size_t vrk_sdf_field_bytes(int nx, int ny, int nz);
 int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear);
 int vrk_sdf_to_surface(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, cudaSurfaceObject_t surf);

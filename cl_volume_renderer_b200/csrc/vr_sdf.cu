@@ -206,12 +206,12 @@ void vrk_sdf_slab_mark_imported(vr_sdf_slab* s) { s->all_active = true; }
 int vrk_sdf_slab_level(const vr_sdf_slab* s) { return s->level; }
 bool vrk_sdf_slab_finished(const vr_sdf_slab* s) { return s->level + 1 >= s->max_it; }
 
-int vrk_sdf_slab_assemble(vr_sdf_slab* s, int8_t* field) {
+int vrk_sdf_slab_assemble(vr_sdf_slab* s, int8_t* field, cudaSurfaceObject_t surf) {
   const WaveDims& w = s->w;
   const unsigned nxwf = (unsigned)((8 * w.bx + 31) / 32);
   const unsigned items = nxwf * (unsigned)w.by * (8u * (unsigned)w.bz);
   const unsigned bg = (unsigned)std::min<size_t>(div_up(items, 8), (size_t)s->ctx->sm_count * 16);
-  k_sdf_assemble<<<bg, 256, 0, s->ctx->stream>>>(w, s->max_it, s->E(), s->planes, (unsigned)s->nwords, field, nxwf, items);
+  k_sdf_assemble<<<bg, 256, 0, s->ctx->stream>>>(w, s->max_it, s->E(), s->planes, (unsigned)s->nwords, field, nxwf, items, surf);
   s->ctx->launches++;
   VR_CUDA(cudaGetLastError());
   return VR_OK;
@@ -255,14 +255,17 @@ int vrk_sdf_build_variant(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int n
                           int* max_it_out);  // vr_sdf_variants.cu
 
 int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field, int* levels_out,
-                  int* max_it_out) {
+                  int* max_it_out, cudaSurfaceObject_t surf) {
   static const char* mode = getenv("VR_SDF_MODE");
-  if (mode && *mode && strcmp(mode, "default")) return vrk_sdf_build_variant(ctx, vol, nx, ny, nz, tf, field, levels_out, max_it_out);
+  if (mode && *mode && strcmp(mode, "default")) {
+    VR_TRY(vrk_sdf_build_variant(ctx, vol, nx, ny, nz, tf, field, levels_out, max_it_out));
+    return surf ? vrk_sdf_to_surface(ctx, field, nx, ny, nz, surf) : VR_OK;
+  }
   const int max_it = std::min(std::max(nx, std::max(ny, nz)) / 2, 127);  // signed_distance_field.cpp:11
   vr_sdf_slab* s = nullptr;
   VR_TRY(vrk_sdf_slab_create(ctx, vol, nx, ny, nz, tf, max_it, &s));
   int st = vrk_sdf_slab_advance(s, max_it, nullptr);
-  if (st == VR_OK) st = vrk_sdf_slab_assemble(s, field);
+  if (st == VR_OK) st = vrk_sdf_slab_assemble(s, field, surf);
   // diagnostics: the last level that set a bit
   int levels = 0;
   if (st == VR_OK) {

@@ -137,7 +137,8 @@ static __global__ void __launch_bounds__(256) k_sdf_band_bits(WaveDims g, const 
 // lane = (8-bit piece) * 8 + row, so the 8 lanes of a piece write the 64 contiguous bytes of one z-slice of a brick.
 static __global__ void __launch_bounds__(256) k_sdf_assemble(WaveDims g, int max_it, const uint32_t* __restrict__ E,
                                                       const uint32_t* __restrict__ planes, unsigned nwords,
-                                                      int8_t* __restrict__ field, unsigned nxwf, unsigned items) {
+                                                      int8_t* __restrict__ field, unsigned nxwf, unsigned items,
+                                                             cudaSurfaceObject_t surf) {
   const unsigned lane = threadIdx.x & 31;
   const int yr = lane & 7, piece = lane >> 3;
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -173,6 +174,12 @@ static __global__ void __launch_bounds__(256) k_sdf_assemble(WaveDims g, int max
     }
     const size_t brick = ((size_t)(z >> 3) * g.by + yg) * g.bx + brick_x;
     *reinterpret_cast<uint2*>(field + brick * BRV + ((z & 7) << 6) + (yr << 3)) = make_uint2(out[0], out[1]);
+    if (surf && y < g.ny && z < g.nz) {  // the same 8 voxels into the 3-D array the marcher gathers from (no apron there)
+      const int x0 = brick_x * 8;
+      if (x0 + 8 <= g.nx) surf3Dwrite(make_uint2(out[0], out[1]), surf, x0, y, z);
+      else
+        for (int k = 0; x0 + k < g.nx; ++k) surf3Dwrite((signed char)((out[k >> 2] >> (8 * (k & 3))) & 0xFFu), surf, x0 + k, y, z);
+    }
   }
 }
 

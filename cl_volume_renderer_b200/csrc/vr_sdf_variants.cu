@@ -1109,7 +1109,7 @@ int vrk_sdf_build_variant(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int n
                                                          stamps[(it + 1) & 1], changed);
         ctx->launches++;
       }
-      k_sdf_assemble<<<bg, 256, 0, ctx->stream>>>(w, max_it, E, planes, (unsigned)nwords, field, nxwf, band_items);
+      k_sdf_assemble<<<bg, 256, 0, ctx->stream>>>(w, max_it, E, planes, (unsigned)nwords, field, nxwf, band_items, 0);
       ctx->launches++;
       VR_CUDA(cudaGetLastError());
       unsigned* hc = reinterpret_cast<unsigned*>(ctx->scratch_host);
