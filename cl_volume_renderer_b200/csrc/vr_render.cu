@@ -754,6 +754,8 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
         if (r->count) k_trace_pt<true, true, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else if (pt_ctas == 8) k_trace_pt<false, true, 8><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else if (pt_ctas == 16) k_trace_pt<false, true, 16><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        else if (r->sdf->surf && pt_ctas == 10) k_trace_pt<false, true, 10, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        else if (r->sdf->surf && pt_ctas == 8) k_trace_pt<false, true, 8, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else if (r->sdf->surf) k_trace_pt<false, true, 12, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else if (pt_ctas == 10) k_trace_pt<false, true, 10><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else k_trace_pt<false, true, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
