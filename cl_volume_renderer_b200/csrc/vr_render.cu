@@ -126,9 +126,9 @@ __device__ __forceinline__ uchar4 env_sample(const RenderParams& p, f3 d) {
   return __ldg(p.env + (size_t)iy * p.env_w + ix);
 }
 
-// get_hemisphere_direction_reflective, utility_sampling.cl:40-50
-__device__ __forceinline__ f3 hemisphere_reflective(f3 normal, int seed, float roughness, unsigned gx, unsigned gy) {
-  const uint32_t useed = (uint32_t)seed + (gx + 1u) * (gy + 1u);
+// get_hemisphere_direction_reflective, utility_sampling.cl:40-50; xyprod = (get_global_id(0) + 1) * (get_global_id(1) + 1)
+__device__ __forceinline__ f3 hemisphere_reflective_p(f3 normal, int seed, float roughness, unsigned xyprod) {
+  const uint32_t useed = (uint32_t)seed + xyprod;
   const int rx = (int)hash_u32(useed * 0x182205bdu);
   const int ry = (int)hash_u32(useed * 0xe8d052f3u);
   const int rz = (int)hash_u32(useed * 0xf1981dcfu);
@@ -136,6 +136,9 @@ __device__ __forceinline__ f3 hemisphere_reflective(f3 normal, int seed, float r
   const float decider = dot3(direction, normal);
   const f3 correct = normalize3(direction * decider);
   return normalize3(normal * (1.0f - roughness) + correct * roughness);
+}
+__device__ __forceinline__ f3 hemisphere_reflective(f3 normal, int seed, float roughness, unsigned gx, unsigned gy) {
+  return hemisphere_reflective_p(normal, seed, roughness, (gx + 1u) * (gy + 1u));
 }
 
 // march_to_next_event, utility_ray.cl:157-168 with march (:148-154) and get_event_and_value (:126-138) fused.
@@ -401,12 +404,16 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
   int mode = M_IDLE;
   bool marching = false;
   int ev = EVP_NONE;
-  int x = 0, y = 0, seed = 0;
+  // Register diet (ncu: at 40 registers the spills of this kernel made 59 M local loads/stores per launch, 213 M sectors of
+  // L1<->L2 traffic beside 337 M sectors of gathers): the pixel enters the RNG only as (x+1)*(y+1); base point, shading normal
+  // and cache voxel of the primary hit are re-read from the record (L2-resident) the two times they are needed instead of
+  // living in registers; the three radiance accumulators (<= 510 each: two adds of <= 255) share one register.
+  unsigned xyp = 0, rec = 0;
+  int seed = 0;
   f3 o = {0, 0, 0}, dv = {0, 0, 0};  // current ray
   int d = 0, steps_left = 0;
-  f3 base = {0, 0, 0}, normal = {0, 0, 0};
   float atten = 0, er = 0, eg = 0, eb = 0;
-  unsigned bv0 = 0, bv1 = 0, bv2 = 0, voxel = 0;
+  unsigned bvp = 0;  // bv0 | bv1 << 10 | bv2 << 20
   int clause_col = 0;  // 1-based index of the clause that last wrote the colour (0: colour still {0,0,0,0})
   int po = 0, pi = 0;  // the loop variables o (1..2) and i (8..10) of ray_marching.cl:47,52
   bool exhausted = false;
@@ -443,9 +450,10 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
           const float factor = 8.0f / (float)pi;
           const uchar4 lm = env_sample(p, dv);
           if (COUNT) c_env++;
-          bv0 = f2u((float)bv0 + atten * er * (float)lm.x * factor / 1.0f);
-          bv1 = f2u((float)bv1 + atten * eg * (float)lm.y * factor / 1.0f);
-          bv2 = f2u((float)bv2 + atten * eb * (float)lm.z * factor / 1.0f);
+          const unsigned bv0 = f2u((float)(bvp & 1023u) + atten * er * (float)lm.x * factor / 1.0f);
+          const unsigned bv1 = f2u((float)((bvp >> 10) & 1023u) + atten * eg * (float)lm.y * factor / 1.0f);
+          const unsigned bv2 = f2u((float)(bvp >> 20) + atten * eb * (float)lm.z * factor / 1.0f);
+          bvp = bv0 | (bv1 << 10) | (bv2 << 20);
           next_o = true;  // break
         } else {
           const bool more = pi < 10;
@@ -466,15 +474,17 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
         if (next_o) {
           if (po == 1) {
             po = 2; pi = 8;
-            o = base;
-            bn = normal; bseed = seed + po;
+            const HitRecord h2 = load_record(p.queue, rec);  // hit_information.origin + direction and the primary normal again
+            o = h2.base;
+            bn = h2.normal; bseed = seed + po;
             need_bounce = true; reset_atten = true; need_start = true;
           } else {
-            bv0 /= 2u; bv1 /= 2u; bv2 /= 2u;
-            const uint32_t low = (bv0 & 0xFFFFu) + ((bv1 & 0xFFFFu) << 16);
-            const uint32_t high = (bv2 & 0xFFFFu);
-            if (low) atomicAdd(p.cache + 2 * (size_t)voxel, low);
-            if (high) atomicAdd(p.cache + 2 * (size_t)voxel + 1, high);
+            const unsigned bv0 = (bvp & 1023u) / 2u, bv1 = ((bvp >> 10) & 1023u) / 2u, bv2 = (bvp >> 20) / 2u;  // buffer_value / dist_count
+            const uint32_t low = bv0 + (bv1 << 16);
+            const uint32_t high = bv2;
+            const size_t voxel = p.queue[3 * (size_t)rec].z;
+            if (low) atomicAdd(p.cache + 2 * voxel, low);
+            if (high) atomicAdd(p.cache + 2 * voxel + 1, high);
             mode = M_IDLE;
           }
         }
@@ -499,7 +509,7 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
             // from the same voxel run close together in time and find its neighbourhood in L1/L2 (2.74 -> 2.51 ms per 64-frame
             // step on the bench scene; groups of 2..32 pixels measure the same, so it is temporal, not intra-warp, locality).
             // VR_PT_ORDER=0: frame-major, consecutive items are neighbouring pixels of one frame.
-            unsigned f, rec;
+            unsigned f;
             if (p.pixel_major) {  // groups of pixel_major pixels x nframes frames, the pixels of a group fastest
               const unsigned pb = (unsigned)p.pixel_major, gsz = pb * (unsigned)p.nframes;
               const unsigned grp = idx / gsz, within = idx - grp * gsz;
@@ -522,17 +532,18 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
             if (COUNT && take) { c_adm++; c_normals++; }
             }
           } else {
+            rec = idx;
             h = load_record(p.queue, idx);
           }
         }
         if (take) {  // ray_marching.cl:42-50 for o = 1
-          x = h.xy & 0xFFFF; y = h.xy >> 16; seed = h.seed; voxel = h.voxel; clause_col = h.clause;
-          base = h.base; normal = h.normal;
+          xyp = (unsigned)((h.xy & 0xFFFF) + 1) * (unsigned)((h.xy >> 16) + 1);
+          seed = h.seed; clause_col = h.clause;
           er = energy(0); eg = energy(1); eb = energy(2);
-          bv0 = bv1 = bv2 = 0;
+          bvp = 0;
           po = 1; pi = 8;
-          o = base;
-          bn = normal; bseed = seed + po;
+          o = h.base;
+          bn = h.normal; bseed = seed + po;
           need_bounce = true; reset_atten = true; need_start = true;
           mode = M_SECOND;
         }
@@ -543,7 +554,7 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
 
     // ---- the one bounce site: ray_bounce_fake_reflectance + `origin += normal*2` + attenuation ------------------------------------
     if (need_bounce) {
-      dv = hemisphere_reflective(bn, bseed, energy(3), (unsigned)x, (unsigned)y);
+      dv = hemisphere_reflective_p(bn, bseed, energy(3), xyp);
       o = o + bn * 2.0f;
       const float a = fabsf(dot3(dv, bn));
       atten = reset_atten ? a : atten * a;
