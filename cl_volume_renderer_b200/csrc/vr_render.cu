@@ -35,6 +35,7 @@ struct RenderParams {
   int token_cap;
   int nframes;          // frames in this launch: blockIdx.z selects the seed
   int pixel_major;      // k_trace_pt<.., REUSE> item order (see there)
+  int rule_a, rule_b;   // k_trace_pt leaves its step loop when marching lanes * rule_a < waiting lanes * rule_b (VR_PT_RULE=a,b)
   int seeds[VR_MAX_BATCH];
   unsigned long long* counters;
   // hybrid schedule: k_trace<QUEUE> appends admitted primary hits here, k_trace_pt runs their secondary paths.
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(128, 12) k_primary(const RenderParams p) {
 // 1..3 segments of 1..70 steps each, twice).  In the hybrid schedule k_trace<QUEUE> stops at the admitted primary hit and
 // appends a HitRecord; here a lane is a SLOT: warps pull records from the queue, all lanes with a segment in flight step
 // together, and finished segments are processed in batches.  Event processing costs more than stepping (normalisations,
-// the RNG bounce, the env lookup), so (a) the warp leaves the step loop as soon as more lanes wait than march, and
+// the RNG bounce, the env lookup), so (a) the warp leaves the step loop only when the marching lanes are outnumbered 5 : 1, and
 // (b) every lane that needs a bounce — new record, secondary hit, start of o = 2 — goes through ONE bounce site.
 // What is computed per sample, every fp32 operation and its order, is unchanged; only the schedule differs.
 enum { M_IDLE = 0, M_SECOND = 2 };
@@ -596,9 +597,10 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
       }
       const unsigned act = __ballot_sync(0xffffffffu, marching);
       if (!act) break;
-      // majority rule: leave as soon as more lanes wait for event processing (or a refill) than are marching
+      // leave rule: event processing (normalisations, the RNG bounce, env lookups) costs far more than a step, so the warp keeps
+      // stepping until the lanes that still march are outnumbered 5 : 1 by the lanes that wait for an event or a refill
       const unsigned waiting = __ballot_sync(0xffffffffu, !marching && (mode != M_IDLE || !exhausted));
-      if (__popc(act) < __popc(waiting)) break;
+      if (__popc(act) * p.rule_a < __popc(waiting) * p.rule_b) break;
     }
   }
   if (COUNT) {
@@ -709,6 +711,15 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     p.nframes = nframes;
     static const int pixel_major = getenv("VR_PT_ORDER") ? std::max(atoi(getenv("VR_PT_ORDER")), 0) : 1;
     p.pixel_major = pixel_major;
+    static int rule[2] = {0, 0};
+    if (!rule[0]) {
+      // measured on the bench scene (ms per 64-frame step, default / close-up view): 1,1 2.43 / 6.92; 2,1 2.24 / 6.39;
+      // 4,1 2.17 / 6.15; 6,1 2.17 / 6.09; 8,1 2.20 / 6.10; 16,1 2.28 / 6.28; never leave early 2.46 / 6.64; 1,2 2.85 / 8.17
+      rule[0] = 5; rule[1] = 1;
+      if (const char* e = getenv("VR_PT_RULE")) sscanf(e, "%d,%d", &rule[0], &rule[1]);
+      if (rule[0] < 1 || rule[1] < 1) { rule[0] = 5; rule[1] = 1; }
+    }
+    p.rule_a = rule[0]; p.rule_b = rule[1];
     for (int k = 0; k < nframes; ++k) p.seeds[k] = seeds[k];
     p.token_cap = r->token_cap;
     p.counters = r->counters;
