@@ -86,7 +86,7 @@ __device__ __forceinline__ Ray generate_ray(f3 cam_pos, f3 cam_dir, f3 cam_side,
   const float x_offset = x_f / (float)x_total * aspect_ratio;
   const float y_offset = y_f / (float)y_total;
   f3 point = (cam_dir + x_offset * cam_side) + y_offset * cam_up;
-  return {cam_pos, normalize3(point)};
+  return {cam_pos, normalize3_shared_rcp(point)};
 }
 
 __device__ __forceinline__ bool lim(float p, int dim) { return p <= (float)dim && p >= 0.0f; }
@@ -135,8 +135,8 @@ __device__ __forceinline__ f3 hemisphere_reflective_p(f3 normal, int seed, float
   const int rz = (int)hash_u32(useed * 0xf1981dcfu);
   f3 direction = {(float)((rx % 2048) - 1024), (float)((ry % 2048) - 1024), (float)((rz % 2048) - 1024)};
   const float decider = dot3(direction, normal);
-  const f3 correct = normalize3(direction * decider);
-  return normalize3(normal * (1.0f - roughness) + correct * roughness);
+  const f3 correct = normalize3_shared_rcp(direction * decider);
+  return normalize3_shared_rcp(normal * (1.0f - roughness) + correct * roughness);
 }
 __device__ __forceinline__ f3 hemisphere_reflective(f3 normal, int seed, float roughness, unsigned gx, unsigned gy) {
   return hemisphere_reflective_p(normal, seed, roughness, (gx + 1u) * (gy + 1u));
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(128, 12) k_trace(const RenderParams p) {
           HitRecord h;
           h.xy = x | (y << 16); h.seed = seed; h.voxel = (unsigned)voxel; h.clause = colour_clause;
           h.base = cur.o + cur.d;
-          h.normal = -normalize3(grad);
+          h.normal = -normalize3_shared_rcp(grad);
           store_record(p.queue, slot, h);
           c_adm++;
           c_normals++;
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(128, 12) k_trace(const RenderParams p) {
         c_adm++;
         c_normals++;
         const Ray hit_information = cur;
-        const f3 normal = -normalize3(grad);
+        const f3 normal = -normalize3_shared_rcp(grad);
         float r_energy = (float)color[0] / 255.0f;
         float g_energy = (float)color[1] / 255.0f;
         float b_energy = (float)color[2] / 255.0f;
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(128, 12) k_trace(const RenderParams p) {
               bv2 = f2u((float)bv2 + atten * b_energy * (float)lm.z * factor / 1.0f);
               break;
             } else if (ev == EV_HIT) {
-              const f3 n2 = -normalize3(grad);
+              const f3 n2 = -normalize3_shared_rcp(grad);
               c_normals++;
               cur.o = cur.o + cur.d;
               cur.d = hemisphere_reflective(n2, seed + o + i, (float)color[3] / 255.0f, (unsigned)x, (unsigned)y);
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(128, 12) k_primary(const RenderParams p) {
       HitRecord h;
       h.xy = x | (y << 16); h.seed = 0; h.voxel = (unsigned)voxel; h.clause = colour_clause;
       h.base = cur.o + cur.d;
-      h.normal = -normalize3(grad);
+      h.normal = -normalize3_shared_rcp(grad);
       store_record(p.queue, slot, h);
     }
   }
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
       if (!marching) {  // body of the i-loop, ray_marching.cl:53-72
         bool next_o = false;
         if (ev == EVP_EXIT) {
-          const float factor = 8.0f / (float)pi;
+          const float factor = pi == 8 ? 8.0f / 8.0f : (pi == 9 ? 8.0f / 9.0f : 8.0f / 10.0f);  // 8.0f / i, i in {8,9,10}: constants
           const uchar4 lm = env_sample(p, dv);
           if (COUNT) c_env++;
           const unsigned bv0 = f2u((float)(bvp & 1023u) + atten * er * (float)lm.x * factor / 1.0f);
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
             if (COUNT) c_normals++;
             er *= energy(0); eg *= energy(1); eb *= energy(2);
             if (more) {  // at i == 10 the new ray (ray_marching.cl:64-67) is never marched and atten is reset next
-              bn = -normalize3(grad);
+              bn = -normalize3_shared_rcp(grad);
               o = o + dv;
               bseed = seed + po + pi;
               need_bounce = true;
