@@ -311,6 +311,9 @@ class renderer : public frame_emitter {
     if (r && w == rw && h == rh) return;
     if (r) vr_renderer_destroy(r);
     vr_fail_hard(vr_renderer_create(ctx.get(), w, h, &r));
+    // the UI calls render_frame once per sample while the camera rests (ui.cpp:296): keep the seed-independent primary
+    // segment between calls; camera moves, flushes and row-window changes re-march (include/vr.h)
+    vr_fail_hard(vr_renderer_set_primary_reuse(r, 2));
     rw = w; rh = h;
     if (flush_pending || flushed_once) do_flush();
     else if (volume && emap) vr_fail_hard(vr_renderer_set_scene(r, volume->get_reference_volume(), emap->get_buffer()));
