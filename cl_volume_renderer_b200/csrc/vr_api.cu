@@ -444,15 +444,20 @@ extern "C" int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_rendere
   if (!r) return VR_ERR_NOMEM;
   r->ctx = ctx; r->W = width; r->H = height; r->row0 = 0; r->row1 = height;
   const size_t px = (size_t)width * height;
-  VR_CUDA(pool_alloc(ctx, &r->frame, px * 4));
-  VR_CUDA(pool_alloc(ctx, &r->hit, px * 4));
-  VR_CUDA(pool_alloc(ctx, &r->counters, 8 * sizeof(unsigned long long)));
   if (const char* m = getenv("VR_TRACE_MODE")) r->trace_mode = std::min(std::max(atoi(m), 0), 2);
-  VR_CUDA(pinned_acquire(ctx, reinterpret_cast<void**>(&r->frame_host), px * 4));
-  VR_CUDA(cudaMemsetAsync(r->frame, 0, px * 4, ctx->stream));
-  VR_CUDA(cudaMemsetAsync(r->hit, 0xFF, px * 4, ctx->stream));
-  VR_CUDA(cudaMemsetAsync(r->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-  VR_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaError_t e = pool_alloc(ctx, &r->frame, px * 4);
+  if (e == cudaSuccess) e = pool_alloc(ctx, &r->hit, px * 4);
+  if (e == cudaSuccess) e = pool_alloc(ctx, &r->counters, 8 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = pinned_acquire(ctx, reinterpret_cast<void**>(&r->frame_host), px * 4);
+  if (e == cudaSuccess) e = cudaMemsetAsync(r->frame, 0, px * 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(r->hit, 0xFF, px * 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(r->counters, 0, 8 * sizeof(unsigned long long), ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    vr_set_error("vr_renderer_create: %s", cudaGetErrorString(e));
+    vr_renderer_destroy(r);  // releases whatever was acquired
+    return VR_ERR_CUDA;
+  }
   *out = r;
   return VR_OK;
 }
