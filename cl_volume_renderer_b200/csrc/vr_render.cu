@@ -728,7 +728,7 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     static int per_sm[4] = {0, 0, 0, 0};  // resident CTAs per SM of the k_trace_pt instantiations
     static int pt_ctas = 12;              // VR_PT_CTAS: register budget of the production variant (8: 64 regs, 10: 48, 12: 40)
     if (!per_sm[0]) {
-      if (const char* e = getenv("VR_PT_CTAS")) pt_ctas = atoi(e) == 8 ? 8 : (atoi(e) == 10 ? 10 : (atoi(e) == 16 ? 16 : 12));
+      if (const char* e = getenv("VR_PT_CTAS")) pt_ctas = atoi(e) == 8 ? 8 : (atoi(e) == 10 ? 10 : (atoi(e) == 16 ? 16 : (atoi(e) == 14 ? 14 : 12)));
       VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_trace_pt<false, false, 12>, 128, 0));
       VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_trace_pt<true, false, 12>, 128, 0));
       if (pt_ctas == 8) VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_trace_pt<false, true, 8>, 128, 0));
@@ -776,6 +776,8 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
         if (r->count) k_trace_pt<true, true, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else if (pt_ctas == 8) k_trace_pt<false, true, 8><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else if (pt_ctas == 16) k_trace_pt<false, true, 16><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        else if (r->sdf->surf && pt_ctas == 14) k_trace_pt<false, true, 14, true><<<(unsigned)ctx->sm_count * 14, 128, 0, ctx->stream>>>(p, p.qcount + 1);
+        else if (r->sdf->surf && pt_ctas == 16) k_trace_pt<false, true, 16, true><<<(unsigned)ctx->sm_count * 16, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else if (r->sdf->surf && pt_ctas == 10) k_trace_pt<false, true, 10, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else if (r->sdf->surf && pt_ctas == 8) k_trace_pt<false, true, 8, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
         else if (r->sdf->surf) k_trace_pt<false, true, 12, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
