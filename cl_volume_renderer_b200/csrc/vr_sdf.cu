@@ -37,7 +37,7 @@
 // per-word index arithmetic of k_sdf_wave3 (ncu: ~250 instructions per word, issue-bound) is shared by the 8 words of a
 // thread's column: ~40 instructions per word.  No block-level synchronisation.
 template <int XW>  // words per tile row: lane = lx + XW*ly, tile = XW words x (32/XW) rows x WT_Z planes
-__global__ void __launch_bounds__(128) k_sdf_wave5(WaveDims g, int tx, int ty, int tz, int level,
+__global__ void __launch_bounds__(256) k_sdf_wave5(WaveDims g, int tx, int ty, int tz, int level,
                                                    const uint32_t* __restrict__ Rin, uint32_t* __restrict__ Rout,
                                                    uint32_t* __restrict__ planes, unsigned nwords, const int* __restrict__ stamp_in,
                                                    int* __restrict__ stamp_out, unsigned* __restrict__ changed_tiles,
@@ -186,11 +186,12 @@ int vrk_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* done) {
   vr_ctx* ctx = s->ctx;
   const WaveDims& w = s->w;
   static const int grid_mult = getenv("VR_SDF_GRID") ? std::max(atoi(getenv("VR_SDF_GRID")), 1) : 64;  // measured at 512^3: 8..12 3.9 ms, 16 3.53, 32 (a warp per tile, no loop) 3.43
-  const unsigned wg5 = (unsigned)std::min<size_t>(div_up(s->ntiles, 4), (size_t)ctx->sm_count * grid_mult);
+  static const int cta_warps = getenv("VR_SDF_WARPS") ? std::min(std::max(atoi(getenv("VR_SDF_WARPS")), 1), 8) : 4;
+  const unsigned wg5 = (unsigned)std::min<size_t>(div_up(s->ntiles, cta_warps), (size_t)ctx->sm_count * grid_mult * 4 / cta_warps);
   int n = 0;
   for (; n < nlevels && s->level + 1 < s->max_it; ++n, ++s->level) {
     const int it = s->level;
-    k_sdf_wave5<4><<<wg5, 128, 0, ctx->stream>>>(w, w.tx, w.ty, w.tz, it, s->R((it + 1) & 1), s->R(it & 1), s->planes,
+    k_sdf_wave5<4><<<wg5, 32 * cta_warps, 0, ctx->stream>>>(w, w.tx, w.ty, w.tz, it, s->R((it + 1) & 1), s->R(it & 1), s->planes,
                                                 (unsigned)s->nwords, s->stamps(it & 1), s->stamps((it + 1) & 1), s->changed(),
                                                 s->all_active ? 1 : 0);
     s->all_active = false;
