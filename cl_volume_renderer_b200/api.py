@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libvr.so")
 VR_TF_USE_GRADIENT = 1
 VR_TF_THRESHOLD = 2
 VR_TF_MAX_RECTS = 16
+VR_FILTER2D_REFERENCE = 0  # 2d_image_filter.cl as written
+VR_FILTER2D_BILATERAL = 1  # the corrected bilateral
 
 
 class VrError(RuntimeError):
@@ -79,6 +81,8 @@ SYMBOLS = {
     "vr_render_frame": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, _P]),
     "vr_render_frames": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int, _P]),
     "vr_render_tf": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "vr_renderer_filter_frame": (C.c_int, [_P, C.c_int, C.c_float, C.c_int, _P]),
+    "vr_image_filter": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "vr_renderer_host_frame": (_P, [_P]),
     "vr_cache_download": (C.c_int, [_P, _P]),
     "vr_renderer_sdf": (_P, [_P]),
@@ -175,6 +179,15 @@ class Context:
     @property
     def stream(self):
         return lib().vr_ctx_stream(self.h)
+
+    def image_filter(self, rgba, kernel_size, sigma, mode=VR_FILTER2D_REFERENCE):
+        """2d_image_filter.cl bilateral_filter(frame, kernel_size, sigma) on a host RGBA8 image [h, w, 4]"""
+        rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+        assert rgba.ndim == 3 and rgba.shape[2] == 4
+        out = np.empty_like(rgba)
+        _check(lib().vr_image_filter(self.h, _vp(rgba), rgba.shape[1], rgba.shape[0], int(kernel_size), C.c_float(sigma),
+                                     int(mode), _vp(out)))
+        return out
 
     @property
     def launches(self):
@@ -394,6 +407,13 @@ class Renderer:
     def resolve(self, readback=True):
         out = np.empty((self.H, self.W, 4), dtype=np.uint8) if readback else None
         _check(lib().vr_renderer_resolve(self.h, _vp(out) if readback else None))
+        return out
+
+    def filter_frame(self, kernel_size, sigma, mode=VR_FILTER2D_REFERENCE, readback=True):
+        """2d_image_filter.cl over the renderer's current device frame"""
+        out = np.empty((self.H, self.W, 4), dtype=np.uint8) if readback else None
+        _check(lib().vr_renderer_filter_frame(self.h, int(kernel_size), C.c_float(sigma), int(mode),
+                                              _vp(out) if readback else None))
         return out
 
     def render_tf(self, width, height):

@@ -601,6 +601,56 @@ extern "C" int vr_renderer_resolve(vr_renderer* r, uint8_t* host_rgba) {
   return read_frame(r, host_rgba);
 }
 
+// ---- 2-D frame filter: 2d_image_filter.cl:6-43 -------------------------------------------------------------------------
+static int filter2d_check(int kernel_size, float sigma, int mode) {
+  VR_REQUIRE(mode == VR_FILTER2D_REFERENCE || mode == VR_FILTER2D_BILATERAL, "frame filter: unknown mode");
+  VR_REQUIRE(kernel_size >= 0 && kernel_size <= (mode == VR_FILTER2D_REFERENCE ? 64 : 15),
+             "frame filter: kernel_size out of range ([0,64] reference mode, [0,15] bilateral mode)");
+  VR_REQUIRE(sigma > 0.0f && std::isfinite(sigma), "frame filter: sigma must be a positive finite number");
+  return VR_OK;
+}
+
+extern "C" int vr_renderer_filter_frame(vr_renderer* r, int kernel_size, float sigma, int mode, uint8_t* host_rgba) {
+  VR_REQUIRE(r, "vr_renderer_filter_frame: null argument");
+  VR_TRY(filter2d_check(kernel_size, sigma, mode));
+  vr_ctx* ctx = r->ctx;
+  VR_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)r->W * r->H * 4;
+  uchar4* snapshot = nullptr;  // the kernel's taps read the unfiltered frame; r->frame keeps its address (it may have been handed out)
+  VR_CUDA(pool_alloc(ctx, &snapshot, bytes));
+  int st = VR_OK;
+  cudaError_t e = cudaMemcpyAsync(snapshot, r->frame, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e != cudaSuccess) { vr_set_error("vr_renderer_filter_frame: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  if (st == VR_OK) st = vrk_filter2d(ctx, snapshot, r->frame, r->W, r->H, kernel_size, sigma, mode);
+  pool_free(ctx, snapshot);  // stream-ordered: released after the kernel
+  VR_TRY(st);
+  return read_frame(r, host_rgba);
+}
+
+extern "C" int vr_image_filter(vr_ctx* ctx, const uint8_t* rgba_in, int w, int h, int kernel_size, float sigma, int mode,
+                               uint8_t* rgba_out) {
+  VR_REQUIRE(ctx && rgba_in && rgba_out, "vr_image_filter: null argument");
+  VR_REQUIRE(w > 0 && h > 0 && (size_t)w * h < ((size_t)1 << 30), "vr_image_filter: bad image size");
+  VR_TRY(filter2d_check(kernel_size, sigma, mode));
+  VR_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)w * h * 4;
+  uchar4 *src = nullptr, *dst = nullptr;
+  int st = VR_OK;
+  cudaError_t e = pool_alloc(ctx, &src, bytes);
+  if (e == cudaSuccess) e = pool_alloc(ctx, &dst, bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(src, rgba_in, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) { vr_set_error("vr_image_filter: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  if (st == VR_OK) st = vrk_filter2d(ctx, src, dst, w, h, kernel_size, sigma, mode);
+  if (st == VR_OK) {
+    e = cudaMemcpyAsync(rgba_out, dst, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { vr_set_error("vr_image_filter: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  }
+  pool_free(ctx, src);
+  pool_free(ctx, dst);
+  return st;
+}
+
 extern "C" uint8_t* vr_renderer_host_frame(vr_renderer* r) { return r ? r->frame_host : nullptr; }
 
 extern "C" int vr_cache_download(const vr_renderer* r, uint16_t* out) {

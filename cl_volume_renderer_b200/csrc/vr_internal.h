@@ -173,4 +173,6 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
                bool resolve, bool first_of_call = true);
 
 int vrk_xchg(vr_renderer* r, uint2* xchg, bool scatter);
+// 2d_image_filter.cl: src != dst, both w*h RGBA8 on the device
+int vrk_filter2d(vr_ctx* ctx, const uchar4* src, uchar4* dst, int w, int h, int kernel_size, float sigma, int mode);
 TfTable vr_make_tf_table(const vr_tf_rect* rects, int n);

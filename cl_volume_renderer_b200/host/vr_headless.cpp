@@ -5,7 +5,8 @@
 //
 //   vr_headless <volume.nrrd> <envmap.hdr|.ppm|.WxH.rgba> [--w 1920] [--h 1080] [--spp 64] [--out frame.ppm]
 //               [--pos x y z] [--look a b] [--tf "min_v,max_v,min_g,max_g,r,g,b,a;..."] [--filter] [--clip x0 y0 z0 x1 y1 z1]
-//               [--tf-image tf.ppm] [--raw frame.rgba]
+//               [--tf-image tf.ppm] [--raw frame.rgba] [--frame-filter kernel_size sigma reference|bilateral]
+// --frame-filter runs opencl_kernels/2d_image_filter.cl over the final frame ("reference" = the kernel as written).
 #include <cstring>
 #include <fstream>
 
@@ -31,6 +32,8 @@ int main(int argc, char** argv) {
   std::string out = "frame.ppm", raw_out, tf_image, tf_spec;
   double pos[3] = {0, 0, 0}, look[2] = {0.9, 6.183};  // ui.cpp:178
   bool have_pos = false, filter = false, clip = false;
+  int ff_k = -1, ff_mode = VR_FILTER2D_REFERENCE;
+  float ff_sigma = 1.0f;
   size_t cmin[3] = {0, 0, 0}, cmax[3] = {0, 0, 0};
   for (int i = 3; i < argc; ++i) {
     const std::string a = argv[i];
@@ -43,6 +46,14 @@ int main(int argc, char** argv) {
     else if (a == "--tf-image") { need(1); tf_image = argv[++i]; }
     else if (a == "--tf") { need(1); tf_spec = argv[++i]; }
     else if (a == "--filter") filter = true;
+    else if (a == "--frame-filter") {
+      need(3);
+      ff_k = atoi(argv[++i]);
+      ff_sigma = (float)atof(argv[++i]);
+      const std::string m = argv[++i];
+      if (m != "reference" && m != "bilateral") { std::cerr << "--frame-filter mode must be reference or bilateral\n"; return 2; }
+      ff_mode = m == "reference" ? VR_FILTER2D_REFERENCE : VR_FILTER2D_BILATERAL;
+    }
     else if (a == "--pos") { need(3); for (int k = 0; k < 3; ++k) pos[k] = atof(argv[++i]); have_pos = true; }
     else if (a == "--look") { need(2); look[0] = atof(argv[++i]); look[1] = atof(argv[++i]); }
     else if (a == "--clip") { need(6); for (int k = 0; k < 3; ++k) cmin[k] = atol(argv[++i]); for (int k = 0; k < 3; ++k) cmax[k] = atol(argv[++i]); clip = true; }
@@ -93,6 +104,7 @@ int main(int argc, char** argv) {
     state.cam_changed = true;
     frame = emitter->render_frame(state, changed);
   }
+  if (frame && ff_k >= 0) frame = render_ctx.filter_frame(ff_k, ff_sigma, ff_mode);
   if (frame) {
     write_ppm(out, static_cast<unsigned char*>(frame), W, H, true);
     if (!raw_out.empty()) {

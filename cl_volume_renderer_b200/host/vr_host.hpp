@@ -304,6 +304,14 @@ class renderer : public frame_emitter {
     vr_fail_hard(vr_render_tf(r, (int)width, (int)height, tfframe.data()));
     return tfframe.data();
   }
+  // opencl_kernels/2d_image_filter.cl:6-43 `bilateral_filter(frame, kernel_size, sigma)`: the reference ships the kernel but has
+  // no host method that launches it; this is the one it would take.  Filters the frame last rendered and returns the same
+  // pointer render_frame() returns.  mode: VR_FILTER2D_REFERENCE (the kernel as written) or VR_FILTER2D_BILATERAL.
+  void* filter_frame(int kernel_size, float sigma, int mode = VR_FILTER2D_REFERENCE) {
+    ensure(rw ? rw : SCREEN_WIDTH, rh ? rh : SCREEN_HEIGHT);
+    vr_fail_hard(vr_renderer_filter_frame(r, kernel_size, sigma, mode, vr_renderer_host_frame(r)));
+    return vr_renderer_host_frame(r);
+  }
   vr_renderer* handle() const { return r; }
 
  private:

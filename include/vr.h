@@ -149,6 +149,25 @@ int vr_cache_download(const vr_renderer* r, uint16_t* out);
 /* the SDF the renderer built at the last flush (renderer.hpp:19) */
 const vr_sdf* vr_renderer_sdf(const vr_renderer* r);
 
+/* ---- 2-D frame filter (opencl_kernels/2d_image_filter.cl:6-43 `bilateral_filter(frame, kernel_size, sigma)`) -------
+ * The reference ships this kernel but no host code launches it; the call takes the kernel's own arguments.
+ *   VR_FILTER2D_REFERENCE : the kernel's arithmetic exactly as written (bit-identical to the source compiled for the CPU):
+ *                           gauss() = a/(2*sigma^2) without an exponential, spatial term from pos - off, unsigned colour
+ *                           differences, the centre colour accumulated, all channels divided by the red weight sum, alpha 0.
+ *                           kernel_size in [0, 64].
+ *   VR_FILTER2D_BILATERAL : the bilateral filter it set out to be: exp(-(dx^2+dy^2)/(2 sigma^2)) * exp(-(tap-centre)^2/(2 sigma^2))
+ *                           per channel, centre tap included, taps outside the frame skipped, rounded to nearest, alpha kept.
+ *                           kernel_size in [0, 15].
+ * The reference kernel works in place on a __read_write image (taps race with neighbouring writes); here every tap reads the
+ * unfiltered frame.  sigma must be > 0. */
+enum { VR_FILTER2D_REFERENCE = 0, VR_FILTER2D_BILATERAL = 1 };
+/* filters the renderer's current device frame (the result of the last render_frame / resolve) and optionally reads it back;
+ * the next render_frame overwrites it */
+int vr_renderer_filter_frame(vr_renderer* r, int kernel_size, float sigma, int mode, uint8_t* host_rgba);
+/* the same on a caller-supplied RGBA8 image, host to host (rgba_out may equal rgba_in) */
+int vr_image_filter(vr_ctx* ctx, const uint8_t* rgba_in, int w, int h, int kernel_size, float sigma, int mode,
+                    uint8_t* rgba_out);
+
 /* ---- multi-GPU hooks (no reference counterpart: the reference is single-device) ---------------------- */
 /* per-rank token cap for the spp split: 256/R keeps the summed cache under the reference's cap of 256
  * (ray_marching.cl:39) and every 16-bit lane below overflow. Default 256. */

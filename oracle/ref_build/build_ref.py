@@ -25,7 +25,7 @@ kdir = os.path.join(ref, "opencl_kernels")
 os.makedirs(out, exist_ok=True)
 
 KERNEL_FILES = ["ray_marching.cl", "signed_distance_field.cl", "histogram.cl", "volume_filter.cl", "buffer_reset.cl",
-                "reference_volume_figures.cl", "reference_volume_clip.cl"]
+                "reference_volume_figures.cl", "reference_volume_clip.cl", "2d_image_filter.cl"]
 INC = re.compile(r'^\s*#clw_include_once\s+"([^"]+)"\s*$')
 
 

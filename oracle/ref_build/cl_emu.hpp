@@ -20,6 +20,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <limits>
 #include <sys/types.h>
 #include <type_traits>
 
@@ -36,27 +37,40 @@ typedef unsigned short ushort;
 // ---- vector types ------------------------------------------------------------------------------------------------
 #define EMU_ARITH(A) typename std::enable_if<std::is_arithmetic<A>::value || std::is_enum<A>::value, int>::type = 0
 
+// scalar conversion used by the vector constructors: float -> integer is round-toward-zero, saturating, NaN -> 0 (what
+// the hardware's conversion instruction does and what oracle.cpp defines); everything else is the plain C conversion
+template <class T, class A>
+inline T emu_cv(A a) {
+  if constexpr (std::is_integral<T>::value && std::is_floating_point<A>::value) {
+    if (a != a) return (T)0;
+    const double d = (double)a, lo = (double)std::numeric_limits<T>::min(), hi = (double)std::numeric_limits<T>::max();
+    return d <= lo ? std::numeric_limits<T>::min() : (d >= hi ? std::numeric_limits<T>::max() : (T)d);
+  } else {
+    return (T)a;
+  }
+}
+
 template <class T>
 struct vec2 {
   T x, y;
   vec2() : x(0), y(0) {}
-  template <class A, EMU_ARITH(A)> vec2(A a) : x((T)a), y((T)a) {}
-  template <class A, class B> vec2(A a, B b) : x((T)a), y((T)b) {}
+  template <class A, EMU_ARITH(A)> vec2(A a) : x(emu_cv<T>(a)), y(emu_cv<T>(a)) {}
+  template <class A, class B> vec2(A a, B b) : x(emu_cv<T>(a)), y(emu_cv<T>(b)) {}
   template <class U> explicit vec2(const vec2<U>& o) : x((T)o.x), y((T)o.y) {}
 };
 template <class T>
 struct vec3 {
   T x, y, z;
   vec3() : x(0), y(0), z(0) {}
-  template <class A, EMU_ARITH(A)> vec3(A a) : x((T)a), y((T)a), z((T)a) {}
-  template <class A, class B, class C> vec3(A a, B b, C c) : x((T)a), y((T)b), z((T)c) {}
+  template <class A, EMU_ARITH(A)> vec3(A a) : x(emu_cv<T>(a)), y(emu_cv<T>(a)), z(emu_cv<T>(a)) {}
+  template <class A, class B, class C> vec3(A a, B b, C c) : x(emu_cv<T>(a)), y(emu_cv<T>(b)), z(emu_cv<T>(c)) {}
 };
 template <class T>
 struct vec4 {
   T x, y, z, w;
   vec4() : x(0), y(0), z(0), w(0) {}
-  template <class A, EMU_ARITH(A)> vec4(A a) : x((T)a), y((T)a), z((T)a), w((T)a) {}
-  template <class A, class B, class C, class D> vec4(A a, B b, C c, D d) : x((T)a), y((T)b), z((T)c), w((T)d) {}
+  template <class A, EMU_ARITH(A)> vec4(A a) : x(emu_cv<T>(a)), y(emu_cv<T>(a)), z(emu_cv<T>(a)), w(emu_cv<T>(a)) {}
+  template <class A, class B, class C, class D> vec4(A a, B b, C c, D d) : x(emu_cv<T>(a)), y(emu_cv<T>(b)), z(emu_cv<T>(c)), w(emu_cv<T>(d)) {}
 };
 typedef vec2<float> float2;
 typedef vec3<float> float3;
@@ -132,6 +146,9 @@ struct emu_image {
   void* data;
   int w, h, d;
   int fmt;
+  // __read_write images (2d_image_filter.cl:6): when set, writes go here and reads keep seeing `data` — "every work-item
+  // reads the frame as it was before the launch", the one scheduling-independent meaning of the in-place kernel
+  void* wdata = nullptr;
 };
 typedef emu_image* image2d_t;
 typedef emu_image* image3d_t;
@@ -178,6 +195,18 @@ inline uint4 read_imageui(const emu_image* im, sampler_t s, float2 c) {
   const uint8_t* p = (const uint8_t*)im->data + 4 * ((size_t)iy * im->w + ix);
   return uint4(p[0], p[1], p[2], p[3]);
 }
+// read_imageui(image2d RGBA8, sampler, int2): integer coordinates are used as they are; CLK_ADDRESS_CLAMP outside = border 0
+inline uint4 read_imageui(const emu_image* im, sampler_t s, int2 c) {
+  long ix = c.x, iy = c.y;
+  if (s & CLK_ADDRESS_CLAMP_TO_EDGE) {
+    ix = ix < 0 ? 0 : (ix > im->w - 1 ? im->w - 1 : ix);
+    iy = iy < 0 ? 0 : (iy > im->h - 1 ? im->h - 1 : iy);
+  } else if (ix < 0 || iy < 0 || ix >= im->w || iy >= im->h) {
+    return uint4(0, 0, 0, 0);
+  }
+  const uint8_t* p = (const uint8_t*)im->data + 4 * ((size_t)iy * im->w + ix);
+  return uint4(p[0], p[1], p[2], p[3]);
+}
 inline int emu_sat(long v, long lo, long hi) { return (int)(v < lo ? lo : (v > hi ? hi : v)); }
 inline void write_imagei(emu_image* im, int4 c, int4 v) {
   if (c.x < 0 || c.y < 0 || c.x >= im->w || c.y >= im->h) return;
@@ -195,7 +224,7 @@ inline void write_imagei(emu_image* im, int4 c, int4 v) {
 inline void write_imagei(emu_image* im, int2 c, int4 v) { write_imagei(im, int4(c.x, c.y, 0, 0), v); }
 inline void write_imageui(emu_image* im, int2 c, uint4 v) {
   if (c.x < 0 || c.y < 0 || c.x >= im->w || c.y >= im->h) return;
-  uint8_t* p = (uint8_t*)im->data + 4 * ((size_t)c.y * im->w + c.x);
+  uint8_t* p = (uint8_t*)(im->wdata ? im->wdata : im->data) + 4 * ((size_t)c.y * im->w + c.x);
   p[0] = (uint8_t)min(v.x, 255u); p[1] = (uint8_t)min(v.y, 255u); p[2] = (uint8_t)min(v.z, 255u); p[3] = (uint8_t)min(v.w, 255u);
 }
 

@@ -41,6 +41,9 @@ namespace k_figures {
 namespace k_clip {
 #include "gen_reference_volume_clip.inc"
 }
+namespace k_image_filter {
+#include "gen_2d_image_filter.inc"
+}
 
 namespace {
 // app/common.hpp:59-66
@@ -168,6 +171,15 @@ void ref_clip(const int16_t* vol, int nx, int ny, int nz, const int start[3], co
   unsigned len[4] = {(unsigned)size[0], (unsigned)size[1], (unsigned)size[2], 4};
   ndrange(evenness(size[0], 4), evenness(size[1], 4), evenness(size[2], 4), emu_tf{nullptr, 0}, 1,
           [&] { k_clip::apply_clip(&v, &o, st, len); });
+}
+
+// 2d_image_filter.cl:6-43 — no host call site exists in the reference (the kernel is dead code, "not tested"); launched here
+// over exactly w x h work-items.  The kernel filters `frame` in place through a __read_write image, which makes a work-item's
+// taps race with its neighbours' writes; reads are served from the input copy and writes go to `out` (cl_emu.hpp, emu_image::wdata).
+void ref_image_filter2d(const uint8_t* rgba_in, int w, int h, int kernel_size, float sigma, uint8_t* rgba_out, int threads) {
+  memcpy(rgba_out, rgba_in, (size_t)w * h * 4);
+  emu_image f{const_cast<uint8_t*>(rgba_in), w, h, 1, EMU_U8x4, rgba_out};
+  ndrange(w, h, 1, emu_tf{nullptr, 0}, nthreads(threads), [&] { k_image_filter::bilateral_filter(&f, kernel_size, sigma); });
 }
 
 // app/renderer.cpp:32-35 around buffer_reset

@@ -48,3 +48,17 @@ for name, tf in (("default", synth.default_tf()), ("two_clause", tf2)):
     out[f"render_{name}_cache_val"] = r.cache[nz]
 np.savez_compressed(os.path.join(HERE, "ref_kernels.npz"), **out)
 print({k: (v.shape, str(v.dtype)) for k, v in out.items()})
+
+# 2d_image_filter.cl (dead code in the reference: no host call site) — inputs are stored as well
+f2 = {}
+rs = np.random.default_rng(20261018)
+noise = rs.integers(0, 256, (40, 48, 4), dtype=np.uint8)
+noise[:9, :11] = noise[0, 0]          # flat patch: red weight sum 0 -> 0/0
+noise[20:30, 5:25, 0] = 200           # flat in red only
+env_small = synth.synth_env(64, 32)   # smooth gradients + the bright disc
+f2["in_noise"], f2["in_env"] = noise, env_small
+for name, img in (("noise", noise), ("env", env_small)):
+    for k, sigma in ((1, 1.0), (2, 0.6), (3, 2.5), (9, 4.0)):
+        f2[f"out_{name}_k{k}_s{sigma}"] = R.image_filter2d(img, k, sigma)
+np.savez_compressed(os.path.join(HERE, "ref_filter2d.npz"), **f2)
+print({k: (v.shape, str(v.dtype)) for k, v in f2.items()})

@@ -144,6 +144,24 @@ def clip(vol, start, size):
     return out
 
 
+def image_filter2d(rgba, kernel_size, sigma):
+    """2d_image_filter.cl bilateral_filter, literal (reads see the input frame)"""
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = rgba.shape[:2]
+    out = np.empty_like(rgba)
+    lib().orc_image_filter2d(_p(rgba), w, h, int(kernel_size), C.c_float(sigma), _p(out))
+    return out
+
+
+def image_bilateral2d(rgba, kernel_size, sigma):
+    """the corrected 2-D bilateral (our definition, oracle.cpp)"""
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = rgba.shape[:2]
+    out = np.empty_like(rgba)
+    lib().orc_image_bilateral2d(_p(rgba), w, h, int(kernel_size), C.c_float(sigma), _p(out))
+    return out
+
+
 def env_lookup(env_rgba, dirs):
     env_rgba = np.ascontiguousarray(env_rgba, dtype=np.uint8)
     h, w = env_rgba.shape[:2]

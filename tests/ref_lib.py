@@ -86,6 +86,15 @@ def clip(vol, start, size):
     return out
 
 
+def image_filter2d(rgba, kernel_size, sigma, threads=0):
+    """the reference's 2d_image_filter.cl bilateral_filter over w x h work-items; reads see the input frame"""
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = rgba.shape[:2]
+    out = np.empty_like(rgba)
+    lib().ref_image_filter2d(_p(rgba), w, h, int(kernel_size), C.c_float(sigma), _p(out), threads)
+    return out
+
+
 class Renderer:
     """The reference `render` kernel over a CPU NDRange; token cap is the kernel's hard-coded 256."""
 

@@ -454,3 +454,49 @@ def test_frame_reset_clears_everything_sparse_or_full(vr_ctx, both):
     assert np.array_equal(r.cache_download().reshape(-1, 4)[:, 3], ref.cache.reshape(-1, 4)[:, 3])
     assert np.array_equal(got[..., 3], want[..., 3]) and _psnr(got[..., :3], want[..., :3]) >= 45.0
     r.close(); [k.close() for k in keep]
+
+
+# ---- 2-D frame filter: 2d_image_filter.cl -----------------------------------------------------------------------
+def test_image_filter2d_reference_mode_bit_exact(vr_ctx):
+    g = np.load(os.path.join(GOLDEN, "ref_filter2d.npz"))
+    for key in g.files:  # outputs of the reference kernel itself (k = 9 takes the untiled path)
+        if key.startswith("out_"):
+            _, name, k, s = key.split("_")
+            got = vr_ctx.image_filter(g["in_" + name], int(k[1:]), float(s[1:]), api.VR_FILTER2D_REFERENCE)
+            assert np.array_equal(got, g[key]), key
+    rs = np.random.default_rng(2)
+    for (h, w, k, sigma) in [(61, 97, 2, 1.5), (8, 200, 8, 3.0), (130, 33, 4, 0.7), (3, 3, 0, 1.0), (70, 70, 20, 9.0)]:
+        img = rs.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        img[: h // 2, : w // 4] = img[0, 0]
+        got = vr_ctx.image_filter(img, k, sigma, api.VR_FILTER2D_REFERENCE)
+        assert np.array_equal(got, o.image_filter2d(img, k, sigma)), (h, w, k, sigma)
+
+
+def test_image_filter2d_bilateral_mode(vr_ctx):
+    # expf differs by an ulp between CUDA and glibc: a rounded channel may move by one count
+    rs = np.random.default_rng(4)
+    for (h, w, k, sigma) in [(61, 97, 2, 12.0), (40, 64, 8, 30.0), (33, 130, 12, 6.0), (9, 9, 0, 1.0), (16, 16, 15, 50.0)]:
+        img = rs.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        got = vr_ctx.image_filter(img, k, sigma, api.VR_FILTER2D_BILATERAL)
+        want = o.image_bilateral2d(img, k, sigma)
+        d = np.abs(got.astype(int) - want.astype(int))
+        assert d.max() <= 1 and (d == 0).mean() >= 0.99, (h, w, k, sigma, d.max(), (d == 0).mean())
+        assert np.array_equal(got[..., 3], img[..., 3])
+
+
+def test_renderer_filter_frame_and_argument_checks(vr_ctx):
+    n, W, H = 48, 96, 64
+    vol, env = api.Volume(vr_ctx, synth.synth_ct(n)), api.EnvMap(vr_ctx, synth.synth_env(128, 64))
+    r = api.Renderer(vr_ctx, W, H)
+    r.image_set(vol, env)
+    r.set_tf(synth.default_tf())
+    r.flush_changes()
+    pos, d = synth.default_camera(n)
+    frame = r.render_frame(pos, d, 1)
+    got = r.filter_frame(2, 1.5)
+    assert np.array_equal(got, o.image_filter2d(frame, 2, 1.5))
+    assert np.array_equal(r.render_frame(pos, d, 2)[..., 3], frame[..., 3])  # the next frame overwrites the filtered one
+    for bad in [(-1, 1.0, 0), (65, 1.0, 0), (16, 1.0, 1), (2, 0.0, 0), (2, float("nan"), 0), (2, 1.0, 7)]:
+        with pytest.raises(api.VrError):
+            r.filter_frame(*bad)
+    r.close(); env.close(); vol.close()

@@ -61,6 +61,40 @@ def test_golden_render(name, tf):
     assert np.array_equal(f2[frame[..., 3] == 200], frame[frame[..., 3] == 200])
 
 
+def test_golden_image_filter2d():
+    # 2d_image_filter.cl: outputs of the reference kernel itself (oracle/_ref) on stored inputs
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_filter2d.npz"))
+    n = 0
+    for key in g.files:
+        if not key.startswith("out_"):
+            continue
+        _, name, k, s = key.split("_")
+        got = o.image_filter2d(g["in_" + name], int(k[1:]), float(s[1:]))
+        assert np.array_equal(got, g[key]), key
+        n += 1
+    assert n == 8
+    # the quirks are really there: alpha 0; red passes through (r*W/W) up to one count; where red is flat the red weight sum
+    # is 0, so red = 0/0 = NaN -> 0 and green / blue = x/0 = inf -> 255 (or NaN -> 0)
+    out = g["out_noise_k2_s0.6"]
+    assert (out[..., 3] == 0).all()
+    assert (out[22:28, 8:22, 0] == 0).all() and np.isin(out[22:28, 8:22, 1:3], (0, 255)).all()
+    d = out[..., 0].astype(int) - g["in_noise"][..., 0].astype(int)
+    assert ((d == 0) | (d == -1) | (out[..., 0] == 0)).all()
+
+
+def test_image_bilateral2d_definition():
+    # the corrected filter (our definition): identity on flat images, keeps alpha, smooths noise, stays within the tap range
+    flat = np.full((12, 16, 4), 77, dtype=np.uint8)
+    assert np.array_equal(o.image_bilateral2d(flat, 3, 2.0), flat)
+    rs = np.random.default_rng(5)
+    img = rs.integers(90, 110, (24, 32, 4), dtype=np.uint8)
+    out = o.image_bilateral2d(img, 2, 30.0)
+    assert np.array_equal(out[..., 3], img[..., 3])
+    assert out[..., :3].astype(float).std() < 0.5 * img[..., :3].astype(float).std()
+    assert out[..., :3].min() >= 90 and out[..., :3].max() <= 109
+    assert np.array_equal(o.image_bilateral2d(img, 0, 1.0), img)  # centre tap only
+
+
 live = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref.so not built (needs /root/reference)")
 
 
@@ -121,3 +155,12 @@ def test_live_token_cap_256():
         fb = b.render_frame(pos, d, k, threads=1)
     assert a.cache.reshape(-1, 4)[:, 3].max() == 256
     assert np.array_equal(a.cache, b.cache) and np.array_equal(fa, fb)
+
+
+@live
+def test_live_image_filter2d():
+    rs = np.random.default_rng(11)
+    for (h, w, k, sigma) in [(24, 40, 1, 1.0), (17, 23, 2, 0.6), (33, 19, 3, 2.5), (8, 8, 5, 10.0), (5, 7, 0, 1.0), (40, 40, 12, 0.25)]:
+        img = rs.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        img[: h // 3, : w // 3] = img[0, 0]
+        assert np.array_equal(o.image_filter2d(img, k, sigma), R.image_filter2d(img, k, sigma)), (h, w, k, sigma)
