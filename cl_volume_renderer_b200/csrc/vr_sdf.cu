@@ -36,7 +36,7 @@
 // y- and x-dilated rows yd(z') are computed once per plane (10 per tile) and reused by the planes z'-1 and z'+1, and all the
 // per-word index arithmetic of k_sdf_wave3 (ncu: ~250 instructions per word, issue-bound) is shared by the 8 words of a
 // thread's column: ~40 instructions per word.  No block-level synchronisation.
-template <int XW>  // words per tile row: lane = lx + XW*ly, tile = XW words x (32/XW) rows x WT_Z planes
+template <int XW, int TZ>  // words per tile row: lane = lx + XW*ly, tile = XW words x (32/XW) rows x TZ planes
 __global__ void __launch_bounds__(256) k_sdf_wave5(WaveDims g, int tx, int ty, int tz, int level,
                                                    const uint32_t* __restrict__ Rin, uint32_t* __restrict__ Rout,
                                                    uint32_t* __restrict__ planes, unsigned nwords, const int* __restrict__ stamp_in,
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_sdf_wave5(WaveDims g, int tx, int ty, i
     if (level != 1 && !all_active && stamp_in[tile] != level) continue;  // warp-uniform
     const int ttx = tile % tx, tq = tile / tx;
     const int tty = tq % ty, ttz = tq / ty;
-    const int xw = ttx * XW + lx, y = tty * YR + ly, z0 = ttz * WT_Z;
+    const int xw = ttx * XW + lx, y = tty * YR + ly, z0 = ttz * TZ;
     const bool xin = xw < g.nxw;
     const bool first = xw == 0, last = xw == g.nxw - 1;
     const uint32_t lm = last ? (1u << g.lastbit) : 0u;  // x == nx-1 is its own +1 neighbour
@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(256) k_sdf_wave5(WaveDims g, int tx, int ty, i
     const uint32_t* pm = Rin + (unsigned)max(yc - 1, 0) * (unsigned)g.nxw + (unsigned)min(xw, g.nxw - 1);
     const uint32_t* pp = Rin + (unsigned)min(yc + 1, g.ny - 1) * (unsigned)g.nxw + (unsigned)min(xw, g.nxw - 1);
     const bool lload = lx == 0 && xw > 0 && xin, rload = lx == XW - 1 && xw + 1 < g.nxw;
-    uint32_t ydz[WT_Z + 2];
+    uint32_t ydz[TZ + 2];
 #pragma unroll
-    for (int k = 0; k < WT_Z + 2; ++k) {
+    for (int k = 0; k < TZ + 2; ++k) {
       const unsigned zo = (unsigned)min(max(z0 - 1 + k, 0), g.nz - 1) * plane_stride;
       const uint32_t c0 = xin ? pm[zo] : 0u, c1 = xin ? pp[zo] : 0u;
       uint32_t l0 = __shfl_up_sync(0xffffffffu, c0, 1), r0 = __shfl_down_sync(0xffffffffu, c0, 1);
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) k_sdf_wave5(WaveDims g, int tx, int ty, i
       const uint32_t vm = valid_mask(g, xw);
       const unsigned lv = (unsigned)level + 1u;
 #pragma unroll
-      for (int j = 0; j < WT_Z; ++j) {
+      for (int j = 0; j < TZ; ++j) {
         const int z = z0 + j;
         if (z >= g.nz) break;
         const unsigned w = (unsigned)z * plane_stride + (unsigned)y * (unsigned)g.nxw + (unsigned)xw;
@@ -136,6 +136,7 @@ struct vr_sdf_slab {
   int max_it = 0;      // of the GLOBAL volume (signed_distance_field.cpp:11)
   int level = 1;       // next level to run
   size_t nwords = 0, ntiles = 0;
+  int tile_z = WT_Z;   // planes per warp tile of k_sdf_wave5
   uint32_t* scratch = nullptr;  // E | R0 | R1 | stamps[2][ntiles] | changed[130]
   uint32_t* planes = nullptr;
   bool all_active = false;
@@ -153,7 +154,10 @@ int vrk_sdf_slab_create(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz,
   w.nx = nx; w.ny = ny; w.nz = nz;
   w.nxw = (nx + 31) / 32;
   w.bx = nx / BR + 1; w.by = ny / BR + 1; w.bz = nz / BR + 1;
-  w.tx = (w.nxw + WT_XW - 1) / WT_XW; w.ty = (ny + WT_Y - 1) / WT_Y; w.tz = (nz + WT_Z - 1) / WT_Z;
+  // measured at 512^3 (VR_SDF_TZ): see DESIGN.md 4.2
+  static const int tile_z_env = getenv("VR_SDF_TZ") ? atoi(getenv("VR_SDF_TZ")) : WT_Z;
+  s->tile_z = (tile_z_env == 2 || tile_z_env == 4 || tile_z_env == 16) ? tile_z_env : WT_Z;
+  w.tx = (w.nxw + WT_XW - 1) / WT_XW; w.ty = (ny + WT_Y - 1) / WT_Y; w.tz = (nz + s->tile_z - 1) / s->tile_z;
   w.lastbit = (unsigned)((nx - 1) & 31);
   s->nwords = (size_t)w.nxw * ny * nz;
   s->ntiles = (size_t)w.tx * w.ty * w.tz;
@@ -191,9 +195,17 @@ int vrk_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* done) {
   int n = 0;
   for (; n < nlevels && s->level + 1 < s->max_it; ++n, ++s->level) {
     const int it = s->level;
-    k_sdf_wave5<4><<<wg5, 32 * cta_warps, 0, ctx->stream>>>(w, w.tx, w.ty, w.tz, it, s->R((it + 1) & 1), s->R(it & 1), s->planes,
-                                                (unsigned)s->nwords, s->stamps(it & 1), s->stamps((it + 1) & 1), s->changed(),
-                                                s->all_active ? 1 : 0);
+#define VR_WAVE5(TZ)                                                                                                          \
+  k_sdf_wave5<4, TZ><<<wg5, 32 * cta_warps, 0, ctx->stream>>>(w, w.tx, w.ty, w.tz, it, s->R((it + 1) & 1), s->R(it & 1), s->planes, \
+                                                              (unsigned)s->nwords, s->stamps(it & 1), s->stamps((it + 1) & 1),   \
+                                                              s->changed(), s->all_active ? 1 : 0)
+    switch (s->tile_z) {
+      case 2: VR_WAVE5(2); break;
+      case 4: VR_WAVE5(4); break;
+      case 16: VR_WAVE5(16); break;
+      default: VR_WAVE5(8); break;
+    }
+#undef VR_WAVE5
     s->all_active = false;
     ctx->launches++;
   }
