@@ -64,17 +64,22 @@ extern "C" int vr_ctx_create(int device_ordinal, vr_ctx** out) {
   if (!c) return VR_ERR_NOMEM;
   c->device = device_ordinal;
   c->sm_count = prop.multiProcessorCount;
-  VR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  VR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  VR_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
-  VR_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  VR_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   cudaMemPool_t pool;
-  VR_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
-  uint64_t keep = UINT64_MAX;
-  VR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  VR_CUDA(cudaMalloc(&c->scratch, 4096));
-  VR_CUDA(cudaMallocHost(&c->scratch_host, 4096));
+  const uint64_t keep = UINT64_MAX;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaDeviceGetDefaultMemPool(&pool, device_ordinal);
+  if (e == cudaSuccess) e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, const_cast<uint64_t*>(&keep));
+  if (e == cudaSuccess) e = cudaMalloc(&c->scratch, 4096);
+  if (e == cudaSuccess) e = cudaMallocHost(&c->scratch_host, 4096);
+  if (e != cudaSuccess) {
+    vr_set_error("vr_ctx_create: %s", cudaGetErrorString(e));
+    vr_ctx_destroy(c);  // releases whatever was created
+    return VR_ERR_CUDA;
+  }
   *out = c;
   return VR_OK;
 }
@@ -82,16 +87,16 @@ extern "C" int vr_ctx_create(int device_ordinal, vr_ctx** out) {
 extern "C" void vr_ctx_destroy(vr_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  cudaFree(c->scratch);
-  cudaFreeHost(c->scratch_host);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->scratch) cudaFree(c->scratch);
+  if (c->scratch_host) cudaFreeHost(c->scratch_host);
   for (auto& b : c->pinned) cudaFreeHost(b.p);
   for (auto& a : c->sdf_arrays) { cudaDestroySurfaceObject(a.surf); cudaFreeArray(a.arr); }
-  cudaEventDestroy(c->ev_fork);
-  cudaEventDestroy(c->ev_join);
-  cudaStreamDestroy(c->aux_stream);
-  cudaStreamDestroy(c->copy_stream);
-  cudaStreamDestroy(c->stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
@@ -132,11 +137,18 @@ static int volume_upload_impl(vr_ctx* ctx, const int16_t* voxels, int nx, int ny
   v->ctx = ctx;
   v->onx = v->nx = nx; v->ony = v->ny = ny; v->onz = v->nz = nz;
   const size_t bytes = v->count() * sizeof(int16_t);
-  VR_CUDA(pool_alloc(ctx, &v->original, bytes));
-  VR_CUDA(cudaMemcpyAsync(v->original, voxels, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  cudaError_t e = pool_alloc(ctx, &v->original, bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(v->original, voxels, bytes, cudaMemcpyHostToDevice, ctx->stream);
   v->zlo = zlo; v->zhi = zhi;
-  int s = vrk_fetch_stats(ctx, v->original, nx, ny, nz, v->stats, zlo, zhi);  // reference_volume.cpp:22-41
-  if (s != VR_OK) { pool_free(ctx, v->original); delete v; return s; }
+  int s = VR_OK;
+  if (e != cudaSuccess) { vr_set_error("vr_volume_upload: %s", cudaGetErrorString(e)); s = VR_ERR_CUDA; }
+  if (s == VR_OK) s = vrk_fetch_stats(ctx, v->original, nx, ny, nz, v->stats, zlo, zhi);  // reference_volume.cpp:22-41
+  if (s != VR_OK) {
+    cudaStreamSynchronize(ctx->stream);  // the (possibly staged) copy must not outlive the caller's buffer
+    pool_free(ctx, v->original);
+    delete v;
+    return s;
+  }
   *out = v;
   return VR_OK;
 }
@@ -302,9 +314,15 @@ extern "C" int vr_envmap_bind(vr_ctx* ctx, const uint8_t* rgba8, int w, int h, v
   vr_envmap* e = new (std::nothrow) vr_envmap();
   if (!e) return VR_ERR_NOMEM;
   e->ctx = ctx; e->w = w; e->h = h;
-  VR_CUDA(pool_alloc(ctx, &e->texels, (size_t)w * h * 4));
-  VR_CUDA(cudaMemcpyAsync(e->texels, rgba8, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
-  VR_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaError_t ce = pool_alloc(ctx, &e->texels, (size_t)w * h * 4);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->texels, rgba8, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) {
+    vr_set_error("vr_envmap_bind: %s", cudaGetErrorString(ce));
+    pool_free(ctx, e->texels);
+    delete e;
+    return VR_ERR_CUDA;
+  }
   *out = e;
   return VR_OK;
 }

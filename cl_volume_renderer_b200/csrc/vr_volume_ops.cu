@@ -158,24 +158,41 @@ int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int
 }
 
 // ---- apply_clip: reference_volume_clip.cl:4-15 ---------------------------------------------------------------
+// Pure copy (4 bytes per output voxel).  A thread produces 8 consecutive output voxels and writes them with one 16-byte
+// store (the destination is a fresh allocation, so 16-byte aligned; output rows are not, so a group may straddle rows: the
+// (x,y,z) of its first voxel comes from one 32-bit division pair, the rest by carry).  Source rows start at arbitrary
+// offsets, so the reads are 2-byte loads — consecutive lanes read consecutive addresses, L1 merges them into full sectors.
+// Reads outside the source are border reads (0), as the reference's samplerless read_imagei on a CLK_ADDRESS_CLAMP-less
+// image is only ever used in range (reference_volume.cpp:57-59 asserts it) — kept defined here.
 __global__ void __launch_bounds__(256) k_clip(VolView src, int sx, int sy, int sz, int16_t* __restrict__ dst, int nx,
-                                              int ny, int nz) {
-  const size_t n = (size_t)nx * ny * nz;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    int x = (int)(i % nx);
-    size_t t = i / nx;
-    int y = (int)(t % ny);
-    int z = (int)(t / ny);
-    dst[i] = (int16_t)src.at(sx + x, sy + y, sz + z);
+                                              int ny, unsigned n) {
+  const unsigned ngroups = (n + 7u) >> 3;
+  for (unsigned gi = blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += gridDim.x * blockDim.x) {
+    const unsigned i0 = gi << 3;
+    int x = (int)(i0 % (unsigned)nx);
+    const unsigned t = i0 / (unsigned)nx;
+    int y = (int)(t % (unsigned)ny), z = (int)(t / (unsigned)ny);
+    unsigned v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = (unsigned)(unsigned short)src.at(sx + x, sy + y, sz + z);  // the last group may run past n: those reads are in range or 0
+      if (++x == nx) { x = 0; if (++y == ny) { y = 0; ++z; } }
+    }
+    if (i0 + 8u <= n) {
+      *reinterpret_cast<uint4*>(dst + i0) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+    } else {
+      for (unsigned k = 0; i0 + k < n; ++k) dst[i0 + k] = (int16_t)v[k];
+    }
   }
 }
 
 int vrk_clip(vr_ctx* ctx, const int16_t* src, int snx, int sny, int snz, const uint32_t start[3], int16_t* dst, int nx,
              int ny, int nz) {
   VolView v{src, snx, sny, snz};
-  size_t n = (size_t)nx * ny * nz;
-  unsigned blocks = (unsigned)std::min<size_t>(div_up(n, 256), (size_t)ctx->sm_count * 16);
-  k_clip<<<blocks, 256, 0, ctx->stream>>>(v, (int)start[0], (int)start[1], (int)start[2], dst, nx, ny, nz);
+  const size_t n = (size_t)nx * ny * nz;  // < 2^32 - 1: the output is a sub-box of an uploaded volume or at most as large
+  VR_REQUIRE(n < ((size_t)1 << 32) - 8, "vr_volume_clip: more than 2^32-9 voxels");
+  unsigned blocks = (unsigned)std::min<size_t>(div_up(div_up(n, 8), 256), (size_t)ctx->sm_count * 16);
+  k_clip<<<blocks, 256, 0, ctx->stream>>>(v, (int)start[0], (int)start[1], (int)start[2], dst, nx, ny, (unsigned)n);
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
   return VR_OK;

@@ -16,6 +16,8 @@ def run(n):
     r.render_tf(500, 500)                                          # k_histogram, k_tf_color_frame
     pos, d = synth.default_camera(n)
     r.render_frames(pos, d, synth.glibc_rand(16), readback=False)  # k_trace, k_trace_pt, k_resolve
+    r.filter_frame(2, 1.5, api.VR_FILTER2D_REFERENCE, readback=False)   # k_filter2d_reference (2d_image_filter.cl as written)
+    r.filter_frame(4, 12.0, api.VR_FILTER2D_BILATERAL, readback=False)  # k_filter2d_bilateral
     r.sdf_download()                                               # k_sdf_unbrick
     r.close()
     vol.clip((8, 8, 8), (n - 8, n - 8, n - 8))                     # k_clip
@@ -41,6 +43,7 @@ def report(path, n):
     for k, (cnt, us) in agg.items():
         b = alg.get(k)
         if k.startswith('k_sdf_level'): b = None
+        if k.startswith('k_filter2d'): b = 8 * 1920 * 1080
         gbs = b * cnt / (us * 1e-6) / 1e9 if b else None  # alg bytes per launch x launches / total time
         out[k] = {"launches": cnt, "total_us": round(us, 1), "alg_bytes": b, "alg_GBps": round(gbs, 1) if gbs else None,
                   "frac_of_6461.5": round(gbs / 6461.5, 3) if gbs else None}
