@@ -108,15 +108,23 @@ __global__ void __launch_bounds__(256) k_sdf_wave5(WaveDims g, int tx, int ty, i
   }
 }
 
-// bricked -> x-fastest linear (vr_sdf_download; tests/sdf/sdf_test.cpp:24-31 order)
+// bricked -> x-fastest linear (vr_sdf_download; tests/sdf/sdf_test.cpp:24-31 order).  A brick row is 8 contiguous bytes, so a
+// thread moves one 8-voxel group with one 8-byte load; the store is 8 bytes too when the linear rows are 8-byte aligned
+// (nx % 8 == 0), byte stores otherwise.  Consecutive threads walk along x, then y, then z.
+template <bool ALIGNED>
 __global__ void __launch_bounds__(256) k_sdf_unbrick(BrickDims g, const int8_t* __restrict__ field,
                                                      int8_t* __restrict__ linear) {
-  const size_t n = (size_t)g.nx * g.ny * g.nz;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % g.nx);
-    const size_t t = i / g.nx;
+  const unsigned gx = (unsigned)(g.nx + 7) >> 3;
+  const size_t ngroups = (size_t)gx * g.ny * g.nz;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ngroups; i += (size_t)gridDim.x * blockDim.x) {
+    const int x0 = (int)(i % gx) << 3;
+    const size_t t = i / gx;
     const int y = (int)(t % g.ny), z = (int)(t / g.ny);
-    linear[i] = field[brick_voxel_addr(g, x, y, z)];
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(field + brick_voxel_addr(g, x0, y, z)));
+    int8_t* dst = linear + ((size_t)z * g.ny + y) * g.nx + x0;
+    if (ALIGNED) *reinterpret_cast<uint2*>(dst) = v;
+    else
+      for (int k = 0; k < 8 && x0 + k < g.nx; ++k) dst[k] = (int8_t)(((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 0xFF);
   }
 }
 
@@ -298,9 +306,10 @@ int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const
 
 int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear) {
   BrickDims g{nx, ny, nz, nx / BR + 1, ny / BR + 1, nz / BR + 1};
-  const size_t n = (size_t)nx * ny * nz;
-  const unsigned blocks = (unsigned)std::min<size_t>(div_up(n, 256), (size_t)ctx->sm_count * 16);
-  k_sdf_unbrick<<<blocks, 256, 0, ctx->stream>>>(g, field, linear);
+  const size_t ngroups = (size_t)((nx + 7) / 8) * ny * nz;
+  const unsigned blocks = (unsigned)std::min<size_t>(div_up(ngroups, 256), (size_t)ctx->sm_count * 16);
+  if (nx % 8 == 0) k_sdf_unbrick<true><<<blocks, 256, 0, ctx->stream>>>(g, field, linear);
+  else k_sdf_unbrick<false><<<blocks, 256, 0, ctx->stream>>>(g, field, linear);
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
   return VR_OK;
