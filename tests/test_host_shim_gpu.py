@@ -80,3 +80,10 @@ def test_headless_cli_matches_oracle(tmp_path):
     assert np.array_equal(img, got[::-1, :, :3])  # the frame's row 0 is the bottom of the view
     tf = open(tmp_path / "tf.ppm", "rb").read()
     assert tf.startswith(b"P6\n500 500\n255\n") and len(tf) == 15 + 500 * 500 * 3
+    # --frame-filter: 2d_image_filter.cl over the final frame (reference mode = the kernel as written, bit-exact)
+    out2 = subprocess.run([cli, str(tmp_path / "vol.nrrd"), str(tmp_path / "env.hdr"), "--w", str(W), "--h", str(H), "--spp", str(spp),
+                           "--out", str(tmp_path / "g.ppm"), "--raw", str(tmp_path / "g.rgba"), "--frame-filter", "2", "1.5", "reference"],
+                          capture_output=True, text=True, timeout=120)
+    assert out2.returncode == 0, out2.stderr + out2.stdout
+    got2 = np.fromfile(tmp_path / "g.rgba", dtype=np.uint8).reshape(H, W, 4)
+    assert np.array_equal(got2, o.image_filter2d(got, 2, 1.5))
