@@ -62,6 +62,24 @@ finally:
             os.remove(p)
 print("built", os.path.join(out, "libref.so"))
 
+# The same expanded kernel text, embedded as byte arrays, for the mini OpenCL host (ocl_host.cpp): on a GPU box whose driver
+# ships an OpenCL runtime it runs the reference's unmodified kernels on the GPU itself.  /root/reference does not exist there,
+# so the text travels inside the (git-ignored) binary; the generated include is deleted after the compile.
+OCL_FILES = ["ray_marching.cl", "signed_distance_field.cl", "buffer_reset.cl", "reference_volume_figures.cl"]
+inc = os.path.join(out, "gen_ocl_sources.inc")
+with open(inc, "w") as f:
+    for name in OCL_FILES:
+        data = expand(name, set()).encode("utf-8") + b"\0"
+        f.write("static const unsigned char ocl_src_%s[] = {%s};\n" % (name.replace(".cl", ""), ",".join(str(b) for b in data)))
+cmd = [cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-I", out, os.path.join(here, "ocl_host.cpp"), "-ldl", "-o",
+       os.path.join(out, "libref_ocl.so")]
+try:
+    subprocess.check_call(cmd)
+finally:
+    if not os.environ.get("KEEP_GEN"):
+        os.remove(inc)
+print("built", os.path.join(out, "libref_ocl.so"))
+
 # The reference's own loaders (NRRD, env map through the vendored stb_image) compile as they are: a small main() around
 # them gives tests/test_io_cpu.py the reference's behaviour for the ingest row.
 app = os.path.join(ref, "app")
