@@ -520,6 +520,39 @@ def run_ours(args, rank, world, local_rank):
                "sample": f"{nfr} x 1 spp frame of the same 1920x1080/512^3 scene ({what}; SDF taken from the GPU build, which "
                          f"the parity tests pin bit-exact)"}
 
+    # ---- the reference's own OpenCL kernels on THIS GPU (rank 0, N=1 only; part of the baseline leg, reported beside cpu_baseline):
+    # when the driver ships an OpenCL runtime, oracle/_ref/libref_ocl.so JIT-compiles the reference's unmodified kernels with
+    # the reference's options and runs the reference's host sequences (SDF build loop with its blocking counter transfers,
+    # render_frame with its blocking frame pull) on the same B200, same scene, same seeds, from a reset cache.
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import ref_ocl_lib as RO
+            if RO.available():
+                RO.set_nearest(False)  # as shipped
+                sc = RO.Scene(vol_np, env_np, tf_code, W, H)
+                sc.render(pos, d, seeds[:2], readback=False)
+                sc.reset()
+                _, ms_pull = sc.render(pos, d, seeds[:SPP], pull_every_frame=True)
+                sc.reset()
+                _, ms_kernel = sc.render(pos, d, seeds[:SPP], pull_every_frame=False, readback=False)
+                ref_gpu = {"device": RO.info(), "what": "the reference's unmodified OpenCL kernels (as shipped, -cl-mad-enable -cl-std=CL1.2) "
+                                                        "and host sequences on this GPU: 64 x render_frame of the bench scene from a reset "
+                                                        "cache (renderer.cpp:131-158); SDF build loop of signed_distance_field.cpp:7-35",
+                           "value": W * H * SPP / ms_pull / 1e3, "unit": "Msamples/s", "ms_per_frame": ms_pull / SPP,
+                           "kernel_only": {"value": W * H * SPP / ms_kernel / 1e3, "unit": "Msamples/s", "ms_per_frame": ms_kernel / SPP,
+                                           "what": "same launches without the per-frame blocking frame pull"},
+                           "sdf_build_ms": sc.sdf_ms, "sdf_iterations": sc.sdf_iterations, "jit_ms": sc.sdf_jit_ms + sc.render_jit_ms,
+                           "note": "every sampler of the reference requests CLK_FILTER_LINEAR on integer images (undefined in OpenCL 1.2); "
+                                   "NVIDIA's texture units interpolate, so as shipped the rays see other values than under the "
+                                   "spec-defined NEAREST reading this repository implements (DESIGN.md 2.1); same amount of work"}
+                sc.close()
+            else:
+                ref_gpu = {"unavailable": RO.error()}
+        except Exception as e:  # the baseline must never take the bench line down
+            ref_gpu = {"unavailable": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         hbm, peak_src = peaks()
         b_trace = alg_bytes_per_sample(counters, trace_only=True)
@@ -573,6 +606,7 @@ def run_ours(args, rank, world, local_rank):
                                         "env": counters["env"] / S, "primary_hits": counters["primary_hits"] / S,
                                         "admitted": counters["admitted"] / S}},
             "cpu_baseline": cpu,
+            "reference_on_gpu": ref_gpu,
             "closeup": closeup,
             "per_frame_schedule": per_frame,
             "saturated_cache": saturated,
