@@ -65,7 +65,8 @@ print("built", os.path.join(out, "libref.so"))
 # The same expanded kernel text, embedded as byte arrays, for the mini OpenCL host (ocl_host.cpp): on a GPU box whose driver
 # ships an OpenCL runtime it runs the reference's unmodified kernels on the GPU itself.  /root/reference does not exist there,
 # so the text travels inside the (git-ignored) binary; the generated include is deleted after the compile.
-OCL_FILES = ["ray_marching.cl", "signed_distance_field.cl", "buffer_reset.cl", "reference_volume_figures.cl"]
+OCL_FILES = ["ray_marching.cl", "signed_distance_field.cl", "buffer_reset.cl", "reference_volume_figures.cl", "histogram.cl",
+             "volume_filter.cl", "reference_volume_clip.cl"]
 inc = os.path.join(out, "gen_ocl_sources.inc")
 with open(inc, "w") as f:
     for name in OCL_FILES:

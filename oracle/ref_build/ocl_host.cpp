@@ -410,6 +410,116 @@ int ocl_fetch_stats(const int16_t* vol, int nx, int ny, int nz, int32_t out[4], 
   return rc;
 }
 
+// tf_sort_values as launched by renderer::render_tf, app/renderer.cpp:49-61.  The kernel indexes frame[x*height + y] with x up to
+// `width` and y up to `height`, i.e. it writes past width*height; the device buffer is padded so those writes stay
+// inside it, and only the first width*height counters are returned.  The caller must pass a range whose minima are the volume's
+// own (no negative index), as render_tf does.
+int ocl_histogram(const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4], uint32_t* bins_out, double* ms_out) {
+  if (ocl_init()) return -1;
+  cl_int err = 0;
+  const size_t nb = (size_t)width * height, padded = nb + (size_t)height + 64;
+  cl_mem img = make_image(CL_R, CL_SIGNED_INT16, nx, ny, nz, &err);
+  if (err != 0) { set_err("clCreateImage(volume) -> %d", (int)err); return -1; }
+  cl_mem bins = p_clCreateBuffer(g_ctx, CL_MEM_READ_WRITE, padded * sizeof(uint32_t), nullptr, &err);
+  cl_program p = nullptr;
+  cl_kernel k = nullptr;
+  int rc = -1;
+  do {
+    if (err != 0) { set_err("clCreateBuffer(bins) -> %d", (int)err); break; }
+    if (write_image(img, nx, ny, nz, vol)) break;
+    std::vector<uint32_t> zeros(padded, 0u);
+    if (p_clEnqueueWriteBuffer(g_q, bins, CL_TRUE, 0, padded * sizeof(uint32_t), zeros.data(), 0, nullptr, nullptr) != 0) { set_err("write bins"); break; }
+    if (build_kernel(ocl_src_histogram, "", "tf_sort_values", &p, &k)) break;
+    if (set_arg(k, 0, img) || set_arg(k, 1, bins) || set_arg(k, 2, width) || set_arg(k, 3, height) || set_arg(k, 4, range[0]) ||
+        set_arg(k, 5, range[1]) || set_arg(k, 6, range[2]) || set_arg(k, 7, range[3]))
+      break;
+    const size_t global[3] = {evenness(nx, 8), evenness(ny, 8), evenness(nz, 8)}, local[3] = {4, 4, 4};
+    p_clFinish(g_q);
+    const double t0 = now_ms();
+    if (launch(k, 3, global, local)) break;
+    if (p_clFinish(g_q) != 0) { set_err("clFinish(tf_sort_values)"); break; }
+    if (ms_out) *ms_out = now_ms() - t0;
+    if (p_clEnqueueReadBuffer(g_q, bins, CL_TRUE, 0, nb * sizeof(uint32_t), bins_out, 0, nullptr, nullptr) != 0) { set_err("read bins"); break; }
+    rc = 0;
+  } while (0);
+  if (k) p_clReleaseKernel(k);
+  if (p) p_clReleaseProgram(p);
+  if (bins) p_clReleaseMemObject(bins);
+  p_clReleaseMemObject(img);
+  return rc;
+}
+
+// reference_volume::filter, app/reference_volume.cpp:70-80 (volume_filter.cl bilateral_filter)
+int ocl_bilateral(const int16_t* vol, int nx, int ny, int nz, int16_t* out, double* ms_out) {
+  if (ocl_init()) return -1;
+  cl_int err = 0;
+  cl_mem img = make_image(CL_R, CL_SIGNED_INT16, nx, ny, nz, &err);
+  if (err != 0) { set_err("clCreateImage(volume) -> %d", (int)err); return -1; }
+  cl_mem buf = make_image(CL_R, CL_SIGNED_INT16, nx, ny, nz, &err);
+  cl_program p = nullptr;
+  cl_kernel k = nullptr;
+  int rc = -1;
+  do {
+    if (err != 0) { set_err("clCreateImage(buffer) -> %d", (int)err); break; }
+    if (write_image(img, nx, ny, nz, vol)) break;
+    if (build_kernel(ocl_src_volume_filter, "", "bilateral_filter", &p, &k)) break;
+    if (set_arg(k, 0, img) || set_arg(k, 1, buf)) break;
+    const size_t global[3] = {evenness(nx, 8), evenness(ny, 8), evenness(nz, 8)}, local[3] = {4, 4, 4};
+    p_clFinish(g_q);
+    const double t0 = now_ms();
+    if (launch(k, 3, global, local)) break;
+    if (p_clFinish(g_q) != 0) { set_err("clFinish(bilateral_filter)"); break; }
+    if (ms_out) *ms_out = now_ms() - t0;
+    if (read_image(buf, nx, ny, nz, out)) break;
+    rc = 0;
+  } while (0);
+  if (k) p_clReleaseKernel(k);
+  if (p) p_clReleaseProgram(p);
+  if (buf) p_clReleaseMemObject(buf);
+  p_clReleaseMemObject(img);
+  return rc;
+}
+
+// reference_volume::set_clipping, app/reference_volume.cpp:54-68 (reference_volume_clip.cl apply_clip)
+int ocl_clip(const int16_t* vol, int nx, int ny, int nz, const unsigned start[3], const unsigned size[3], int16_t* out, double* ms_out) {
+  if (ocl_init()) return -1;
+  cl_int err = 0;
+  cl_mem img = make_image(CL_R, CL_SIGNED_INT16, nx, ny, nz, &err);
+  if (err != 0) { set_err("clCreateImage(volume) -> %d", (int)err); return -1; }
+  cl_mem dst = make_image(CL_R, CL_SIGNED_INT16, size[0], size[1], size[2], &err);
+  cl_mem b0 = nullptr, b1 = nullptr;
+  cl_program p = nullptr;
+  cl_kernel k = nullptr;
+  int rc = -1;
+  do {
+    if (err != 0) { set_err("clCreateImage(cropped) -> %d", (int)err); break; }
+    const unsigned st[3] = {start[0], start[1], start[2]}, len[4] = {size[0], size[1], size[2], 4};
+    b0 = p_clCreateBuffer(g_ctx, CL_MEM_READ_WRITE, sizeof(st), nullptr, &err);
+    if (err == 0) b1 = p_clCreateBuffer(g_ctx, CL_MEM_READ_WRITE, sizeof(len), nullptr, &err);
+    if (err != 0) { set_err("clCreateBuffer(clip) -> %d", (int)err); break; }
+    if (p_clEnqueueWriteBuffer(g_q, b0, CL_TRUE, 0, sizeof(st), st, 0, nullptr, nullptr) != 0 ||
+        p_clEnqueueWriteBuffer(g_q, b1, CL_TRUE, 0, sizeof(len), len, 0, nullptr, nullptr) != 0) { set_err("write clip args"); break; }
+    if (write_image(img, nx, ny, nz, vol)) break;
+    if (build_kernel(ocl_src_reference_volume_clip, "", "apply_clip", &p, &k)) break;
+    if (set_arg(k, 0, img) || set_arg(k, 1, dst) || set_arg(k, 2, b0) || set_arg(k, 3, b1)) break;
+    const size_t global[3] = {evenness(size[0], 4), evenness(size[1], 4), evenness(size[2], 4)}, local[3] = {4, 4, 4};
+    p_clFinish(g_q);
+    const double t0 = now_ms();
+    if (launch(k, 3, global, local)) break;
+    if (p_clFinish(g_q) != 0) { set_err("clFinish(apply_clip)"); break; }
+    if (ms_out) *ms_out = now_ms() - t0;
+    if (read_image(dst, size[0], size[1], size[2], out)) break;
+    rc = 0;
+  } while (0);
+  if (k) p_clReleaseKernel(k);
+  if (p) p_clReleaseProgram(p);
+  if (b0) p_clReleaseMemObject(b0);
+  if (b1) p_clReleaseMemObject(b1);
+  if (dst) p_clReleaseMemObject(dst);
+  p_clReleaseMemObject(img);
+  return rc;
+}
+
 // What does this OpenCL implementation return for read_imagei with a CLK_FILTER_LINEAR sampler on a CL_SIGNED_INT16 image (undefined
 // by the specification, requested by every sampler of the reference)?  OUR OWN probe kernel, not reference code: for n float4
 // coordinates it records {linear sampler + float coords, nearest sampler + float coords, linear sampler + int coords}.

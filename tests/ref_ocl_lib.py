@@ -62,6 +62,34 @@ def fetch_stats(vol):
     return list(st), ms.value
 
 
+def histogram(vol, width, height, rng):
+    """tf_sort_values (renderer.cpp:49-61); rng minima must be the volume's own stats (no negative index)"""
+    vol = np.ascontiguousarray(vol, dtype=np.int16)
+    nz, ny, nx = vol.shape
+    bins = np.zeros(width * height, dtype=np.uint32)
+    ms = C.c_double(0)
+    _check(lib().ocl_histogram(_p(vol), nx, ny, nz, width, height, (C.c_float * 4)(*[float(x) for x in rng]), _p(bins), C.byref(ms)))
+    return bins, ms.value
+
+
+def bilateral(vol):
+    vol = np.ascontiguousarray(vol, dtype=np.int16)
+    nz, ny, nx = vol.shape
+    out = np.zeros_like(vol)
+    ms = C.c_double(0)
+    _check(lib().ocl_bilateral(_p(vol), nx, ny, nz, _p(out), C.byref(ms)))
+    return out, ms.value
+
+
+def clip(vol, start, size):
+    vol = np.ascontiguousarray(vol, dtype=np.int16)
+    nz, ny, nx = vol.shape
+    out = np.zeros((size[2], size[1], size[0]), dtype=np.int16)
+    ms = C.c_double(0)
+    _check(lib().ocl_clip(_p(vol), nx, ny, nz, (C.c_uint * 3)(*start), (C.c_uint * 3)(*size), _p(out), C.byref(ms)))
+    return out, ms.value
+
+
 def probe_sample(vol, coords):
     """[n, 3] ints: read_imagei on a SIGNED_INT16 3-D image with {linear sampler + float coords, nearest sampler + float coords,
     linear sampler + int coords} at the float coordinates `coords` [n, 3] (x, y, z) — our own probe kernel"""

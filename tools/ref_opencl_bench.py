@@ -77,6 +77,40 @@ def main():
                           "frame_opencl_vs_oracle": frame_metrics(ocl_frame, orc_frame), "frame_opencl_vs_cuda": frame_metrics(ocl_frame, cu_frame)}), flush=True)
         r.close(); env.close(); vol.close(); sc.close()
 
+    # ---- volume kernels: tf_sort_values, bilateral_filter, apply_clip ----------------------------------------------------------
+    for nearest in (True, False):
+        R.set_nearest(nearest)
+        for dims in ((45, 37, 29), (128, 128, 128), (n_big, n_big, n_big)):
+            v = synth.synth_ct(0, dims=dims) if dims[0] != dims[1] else synth.synth_ct(dims[0])
+            vol = api.Volume(ctx, v)
+            st = vol.stats()
+            rng = [float(x) for x in st]
+            small = v.size <= 128 ** 3
+            hb, h_ms = R.histogram(v, 500, 500, rng)
+            cu_h = vol.histogram(500, 500, rng)
+            fb, f_ms = R.bilateral(v)
+            cs = tuple(max(d // 8, 1) for d in dims)
+            size = tuple(dims[k] - 2 * cs[k] for k in range(3))
+            cb, c_ms = R.clip(v, cs, size)
+            vol.clip(cs, tuple(cs[k] + size[k] for k in range(3)))
+            cu_c = vol.download()
+            vol2 = api.Volume(ctx, v)
+            vol2.filter()
+            cu_f = vol2.download()
+            row = {"volume_ops": "x".join(map(str, dims)), "sampler": "CLK_FILTER_NEAREST (one-token substitution)" if nearest else "as shipped",
+                   "reference_opencl_ms": {"tf_sort_values": h_ms, "bilateral_filter": f_ms, "apply_clip": c_ms},
+                   "histogram_opencl_vs_cuda": {"bins_differing": int((hb != cu_h).sum()), "voxels_moved": int(np.abs(hb.astype(np.int64) - cu_h.astype(np.int64)).sum() // 2),
+                                                "total_opencl": int(hb.sum()), "total_cuda": int(cu_h.sum())},
+                   "bilateral_opencl_vs_cuda": {"identical": float((fb == cu_f).mean()), "max_abs_diff": int(np.abs(fb.astype(np.int32) - cu_f.astype(np.int32)).max())},
+                   "clip_opencl_eq_cuda": bool(np.array_equal(cb, cu_c))}
+            if small:
+                ob = o.histogram(v, 500, 500, rng)
+                of = o.bilateral(v)
+                row["histogram_opencl_vs_oracle"] = {"bins_differing": int((hb != ob).sum()), "voxels_moved": int(np.abs(hb.astype(np.int64) - ob.astype(np.int64)).sum() // 2)}
+                row["bilateral_opencl_vs_oracle"] = {"identical": float((fb == of).mean()), "max_abs_diff": int(np.abs(fb.astype(np.int32) - of.astype(np.int32)).max())}
+            print(json.dumps(row), flush=True)
+            vol2.close(); vol.close()
+
     # ---- the bench scene, reference-on-GPU vs CUDA ---------------------------------------------------------------------------
     for nearest in (False, True):
         bench_scene(ctx, n_big, frames, tf_src, nearest)
