@@ -164,3 +164,17 @@ def test_live_image_filter2d():
         img = rs.integers(0, 256, (h, w, 4), dtype=np.uint8)
         img[: h // 3, : w // 3] = img[0, 0]
         assert np.array_equal(o.image_filter2d(img, k, sigma), R.image_filter2d(img, k, sigma)), (h, w, k, sigma)
+
+
+def test_opencl_host_library_loads_and_reports_unavailability():
+    # oracle/_ref/libref_ocl.so (the reference's OpenCL kernels on a real device): present when /root/reference was there to
+    # build it; without an OpenCL platform it must say so instead of failing (the GPU tests that use it are then skipped)
+    import ref_ocl_lib as RO
+    if not os.path.exists(RO.SO):
+        pytest.skip("oracle/_ref/libref_ocl.so not built")
+    l = RO.lib()
+    for name in ("ocl_init", "ocl_scene_create", "ocl_scene_render", "ocl_scene_cache_download", "ocl_scene_sdf_download",
+                 "ocl_fetch_stats", "ocl_histogram", "ocl_bilateral", "ocl_clip", "ocl_probe_sample", "ocl_set_nearest"):
+        assert hasattr(l, name)
+    if not RO.available():
+        assert RO.error() != ""
