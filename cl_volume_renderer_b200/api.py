@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libvr.so")
 VR_TF_USE_GRADIENT = 1
 VR_TF_THRESHOLD = 2
 VR_TF_MAX_RECTS = 16
+VR_SAMPLING_NEAREST = 0    # the filter OpenCL defines for integer images (default)
+VR_SAMPLING_HW_LINEAR = 1  # the reference's samplers as NVIDIA hardware executes them (texture-unit interpolation)
 VR_FILTER2D_REFERENCE = 0  # 2d_image_filter.cl as written
 VR_FILTER2D_BILATERAL = 1  # the corrected bilateral
 
@@ -81,6 +83,7 @@ SYMBOLS = {
     "vr_render_frame": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, _P]),
     "vr_render_frames": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int, _P]),
     "vr_render_tf": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "vr_renderer_set_sampling": (C.c_int, [_P, C.c_int]),
     "vr_renderer_filter_frame": (C.c_int, [_P, C.c_int, C.c_float, C.c_int, _P]),
     "vr_image_filter": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "vr_renderer_host_frame": (_P, [_P]),
@@ -482,6 +485,10 @@ class Renderer:
     @property
     def xchg_bytes(self):
         return int(lib().vr_renderer_xchg_bytes(self.h))
+
+    def set_sampling(self, mode):
+        """takes effect at the next flush_changes()"""
+        _check(lib().vr_renderer_set_sampling(self.h, mode))
 
     def set_trace_mode(self, mode):
         _check(lib().vr_renderer_set_trace_mode(self.h, mode))

@@ -480,10 +480,87 @@ extern "C" int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_rendere
   return VR_OK;
 }
 
+// VR_SAMPLING_HW_LINEAR: the current volume and the environment map behind texture objects (CUDA arrays owned by the renderer)
+static void release_textures(vr_renderer* r) {
+  if (!r->vol_tex && !r->env_tex && !r->vol_arr && !r->env_arr) return;
+  cudaStreamSynchronize(r->ctx->stream);
+  if (r->vol_tex) cudaDestroyTextureObject(r->vol_tex);
+  if (r->env_tex) cudaDestroyTextureObject(r->env_tex);
+  if (r->vol_arr) cudaFreeArray(r->vol_arr);
+  if (r->env_arr) cudaFreeArray(r->env_arr);
+  r->vol_tex = r->env_tex = 0;
+  r->vol_arr = r->env_arr = nullptr;
+}
+
+static int build_textures(vr_renderer* r) {
+  release_textures(r);
+  vr_ctx* ctx = r->ctx;
+  const vr_volume* v = r->vol;
+  const vr_envmap* env = r->env;
+  int st = VR_OK;
+  cudaChannelFormatDesc d16 = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindSigned);
+  cudaError_t e = cudaMalloc3DArray(&r->vol_arr, &d16, make_cudaExtent(v->nx, v->ny, v->nz));
+  if (e == cudaSuccess) {
+    cudaMemcpy3DParms p{};
+    p.srcPtr = make_cudaPitchedPtr(const_cast<int16_t*>(v->current()), (size_t)v->nx * sizeof(int16_t), v->nx, v->ny);
+    p.dstArray = r->vol_arr;
+    p.extent = make_cudaExtent(v->nx, v->ny, v->nz);
+    p.kind = cudaMemcpyDeviceToDevice;
+    e = cudaMemcpy3DAsync(&p, ctx->stream);
+  }
+  if (e == cudaSuccess) {
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = r->vol_arr;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;  // CLK_ADDRESS_CLAMP: border colour 0
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 0;
+    e = cudaCreateTextureObject(&r->vol_tex, &rd, &td, nullptr);
+  }
+  if (e == cudaSuccess) {
+    cudaChannelFormatDesc d8 = cudaCreateChannelDesc<uchar4>();
+    e = cudaMallocArray(&r->env_arr, &d8, env->w, env->h);
+  }
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DToArrayAsync(r->env_arr, 0, 0, env->texels, (size_t)env->w * 4, (size_t)env->w * 4, env->h, cudaMemcpyDeviceToDevice,
+                                 ctx->stream);
+  if (e == cudaSuccess) {
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = r->env_arr;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;  // CLK_ADDRESS_CLAMP_TO_EDGE
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;                                       // CLK_NORMALIZED_COORDS_TRUE
+    e = cudaCreateTextureObject(&r->env_tex, &rd, &td, nullptr);
+  }
+  if (e != cudaSuccess) {
+    vr_set_error("vr_renderer_flush: texture setup for hw-linear sampling: %s", cudaGetErrorString(e));
+    release_textures(r);
+    st = VR_ERR_CUDA;
+  }
+  return st;
+}
+
+extern "C" int vr_renderer_set_sampling(vr_renderer* r, int mode) {
+  VR_REQUIRE(r && (mode == VR_SAMPLING_NEAREST || mode == VR_SAMPLING_HW_LINEAR), "vr_renderer_set_sampling: unknown mode");
+  if (mode != r->sampling) {
+    VR_CUDA(cudaSetDevice(r->ctx->device));
+    release_textures(r);  // rebuilt by the next flush when needed
+    r->sampling = mode;
+    r->primary_valid = false;
+  }
+  return VR_OK;
+}
+
 extern "C" void vr_renderer_destroy(vr_renderer* r) {
   if (!r) return;
   cudaSetDevice(r->ctx->device);
   cudaStreamSynchronize(r->ctx->stream);
+  release_textures(r);
   vr_sdf_destroy(r->sdf);
   pool_free(r->ctx, r->cache);
   pool_free(r->ctx, r->hit);
@@ -574,6 +651,7 @@ extern "C" int vr_renderer_flush(vr_renderer* r) {
   vr_sdf_destroy(r->sdf);
   r->sdf = fresh;
   VR_CUDA(cudaMemsetAsync(r->hit, 0xFF, (size_t)r->W * r->H * 4, r->ctx->stream));
+  if (r->sampling == VR_SAMPLING_HW_LINEAR) VR_TRY(build_textures(r));
   return VR_OK;
 }
 

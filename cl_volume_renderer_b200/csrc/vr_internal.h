@@ -112,6 +112,11 @@ struct vr_renderer {
   uchar4* frame = nullptr;    // device RGBA8
   uint8_t* frame_host = nullptr;  // pinned staging (used when the caller's buffer is pageable)
   int token_cap = 256;
+  // vr_renderer_set_sampling: VR_SAMPLING_HW_LINEAR traces through texture objects built by the flush (copies of the current
+  // volume and of the environment map in CUDA arrays)
+  int sampling = VR_SAMPLING_NEAREST;
+  cudaArray_t vol_arr = nullptr, env_arr = nullptr;
+  cudaTextureObject_t vol_tex = 0, env_tex = 0;
   // Which cache entries can be non-zero: 0 none (just reset), 1 only cache[hit[pix]] of the current `hit` buffer (every trace
   // since the last reset used the camera / rows in dirty_pos.. below), 2 unknown (full reset needed).  A frame reset then
   // clears W*H entries instead of 8 bytes x voxels (vr_renderer_reset_cache).

@@ -24,6 +24,9 @@ struct RenderParams {
   VolView vol;
   SdfView sdf;
   cudaSurfaceObject_t sdf_surf;  // VR_SDF_SURF=1: the field behind a surface object (k_trace_pt<.., SURF>)
+  // VR_SAMPLING_HW_LINEAR (k_trace<.., LINEAR>): the volume (int16, linear filter, border 0, unnormalised coordinates) and the
+  // environment map (RGBA8, linear filter, clamp to edge, normalised coordinates) behind texture objects with normalised-float reads
+  cudaTextureObject_t vol_tex, env_tex;
   const uchar4* __restrict__ env;
   int env_w, env_h;
   uint32_t* __restrict__ cache;
@@ -112,7 +115,24 @@ __device__ __forceinline__ bool cut_box(const VolView& v, Ray shot, f3* cut_poin
   return res;
 }
 
-// sample_environment_map, utility_environment_map.cl:3-13: normalised coords, clamp to edge, nearest texel
+// What NVIDIA's OpenCL returns for read_imagei with the reference's CLK_FILTER_LINEAR | CLK_ADDRESS_CLAMP sampler on the int16
+// volume (undefined by OpenCL 1.2): the texture unit interpolates the texels (centres at +0.5, 8-bit weights,
+// border 0) and the result is rounded to an integer.  The same unit through a normalised-float read gives value / 32767;
+// rint(t * 32767) in double equals the OpenCL value on all 48 196 probe samples (profiles/r1b_cuda_texture_vs_opencl_linear.txt).
+__device__ __forceinline__ int vol_linear(const RenderParams& p, float x, float y, float z) {
+  return __double2int_rn((double)tex3D<float>(p.vol_tex, x, y, z) * 32767.0);
+}
+// gradient_prewitt_nn at a float position with that sampler, utility_filter.cl:2-35: taps at p +- 1 on each axis
+__device__ __forceinline__ f3 gradient_linear(const RenderParams& p, f3 o) {
+  const int dx = vol_linear(p, o.x + 1.0f, o.y, o.z) - vol_linear(p, o.x - 1.0f, o.y, o.z);
+  const int dy = vol_linear(p, o.x, o.y + 1.0f, o.z) - vol_linear(p, o.x, o.y - 1.0f, o.z);
+  const int dz = vol_linear(p, o.x, o.y, o.z + 1.0f) - vol_linear(p, o.x, o.y, o.z - 1.0f);
+  return {(float)dx, (float)dy, (float)dz};
+}
+
+// sample_environment_map, utility_environment_map.cl:3-13: normalised coords, clamp to edge; nearest texel, or (LINEAR) the
+// texture unit's bilinear interpolation of the RGBA8 texels rounded to integers
+template <bool LINEAR = false>
 __device__ __forceinline__ uchar4 env_sample(const RenderParams& p, f3 d) {
   float u = atan2f(d.x, d.z);
   float v = asinf(-d.y);
@@ -120,6 +140,11 @@ __device__ __forceinline__ uchar4 env_sample(const RenderParams& p, f3 d) {
   v = v * 0.318309886f;
   u = u + 0.5f;
   v = v + 0.5f;
+  if (LINEAR) {
+    const float4 t = tex2D<float4>(p.env_tex, u, v);
+    return make_uchar4((unsigned char)__double2int_rn((double)t.x * 255.0), (unsigned char)__double2int_rn((double)t.y * 255.0),
+                       (unsigned char)__double2int_rn((double)t.z * 255.0), (unsigned char)__double2int_rn((double)t.w * 255.0));
+  }
   int ix = f2i(floorf(u * (float)p.env_w));
   int iy = f2i(floorf(v * (float)p.env_h));
   ix = min(max(ix, 0), p.env_w - 1);
@@ -146,10 +171,36 @@ __device__ __forceinline__ f3 hemisphere_reflective(f3 normal, int seed, float r
 //   r        in/out: the ray, advanced to the event position
 //   grad     out: gradient at the hit voxel (valid when EV_HIT) — the shading normal needs it next
 //   color    in/out: written only when a TF clause with a colour matched (like `*color = tmp_color`)
-template <bool COUNT>
+template <bool COUNT, bool LINEAR = false>
 __device__ __forceinline__ int march_to_next_event(const RenderParams& p, Ray& r, f3& grad, int color[4],
                                                    int& colour_clause, unsigned& steps) {
   const int nx = p.vol.nx, ny = p.vol.ny, nz = p.vol.nz;
+  if (LINEAR) {
+    // The reference's loop as written, with the sampler behaviour of NVIDIA hardware: the SDF is read at integer coordinates
+    // (a plain texel read), value and gradient taps at the float position are interpolated.  The event test then no longer
+    // coincides with the sign of the (per-voxel) SDF, so every step evaluates the transfer function (7 fetches + 1 SDF byte).
+    for (int i = 0; i < 70; ++i) {
+      const int d = p.sdf.at(f2i(r.o.x), f2i(r.o.y), f2i(r.o.z));  // march(), utility_ray.cl:148-154
+      const float step_size = max_cl((float)d, 0.5f);
+      r.o = r.o + step_size * r.d;
+      if (COUNT) steps++;
+      const bool exited = (r.o.x < 0.0f) | (r.o.y < 0.0f) | (r.o.z < 0.0f) | ((float)nx < r.o.x) | ((float)ny < r.o.y) | ((float)nz < r.o.z);
+      if (exited) return EV_EXIT;
+      grad = gradient_linear(p, r.o);                              // get_event_and_value, utility_ray.cl:126-138
+      const int value = vol_linear(p, r.o.x, r.o.y, r.o.z);
+      const int clause = tf_match(p.tf, (int)(short)value, f2s(length3(grad)));
+      if (clause == 0) continue;
+      if (clause > 0) {
+        const vr_tf_rect& q = p.tf.r[clause - 1];
+        if (!(q.flags & VR_TF_THRESHOLD)) {
+          color[0] = q.rgba[0]; color[1] = q.rgba[1]; color[2] = q.rgba[2]; color[3] = q.rgba[3];
+          colour_clause = clause;
+        }
+      }
+      return EV_HIT;
+    }
+    return EV_NONE;
+  }
   // SDF value at trunc(origin); border (any coordinate outside the field) reads 0
   int d = p.sdf.at(f2i(r.o.x), f2i(r.o.y), f2i(r.o.z));
   for (int i = 0; i < 70; ++i) {
@@ -186,8 +237,8 @@ __device__ __forceinline__ int march_to_next_event(const RenderParams& p, Ray& r
   return EV_NONE;
 }
 
-template <bool COUNT, bool QUEUE>
-__global__ void __launch_bounds__(128, 12) k_trace(const RenderParams p) {
+template <bool COUNT, bool QUEUE, bool LINEAR = false>
+__global__ void __launch_bounds__(128, LINEAR ? 6 : 12) k_trace(const RenderParams p) {
   // one warp = an 8x4 pixel tile: neighbouring primary rays walk neighbouring voxels
   const int x = blockIdx.x * 8 + (threadIdx.x & 7);
   const int y = p.row0 + blockIdx.y * 16 + (threadIdx.x >> 3);
@@ -209,11 +260,11 @@ __global__ void __launch_bounds__(128, 12) k_trace(const RenderParams p) {
     f3 grad = {0.0f, 0.0f, 0.0f};
     int color[4] = {0, 0, 0, 0};
     int colour_clause = 0;
-    if (is_cut) ev = march_to_next_event<COUNT>(p, cur, grad, color, colour_clause, c_steps);
+    if (is_cut) ev = march_to_next_event<COUNT, LINEAR>(p, cur, grad, color, colour_clause, c_steps);
 
     if (ev != EV_HIT) {
       // ray_marching.cl:172-178,188-194: environment colour, alpha 200
-      uchar4 e = env_sample(p, vray.d);
+      uchar4 e = env_sample<LINEAR>(p, vray.d);
       e.w = 200;
       p.frame[pix] = e;
       p.hit[pix] = VR_MISS;
@@ -272,10 +323,10 @@ __global__ void __launch_bounds__(128, 12) k_trace(const RenderParams p) {
           cur.o = cur.o + normal * 2.0f;
           float atten = fabsf(dot3(cur.d, normal));
           for (int i = 8; i <= 10; ++i) {
-            ev = march_to_next_event<COUNT>(p, cur, grad, color, colour_clause, c_steps);
+            ev = march_to_next_event<COUNT, LINEAR>(p, cur, grad, color, colour_clause, c_steps);
             if (ev == EV_EXIT) {
               const float factor = 8.0f / (float)i;
-              const uchar4 lm = env_sample(p, cur.d);
+              const uchar4 lm = env_sample<LINEAR>(p, cur.d);
               c_env++;
               // uint += float (ray_marching.cl:59-61): to float, add, truncate back
               bv0 = f2u((float)bv0 + atten * r_energy * (float)lm.x * factor / 1.0f);
@@ -698,6 +749,7 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     p.vol = VolView{r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz};
     p.sdf = SdfView{r->sdf->field, r->sdf->nx, r->sdf->ny, r->sdf->nz, r->sdf->nx / 8 + 1, r->sdf->ny / 8 + 1};
     p.sdf_surf = r->sdf->surf;
+    p.vol_tex = r->vol_tex; p.env_tex = r->env_tex;
     p.env = r->env->texels;
     p.env_w = r->env->w;
     p.env_h = r->env->h;
@@ -739,7 +791,13 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     }
     const size_t pixels = (size_t)r->W * rows * nframes;
     dim3 grid(div_up(r->W, 8), div_up(rows, 16), nframes);
-    if (r->trace_mode >= 1) {
+    if (r->sampling == VR_SAMPLING_HW_LINEAR) {
+      // the literal per-pixel kernel with the texture-unit sampling (vr_renderer_set_sampling); textures are built by the flush
+      if (!r->vol_tex || !r->env_tex) { vr_set_error("vrk_render: hw-linear sampling needs a vr_renderer_flush after vr_renderer_set_sampling"); return VR_ERR_INVALID; }
+      r->primary_valid = false;
+      if (r->count) k_trace<true, false, true><<<grid, 128, 0, ctx->stream>>>(p);
+      else k_trace<false, false, true><<<grid, 128, 0, ctx->stream>>>(p);
+    } else if (r->trace_mode >= 1) {
       // mode 1 (hybrid): dense thread-per-pixel k_trace per frame queues admitted hits, persistent warps run their secondary paths
       // mode 2 (primary reuse, default): k_primary once per pixel, persistent warps run admission + secondary paths per (pixel, frame)
       const bool reuse = r->trace_mode == 2;

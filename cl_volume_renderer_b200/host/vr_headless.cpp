@@ -6,6 +6,9 @@
 //   vr_headless <volume.nrrd> <envmap.hdr|.ppm|.WxH.rgba> [--w 1920] [--h 1080] [--spp 64] [--out frame.ppm]
 //               [--pos x y z] [--look a b] [--tf "min_v,max_v,min_g,max_g,r,g,b,a;..."] [--filter] [--clip x0 y0 z0 x1 y1 z1]
 //               [--tf-image tf.ppm] [--raw frame.rgba] [--frame-filter kernel_size sigma reference|bilateral]
+//               [--sampling nearest|hw-linear]
+// --sampling hw-linear: value / gradient / environment reads interpolated by the texture unit, as NVIDIA hardware executes the
+// reference's CLK_FILTER_LINEAR samplers (default nearest: the filter OpenCL defines for integer images).
 // --frame-filter runs opencl_kernels/2d_image_filter.cl over the final frame ("reference" = the kernel as written).
 #include <cstring>
 #include <fstream>
@@ -32,7 +35,7 @@ int main(int argc, char** argv) {
   std::string out = "frame.ppm", raw_out, tf_image, tf_spec;
   double pos[3] = {0, 0, 0}, look[2] = {0.9, 6.183};  // ui.cpp:178
   bool have_pos = false, filter = false, clip = false;
-  int ff_k = -1, ff_mode = VR_FILTER2D_REFERENCE;
+  int ff_k = -1, ff_mode = VR_FILTER2D_REFERENCE, sampling = VR_SAMPLING_NEAREST;
   float ff_sigma = 1.0f;
   size_t cmin[3] = {0, 0, 0}, cmax[3] = {0, 0, 0};
   for (int i = 3; i < argc; ++i) {
@@ -46,6 +49,12 @@ int main(int argc, char** argv) {
     else if (a == "--tf-image") { need(1); tf_image = argv[++i]; }
     else if (a == "--tf") { need(1); tf_spec = argv[++i]; }
     else if (a == "--filter") filter = true;
+    else if (a == "--sampling") {
+      need(1);
+      const std::string m = argv[++i];
+      if (m != "nearest" && m != "hw-linear") { std::cerr << "--sampling must be nearest or hw-linear\n"; return 2; }
+      sampling = m == "nearest" ? VR_SAMPLING_NEAREST : VR_SAMPLING_HW_LINEAR;
+    }
     else if (a == "--frame-filter") {
       need(3);
       ff_k = atoi(argv[++i]);
@@ -63,6 +72,7 @@ int main(int argc, char** argv) {
   clw_context ctx;
   renderer render_ctx(ctx);
   frame_emitter* emitter = &render_ctx;
+  render_ctx.set_sampling(sampling);
 
   nrrd_loader vloader;
   volume_block v = vloader.load_file(argv[1]);

@@ -312,6 +312,12 @@ class renderer : public frame_emitter {
     vr_fail_hard(vr_renderer_filter_frame(r, kernel_size, sigma, mode, vr_renderer_host_frame(r)));
     return vr_renderer_host_frame(r);
   }
+  // VR_SAMPLING_NEAREST (default: the filter OpenCL defines for the reference's integer images) or VR_SAMPLING_HW_LINEAR (what
+  // NVIDIA hardware does with the reference's CLK_FILTER_LINEAR samplers); takes effect at the next flush_changes()
+  void set_sampling(int mode) {
+    sampling = mode;
+    if (r) vr_fail_hard(vr_renderer_set_sampling(r, mode));
+  }
   vr_renderer* handle() const { return r; }
 
  private:
@@ -319,6 +325,7 @@ class renderer : public frame_emitter {
     if (r && w == rw && h == rh) return;
     if (r) vr_renderer_destroy(r);
     vr_fail_hard(vr_renderer_create(ctx.get(), w, h, &r));
+    vr_fail_hard(vr_renderer_set_sampling(r, sampling));
     // the UI calls render_frame once per sample while the camera rests (ui.cpp:296): keep the seed-independent primary
     // segment between calls; camera moves, flushes and row-window changes re-march (include/vr.h)
     vr_fail_hard(vr_renderer_set_primary_reuse(r, 2));
@@ -336,6 +343,7 @@ class renderer : public frame_emitter {
   clw_context& ctx;
   vr_renderer* r = nullptr;
   int rw = 0, rh = 0;
+  int sampling = VR_SAMPLING_NEAREST;
   bool flush_pending = false, flushed_once = false;
   std::vector<unsigned char> tfframe;
   const reference_volume* volume = nullptr;

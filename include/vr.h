@@ -149,6 +149,19 @@ int vr_cache_download(const vr_renderer* r, uint16_t* out);
 /* the SDF the renderer built at the last flush (renderer.hpp:19) */
 const vr_sdf* vr_renderer_sdf(const vr_renderer* r);
 
+/* ---- sampling of the volume and the environment map by the path tracer ----------------------------------------------------
+ * Every sampler of the reference requests CLK_FILTER_LINEAR on INTEGER images (utility_ray.cl:130,149, utility_filter.cl:4,
+ * utility_environment_map.cl:4), for which OpenCL 1.2 defines no result.
+ *   VR_SAMPLING_NEAREST   (default) the filter OpenCL defines for integer images: texel floor(coord), border 0.  All schedules.
+ *   VR_SAMPLING_HW_LINEAR what NVIDIA hardware does with the kernels AS SHIPPED (measured through the driver's OpenCL runtime):
+ *                         value and gradient taps of get_event_and_value and the environment colour are interpolated by the
+ *                         texture unit (texel centres at +0.5, 8-bit weights, border 0 / clamp to edge) and rounded to
+ *                         integers; integer-coordinate reads (the SDF read of march) stay texel reads.  One thread per pixel
+ *                         and frame (the reference's own schedule); the SDF build is unaffected (samplerless reads).
+ * Takes effect at the next vr_renderer_flush (which copies the volume and the environment map into texture arrays). */
+enum { VR_SAMPLING_NEAREST = 0, VR_SAMPLING_HW_LINEAR = 1 };
+int vr_renderer_set_sampling(vr_renderer* r, int mode);
+
 /* ---- 2-D frame filter (opencl_kernels/2d_image_filter.cl:6-43 `bilateral_filter(frame, kernel_size, sigma)`) -------
  * The reference ships this kernel but no host code launches it; the call takes the kernel's own arguments.
  *   VR_FILTER2D_REFERENCE : the kernel's arithmetic exactly as written (bit-identical to the source compiled for the CPU):

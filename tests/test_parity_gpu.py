@@ -500,3 +500,38 @@ def test_renderer_filter_frame_and_argument_checks(vr_ctx):
         with pytest.raises(api.VrError):
             r.filter_frame(*bad)
     r.close(); env.close(); vol.close()
+
+
+# ---- sampling modes -------------------------------------------------------------------------------------------------------
+def test_sampling_mode_switch_and_texture_lifecycle(vr_ctx):
+    """VR_SAMPLING_HW_LINEAR needs a flush (textures), renders, differs from the NEAREST reading on interpolated data, and switching
+    back restores the NEAREST results exactly (parity of the linear mode itself: tests/test_ref_opencl_gpu.py)."""
+    n, W, H = 48, 96, 64
+    v, envimg, tf = synth.synth_ct(n), synth.synth_env(128, 64), synth.default_tf()
+    vol, env = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
+    r = api.Renderer(vr_ctx, W, H)
+    r.image_set(vol, env)
+    r.set_tf(tf)
+    r.flush_changes()
+    pos, d = synth.default_camera(n)
+    seeds = synth.glibc_rand(3)
+    for s in seeds:
+        near_frame = r.render_frame(pos, d, s)
+    near_cache = r.cache_download()
+    r.set_sampling(api.VR_SAMPLING_HW_LINEAR)
+    with pytest.raises(api.VrError):
+        r.render_frame(pos, d, seeds[0])  # no textures yet
+    r.flush_changes()
+    for s in seeds:
+        lin_frame = r.render_frame(pos, d, s)
+    lin_cache = r.cache_download()
+    assert lin_cache.any() and not np.array_equal(lin_cache, near_cache)
+    assert (lin_frame[..., 3] == near_frame[..., 3]).mean() > 0.9  # same silhouette up to the interpolation at the surface
+    with pytest.raises(api.VrError):
+        r.set_sampling(7)
+    r.set_sampling(api.VR_SAMPLING_NEAREST)
+    r.flush_changes()
+    for s in seeds:
+        again = r.render_frame(pos, d, s)
+    assert np.array_equal(r.cache_download(), near_cache) and np.array_equal(again, near_frame)
+    r.close(); env.close(); vol.close()

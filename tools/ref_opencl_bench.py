@@ -50,7 +50,7 @@ def main():
 
     # ---- parity on a small scene: reference-on-GPU vs CPU oracle vs CUDA -------------------------------------------------
     for (n, W, H, nf, cam, nearest) in [(64, 160, 120, 6, "default", True), (96, 200, 136, 3, "closeup", True), (128, 320, 240, 16, "default", True),
-                                        (64, 160, 120, 6, "default", False)]:
+                                        (64, 160, 120, 6, "default", False), (96, 200, 136, 3, "closeup", False), (128, 320, 240, 16, "default", False)]:
         R.set_nearest(nearest)
         v, envimg = synth.synth_ct(n), synth.synth_env(128, 64)
         pos, d = synth.default_camera(n) if cam == "default" else synth.closeup_camera(n)
@@ -65,11 +65,14 @@ def main():
             orc_frame = orc.render_frame(pos, d, s)
         vol, env = api.Volume(ctx, v), api.EnvMap(ctx, envimg)
         r = api.Renderer(ctx, W, H)
+        if not nearest:
+            r.set_sampling(api.VR_SAMPLING_HW_LINEAR)   # the CUDA path sampling through the texture unit, like the kernels as shipped
         r.image_set(vol, env); r.next_event_code_set(tf_src); r.flush_changes()
         for s in seeds:
             cu_frame = r.render_frame(pos, d, s)
         cu_cache = r.cache_download()
         print(json.dumps({"parity": f"{n}^3 {W}x{H} {nf} frames {cam}", "sampler": "CLK_FILTER_NEAREST (one-token substitution)" if nearest else "as shipped (CLK_FILTER_LINEAR on integer images)",
+                          "cuda_sampling": "VR_SAMPLING_NEAREST" if nearest else "VR_SAMPLING_HW_LINEAR",
                           "sdf_opencl_eq_oracle": bool(np.array_equal(sc.sdf(), want_sdf)), "sdf_opencl_eq_cuda": bool(np.array_equal(sc.sdf(), r.sdf_download())),
                           "sdf_iterations": sc.sdf_iterations, "stats_opencl": st, "stats_oracle": o.fetch_stats(v), "stats_cuda": vol.stats(),
                           "cache_opencl_vs_oracle": cache_metrics(ocl_cache, orc.cache), "cache_opencl_vs_cuda": cache_metrics(ocl_cache, cu_cache),
