@@ -138,6 +138,8 @@ def bench_scene(ctx, n_big, frames, tf_src, nearest):
     _, stats_ms = R.fetch_stats(v)
     vol, env = api.Volume(ctx, v), api.EnvMap(ctx, envimg)
     r = api.Renderer(ctx, W, H)
+    if not nearest:
+        r.set_sampling(api.VR_SAMPLING_HW_LINEAR)   # like for like: the CUDA path sampling through the texture unit
     r.image_set(vol, env); r.next_event_code_set(tf_src)
     ctx.synchronize(); t0 = time.perf_counter()
     r.flush_changes(); ctx.synchronize()
@@ -161,7 +163,8 @@ def bench_scene(ctx, n_big, frames, tf_src, nearest):
                           "scene_create_s": create_s, "fetch_stats_ms": stats_ms,
                           "render_ms_per_frame_with_pull": ms_pull / frames, "msamples_per_s_with_pull": samples / ms_pull / 1e3,
                           "render_ms_per_frame_kernel_only": ms_nopull / frames, "msamples_per_s_kernel_only": samples / ms_nopull / 1e3},
-                      "cuda": {"flush_ms_cache_reset_plus_sdf": cu_flush_ms, "render_ms_per_frame_batched": cu_ms / frames,
+                      "cuda": {"sampling": "VR_SAMPLING_NEAREST" if nearest else "VR_SAMPLING_HW_LINEAR (k_trace<LINEAR>, thread per pixel and frame)",
+                               "flush_ms_cache_reset_plus_sdf": cu_flush_ms, "render_ms_per_frame_batched": cu_ms / frames,
                                "msamples_per_s_batched": samples / cu_ms / 1e3, "render_ms_per_frame_with_pull": cu_pull_ms / frames,
                                "msamples_per_s_with_pull": samples / cu_pull_ms / 1e3},
                       "sdf_opencl_eq_cuda": bool(np.array_equal(sc.sdf(), r.sdf_download())),
