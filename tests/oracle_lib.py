@@ -162,6 +162,21 @@ def image_bilateral2d(rgba, kernel_size, sigma):
     return out
 
 
+def set_sampling(mode):
+    """0: NEAREST (default); 1: the linear filtering NVIDIA hardware applies to the reference's integer images (oracle.cpp
+    hw_linear_fetch).  Applies to Renderer.render_frame from now on."""
+    lib().orc_set_sampling(int(mode))
+
+
+def hw_linear_fetch(vol, coords):
+    vol = np.ascontiguousarray(vol, dtype=np.int16)
+    nz, ny, nx = vol.shape
+    c = np.ascontiguousarray(coords, dtype=np.float32)
+    out = np.empty(len(c), dtype=np.int32)
+    lib().orc_hw_linear_fetch(_p(vol), nx, ny, nz, _p(c), len(c), _p(out))
+    return out
+
+
 def env_lookup(env_rgba, dirs):
     env_rgba = np.ascontiguousarray(env_rgba, dtype=np.uint8)
     h, w = env_rgba.shape[:2]

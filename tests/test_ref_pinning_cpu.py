@@ -178,3 +178,27 @@ def test_opencl_host_library_loads_and_reports_unavailability():
         assert hasattr(l, name)
     if not RO.available():
         assert RO.error() != ""
+
+
+def test_golden_hw_linear_filter_model():
+    """oracle.cpp's hw_linear_fetch — the model of what NVIDIA's OpenCL runtime returns for the reference's CLK_FILTER_LINEAR reads of
+    an int16 3-D image — against 874 545 samples measured on the B200 with that runtime (tools/ocl_linear_probe.py, ocl_linear_probe2.py):
+    random coordinates, fine sweeps, out-of-range coordinates (border colour), impulse responses of either sign.  Bit-exact."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "opencl_linear_probe.npz"))
+    n = 0
+    for name in ("random", "sweep_z", "sweep_diag", "sweep_xy", "sweep_xz"):
+        assert np.array_equal(o.hw_linear_fetch(g["vol"], g[name + "_coords"]), g[name + "_out"]), name
+        n += len(g[name + "_out"])
+    assert np.array_equal(o.hw_linear_fetch(g["border_vol"], g["border_coords"]), g["border_out"])
+    n += len(g["border_out"])
+    for V in (16384, -16384, 1000):
+        imp = np.zeros((9, 9, 9), dtype=np.int16)
+        imp[4, 4, 4] = V
+        assert np.array_equal(o.hw_linear_fetch(imp, g["impulse_coords"]), g[f"impulse_{V}_out"].astype(np.int32)), V
+        n += len(g["impulse_coords"])
+    assert n == 874545
+    # at texel centres the filter is the identity, so there it agrees with the NEAREST reading
+    v = g["vol"]
+    zz, yy, xx = np.meshgrid(*[np.arange(s) + 0.5 for s in v.shape], indexing="ij")
+    c = np.stack([xx.ravel(), yy.ravel(), zz.ravel()], 1).astype(np.float32)
+    assert np.array_equal(o.hw_linear_fetch(v, c), v.ravel().astype(np.int32))
