@@ -542,7 +542,7 @@ def test_hw_linear_sampling_matches_oracle_model(vr_ctx, n, W, H, frames, cam):
     """VR_SAMPLING_HW_LINEAR (texture unit) against the oracle's model of that filter (oracle.cpp hw_linear_fetch, pinned bit-exactly
     against 874 545 samples of NVIDIA's OpenCL runtime, tests/test_ref_pinning_cpu.py).  The volume reads decide which voxels are hit
     and which samples are admitted: those must be identical.  The bilinear environment lookup of the oracle models the scaling of
-    the normalised coordinate as an exact product (not probed), so a colour may differ by one count per sample."""
+    the normalised coordinate as an exact product (not probed separately); measured: the whole cache is identical."""
     v, envimg, tf = synth.synth_ct(n), synth.synth_env(128, 64), synth.default_tf()
     pos, d = synth.default_camera(n) if cam == "default" else synth.closeup_camera(n)
     seeds = synth.glibc_rand(frames)
@@ -569,5 +569,5 @@ def test_hw_linear_sampling_matches_oracle_model(vr_ctx, n, W, H, frames, cam):
     assert (diff <= np.maximum(b[:, 3:4], 1)).all()              # at most one count per admitted sample
     touched = b[:, 3] > 0
     print("hw-linear vs oracle model: colour lanes identical", float((diff[touched] == 0).mean()), "max diff", int(diff.max()))
-    assert (diff[touched] == 0).mean() >= 0.5
+    assert (diff[touched] == 0).mean() >= 0.99                   # measured on B200: 1.0, max diff 0, on both scenes
     r.close(); env.close(); vol.close()
