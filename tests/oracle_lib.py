@@ -177,6 +177,33 @@ def hw_linear_fetch(vol, coords):
     return out
 
 
+def fetch_stats_shipped(vol, edge):
+    """fetch_stats with the hardware filter (oracle.cpp orc_fetch_stats_shipped); edge: what texel -1 reads under the sampler without
+    an addressing mode (0 border colour, 1 nearest edge texel)"""
+    vol = np.ascontiguousarray(vol, dtype=np.int16)
+    nz, ny, nx = vol.shape
+    st = (C.c_int32 * 4)()
+    lib().orc_fetch_stats_shipped(_p(vol), nx, ny, nz, int(edge), st)
+    return list(st)
+
+
+def histogram_shipped(vol, edge, width, height, rng):
+    vol = np.ascontiguousarray(vol, dtype=np.int16)
+    nz, ny, nx = vol.shape
+    bins = np.zeros(width * height, dtype=np.uint32)
+    lib().orc_histogram_shipped(_p(vol), nx, ny, nz, int(edge), width, height, C.c_float(rng[0]), C.c_float(rng[1]), C.c_float(rng[2]),
+                                C.c_float(rng[3]), _p(bins))
+    return bins
+
+
+def bilateral_shipped(vol):
+    vol = np.ascontiguousarray(vol, dtype=np.int16)
+    nz, ny, nx = vol.shape
+    out = np.empty_like(vol)
+    lib().orc_bilateral_shipped(_p(vol), nx, ny, nz, _p(out))
+    return out
+
+
 def env_lookup(env_rgba, dirs):
     env_rgba = np.ascontiguousarray(env_rgba, dtype=np.uint8)
     h, w = env_rgba.shape[:2]

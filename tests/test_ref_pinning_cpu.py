@@ -257,6 +257,17 @@ def test_oracle_volume_kernels_against_opencl_run_on_gpu():
     assert np.array_equal(o.clip(v, (3, 5, 2), (30, 20, 20)), OCL["nearest_ragged_clip"])
     dd = np.abs(o.bilateral(v).astype(np.int32) - OCL["nearest_ragged_bilateral"].astype(np.int32))
     assert dd.max() <= 1 and (dd == 0).mean() >= 0.99  # exp: NVIDIA's vs glibc's, an ulp
-    # as shipped the hardware interpolates: the recorded outputs differ (kept in the fixture for the linear reading of these kernels)
+    # as shipped the hardware interpolates: the recorded outputs differ ...
     assert OCL["shipped_ragged_stats"].tolist() != st and not np.array_equal(OCL["shipped_ragged_bilateral"], OCL["nearest_ragged_bilateral"])
     assert np.array_equal(OCL["shipped_ragged_clip"], OCL["nearest_ragged_clip"])  # samplerless reads
+    # ... and the oracle's hardware-filter model reproduces them: fetch_stats / tf_sort_values read through a sampler without an
+    # addressing mode, which behaves like clamp-to-edge (edge = 1; with the border colour 3443 of 48 214 voxels land elsewhere)
+    assert o.fetch_stats_shipped(v, 1) == OCL["shipped_ragged_stats"].tolist()
+    for key, (n, *_rest) in OCL_SCENES.items():
+        assert o.fetch_stats_shipped(synth.synth_ct(n), 1) == OCL[f"shipped_{key}_stats"].tolist()
+    bins = np.zeros(500 * 500, dtype=np.uint32)
+    bins[OCL["shipped_ragged_hist_idx"]] = OCL["shipped_ragged_hist_val"]
+    assert np.array_equal(o.histogram_shipped(v, 1, 500, 500, [float(x) for x in st]), bins)
+    assert not np.array_equal(o.histogram_shipped(v, 0, 500, 500, [float(x) for x in st]), bins)
+    dd = np.abs(o.bilateral_shipped(v).astype(np.int32) - OCL["shipped_ragged_bilateral"].astype(np.int32))
+    assert dd.max() <= 1 and (dd == 0).mean() >= 0.99
