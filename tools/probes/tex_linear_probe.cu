@@ -1,6 +1,6 @@
 // tex_linear_probe.cu — does the CUDA texture unit (tex3D<float> on an int16 array, cudaReadModeNormalizedFloat, linear filter, border
 // addressing, unnormalised coordinates) return what NVIDIA's OpenCL returns for read_imagei + CLK_FILTER_LINEAR on a SIGNED_INT16
-// image (profiles/r1b_opencl_linear_filter_probe2.npz)?  Decides whether an opt-in "sample like the reference does on NVIDIA
+// image (tests/golden/opencl_linear_probe.npz)?  Decides whether an opt-in "sample like the reference does on NVIDIA
 // hardware" mode can be built on texture objects.
 //   tex_linear_probe vol.i16 nx ny nz coords.f32 n out.f32
 #include <cuda_runtime.h>

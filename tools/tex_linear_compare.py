@@ -1,5 +1,6 @@
 """Compares the CUDA texture unit's linear filtering of an int16 volume (tools/probes/tex_linear_probe) with what NVIDIA's OpenCL
-returned for read_imagei + CLK_FILTER_LINEAR on the same volume and coordinates (profiles/r1b_opencl_linear_filter_probe2.npz)."""
+returned for read_imagei + CLK_FILTER_LINEAR on the same volume and coordinates (tests/golden/opencl_linear_probe.npz, recorded by
+tools/ocl_linear_probe2.py)."""
 import os
 import subprocess
 import sys
@@ -8,11 +9,11 @@ import tempfile
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-d = np.load(os.path.join(ROOT, "profiles", "r1b_opencl_linear_filter_probe2.npz"))
+d = np.load(os.path.join(ROOT, "tests", "golden", "opencl_linear_probe.npz"))
 vol = d["vol"]
-sets = {"random": (d["random_coords"], d["random_out"][:, 0])}
+sets = {"random": (d["random_coords"], d["random_out"])}
 for k in ("z", "diag", "xy", "xz"):
-    sets["sweep_" + k] = (d[f"sweep_{k}_coords"], d[f"sweep_{k}_out"][:, 0])
+    sets["sweep_" + k] = (d[f"sweep_{k}_coords"], d[f"sweep_{k}_out"])
 tmp = tempfile.mkdtemp()
 vol.tofile(os.path.join(tmp, "vol.i16"))
 for name, (c, want) in sets.items():
