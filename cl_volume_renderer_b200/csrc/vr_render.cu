@@ -724,6 +724,10 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
   if (rows <= 0) return VR_OK;
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
   if (nframes < 1 || nframes > VR_MAX_BATCH) { vr_set_error("vrk_render: bad batch size"); return VR_ERR_INVALID; }
+  if (trace && r->sampling == VR_SAMPLING_HW_LINEAR && (!r->vol_tex || !r->env_tex)) {  // textures are built by the flush
+    vr_set_error("vrk_render: hw-linear sampling needs a vr_renderer_flush after vr_renderer_set_sampling");
+    return VR_ERR_INVALID;
+  }
   if (r->timing && trace) {
     while (r->ev.size() < r->ev_used + 3) {
       cudaEvent_t e;
@@ -792,8 +796,7 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     const size_t pixels = (size_t)r->W * rows * nframes;
     dim3 grid(div_up(r->W, 8), div_up(rows, 16), nframes);
     if (r->sampling == VR_SAMPLING_HW_LINEAR) {
-      // the literal per-pixel kernel with the texture-unit sampling (vr_renderer_set_sampling); textures are built by the flush
-      if (!r->vol_tex || !r->env_tex) { vr_set_error("vrk_render: hw-linear sampling needs a vr_renderer_flush after vr_renderer_set_sampling"); return VR_ERR_INVALID; }
+      // the literal per-pixel kernel with the texture-unit sampling (vr_renderer_set_sampling)
       r->primary_valid = false;
       if (r->count) k_trace<true, false, true><<<grid, 128, 0, ctx->stream>>>(p);
       else k_trace<false, false, true><<<grid, 128, 0, ctx->stream>>>(p);
