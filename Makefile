@@ -6,7 +6,7 @@ CSRC := $(PKG)/csrc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 # --fmad=false: the numeric contract — no contraction, so ray positions match the oracle bit for bit
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo --fmad=false -Xcompiler -fPIC -ccbin $(CXX) -Xptxas -v
-CU_SRCS := $(CSRC)/vr_api.cu $(CSRC)/vr_volume_ops.cu $(CSRC)/vr_sdf.cu $(CSRC)/vr_sdf_variants.cu $(CSRC)/vr_render.cu $(CSRC)/vr_frame_filter.cu
+CU_SRCS := $(CSRC)/vr_api.cu $(CSRC)/vr_volume_ops.cu $(CSRC)/vr_sdf.cu $(CSRC)/vr_sdf_variants.cu $(CSRC)/vr_render.cu $(CSRC)/vr_frame_filter.cu $(CSRC)/vr_volume_ops_linear.cu
 CU_OBJS := $(CU_SRCS:.cu=.o)
 
 all: $(PKG)/libvr.so host oracle

@@ -84,6 +84,7 @@ SYMBOLS = {
     "vr_render_frames": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int, _P]),
     "vr_render_tf": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "vr_renderer_set_sampling": (C.c_int, [_P, C.c_int]),
+    "vr_volume_set_sampling": (C.c_int, [_P, C.c_int]),
     "vr_renderer_filter_frame": (C.c_int, [_P, C.c_int, C.c_float, C.c_int, _P]),
     "vr_image_filter": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "vr_renderer_host_frame": (_P, [_P]),
@@ -236,6 +237,11 @@ class Volume:
         s = (C.c_int32 * 4)()
         _check(lib().vr_volume_stats(self.h, s))
         return list(s)
+
+    def set_sampling(self, mode):
+        """VR_SAMPLING_HW_LINEAR: stats (recomputed now), histogram / TF image and the bilateral filter read the volume the way NVIDIA
+        hardware serves the reference's CLK_FILTER_LINEAR samplers"""
+        _check(lib().vr_volume_set_sampling(self.h, mode))
 
     def set_value_clip(self, lo, hi):
         _check(lib().vr_volume_set_value_clip(self.h, lo, hi))

@@ -198,6 +198,64 @@ extern "C" int vr_volume_upload_async(vr_ctx* ctx, const int16_t* voxels, int nx
   return VR_OK;
 }
 
+// VR_SAMPLING_HW_LINEAR for the volume kernels: the current volume in a CUDA array behind two texture objects
+static void volume_release_textures(vr_volume* v) {
+  if (!v->arr && !v->tex_border && !v->tex_edge) return;
+  cudaStreamSynchronize(v->ctx->stream);
+  if (v->tex_border) cudaDestroyTextureObject(v->tex_border);
+  if (v->tex_edge) cudaDestroyTextureObject(v->tex_edge);
+  if (v->arr) cudaFreeArray(v->arr);
+  v->tex_border = v->tex_edge = 0;
+  v->arr = nullptr;
+}
+static int volume_build_textures(vr_volume* v) {
+  volume_release_textures(v);
+  cudaChannelFormatDesc d16 = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindSigned);
+  cudaError_t e = cudaMalloc3DArray(&v->arr, &d16, make_cudaExtent(v->nx, v->ny, v->nz));
+  if (e == cudaSuccess) {
+    cudaMemcpy3DParms p{};
+    p.srcPtr = make_cudaPitchedPtr(const_cast<int16_t*>(v->current()), (size_t)v->nx * sizeof(int16_t), v->nx, v->ny);
+    p.dstArray = v->arr;
+    p.extent = make_cudaExtent(v->nx, v->ny, v->nz);
+    p.kind = cudaMemcpyDeviceToDevice;
+    e = cudaMemcpy3DAsync(&p, v->ctx->stream);
+  }
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = v->arr;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = k == 0 ? cudaAddressModeBorder : cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 0;
+    e = cudaCreateTextureObject(k == 0 ? &v->tex_border : &v->tex_edge, &rd, &td, nullptr);
+  }
+  if (e != cudaSuccess) {
+    vr_set_error("volume textures for hw-linear sampling: %s", cudaGetErrorString(e));
+    volume_release_textures(v);
+    return VR_ERR_CUDA;
+  }
+  return VR_OK;
+}
+
+extern "C" int vr_volume_set_sampling(vr_volume* v, int mode) {
+  VR_REQUIRE(v && (mode == VR_SAMPLING_NEAREST || mode == VR_SAMPLING_HW_LINEAR), "vr_volume_set_sampling: unknown mode");
+  VR_TRY(volume_finish(v));
+  if (mode == v->sampling) return VR_OK;
+  VR_CUDA(cudaSetDevice(v->ctx->device));
+  if (mode == VR_SAMPLING_HW_LINEAR) {
+    VR_TRY(volume_build_textures(v));
+    int st = vrk_fetch_stats_linear(v->ctx, v->tex_border, v->tex_edge, v->nx, v->ny, v->nz, v->stats, v->zlo, v->zhi);
+    if (st != VR_OK) { volume_release_textures(v); return st; }
+  } else {
+    volume_release_textures(v);
+    VR_TRY(vrk_fetch_stats(v->ctx, v->current(), v->nx, v->ny, v->nz, v->stats, v->zlo, v->zhi));
+  }
+  v->sampling = mode;
+  return VR_OK;
+}
+
 extern "C" int vr_volume_wait(vr_volume* v) {
   VR_REQUIRE(v, "vr_volume_wait: null argument");
   return volume_finish(v);
@@ -226,6 +284,7 @@ extern "C" void vr_volume_destroy(vr_volume* v) {
   cudaSetDevice(v->ctx->device);
   volume_finish(v);
   cudaStreamSynchronize(v->ctx->stream);
+  volume_release_textures(v);
   pool_free(v->ctx, v->original);
   pool_free(v->ctx, v->cropped);
   cudaStreamSynchronize(v->ctx->stream);
@@ -261,6 +320,7 @@ extern "C" int vr_volume_clip(vr_volume* v, const uint32_t mn[3], const uint32_t
   v->cropped = dst;
   v->nx = nx; v->ny = ny; v->nz = nz;
   v->zlo = 0; v->zhi = nz;
+  if (v->sampling == VR_SAMPLING_HW_LINEAR) VR_TRY(volume_build_textures(v));  // the textures follow the current volume
   return VR_OK;
 }
 
@@ -270,12 +330,14 @@ extern "C" int vr_volume_filter(vr_volume* v) {
   VR_CUDA(cudaSetDevice(v->ctx->device));
   int16_t* dst = nullptr;
   VR_CUDA(pool_alloc(v->ctx, &dst, v->count() * sizeof(int16_t)));
-  int s = vrk_bilateral(v->ctx, v->current(), dst, v->nx, v->ny, v->nz);
+  int s = v->sampling == VR_SAMPLING_HW_LINEAR ? vrk_bilateral_linear(v->ctx, v->tex_border, v->nx, v->ny, v->nz, dst)
+                                               : vrk_bilateral(v->ctx, v->current(), dst, v->nx, v->ny, v->nz);
   if (s != VR_OK) { pool_free(v->ctx, dst); return s; }
   VR_CUDA(cudaStreamSynchronize(v->ctx->stream));
   // `ref = std::move(buffer)` (reference_volume.cpp:77): the filtered data replaces the current volume
   if (v->cropped) { pool_free(v->ctx, v->cropped); v->cropped = dst; }
   else { pool_free(v->ctx, v->original); v->original = dst; }
+  if (v->sampling == VR_SAMPLING_HW_LINEAR) VR_TRY(volume_build_textures(v));
   return VR_OK;
 }
 
@@ -296,7 +358,9 @@ extern "C" int vr_histogram(const vr_volume* v, int width, int height, const flo
   uint32_t* bins = nullptr;
   const size_t bytes = sizeof(uint32_t) * (size_t)width * height;
   VR_CUDA(pool_alloc(v->ctx, &bins, bytes));
-  int s = vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi, v->stats[0]);
+  int s = v->sampling == VR_SAMPLING_HW_LINEAR
+              ? vrk_histogram_linear(v->ctx, v->tex_border, v->tex_edge, v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi)
+              : vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi, v->stats[0]);
   if (s == VR_OK) {
     cudaError_t e = cudaMemcpyAsync(bins_out, bins, bytes, cudaMemcpyDeviceToHost, v->ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(v->ctx->stream);
@@ -894,8 +958,11 @@ extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba
   if (e == cudaSuccess) e = pool_alloc(ctx, &scratch, 2049 * sizeof(int));
   if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
   if (status == VR_OK)
-    status = vrk_histogram(ctx, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height, range, bins, r->vol->zlo,
-                           r->vol->zhi, r->vol->stats[0]);
+    status = r->vol->sampling == VR_SAMPLING_HW_LINEAR
+                 ? vrk_histogram_linear(ctx, r->vol->tex_border, r->vol->tex_edge, r->vol->nx, r->vol->ny, r->vol->nz, width, height, range,
+                                        bins, r->vol->zlo, r->vol->zhi)
+                 : vrk_histogram(ctx, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height, range, bins, r->vol->zlo,
+                                 r->vol->zhi, r->vol->stats[0]);
   // renderer.cpp:65-96 without the host round trip: rounding, distinct-value ranking and colouring stay on the device
   if (status == VR_OK) status = vrk_tf_image(ctx, reinterpret_cast<int32_t*>(bins), scratch, width, height, img);
   if (status == VR_OK) {

@@ -72,6 +72,11 @@ struct vr_volume {
   int32_t* stats_dev = nullptr;
   int32_t* stats_pin = nullptr;
   int zlo = 0, zhi = 0;  // planes the stats / histogram cover (whole volume unless uploaded as a z-slab with halo planes)
+  // vr_volume_set_sampling(VR_SAMPLING_HW_LINEAR): a copy of the current volume in a CUDA array behind two texture objects (border
+  // colour 0 / clamp to edge), rebuilt whenever the current volume changes (clip, filter)
+  int sampling = VR_SAMPLING_NEAREST;
+  cudaArray_t arr = nullptr;
+  cudaTextureObject_t tex_border = 0, tex_edge = 0;
   int value_clip[2] = {INT32_MIN, INT32_MAX};     // reference_volume.hpp:35-36
   int gradient_clip[2] = {INT32_MIN, INT32_MAX};
   const int16_t* current() const { return cropped ? cropped : original; }
@@ -178,6 +183,12 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
                bool resolve, bool first_of_call = true);
 
 int vrk_xchg(vr_renderer* r, uint2* xchg, bool scatter);
+// the volume kernels under VR_SAMPLING_HW_LINEAR (vr_volume_ops_linear.cu)
+int vrk_fetch_stats_linear(vr_ctx* ctx, cudaTextureObject_t border, cudaTextureObject_t edge, int nx, int ny, int nz, int32_t out[4],
+                           int zlo, int zhi);
+int vrk_histogram_linear(vr_ctx* ctx, cudaTextureObject_t border, cudaTextureObject_t edge, int nx, int ny, int nz, int width, int height,
+                         const float range[4], uint32_t* bins_dev, int zlo, int zhi);
+int vrk_bilateral_linear(vr_ctx* ctx, cudaTextureObject_t border, int nx, int ny, int nz, int16_t* dst);
 // 2d_image_filter.cl: src != dst, both w*h RGBA8 on the device
 int vrk_filter2d(vr_ctx* ctx, const uchar4* src, uchar4* dst, int w, int h, int kernel_size, float sigma, int mode);
 TfTable vr_make_tf_table(const vr_tf_rect* rects, int n);

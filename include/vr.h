@@ -161,6 +161,11 @@ const vr_sdf* vr_renderer_sdf(const vr_renderer* r);
  * Takes effect at the next vr_renderer_flush (which copies the volume and the environment map into texture arrays). */
 enum { VR_SAMPLING_NEAREST = 0, VR_SAMPLING_HW_LINEAR = 1 };
 int vr_renderer_set_sampling(vr_renderer* r, int mode);
+/* The same choice for the volume kernels that read through a sampler: fetch_stats (recomputed by this call, so vr_volume_stats /
+ * vr_volume_clipped_stats follow), tf_sort_values (vr_histogram, vr_render_tf) and bilateral_filter (vr_volume_filter).  Their value
+ * read uses a sampler without an addressing mode (reference_volume_figures.cl:12, histogram.cl:7), which NVIDIA hardware serves like
+ * clamp-to-edge.  apply_clip and the SDF build read without a sampler and are the same under both readings. */
+int vr_volume_set_sampling(vr_volume* vol, int mode);
 
 /* ---- 2-D frame filter (opencl_kernels/2d_image_filter.cl:6-43 `bilateral_filter(frame, kernel_size, sigma)`) -------
  * The reference ships this kernel but no host code launches it; the call takes the kernel's own arguments.

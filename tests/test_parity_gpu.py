@@ -571,3 +571,24 @@ def test_hw_linear_sampling_matches_oracle_model(vr_ctx, n, W, H, frames, cam):
     print("hw-linear vs oracle model: colour lanes identical", float((diff[touched] == 0).mean()), "max diff", int(diff.max()))
     assert (diff[touched] == 0).mean() >= 0.99                   # measured on B200: 1.0, max diff 0, on both scenes
     r.close(); env.close(); vol.close()
+
+
+def test_volume_kernels_hw_linear_match_oracle_model(vr_ctx):
+    """fetch_stats, tf_sort_values and bilateral_filter under vr_volume_set_sampling(VR_SAMPLING_HW_LINEAR) against the oracle's
+    restatement with the hardware-filter model (orc_*_shipped), which tests/test_ref_pinning_cpu.py pins against the outputs of the
+    reference's OpenCL kernels as shipped, recorded on the B200 (same ragged volume)."""
+    v = synth.synth_ct(0, dims=(45, 37, 29))
+    vol = api.Volume(vr_ctx, v)
+    near_stats = vol.stats()
+    vol.set_sampling(api.VR_SAMPLING_HW_LINEAR)
+    assert vol.stats() == o.fetch_stats_shipped(v, 1)
+    assert vol.stats() != near_stats
+    rng = [float(x) for x in near_stats]
+    assert np.array_equal(vol.histogram(500, 500, rng), o.histogram_shipped(v, 1, 500, 500, rng))
+    vol.filter()
+    got, want = vol.download(), o.bilateral_shipped(v)
+    dd = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert dd.max() <= 1 and (dd == 0).mean() >= 0.99
+    vol.set_sampling(api.VR_SAMPLING_NEAREST)   # back: the NEAREST stats of the (now filtered) volume
+    assert vol.stats() == o.fetch_stats(got)
+    vol.close()
