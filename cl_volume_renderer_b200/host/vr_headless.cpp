@@ -78,6 +78,7 @@ int main(int argc, char** argv) {
   volume_block v = vloader.load_file(argv[1]);
   const double scale = v.m_voxel_count_x / 256.0;
   reference_volume rv(ctx, &v);
+  rv.set_sampling(sampling);
   rv.set_value_clip({-2000, 3000});
   rv.set_gradient_clip({0, 4000});
   if (clip) rv.set_clipping({cmin[0], cmin[1], cmin[2]}, {cmax[0], cmax[1], cmax[2]});

@@ -143,6 +143,9 @@ class reference_volume {
     cropped_volume_size = {max[0] - min[0], max[1] - min[1], max[2] - min[2]};
   }
   void filter() { vr_fail_hard(vr_volume_filter(vol)); }  // reference_volume.cpp:70-80
+  // VR_SAMPLING_NEAREST (default) or VR_SAMPLING_HW_LINEAR: how fetch_stats (recomputed now), the TF histogram and filter() read the
+  // volume — the filter OpenCL defines for integer images, or what NVIDIA hardware does with the reference's samplers (include/vr.h)
+  void set_sampling(int mode) { vr_fail_hard(vr_volume_set_sampling(vol, mode)); }
   std::array<int, 2> get_value_range() const { return {std::max(value_clip[0], value_range[0]), std::min(value_clip[1], value_range[1])}; }
   std::array<int, 2> get_gradient_range() const {
     return {std::max(gradient_clip[0], gradient_range[0]), std::min(gradient_clip[1], gradient_range[1])};
