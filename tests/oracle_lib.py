@@ -204,6 +204,27 @@ def bilateral_shipped(vol):
     return out
 
 
+def quiet_cells(vol, tf):
+    """per 2x2x2 cell: can an interpolated value there meet a TF clause?  1 = no (oracle.cpp orc_quiet_cells); (nz+1, ny+1, nx+1)"""
+    vol = np.ascontiguousarray(vol, dtype=np.int16)
+    nz, ny, nx = vol.shape
+    arr, n = tf_rects(tf)
+    q = np.zeros((nz + 1, ny + 1, nx + 1), dtype=np.uint8)
+    lib().orc_quiet_cells(_p(vol), nx, ny, nz, arr, n, _p(q))
+    return q
+
+
+def set_quiet_cells(q):
+    """install (or, with None, remove) the flags: linear event tests then count how many could be skipped and verify none is an event"""
+    lib().orc_set_quiet_cells(_p(q) if q is not None else None)
+
+
+def quiet_stats():
+    st = (C.c_uint64 * 3)()
+    lib().orc_quiet_stats(st)
+    return {"event_tests": int(st[0]), "skippable": int(st[1]), "violations": int(st[2])}
+
+
 def env_lookup(env_rgba, dirs):
     env_rgba = np.ascontiguousarray(env_rgba, dtype=np.uint8)
     h, w = env_rgba.shape[:2]

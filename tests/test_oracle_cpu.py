@@ -122,3 +122,26 @@ def test_tf_count_rounding_integer_form_equals_reference_expression():
     vals = [10 ** k + d for k in range(10) for d in range(-3, 4) if 1 <= 10 ** k + d < 2 ** 31]
     vals += list(range(1, 30000)) + [int(x) for x in np.random.default_rng(0).integers(1, 2 ** 31 - 1, 50000)]
     assert all(ref(v) == dev(v) for v in vals)
+
+
+def test_quiet_cells_are_conservative_under_the_linear_reading():
+    """An interpolated value is a convex combination of the 2x2x2 texels of its cell, so a cell whose value interval meets no TF clause
+    cannot produce an event: checked on every event test of a small render (the basis of the skip structure sketched in DESIGN.md 6)."""
+    n, W, H = 64, 160, 120
+    tf2 = [{"min_v": 900.0, "max_v": 1200.0, "min_g": 0.0, "max_g": 0.0, "flags": 0, "rgba": (255, 64, 32, 128)},
+           {"min_v": 500.0, "max_v": 1500.0, "min_g": 100.0, "max_g": 2000.0, "flags": 1, "rgba": (40, 200, 255, 255)}]
+    for tf, cam in ((synth.default_tf(), synth.default_camera(n)), (tf2, synth.closeup_camera(n)), (synth.threshold_tf(800), synth.default_camera(n))):
+        v, envimg = synth.synth_ct(n), synth.synth_env(64, 32)
+        q = o.quiet_cells(v, tf)
+        o.set_quiet_cells(q)
+        o.set_sampling(1)
+        try:
+            r = o.Renderer(v, envimg, tf, W, H)
+            for s in synth.glibc_rand(2):
+                r.render_frame(cam[0], cam[1], s)
+            st = o.quiet_stats()
+        finally:
+            o.set_sampling(0)
+            o.set_quiet_cells(None)
+        assert st["event_tests"] > 20000 and st["violations"] == 0
+        assert st["skippable"] > 0.5 * st["event_tests"]
