@@ -2,7 +2,7 @@
 // OpenCL driver, when the GPU box has one), with the reference's own host sequences restated around them.
 //
 // TEST INFRASTRUCTURE (oracle/_ref/libref_ocl.so): used by tests/test_ref_opencl_gpu.py to check the CUDA path against the
-// reference itself running on the same GPU, and by tools/ref_opencl_bench.py for the "reference on this GPU" timing.  Never
+// reference itself running on the same GPU, and by tests/probes/ref_opencl_bench.py for the "reference on this GPU" timing.  Never
 // linked into the product.
 //
 // The image has no OpenCL headers and the box has no /etc/OpenCL/vendors: the few OpenCL 1.2 types, constants and entry

@@ -1,7 +1,7 @@
 """Assembles tests/golden/opencl_linear_probe.npz from the two probe outputs recorded on a GPU box with the driver's OpenCL runtime:
 
-    python tools/ocl_linear_probe.py  > gpurun_out/ocl_linear_probe.json     # sweeps + out-of-range coordinates, 8x7x6 volume
-    python tools/ocl_linear_probe2.py gpurun_out/ocl_linear_probe2.npz       # impulses, sweeps, 40 000 random samples, 16^3 volume
+    python tests/probes/ocl_linear_probe.py  > gpurun_out/ocl_linear_probe.json     # sweeps + out-of-range coordinates, 8x7x6 volume
+    python tests/probes/ocl_linear_probe2.py gpurun_out/ocl_linear_probe2.npz       # impulses, sweeps, 40 000 random samples, 16^3 volume
     python tests/golden/make_linear_probe_golden.py gpurun_out/ocl_linear_probe.json gpurun_out/ocl_linear_probe2.npz
 
 Only the value read with the linear sampler and float coordinates is kept (column 0 of the probe kernel's output)."""

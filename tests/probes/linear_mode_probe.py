@@ -1,7 +1,7 @@
 """Quick look: CUDA VR_SAMPLING_HW_LINEAR against the reference's OpenCL kernels as shipped, small scenes only."""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tests", "probes"))
 import numpy as np
 import ref_ocl_lib as R
 from cl_volume_renderer_b200 import api, synth

@@ -1,11 +1,11 @@
 """What NVIDIA's OpenCL returns for read_imagei + CLK_FILTER_LINEAR on a SIGNED_INT16 3-D image (undefined by OpenCL 1.2, requested by
 every sampler of the reference): dumps sampled values for a coordinate sweep so that a model can be fitted offline.
-    python tools/ocl_linear_probe.py > gpurun_out/ocl_linear_probe.json"""
+    python tests/probes/ocl_linear_probe.py > gpurun_out/ocl_linear_probe.json"""
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402

@@ -1,10 +1,10 @@
 """Second, larger probe of read_imagei + CLK_FILTER_LINEAR on a SIGNED_INT16 3-D image under NVIDIA's OpenCL (see ocl_linear_probe.py):
 impulse responses (effective trilinear weights), fine 1-D / diagonal sweeps, random samples of a random volume.
-    python tools/ocl_linear_probe2.py gpurun_out/ocl_linear_probe2.npz"""
+    python tests/probes/ocl_linear_probe2.py gpurun_out/ocl_linear_probe2.npz"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402

@@ -1,7 +1,7 @@
 """The reference's UNMODIFIED OpenCL kernels on the GPU of this box (NVIDIA's OpenCL runtime) beside the CUDA path:
 parity metrics on a small scene, then the bench scene (512^3, 1920x1080) timed both ways.
 
-    python tools/ref_opencl_bench.py [n_big=512] [frames=16]     -> JSON lines on stdout
+    python tests/probes/ref_opencl_bench.py [n_big=512] [frames=16]     -> JSON lines on stdout
 
 TEST INFRASTRUCTURE (uses oracle/_ref/libref_ocl.so and the CPU oracle); not part of the product or of bench.py's arms."""
 import json
@@ -9,7 +9,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402

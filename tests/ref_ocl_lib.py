@@ -1,6 +1,6 @@
 """ctypes binding of oracle/_ref/libref_ocl.so — the reference's UNMODIFIED OpenCL kernels run on a real OpenCL device
 (the B200 itself, through the NVIDIA driver's OpenCL runtime, when the GPU box has one), with the reference's host sequences
-restated around them (oracle/ref_build/ocl_host.cpp).  TEST INFRASTRUCTURE: tests/ and tools/ref_opencl_bench.py only.
+restated around them (oracle/ref_build/ocl_host.cpp).  TEST INFRASTRUCTURE: tests/ and tests/probes/ref_opencl_bench.py only.
 
 available() is False when the library was not built or no OpenCL platform / device can be opened (this container)."""
 import ctypes as C

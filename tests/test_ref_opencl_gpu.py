@@ -7,7 +7,7 @@ Skipped when the box has no OpenCL runtime for the GPU.  Two readings of the ker
     CLK_FILTER_NEAREST, everything else is the reference's text, NVIDIA's compiler (-cl-mad-enable) and NVIDIA's built-ins.
     This is the semantics of oracle.cpp and of the CUDA path and the parity bar is asserted against it.
   * as shipped: NVIDIA's texture units do interpolate integer texels, so the values a ray sees differ; recorded by
-    tools/ref_opencl_bench.py (profiles/), only the sampler-free SDF build is asserted here.
+    tests/probes/ref_opencl_bench.py (profiles/), only the sampler-free SDF build is asserted here.
 Measured on B200 (profiles/r1b_reference_opencl_on_b200.jsonl): SDF and stats bit-identical; voxel cache 100 % / 99.99 % / 99.98 % of
 the touched lanes identical on the three scenes below; frames: alpha identical, PSNR 51 / 32 / 56 dB — the reference resolves a
 pixel while other work-items still add to its voxel (ray_marching.cl:82 races with :76), so on a parallel device its

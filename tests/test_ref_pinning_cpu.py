@@ -182,7 +182,7 @@ def test_opencl_host_library_loads_and_reports_unavailability():
 
 def test_golden_hw_linear_filter_model():
     """oracle.cpp's hw_linear_fetch — the model of what NVIDIA's OpenCL runtime returns for the reference's CLK_FILTER_LINEAR reads of
-    an int16 3-D image — against 874 545 samples measured on the B200 with that runtime (tools/ocl_linear_probe.py, ocl_linear_probe2.py):
+    an int16 3-D image — against 874 545 samples measured on the B200 with that runtime (tests/probes/ocl_linear_probe.py, ocl_linear_probe2.py):
     random coordinates, fine sweeps, out-of-range coordinates (border colour), impulse responses of either sign.  Bit-exact."""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "opencl_linear_probe.npz"))
     n = 0

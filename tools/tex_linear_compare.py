@@ -1,6 +1,6 @@
 """Compares the CUDA texture unit's linear filtering of an int16 volume (tools/probes/tex_linear_probe) with what NVIDIA's OpenCL
 returned for read_imagei + CLK_FILTER_LINEAR on the same volume and coordinates (tests/golden/opencl_linear_probe.npz, recorded by
-tools/ocl_linear_probe2.py)."""
+tests/probes/ocl_linear_probe2.py)."""
 import os
 import subprocess
 import sys
