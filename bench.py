@@ -30,6 +30,7 @@ import numpy as np  # noqa: E402
 VOL_N = 512
 W, H = 1920, 1080
 SPP = 64
+C3_SPP = 1024
 ENV_W, ENV_H = 2048, 1024
 WORKLOAD = (f"{VOL_N}^3 short synthetic CT (synth_ct), {W}x{H}, {SPP} spp from a reset voxel cache, default TF rect(500,1200), "
             f"synthetic env {ENV_W}x{ENV_H}, camera (-400,400,-400) look (0.9,6.183)")
@@ -212,60 +213,247 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------------------------------
-class _DevArray:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
-
-
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from cl_volume_renderer_b200 import api, synth
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = f"cuda:{local_rank}"
     ctx = api.Context(local_rank)
-    ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
-
-    vol_np, env_np, pos, d = make_scene()
-    # pinned host copies: the e2e leg uploads from these
-    vol_pin = torch.empty(vol_np.shape, dtype=torch.int16, pin_memory=True)
-    vol_pin.numpy()[...] = vol_np
-    env_pin = torch.empty(env_np.shape, dtype=torch.uint8, pin_memory=True)
-    env_pin.numpy()[...] = env_np
-    tf_code = api.tf_format(synth.default_tf())
-    all_seeds = synth.glibc_rand(SPP * max(world, 1))
-    seeds = all_seeds[SPP * rank: SPP * (rank + 1)]
-
-    vol = api.Volume(ctx, vol_pin.numpy())
-    env = api.EnvMap(ctx, env_pin.numpy())
-    r = api.Renderer(ctx, W, H)
-    r.image_set(vol, env)
-    r.next_event_code_set(tf_code)
-    r.set_token_cap(max(256 // world, 1))
-    r.flush_changes()
-    ctx.synchronize()
-    xchg_t = None
     if world > 1:
-        # compact exchange buffer: one 8-byte cache entry per pixel (all ranks trace the same camera, hence the same voxels)
-        xchg_t = torch.as_tensor(_DevArray(r.xchg_device_ptr, r.xchg_bytes // 4, "<i4"), device=f"cuda:{local_rank}")
-
-    def step():
-        r.reset_cache()
-        r.render_frames(pos, d, seeds, readback=False)
-        if world > 1:
-            r.xchg_gather()
-            with torch.cuda.stream(ext):
-                dist.all_reduce(xchg_t)  # int32 view of the packed lanes: sums cannot carry across lanes (cap 256/N)
-            r.xchg_scatter()
-            r.resolve(readback=False)
+        # torch.distributed is plumbing only (gloo: hands the NCCL id to the ranks); every data-path collective goes through the
+        # library's own NCCL communicator behind the C-ABI (vr_comm_init / vr_cache_allreduce / vr_frame_allgather / ...)
+        dist.init_process_group("gloo")
+        box = [api.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(rank, world, box[0])
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
 
     def barrier():
         ctx.synchronize()
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            ctx.comm_barrier()
+
+    def rank_max(x):
+        return float(ctx.comm_allreduce(np.array([x], dtype=np.float64), "max")[0]) if world > 1 else float(x)
+
+    def rank_min_int(x):
+        return int(ctx.comm_allreduce(np.array([x], dtype=np.int32), "min")[0]) if world > 1 else int(x)
+
+    def timed(fn, steps, warmup):
+        """CUDA events on the context's stream around `steps` calls, max over ranks; -> ms per call"""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(steps):
+            fn()
+        e1.record(ext)
+        e1.synchronize()
+        barrier()
+        return rank_max(e0.elapsed_time(e1)) / steps
+
+    vol_np, env_np, pos, d = make_scene()
+    vol_pin = torch.empty(vol_np.shape, dtype=torch.int16, pin_memory=True)   # the e2e legs upload from pinned host memory
+    vol_pin.numpy()[...] = vol_np
+    env_pin = torch.empty(env_np.shape, dtype=torch.uint8, pin_memory=True)
+    env_pin.numpy()[...] = env_np
+    tf_code = api.tf_format(synth.default_tf())
+    all_seeds = synth.glibc_rand(max(SPP * world, C3_SPP))
+    seeds = all_seeds[SPP * rank: SPP * (rank + 1)]
+    cpos, cdir = synth.closeup_camera(VOL_N)
+
+    vol = api.Volume(ctx, vol_pin.numpy())
+    env = api.EnvMap(ctx, env_pin.numpy())
+    hbm, peak_src = peaks()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def render_set(sampling, steps, warmup, full):
+        """One line-set of the path tracer under a sampling mode: timed steps (value), counters + kernel times (roofline), and —
+        when `full` — the close-up view, the per-frame schedule and the saturated-cache rate."""
+        r = api.Renderer(ctx, W, H)
+        r.set_sampling(sampling)
+        r.image_set(vol, env)
+        r.next_event_code_set(tf_code)
+        r.flush_changes()
+        ctx.synchronize()
+
+        def step():
+            r.reset_cache()
+            r.render_frames(pos, d, seeds, readback=False)
+            if world > 1:
+                r.cache_allreduce()   # every rank accumulated a full 64-spp job (cap 256): wide lanes, resolve from the global sums
+
+        r.enable_counters(True)
+        r.reset_cache()
+        r.render_frames(pos, d, seeds, readback=False)
+        counters = r.counters(reset=True)
+        r.enable_counters(False)
+        for _ in range(warmup):
+            step()
+        barrier()
+        launches0 = ctx.launches
+        r.enable_timing(True)
+        r.kernel_times(reset=True)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(steps):
+            step()
+        e1.record(ext)
+        e1.synchronize()
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms_local = e0.elapsed_time(e1)
+        trace_ms, resolve_ms, nframes = r.kernel_times(reset=True)
+        r.enable_timing(False)
+        launches = ctx.launches - launches0
+        ms = rank_max(ms_local)
+        out = {"value": W * H * SPP * world * steps / ms / 1e3, "ms_per_step": ms / steps, "clocks": clocks, "gpu_launches": int(launches)}
+        b_trace = alg_bytes_per_sample(counters, trace_only=True)
+        n_launch = max(nframes // SPP, 1)
+        launch_ms = trace_ms / n_launch
+        achieved = b_trace * W * H * SPP / (launch_ms * 1e-3) / 1e9
+        S = float(counters["samples"])
+        out["roofline"] = {
+            "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": peak_src,
+            "alg_bytes_per_sample": b_trace, "samples_per_launch": W * H * SPP, "launch_ms": launch_ms,
+            "resolve_launch_ms": resolve_ms / n_launch, "trace_share_of_step": trace_ms / ms_local if ms_local > 0 else None,
+            "per_sample": {k: counters[k] / S for k in ("steps", "normals", "env", "primary_hits", "admitted")}}
+        if full:
+            r.set_trace_mode(1)
+            pms = timed(step, 3, 2)
+            r.set_trace_mode(2)
+            out["per_frame_schedule"] = {
+                "value": W * H * SPP / pms / 1e3, "unit": "Msamples/s", "ms_per_step": pms,
+                "what": "same step with vr_renderer_set_trace_mode(1): k_trace re-marches the primary ray of every pixel in each of the "
+                        "64 frames (no reuse of the seed-independent part), persistent warps run the secondary paths"}
+            r.reset_cache()
+            for _ in range(5):
+                r.render_frames(pos, d, seeds, readback=False)   # 320 spp without a reset
+            sms = timed(lambda: r.render_frames(pos, d, seeds, readback=False), 3, 0)
+            out["saturated_cache"] = {"value": W * H * SPP / sms / 1e3, "unit": "Msamples/s", "ms_per_step": sms,
+                                      "what": "64 spp after 320 spp without a cache reset (voxels under more than one pixel are at the 256 cap)"}
+
+            def cstep():
+                r.reset_cache()
+                r.render_frames(cpos, cdir, seeds, readback=False)
+            r.enable_counters(True)
+            cstep()
+            cc = r.counters(reset=True)
+            r.enable_counters(False)
+            cms = timed(cstep, 3, 2)
+            cb = alg_bytes_per_sample(cc, trace_only=False)
+            out["closeup"] = {"value": W * H * SPP / cms / 1e3, "unit": "Msamples/s", "ms_per_step": cms, "camera": "synth.closeup_camera",
+                              "shaded_fraction": cc["primary_hits"] / float(cc["samples"]),
+                              "steps_per_sample": cc["steps"] / float(cc["samples"]), "alg_bytes_per_sample": cb,
+                              "alg_gbs": cb * W * H * SPP / (cms * 1e-3) / 1e9}
+        return out, r
+
+    # ---- e2e: the same metric through the C-ABI with host buffers --------------------------------------------------------
+    def e2e_set(sampling, nsteps):
+        """per step one headless job: volume + env map from pinned host memory, flush (cache reset + SDF build [+ textures and step
+        field]), 64 spp, final frame read back to the host"""
+        res = {}
+        r2 = api.Renderer(ctx, W, H)                   # one long-lived renderer serves the stream of jobs
+        r2.set_sampling(sampling)
+        hf = r2.host_frame()
+        if world == 1:
+            def job(v_ready, start_next):
+                en2 = api.EnvMap(ctx, env_pin.numpy())         # first: H2D copies are served in issue order by one copy engine
+                nxt = api.Volume(ctx, vol_pin.numpy(), async_upload=True) if start_next else None   # H2D 256 MiB + fetch_stats, async
+                r2.image_set(v_ready, en2)
+                r2.next_event_code_set(tf_code)
+                r2.flush_changes()
+                r2.render_frames(pos, d, seeds, out=hf)
+                chk = int(hf[::97, ::89].sum())
+                ctx.synchronize()
+                en2.close(); v_ready.close()
+                return nxt, chk
+            v = api.Volume(ctx, vol_pin.numpy(), async_upload=True)
+            for _ in range(3):
+                v, _ = job(v, True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(nsteps):
+                v, _ = job(v, True)
+            barrier()
+            dt = time.perf_counter() - t0
+            v.close()
+            res["value"] = W * H * SPP * nsteps / dt / 1e6
+            res["h2d_bytes_per_step"] = int(vol_np.nbytes + env_np.nbytes)
+            res["what"] = ("per step (one headless job): volume + env map uploaded from pinned host memory, vr_renderer_flush (cache "
+                           "reset + SDF build), vr_render_frames(64 seeds), final frame read back; jobs are pipelined: "
+                           "vr_volume_upload_async copies job k+1's volume on the copy stream while job k computes (every job's H2D and "
+                           "D2H are inside the timed region)")
+        else:
+            z0, z1 = ctx.comm_slab(VOL_N)
+            own = vol_pin.numpy()[z0:z1]
+            r2.set_sharded_build(True)
+
+            def job():
+                en2 = api.EnvMap(ctx, env_pin.numpy())
+                v2 = api.Volume(ctx, own, sharded_dims=(VOL_N, VOL_N, VOL_N))   # H2D of this rank's planes, the rest over NVLink
+                r2.image_set(v2, en2)
+                r2.next_event_code_set(tf_code)
+                r2.flush_changes()                                              # z-slab SDF build + gather of the field
+                r2.render_frames(pos, d, seeds, readback=False)
+                r2.cache_allreduce(readback=True, out=hf)
+                chk = int(hf[::97, ::89].sum())
+                en2.close(); v2.close()
+                return chk
+            for _ in range(2):
+                job()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(nsteps):
+                job()
+            barrier()
+            dt = rank_max(time.perf_counter() - t0)
+            res["value"] = W * H * SPP * world * nsteps / dt / 1e6
+            res["h2d_bytes_per_step"] = int(own.nbytes + env_np.nbytes)
+            res["what"] = ("per step (one headless job on N ranks): every rank uploads ITS z-slab of the volume from pinned host memory "
+                           "(vr_volume_upload_sharded: the other planes arrive over NVLink) and the env map, vr_renderer_flush builds the "
+                           "SDF z-slab-sharded (halo swaps + gather, NCCL behind the C-ABI), every rank traces its own 64 seeds, "
+                           "vr_cache_allreduce sums the touched cache entries and every rank reads the resolved frame back")
+        res.update({"unit": "Msamples/s", "d2h_bytes_per_step": int(W * H * 4), "steps": nsteps})
+        r2.close()
+        return res
+
+    def e2e_sequential_and_interactive(sampling):
+        def one(interactive):
+            v2 = api.Volume(ctx, vol_pin.numpy())
+            en2 = api.EnvMap(ctx, env_pin.numpy())
+            r2 = api.Renderer(ctx, W, H)
+            r2.set_sampling(sampling)
+            r2.image_set(v2, en2)
+            r2.next_event_code_set(tf_code)
+            r2.flush_changes()
+            hf = r2.host_frame()
+            if interactive:
+                r2.set_primary_reuse(2)                    # camera unchanged between the calls: primary records are kept
+                for k in range(SPP):
+                    r2.render_frame(pos, d, seeds[k], out=hf)  # the frame is pulled every call (renderer.cpp:150)
+            else:
+                r2.render_frames(pos, d, seeds, out=hf)
+            chk = int(hf[::97, ::89].sum())
+            r2.close(); en2.close(); v2.close()
+            return chk
+        out = {}
+        for name, inter in (("sequential", False), ("interactive", True)):
+            one(inter)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                one(inter)
+            barrier()
+            out[name] = W * H * SPP * 3 / (time.perf_counter() - t0) / 1e6
+        return out
 
     # ---- SDF build time (second half of BASELINE's metric) ----
     sdf_ms = []
@@ -277,219 +465,167 @@ def run_ours(args, rank, world, local_rank):
         levels = s.levels
         s.close()
 
-    # ---- algorithmic counters of one step (same scene, same seeds) ----
-    r.enable_counters(True)
-    r.reset_cache()
-    r.render_frames(pos, d, seeds, readback=False)
-    counters = r.counters(reset=True)
-    r.enable_counters(False)
+    main, r = render_set(api.VR_SAMPLING_NEAREST, args.steps, args.warmup, full=(world == 1))
+    lin, rl = render_set(api.VR_SAMPLING_HW_LINEAR, max(args.steps, 3), 3, full=(world == 1))
+    rl.close()
 
-    # ---- warm-up, then the timed region ----
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    launches0 = ctx.launches
-    r.enable_timing(True)
-    r.kernel_times(reset=True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
-    for _ in range(args.steps):
-        step()
-    e1.record(ext)
-    e1.synchronize()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    trace_ms, resolve_ms, nframes = r.kernel_times(reset=True)
-    r.enable_timing(False)
-    launches = ctx.launches - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    samples_per_step = W * H * SPP * world
-    value = samples_per_step * args.steps / ms_max / 1e3  # Msamples/s
-
-    # ---- A/B: the per-frame schedule (mode 1: every frame re-marches its primary rays, as 64 launches of the reference would) ----
-    per_frame = None
+    e2e_main = e2e_set(api.VR_SAMPLING_NEAREST, 6)
+    e2e_lin = e2e_set(api.VR_SAMPLING_HW_LINEAR, 6)
     if world == 1:
-        r.set_trace_mode(1)
-        for _ in range(2):
-            step()
-        barrier()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record(ext)
-        for _ in range(3):
-            step()
-        p1.record(ext)
-        p1.synchronize()
-        pms = p0.elapsed_time(p1) / 3
-        r.set_trace_mode(2)
-        per_frame = {"value": W * H * SPP / pms / 1e3, "unit": "Msamples/s", "ms_per_step": pms,
-                     "what": "same step with vr_renderer_set_trace_mode(1): k_trace re-marches the primary ray of every pixel in "
-                             "each of the 64 frames (no reuse of the seed-independent part)"}
+        si = e2e_sequential_and_interactive(api.VR_SAMPLING_NEAREST)
+        e2e_main["sequential"] = {"value": si["sequential"], "unit": "Msamples/s", "what": "the same jobs one after the other with the blocking vr_volume_upload"}
+        e2e_main["interactive"] = {"value": si["interactive"], "unit": "Msamples/s", "d2h_bytes_per_step": int(W * H * 4 * SPP),
+                                   "what": "same, but 64 x vr_render_frame with every frame read back (the reference UI's usage, "
+                                           "renderer.cpp:131-158), vr_renderer_set_primary_reuse(2)"}
+        sil = e2e_sequential_and_interactive(api.VR_SAMPLING_HW_LINEAR)
+        e2e_lin["interactive"] = {"value": sil["interactive"], "unit": "Msamples/s", "d2h_bytes_per_step": int(W * H * 4 * SPP)}
 
-    # ---- saturated-cache rate: once a voxel holds 256 tokens its samples stop at the token check ----
-    saturated = None
-    if world == 1:
-        r.reset_cache()
-        for _ in range(5):
-            r.render_frames(pos, d, seeds, readback=False)   # 320 spp without a reset
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(ext)
-        for _ in range(3):
-            r.render_frames(pos, d, seeds, readback=False)
-        s1.record(ext)
-        s1.synchronize()
-        sms = s0.elapsed_time(s1) / 3
-        saturated = {"value": W * H * SPP / sms / 1e3, "unit": "Msamples/s", "ms_per_step": sms,
-                     "what": "64 spp after 320 spp without a cache reset (voxels under more than one pixel are at the 256 cap)"}
+    # ---- BASELINE config 3: 1024 spp of the scene, strong-split by spp over the ranks ------------------------------------------------
+    def c3_strong():
+        mine = all_seeds[rank:C3_SPP:world]                 # 1024 / N frames on this rank
+        r.set_token_cap(max(256 // world, 1))               # the summed cache obeys the reference's cap of 256: packed lanes cannot carry
 
-    # ---- secondary view: close-up camera (about a third of the pixels shaded instead of 8 %) ----
-    cpos, cdir = synth.closeup_camera(VOL_N)
-    closeup = None
-    if world == 1:
-        def cstep():
+        def job():
             r.reset_cache()
-            r.render_frames(cpos, cdir, seeds, readback=False)
-        r.enable_counters(True)
-        cstep()
-        cc = r.counters(reset=True)
-        r.enable_counters(False)
-        for _ in range(2):
-            cstep()
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record(ext)
-        for _ in range(3):
-            cstep()
-        c1.record(ext)
-        c1.synchronize()
-        cms = c0.elapsed_time(c1) / 3
-        cb = alg_bytes_per_sample(cc, trace_only=False)
-        closeup = {"value": W * H * SPP / cms / 1e3, "unit": "Msamples/s", "ms_per_step": cms,
-                   "camera": "synth.closeup_camera", "shaded_fraction": cc["primary_hits"] / float(cc["samples"]),
-                   "steps_per_sample": cc["steps"] / float(cc["samples"]), "alg_bytes_per_sample": cb,
-                   "alg_gbs": cb * W * H * SPP / (cms * 1e-3) / 1e9}
+            for k in range(0, len(mine), 64):
+                r.render_frames(pos, d, mine[k:k + 64], readback=False)
+            r.cache_allreduce()
+        ms = timed(job, 2, 1)
+        r.set_token_cap(256)
+        return {"value": W * H * C3_SPP / ms / 1e3, "unit": "Msamples/s", "ms_per_job": ms, "spp_total": C3_SPP, "spp_per_rank": len(mine),
+                "token_cap_per_rank": max(256 // world, 1), "scaling": "strong",
+                "what": "BASELINE config 3: ONE 1024-spp job of the bench scene from a reset cache; rank r traces seeds r, r+N, ... with a "
+                        "token cap of 256/N, then vr_cache_allreduce (compact: one entry per shaded pixel) + resolve on every rank; "
+                        "time of the whole job, max over ranks.  A voxel under p pixels is offered 1024p/N samples per rank and admits "
+                        "min(256, 1024p)/N of them: the total work is the same at every N"}
 
-    # ---- e2e: the same metric through the C-ABI with host buffers ----
-    # headless job: upload the scene from pinned host memory, flush (cache alloc/reset + SDF build), accumulate the step's
-    # 64 samples per pixel with vr_render_frames, read the final frame back.  `interactive` = the reference UI's usage
-    # instead: 64 x vr_render_frame, every frame read back (renderer.cpp:150).
-    e2e_steps = 3
+    # ---- BASELINE config 4: 1024^3 volume, 3840x2160, 256 spp, image-tile split ---------------------------------------------------
+    big = {}
 
-    def e2e_step(interactive):
-        v2 = api.Volume(ctx, vol_pin.numpy())          # H2D 256 MiB + fetch_stats
-        en2 = api.EnvMap(ctx, env_pin.numpy())         # H2D 8 MiB
-        r2 = api.Renderer(ctx, W, H)
-        r2.image_set(v2, en2)
-        r2.next_event_code_set(tf_code)
-        r2.set_token_cap(max(256 // world, 1))
-        r2.flush_changes()                             # cache alloc + reset + SDF build
-        hf = r2.host_frame()
-        if interactive:
-            r2.set_primary_reuse(2)                    # camera unchanged between the calls: primary records are kept
-            for k in range(SPP):
-                r2.render_frame(pos, d, seeds[k], out=hf)  # D2H W*H*4 per frame
-        elif world == 1:
-            r2.render_frames(pos, d, seeds, out=hf)        # one D2H of the final frame
-        else:
-            r2.render_frames(pos, d, seeds, readback=False)
-            r2.xchg_gather()
-            c2 = torch.as_tensor(_DevArray(r2.xchg_device_ptr, r2.xchg_bytes // 4, "<i4"), device=f"cuda:{local_rank}")
-            with torch.cuda.stream(ext):
-                dist.all_reduce(c2)
-            r2.xchg_scatter()
-            api._check(api.lib().vr_renderer_resolve(r2.h, hf.ctypes.data_as(api.C.c_void_p)))
-        checksum = int(hf[::97, ::89].sum())
-        r2.close(); en2.close(); v2.close()
-        return checksum
+    def big_volume():
+        """1024^3 int16 on the device: the 512^3 synthetic CT upsampled x2 (trilinear) by torch — generating it with numpy on the host
+        costs minutes; -> (api.Volume, torch tensor that owns nothing the library needs after the copy)"""
+        if "vol" not in big:
+            import torch.nn.functional as F
+            t = torch.from_numpy(vol_np).to(dev).float()[None, None]
+            up = F.interpolate(t, scale_factor=2, mode="trilinear", align_corners=False)[0, 0].round_().to(torch.int16).contiguous()
+            del t
+            torch.cuda.synchronize()
+            big["vol"] = api.Volume.from_device(ctx, up.data_ptr(), 2 * VOL_N, 2 * VOL_N, 2 * VOL_N)
+            del up
+            torch.cuda.empty_cache()
+        return big["vol"]
 
-    def time_e2e(interactive):
-        e2e_step(interactive)
+    def c4_tiles():
+        n4, W4, H4, SPP4, BLOCK = 2 * VOL_N, 3840, 2160, 256, 24
+        v4 = big_volume()
+        r4 = api.Renderer(ctx, W4, H4)
+        r4.image_set(v4, env)
+        r4.next_event_code_set(tf_code)
+        r4.set_sharded_build(True)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step(interactive)
+        r4.flush_changes()
         barrier()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return samples_per_step * e2e_steps / float(tt.item()) / 1e6
+        flush_ms = rank_max(1e3 * (time.perf_counter() - t0))
+        p4, d4 = synth.closeup_camera(n4)
+        s4 = all_seeds[:SPP4]
+        r4.set_row_blocks(BLOCK, rank, world)
 
-    # pipelined headless jobs: the volume of job k+1 is uploaded (vr_volume_upload_async, copy stream) while job k builds its
-    # SDF, renders its 64 spp and reads its frame back.  Every job still pays its own H2D + D2H inside the timed region;
-    # the copy simply no longer waits for the compute stream.
-    def time_e2e_pipelined(nsteps):
-        r2 = api.Renderer(ctx, W, H)                   # one long-lived renderer serves the stream of jobs
-        r2.set_token_cap(max(256 // world, 1))
-        hf = r2.host_frame()
+        def job():
+            r4.reset_cache()
+            for k in range(0, SPP4, 64):
+                r4.render_frames(p4, d4, s4[k:k + 64], readback=False)
+            r4.frame_allgather()
+        ms = timed(job, 2, 1)
+        frame = r4.frame_allgather(readback=True)
+        res = {"value": W4 * H4 * SPP4 / ms / 1e3, "unit": "Msamples/s", "ms_per_job": ms, "scaling": "strong", "volume": f"{n4}^3",
+               "frame": f"{W4}x{H4}", "spp": SPP4, "rows_per_block": BLOCK, "flush_ms_incl_sharded_sdf_build": flush_ms,
+               "shaded_fraction": float((frame[..., 3] == 1).mean()), "frame_checksum": int(frame.astype(np.uint64).sum()),
+               "memory_per_rank_gib": round((2 + 1 + 2 + 8) * n4 ** 3 / 2 ** 30, 1),
+               "what": "BASELINE config 4: 1024^3 volume (the 512^3 synthetic CT upsampled x2 on the device), close-up camera, 256 spp; "
+                       "rows dealt out in blocks of 24 (vr_renderer_set_row_blocks), every rank traces its blocks into its own cache, "
+                       "vr_frame_allgather completes the frame on every rank; time of the whole job incl. the all-gather, max over ranks"}
+        r4.close()
+        return res
 
-        def job(v_ready, start_next):
-            en2 = api.EnvMap(ctx, env_pin.numpy())         # first: H2D copies are served in issue order by one copy engine
-            nxt = api.Volume(ctx, vol_pin.numpy(), async_upload=True) if start_next else None   # H2D 256 MiB + fetch_stats, async
-            r2.image_set(v_ready, en2)
-            r2.next_event_code_set(tf_code)
-            r2.flush_changes()                             # frame reset + SDF build for the new volume
-            if world == 1:
-                r2.render_frames(pos, d, seeds, out=hf)
+    # ---- BASELINE config 5: SDF build + histogram + volume filter sweep, z-slab sharded -----------------------------------------
+    def c5_sweep():
+        rows = []
+        tf = synth.default_tf()
+        for n5 in (128, 256, 512, 1024):
+            if n5 == VOL_N:
+                v5, own = vol, False
+            elif n5 == 2 * VOL_N:
+                v5, own = big_volume(), False
             else:
-                r2.render_frames(pos, d, seeds, readback=False)
-                r2.xchg_gather()
-                c2 = torch.as_tensor(_DevArray(r2.xchg_device_ptr, r2.xchg_bytes // 4, "<i4"), device=f"cuda:{local_rank}")
-                with torch.cuda.stream(ext):
-                    dist.all_reduce(c2)
-                r2.xchg_scatter()
-                api._check(api.lib().vr_renderer_resolve(r2.h, hf.ctypes.data_as(api.C.c_void_p)))
-            chk = int(hf[::97, ::89].sum())
-            ctx.synchronize()
-            en2.close(); v_ready.close()
-            return nxt, chk
-        v = api.Volume(ctx, vol_pin.numpy(), async_upload=True)
-        for _ in range(3):                        # warm-up jobs (pool growth, the second SDF array); leave the next volume in flight
-            v, _ = job(v, True)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(nsteps):
-            v, _ = job(v, True)                   # nsteps uploads are issued inside the timed region
-        barrier()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
-        v.close(); r2.close()
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return samples_per_step * nsteps / float(tt.item()) / 1e6
-
-    if os.environ.get("VR_E2E_BREAKDOWN"):
-        for it in range(2):
-            marks = []
-            def m(name):
-                ctx.synchronize(); marks.append((name, time.perf_counter()))
-            m("start")
-            v2 = api.Volume(ctx, vol_pin.numpy()); m("volume_upload+stats")
-            en2 = api.EnvMap(ctx, env_pin.numpy()); m("env")
-            r2 = api.Renderer(ctx, W, H); m("renderer_create")
-            r2.image_set(v2, en2); r2.next_event_code_set(tf_code); r2.set_token_cap(max(256 // world, 1))
-            r2.flush_changes(); m("flush")
-            hf = r2.host_frame()
-            r2.render_frames(pos, d, seeds, readback=False); m("render_frames")
+                v5, own = api.Volume(ctx, synth.synth_ct(n5)), True
+            st = v5.stats()
+            rng = [float(x) for x in st]
+            row = {"n": n5}
+            # SDF
+            ts, chk = [], None
+            for rep in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                s5 = api.Sdf(ctx, v5, tf, sharded=True)
+                ts.append(rank_max(1e3 * (time.perf_counter() - t0)))
+                chk = s5.checksum()
+                s5.close()
+            row["sdf_build_ms"] = min(ts)
             if world > 1:
-                r2.xchg_gather(); m("gather")
-                c2 = torch.as_tensor(_DevArray(r2.xchg_device_ptr, r2.xchg_bytes // 4, "<i4"), device=f"cuda:{local_rank}")
-                m("as_tensor")
-                with torch.cuda.stream(ext):
-                    dist.all_reduce(c2)
-                m("all_reduce")
-                r2.xchg_scatter(); m("scatter")
-            api._check(api.lib().vr_renderer_resolve(r2.h, hf.ctypes.data_as(api.C.c_void_p))); m("resolve+readback")
-            r2.close(); m("renderer_close"); en2.close(); v2.close(); m("scene_close")
-            log(f"[rank {rank}] e2e breakdown: " + ", ".join(f"{n} {1e3*(t-marks[i][1]):.2f}ms" for i, (n, t) in enumerate(marks[1:])))
-    e2e_sequential = time_e2e(False)
-    e2e_value = time_e2e_pipelined(2 * e2e_steps)
-    e2e_interactive = time_e2e(True) if world == 1 else None
+                s1 = api.Sdf(ctx, v5, tf)      # the single-GPU build of the same volume on this rank
+                row["sdf_identical_to_single_gpu_build"] = bool(rank_min_int(int(s1.checksum() == chk)))
+                s1.close()
+            # histogram (500x500 as the UI asks for, ui.cpp:148)
+            ts = []
+            for rep in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                bins = v5.histogram_sharded(500, 500, rng)
+                ts.append(rank_max(1e3 * (time.perf_counter() - t0)))
+            row["histogram_ms_incl_1MB_readback"] = min(ts)
+            if world > 1:
+                row["histogram_identical_to_single_gpu"] = bool(rank_min_int(int(np.array_equal(bins, v5.histogram(500, 500, rng)))))
+            # bilateral filter on a copy (it replaces the volume)
+            ts = []
+            want = None
+            if world > 1:
+                c1 = api.Volume.from_device(ctx, _volume_device_ptr(v5), n5, n5, n5)
+                c1.filter()
+                want = c1.checksum()
+                c1.close()
+            for rep in range(2):
+                cpy = api.Volume.from_device(ctx, _volume_device_ptr(v5), n5, n5, n5)
+                barrier()
+                t0 = time.perf_counter()
+                cpy.filter_sharded()
+                ctx.synchronize()
+                ts.append(rank_max(1e3 * (time.perf_counter() - t0)))
+                got = cpy.checksum()
+                cpy.close()
+            row["bilateral_ms"] = min(ts)
+            if world > 1:
+                row["bilateral_identical_to_single_gpu"] = bool(rank_min_int(int(got == want)))
+            rows.append(row)
+            if own:
+                v5.close()
+        return {"rows": rows, "what": "BASELINE config 5: vr_sdf_build_sharded (z-slabs + 16 halo planes, bit-volume halo swaps every 14 "
+                                      "levels with ncclSend/ncclRecv, gather of the field), vr_histogram_sharded (slab counts + all-reduce), "
+                                      "vr_volume_filter_sharded (slab + 2 halo planes, gather) — wall time per call incl. its "
+                                      "synchronisation, min of 2-3 repetitions after the first, max over ranks; results compared with the "
+                                      "single-GPU calls on every rank through device-side checksums"}
+
+    def _volume_device_ptr(v):
+        p = api.lib().vr_volume_device_ptr(v.h)
+        assert p
+        return p
+
+    c3 = c3_strong()
+    c4 = c4_tiles() if not args.skip_big else None
+    c5 = c5_sweep() if not args.skip_big else None
+    if "vol" in big:
+        big["vol"].close()
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ----
     cpu = None
@@ -545,8 +681,8 @@ def run_ours(args, rank, world, local_rank):
                                            "what": "same launches without the per-frame blocking frame pull"},
                            "sdf_build_ms": sc.sdf_ms, "sdf_iterations": sc.sdf_iterations, "jit_ms": sc.sdf_jit_ms + sc.render_jit_ms,
                            "note": "every sampler of the reference requests CLK_FILTER_LINEAR on integer images (undefined in OpenCL 1.2); "
-                                   "NVIDIA's texture units interpolate, so as shipped the rays see other values than under the "
-                                   "spec-defined NEAREST reading this repository implements (DESIGN.md 2.1); same amount of work"}
+                                   "NVIDIA's texture units interpolate: this run computes what vr_renderer_set_sampling("
+                                   "VR_SAMPLING_HW_LINEAR) computes (the `hw_linear` line-set), not the NEAREST reading of the top-level line"}
                 sc.close()
             else:
                 ref_gpu = {"unavailable": RO.error()}
@@ -554,62 +690,48 @@ def run_ours(args, rank, world, local_rank):
             ref_gpu = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
-        hbm, peak_src = peaks()
-        b_trace = alg_bytes_per_sample(counters, trace_only=True)
-        n_launches = max(nframes // SPP, 1)             # one trace launch (k_trace + k_trace_pt) covers the 64 frames of a step
-        trace_launch_ms = trace_ms / n_launches
-        achieved = b_trace * W * H * SPP / (trace_launch_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_k_trace.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        S = float(counters["samples"])
+        def prof(name):
+            pth = os.path.join(ROOT, "profiles", name)
+            return json.load(open(pth)) if os.path.exists(pth) else None
+        traffic = (prof("traffic_k_trace.json") or {}).get("dram_bytes_per_launch")
+        main["roofline"].update({
+            "kernel": "trace phase = k_primary (seed-independent part of the 64 samples of a pixel: ray, box cut, primary march, env colour / "
+                      "hit voxel + normal; once per pixel and step) + k_trace_pt (token admission + secondary paths per pixel and frame), "
+                      "one launch pair per 64-frame step",
+            "traffic": traffic,
+            "note": "achieved = the reference algorithm's bytes (SURVEY 8d: 15 B per march step, ...) for the 64 samples per pixel over the "
+                    "measured trace time; the kernels move fewer bytes (one SDF byte per step instead of 15, the primary segment once per "
+                    "pixel instead of 64 times, DESIGN.md 4.1), so HBM is not what bounds them: see `issue_bound`",
+            "issue_bound": prof("issue_k_trace_pt.json")})
+        lin["roofline"].update({
+            "kernel": "the same launch pair with LINEAR instantiations: a quiet step is one 2-byte gather from the step field, an event "
+                      "test seven filtered texture fetches (vr_quiet.cu, DESIGN.md 4.1)",
+            "traffic": (prof("traffic_k_trace_lin.json") or {}).get("dram_bytes_per_launch"),
+            "issue_bound": prof("issue_k_trace_pt_lin.json")})
+        lin.update({"metric": "path_msamples_per_s", "unit": "Msamples/s", "e2e": e2e_lin,
+                    "what": "the same step with vr_renderer_set_sampling(VR_SAMPLING_HW_LINEAR): volume, gradient taps and environment map "
+                            "read the way NVIDIA hardware serves the reference's CLK_FILTER_LINEAR samplers — what the reference's OpenCL "
+                            "kernels compute on this GPU (`reference_on_gpu`)"})
+        if ref_gpu and "kernel_only" in ref_gpu and "per_frame_schedule" in lin:
+            lin["vs_reference_on_gpu"] = {"batched_over_kernel_only": lin["value"] / ref_gpu["kernel_only"]["value"],
+                                          "per_frame_schedule_over_kernel_only": lin["per_frame_schedule"]["value"] / ref_gpu["kernel_only"]["value"],
+                                          "interactive_over_render_frame_loop": e2e_lin.get("interactive", {}).get("value", 0.0) / ref_gpu["value"]}
         out = {
-            "metric": "path_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": "path_msamples_per_s", "value": main["value"], "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "parallelism": (f"spp-split x{world}: 64 spp per rank, per-rank token cap 256/{world} (the reference's cap of 256 "
-                                       f"per voxel holds for the summed cache); voxels under several pixels reach the per-rank cap "
-                                       f"inside the step and their later samples stop at the token check, as in the reference's "
-                                       f"steady state, so per-rank work shrinks with N") if world > 1 else "single GPU",
+            "config": {"workload": WORKLOAD, "sampling": "VR_SAMPLING_NEAREST (the filter OpenCL defines for integer images); the "
+                                                         "interpolating reading NVIDIA hardware executes is the `hw_linear` line-set",
+                       "parallelism": (f"spp-split x{world}, weak: every rank traces its own 64 seeds of the scene with the full token cap of 256 "
+                                       f"(the same work per rank as the single-GPU step), then vr_cache_allreduce sums the touched cache "
+                                       f"entries — one per shaded pixel, lanes as uint32 words — over NCCL behind the C-ABI and every rank "
+                                       f"resolves the {64 * world}-spp frame; the reference's cap of 256 then holds per rank, not for the sum: "
+                                       f"the 1024-spp job with the cap of 256 for the sum is `c3_strong`") if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (cache 1 GiB + volume 256 MiB + SDF 128 MiB), no flush"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Msamples/s",
-                    "h2d_bytes_per_step": int(vol_np.nbytes + env_np.nbytes), "d2h_bytes_per_step": int(W * H * 4),
-                    "steps": 2 * e2e_steps,
-                    "what": "per step (one headless job): volume + env map uploaded from pinned host memory, vr_renderer_flush "
-                            "(cache alloc/reset + SDF build), vr_render_frames(64 seeds), final frame read back to the host; "
-                            "jobs are pipelined: vr_volume_upload_async copies job k+1's volume on the copy stream while job k "
-                            "computes (every job's H2D and D2H are inside the timed region); one renderer object serves all "
-                            "jobs",
-                    "sequential": {"value": e2e_sequential, "unit": "Msamples/s", "steps": e2e_steps,
-                                   "what": "the same jobs one after the other with the blocking vr_volume_upload"},
-                    "interactive": {"value": e2e_interactive, "unit": "Msamples/s", "d2h_bytes_per_step": int(W * H * 4 * SPP),
-                                    "what": "same, but 64 x vr_render_frame with every frame read back (the reference UI's "
-                                            "usage, renderer.cpp:131-158), vr_renderer_set_primary_reuse(2)"}},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "trace phase = k_primary (seed-independent part of the 64 samples of a pixel: ray, "
-                                                   "box cut, primary march, env colour / hit voxel + normal; once per pixel and "
-                                                   "step) + k_trace_pt (token admission + secondary paths per pixel and frame), "
-                                                   "one launch pair per 64-frame step",
-                         "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
-                         "alg_bytes_per_sample": b_trace, "samples_per_launch": W * H * SPP,
-                         "launch_ms": trace_launch_ms, "resolve_launch_ms": resolve_ms / n_launches,
-                         "note": "achieved = the reference algorithm's bytes (SURVEY 8d: 15 B per march step, ...) for the 64 samples "
-                                 "per pixel over the measured trace time; the kernels move fewer bytes: one SDF byte per step "
-                                 "instead of 15 and the primary segment once per pixel instead of 64 times (DESIGN.md 4.1). "
-                                 "Scattered 1-byte gathers: issue-bound, not HBM-bound (profiles/)",
-                         "trace_share_of_step": trace_ms / ms if ms > 0 else None,
-                         "per_sample": {"steps": counters["steps"] / S, "normals": counters["normals"] / S,
-                                        "env": counters["env"] / S, "primary_hits": counters["primary_hits"] / S,
-                                        "admitted": counters["admitted"] / S}},
-            "cpu_baseline": cpu,
-            "reference_on_gpu": ref_gpu,
-            "closeup": closeup,
-            "per_frame_schedule": per_frame,
-            "saturated_cache": saturated,
+            "clocks": main["clocks"], "e2e": e2e_main, "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
+            "cpu_baseline": cpu, "reference_on_gpu": ref_gpu,
+            "closeup": main.get("closeup"), "per_frame_schedule": main.get("per_frame_schedule"), "saturated_cache": main.get("saturated_cache"),
+            "hw_linear": lin, "c3_strong": c3, "c4_tiles": c4, "c5_sweep": c5,
             "sdf_build_ms": {"value": float(np.median(sdf_ms)), "levels": levels, "volume": f"{VOL_N}^3",
                              "note": "vr_sdf_build wall time incl. allocation, excl. upload (app/sdf_benchmark.cpp:15-20)"},
         }
@@ -626,6 +748,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-big", action="store_true", help="skip the 1024^3 legs (c4_tiles, c5_sweep)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

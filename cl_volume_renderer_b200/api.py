@@ -9,7 +9,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvr.so")
+# VR_LIB: tools/ and the A/B tests point this harness at tools/ab/libvr_ab.so (the -DVR_AB build); the product library is libvr.so
+LIB_PATH = os.environ.get("VR_LIB") or os.path.join(_HERE, "libvr.so")
+VR_COMM_ID_BYTES = 128
 
 VR_TF_USE_GRADIENT = 1
 VR_TF_THRESHOLD = 2
@@ -42,11 +44,16 @@ SYMBOLS = {
     "vr_ctx_synchronize": (C.c_int, [_P]),
     "vr_ctx_stream": (_P, [_P]),
     "vr_ctx_launch_count": (C.c_uint64, [_P]),
+    "vr_ctx_array_count": (C.c_int, [_P]),
     "vr_tf_parse": (C.c_int, [C.c_char_p, C.POINTER(TfRect), C.c_int, C.POINTER(C.c_int)]),
     "vr_tf_format": (C.c_int, [C.POINTER(TfRect), C.c_int, C.c_char_p, C.c_size_t]),
     "vr_volume_upload": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "vr_volume_upload_async": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "vr_volume_wait": (C.c_int, [_P]),
+    "vr_volume_upload_device": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vr_sdf_checksum": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "vr_volume_checksum": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "vr_volume_device_ptr": (_P, [_P]),
     "vr_volume_destroy": (None, [_P]),
     "vr_volume_stats": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "vr_volume_set_value_clip": (C.c_int, [_P, C.c_int, C.c_int]),
@@ -90,6 +97,8 @@ SYMBOLS = {
     "vr_renderer_host_frame": (_P, [_P]),
     "vr_cache_download": (C.c_int, [_P, _P]),
     "vr_renderer_sdf": (_P, [_P]),
+    "vr_renderer_hit_download": (C.c_int, [_P, _P]),
+    "vr_cache_download_at": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "vr_renderer_set_token_cap": (C.c_int, [_P, C.c_int]),
     "vr_renderer_set_rows": (C.c_int, [_P, C.c_int, C.c_int]),
     "vr_renderer_cache_device_ptr": (_P, [_P]),
@@ -106,6 +115,26 @@ SYMBOLS = {
     "vr_renderer_set_primary_reuse": (C.c_int, [_P, C.c_int]),
     "vr_renderer_enable_timing": (C.c_int, [_P, C.c_int]),
     "vr_renderer_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
+    "vr_renderer_filtered_device_ptr": (_P, [_P]),
+    "vr_renderer_set_tuning": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "vr_renderer_quiet_download": (C.c_int, [_P, _P]),
+    "vr_debug_rng_dump": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P]),
+    "vr_comm_unique_id": (C.c_int, [_P]),
+    "vr_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "vr_comm_destroy": (None, [_P]),
+    "vr_comm_rank": (C.c_int, [_P]),
+    "vr_comm_size": (C.c_int, [_P]),
+    "vr_comm_barrier": (C.c_int, [_P]),
+    "vr_comm_allreduce_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
+    "vr_comm_slab": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vr_cache_allreduce": (C.c_int, [_P, _P]),
+    "vr_renderer_set_row_blocks": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
+    "vr_frame_allgather": (C.c_int, [_P, _P]),
+    "vr_volume_upload_sharded": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vr_sdf_build_sharded": (C.c_int, [_P, _P, C.POINTER(TfRect), C.c_int, C.POINTER(_P)]),
+    "vr_renderer_set_sharded_build": (C.c_int, [_P, C.c_int]),
+    "vr_histogram_sharded": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), _P]),
+    "vr_volume_filter_sharded": (C.c_int, [_P]),
 }
 
 _lib = None
@@ -197,20 +226,87 @@ class Context:
     def launches(self):
         return int(lib().vr_ctx_launch_count(self.h))
 
+    @property
+    def array_count(self):
+        return int(lib().vr_ctx_array_count(self.h))
+
+    # ---- multi-GPU: NCCL communicator behind the C-ABI (include/vr.h) ----
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * VR_COMM_ID_BYTES)()
+        _check(lib().vr_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, rank, nranks, uid):
+        buf = (C.c_uint8 * VR_COMM_ID_BYTES).from_buffer_copy(uid)
+        _check(lib().vr_comm_init(self.h, rank, nranks, buf))
+
+    @property
+    def comm_rank(self):
+        return lib().vr_comm_rank(self.h)
+
+    @property
+    def comm_size(self):
+        return lib().vr_comm_size(self.h)
+
+    def comm_barrier(self):
+        _check(lib().vr_comm_barrier(self.h))
+
+    def comm_allreduce(self, values, op="sum"):
+        """small host array (int32 / uint32 / float64) reduced over the ranks in place; returns it"""
+        a = np.ascontiguousarray(values)
+        dt = {np.dtype(np.int32): 0, np.dtype(np.uint32): 1, np.dtype(np.float64): 2}[a.dtype]
+        _check(lib().vr_comm_allreduce_host(self.h, _vp(a), a.size, dt, {"sum": 0, "min": 1, "max": 2}[op]))
+        return a
+
+    def comm_slab(self, nz, rank=None):
+        z0, z1 = C.c_int(0), C.c_int(0)
+        _check(lib().vr_comm_slab(self.h, nz, self.comm_rank if rank is None else rank, C.byref(z0), C.byref(z1)))
+        return z0.value, z1.value
+
+    def rng_dump(self, seeds, gids, normal_rough):
+        """device RNG known answers: -> (ra [n,3] int32, comp [n,3] int32, dir [n,3] float32)"""
+        seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+        gids = np.ascontiguousarray(gids, dtype=np.uint32).reshape(-1, 2)
+        nr = np.ascontiguousarray(normal_rough, dtype=np.float32).reshape(-1, 4)
+        n = seeds.size
+        ra, comp, d = np.empty((n, 3), np.int32), np.empty((n, 3), np.int32), np.empty((n, 3), np.float32)
+        _check(lib().vr_debug_rng_dump(self.h, _vp(seeds), _vp(gids), _vp(nr), n, _vp(ra), _vp(comp), _vp(d)))
+        return ra, comp, d
+
 
 class Volume:
     """reference_volume (app/reference_volume.hpp:27-63)"""
 
-    def __init__(self, ctx, voxels, interior=None, async_upload=False):
+    @classmethod
+    def from_device(cls, ctx, device_ptr, nx, ny, nz):
+        """voxels already in the context's device memory (vr_volume_upload_device)"""
+        self = cls.__new__(cls)
+        self.ctx, self.h, self._keep = ctx, _P(), None
+        _check(lib().vr_volume_upload_device(ctx.h, C.c_void_p(device_ptr), nx, ny, nz, C.byref(self.h)))
+        return self
+
+    def checksum(self):
+        c = C.c_uint64(0)
+        _check(lib().vr_volume_checksum(self.h, C.byref(c)))
+        return int(c.value)
+
+    def __init__(self, ctx, voxels, interior=None, async_upload=False, sharded_dims=None):
         """interior=(z_lo, z_hi): `voxels` is a z-slab with halo planes; stats / histogram cover planes [z_lo, z_hi) only.
-        async_upload: return at once (vr_volume_upload_async); `voxels` must not change until wait() / first use."""
+        async_upload: return at once (vr_volume_upload_async); `voxels` must not change until wait() / first use.
+        sharded_dims=(nx, ny, nz): `voxels` holds only this rank's planes ctx.comm_slab(nz) of that volume (vr_volume_upload_sharded)."""
         voxels = np.ascontiguousarray(voxels, dtype=np.int16)
         assert voxels.ndim == 3, "volume must be [nz, ny, nx]"
         nz, ny, nx = voxels.shape
         self.ctx = ctx
         self.h = _P()
         self._keep = voxels
-        if async_upload:
+        if sharded_dims is not None:
+            gx, gy, gz = sharded_dims
+            z0, z1 = ctx.comm_slab(gz)
+            assert (nx, ny, nz) == (gx, gy, z1 - z0), "sharded upload: pass exactly this rank's planes"
+            _check(lib().vr_volume_upload_sharded(ctx.h, _vp(voxels), gx, gy, gz, C.byref(self.h)))
+        elif async_upload:
             assert interior is None
             _check(lib().vr_volume_upload_async(ctx.h, _vp(voxels), nx, ny, nz, C.byref(self.h)))
         elif interior is None:
@@ -265,6 +361,14 @@ class Volume:
     def filter(self):
         _check(lib().vr_volume_filter(self.h))
 
+    def filter_sharded(self):
+        _check(lib().vr_volume_filter_sharded(self.h))
+
+    def histogram_sharded(self, width, height, rng):
+        bins = np.empty(width * height, dtype=np.uint32)
+        _check(lib().vr_histogram_sharded(self.h, width, height, (C.c_float * 4)(*rng), _vp(bins)))
+        return bins
+
     def download(self):
         nx, ny, nz = self.dims()
         out = np.empty((nz, ny, nx), dtype=np.int16)
@@ -293,11 +397,12 @@ class EnvMap:
 class Sdf:
     """signed_distance_field (app/signed_distance_field.hpp:5-12)"""
 
-    def __init__(self, ctx, volume, tf_specs):
+    def __init__(self, ctx, volume, tf_specs, sharded=False):
         arr, n = make_rects(tf_specs)
         self.h = _P()
         self.dims = volume.dims()
-        _check(lib().vr_sdf_build(ctx.h, volume.h, arr, n, C.byref(self.h)))
+        fn = lib().vr_sdf_build_sharded if sharded else lib().vr_sdf_build
+        _check(fn(ctx.h, volume.h, arr, n, C.byref(self.h)))
 
     def close(self):
         if self.h:
@@ -313,6 +418,11 @@ class Sdf:
     @property
     def levels(self):
         return lib().vr_sdf_levels(self.h)
+
+    def checksum(self):
+        c = C.c_uint64(0)
+        _check(lib().vr_sdf_checksum(self.h, C.byref(c)))
+        return int(c.value)
 
 
 class SdfSlab:
@@ -436,6 +546,17 @@ class Renderer:
         _check(lib().vr_cache_download(self.h, _vp(out)))
         return out
 
+    def hit_download(self):
+        out = np.empty((self.H, self.W), dtype=np.uint32)
+        _check(lib().vr_renderer_hit_download(self.h, _vp(out)))
+        return out
+
+    def cache_download_at(self, voxels):
+        voxels = np.ascontiguousarray(voxels, dtype=np.uint32)
+        out = np.empty((voxels.size, 4), dtype=np.uint16)
+        _check(lib().vr_cache_download_at(self.h, _vp(voxels), voxels.size, _vp(out)))
+        return out
+
     def sdf_download(self):
         nx, ny, nz = self.volume.dims()
         out = np.empty((nz, ny, nx), dtype=np.int8)
@@ -495,6 +616,35 @@ class Renderer:
     def set_sampling(self, mode):
         """takes effect at the next flush_changes()"""
         _check(lib().vr_renderer_set_sampling(self.h, mode))
+
+    def set_tuning(self, key, value):
+        _check(lib().vr_renderer_set_tuning(self.h, key.encode(), int(value)))
+
+    def quiet_download(self):
+        """hw-linear step field: quiet-octant byte per voxel cell [nz, ny, nx]"""
+        nx, ny, nz = self.volume.dims()
+        out = np.empty((nz, ny, nx), dtype=np.uint8)
+        _check(lib().vr_renderer_quiet_download(self.h, _vp(out)))
+        return out
+
+    def cache_allreduce(self, readback=False, out=None):
+        """spp split: sum the touched cache entries over the ranks of the context's communicator and resolve"""
+        if readback and out is None:
+            out = np.empty((self.H, self.W, 4), dtype=np.uint8)
+        _check(lib().vr_cache_allreduce(self.h, _vp(out) if readback else None))
+        return out if readback else None
+
+    def set_row_blocks(self, block_rows, rank, nranks):
+        _check(lib().vr_renderer_set_row_blocks(self.h, block_rows, rank, nranks))
+
+    def frame_allgather(self, readback=False, out=None):
+        if readback and out is None:
+            out = np.empty((self.H, self.W, 4), dtype=np.uint8)
+        _check(lib().vr_frame_allgather(self.h, _vp(out) if readback else None))
+        return out if readback else None
+
+    def set_sharded_build(self, on=True):
+        _check(lib().vr_renderer_set_sharded_build(self.h, 1 if on else 0))
 
     def set_trace_mode(self, mode):
         _check(lib().vr_renderer_set_trace_mode(self.h, mode))

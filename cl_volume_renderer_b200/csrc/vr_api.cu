@@ -40,6 +40,51 @@ static void pinned_release(vr_ctx* ctx, void* p) {
     if (b.p == p) b.in_use = false;
 }
 
+// 3-D CUDA arrays behind surface objects, recycled by (size, bits).  Releasing keeps at most two unused arrays (the flush
+// builds the fresh SDF before it lets go of the old one, so two of a size are the steady state); older ones are freed, so a
+// session that walks through many clip boxes does not accumulate an array per size.
+int array3d_acquire(vr_ctx* ctx, int nx, int ny, int nz, int bits, cudaArray_t* arr, cudaSurfaceObject_t* surf) {
+  for (auto& a : ctx->arrays3d)
+    if (!a.in_use && a.nx == nx && a.ny == ny && a.nz == nz && a.bits == bits) { a.in_use = true; *arr = a.arr; *surf = a.surf; return VR_OK; }
+  cudaChannelFormatDesc desc = bits == 8 ? cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindSigned)
+                                         : cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
+  cudaArray_t a = nullptr;
+  cudaSurfaceObject_t so = 0;
+  cudaError_t e = cudaMalloc3DArray(&a, &desc, make_cudaExtent(nx, ny, nz), cudaArraySurfaceLoadStore);
+  if (e == cudaSuccess) {
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = a;
+    e = cudaCreateSurfaceObject(&so, &rd);
+  }
+  if (e != cudaSuccess) {
+    if (a) cudaFreeArray(a);
+    vr_set_error("3-D array %dx%dx%d (%d bits): %s", nx, ny, nz, bits, cudaGetErrorString(e));
+    return VR_ERR_CUDA;
+  }
+  ctx->arrays3d.push_back({a, so, nx, ny, nz, bits, true, 0});
+  *arr = a; *surf = so;
+  return VR_OK;
+}
+void array3d_release(vr_ctx* ctx, cudaArray_t arr) {
+  if (!arr) return;
+  for (auto& a : ctx->arrays3d)
+    if (a.arr == arr) { a.in_use = false; a.released = ++ctx->array_clock; }
+  for (;;) {
+    int unused = 0, oldest = -1;
+    for (size_t i = 0; i < ctx->arrays3d.size(); ++i)
+      if (!ctx->arrays3d[i].in_use) {
+        ++unused;
+        if (oldest < 0 || ctx->arrays3d[i].released < ctx->arrays3d[oldest].released) oldest = (int)i;
+      }
+    if (unused <= 2) break;
+    cudaStreamSynchronize(ctx->stream);
+    cudaDestroySurfaceObject(ctx->arrays3d[oldest].surf);
+    cudaFreeArray(ctx->arrays3d[oldest].arr);
+    ctx->arrays3d.erase(ctx->arrays3d.begin() + oldest);
+  }
+}
+
 // ---- context -------------------------------------------------------------------------------------------------
 extern "C" int vr_ctx_create(int device_ordinal, vr_ctx** out) {
   VR_REQUIRE(out, "vr_ctx_create: null out");
@@ -91,7 +136,8 @@ extern "C" void vr_ctx_destroy(vr_ctx* c) {
   if (c->scratch) cudaFree(c->scratch);
   if (c->scratch_host) cudaFreeHost(c->scratch_host);
   for (auto& b : c->pinned) cudaFreeHost(b.p);
-  for (auto& a : c->sdf_arrays) { cudaDestroySurfaceObject(a.surf); cudaFreeArray(a.arr); }
+  for (auto& a : c->arrays3d) { cudaDestroySurfaceObject(a.surf); cudaFreeArray(a.arr); }
+  vr_comm_release(c);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
@@ -108,10 +154,11 @@ extern "C" int vr_ctx_synchronize(vr_ctx* c) {
 
 extern "C" void* vr_ctx_stream(vr_ctx* c) { return c ? (void*)c->stream : nullptr; }
 extern "C" uint64_t vr_ctx_launch_count(const vr_ctx* c) { return c ? c->launches : 0; }
+extern "C" int vr_ctx_array_count(const vr_ctx* c) { return c ? (int)c->arrays3d.size() : 0; }
 
 // ---- volume --------------------------------------------------------------------------------------------------
 // completes a vr_volume_upload_async: waits for the copy stream's event, takes the stats, releases the staging objects
-static int volume_finish(const vr_volume* cv) {
+int volume_finish(const vr_volume* cv) {
   vr_volume* v = const_cast<vr_volume*>(cv);
   if (!v || !v->pending) return VR_OK;
   VR_CUDA(cudaEventSynchronize(v->ready));
@@ -155,6 +202,31 @@ static int volume_upload_impl(vr_ctx* ctx, const int16_t* voxels, int nx, int ny
 
 extern "C" int vr_volume_upload(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz, vr_volume** out) {
   return volume_upload_impl(ctx, voxels, nx, ny, nz, 0, nz, out);
+}
+
+// a volume that already lives on this device (decoded or generated there): device-to-device copy, then fetch_stats
+extern "C" int vr_volume_upload_device(vr_ctx* ctx, const int16_t* device_voxels, int nx, int ny, int nz, vr_volume** out) {
+  VR_REQUIRE(ctx && device_voxels && out, "vr_volume_upload_device: null argument");
+  VR_REQUIRE(nx > 0 && ny > 0 && nz > 0, "vr_volume_upload_device: dimensions must be positive");
+  VR_REQUIRE((size_t)nx * ny * nz < ((size_t)1 << 32) - 1, "vr_volume_upload_device: more than 2^32-2 voxels");
+  VR_CUDA(cudaSetDevice(ctx->device));
+  cudaPointerAttributes at{};
+  VR_REQUIRE(cudaPointerGetAttributes(&at, device_voxels) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device == ctx->device,
+             "vr_volume_upload_device: not a pointer to memory of the context's device");
+  vr_volume* v = new (std::nothrow) vr_volume();
+  if (!v) return VR_ERR_NOMEM;
+  v->ctx = ctx;
+  v->onx = v->nx = nx; v->ony = v->ny = ny; v->onz = v->nz = nz;
+  v->zlo = 0; v->zhi = nz;
+  const size_t bytes = v->count() * sizeof(int16_t);
+  cudaError_t e = pool_alloc(ctx, &v->original, bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(v->original, device_voxels, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+  int s = VR_OK;
+  if (e != cudaSuccess) { vr_set_error("vr_volume_upload_device: %s", cudaGetErrorString(e)); s = VR_ERR_CUDA; }
+  if (s == VR_OK) s = vrk_fetch_stats(ctx, v->original, nx, ny, nz, v->stats, 0, nz);
+  if (s != VR_OK) { cudaStreamSynchronize(ctx->stream); pool_free(ctx, v->original); delete v; return s; }
+  *out = v;
+  return VR_OK;
 }
 
 // Asynchronous ingest (no reference counterpart: clw_image pushes are blocking, clw_image.hpp:206).  Returns at once; the copy
@@ -320,6 +392,7 @@ extern "C" int vr_volume_clip(vr_volume* v, const uint32_t mn[3], const uint32_t
   v->cropped = dst;
   v->nx = nx; v->ny = ny; v->nz = nz;
   v->zlo = 0; v->zhi = nz;
+  v->generation++;
   if (v->sampling == VR_SAMPLING_HW_LINEAR) VR_TRY(volume_build_textures(v));  // the textures follow the current volume
   return VR_OK;
 }
@@ -337,6 +410,7 @@ extern "C" int vr_volume_filter(vr_volume* v) {
   // `ref = std::move(buffer)` (reference_volume.cpp:77): the filtered data replaces the current volume
   if (v->cropped) { pool_free(v->ctx, v->cropped); v->cropped = dst; }
   else { pool_free(v->ctx, v->original); v->original = dst; }
+  v->generation++;
   if (v->sampling == VR_SAMPLING_HW_LINEAR) VR_TRY(volume_build_textures(v));
   return VR_OK;
 }
@@ -401,39 +475,34 @@ extern "C" void vr_envmap_destroy(vr_envmap* e) {
 }
 
 // ---- SDF -----------------------------------------------------------------------------------------------------
-static int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, vr_sdf** out) {
+int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, vr_sdf** out, bool sharded) {
   VR_CUDA(cudaSetDevice(ctx->device));
   vr_sdf* s = new (std::nothrow) vr_sdf();
   if (!s) return VR_ERR_NOMEM;
   s->ctx = ctx; s->nx = vol->nx; s->ny = vol->ny; s->nz = vol->nz;
   cudaError_t e = pool_alloc(ctx, &s->field, vrk_sdf_field_bytes(vol->nx, vol->ny, vol->nz));
   if (e != cudaSuccess) { delete s; vr_set_error("vr_sdf_build: %s", cudaGetErrorString(e)); return VR_ERR_CUDA; }
-  static const bool use_surf = !(getenv("VR_SDF_SURF") && !atoi(getenv("VR_SDF_SURF")));
-  if (use_surf) {
-    for (auto& a : ctx->sdf_arrays)
-      if (!a.in_use && a.nx == vol->nx && a.ny == vol->ny && a.nz == vol->nz) { a.in_use = true; s->arr = a.arr; s->surf = a.surf; break; }
-    if (!s->arr) {
-      cudaChannelFormatDesc desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindSigned);
-      e = cudaMalloc3DArray(&s->arr, &desc, make_cudaExtent(vol->nx, vol->ny, vol->nz), cudaArraySurfaceLoadStore);
-      if (e == cudaSuccess) {
-        cudaResourceDesc rd{};
-        rd.resType = cudaResourceTypeArray;
-        rd.res.array.array = s->arr;
-        e = cudaCreateSurfaceObject(&s->surf, &rd);
-      }
-      if (e != cudaSuccess) {
-        if (s->arr) cudaFreeArray(s->arr);
-        pool_free(ctx, s->field);
-        delete s;
-        vr_set_error("vr_sdf_build: surface: %s", cudaGetErrorString(e));
-        return VR_ERR_CUDA;
-      }
-      ctx->sdf_arrays.push_back({s->arr, s->surf, vol->nx, vol->ny, vol->nz, true});
-    }
+  // the same values in a 3-D array behind a surface object: what k_trace_pt gathers from
+  if (array3d_acquire(ctx, vol->nx, vol->ny, vol->nz, 8, &s->arr, &s->surf) != VR_OK) {
+    pool_free(ctx, s->field);
+    delete s;
+    return VR_ERR_CUDA;
   }
-  int st = vrk_sdf_build(ctx, vol->current(), vol->nx, vol->ny, vol->nz, tf, s->field, &s->levels, &s->max_it, s->surf);
+  int st = sharded ? vrk_sdf_build_sharded(ctx, vol->current(), vol->nx, vol->ny, vol->nz, tf, s->field, &s->levels, &s->max_it, s->surf)
+                   : vrk_sdf_build(ctx, vol->current(), vol->nx, vol->ny, vol->nz, tf, s->field, &s->levels, &s->max_it, s->surf);
   if (st != VR_OK) { vr_sdf_destroy(s); return st; }
   *out = s;
+  return VR_OK;
+}
+
+// tmp_color of a clause is (int)(c*255) with c in [0,1] (tf_part.cpp:60-77): the packed accumulators of k_trace_pt rely on it
+static int tf_check_colours(const vr_tf_rect* rects, int n, const char* who) {
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 4; ++k)
+      if (rects[i].rgba[k] < 0 || rects[i].rgba[k] > 255) {
+        vr_set_error("%s: clause %d: colour component %d = %d is outside [0,255]", who, i, k, rects[i].rgba[k]);
+        return VR_ERR_INVALID;
+      }
   return VR_OK;
 }
 
@@ -441,7 +510,8 @@ extern "C" int vr_sdf_build(vr_ctx* ctx, const vr_volume* vol, const vr_tf_rect*
   VR_REQUIRE(ctx && vol && out && (rects || n_rects == 0), "vr_sdf_build: null argument");
   VR_TRY(volume_finish(vol));
   VR_REQUIRE(n_rects >= 0 && n_rects <= VR_TF_MAX_RECTS, "vr_sdf_build: too many TF clauses");
-  return sdf_build_impl(ctx, vol, vr_make_tf_table(rects, n_rects), out);
+  VR_TRY(tf_check_colours(rects, n_rects, "vr_sdf_build"));
+  return sdf_build_impl(ctx, vol, vr_make_tf_table(rects, n_rects), out, false);
 }
 
 extern "C" void vr_sdf_destroy(vr_sdf* s) {
@@ -450,8 +520,7 @@ extern "C" void vr_sdf_destroy(vr_sdf* s) {
   cudaStreamSynchronize(s->ctx->stream);
   pool_free(s->ctx, s->field);
   cudaStreamSynchronize(s->ctx->stream);
-  for (auto& a : s->ctx->sdf_arrays)   // the array goes back to the context's cache
-    if (a.arr == s->arr) a.in_use = false;
+  array3d_release(s->ctx, s->arr);  // the array goes back to the context's cache
   delete s;
 }
 
@@ -472,6 +541,22 @@ extern "C" int vr_sdf_download(const vr_sdf* s, int8_t* out) {
 }
 
 extern "C" int vr_sdf_levels(const vr_sdf* s) { return s ? s->levels : 0; }
+
+extern "C" int vr_sdf_checksum(const vr_sdf* s, uint64_t* out) {
+  VR_REQUIRE(s && out, "vr_sdf_checksum: null argument");
+  VR_CUDA(cudaSetDevice(s->ctx->device));
+  return vrk_checksum(s->ctx, s->field, vrk_sdf_field_bytes(s->nx, s->ny, s->nz), out);
+}
+extern "C" const int16_t* vr_volume_device_ptr(const vr_volume* v) {
+  if (!v || volume_finish(v) != VR_OK) return nullptr;
+  return v->current();
+}
+extern "C" int vr_volume_checksum(const vr_volume* v, uint64_t* out) {
+  VR_REQUIRE(v && out, "vr_volume_checksum: null argument");
+  VR_TRY(volume_finish(v));
+  VR_CUDA(cudaSetDevice(v->ctx->device));
+  return vrk_checksum(v->ctx, v->current(), v->count() * sizeof(int16_t), out);
+}
 
 // ---- z-slab SDF build (multi-GPU sharding; driver: cl_volume_renderer_b200/parallel.py) -------------------------------------
 extern "C" int vr_sdf_slab_create(vr_ctx* ctx, const vr_volume* ext_slab, const vr_tf_rect* rects, int n_rects, int max_it_global,
@@ -526,7 +611,6 @@ extern "C" int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_rendere
   if (!r) return VR_ERR_NOMEM;
   r->ctx = ctx; r->W = width; r->H = height; r->row0 = 0; r->row1 = height;
   const size_t px = (size_t)width * height;
-  if (const char* m = getenv("VR_TRACE_MODE")) r->trace_mode = std::min(std::max(atoi(m), 0), 2);
   cudaError_t e = pool_alloc(ctx, &r->frame, px * 4);
   if (e == cudaSuccess) e = pool_alloc(ctx, &r->hit, px * 4);
   if (e == cudaSuccess) e = pool_alloc(ctx, &r->counters, 8 * sizeof(unsigned long long));
@@ -546,24 +630,34 @@ extern "C" int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_rendere
 
 // VR_SAMPLING_HW_LINEAR: the current volume and the environment map behind texture objects (CUDA arrays owned by the renderer)
 static void release_textures(vr_renderer* r) {
-  if (!r->vol_tex && !r->env_tex && !r->vol_arr && !r->env_arr) return;
+  if (!r->vol_tex && !r->env_tex && !r->vol_arr && !r->env_arr && !r->lin_arr) return;
   cudaStreamSynchronize(r->ctx->stream);
+  array3d_release(r->ctx, r->lin_arr);
+  r->lin_arr = nullptr; r->lin_surf = 0;
   if (r->vol_tex) cudaDestroyTextureObject(r->vol_tex);
   if (r->env_tex) cudaDestroyTextureObject(r->env_tex);
   if (r->vol_arr) cudaFreeArray(r->vol_arr);
   if (r->env_arr) cudaFreeArray(r->env_arr);
   r->vol_tex = r->env_tex = 0;
   r->vol_arr = r->env_arr = nullptr;
+  r->tex_dims[0] = 0;
 }
 
+// The arrays are kept while the sizes stay the same (a flush for a new volume of the same size, a TF edit): cudaMalloc3DArray /
+// cudaFreeArray synchronise the device and cost milliseconds; only the contents are copied again.
 static int build_textures(vr_renderer* r) {
-  release_textures(r);
   vr_ctx* ctx = r->ctx;
   const vr_volume* v = r->vol;
   const vr_envmap* env = r->env;
+  const bool same = r->vol_tex && r->env_tex && r->lin_arr && r->tex_dims[0] == v->nx && r->tex_dims[1] == v->ny && r->tex_dims[2] == v->nz &&
+                    r->tex_dims[3] == env->w && r->tex_dims[4] == env->h;
+  if (!same) release_textures(r);
   int st = VR_OK;
-  cudaChannelFormatDesc d16 = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindSigned);
-  cudaError_t e = cudaMalloc3DArray(&r->vol_arr, &d16, make_cudaExtent(v->nx, v->ny, v->nz));
+  cudaError_t e = cudaSuccess;
+  if (!same) {
+    cudaChannelFormatDesc d16 = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindSigned);
+    e = cudaMalloc3DArray(&r->vol_arr, &d16, make_cudaExtent(v->nx, v->ny, v->nz));
+  }
   if (e == cudaSuccess) {
     cudaMemcpy3DParms p{};
     p.srcPtr = make_cudaPitchedPtr(const_cast<int16_t*>(v->current()), (size_t)v->nx * sizeof(int16_t), v->nx, v->ny);
@@ -572,7 +666,7 @@ static int build_textures(vr_renderer* r) {
     p.kind = cudaMemcpyDeviceToDevice;
     e = cudaMemcpy3DAsync(&p, ctx->stream);
   }
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess && !same) {
     cudaResourceDesc rd{};
     rd.resType = cudaResourceTypeArray;
     rd.res.array.array = r->vol_arr;
@@ -583,14 +677,14 @@ static int build_textures(vr_renderer* r) {
     td.normalizedCoords = 0;
     e = cudaCreateTextureObject(&r->vol_tex, &rd, &td, nullptr);
   }
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess && !same) {
     cudaChannelFormatDesc d8 = cudaCreateChannelDesc<uchar4>();
     e = cudaMallocArray(&r->env_arr, &d8, env->w, env->h);
   }
   if (e == cudaSuccess)
     e = cudaMemcpy2DToArrayAsync(r->env_arr, 0, 0, env->texels, (size_t)env->w * 4, (size_t)env->w * 4, env->h, cudaMemcpyDeviceToDevice,
                                  ctx->stream);
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess && !same) {
     cudaResourceDesc rd{};
     rd.resType = cudaResourceTypeArray;
     rd.res.array.array = r->env_arr;
@@ -604,9 +698,14 @@ static int build_textures(vr_renderer* r) {
   if (e != cudaSuccess) {
     vr_set_error("vr_renderer_flush: texture setup for hw-linear sampling: %s", cudaGetErrorString(e));
     release_textures(r);
-    st = VR_ERR_CUDA;
+    return VR_ERR_CUDA;
   }
-  return st;
+  // the step field: SDF byte + quiet-octant bits per voxel cell (vr_quiet.cu), from the SDF the flush has just built
+  if (!same) st = array3d_acquire(ctx, v->nx, v->ny, v->nz, 16, &r->lin_arr, &r->lin_surf);
+  if (st == VR_OK) st = vrk_lin_field_build(ctx, v->current(), v->nx, v->ny, v->nz, r->sdf->field, r->tf_active, r->lin_surf);
+  if (st != VR_OK) { release_textures(r); return st; }
+  r->tex_dims[0] = v->nx; r->tex_dims[1] = v->ny; r->tex_dims[2] = v->nz; r->tex_dims[3] = env->w; r->tex_dims[4] = env->h;
+  return VR_OK;
 }
 
 extern "C" int vr_renderer_set_sampling(vr_renderer* r, int mode) {
@@ -632,6 +731,10 @@ extern "C" void vr_renderer_destroy(vr_renderer* r) {
   pool_free(r->ctx, r->counters);
   pool_free(r->ctx, r->xchg);
   pool_free(r->ctx, r->queue);
+  pool_free(r->ctx, r->filtered);
+  pool_free(r->ctx, r->xc_idx);
+  pool_free(r->ctx, r->xc_counts);
+  pool_free(r->ctx, r->gather_buf);
   cudaStreamSynchronize(r->ctx->stream);
   for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
   pinned_release(r->ctx, r->frame_host);
@@ -650,6 +753,7 @@ extern "C" int vr_renderer_set_scene(vr_renderer* r, const vr_volume* vol, const
 extern "C" int vr_renderer_set_tf(vr_renderer* r, const vr_tf_rect* rects, int n_rects) {
   VR_REQUIRE(r && (rects || n_rects == 0), "vr_renderer_set_tf: null argument");
   VR_REQUIRE(n_rects >= 0 && n_rects <= VR_TF_MAX_RECTS, "vr_renderer_set_tf: too many TF clauses");
+  VR_TRY(tf_check_colours(rects, n_rects, "vr_renderer_set_tf"));
   r->tf_pending = vr_make_tf_table(rects, n_rects);
   r->have_tf = true;
   return VR_OK;
@@ -666,8 +770,7 @@ extern "C" int vr_renderer_set_tf_code(vr_renderer* r, const char* src) {
 extern "C" int vr_renderer_reset_cache(vr_renderer* r) {
   VR_REQUIRE(r && r->cache, "vr_renderer_reset_cache: no cache (call vr_renderer_flush first)");
   VR_CUDA(cudaSetDevice(r->ctx->device));
-  static const bool always_full = getenv("VR_FULL_RESET") && atoi(getenv("VR_FULL_RESET"));
-  if (r->cache_exposed || always_full) r->cache_dirty = 2;
+  if (r->cache_exposed) r->cache_dirty = 2;
   int st = VR_OK;
   if (r->cache_dirty == 1) st = vrk_cache_reset_hits(r->ctx, r->cache, r->hit, (size_t)r->W * r->H);
   else if (r->cache_dirty == 2) st = vrk_cache_reset(r->ctx, r->cache, r->cache_voxels);
@@ -709,13 +812,26 @@ extern "C" int vr_renderer_flush(vr_renderer* r) {
   r->cache_dirty = 0;
   r->tf_active = r->tf_pending;                                  // renderer.cpp:39
   vr_sdf* fresh = nullptr;                                       // renderer.cpp:42
-  int st = sdf_build_impl(ctx, r->vol, r->tf_active, &fresh);
+  int st = sdf_build_impl(ctx, r->vol, r->tf_active, &fresh, r->sharded_build);
   if (forked) VR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // later work on the compute stream sees the reset cache
   VR_TRY(st);
   vr_sdf_destroy(r->sdf);
   r->sdf = fresh;
   VR_CUDA(cudaMemsetAsync(r->hit, 0xFF, (size_t)r->W * r->H * 4, r->ctx->stream));
+  r->flushed_vol = nullptr;
   if (r->sampling == VR_SAMPLING_HW_LINEAR) VR_TRY(build_textures(r));
+  r->flushed_vol = r->vol; r->flushed_env = r->env; r->flushed_generation = r->vol->generation;
+  return VR_OK;
+}
+
+// SDF, cache, hit buffer and textures belong to the scene of the last flush: tracing or resolving with another volume bound, or
+// with the bound volume clipped / filtered since, would index them with the wrong dimensions
+static int check_flushed(const vr_renderer* r, const char* who) {
+  if (!r->sdf || !r->cache) { vr_set_error("%s: call vr_renderer_flush first", who); return VR_ERR_INVALID; }
+  if (r->vol != r->flushed_vol || r->env != r->flushed_env || r->vol->generation != r->flushed_generation) {
+    vr_set_error("%s: the scene changed since the last vr_renderer_flush (set_scene, vr_volume_clip or vr_volume_filter): flush required", who);
+    return VR_ERR_INVALID;
+  }
   return VR_OK;
 }
 
@@ -730,7 +846,7 @@ extern "C" int vr_render_frame(vr_renderer* r, const float pos[3], const float d
                                uint8_t* host_rgba) {
   VR_REQUIRE(r && pos && dir, "vr_render_frame: null argument");
   VR_TRY(volume_finish(r->vol));
-  VR_REQUIRE(r->sdf && r->cache, "vr_render_frame: call vr_renderer_flush first");
+  VR_TRY(check_flushed(r, "vr_render_frame"));
   VR_CUDA(cudaSetDevice(r->ctx->device));
   VR_TRY(vrk_render(r, pos, dir, &seed, 1, true, true));
   return read_frame(r, host_rgba);
@@ -740,7 +856,7 @@ extern "C" int vr_render_frames(vr_renderer* r, const float pos[3], const float 
                                 int n_frames, uint8_t* host_rgba) {
   VR_REQUIRE(r && pos && dir && seeds && n_frames > 0, "vr_render_frames: bad argument");
   VR_TRY(volume_finish(r->vol));
-  VR_REQUIRE(r->sdf && r->cache, "vr_render_frames: call vr_renderer_flush first");
+  VR_TRY(check_flushed(r, "vr_render_frames"));
   VR_CUDA(cudaSetDevice(r->ctx->device));
   // Only the last frame is observable, so the traces of a batch share one launch (their samples commute: integer
   // atomics) and the cache is resolved once at the end.  Which samples a voxel admits once it reaches the token cap
@@ -753,7 +869,8 @@ extern "C" int vr_render_frames(vr_renderer* r, const float pos[3], const float 
 }
 
 extern "C" int vr_renderer_resolve(vr_renderer* r, uint8_t* host_rgba) {
-  VR_REQUIRE(r && r->sdf && r->cache, "vr_renderer_resolve: call vr_renderer_flush first");
+  VR_REQUIRE(r, "vr_renderer_resolve: null argument");
+  VR_TRY(check_flushed(r, "vr_renderer_resolve"));
   VR_CUDA(cudaSetDevice(r->ctx->device));
   const float z[3] = {0, 0, 0};
   const int32_t zero = 0;
@@ -776,16 +893,17 @@ extern "C" int vr_renderer_filter_frame(vr_renderer* r, int kernel_size, float s
   vr_ctx* ctx = r->ctx;
   VR_CUDA(cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)r->W * r->H * 4;
-  uchar4* snapshot = nullptr;  // the kernel's taps read the unfiltered frame; r->frame keeps its address (it may have been handed out)
-  VR_CUDA(pool_alloc(ctx, &snapshot, bytes));
-  int st = VR_OK;
-  cudaError_t e = cudaMemcpyAsync(snapshot, r->frame, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
-  if (e != cudaSuccess) { vr_set_error("vr_renderer_filter_frame: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
-  if (st == VR_OK) st = vrk_filter2d(ctx, snapshot, r->frame, r->W, r->H, kernel_size, sigma, mode);
-  pool_free(ctx, snapshot);  // stream-ordered: released after the kernel
-  VR_TRY(st);
-  return read_frame(r, host_rgba);
+  // The filtered image goes to its own buffer: the traced frame must stay as it is, because with primary reuse across calls
+  // (vr_renderer_set_primary_reuse(r, 2)) the environment pixels are written once per camera and only shaded pixels are
+  // re-resolved — filtering in place would leave a blurred background in every later frame.
+  if (!r->filtered) VR_CUDA(pool_alloc(ctx, &r->filtered, bytes));
+  VR_TRY(vrk_filter2d(ctx, r->frame, r->filtered, r->W, r->H, kernel_size, sigma, mode));
+  if (!host_rgba) return VR_OK;
+  VR_CUDA(cudaMemcpyAsync(host_rgba, r->filtered, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VR_OK;
 }
+extern "C" void* vr_renderer_filtered_device_ptr(const vr_renderer* r) { return r ? (void*)r->filtered : nullptr; }
 
 extern "C" int vr_image_filter(vr_ctx* ctx, const uint8_t* rgba_in, int w, int h, int kernel_size, float sigma, int mode,
                                uint8_t* rgba_out) {
@@ -819,6 +937,39 @@ extern "C" int vr_cache_download(const vr_renderer* r, uint16_t* out) {
   VR_CUDA(cudaMemcpyAsync(out, r->cache, r->cache_voxels * 8, cudaMemcpyDeviceToHost, r->ctx->stream));
   VR_CUDA(cudaStreamSynchronize(r->ctx->stream));
   return VR_OK;
+}
+
+// per pixel: voxel number of the primary hit the last trace found (utility.cl:21 order), 0xFFFFFFFF for environment pixels
+extern "C" int vr_renderer_hit_download(const vr_renderer* r, uint32_t* out) {
+  VR_REQUIRE(r && out && r->hit, "vr_renderer_hit_download: null argument");
+  VR_CUDA(cudaSetDevice(r->ctx->device));
+  VR_CUDA(cudaMemcpyAsync(out, r->hit, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost, r->ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(r->ctx->stream));
+  return VR_OK;
+}
+
+// the cache entries of n given voxels (4 ushort each): parity checks at sizes where the whole cache is gigabytes
+extern "C" int vr_cache_download_at(const vr_renderer* r, const uint32_t* voxels, size_t n, uint16_t* out) {
+  VR_REQUIRE(r && voxels && out && r->cache, "vr_cache_download_at: no cache");
+  for (size_t i = 0; i < n; ++i) VR_REQUIRE(voxels[i] < r->cache_voxels, "vr_cache_download_at: voxel out of range");
+  vr_ctx* ctx = r->ctx;
+  VR_CUDA(cudaSetDevice(ctx->device));
+  if (!n) return VR_OK;
+  uint32_t* idx = nullptr;
+  uint2* ent = nullptr;
+  VR_CUDA(pool_alloc(ctx, &idx, n * 4));
+  VR_CUDA(pool_alloc(ctx, &ent, n * 8));
+  int st = VR_OK;
+  cudaError_t e = cudaMemcpyAsync(idx, voxels, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) { vr_set_error("vr_cache_download_at: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  if (st == VR_OK) st = vrk_cache_gather(ctx, r->cache, idx, n, ent);
+  if (st == VR_OK) {
+    e = cudaMemcpyAsync(out, ent, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { vr_set_error("vr_cache_download_at: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  }
+  pool_free(ctx, idx); pool_free(ctx, ent);
+  return st;
 }
 
 extern "C" const vr_sdf* vr_renderer_sdf(const vr_renderer* r) { return r ? r->sdf : nullptr; }
@@ -872,17 +1023,19 @@ extern "C" int vr_renderer_counters(const vr_renderer* r, uint64_t out[6], int r
 }
 
 static int ensure_xchg(vr_renderer* r) {
-  if (!r->xchg) VR_CUDA(pool_alloc(r->ctx, &r->xchg, (size_t)r->W * r->H * sizeof(uint2)));
+  if (!r->xchg) VR_CUDA(pool_alloc(r->ctx, &r->xchg, (size_t)r->W * r->H * sizeof(uint4)));  // sized for the wide form of vr_cache_allreduce
   return VR_OK;
 }
 extern "C" int vr_renderer_xchg_gather(vr_renderer* r) {
-  VR_REQUIRE(r && r->cache, "vr_renderer_xchg_gather: call vr_renderer_flush first");
+  VR_REQUIRE(r, "vr_renderer_xchg_gather: null argument");
+  VR_TRY(check_flushed(r, "vr_renderer_xchg_gather"));
   VR_CUDA(cudaSetDevice(r->ctx->device));
   VR_TRY(ensure_xchg(r));
   return vrk_xchg(r, r->xchg, false);
 }
 extern "C" int vr_renderer_xchg_scatter(vr_renderer* r) {
-  VR_REQUIRE(r && r->cache && r->xchg, "vr_renderer_xchg_scatter: nothing gathered");
+  VR_REQUIRE(r && r->xchg, "vr_renderer_xchg_scatter: nothing gathered");
+  VR_TRY(check_flushed(r, "vr_renderer_xchg_scatter"));
   VR_CUDA(cudaSetDevice(r->ctx->device));
   return vrk_xchg(r, r->xchg, true);
 }
@@ -974,4 +1127,75 @@ extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba
   pool_free(ctx, bins);
   pool_free(ctx, img);
   return status;
+}
+
+// ---- schedule tuning, hw-linear diagnostics, device RNG known answers ---------------------------------------------------------
+extern "C" int vr_renderer_set_tuning(vr_renderer* r, const char* key, int value) {
+  VR_REQUIRE(r && key, "vr_renderer_set_tuning: null argument");
+  auto& t = r->tune;
+  if (!strcmp(key, "pixel_major")) { VR_REQUIRE(value >= 0 && value <= 4096, "pixel_major out of range"); t.pixel_major = value; }
+  else if (!strcmp(key, "rule_a")) { VR_REQUIRE(value >= 1 && value <= 1024, "rule_a out of range"); t.rule[0] = value; }
+  else if (!strcmp(key, "rule_b")) { VR_REQUIRE(value >= 1 && value <= 1024, "rule_b out of range"); t.rule[1] = value; }
+  else if (!strcmp(key, "lin_fast_a")) { VR_REQUIRE(value >= 0 && value <= 1024, "lin_fast_a out of range"); t.lin_rule[0] = value; }
+  else if (!strcmp(key, "lin_fast_b")) { VR_REQUIRE(value >= 0 && value <= 1024, "lin_fast_b out of range"); t.lin_rule[1] = value; }
+  else if (!strcmp(key, "lin_slow_a")) { VR_REQUIRE(value >= 0 && value <= 1024, "lin_slow_a out of range"); t.lin_rule[2] = value; }
+  else if (!strcmp(key, "lin_slow_b")) { VR_REQUIRE(value >= 0 && value <= 1024, "lin_slow_b out of range"); t.lin_rule[3] = value; }
+  else if (!strcmp(key, "pt_ctas")) {
+#ifdef VR_AB
+    t.pt_ctas = value;
+#else
+    vr_set_error("vr_renderer_set_tuning: pt_ctas needs the A/B build of the library (make ab)");
+    return VR_ERR_INVALID;
+#endif
+  } else { vr_set_error("vr_renderer_set_tuning: unknown key '%s'", key); return VR_ERR_INVALID; }
+  return VR_OK;
+}
+
+extern "C" int vr_renderer_quiet_download(const vr_renderer* r, uint8_t* out) {
+  VR_REQUIRE(r && out, "vr_renderer_quiet_download: null argument");
+  VR_REQUIRE(r->lin_surf && r->flushed_vol, "vr_renderer_quiet_download: no step field (hw-linear sampling + flush)");
+  vr_ctx* ctx = r->ctx;
+  VR_CUDA(cudaSetDevice(ctx->device));
+  const vr_volume* v = r->flushed_vol;
+  uint8_t* dev = nullptr;
+  VR_CUDA(pool_alloc(ctx, &dev, v->count()));
+  int st = vrk_lin_field_masks(ctx, r->lin_surf, v->nx, v->ny, v->nz, dev);
+  if (st == VR_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, dev, v->count(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { vr_set_error("vr_renderer_quiet_download: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  }
+  pool_free(ctx, dev);
+  return st;
+}
+
+extern "C" int vr_debug_rng_dump(vr_ctx* ctx, const int32_t* seeds, const uint32_t* gid_xy, const float* normal_rough, int n,
+                                 int32_t* ra_out, int32_t* comp_out, float* dir_out) {
+  VR_REQUIRE(ctx && seeds && gid_xy && normal_rough && ra_out && comp_out && dir_out && n > 0, "vr_debug_rng_dump: bad argument");
+  VR_CUDA(cudaSetDevice(ctx->device));
+  int32_t *d_seeds = nullptr, *d_ra = nullptr, *d_comp = nullptr;
+  uint32_t* d_gid = nullptr;
+  float *d_nr = nullptr, *d_dir = nullptr;
+  const size_t N = (size_t)n;
+  cudaError_t e = pool_alloc(ctx, &d_seeds, 4 * N);
+  if (e == cudaSuccess) e = pool_alloc(ctx, &d_gid, 8 * N);
+  if (e == cudaSuccess) e = pool_alloc(ctx, &d_nr, 16 * N);
+  if (e == cudaSuccess) e = pool_alloc(ctx, &d_ra, 12 * N);
+  if (e == cudaSuccess) e = pool_alloc(ctx, &d_comp, 12 * N);
+  if (e == cudaSuccess) e = pool_alloc(ctx, &d_dir, 12 * N);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_seeds, seeds, 4 * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_gid, gid_xy, 8 * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_nr, normal_rough, 16 * N, cudaMemcpyHostToDevice, ctx->stream);
+  int st = VR_OK;
+  if (e != cudaSuccess) { vr_set_error("vr_debug_rng_dump: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  if (st == VR_OK) st = vrk_rng_dump(ctx, d_seeds, d_gid, n, d_nr, d_ra, d_comp, d_dir);
+  if (st == VR_OK) {
+    e = cudaMemcpyAsync(ra_out, d_ra, 12 * N, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(comp_out, d_comp, 12 * N, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dir_out, d_dir, 12 * N, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { vr_set_error("vr_debug_rng_dump: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  }
+  pool_free(ctx, d_seeds); pool_free(ctx, d_gid); pool_free(ctx, d_nr); pool_free(ctx, d_ra); pool_free(ctx, d_comp); pool_free(ctx, d_dir);
+  return st;
 }

@@ -45,10 +45,16 @@ struct vr_ctx {
   // pinned host frame buffers are recycled across renderers: cudaMallocHost / cudaFreeHost cost milliseconds each
   struct PinnedBuf { void* p; size_t bytes; bool in_use; };
   std::vector<PinnedBuf> pinned;
-  // 3-D arrays (+ surface objects) of the SDF are recycled by size as well: cudaMalloc3DArray / cudaFreeArray synchronise
-  struct SdfArray { cudaArray_t arr; cudaSurfaceObject_t surf; int nx, ny, nz; bool in_use; };
-  std::vector<SdfArray> sdf_arrays;
+  // 3-D arrays (+ surface objects) of the SDF (8 bits per voxel) and of the hw-linear step field (16 bits) are recycled by size
+  // as well: cudaMalloc3DArray / cudaFreeArray synchronise.  At most two unused arrays are kept (array3d_release).
+  struct Array3D { cudaArray_t arr; cudaSurfaceObject_t surf; int nx, ny, nz, bits; bool in_use; uint64_t released; };
+  std::vector<Array3D> arrays3d;
+  uint64_t array_clock = 0;
+  void* comm = nullptr;  // ncclComm_t once vr_comm_init was called (vr_comm.cu)
+  int comm_rank = 0, comm_size = 1;
 };
+int array3d_acquire(vr_ctx* ctx, int nx, int ny, int nz, int bits, cudaArray_t* arr, cudaSurfaceObject_t* surf);
+void array3d_release(vr_ctx* ctx, cudaArray_t arr);
 
 // Device-side TF table, passed to kernels by value.
 struct TfTable {
@@ -77,6 +83,9 @@ struct vr_volume {
   int sampling = VR_SAMPLING_NEAREST;
   cudaArray_t arr = nullptr;
   cudaTextureObject_t tex_border = 0, tex_edge = 0;
+  // bumped whenever the current volume changes (clip, filter): a renderer whose SDF / cache / textures were built from an older
+  // generation refuses to trace until it is flushed again (the reference always flushes after set_clipping, ui.cpp:273-278)
+  uint64_t generation = 1;
   int value_clip[2] = {INT32_MIN, INT32_MAX};     // reference_volume.hpp:35-36
   int gradient_clip[2] = {INT32_MIN, INT32_MAX};
   const int16_t* current() const { return cropped ? cropped : original; }
@@ -122,6 +131,21 @@ struct vr_renderer {
   int sampling = VR_SAMPLING_NEAREST;
   cudaArray_t vol_arr = nullptr, env_arr = nullptr;
   cudaTextureObject_t vol_tex = 0, env_tex = 0;
+  int tex_dims[5] = {0, 0, 0, 0, 0};  // volume and env-map sizes the arrays were allocated for
+  cudaArray_t lin_arr = nullptr;      // the step field of the hw-linear path (vr_quiet.cu), 16 bits per voxel cell
+  cudaSurfaceObject_t lin_surf = 0;
+  // what the last flush was built from: tracing with anything else bound is refused (vr_renderer_check_flushed)
+  const vr_volume* flushed_vol = nullptr;
+  const vr_envmap* flushed_env = nullptr;
+  uint64_t flushed_generation = 0;
+  uchar4* filtered = nullptr;         // vr_renderer_filter_frame writes here: the traced frame stays as it is
+  // schedule tuning (vr_renderer_set_tuning): never changes a result
+  struct Tuning {
+    int pixel_major = 1;               // k_trace_pt<.., REUSE> item order: groups of this many pixels x all frames (0: frame-major)
+    int rule[2] = {5, 1};              // k_trace_pt leaves its march region when marching lanes * rule[0] < waiting lanes * rule[1]
+    int lin_rule[4] = {2, 1, 2, 1};    // hw-linear: the same for the quiet-step loop and the event-test loop
+    int pt_ctas = 0;                   // -DVR_AB builds only: register budget variant of k_trace_pt
+  } tune;
   // Which cache entries can be non-zero: 0 none (just reset), 1 only cache[hit[pix]] of the current `hit` buffer (every trace
   // since the last reset used the camera / rows in dirty_pos.. below), 2 unknown (full reset needed).  A frame reset then
   // clears W*H entries instead of 8 bytes x voxels (vr_renderer_reset_cache).
@@ -141,6 +165,13 @@ struct vr_renderer {
   uint4* queue = nullptr;  // hybrid schedule: admitted primary hits (3 x uint4 each)
   size_t queue_cap = 0;
   uint2* xchg = nullptr;  // W*H compact cache entries for the spp-split exchange (allocated on first use)
+  uint32_t* xc_idx = nullptr;    // per shaded pixel: its entry in the dense exchange array (vr_cache_allreduce)
+  unsigned* xc_counts = nullptr; // per 256-pixel block: shaded pixels before it; [blocks] = total
+  // image-tile split: rows are dealt out in blocks of blk_rows, block b belongs to rank b % blk_n (vr_renderer_set_row_blocks)
+  int blk_rows = 0, blk_rank = 0, blk_n = 1;
+  uint32_t* gather_buf = nullptr;  // vr_frame_allgather staging: (1 + ranks) chunks
+  size_t gather_bytes = 0;
+  bool sharded_build = false;      // vr_renderer_set_sharded_build: the flush builds the SDF z-slab-sharded over the communicator
   bool timing = false;
   std::vector<cudaEvent_t> ev;  // 3 events per timed launch: before trace, between, after resolve
   size_t ev_used = 0;
@@ -172,6 +203,9 @@ int vrk_tf_image(vr_ctx* ctx, int32_t* bins_dev, int* scratch_dev, int width, in
 // surf != 0: the field is also written into that surface (the production schedule does it in its assembly pass)
 int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field,
                   int* levels_out, int* max_it_out, cudaSurfaceObject_t surf = 0);
+// the same field built z-slab-sharded over the context's communicator (vr_comm.cu); falls back to vrk_sdf_build without one
+int vrk_sdf_build_sharded(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field, int* levels_out,
+                          int* max_it_out, cudaSurfaceObject_t surf);
 size_t vrk_sdf_field_bytes(int nx, int ny, int nz);
 int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear);
 int vrk_sdf_to_surface(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, cudaSurfaceObject_t surf);
@@ -183,6 +217,20 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
                bool resolve, bool first_of_call = true);
 
 int vrk_xchg(vr_renderer* r, uint2* xchg, bool scatter);
+int vrk_xc_gather(vr_renderer* r, unsigned** count_dev, bool wide);
+int vrk_xc_scatter_resolve(vr_renderer* r, bool wide);
+int vrk_checksum(vr_ctx* ctx, const void* dev, size_t bytes, uint64_t* out);
+int vrk_cache_gather(vr_ctx* ctx, const uint32_t* cache, const uint32_t* idx_dev, size_t n, uint2* out_dev);
+void vr_comm_release(vr_ctx* ctx);
+int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, vr_sdf** out, bool sharded);
+int volume_finish(const vr_volume* cv);
+// hw-linear step field: per voxel cell the SDF byte + 8 quiet-octant bits, written into a 16-bit 3-D surface (vr_quiet.cu)
+int vrk_lin_field_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const int8_t* sdf_bricked, const TfTable& tf,
+                        cudaSurfaceObject_t out);
+int vrk_lin_field_masks(vr_ctx* ctx, cudaSurfaceObject_t field, int nx, int ny, int nz, uint8_t* masks_dev);
+// device RNG known-answer dump (tests): hemisphere integer triples and directions over a (seed, gid) grid (vr_render.cu)
+int vrk_rng_dump(vr_ctx* ctx, const int32_t* seeds_dev, const uint32_t* gid_dev, int n, const float* normal_rough_dev, int32_t* ra_dev,
+                 int32_t* comp_dev, float* dir_dev);
 // the volume kernels under VR_SAMPLING_HW_LINEAR (vr_volume_ops_linear.cu)
 int vrk_fetch_stats_linear(vr_ctx* ctx, cudaTextureObject_t border, cudaTextureObject_t edge, int nx, int ny, int nz, int32_t out[4],
                            int zlo, int zhi);

@@ -27,12 +27,17 @@ struct RenderParams {
   // VR_SAMPLING_HW_LINEAR (k_trace<.., LINEAR>): the volume (int16, linear filter, border 0, unnormalised coordinates) and the
   // environment map (RGBA8, linear filter, clamp to edge, normalised coordinates) behind texture objects with normalised-float reads
   cudaTextureObject_t vol_tex, env_tex;
+  // VR_SAMPLING_HW_LINEAR: the step field (vr_quiet.cu) — per voxel cell the SDF byte and one "quiet" bit per octant, 16 bits behind
+  // a surface object
+  cudaSurfaceObject_t lin_surf;
+  int lin_fa, lin_fb, lin_sa, lin_sb;  // k_trace_pt<.., LINEAR>: leave rules of the quiet-step loop and of the event-test loop
   const uchar4* __restrict__ env;
   int env_w, env_h;
   uint32_t* __restrict__ cache;
   uint32_t* __restrict__ hit;
   uchar4* __restrict__ frame;
   int W, H, row0, row1;
+  int blk_rows, blk_rank, blk_n;  // image-tile split: row block b = y / blk_rows is traced by rank b % blk_n (blk_n <= 1: every row)
   f3 cam_pos, cam_dir;
   f3 cam_side, cam_up;  // camera basis of generate_ray, evaluated once on the host in the same fp32 op order
   int token_cap;
@@ -93,6 +98,9 @@ __device__ __forceinline__ Ray generate_ray(f3 cam_pos, f3 cam_dir, f3 cam_side,
 }
 
 __device__ __forceinline__ bool lim(float p, int dim) { return p <= (float)dim && p >= 0.0f; }
+__device__ __forceinline__ bool row_owned(const RenderParams& p, int y) {
+  return p.blk_n <= 1 || (y / p.blk_rows) % p.blk_n == p.blk_rank;
+}
 
 // cut_min_eval + cut, utility_ray.cl:19-31,37-66
 __device__ __forceinline__ float cut_min_eval(float a, float b) {
@@ -130,6 +138,27 @@ __device__ __forceinline__ f3 gradient_linear(const RenderParams& p, f3 o) {
   return {(float)dx, (float)dy, (float)dz};
 }
 
+// ---- the step field of VR_SAMPLING_HW_LINEAR (built by vr_quiet.cu at the flush) -------------------------------------------------
+// Under the interpolating reading the event test of a step no longer coincides with the sign of the per-voxel SDF, so the
+// reference's loop costs 7 filtered fetches + 1 SDF byte per step.  But the filtered value at p is a convex combination
+// (non-negative weights that sum to 1, result rounded to an integer) of the 2x2x2 texels of the hardware cell c = floor(p - 0.5
+// in 8-bit fixed point), which is floor(p) - 1 or floor(p) per axis.  If the value interval of those eight texels meets no clause
+// of the transfer function, no event is possible at p whatever the gradient is.  The field holds, per voxel cell floor(p), the
+// SDF byte march() reads next (low byte) and that verdict for each of the 8 octants of the cell (high byte, bit ux + 2 uy + 4 uz,
+// u = 1 when the coordinate's fraction is >= 127.5/256: the rounding of the fixed-point conversion) — ONE 2-byte gather per step
+// decides whether the seven fetches can be skipped.  Conservative, hence bit-identical; the oracle counts 89-92 % of all event
+// tests as skippable (orc_quiet_cells).  Outside the array the surface returns 0: step 0.5, not quiet.
+__device__ __forceinline__ unsigned lin_cell(const RenderParams& p, int x, int y, int z) {
+  return surf3Dread<unsigned short>(p.lin_surf, x * 2, y, z, cudaBoundaryModeZero);
+}
+__device__ __forceinline__ int lin_sdf(unsigned cell) { return (int)(signed char)(cell & 0xFFu); }
+// o - floor(o) is exact in fp32 for o >= 0 (Sterbenz), so the comparison equals the oracle's double evaluation of the fixed-point cell
+__device__ __forceinline__ bool lin_quiet(unsigned cell, f3 o, int vx, int vy, int vz) {
+  const float h = 0.498046875f;  // 127.5 / 256
+  const unsigned oct = (o.x - (float)vx >= h ? 1u : 0u) | (o.y - (float)vy >= h ? 2u : 0u) | (o.z - (float)vz >= h ? 4u : 0u);
+  return ((cell >> (8u + oct)) & 1u) != 0u;
+}
+
 // sample_environment_map, utility_environment_map.cl:3-13: normalised coords, clamp to edge; nearest texel, or (LINEAR) the
 // texture unit's bilinear interpolation of the RGBA8 texels rounded to integers
 template <bool LINEAR = false>
@@ -153,12 +182,19 @@ __device__ __forceinline__ uchar4 env_sample(const RenderParams& p, f3 d) {
 }
 
 // get_hemisphere_direction_reflective, utility_sampling.cl:40-50; xyprod = (get_global_id(0) + 1) * (get_global_id(1) + 1)
-__device__ __forceinline__ f3 hemisphere_reflective_p(f3 normal, int seed, float roughness, unsigned xyprod) {
+// the integer part, utility_sampling.cl:41-45: ra = the three hashes, comp = (ra % 2048) - 1024 with C's signed remainder
+__device__ __forceinline__ void rng_triple(int seed, unsigned xyprod, int ra[3], int comp[3]) {
   const uint32_t useed = (uint32_t)seed + xyprod;
-  const int rx = (int)hash_u32(useed * 0x182205bdu);
-  const int ry = (int)hash_u32(useed * 0xe8d052f3u);
-  const int rz = (int)hash_u32(useed * 0xf1981dcfu);
-  f3 direction = {(float)((rx % 2048) - 1024), (float)((ry % 2048) - 1024), (float)((rz % 2048) - 1024)};
+  ra[0] = (int)hash_u32(useed * 0x182205bdu);
+  ra[1] = (int)hash_u32(useed * 0xe8d052f3u);
+  ra[2] = (int)hash_u32(useed * 0xf1981dcfu);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) comp[k] = (ra[k] % 2048) - 1024;
+}
+__device__ __forceinline__ f3 hemisphere_reflective_p(f3 normal, int seed, float roughness, unsigned xyprod) {
+  int ra[3], comp[3];
+  rng_triple(seed, xyprod, ra, comp);
+  f3 direction = {(float)comp[0], (float)comp[1], (float)comp[2]};
   const float decider = dot3(direction, normal);
   const f3 correct = normalize3_shared_rcp(direction * decider);
   return normalize3_shared_rcp(normal * (1.0f - roughness) + correct * roughness);
@@ -176,26 +212,27 @@ __device__ __forceinline__ int march_to_next_event(const RenderParams& p, Ray& r
                                                    int& colour_clause, unsigned& steps) {
   const int nx = p.vol.nx, ny = p.vol.ny, nz = p.vol.nz;
   if (LINEAR) {
-    // The reference's loop as written, with the sampler behaviour of NVIDIA hardware: the SDF is read at integer coordinates
-    // (a plain texel read), value and gradient taps at the float position are interpolated.  The event test then no longer
-    // coincides with the sign of the (per-voxel) SDF, so every step evaluates the transfer function (7 fetches + 1 SDF byte).
+    // The reference's loop with the sampler behaviour of NVIDIA hardware: the SDF is read at integer coordinates (a plain texel
+    // read), value and gradient taps at the float position are interpolated — but only where the step field cannot rule an
+    // event out (see lin_cell above); a quiet step is one 2-byte gather.
+    unsigned cell = lin_cell(p, f2i(r.o.x), f2i(r.o.y), f2i(r.o.z));  // march(), utility_ray.cl:148-154
     for (int i = 0; i < 70; ++i) {
-      const int d = p.sdf.at(f2i(r.o.x), f2i(r.o.y), f2i(r.o.z));  // march(), utility_ray.cl:148-154
-      const float step_size = max_cl((float)d, 0.5f);
+      const float step_size = max_cl((float)lin_sdf(cell), 0.5f);
       r.o = r.o + step_size * r.d;
       if (COUNT) steps++;
-      const bool exited = (r.o.x < 0.0f) | (r.o.y < 0.0f) | (r.o.z < 0.0f) | ((float)nx < r.o.x) | ((float)ny < r.o.y) | ((float)nz < r.o.z);
+      const int x = ifloor(r.o.x), y = ifloor(r.o.y), z = ifloor(r.o.z);
+      cell = lin_cell(p, x, y, z);  // inside [0,dim] floor == trunc: also the next march's SDF read
+      if (lin_quiet(cell, r.o, x, y, z)) continue;
+      const bool exited = ((x | y | z) < 0) | ((float)nx < r.o.x) | ((float)ny < r.o.y) | ((float)nz < r.o.z);
       if (exited) return EV_EXIT;
       grad = gradient_linear(p, r.o);                              // get_event_and_value, utility_ray.cl:126-138
       const int value = vol_linear(p, r.o.x, r.o.y, r.o.z);
       const int clause = tf_match(p.tf, (int)(short)value, f2s(length3(grad)));
       if (clause == 0) continue;
-      if (clause > 0) {
-        const vr_tf_rect& q = p.tf.r[clause - 1];
-        if (!(q.flags & VR_TF_THRESHOLD)) {
-          color[0] = q.rgba[0]; color[1] = q.rgba[1]; color[2] = q.rgba[2]; color[3] = q.rgba[3];
-          colour_clause = clause;
-        }
+      const vr_tf_rect& q = p.tf.r[clause - 1];
+      if (!(q.flags & VR_TF_THRESHOLD)) {
+        color[0] = q.rgba[0]; color[1] = q.rgba[1]; color[2] = q.rgba[2]; color[3] = q.rgba[3];
+        colour_clause = clause;
       }
       return EV_HIT;
     }
@@ -243,7 +280,7 @@ __global__ void __launch_bounds__(128, LINEAR ? 6 : 12) k_trace(const RenderPara
   const int x = blockIdx.x * 8 + (threadIdx.x & 7);
   const int y = p.row0 + blockIdx.y * 16 + (threadIdx.x >> 3);
   unsigned c_steps = 0, c_normals = 0, c_env = 0, c_hits = 0, c_adm = 0, c_samples = 0;
-  if (x < p.W && y < p.row1) {
+  if (x < p.W && y < p.row1 && row_owned(p, y)) {
     c_samples = 1;
     const size_t pix = (size_t)y * p.W + x;
     const int seed = p.seeds[blockIdx.z];
@@ -372,12 +409,12 @@ __global__ void __launch_bounds__(128, LINEAR ? 6 : 12) k_trace(const RenderPara
 // the shading normal (:42) — depends on the camera only.  A progressive batch (vr_render_frames: n seeds, one camera)
 // therefore evaluates it ONCE per pixel; the n samples of the pixel differ from the token admission (:39) onwards, which
 // k_trace_pt<.., true> runs per (pixel, frame).  Same values as n executions of the reference kernel, 1/n of the work.
-template <bool COUNT>
-__global__ void __launch_bounds__(128, 12) k_primary(const RenderParams p) {
+template <bool COUNT, bool LINEAR = false>
+__global__ void __launch_bounds__(128, LINEAR ? 8 : 12) k_primary(const RenderParams p) {
   const int x = blockIdx.x * 8 + (threadIdx.x & 7);
   const int y = p.row0 + blockIdx.y * 16 + (threadIdx.x >> 3);
   unsigned c_steps = 0, c_env = 0, c_hits = 0, c_samples = 0;
-  if (x < p.W && y < p.row1) {
+  if (x < p.W && y < p.row1 && row_owned(p, y)) {
     c_samples = 1;
     const size_t pix = (size_t)y * p.W + x;
     Ray vray = generate_ray(p.cam_pos, p.cam_dir, p.cam_side, p.cam_up, x, y, p.W, p.H);
@@ -391,9 +428,9 @@ __global__ void __launch_bounds__(128, 12) k_primary(const RenderParams p) {
     f3 grad = {0.0f, 0.0f, 0.0f};
     int color[4] = {0, 0, 0, 0};
     int colour_clause = 0;
-    if (is_cut) ev = march_to_next_event<COUNT>(p, cur, grad, color, colour_clause, c_steps);
+    if (is_cut) ev = march_to_next_event<COUNT, LINEAR>(p, cur, grad, color, colour_clause, c_steps);
     if (ev != EV_HIT) {
-      uchar4 e = env_sample(p, vray.d);
+      uchar4 e = env_sample<LINEAR>(p, vray.d);
       e.w = 200;
       p.frame[pix] = e;
       p.hit[pix] = VR_MISS;
@@ -442,7 +479,14 @@ __global__ void __launch_bounds__(128, 12) k_primary(const RenderParams p) {
 enum { M_IDLE = 0, M_SECOND = 2 };
 enum { EVP_NONE = 0, EVP_HIT = 1, EVP_EXIT = 2, EVP_SDF_NEG = 3, EVP_FARFACE = 4 };
 
-template <bool COUNT, bool REUSE, int CTAS, bool SURF = false>
+//
+// LINEAR (VR_SAMPLING_HW_LINEAR): a marching lane is in one of two states.  FAST: its last gather from the step field said "quiet"
+// — it steps again at the cost of one 2-byte gather.  PENDING: it stands at a position where an event is possible and needs the
+// reference's event test there (value + six gradient taps through the texture unit, the transfer function); without an event it
+// steps on and the next gather decides its state.  The warp runs the two kinds in separate loops so that the lanes of an
+// iteration all do the same thing: the quiet-step loop until too few lanes are FAST, then the event-test loop until too few are
+// PENDING, and back — until the lanes waiting for event processing or a refill outnumber the rest (the rule above).
+template <bool COUNT, bool REUSE, int CTAS, bool SURF = false, bool LINEAR = false>
 __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, unsigned* __restrict__ work_counter) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -455,6 +499,8 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
   // slot state
   int mode = M_IDLE;
   bool marching = false;
+  bool pending = false;               // LINEAR: the event test at the current position is still to be done
+  f3 hgrad = {0.0f, 0.0f, 0.0f};      // LINEAR: gradient of that test when it found a hit
   int ev = EVP_NONE;
   // Register diet (ncu: at 40 registers the spills of this kernel made 59 M local loads/stores per launch, 213 M sectors of
   // L1<->L2 traffic beside 337 M sectors of gathers): the pixel enters the RNG only as (x+1)*(y+1); base point, shading normal
@@ -480,9 +526,10 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
     int bseed = 0;
 
     // ---- events of the slots whose segment ended ---------------------------------------------------------------------------
-    if (mode != M_IDLE && !marching) {
+    if (mode != M_IDLE && !marching && !(LINEAR && pending)) {
       f3 grad = {0.0f, 0.0f, 0.0f};
-      if (ev == EVP_SDF_NEG || ev == EVP_FARFACE) {
+      if (LINEAR) grad = hgrad;
+      if (!LINEAR && (ev == EVP_SDF_NEG || ev == EVP_FARFACE)) {
         const int vx = ifloor(o.x), vy = ifloor(o.y), vz = ifloor(o.z);
         grad = gradient_voxel(p.vol, vx, vy, vz);
         const int value = ev == EVP_SDF_NEG ? p.vol.at(vx, vy, vz) : 0;
@@ -500,7 +547,7 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
         bool next_o = false;
         if (ev == EVP_EXIT) {
           const float factor = pi == 8 ? 8.0f / 8.0f : (pi == 9 ? 8.0f / 9.0f : 8.0f / 10.0f);  // 8.0f / i, i in {8,9,10}: constants
-          const uchar4 lm = env_sample(p, dv);
+          const uchar4 lm = env_sample<LINEAR>(p, dv);
           if (COUNT) c_env++;
           const unsigned bv0 = f2u((float)(bvp & 1023u) + atten * er * (float)lm.x * factor / 1.0f);
           const unsigned bv1 = f2u((float)((bvp >> 10) & 1023u) + atten * eg * (float)lm.y * factor / 1.0f);
@@ -612,13 +659,77 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
       atten = reset_atten ? a : atten * a;
     }
     if (need_start) {  // first half of march(), utility_ray.cl:148-150
-      if (SURF) d = surf3Dread<signed char>(p.sdf_surf, f2i(o.x), f2i(o.y), f2i(o.z), cudaBoundaryModeZero);
+      if (LINEAR) d = lin_sdf(lin_cell(p, f2i(o.x), f2i(o.y), f2i(o.z)));
+      else if (SURF) d = surf3Dread<signed char>(p.sdf_surf, f2i(o.x), f2i(o.y), f2i(o.z), cudaBoundaryModeZero);
       else d = p.sdf.at(f2i(o.x), f2i(o.y), f2i(o.z));
       steps_left = 70;
       marching = true;
+      pending = false;
       ev = EVP_NONE;
     }
     if (!__ballot_sync(0xffffffffu, mode != M_IDLE)) break;  // queue empty and every slot free
+
+    if (LINEAR) {
+      // one march() + the gather that classifies the new position (utility_ray.cl:148-154, :112-117)
+      auto advance = [&]() {
+        const float step_size = max_cl((float)d, 0.5f);
+        o = o + step_size * dv;
+        if (COUNT) c_steps++;
+        steps_left--;
+        const int vx = ifloor(o.x), vy = ifloor(o.y), vz = ifloor(o.z);
+        const unsigned cell = lin_cell(p, vx, vy, vz);
+        d = lin_sdf(cell);
+        if (lin_quiet(cell, o, vx, vy, vz)) {  // no event possible here: get_event_and_value returns None
+          pending = false;
+          marching = steps_left != 0;
+          if (!marching) ev = EVP_NONE;
+        } else {
+          const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
+          marching = false;
+          pending = !exited;
+          if (exited) ev = EVP_EXIT;
+        }
+      };
+      for (;;) {
+        // ---- quiet-step loop ----
+        for (;;) {
+          if (marching) advance();
+          const unsigned act = __ballot_sync(0xffffffffu, marching);
+          if (!act) break;
+          const unsigned others = __ballot_sync(0xffffffffu, !marching && (pending || mode != M_IDLE || !exhausted));
+          if (__popc(act) * p.lin_fa < __popc(others) * p.lin_fb) break;
+        }
+        // ---- event-test loop: get_event_and_value (utility_ray.cl:126-138) where an event is possible ----
+        for (;;) {
+          if (!__ballot_sync(0xffffffffu, pending)) break;
+          if (pending) {
+            const f3 grad = gradient_linear(p, o);
+            const int value = vol_linear(p, o.x, o.y, o.z);
+            const int clause = tf_match(p.tf, (int)(short)value, f2s(length3(grad)));
+            if (clause != 0) {
+              if (!(p.tf.r[clause - 1].flags & VR_TF_THRESHOLD)) clause_col = clause;
+              hgrad = grad;
+              ev = EVP_HIT;
+              pending = false;
+            } else if (steps_left == 0) {
+              ev = EVP_NONE;
+              pending = false;
+            } else {
+              advance();
+            }
+          }
+          const unsigned pend = __ballot_sync(0xffffffffu, pending);
+          if (!pend) break;
+          const unsigned others = __ballot_sync(0xffffffffu, !pending && (marching || mode != M_IDLE || !exhausted));
+          if (__popc(pend) * p.lin_sa < __popc(others) * p.lin_sb) break;
+        }
+        const unsigned go = __ballot_sync(0xffffffffu, marching || pending);
+        if (!go) break;
+        const unsigned waiting = __ballot_sync(0xffffffffu, !marching && !pending && (mode != M_IDLE || !exhausted));
+        if (__popc(go) * p.rule_a < __popc(waiting) * p.rule_b) break;
+      }
+      continue;
+    }
 
     // ---- step loop: march (second half) + get_event_and_value with the SDF-sign shortcut -------------------------------------------
     for (;;) {
@@ -666,6 +777,20 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
 }
 
 // phase 2: ray_marching.cl:82-99
+__device__ __forceinline__ uchar4 resolve_rgbw(uint32_t r, uint32_t g, uint32_t b, uint32_t w);
+__device__ __forceinline__ uchar4 resolve_entry(const uint2 c) {
+  return resolve_rgbw(c.x & 0xFFFFu, c.x >> 16, c.y & 0xFFFFu, c.y >> 16);
+}
+__device__ __forceinline__ uchar4 resolve_rgbw(uint32_t r, uint32_t g, uint32_t b, uint32_t w) {
+  if (w != 0) { r /= w; g /= w; b /= w; } else { r = g = b = 0; }
+  const float inv_gamma = 1.0f / 1.77777777f;
+  const float brightness = 4.0f;
+  float fr = (float)r / 255.0f, fg = (float)g / 255.0f, fb = (float)b / 255.0f;
+  fr = powf(fr * brightness, inv_gamma) * 255.0f;
+  fg = powf(fg * brightness, inv_gamma) * 255.0f;
+  fb = powf(fb * brightness, inv_gamma) * 255.0f;
+  return make_uchar4((unsigned char)min(f2u(fr), 255u), (unsigned char)min(f2u(fg), 255u), (unsigned char)min(f2u(fb), 255u), 1);
+}
 __global__ void __launch_bounds__(256) k_resolve(const uint32_t* __restrict__ hit, const uint2* __restrict__ cache,
                                                  uchar4* __restrict__ frame, int W, int row0, int row1) {
   const size_t n = (size_t)W * (row1 - row0);
@@ -674,17 +799,7 @@ __global__ void __launch_bounds__(256) k_resolve(const uint32_t* __restrict__ hi
   const size_t pix = (size_t)row0 * W + i;
   const uint32_t voxel = hit[pix];
   if (voxel == VR_MISS) return;
-  const uint2 c = cache[voxel];
-  uint32_t r = c.x & 0xFFFFu, g = c.x >> 16, b = c.y & 0xFFFFu, w = c.y >> 16;
-  if (w != 0) { r /= w; g /= w; b /= w; } else { r = g = b = 0; }
-  const float inv_gamma = 1.0f / 1.77777777f;
-  const float brightness = 4.0f;
-  float fr = (float)r / 255.0f, fg = (float)g / 255.0f, fb = (float)b / 255.0f;
-  fr = powf(fr * brightness, inv_gamma) * 255.0f;
-  fg = powf(fg * brightness, inv_gamma) * 255.0f;
-  fb = powf(fb * brightness, inv_gamma) * 255.0f;
-  frame[pix] = make_uchar4((unsigned char)min(f2u(fr), 255u), (unsigned char)min(f2u(fg), 255u),
-                           (unsigned char)min(f2u(fb), 255u), 1);
+  frame[pix] = resolve_entry(cache[voxel]);
 }
 
 // Host evaluation of utility_ray.cl:70-76 in fp32, same operation order as the device helpers (dot3/length3/normalize3).
@@ -717,6 +832,95 @@ void camera_basis(const float dir[3], f3* side, f3* up) {
 }
 }  // namespace
 
+// launch of one k_trace_pt instantiation on persistent CTAs: as many as are resident at once
+template <bool COUNT, bool REUSE, int CTAS, bool SURF, bool LINEAR>
+static int launch_pt(vr_ctx* ctx, const RenderParams& p, unsigned* work_counter) {
+  static int per_sm = 0;  // every device this library accepts is a B200: one answer per instantiation
+  if (!per_sm) VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_pt<COUNT, REUSE, CTAS, SURF, LINEAR>, 128, 0));
+  const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)std::max(1, per_sm);
+  k_trace_pt<COUNT, REUSE, CTAS, SURF, LINEAR><<<blocks, 128, 0, ctx->stream>>>(p, work_counter);
+  ctx->launches++;
+  return VR_OK;
+}
+// register budget of the production variants: 12 CTAs/SM = 40 registers (NEAREST), 8 CTAs/SM = 64 registers (LINEAR: texture
+// handles, the gradient of a pending hit).  A -DVR_AB build adds the other budgets for A/B runs (vr_renderer_set_tuning).
+template <bool COUNT, bool REUSE, bool LINEAR>
+static int launch_pt_select(vr_renderer* r, const RenderParams& p, unsigned* wc) {
+  vr_ctx* ctx = r->ctx;
+  if (LINEAR) {
+#ifdef VR_AB
+    if (!COUNT && r->tune.pt_ctas == 6) return launch_pt<COUNT, REUSE, 6, true, true>(ctx, p, wc);
+    if (!COUNT && r->tune.pt_ctas == 10) return launch_pt<COUNT, REUSE, 10, true, true>(ctx, p, wc);
+    if (!COUNT && r->tune.pt_ctas == 12) return launch_pt<COUNT, REUSE, 12, true, true>(ctx, p, wc);
+#endif
+    return launch_pt<COUNT, REUSE, 8, true, true>(ctx, p, wc);
+  }
+  const bool surf = REUSE && !COUNT && r->sdf->surf != 0;  // the surface-object gather serves the production schedule
+#ifdef VR_AB
+  if (REUSE && !COUNT) {
+    const int c = r->tune.pt_ctas;
+    if (surf && c == 8) return launch_pt<false, true, 8, true, false>(ctx, p, wc);
+    if (surf && c == 10) return launch_pt<false, true, 10, true, false>(ctx, p, wc);
+    if (surf && c == 14) return launch_pt<false, true, 14, true, false>(ctx, p, wc);
+    if (surf && c == 16) return launch_pt<false, true, 16, true, false>(ctx, p, wc);
+    if (!surf && c == 8) return launch_pt<false, true, 8, false, false>(ctx, p, wc);
+    if (!surf && c == 10) return launch_pt<false, true, 10, false, false>(ctx, p, wc);
+  }
+#endif
+  if (surf) return launch_pt<COUNT, REUSE, 12, true, false>(ctx, p, wc);
+  return launch_pt<COUNT, REUSE, 12, false, false>(ctx, p, wc);
+}
+
+template <bool COUNT, bool LINEAR>
+static int launch_trace(vr_renderer* r, RenderParams& p, const float pos[3], const float dir[3], int rows, int nframes, bool first_of_call) {
+  vr_ctx* ctx = r->ctx;
+  const size_t pixels = (size_t)r->W * rows * nframes;
+  dim3 grid(div_up(r->W, 8), div_up(rows, 16), nframes);
+  if (r->trace_mode == 0) {  // one thread per pixel and frame for its whole life
+    r->primary_valid = false;
+    k_trace<COUNT, false, LINEAR><<<grid, 128, 0, ctx->stream>>>(p);
+    ctx->launches++;
+    return VR_OK;
+  }
+  // mode 1 (hybrid): dense thread-per-pixel k_trace per frame queues admitted hits, persistent warps run their secondary paths
+  // mode 2 (primary reuse, default): k_primary once per pixel, persistent warps run admission + secondary paths per (pixel, frame)
+  const bool reuse = r->trace_mode == 2;
+  const size_t cap = reuse ? (size_t)r->W * rows : std::min<size_t>(pixels, (size_t)32 << 20);
+  if (r->queue_cap < cap) {
+    if (r->queue) VR_CUDA(cudaFreeAsync(r->queue, ctx->stream));
+    r->queue = nullptr; r->queue_cap = 0;
+    r->primary_valid = false;
+    VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&r->queue), cap * 3 * sizeof(uint4), ctx->stream));
+    r->queue_cap = cap;
+  }
+  p.queue = r->queue;
+  p.qcap = (unsigned)r->queue_cap;
+  p.qcount = reinterpret_cast<unsigned*>(r->counters + 6);
+  if (!reuse) {
+    r->primary_valid = false;
+    VR_CUDA(cudaMemsetAsync(p.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
+    k_trace<COUNT, true, LINEAR><<<grid, 128, 0, ctx->stream>>>(p);
+    ctx->launches++;
+    return launch_pt_select<COUNT, false, LINEAR>(r, p, p.qcount + 1);
+  }
+  // The records stay valid while camera, rows and scene are unchanged.  Within one call they are always reused; across
+  // calls only on request (vr_renderer_set_primary_reuse(r, 2): the frame_emitter loop calls render_frame once per
+  // sample).  With the per-sample counters on, every batch re-marches (k_primary adds its share for the batch).
+  const bool same = r->primary_valid && !memcmp(r->primary_pos, pos, 12) && !memcmp(r->primary_dir, dir, 12) &&
+                    r->primary_rows[0] == r->row0 && r->primary_rows[1] == r->row1;
+  if (!same || COUNT || (first_of_call && !r->primary_across_calls)) {
+    VR_CUDA(cudaMemsetAsync(p.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
+    dim3 g1(div_up(r->W, 8), div_up(rows, 16), 1);
+    k_primary<COUNT, LINEAR><<<g1, 128, 0, ctx->stream>>>(p);
+    ctx->launches++;
+    memcpy(r->primary_pos, pos, 12); memcpy(r->primary_dir, dir, 12);
+    r->primary_rows[0] = r->row0; r->primary_rows[1] = r->row1;
+    r->primary_valid = true;
+  }
+  VR_CUDA(cudaMemsetAsync(p.qcount + 1, 0, sizeof(unsigned), ctx->stream));
+  return launch_pt_select<COUNT, true, LINEAR>(r, p, p.qcount + 1);
+}
+
 int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int32_t* seeds, int nframes, bool trace,
                bool resolve, bool first_of_call) {
   vr_ctx* ctx = r->ctx;
@@ -724,7 +928,8 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
   if (rows <= 0) return VR_OK;
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
   if (nframes < 1 || nframes > VR_MAX_BATCH) { vr_set_error("vrk_render: bad batch size"); return VR_ERR_INVALID; }
-  if (trace && r->sampling == VR_SAMPLING_HW_LINEAR && (!r->vol_tex || !r->env_tex)) {  // textures are built by the flush
+  const bool lin = r->sampling == VR_SAMPLING_HW_LINEAR;
+  if (trace && lin && (!r->vol_tex || !r->env_tex || !r->lin_surf)) {  // textures and step field are built by the flush
     vr_set_error("vrk_render: hw-linear sampling needs a vr_renderer_flush after vr_renderer_set_sampling");
     return VR_ERR_INVALID;
   }
@@ -754,6 +959,7 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     p.sdf = SdfView{r->sdf->field, r->sdf->nx, r->sdf->ny, r->sdf->nz, r->sdf->nx / 8 + 1, r->sdf->ny / 8 + 1};
     p.sdf_surf = r->sdf->surf;
     p.vol_tex = r->vol_tex; p.env_tex = r->env_tex;
+    p.lin_surf = r->lin_surf;
     p.env = r->env->texels;
     p.env_w = r->env->w;
     p.env_h = r->env->h;
@@ -761,105 +967,25 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     p.hit = r->hit;
     p.frame = r->frame;
     p.W = r->W; p.H = r->H; p.row0 = r->row0; p.row1 = r->row1;
+    p.blk_rows = std::max(r->blk_rows, 1); p.blk_rank = r->blk_rank; p.blk_n = r->blk_n;
     p.cam_pos = {pos[0], pos[1], pos[2]};
     p.cam_dir = {dir[0], dir[1], dir[2]};
     camera_basis(dir, &p.cam_side, &p.cam_up);
     p.nframes = nframes;
-    static const int pixel_major = getenv("VR_PT_ORDER") ? std::max(atoi(getenv("VR_PT_ORDER")), 0) : 1;
-    p.pixel_major = pixel_major;
-    static int rule[2] = {0, 0};
-    if (!rule[0]) {
-      // measured on the bench scene (ms per 64-frame step, default / close-up view): 1,1 2.43 / 6.92; 2,1 2.24 / 6.39;
-      // 4,1 2.17 / 6.15; 6,1 2.17 / 6.09; 8,1 2.20 / 6.10; 16,1 2.28 / 6.28; never leave early 2.46 / 6.64; 1,2 2.85 / 8.17
-      rule[0] = 5; rule[1] = 1;
-      if (const char* e = getenv("VR_PT_RULE")) sscanf(e, "%d,%d", &rule[0], &rule[1]);
-      if (rule[0] < 1 || rule[1] < 1) { rule[0] = 5; rule[1] = 1; }
-    }
-    p.rule_a = rule[0]; p.rule_b = rule[1];
+    p.pixel_major = r->tune.pixel_major;
+    p.rule_a = r->tune.rule[0]; p.rule_b = r->tune.rule[1];
+    p.lin_fa = r->tune.lin_rule[0]; p.lin_fb = r->tune.lin_rule[1]; p.lin_sa = r->tune.lin_rule[2]; p.lin_sb = r->tune.lin_rule[3];
     for (int k = 0; k < nframes; ++k) p.seeds[k] = seeds[k];
     p.token_cap = r->token_cap;
     p.counters = r->counters;
     p.queue = nullptr; p.qcount = nullptr; p.qcap = 0;
     p.tf = r->tf_active;
-    static int per_sm[4] = {0, 0, 0, 0};  // resident CTAs per SM of the k_trace_pt instantiations
-    static int pt_ctas = 12;              // VR_PT_CTAS: register budget of the production variant (8: 64 regs, 10: 48, 12: 40)
-    if (!per_sm[0]) {
-      if (const char* e = getenv("VR_PT_CTAS")) pt_ctas = atoi(e) == 8 ? 8 : (atoi(e) == 10 ? 10 : (atoi(e) == 16 ? 16 : (atoi(e) == 14 ? 14 : 12)));
-      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_trace_pt<false, false, 12>, 128, 0));
-      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_trace_pt<true, false, 12>, 128, 0));
-      if (pt_ctas == 8) VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_trace_pt<false, true, 8>, 128, 0));
-      else if (pt_ctas == 16) VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_trace_pt<false, true, 16>, 128, 0));
-      else if (pt_ctas == 10) VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_trace_pt<false, true, 10>, 128, 0));
-      else VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_trace_pt<false, true, 12>, 128, 0));
-      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_trace_pt<true, true, 12>, 128, 0));
-    }
-    const size_t pixels = (size_t)r->W * rows * nframes;
-    dim3 grid(div_up(r->W, 8), div_up(rows, 16), nframes);
-    if (r->sampling == VR_SAMPLING_HW_LINEAR) {
-      // the literal per-pixel kernel with the texture-unit sampling (vr_renderer_set_sampling)
-      r->primary_valid = false;
-      if (r->count) k_trace<true, false, true><<<grid, 128, 0, ctx->stream>>>(p);
-      else k_trace<false, false, true><<<grid, 128, 0, ctx->stream>>>(p);
-    } else if (r->trace_mode >= 1) {
-      // mode 1 (hybrid): dense thread-per-pixel k_trace per frame queues admitted hits, persistent warps run their secondary paths
-      // mode 2 (primary reuse, default): k_primary once per pixel, persistent warps run admission + secondary paths per (pixel, frame)
-      const bool reuse = r->trace_mode == 2;
-      const size_t cap = reuse ? (size_t)r->W * rows : std::min<size_t>(pixels, (size_t)32 << 20);
-      if (r->queue_cap < cap) {
-        if (r->queue) VR_CUDA(cudaFreeAsync(r->queue, ctx->stream));
-        r->queue = nullptr; r->queue_cap = 0;
-        r->primary_valid = false;
-        VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&r->queue), cap * 3 * sizeof(uint4), ctx->stream));
-        r->queue_cap = cap;
-      }
-      p.queue = r->queue;
-      p.qcap = (unsigned)r->queue_cap;
-      p.qcount = reinterpret_cast<unsigned*>(r->counters + 6);
-      if (reuse) {
-        // The records stay valid while camera, rows and scene are unchanged.  Within one call they are always reused; across
-        // calls only on request (vr_renderer_set_primary_reuse(r, 2): the frame_emitter loop calls render_frame once per
-        // sample).  With the per-sample counters on, every batch re-marches (k_primary adds its share for the batch).
-        const bool same = r->primary_valid && !memcmp(r->primary_pos, pos, 12) && !memcmp(r->primary_dir, dir, 12) &&
-                          r->primary_rows[0] == r->row0 && r->primary_rows[1] == r->row1;
-        if (!same || r->count || (first_of_call && !r->primary_across_calls)) {
-          VR_CUDA(cudaMemsetAsync(p.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
-          dim3 g1(div_up(r->W, 8), div_up(rows, 16), 1);
-          if (r->count) k_primary<true><<<g1, 128, 0, ctx->stream>>>(p);
-          else k_primary<false><<<g1, 128, 0, ctx->stream>>>(p);
-          ctx->launches++;
-          memcpy(r->primary_pos, pos, 12); memcpy(r->primary_dir, dir, 12);
-          r->primary_rows[0] = r->row0; r->primary_rows[1] = r->row1;
-          r->primary_valid = true;
-        }
-        VR_CUDA(cudaMemsetAsync(p.qcount + 1, 0, sizeof(unsigned), ctx->stream));
-        const int v = r->count ? 3 : 2;
-        const unsigned blocks = (unsigned)ctx->sm_count * std::max(1, per_sm[v]);
-        if (r->count) k_trace_pt<true, true, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else if (pt_ctas == 8) k_trace_pt<false, true, 8><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else if (pt_ctas == 16) k_trace_pt<false, true, 16><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else if (r->sdf->surf && pt_ctas == 14) k_trace_pt<false, true, 14, true><<<(unsigned)ctx->sm_count * 14, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else if (r->sdf->surf && pt_ctas == 16) k_trace_pt<false, true, 16, true><<<(unsigned)ctx->sm_count * 16, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else if (r->sdf->surf && pt_ctas == 10) k_trace_pt<false, true, 10, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else if (r->sdf->surf && pt_ctas == 8) k_trace_pt<false, true, 8, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else if (r->sdf->surf) k_trace_pt<false, true, 12, true><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else if (pt_ctas == 10) k_trace_pt<false, true, 10><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else k_trace_pt<false, true, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-      } else {
-        r->primary_valid = false;
-        VR_CUDA(cudaMemsetAsync(p.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
-        if (r->count) k_trace<true, true><<<grid, 128, 0, ctx->stream>>>(p);
-        else k_trace<false, true><<<grid, 128, 0, ctx->stream>>>(p);
-        const unsigned blocks = (unsigned)ctx->sm_count * std::max(1, per_sm[r->count ? 1 : 0]);
-        if (r->count) k_trace_pt<true, false, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        else k_trace_pt<false, false, 12><<<blocks, 128, 0, ctx->stream>>>(p, p.qcount + 1);
-        ctx->launches++;
-      }
-    } else {
-      r->primary_valid = false;
-      if (r->count) k_trace<true, false><<<grid, 128, 0, ctx->stream>>>(p);
-      else k_trace<false, false><<<grid, 128, 0, ctx->stream>>>(p);
-    }
-    ctx->launches++;
+    int st;
+    if (lin) st = r->count ? launch_trace<true, true>(r, p, pos, dir, rows, nframes, first_of_call)
+                           : launch_trace<false, true>(r, p, pos, dir, rows, nframes, first_of_call);
+    else st = r->count ? launch_trace<true, false>(r, p, pos, dir, rows, nframes, first_of_call)
+                       : launch_trace<false, false>(r, p, pos, dir, rows, nframes, first_of_call);
+    VR_TRY(st);
   }
   if (e1) VR_CUDA(cudaEventRecord(e1, ctx->stream));
   if (resolve) {
@@ -873,13 +999,114 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
   return VR_OK;
 }
 
-// ---- compact cache exchange for the spp split (multi-GPU hook, no reference counterpart) -----------------------------
-// Every rank of an spp split traces the SAME camera, so the primary hit voxel of a pixel — and therefore the set of
-// cache entries touched since the last reset — is identical on all ranks.  Instead of all-reducing the dense cache
-// (8 bytes x voxels: 1 GiB at 512^3) the ranks exchange one 8-byte entry per pixel (16 MB at 1080p):
-//   gather : xchg[pix] = cache[hit[pix]]  (0 for environment pixels)
-//   (caller: sum-all-reduce xchg as int32 words — 16-bit lanes cannot carry with a per-rank token cap of 256/N)
-//   scatter: cache[hit[pix]] = xchg[pix]  (pixels sharing a voxel write the same global sum)
+// ---- compact cache exchange for the spp split (multi-GPU, no reference counterpart) -----------------------------------
+// Every rank of an spp split traces the SAME camera, so the primary hit voxel of a pixel — and therefore the set of cache
+// entries touched since the last reset — is identical on all ranks.  Instead of all-reducing the dense cache (8 bytes x voxels:
+// 1 GiB at 512^3) the ranks exchange one 8-byte entry per SHADED pixel: the shaded pixels are numbered in pixel order (a
+// prefix sum over the hit buffer, identical on all ranks because the hit buffer is), gathered into a dense array of that many
+// entries (1.3 MB instead of 16.6 MB at the bench's 8 % shaded pixels), summed across ranks as uint32 words — 16-bit lanes
+// cannot carry with a per-rank token cap of 256/N — and written back by the kernel that also resolves the frame.
+//   k_xc_count / k_xc_scan / k_xc_gather : xchg[rank_of(pix)] = cache[hit[pix]]
+//   (vr_comm.cu: ncclAllReduce over 2 * count uint32)
+//   k_xc_scatter_resolve : cache[hit[pix]] = xchg[..] (pixels sharing a voxel write the same global sum) and frame[pix] resolved
+__global__ void __launch_bounds__(256) k_xc_count(const uint32_t* __restrict__ hit, size_t n, unsigned* __restrict__ block_counts) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const int c = __syncthreads_count(i < n && hit[i] != VR_MISS);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = (unsigned)c;
+}
+// one block: exclusive scan of nb counts in place, counts[nb] = total
+__global__ void __launch_bounds__(1024) k_xc_scan(unsigned* __restrict__ counts, unsigned nb) {
+  __shared__ unsigned s[1024];
+  const unsigned t = threadIdx.x, chunk = (nb + 1023u) / 1024u;
+  const unsigned lo = min(t * chunk, nb), hi = min(lo + chunk, nb);
+  unsigned sum = 0;
+  for (unsigned i = lo; i < hi; ++i) sum += counts[i];
+  s[t] = sum;
+  __syncthreads();
+  for (unsigned o = 1; o < 1024; o <<= 1) {
+    const unsigned v = t >= o ? s[t - o] : 0u;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  unsigned run = s[t] - sum;
+  for (unsigned i = lo; i < hi; ++i) { const unsigned c = counts[i]; counts[i] = run; run += c; }
+  if (t == 1023) counts[nb] = s[t];
+}
+// WIDE: the four 16-bit lanes of an entry go into four uint32 words, for ranks that each accumulate up to the full cap of 256
+// tokens (a weak-scaling spp split: N x 64 spp with N x 256 tokens per voxel in total) — the packed lanes would overflow in the sum
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_xc_gather(const uint32_t* __restrict__ hit, const uint2* __restrict__ cache,
+                                                   const unsigned* __restrict__ block_off, uint32_t* __restrict__ cidx,
+                                                   uint2* __restrict__ xchg, size_t n) {
+  __shared__ unsigned wsum[8];
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t voxel = i < n ? hit[i] : VR_MISS;
+  const bool shaded = voxel != VR_MISS;
+  const unsigned m = __ballot_sync(0xffffffffu, shaded);
+  if (lane == 0) wsum[warp] = (unsigned)__popc(m);
+  __syncthreads();
+  unsigned off = block_off[blockIdx.x];
+  for (unsigned w = 0; w < warp; ++w) off += wsum[w];
+  if (shaded) {
+    const unsigned idx = off + (unsigned)__popc(m & ((1u << lane) - 1u));
+    cidx[i] = idx;
+    const uint2 c = cache[voxel];
+    if (WIDE) reinterpret_cast<uint4*>(xchg)[idx] = make_uint4(c.x & 0xFFFFu, c.x >> 16, c.y & 0xFFFFu, c.y >> 16);
+    else xchg[idx] = c;
+  }
+}
+__global__ void __launch_bounds__(256) k_xc_scatter_resolve(const uint32_t* __restrict__ hit, const uint32_t* __restrict__ cidx,
+                                                            const uint2* __restrict__ xchg, uint2* __restrict__ cache,
+                                                            uchar4* __restrict__ frame, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t voxel = hit[i];
+  if (voxel == VR_MISS) return;
+  const uint2 e = xchg[cidx[i]];
+  cache[voxel] = e;
+  frame[i] = resolve_entry(e);
+}
+// wide sums: resolved as they are (ray_marching.cl:82-99 on the global totals); the per-rank caches keep their partial sums
+__global__ void __launch_bounds__(256) k_xc_resolve_wide(const uint32_t* __restrict__ hit, const uint32_t* __restrict__ cidx,
+                                                         const uint4* __restrict__ xw, uchar4* __restrict__ frame, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (hit[i] == VR_MISS) return;
+  const uint4 e = xw[cidx[i]];
+  frame[i] = resolve_rgbw(e.x, e.y, e.z, e.w);
+}
+
+// gather: returns the number of entries through *count_dev (device, read by the caller); needs the full frame traced
+int vrk_xc_gather(vr_renderer* r, unsigned** count_dev, bool wide) {
+  vr_ctx* ctx = r->ctx;
+  const size_t n = (size_t)r->W * r->H;
+  const unsigned nb = div_up(n, 256);
+  if (!r->xchg) VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&r->xchg), n * sizeof(uint4), ctx->stream));  // room for the wide form
+  if (!r->xc_idx) VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&r->xc_idx), n * sizeof(uint32_t), ctx->stream));
+  if (!r->xc_counts) VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&r->xc_counts), ((size_t)nb + 1) * sizeof(unsigned), ctx->stream));
+  k_xc_count<<<nb, 256, 0, ctx->stream>>>(r->hit, n, r->xc_counts);
+  k_xc_scan<<<1, 1024, 0, ctx->stream>>>(r->xc_counts, nb);
+  if (wide) k_xc_gather<true><<<nb, 256, 0, ctx->stream>>>(r->hit, reinterpret_cast<const uint2*>(r->cache), r->xc_counts, r->xc_idx, r->xchg, n);
+  else k_xc_gather<false><<<nb, 256, 0, ctx->stream>>>(r->hit, reinterpret_cast<const uint2*>(r->cache), r->xc_counts, r->xc_idx, r->xchg, n);
+  ctx->launches += 3;
+  VR_CUDA(cudaGetLastError());
+  *count_dev = r->xc_counts + nb;
+  return VR_OK;
+}
+int vrk_xc_scatter_resolve(vr_renderer* r, bool wide) {
+  const size_t n = (size_t)r->W * r->H;
+  if (wide) k_xc_resolve_wide<<<div_up(n, 256), 256, 0, r->ctx->stream>>>(r->hit, r->xc_idx, reinterpret_cast<const uint4*>(r->xchg), r->frame, n);
+  else k_xc_scatter_resolve<<<div_up(n, 256), 256, 0, r->ctx->stream>>>(r->hit, r->xc_idx, r->xchg, reinterpret_cast<uint2*>(r->cache),
+                                                                  r->frame, n);
+  r->ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}
+
+// the per-pixel form (one entry per pixel, zeros for environment pixels): kept for callers that run the collective themselves
+// on the raw device pointer (vr_renderer_xchg_device_ptr)
 __global__ void __launch_bounds__(256) k_xchg_gather(const uint32_t* __restrict__ hit, const uint2* __restrict__ cache,
                                                      uint2* __restrict__ xchg, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -902,6 +1129,31 @@ int vrk_xchg(vr_renderer* r, uint2* xchg, bool scatter) {
   else
     k_xchg_gather<<<div_up(n, 256), 256, 0, r->ctx->stream>>>(r->hit, reinterpret_cast<const uint2*>(r->cache), xchg, n);
   r->ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}
+
+// ---- device RNG known-answer dump (tests/test_parity_gpu.py::test_device_rng_known_answers) ------------------------------------------
+// Runs the device functions the trace kernels call (rng_triple, hemisphere_reflective_p) over a caller-supplied (seed, gid0, gid1)
+// list and returns the integer triples, the components and the final directions for a fixed normal / roughness per item.
+__global__ void __launch_bounds__(128) k_rng_dump(const int32_t* __restrict__ seeds, const uint32_t* __restrict__ gid, int n,
+                                                  const float* __restrict__ normal_rough, int32_t* __restrict__ ra_out,
+                                                  int32_t* __restrict__ comp_out, float* __restrict__ dir_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned xyp = (gid[2 * i] + 1u) * (gid[2 * i + 1] + 1u);
+  int ra[3], comp[3];
+  rng_triple(seeds[i], xyp, ra, comp);
+  for (int k = 0; k < 3; ++k) { ra_out[3 * i + k] = ra[k]; comp_out[3 * i + k] = comp[k]; }
+  const f3 nrm = {normal_rough[4 * i], normal_rough[4 * i + 1], normal_rough[4 * i + 2]};
+  const f3 d = hemisphere_reflective_p(nrm, seeds[i], normal_rough[4 * i + 3], xyp);
+  dir_out[3 * i] = d.x; dir_out[3 * i + 1] = d.y; dir_out[3 * i + 2] = d.z;
+}
+
+int vrk_rng_dump(vr_ctx* ctx, const int32_t* seeds_dev, const uint32_t* gid_dev, int n, const float* normal_rough_dev, int32_t* ra_dev,
+                 int32_t* comp_dev, float* dir_dev) {
+  k_rng_dump<<<div_up((size_t)n, 128), 128, 0, ctx->stream>>>(seeds_dev, gid_dev, n, normal_rough_dev, ra_dev, comp_dev, dir_dev);
+  ctx->launches++;
   VR_CUDA(cudaGetLastError());
   return VR_OK;
 }

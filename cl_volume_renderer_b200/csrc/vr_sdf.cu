@@ -27,7 +27,8 @@
 //                      x == nx / y == ny / z == nz — what the ray marcher gathers from), written exactly once, coalesced
 //   The build is an object that advances level by level (vr_sdf_slab): the single-GPU build runs it to the end, the z-slab
 //   sharded build (parallel.py) swaps halo planes of the bit volume between its ranks every K levels.
-// Alternative schedules, all bit-exact, selected with VR_SDF_MODE for A/B: vr_sdf_variants.cu (DESIGN.md §4.2 has the table).
+// Alternative schedules, all bit-exact, live in vr_sdf_variants.cu and are linked into the A/B build only (`make ab` ->
+// libvr_ab.so, selected there with VR_SDF_MODE; DESIGN.md §4.2 has the table).
 #include <cstring>
 #include "vr_sdf_common.cuh"
 
@@ -163,8 +164,12 @@ int vrk_sdf_slab_create(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz,
   w.nxw = (nx + 31) / 32;
   w.bx = nx / BR + 1; w.by = ny / BR + 1; w.bz = nz / BR + 1;
   // measured at 512^3 (VR_SDF_TZ): see DESIGN.md 4.2
+#ifdef VR_AB
   static const int tile_z_env = getenv("VR_SDF_TZ") ? atoi(getenv("VR_SDF_TZ")) : WT_Z;
   s->tile_z = (tile_z_env == 2 || tile_z_env == 4 || tile_z_env == 16) ? tile_z_env : WT_Z;
+#else
+  s->tile_z = WT_Z;
+#endif
   w.tx = (w.nxw + WT_XW - 1) / WT_XW; w.ty = (ny + WT_Y - 1) / WT_Y; w.tz = (nz + s->tile_z - 1) / s->tile_z;
   w.lastbit = (unsigned)((nx - 1) & 31);
   s->nwords = (size_t)w.nxw * ny * nz;
@@ -197,8 +202,13 @@ int vrk_sdf_slab_create(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz,
 int vrk_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* done) {
   vr_ctx* ctx = s->ctx;
   const WaveDims& w = s->w;
-  static const int grid_mult = getenv("VR_SDF_GRID") ? std::max(atoi(getenv("VR_SDF_GRID")), 1) : 64;  // measured at 512^3: 8..12 3.9 ms, 16 3.53, 32 (a warp per tile, no loop) 3.43
+  // measured at 512^3 (grid multiplier): 8..12 3.9 ms, 16 3.53, 32 (a warp per tile, no loop) 3.43
+#ifdef VR_AB
+  static const int grid_mult = getenv("VR_SDF_GRID") ? std::max(atoi(getenv("VR_SDF_GRID")), 1) : 64;
   static const int cta_warps = getenv("VR_SDF_WARPS") ? std::min(std::max(atoi(getenv("VR_SDF_WARPS")), 1), 8) : 4;
+#else
+  const int grid_mult = 64, cta_warps = 4;
+#endif
   const unsigned wg5 = (unsigned)std::min<size_t>(div_up(s->ntiles, cta_warps), (size_t)ctx->sm_count * grid_mult * 4 / cta_warps);
   int n = 0;
   for (; n < nlevels && s->level + 1 < s->max_it; ++n, ++s->level) {
@@ -208,9 +218,11 @@ int vrk_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* done) {
                                                               (unsigned)s->nwords, s->stamps(it & 1), s->stamps((it + 1) & 1),   \
                                                               s->changed(), s->all_active ? 1 : 0)
     switch (s->tile_z) {
+#ifdef VR_AB
       case 2: VR_WAVE5(2); break;
       case 4: VR_WAVE5(4); break;
       case 16: VR_WAVE5(16); break;
+#endif
       default: VR_WAVE5(8); break;
     }
 #undef VR_WAVE5
@@ -273,16 +285,20 @@ int vrk_sdf_to_surface(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz,
   return VR_OK;
 }
 
+#ifdef VR_AB
 int vrk_sdf_build_variant(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field, int* levels_out,
-                          int* max_it_out);  // vr_sdf_variants.cu
+                          int* max_it_out);  // vr_sdf_variants.cu: the schedules tried on the way, linked into the A/B build only
+#endif
 
 int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field, int* levels_out,
                   int* max_it_out, cudaSurfaceObject_t surf) {
+#ifdef VR_AB
   static const char* mode = getenv("VR_SDF_MODE");
   if (mode && *mode && strcmp(mode, "default")) {
     VR_TRY(vrk_sdf_build_variant(ctx, vol, nx, ny, nz, tf, field, levels_out, max_it_out));
     return surf ? vrk_sdf_to_surface(ctx, field, nx, ny, nz, surf) : VR_OK;
   }
+#endif
   const int max_it = std::min(std::max(nx, std::max(ny, nz)) / 2, 127);  // signed_distance_field.cpp:11
   vr_sdf_slab* s = nullptr;
   VR_TRY(vrk_sdf_slab_create(ctx, vol, nx, ny, nz, tf, max_it, &s));

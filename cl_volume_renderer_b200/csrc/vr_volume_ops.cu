@@ -489,3 +489,42 @@ int vrk_cache_reset(vr_ctx* ctx, uint32_t* cache, size_t voxels, cudaStream_t st
   VR_CUDA(cudaGetLastError());
   return VR_OK;
 }
+
+// ---- position-weighted 64-bit checksum of a device buffer (instrumentation: multi-GPU results are compared at full size without
+// moving gigabytes to the host) ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_checksum(const uint32_t* __restrict__ words, size_t nwords, const uint8_t* __restrict__ tail,
+                                                  int ntail, unsigned long long* __restrict__ out) {
+  unsigned long long acc = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x)
+    acc += (unsigned long long)words[i] * (2ull * (i % 1000003ull) + 1ull);
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) acc += (unsigned long long)tail[threadIdx.x] * (977ull + threadIdx.x);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+int vrk_checksum(vr_ctx* ctx, const void* dev, size_t bytes, uint64_t* out) {
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(ctx->scratch) + 64;  // bytes 512.. of the 4 KiB scratch
+  VR_CUDA(cudaMemsetAsync(acc, 0, 8, ctx->stream));
+  const size_t nwords = bytes / 4;
+  const unsigned blocks = (unsigned)std::min<size_t>(std::max<size_t>(div_up(nwords, 256), 1), (size_t)ctx->sm_count * 8);
+  k_checksum<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(dev), nwords, reinterpret_cast<const uint8_t*>(dev) + nwords * 4,
+                                              (int)(bytes - nwords * 4), acc);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  unsigned long long* pin = reinterpret_cast<unsigned long long*>(ctx->scratch_host) + 64;
+  VR_CUDA(cudaMemcpyAsync(pin, acc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = *pin;
+  return VR_OK;
+}
+
+__global__ void __launch_bounds__(256) k_cache_gather(const uint2* __restrict__ cache, const uint32_t* __restrict__ idx, size_t n,
+                                                      uint2* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = cache[idx[i]];
+}
+int vrk_cache_gather(vr_ctx* ctx, const uint32_t* cache, const uint32_t* idx_dev, size_t n, uint2* out_dev) {
+  k_cache_gather<<<div_up(n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint2*>(cache), idx_dev, n, out_dev);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}

@@ -64,6 +64,8 @@ int vr_ctx_synchronize(vr_ctx* ctx);
 void* vr_ctx_stream(vr_ctx* ctx);
 /* number of kernels this context has launched so far */
 uint64_t vr_ctx_launch_count(const vr_ctx* ctx);
+/* number of 3-D CUDA arrays (SDF surfaces, hw-linear step fields) the context holds, in use or cached for reuse */
+int vr_ctx_array_count(const vr_ctx* ctx);
 
 /* ---- transfer function ---------------------------------------------------------------------------- */
 /* Strict parser for the two generated forms of `is_event_gen` (host only, needs no GPU).
@@ -81,6 +83,8 @@ int vr_volume_upload(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz,
  * until vr_volume_wait — or any other call that uses the volume, which waits implicitly — returns. */
 int vr_volume_upload_async(vr_ctx* ctx, const int16_t* voxels, int nx, int ny, int nz, vr_volume** out);
 int vr_volume_wait(vr_volume* vol);
+/* the same for voxels that already live in the context's device memory (decoded or generated there): device-to-device copy */
+int vr_volume_upload_device(vr_ctx* ctx, const int16_t* device_voxels, int nx, int ny, int nz, vr_volume** out);
 void vr_volume_destroy(vr_volume* vol);
 /* {min value, max value, min (int)|grad|, max (int)|grad|} over the ORIGINAL volume, unclamped
  * (reference_volume.cpp:33-37).  The clip getters (reference_volume.cpp:82-88) live in the C++ shim. */
@@ -99,6 +103,8 @@ int vr_volume_clip(vr_volume* vol, const uint32_t min[3], const uint32_t max[3])
 int vr_volume_filter(vr_volume* vol);
 /* current volume back to the host (parity tests) */
 int vr_volume_download(const vr_volume* vol, int16_t* out);
+/* device pointer of the current volume (x fastest, read-only for the caller; valid until the next clip / filter / destroy) */
+const int16_t* vr_volume_device_ptr(const vr_volume* vol);
 /* tf_sort_values, histogram.cl:4-32 as launched by renderer.cpp:57-61.
  * range = {min_v, max_v, min_g, max_g}; bins_out = width*height uint32, index x*height + y. */
 int vr_histogram(const vr_volume* vol, int width, int height, const float range[4], uint32_t* bins_out);
@@ -114,6 +120,10 @@ void vr_sdf_destroy(vr_sdf* sdf);
 int vr_sdf_download(const vr_sdf* sdf, int8_t* out);
 /* number of wavefront levels the build ran (diagnostics) */
 int vr_sdf_levels(const vr_sdf* sdf);
+/* position-weighted 64-bit checksums computed on the device: compare SDF fields / volumes at full size (multi-GPU runs at 1024^3)
+ * without moving them to the host */
+int vr_sdf_checksum(const vr_sdf* sdf, uint64_t* out);
+int vr_volume_checksum(const vr_volume* vol, uint64_t* out);
 
 /* ---- renderer : frame_emitter (app/ui.hpp:29-37, app/renderer.cpp) ---------------------------------- */
 /* renderer(ctx), renderer.cpp:8-17 — the reference fixes the frame at SCREEN_WIDTH x SCREEN_HEIGHT
@@ -146,6 +156,10 @@ int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba_out);
 uint8_t* vr_renderer_host_frame(vr_renderer* r);
 /* packed voxel cache, 4 ushort per voxel at (nx*nz*y + nx*z + x)*4 (utility.cl:21) — parity tests */
 int vr_cache_download(const vr_renderer* r, uint16_t* out);
+/* parity checks at sizes where the whole cache is gigabytes: the primary-hit voxel of every pixel as the last trace found it
+ * (W*H uint32, 0xFFFFFFFF = environment pixel), and the cache entries of n given voxels (4 ushort each) */
+int vr_renderer_hit_download(const vr_renderer* r, uint32_t* out);
+int vr_cache_download_at(const vr_renderer* r, const uint32_t* voxels, size_t n, uint16_t* out);
 /* the SDF the renderer built at the last flush (renderer.hpp:19) */
 const vr_sdf* vr_renderer_sdf(const vr_renderer* r);
 
@@ -156,8 +170,9 @@ const vr_sdf* vr_renderer_sdf(const vr_renderer* r);
  *   VR_SAMPLING_HW_LINEAR what NVIDIA hardware does with the kernels AS SHIPPED (measured through the driver's OpenCL runtime):
  *                         value and gradient taps of get_event_and_value and the environment colour are interpolated by the
  *                         texture unit (texel centres at +0.5, 8-bit weights, border 0 / clamp to edge) and rounded to
- *                         integers; integer-coordinate reads (the SDF read of march) stay texel reads.  One thread per pixel
- *                         and frame (the reference's own schedule); the SDF build is unaffected (samplerless reads).
+ *                         integers; integer-coordinate reads (the SDF read of march) stay texel reads.  All schedules; the
+ *                         flush also builds a step field that lets a step skip its seven fetches where the interpolated value
+ *                         cannot meet the transfer function (same results; vr_quiet.cu).  The SDF build is unaffected.
  * Takes effect at the next vr_renderer_flush (which copies the volume and the environment map into texture arrays). */
 enum { VR_SAMPLING_NEAREST = 0, VR_SAMPLING_HW_LINEAR = 1 };
 int vr_renderer_set_sampling(vr_renderer* r, int mode);
@@ -179,9 +194,10 @@ int vr_volume_set_sampling(vr_volume* vol, int mode);
  * The reference kernel works in place on a __read_write image (taps race with neighbouring writes); here every tap reads the
  * unfiltered frame.  sigma must be > 0. */
 enum { VR_FILTER2D_REFERENCE = 0, VR_FILTER2D_BILATERAL = 1 };
-/* filters the renderer's current device frame (the result of the last render_frame / resolve) and optionally reads it back;
- * the next render_frame overwrites it */
+/* filters the renderer's current device frame (the result of the last render_frame / resolve) into a second device buffer
+ * (vr_renderer_filtered_device_ptr) and optionally reads that back; the traced frame itself is left untouched */
 int vr_renderer_filter_frame(vr_renderer* r, int kernel_size, float sigma, int mode, uint8_t* host_rgba);
+void* vr_renderer_filtered_device_ptr(const vr_renderer* r);
 /* the same on a caller-supplied RGBA8 image, host to host (rgba_out may equal rgba_in) */
 int vr_image_filter(vr_ctx* ctx, const uint8_t* rgba_in, int w, int h, int kernel_size, float sigma, int mode,
                     uint8_t* rgba_out);
@@ -207,6 +223,46 @@ void* vr_renderer_xchg_device_ptr(vr_renderer* r);
 size_t vr_renderer_xchg_bytes(const vr_renderer* r);
 /* re-run only the resolve pass (after an external cache all-reduce) and optionally read the frame back */
 int vr_renderer_resolve(vr_renderer* r, uint8_t* host_rgba);
+
+/* ---- multi-GPU collectives behind the C-ABI (NCCL over NVLink, enqueued on the context's stream) --------
+ * One vr_ctx per GPU, one process or thread per vr_ctx.  Rank 0 creates an id (vr_comm_unique_id) and hands it to the other
+ * ranks by whatever means the host has (a file, a socket, MPI, a torch store); every rank then calls vr_comm_init.  Without a
+ * communicator (or with one rank) every call below degenerates to its single-GPU meaning. */
+#define VR_COMM_ID_BYTES 128
+int vr_comm_unique_id(uint8_t id[VR_COMM_ID_BYTES]);
+int vr_comm_init(vr_ctx* ctx, int rank, int nranks, const uint8_t id[VR_COMM_ID_BYTES]);
+void vr_comm_destroy(vr_ctx* ctx); /* also done by vr_ctx_destroy */
+int vr_comm_rank(const vr_ctx* ctx);
+int vr_comm_size(const vr_ctx* ctx);
+int vr_comm_barrier(vr_ctx* ctx);
+/* small host-side reductions for drivers (timings, checksums): dtype 0 int32 / 1 uint32 / 2 float64, op 0 sum / 1 min / 2 max */
+int vr_comm_allreduce_host(vr_ctx* ctx, void* values, int count, int dtype, int op);
+/* the z-partition every sharded call uses: planes [z0, z1) of rank `rank`, multiples of 8 planes (brick layers of the SDF) */
+int vr_comm_slab(const vr_ctx* ctx, int nz, int rank, int* z0, int* z1);
+/* spp split (BASELINE config 3): every rank has traced its own seeds of the SAME camera into its own cache with a token cap of
+ * 256/N (vr_renderer_set_token_cap).  Sums the touched cache entries over the ranks — one 8-byte entry per shaded pixel,
+ * numbered in pixel order, as uint32 words (no carries between the 16-bit lanes by construction) — writes the sums back into
+ * every rank's cache and resolves the frame from them (ray_marching.cl:82-99); host_rgba may be NULL.  When the ranks' caps add
+ * up to more than 256 (N ranks that each accumulate a full 64-spp job: weak scaling) the lanes travel as four uint32 words, the
+ * frame is resolved from those wide sums and the per-rank caches keep their partial sums. */
+int vr_cache_allreduce(vr_renderer* r, uint8_t* host_rgba);
+/* image-tile split (BASELINE config 4): rows are dealt out in blocks of block_rows, block b is traced by rank b % nranks;
+ * every rank keeps its own cache (visible voxels of its rows).  vr_frame_allgather completes the frame on every rank. */
+int vr_renderer_set_row_blocks(vr_renderer* r, int block_rows, int rank, int nranks);
+int vr_frame_allgather(vr_renderer* r, uint8_t* host_rgba);
+/* sharded ingest: rank r passes only ITS planes [z0, z1) of vr_comm_slab (nx*ny*(z1-z0) voxels, preferably pinned); the other
+ * planes arrive from the other ranks over NVLink instead of N copies of the whole volume over PCIe.  Result: the whole volume
+ * on every rank, as after vr_volume_upload. */
+int vr_volume_upload_sharded(vr_ctx* ctx, const int16_t* own_planes, int nx, int ny, int nz, vr_volume** out);
+/* z-slab SDF build (BASELINE config 5): every rank runs the wavefront on its slab + 16 halo planes, swaps the boundary planes
+ * of the bit volume with its z-neighbours every 14 levels and gathers the field; bit-identical to vr_sdf_build.  `vol` is the
+ * whole volume (replicated).  vr_renderer_set_sharded_build makes vr_renderer_flush build its SDF this way. */
+int vr_sdf_build_sharded(vr_ctx* ctx, const vr_volume* vol, const vr_tf_rect* rects, int n_rects, vr_sdf** out);
+int vr_renderer_set_sharded_build(vr_renderer* r, int enable);
+/* tf_sort_values / bilateral_filter over the rank's planes of the replicated volume + all-reduce of the bins / gather of the
+ * filtered planes: same results as vr_histogram / vr_volume_filter on every rank */
+int vr_histogram_sharded(const vr_volume* vol, int width, int height, const float range[4], uint32_t* bins_out);
+int vr_volume_filter_sharded(vr_volume* vol);
 
 /* ---- z-slab sharding (multi-GPU; no reference counterpart — SURVEY.md 8e).  A rank holds planes [z0-h, z1+h) of the volume:
  * vr_volume_upload_slab marks [z_lo, z_hi) (indices into the slab) as its own; stats and histogram count only those, the
@@ -252,6 +308,17 @@ int vr_renderer_set_primary_reuse(vr_renderer* r, int level);
  * the resolve kernel (out_ms[1]) and the number of frames measured since the last reset. */
 int vr_renderer_enable_timing(vr_renderer* r, int enable);
 int vr_renderer_kernel_times(vr_renderer* r, double out_ms[2], int* n_frames, int reset);
+/* Schedule tuning of the persistent-warp tracer; never changes a result.  Keys: "pixel_major" (items per pixel group, 0 =
+ * frame-major), "rule_a"/"rule_b" (leave the march region when marching*a < waiting*b), "lin_fast_a/b", "lin_slow_a/b" (the
+ * same for the two loops of the hw-linear path), "pt_ctas" (register budget; only in the A/B build, tools/ab). */
+int vr_renderer_set_tuning(vr_renderer* r, const char* key, int value);
+/* hw-linear step field: the quiet-octant byte of every voxel cell, x fastest (tests: equals the oracle's orc_quiet_cells) */
+int vr_renderer_quiet_download(const vr_renderer* r, uint8_t* out);
+/* Device RNG known answers (utility_sampling.cl:13-21,40-50): runs the device functions of the trace kernels on n items
+ * (seed, gid0, gid1, normal.xyz + roughness) and returns the three hashes `ra`, the components `(ra % 2048) - 1024`, and the
+ * sampled direction. */
+int vr_debug_rng_dump(vr_ctx* ctx, const int32_t* seeds, const uint32_t* gid_xy, const float* normal_rough, int n, int32_t* ra_out,
+                      int32_t* comp_out, float* dir_out);
 
 #ifdef __cplusplus
 }

@@ -214,6 +214,22 @@ def quiet_cells(vol, tf):
     return q
 
 
+def quiet_cells27(vol, tf):
+    """per voxel cell floor(p) (0..n inclusive): can a value interpolated anywhere in it meet a TF clause?  1 = no; covers the 3x3x3
+    texels around the cell (oracle.cpp orc_quiet_cells27) — the flags the CUDA path packs into its step field"""
+    vol = np.ascontiguousarray(vol, dtype=np.int16)
+    nz, ny, nx = vol.shape
+    arr, n = tf_rects(tf)
+    q = np.zeros((nz + 1, ny + 1, nx + 1), dtype=np.uint8)
+    lib().orc_quiet_cells27(_p(vol), nx, ny, nz, arr, n, _p(q))
+    return q
+
+
+def set_quiet_mode(mode):
+    """0: flags per hardware cell (quiet_cells), 1: flags per voxel cell (quiet_cells27)"""
+    lib().orc_set_quiet_mode(int(mode))
+
+
 def set_quiet_cells(q):
     """install (or, with None, remove) the flags: linear event tests then count how many could be skipped and verify none is an event"""
     lib().orc_set_quiet_cells(_p(q) if q is not None else None)

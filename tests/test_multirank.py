@@ -125,3 +125,87 @@ def test_tile_split_rows_stitch_to_full_frame(vr_ctx):
     same = (got == want).all(axis=-1).mean()
     assert same > 0.97  # only voxels straddling the seam receive samples from both blocks in the full render
     full.close(); e.close(); v.close()
+
+
+# ---- the collectives behind the C-ABI (vr_comm.cu), driven by a torchrun-free C++ host: tests/cpp/multi_gpu_driver.cpp ------------
+def _run_cpp_driver(tmp_path, nranks, n=64, Wd=160, Hd=120, nseeds=8, block_rows=8):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    drv = os.path.join(root, "tests", "cpp", "multi_gpu_driver")
+    assert os.path.exists(drv), "build the driver: make host"
+    vol = synth.synth_ct(n)
+    env = synth.synth_env(128, 64)
+    pos, d = synth.default_camera(n)
+    seeds = synth.glibc_rand(nseeds)
+    vol.tofile(tmp_path / "vol.raw"); env.tofile(tmp_path / "env.raw")
+    np.array(seeds, dtype=np.int32).tofile(tmp_path / "seeds.bin")
+    np.asarray(d, dtype=np.float32).tofile(tmp_path / "dir.bin")
+    out = subprocess.run([drv, str(tmp_path / "vol.raw"), str(n), str(n), str(n), str(tmp_path / "env.raw"), "128", "64", str(Wd), str(Hd),
+                          str(tmp_path / "seeds.bin"), str(nseeds), str(nranks), str(block_rows), str(tmp_path)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "EVERYTHING FINE" in out.stdout, out.stderr + out.stdout
+    return vol, env, pos, d, seeds, out.stdout
+
+
+def _check_cpp_driver_outputs(tmp_path, vol, env, pos, d, seeds, stdout, n=64, Wd=160, Hd=120):
+    tf = synth.default_tf()
+    # sharded ingest: the gathered volume is the volume
+    assert np.array_equal(np.fromfile(tmp_path / "volume_gathered.bin", dtype=np.int16).reshape(vol.shape), vol)
+    # z-slab SDF build inside the flush: bit-identical to the oracle
+    ref = o.Renderer(vol, env, tf, Wd, Hd)
+    assert np.array_equal(np.fromfile(tmp_path / "sdf.bin", dtype=np.int8).reshape(vol.shape), ref.sdf)
+    # spp split: per-rank caps are not reached here, so the summed cache is the sequential cache (integer sums commute)
+    for s in seeds:
+        want = ref.render_frame(pos, d, s)
+    gc = np.fromfile(tmp_path / "cache_spp.bin", dtype=np.uint16).astype(np.int32)
+    wc = ref.cache.astype(np.int32)
+    assert np.array_equal(gc.reshape(-1, 4)[:, 3], wc.reshape(-1, 4)[:, 3])
+    assert (gc == wc).mean() >= 0.999
+    got = np.fromfile(tmp_path / "frame_spp.bin", dtype=np.uint8).reshape(Hd, Wd, 4)
+    assert np.array_equal(got[..., 3], want[..., 3])
+    mse = np.mean((got[..., :3].astype(np.float64) - want[..., :3].astype(np.float64)) ** 2)
+    assert mse == 0 or 10 * np.log10(255.0 ** 2 / mse) >= 45.0
+    # tile split: every rank keeps its own cache, so only voxels seen from rows of two ranks differ from the single render
+    tiles = np.fromfile(tmp_path / "frame_tiles.bin", dtype=np.uint8).reshape(Hd, Wd, 4)
+    assert np.array_equal(tiles[..., 3], want[..., 3])
+    assert (tiles == want).all(axis=-1).mean() > 0.9
+    # z-slab histogram and bilateral filter
+    st = o.fetch_stats(vol)
+    assert f"stats {st[0]} {st[1]} {st[2]} {st[3]}" in stdout
+    rng = [float(x) for x in st]
+    assert np.array_equal(np.fromfile(tmp_path / "bins.bin", dtype=np.uint32), o.histogram(vol, 100, 80, rng))
+    filt = np.fromfile(tmp_path / "filtered.bin", dtype=np.int16).reshape(vol.shape)
+    dd = np.abs(filt.astype(np.int32) - o.bilateral(vol).astype(np.int32))
+    assert dd.max() <= 1 and (dd == 0).mean() >= 0.99
+    assert np.array_equal(np.fromfile(tmp_path / "sdf_thr_filtered.bin", dtype=np.int8).reshape(vol.shape),
+                          o.sdf_build(filt, o.tf_threshold(800))[0])
+
+
+@pytest.mark.gpu
+def test_cpp_host_collectives_one_rank(tmp_path):
+    """every multi-GPU entry point with a one-rank communicator (the driver's GPU box has one GPU): same results as the plain calls"""
+    args = _run_cpp_driver(tmp_path, 1)
+    _check_cpp_driver_outputs(tmp_path, *args)
+
+
+@pytest.mark.gpu
+def test_cpp_host_collectives_two_ranks(tmp_path):
+    """the same on two GPUs: sharded ingest, z-slab SDF with halo swaps, spp split with the compact cache all-reduce, tile split
+    with the frame all-gather, z-slab histogram / filter — C++ threads + NCCL behind the C-ABI, no torch"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    args = _run_cpp_driver(tmp_path, 2)
+    _check_cpp_driver_outputs(tmp_path, *args)
+
+
+@pytest.mark.gpu
+def test_cpp_host_collectives_all_gpus(tmp_path):
+    import torch
+    nranks = torch.cuda.device_count()
+    if nranks < 4:
+        pytest.skip("needs four or more GPUs")
+    nranks = 4 if nranks < 8 else 8
+    n = 128 if nranks == 8 else 64     # z-slabs of 16 planes: the thinnest the halo allows
+    args = _run_cpp_driver(tmp_path, nranks, n=n)
+    _check_cpp_driver_outputs(tmp_path, *args, n=n)

@@ -316,11 +316,14 @@ def test_render_far_face_positions(vr_ctx, mode):
 
 @pytest.mark.parametrize("mode", ["front_overflow", "front", "reg", "wave1", "wave2", "wave3", "wave4", "warp"])
 def test_sdf_alternative_builds_bit_exact(mode):
-    """The SDF build has one default path (frontier lists) and fallbacks / A-B variants selected by VR_SDF_MODE; a frontier
-    list that overflows restarts with the dense per-level kernel.  All must reproduce the reference's golden vector and
-    the oracle on a synthetic volume (own process: the mode is read once per process)."""
+    """The schedules of the SDF build that were tried on the way live in the A/B build of the library (tools/ab/libvr_ab.so, `make ab`;
+    selected with VR_SDF_MODE; a frontier list that overflows restarts with the dense per-level kernel).  All must reproduce the
+    reference's golden vector and the oracle on a synthetic volume (own process: the mode is read once per process)."""
     import subprocess, sys, os
     env = dict(os.environ)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env["VR_LIB"] = os.path.join(root, "tools", "ab", "libvr_ab.so")
+    assert os.path.exists(env["VR_LIB"]), "build the A/B library: make ab"
     if mode == "front_overflow":
         env["VR_SDF_MODE"] = "front"
         env["VR_SDF_FRONT_CAP"] = "64"
@@ -538,7 +541,7 @@ def test_sampling_mode_switch_and_texture_lifecycle(vr_ctx):
 
 
 @pytest.mark.parametrize("n,W,H,frames,cam", [(64, 160, 120, 4, "default"), (96, 200, 136, 2, "closeup")])
-def test_hw_linear_sampling_matches_oracle_model(vr_ctx, n, W, H, frames, cam):
+def test_hw_linear_sampling_matches_oracle_model(vr_ctx, both, n, W, H, frames, cam):
     """VR_SAMPLING_HW_LINEAR (texture unit) against the oracle's model of that filter (oracle.cpp hw_linear_fetch, pinned bit-exactly
     against 874 545 samples of NVIDIA's OpenCL runtime, tests/test_ref_pinning_cpu.py).  The volume reads decide which voxels are hit
     and which samples are admitted: those must be identical.  The bilinear environment lookup of the oracle models the scaling of
@@ -556,11 +559,15 @@ def test_hw_linear_sampling_matches_oracle_model(vr_ctx, n, W, H, frames, cam):
     vol, env = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
     r = api.Renderer(vr_ctx, W, H)
     r.set_sampling(api.VR_SAMPLING_HW_LINEAR)
+    r.set_trace_mode(TRACE_MODE[0])
     r.image_set(vol, env)
     r.set_tf(tf)
     r.flush_changes()
+    r.enable_counters(True)
     for s in seeds:
         got = r.render_frame(pos, d, s)
+    c = r.counters()
+    assert [c[k] for k in ("steps", "normals", "env", "primary_hits", "admitted", "samples")] == [int(x) for x in ref.counters]
     a = r.cache_download().astype(np.int32).reshape(-1, 4)
     b = ref.cache.astype(np.int32).reshape(-1, 4)
     assert np.array_equal(a[:, 3], b[:, 3])                      # tokens: same hits, same admissions
@@ -592,3 +599,186 @@ def test_volume_kernels_hw_linear_match_oracle_model(vr_ctx):
     vol.set_sampling(api.VR_SAMPLING_NEAREST)   # back: the NEAREST stats of the (now filtered) volume
     assert vol.stats() == o.fetch_stats(got)
     vol.close()
+
+
+def test_hw_linear_quiet_field_equals_oracle_analysis(vr_ctx):
+    """The step field of the hw-linear path (vr_quiet.cu): bit (ux + 2 uy + 4 uz) of voxel cell (x, y, z) must be the oracle's verdict
+    for the hardware cell (x-1+ux, y-1+uy, z-1+uz) — orc_quiet_cells stores cell c at index c+1 — for three transfer functions."""
+    v = synth.synth_ct(0, dims=(45, 37, 29))
+    envimg = synth.synth_env(64, 32)
+    tf2 = [{"min_v": 900.0, "max_v": 1200.0, "min_g": 0.0, "max_g": 0.0, "flags": 0, "rgba": (255, 64, 32, 128)},
+           {"min_v": 500.0, "max_v": 1500.0, "min_g": 100.0, "max_g": 2000.0, "flags": 1, "rgba": (40, 200, 255, 255)}]
+    vol, env = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
+    r = api.Renderer(vr_ctx, 64, 48)
+    r.set_sampling(api.VR_SAMPLING_HW_LINEAR)
+    r.image_set(vol, env)
+    nz, ny, nx = v.shape
+    for tf in (synth.default_tf(), tf2, synth.threshold_tf(800)):
+        r.set_tf(tf)
+        r.flush_changes()
+        got = r.quiet_download()
+        q = o.quiet_cells(v, tf)  # [nz+1, ny+1, nx+1]
+        want = np.zeros_like(got)
+        for oct_ in range(8):
+            ux, uy, uz = oct_ & 1, (oct_ >> 1) & 1, oct_ >> 2
+            want |= (q[uz:uz + nz, uy:uy + ny, ux:ux + nx] << oct_).astype(np.uint8)
+        assert np.array_equal(got, want)
+        assert 0.2 < (got == 255).mean() < 1.0
+    r.close(); env.close(); vol.close()
+
+
+def test_hw_linear_batch_thresholds_and_gradient_clauses(vr_ctx, both):
+    """hw-linear path: a 16-frame batch (primary reuse inside one call), a TF with a gradient clause and a colourless threshold
+    TF — tokens, hit / miss classification and the per-sample counters equal the oracle's model; colour lanes within one count."""
+    n, W, H = 64, 128, 96
+    v, envimg = synth.synth_ct(n), synth.synth_env(128, 64)
+    tf2 = [{"min_v": 900.0, "max_v": 1200.0, "min_g": 0.0, "max_g": 0.0, "flags": 0, "rgba": (255, 64, 32, 128)},
+           {"min_v": 500.0, "max_v": 1500.0, "min_g": 100.0, "max_g": 2000.0, "flags": 1, "rgba": (40, 200, 255, 255)}]
+    vol, env = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
+    r = api.Renderer(vr_ctx, W, H)
+    r.set_sampling(api.VR_SAMPLING_HW_LINEAR)
+    r.set_trace_mode(TRACE_MODE[0])
+    r.image_set(vol, env)
+    for tf, cam, frames in ((tf2, synth.closeup_camera(n), 16), (synth.threshold_tf(800), synth.default_camera(n), 3)):
+        seeds = synth.glibc_rand(frames)
+        o.set_sampling(1)
+        try:
+            ref = o.Renderer(v, envimg, tf, W, H)
+            for s in seeds:
+                want = ref.render_frame(cam[0], cam[1], s)
+        finally:
+            o.set_sampling(0)
+        r.set_tf(tf)
+        r.flush_changes()
+        r.enable_counters(True)
+        r.counters(reset=True)
+        got = r.render_frames(cam[0], cam[1], seeds)
+        c = r.counters(reset=True)
+        r.enable_counters(False)
+        assert [c[k] for k in ("steps", "normals", "env", "primary_hits", "admitted", "samples")] == [int(x) for x in ref.counters]
+        a = r.cache_download().astype(np.int32).reshape(-1, 4)
+        b = ref.cache.astype(np.int32).reshape(-1, 4)
+        assert np.array_equal(a[:, 3], b[:, 3])
+        assert np.array_equal(got[..., 3], want[..., 3])
+        diff = np.abs(a[:, :3] - b[:, :3])
+        assert (diff <= np.maximum(b[:, 3:4], 1)).all()
+        touched = b[:, 3] > 0
+        assert not touched.any() or (diff[touched] == 0).mean() >= 0.99
+    r.close(); env.close(); vol.close()
+
+
+# ---- RNG (row a9): the device functions of the trace kernels, known answers ------------------------------------------------------
+def test_device_rng_known_answers(vr_ctx):
+    """utility_sampling.cl:13-21,40-50 on the DEVICE: the integer triples (ra_x, ra_y, ra_z) and components over a (seed, gid) grid
+    equal SURVEY A.4's known answers and the oracle bit for bit; the sampled directions equal the oracle's (same fp32 operation
+    order, no FMA, one shared reciprocal that is checked to give the correctly rounded quotients)."""
+    s0 = 1804289383
+    seeds, gids = [s0 + 1, s0 + 1], [(0, 0), (959, 539)]
+    rng = np.random.default_rng(5)
+    for s in synth.glibc_rand(6) + [0, -1, 2 ** 31 - 1, -2 ** 31]:
+        for o_ in (1, 2, 9, 12):
+            for g in [(0, 0), (1919, 1079), (3839, 2159), (7, 5), (5, 7)] + [tuple(int(x) for x in rng.integers(0, 4096, 2)) for _ in range(40)]:
+                seeds.append(int(np.int32(np.uint32((s + o_) & 0xFFFFFFFF))))
+                gids.append(g)
+    n = len(seeds)
+    nr = np.zeros((n, 4), np.float32)
+    nrm = rng.normal(size=(n, 3)).astype(np.float32)
+    nr[:, :3] = nrm / np.linalg.norm(nrm, axis=1, keepdims=True).astype(np.float32)
+    nr[:, 3] = rng.choice(np.array([1.0, 0.5, 128.0 / 255.0, 0.0, 76.0 / 255.0], np.float32), n)
+    ra, comp, dirs = vr_ctx.rng_dump(seeds, gids, nr)
+    # SURVEY.md A.4 known answers
+    assert ra[0].tolist() == [1742764452, 1176753706, 884373136] and comp[0].tolist() == [-604, 554, 656]
+    assert ra[1].tolist() == [1954444043, -1525972536, -2110478077] and comp[1].tolist() == [-245, -2616, -2813]
+    for i in range(n):
+        wra, wcomp = o.rng_triple(seeds[i], gids[i][0], gids[i][1])
+        assert ra[i].tolist() == list(wra) and comp[i].tolist() == list(wcomp)
+        want = o.hemisphere(nr[i, :3], seeds[i], float(nr[i, 3]), gids[i][0], gids[i][1])
+        assert np.array_equal(dirs[i].view(np.uint32), np.asarray(want, np.float32).view(np.uint32)), (i, dirs[i], want)
+    assert comp.min() >= -3071 and comp.max() <= 1023
+
+
+# ---- API state checks (ADVICE round 1) ------------------------------------------------------------------------------------------
+def test_filter_frame_leaves_the_traced_frame_alone_with_primary_reuse(vr_ctx):
+    """vr_renderer_filter_frame writes to its own buffer: with primary reuse across calls the environment pixels are written once
+    per camera, so filtering in place would leave a blurred background in every later frame."""
+    n, W, H = 48, 96, 64
+    v, envimg, tf = synth.synth_ct(n), synth.synth_env(128, 64), synth.default_tf()
+    vol, env = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
+    r = api.Renderer(vr_ctx, W, H)
+    r.image_set(vol, env); r.set_tf(tf); r.set_primary_reuse(2); r.flush_changes()
+    pos, d = synth.default_camera(n)
+    seeds = synth.glibc_rand(3)
+    f0 = r.render_frame(pos, d, seeds[0])
+    filt = r.filter_frame(3, 2.0, api.VR_FILTER2D_BILATERAL)
+    assert not np.array_equal(filt, f0)
+    f1 = r.render_frame(pos, d, seeds[1])          # same camera: k_primary is skipped, env pixels are NOT rewritten
+    bg = f0[..., 3] == 200
+    assert bg.any() and np.array_equal(f1[bg], f0[bg])
+    ref = o.Renderer(v, envimg, tf, W, H)
+    for s in seeds[:2]:
+        want = ref.render_frame(pos, d, s)
+    assert np.array_equal(f1[..., 3], want[..., 3]) and _psnr(f1[..., :3], want[..., :3]) >= 45.0
+    r.close(); env.close(); vol.close()
+
+
+def test_trace_after_clip_or_filter_requires_a_flush(vr_ctx):
+    """SDF, cache and hit buffer belong to the flushed scene: after vr_volume_clip / vr_volume_filter / set_scene the renderer
+    refuses to trace or resolve until it is flushed (the reference always flushes after set_clipping, ui.cpp:273-278)."""
+    n, W, H = 48, 64, 48
+    v, envimg, tf = synth.synth_ct(n), synth.synth_env(64, 32), synth.default_tf()
+    vol, env = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
+    r = api.Renderer(vr_ctx, W, H)
+    r.image_set(vol, env); r.set_tf(tf); r.flush_changes()
+    pos, d = synth.default_camera(n)
+    r.render_frame(pos, d, 1)
+    vol.clip((0, 0, 0), (40, 48, 48))
+    for call in (lambda: r.render_frame(pos, d, 2), lambda: r.render_frames(pos, d, [3, 4]), lambda: r.resolve(), lambda: r.xchg_gather()):
+        with pytest.raises(api.VrError, match="flush required"):
+            call()
+    r.flush_changes()
+    r.render_frame(pos, d, 2)
+    vol.filter()
+    with pytest.raises(api.VrError, match="flush required"):
+        r.render_frame(pos, d, 3)
+    r.flush_changes()
+    got = r.render_frame(pos, d, 3)
+    ref = o.Renderer(vol.download(), envimg, tf, W, H)
+    want = ref.render_frame(pos, d, 3)
+    assert np.array_equal(got[..., 3], want[..., 3])
+    vol2 = api.Volume(vr_ctx, v)
+    r.image_set(vol2, env)
+    with pytest.raises(api.VrError, match="flush required"):
+        r.render_frame(pos, d, 4)
+    r.close(); env.close(); vol.close(); vol2.close()
+
+
+def test_tf_colours_outside_0_255_are_rejected(vr_ctx):
+    v, envimg = synth.synth_ct(32), synth.synth_env(64, 32)
+    vol, env = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
+    r = api.Renderer(vr_ctx, 32, 32)
+    for bad in ((256, 0, 0, 0), (0, -1, 0, 0), (0, 0, 0, 1000)):
+        tf = [{"min_v": 500.0, "max_v": 1200.0, "min_g": 0.0, "max_g": 0.0, "flags": 0, "rgba": bad}]
+        with pytest.raises(api.VrError, match="outside"):
+            r.set_tf(tf)
+        with pytest.raises(api.VrError, match="outside"):
+            api.Sdf(vr_ctx, vol, tf)
+    r.close(); env.close(); vol.close()
+
+
+def test_array_cache_stays_bounded_over_many_clip_boxes(vr_ctx):
+    """the context recycles the SDF's 3-D arrays by size and keeps at most two unused ones"""
+    v, envimg, tf = synth.synth_ct(48), synth.synth_env(64, 32), synth.default_tf()
+    vol, env = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
+    r = api.Renderer(vr_ctx, 32, 32)
+    r.image_set(vol, env); r.set_tf(tf)
+    base = vr_ctx.array_count
+    for k in range(12):
+        vol.clip((0, 0, 0), (24 + 2 * k, 40, 40))
+        r.flush_changes()
+        assert vr_ctx.array_count <= base + 3   # the renderer's current SDF + at most two cached
+    r.set_sampling(api.VR_SAMPLING_HW_LINEAR)
+    for k in range(6):
+        vol.clip((0, 0, 0), (24 + 2 * k, 40, 40))
+        r.flush_changes()
+        assert vr_ctx.array_count <= base + 4   # + the 16-bit step field
+    r.close(); env.close(); vol.close()
