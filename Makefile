@@ -6,7 +6,7 @@ CSRC := $(PKG)/csrc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 # --fmad=false: the numeric contract — no contraction, so ray positions match the oracle bit for bit
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo --fmad=false -Xcompiler -fPIC -ccbin $(CXX) -Xptxas -v
-CU_SRCS := $(CSRC)/vr_api.cu $(CSRC)/vr_volume_ops.cu $(CSRC)/vr_sdf.cu $(CSRC)/vr_render.cu $(CSRC)/vr_frame_filter.cu $(CSRC)/vr_volume_ops_linear.cu $(CSRC)/vr_quiet.cu $(CSRC)/vr_comm.cu
+CU_SRCS := $(CSRC)/vr_api.cu $(CSRC)/vr_volume_ops.cu $(CSRC)/vr_sdf.cu $(CSRC)/vr_render.cu $(CSRC)/vr_frame_filter.cu $(CSRC)/vr_quiet.cu $(CSRC)/vr_comm.cu
 CU_OBJS := $(CU_SRCS:.cu=.o)
 # A/B build (tools/ab/libvr_ab.so): the same sources with -DVR_AB — the SDF schedules tried on the way (tools/ab/vr_sdf_variants.cu,
 # VR_SDF_MODE), the tile / grid knobs of the wave, the register-budget variants of k_trace_pt.  Not part of the product library.

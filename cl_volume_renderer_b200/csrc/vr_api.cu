@@ -270,45 +270,21 @@ extern "C" int vr_volume_upload_async(vr_ctx* ctx, const int16_t* voxels, int nx
   return VR_OK;
 }
 
-// VR_SAMPLING_HW_LINEAR for the volume kernels: the current volume in a CUDA array behind two texture objects
+// VR_SAMPLING_HW_LINEAR for the volume kernels: the box-averaged copy of the current volume (vr_volume_ops.cu k_boxavg)
 static void volume_release_textures(vr_volume* v) {
-  if (!v->arr && !v->tex_border && !v->tex_edge) return;
-  cudaStreamSynchronize(v->ctx->stream);
-  if (v->tex_border) cudaDestroyTextureObject(v->tex_border);
-  if (v->tex_edge) cudaDestroyTextureObject(v->tex_edge);
-  if (v->arr) cudaFreeArray(v->arr);
-  v->tex_border = v->tex_edge = 0;
-  v->arr = nullptr;
+  if (!v->box) return;
+  pool_free(v->ctx, v->box);
+  v->box = nullptr; v->box_px = 0;
 }
 static int volume_build_textures(vr_volume* v) {
   volume_release_textures(v);
-  cudaChannelFormatDesc d16 = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindSigned);
-  cudaError_t e = cudaMalloc3DArray(&v->arr, &d16, make_cudaExtent(v->nx, v->ny, v->nz));
-  if (e == cudaSuccess) {
-    cudaMemcpy3DParms p{};
-    p.srcPtr = make_cudaPitchedPtr(const_cast<int16_t*>(v->current()), (size_t)v->nx * sizeof(int16_t), v->nx, v->ny);
-    p.dstArray = v->arr;
-    p.extent = make_cudaExtent(v->nx, v->ny, v->nz);
-    p.kind = cudaMemcpyDeviceToDevice;
-    e = cudaMemcpy3DAsync(&p, v->ctx->stream);
-  }
-  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-    cudaResourceDesc rd{};
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = v->arr;
-    cudaTextureDesc td{};
-    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = k == 0 ? cudaAddressModeBorder : cudaAddressModeClamp;
-    td.filterMode = cudaFilterModeLinear;
-    td.readMode = cudaReadModeNormalizedFloat;
-    td.normalizedCoords = 0;
-    e = cudaCreateTextureObject(k == 0 ? &v->tex_border : &v->tex_edge, &rd, &td, nullptr);
-  }
-  if (e != cudaSuccess) {
-    vr_set_error("volume textures for hw-linear sampling: %s", cudaGetErrorString(e));
-    volume_release_textures(v);
-    return VR_ERR_CUDA;
-  }
-  return VR_OK;
+  v->box_px = (v->nx + 1 + 7) / 8 * 8;
+  const size_t n = (size_t)v->box_px * (v->ny + 1) * (v->nz + 1);
+  VR_REQUIRE(n < ((size_t)1 << 32) - 1, "hw-linear sampling: the box-averaged volume would exceed 2^32-2 voxels");
+  VR_CUDA(pool_alloc(v->ctx, &v->box, n * sizeof(int16_t)));
+  int st = vrk_boxavg(v->ctx, v->current(), v->nx, v->ny, v->nz, v->box, v->box_px);
+  if (st != VR_OK) volume_release_textures(v);
+  return st;
 }
 
 extern "C" int vr_volume_set_sampling(vr_volume* v, int mode) {
@@ -318,7 +294,7 @@ extern "C" int vr_volume_set_sampling(vr_volume* v, int mode) {
   VR_CUDA(cudaSetDevice(v->ctx->device));
   if (mode == VR_SAMPLING_HW_LINEAR) {
     VR_TRY(volume_build_textures(v));
-    int st = vrk_fetch_stats_linear(v->ctx, v->tex_border, v->tex_edge, v->nx, v->ny, v->nz, v->stats, v->zlo, v->zhi);
+    int st = vrk_fetch_stats_linear(v->ctx, v->box, v->box_px, v->current(), v->nx, v->ny, v->nz, v->stats, v->zlo, v->zhi);
     if (st != VR_OK) { volume_release_textures(v); return st; }
   } else {
     volume_release_textures(v);
@@ -403,7 +379,7 @@ extern "C" int vr_volume_filter(vr_volume* v) {
   VR_CUDA(cudaSetDevice(v->ctx->device));
   int16_t* dst = nullptr;
   VR_CUDA(pool_alloc(v->ctx, &dst, v->count() * sizeof(int16_t)));
-  int s = v->sampling == VR_SAMPLING_HW_LINEAR ? vrk_bilateral_linear(v->ctx, v->tex_border, v->nx, v->ny, v->nz, dst)
+  int s = v->sampling == VR_SAMPLING_HW_LINEAR ? vrk_bilateral_linear(v->ctx, v->box, v->box_px, v->nx, v->ny, v->nz, dst)
                                                : vrk_bilateral(v->ctx, v->current(), dst, v->nx, v->ny, v->nz);
   if (s != VR_OK) { pool_free(v->ctx, dst); return s; }
   VR_CUDA(cudaStreamSynchronize(v->ctx->stream));
@@ -433,7 +409,8 @@ extern "C" int vr_histogram(const vr_volume* v, int width, int height, const flo
   const size_t bytes = sizeof(uint32_t) * (size_t)width * height;
   VR_CUDA(pool_alloc(v->ctx, &bins, bytes));
   int s = v->sampling == VR_SAMPLING_HW_LINEAR
-              ? vrk_histogram_linear(v->ctx, v->tex_border, v->tex_edge, v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi)
+              ? vrk_histogram_linear(v->ctx, v->box, v->box_px, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi,
+                                     v->stats[0])
               : vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi, v->stats[0]);
   if (s == VR_OK) {
     cudaError_t e = cudaMemcpyAsync(bins_out, bins, bytes, cudaMemcpyDeviceToHost, v->ctx->stream);
@@ -1112,8 +1089,8 @@ extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba
   if (e != cudaSuccess) { vr_set_error("vr_render_tf: %s", cudaGetErrorString(e)); status = VR_ERR_CUDA; }
   if (status == VR_OK)
     status = r->vol->sampling == VR_SAMPLING_HW_LINEAR
-                 ? vrk_histogram_linear(ctx, r->vol->tex_border, r->vol->tex_edge, r->vol->nx, r->vol->ny, r->vol->nz, width, height, range,
-                                        bins, r->vol->zlo, r->vol->zhi)
+                 ? vrk_histogram_linear(ctx, r->vol->box, r->vol->box_px, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height,
+                                        range, bins, r->vol->zlo, r->vol->zhi, r->vol->stats[0])
                  : vrk_histogram(ctx, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height, range, bins, r->vol->zlo,
                                  r->vol->zhi, r->vol->stats[0]);
   // renderer.cpp:65-96 without the host round trip: rounding, distinct-value ranking and colouring stay on the device

@@ -78,11 +78,11 @@ struct vr_volume {
   int32_t* stats_dev = nullptr;
   int32_t* stats_pin = nullptr;
   int zlo = 0, zhi = 0;  // planes the stats / histogram cover (whole volume unless uploaded as a z-slab with halo planes)
-  // vr_volume_set_sampling(VR_SAMPLING_HW_LINEAR): a copy of the current volume in a CUDA array behind two texture objects (border
-  // colour 0 / clamp to edge), rebuilt whenever the current volume changes (clip, filter)
+  // vr_volume_set_sampling(VR_SAMPLING_HW_LINEAR): the box-averaged volume (vr_volume_ops.cu k_boxavg: what the hardware's linear
+  // filter returns at integer coordinates), box_px x (ny+1) x (nz+1), rebuilt whenever the current volume changes (clip, filter)
   int sampling = VR_SAMPLING_NEAREST;
-  cudaArray_t arr = nullptr;
-  cudaTextureObject_t tex_border = 0, tex_edge = 0;
+  int16_t* box = nullptr;
+  int box_px = 0;
   // bumped whenever the current volume changes (clip, filter): a renderer whose SDF / cache / textures were built from an older
   // generation refuses to trace until it is flushed again (the reference always flushes after set_clipping, ui.cpp:273-278)
   uint64_t generation = 1;
@@ -231,12 +231,13 @@ int vrk_lin_field_masks(vr_ctx* ctx, cudaSurfaceObject_t field, int nx, int ny, 
 // device RNG known-answer dump (tests): hemisphere integer triples and directions over a (seed, gid) grid (vr_render.cu)
 int vrk_rng_dump(vr_ctx* ctx, const int32_t* seeds_dev, const uint32_t* gid_dev, int n, const float* normal_rough_dev, int32_t* ra_dev,
                  int32_t* comp_dev, float* dir_dev);
-// the volume kernels under VR_SAMPLING_HW_LINEAR (vr_volume_ops_linear.cu)
-int vrk_fetch_stats_linear(vr_ctx* ctx, cudaTextureObject_t border, cudaTextureObject_t edge, int nx, int ny, int nz, int32_t out[4],
-                           int zlo, int zhi);
-int vrk_histogram_linear(vr_ctx* ctx, cudaTextureObject_t border, cudaTextureObject_t edge, int nx, int ny, int nz, int width, int height,
-                         const float range[4], uint32_t* bins_dev, int zlo, int zhi);
-int vrk_bilateral_linear(vr_ctx* ctx, cudaTextureObject_t border, int nx, int ny, int nz, int16_t* dst);
+// the volume kernels under VR_SAMPLING_HW_LINEAR: box = the box-averaged volume, px its padded row length (vr_volume_ops.cu)
+int vrk_boxavg(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int16_t* out, int px);
+int vrk_fetch_stats_linear(vr_ctx* ctx, const int16_t* box, int px, const int16_t* vol, int nx, int ny, int nz, int32_t out[4], int zlo,
+                           int zhi);
+int vrk_histogram_linear(vr_ctx* ctx, const int16_t* box, int px, const int16_t* vol, int nx, int ny, int nz, int width, int height,
+                         const float range[4], uint32_t* bins_dev, int zlo, int zhi, int vol_min_value);
+int vrk_bilateral_linear(vr_ctx* ctx, const int16_t* box, int px, int nx, int ny, int nz, int16_t* dst);
 // 2d_image_filter.cl: src != dst, both w*h RGBA8 on the device
 int vrk_filter2d(vr_ctx* ctx, const uchar4* src, uchar4* dst, int w, int h, int kernel_size, float sigma, int mode);
 TfTable vr_make_tf_table(const vr_tf_rect* rects, int n);

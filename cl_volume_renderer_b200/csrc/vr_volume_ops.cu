@@ -93,22 +93,71 @@ __device__ __forceinline__ float grad_sq(const Octet& o, int k) {
 #define VX 16  // threads along x (128 voxels)
 #define VY 8
 #define VZ 2
+
+// ---- VR_SAMPLING_HW_LINEAR for the volume kernels: the box-averaged volume ----------------------------------------------------------
+// fetch_stats, tf_sort_values and bilateral_filter read the volume through CLK_FILTER_LINEAR samplers at INTEGER coordinates
+// (reference_volume_figures.cl:14-23, histogram.cl:10-15, utility_filter.cl:38-62).  With texel centres at +0.5 an integer
+// coordinate lies exactly between two texels on every axis: the hardware's fixed-point fractions are 128/256 and its eight
+// weights come out as 32/256 each (oracle.cpp hw_linear_fetch: U = 64 four times, then 32 + 32), so the filtered value is
+//     B(x,y,z) = floor( (sum of the 2x2x2 texels (x-1..x, y-1..y, z-1..z)) / 8 + 1/2 ) = (S + 4) >> 3
+// — no texture unit needed.  k_boxavg writes B with the border addressing of gradient_prewitt_nn / bilateral_kernel (texels
+// outside read 0) for coordinates 0..n inclusive, rows padded to a multiple of 8 with zeros: a volume of (pad8(nx+1), ny+1,
+// nz+1) voxels whose out-of-range reads are 0 is exactly B everywhere, so the vectorised kernels below run on it unchanged.
+// The VALUE read of fetch_stats / tf_sort_values uses a sampler without an addressing mode, served like clamp-to-edge: it
+// differs from B only on the faces x == 0, y == 0, z == 0, where it is recomputed from the volume (box_edge).
+__device__ __forceinline__ int box_border(const VolView& v, int x, int y, int z) {
+  int s = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s += v.at(x - 1 + (c & 1), y - 1 + ((c >> 1) & 1), z - 1 + (c >> 2));
+  return (s + 4) >> 3;
+}
+__device__ __forceinline__ int box_edge(const VolView& v, int x, int y, int z) {
+  int s = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    s += v.at(min(max(x - 1 + (c & 1), 0), v.nx - 1), min(max(y - 1 + ((c >> 1) & 1), 0), v.ny - 1), min(max(z - 1 + (c >> 2), 0), v.nz - 1));
+  return (s + 4) >> 3;
+}
+__global__ void __launch_bounds__(256) k_boxavg(VolView v, int16_t* __restrict__ out, int px) {
+  const size_t n = (size_t)px * (v.ny + 1) * (v.nz + 1);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % px);
+    const size_t t = i / px;
+    const int y = (int)(t % (v.ny + 1)), z = (int)(t / (v.ny + 1));
+    out[i] = x <= v.nx ? (int16_t)box_border(v, x, y, z) : (int16_t)0;
+  }
+}
+int vrk_boxavg(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int16_t* out, int px) {
+  VolView v{vol, nx, ny, nz};
+  const size_t n = (size_t)px * (ny + 1) * (nz + 1);
+  k_boxavg<<<(unsigned)std::min<size_t>(div_up(n, 256), (size_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(v, out, px);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}
+
 // fetch_stats, vectorised.  sqrt and float->int are monotonic, so min/max of (int)sqrt(s) = (int)sqrt(min/max s): the
 // square root is taken once per thread instead of once per voxel — bit-identical.
-__global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8(VolView vol, int32_t* __restrict__ stats, int zlo, int zhi) {
+// LINEAR: `vol` is the box-averaged volume, `orig` the volume itself; only voxels x < lim_x, y < lim_y count.
+template <bool LINEAR>
+__global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8(VolView vol, VolView orig, int lim_x, int lim_y, int32_t* __restrict__ stats,
+                                                               int zlo, int zhi) {
   const int x0 = (blockIdx.x * VX + threadIdx.x) * 8;
   const int y = blockIdx.y * VY + threadIdx.y;
   const int z = blockIdx.z * VZ + threadIdx.z;
   int mnv = INT32_MAX, mxv = INT32_MIN, mng = INT32_MAX, mxg = INT32_MIN;
-  if (x0 < vol.nx && y < vol.ny && z >= zlo && z < zhi) {
+  if (x0 < lim_x && y < lim_y && z >= zlo && z < zhi) {
     const Octet o = load_octet(vol, x0, y, z);
     float smin = grad_sq(o, 0), smax = smin;
-    mnv = mxv = o.c[0];
+    const bool face = LINEAR && (y == 0 || z == 0);
+    mnv = mxv = (LINEAR && (face || x0 == 0)) ? box_edge(orig, x0, y, z) : o.c[0];
 #pragma unroll
     for (int k = 1; k < 8; ++k) {
+      if (x0 + k >= lim_x) break;
       const float s = grad_sq(o, k);
       smin = fminf(smin, s); smax = fmaxf(smax, s);
-      mnv = min(mnv, o.c[k]); mxv = max(mxv, o.c[k]);
+      const int v = face ? box_edge(orig, x0 + k, y, z) : o.c[k];
+      mnv = min(mnv, v); mxv = max(mxv, v);
     }
     mng = f2i(sqrtf(smin)); mxg = f2i(sqrtf(smax));
   }
@@ -139,7 +188,7 @@ int vrk_fetch_stats_enqueue(vr_ctx* ctx, cudaStream_t stream, const int16_t* vol
   VolView v{vol, nx, ny, nz};
   if (nx % 8 == 0) {
     dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
-    k_fetch_stats_v8<<<grid, block, 0, stream>>>(v, dev4, zlo, zhi);
+    k_fetch_stats_v8<false><<<grid, block, 0, stream>>>(v, v, nx, ny, dev4, zlo, zhi);
   } else {
     dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
     k_fetch_stats<<<grid, block, 0, stream>>>(v, dev4, zlo, zhi);
@@ -147,6 +196,23 @@ int vrk_fetch_stats_enqueue(vr_ctx* ctx, cudaStream_t stream, const int16_t* vol
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
   VR_CUDA(cudaMemcpyAsync(pin4, dev4, sizeof(init), cudaMemcpyDeviceToHost, stream));
+  return VR_OK;
+}
+
+// under VR_SAMPLING_HW_LINEAR: box = the box-averaged volume (px x (ny+1) x (nz+1)), vol = the volume itself
+int vrk_fetch_stats_linear(vr_ctx* ctx, const int16_t* box, int px, const int16_t* vol, int nx, int ny, int nz, int32_t out[4], int zlo,
+                           int zhi) {
+  const int32_t init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
+  memcpy(ctx->scratch_host, init, sizeof(init));
+  VR_CUDA(cudaMemcpyAsync(ctx->scratch, ctx->scratch_host, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  VolView b{box, px, ny + 1, nz + 1}, v{vol, nx, ny, nz};
+  dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
+  k_fetch_stats_v8<true><<<grid, block, 0, ctx->stream>>>(b, v, nx, ny, ctx->scratch, zlo, std::min(zhi, nz));
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  VR_CUDA(cudaMemcpyAsync(ctx->scratch_host, ctx->scratch, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->scratch_host, sizeof(init));
   return VR_OK;
 }
 
@@ -209,7 +275,8 @@ int vrk_clip(vr_ctx* ctx, const int16_t* src, int snx, int sny, int snz, const u
 __device__ __forceinline__ int bil_class(int d2) {  // 0,1,2,3,4,5,6,8,9,12 -> 0..9
   return d2 <= 6 ? d2 : (d2 == 8 ? 7 : (d2 == 9 ? 8 : 9));
 }
-__global__ void __launch_bounds__(TX* TY* TZ) k_bilateral(VolView vol, int16_t* __restrict__ dst) {
+// dnx/dny/dnz: dims of the output (== the volume's; under VR_SAMPLING_HW_LINEAR `vol` is the box-averaged volume, one larger)
+__global__ void __launch_bounds__(TX* TY* TZ) k_bilateral(VolView vol, int16_t* __restrict__ dst, int dnx, int dny, int dnz) {
   __shared__ float tile[TZ + 4][TY + 4][TX + 4];
   __shared__ float wtab[10 * BIL_A];
   const int bx = blockIdx.x * TX, by = blockIdx.y * TY, bz = blockIdx.z * TZ;
@@ -232,7 +299,7 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_bilateral(VolView vol, int16_t* 
   }
   __syncthreads();
   const int x = bx + threadIdx.x, y = by + threadIdx.y, z = bz + threadIdx.z;
-  if (x >= vol.nx || y >= vol.ny || z >= vol.nz) return;
+  if (x >= dnx || y >= dny || z >= dnz) return;
   const float mid = tile[threadIdx.z + 2][threadIdx.y + 2][threadIdx.x + 2];
   float out_colour = 0.0f, wp = 0.0f;
 #pragma unroll
@@ -247,13 +314,22 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_bilateral(VolView vol, int16_t* 
         wp += w;
         out_colour += local * w;
       }
-  dst[(size_t)x + (size_t)vol.nx * ((size_t)y + (size_t)vol.ny * (size_t)z)] = (int16_t)f2s(out_colour / wp);
+  dst[(size_t)x + (size_t)dnx * ((size_t)y + (size_t)dny * (size_t)z)] = (int16_t)f2s(out_colour / wp);
 }
 
 int vrk_bilateral(vr_ctx* ctx, const int16_t* src, int16_t* dst, int nx, int ny, int nz) {
   VolView v{src, nx, ny, nz};
   dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
-  k_bilateral<<<grid, block, 0, ctx->stream>>>(v, dst);
+  k_bilateral<<<grid, block, 0, ctx->stream>>>(v, dst, nx, ny, nz);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}
+// centre and taps from the box-averaged volume (border addressing: utility_filter.cl:40), output for the volume's own voxels
+int vrk_bilateral_linear(vr_ctx* ctx, const int16_t* box, int px, int nx, int ny, int nz, int16_t* dst) {
+  VolView b{box, px, ny + 1, nz + 1};
+  dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
+  k_bilateral<<<grid, block, 0, ctx->stream>>>(b, dst, nx, ny, nz);
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
   return VR_OK;
@@ -299,22 +375,24 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_histogram(VolView vol, uint32_t*
 // go to global memory directly; every CTA flushes its window once at the end.  Bit-identical counts: integer adds commute.
 #define HWX 64
 #define HWY 128
-__global__ void __launch_bounds__(VX* VY* VZ) k_histogram_v8(VolView vol, uint32_t* __restrict__ bins, int width, int height,
-                                                             float min_v, float max_v, float min_g, float max_g, int zlo, int zhi,
-                                                             int wx0, int wy0) {
+template <bool LINEAR>
+__global__ void __launch_bounds__(VX* VY* VZ) k_histogram_v8(VolView vol, VolView orig, int lim_x, int lim_y, uint32_t* __restrict__ bins,
+                                                             int width, int height, float min_v, float max_v, float min_g, float max_g,
+                                                             int zlo, int zhi, int wx0, int wy0) {
   __shared__ unsigned win[HWX * HWY];
   const int tid = threadIdx.x + VX * (threadIdx.y + VY * threadIdx.z);
   for (int i = tid; i < HWX * HWY; i += VX * VY * VZ) win[i] = 0;
   __syncthreads();
-  const unsigned tx = div_up_dev(vol.nx, VX * 8), ty = div_up_dev(vol.ny, VY), tz = div_up_dev(vol.nz, VZ);
+  const unsigned tx = div_up_dev(lim_x, VX * 8), ty = div_up_dev(lim_y, VY), tz = div_up_dev(zhi, VZ);
   const float value_range = max_v - min_v, gradient_range = max_g - min_g;
   const long long nbins = (long long)width * height;
   for (unsigned t = blockIdx.x; t < tx * ty * tz; t += gridDim.x) {
     const int x0 = (int)(((t % tx) * VX + threadIdx.x) * 8);
     const int y = (int)(((t / tx) % ty) * VY + threadIdx.y);
     const int z = (int)((t / (tx * ty)) * VZ + threadIdx.z);
-    if (!(x0 < vol.nx && y < vol.ny && z >= zlo && z < zhi)) continue;
+    if (!(x0 < lim_x && y < lim_y && z >= zlo && z < zhi)) continue;
     const Octet o = load_octet(vol, x0, y, z);
+    const bool face = LINEAR && (y == 0 || z == 0);
     // a thread's 8 voxels often share a bin (air, the inside of a homogeneous object): run-length encode them, and merge
     // equal out-of-window bins across the warp, so that a hot bin anywhere in the grid costs one global atomic per warp
     long long run = -1;
@@ -331,11 +409,13 @@ __global__ void __launch_bounds__(VX* VY* VZ) k_histogram_v8(VolView vol, uint32
     };
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
+      if (x0 + k >= lim_x) break;
       const float g = sqrtf(grad_sq(o, k));
+      const int value = (LINEAR && (face || x0 + k == 0)) ? box_edge(orig, x0 + k, y, z) : o.c[k];
       long long flat = -1;
       int w = -1;
-      if (!(g > max_g || (float)o.c[k] > max_v)) {
-        const int px = f2i(roundf((((float)o.c[k] - min_v) / value_range) * (float)width));
+      if (!(g > max_g || (float)value > max_v)) {
+        const int px = f2i(roundf((((float)value - min_v) / value_range) * (float)width));
         const int py = f2i(roundf(((g - min_g) / gradient_range) * (float)height));
         flat = (long long)px * height + py;
         if (flat < 0 || flat >= nbins) flat = -1;
@@ -369,12 +449,29 @@ int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int w
     int wx0 = 0, wy0 = 0;
     if (vr > 0.0f) wx0 = std::max(0, std::min(width - 1, (int)roundf(((float)vol_min_value - range[0]) / vr * (float)width)));
     if (gr > 0.0f) wy0 = std::max(0, std::min(height - 1, (int)roundf((0.0f - range[2]) / gr * (float)height)));
-    k_histogram_v8<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3], zlo, zhi, wx0,
-                                                   wy0);
+    k_histogram_v8<false><<<grid, block, 0, ctx->stream>>>(v, v, nx, ny, bins_dev, width, height, range[0], range[1], range[2], range[3], zlo,
+                                                          std::min(zhi, nz), wx0, wy0);
   } else {
     dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
     k_histogram<<<grid, block, 0, ctx->stream>>>(v, bins_dev, width, height, range[0], range[1], range[2], range[3], zlo, zhi);
   }
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
+}
+
+int vrk_histogram_linear(vr_ctx* ctx, const int16_t* box, int px, const int16_t* vol, int nx, int ny, int nz, int width, int height,
+                         const float range[4], uint32_t* bins_dev, int zlo, int zhi, int vol_min_value) {
+  VR_CUDA(cudaMemsetAsync(bins_dev, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
+  VolView b{box, px, ny + 1, nz + 1}, v{vol, nx, ny, nz};
+  const size_t tiles = (size_t)div_up(nx, VX * 8) * div_up(ny, VY) * div_up(nz, VZ);
+  dim3 grid((unsigned)std::min<size_t>(tiles, (size_t)ctx->sm_count * 6)), block(VX, VY, VZ);
+  const float vr = range[1] - range[0], gr = range[3] - range[2];
+  int wx0 = 0, wy0 = 0;
+  if (vr > 0.0f) wx0 = std::max(0, std::min(width - 1, (int)roundf(((float)vol_min_value - range[0]) / vr * (float)width)));
+  if (gr > 0.0f) wy0 = std::max(0, std::min(height - 1, (int)roundf((0.0f - range[2]) / gr * (float)height)));
+  k_histogram_v8<true><<<grid, block, 0, ctx->stream>>>(b, v, nx, ny, bins_dev, width, height, range[0], range[1], range[2], range[3], zlo,
+                                                        std::min(zhi, nz), wx0, wy0);
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
   return VR_OK;
