@@ -40,6 +40,27 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL announces its version on stdout when NCCL_DEBUG asks for
+# it), so file descriptor 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -201,7 +222,7 @@ def run_reference(args, rank, world):
     value = W * H * args.steps / dt / 1e6
     sample = (f"{args.steps} x 1 spp frame of the workload; {what}; SDF built once beforehand on the CPU in {sdf_s:.1f}s, "
               f"untimed")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "path_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -209,7 +230,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample,
                          "sdf_build_ms_oracle": 1e3 * sdf_s},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 # ------------------------------------------------------------------------------------------------------------------------
@@ -735,7 +756,7 @@ def run_ours(args, rank, world, local_rank):
             "sdf_build_ms": {"value": float(np.median(sdf_ms)), "levels": levels, "volume": f"{VOL_N}^3",
                              "note": "vr_sdf_build wall time incl. allocation, excl. upload (app/sdf_benchmark.cpp:15-20)"},
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     r.close(); env.close(); vol.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -753,6 +774,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -119,6 +119,7 @@ SYMBOLS = {
     "vr_renderer_set_tuning": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "vr_renderer_quiet_download": (C.c_int, [_P, _P]),
     "vr_debug_rng_dump": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P]),
+    "vr_debug_linear_fetch": (C.c_int, [_P, _P, C.c_int, _P]),
     "vr_comm_unique_id": (C.c_int, [_P]),
     "vr_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "vr_comm_destroy": (None, [_P]),
@@ -625,6 +626,13 @@ class Renderer:
         nx, ny, nz = self.volume.dims()
         out = np.empty((nz, ny, nx), dtype=np.uint8)
         _check(lib().vr_renderer_quiet_download(self.h, _vp(out)))
+        return out
+
+    def linear_fetch(self, coords):
+        """hw-linear value at float positions [n,3] through the renderer's texture (vr_debug_linear_fetch)"""
+        xyz = np.ascontiguousarray(coords, dtype=np.float32).reshape(-1, 3)
+        out = np.empty(xyz.shape[0], dtype=np.int32)
+        _check(lib().vr_debug_linear_fetch(self.h, _vp(xyz), xyz.shape[0], _vp(out)))
         return out
 
     def cache_allreduce(self, readback=False, out=None):

@@ -591,6 +591,8 @@ extern "C" int vr_renderer_create(vr_ctx* ctx, int width, int height, vr_rendere
   cudaError_t e = pool_alloc(ctx, &r->frame, px * 4);
   if (e == cudaSuccess) e = pool_alloc(ctx, &r->hit, px * 4);
   if (e == cudaSuccess) e = pool_alloc(ctx, &r->counters, 8 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = pool_alloc(ctx, &r->bbox_dev, 4 * sizeof(int));
+  if (e == cudaSuccess) e = pinned_acquire(ctx, reinterpret_cast<void**>(&r->bbox_pin), 64);
   if (e == cudaSuccess) e = pinned_acquire(ctx, reinterpret_cast<void**>(&r->frame_host), px * 4);
   if (e == cudaSuccess) e = cudaMemsetAsync(r->frame, 0, px * 4, ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(r->hit, 0xFF, px * 4, ctx->stream);
@@ -714,7 +716,10 @@ extern "C" void vr_renderer_destroy(vr_renderer* r) {
   pool_free(r->ctx, r->gather_buf);
   cudaStreamSynchronize(r->ctx->stream);
   for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
+  pool_free(r->ctx, r->bbox_dev);
+  cudaStreamSynchronize(r->ctx->stream);
   pinned_release(r->ctx, r->frame_host);
+  pinned_release(r->ctx, r->bbox_pin);
   delete r;
 }
 
@@ -812,10 +817,26 @@ static int check_flushed(const vr_renderer* r, const char* who) {
   return VR_OK;
 }
 
+// The blocking pull of renderer.cpp:150.  Into the renderer-owned host frame the pull is incremental: while the primary records
+// of the last complete pull are still the current ones (same camera, rows and scene; vr_renderer_set_primary_reuse(r, 2)), only
+// shaded pixels can have changed, and they lie inside the bounding box k_primary reduced.
 static int read_frame(vr_renderer* r, uint8_t* host_rgba) {
   if (!host_rgba) return VR_OK;
-  VR_CUDA(cudaMemcpyAsync(host_rgba, r->frame, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost, r->ctx->stream));
-  VR_CUDA(cudaStreamSynchronize(r->ctx->stream));  // blocking pull, renderer.cpp:150
+  vr_ctx* ctx = r->ctx;
+  const bool own = host_rgba == r->frame_host;
+  if (own && r->host_epoch != 0 && r->host_epoch == r->primary_epoch && r->primary_valid) {
+    const int x0 = r->bbox_pin[0], y0 = r->bbox_pin[1], x1 = r->bbox_pin[2], y1 = r->bbox_pin[3];
+    if (x1 >= x0 && y1 >= y0) {
+      const size_t pitch = (size_t)r->W * 4, off = ((size_t)y0 * r->W + x0) * 4;
+      VR_CUDA(cudaMemcpy2DAsync(host_rgba + off, pitch, reinterpret_cast<const uint8_t*>(r->frame) + off, pitch, (size_t)(x1 - x0 + 1) * 4,
+                                (size_t)(y1 - y0 + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    VR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VR_OK;
+  }
+  VR_CUDA(cudaMemcpyAsync(host_rgba, r->frame, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(ctx->stream));  // also completes the bounding-box transfer of the k_primary before it
+  if (own) r->host_epoch = (r->primary_valid && r->trace_mode == 2 && r->row0 == 0 && r->row1 == r->H) ? r->primary_epoch : 0;
   return VR_OK;
 }
 
@@ -876,6 +897,7 @@ extern "C" int vr_renderer_filter_frame(vr_renderer* r, int kernel_size, float s
   if (!r->filtered) VR_CUDA(pool_alloc(ctx, &r->filtered, bytes));
   VR_TRY(vrk_filter2d(ctx, r->frame, r->filtered, r->W, r->H, kernel_size, sigma, mode));
   if (!host_rgba) return VR_OK;
+  if (host_rgba == r->frame_host) r->host_epoch = 0;  // the host frame now holds the filtered image: the next pull is a full one
   VR_CUDA(cudaMemcpyAsync(host_rgba, r->filtered, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   VR_CUDA(cudaStreamSynchronize(ctx->stream));
   return VR_OK;
@@ -1113,10 +1135,10 @@ extern "C" int vr_renderer_set_tuning(vr_renderer* r, const char* key, int value
   if (!strcmp(key, "pixel_major")) { VR_REQUIRE(value >= 0 && value <= 4096, "pixel_major out of range"); t.pixel_major = value; }
   else if (!strcmp(key, "rule_a")) { VR_REQUIRE(value >= 1 && value <= 1024, "rule_a out of range"); t.rule[0] = value; }
   else if (!strcmp(key, "rule_b")) { VR_REQUIRE(value >= 1 && value <= 1024, "rule_b out of range"); t.rule[1] = value; }
-  else if (!strcmp(key, "lin_fast_a")) { VR_REQUIRE(value >= 0 && value <= 1024, "lin_fast_a out of range"); t.lin_rule[0] = value; }
-  else if (!strcmp(key, "lin_fast_b")) { VR_REQUIRE(value >= 0 && value <= 1024, "lin_fast_b out of range"); t.lin_rule[1] = value; }
-  else if (!strcmp(key, "lin_slow_a")) { VR_REQUIRE(value >= 0 && value <= 1024, "lin_slow_a out of range"); t.lin_rule[2] = value; }
-  else if (!strcmp(key, "lin_slow_b")) { VR_REQUIRE(value >= 0 && value <= 1024, "lin_slow_b out of range"); t.lin_rule[3] = value; }
+  else if (!strcmp(key, "lin_w_fast")) { VR_REQUIRE(value >= 1 && value <= 1024, "lin_w_fast out of range"); t.lin_w[0] = value; }
+  else if (!strcmp(key, "lin_w_slow")) { VR_REQUIRE(value >= 1 && value <= 1024, "lin_w_slow out of range"); t.lin_w[1] = value; }
+  else if (!strcmp(key, "lin_w_event")) { VR_REQUIRE(value >= 1 && value <= 1024, "lin_w_event out of range"); t.lin_w[2] = value; }
+  else if (!strcmp(key, "steps_per_check")) { VR_REQUIRE(value >= 1 && value <= 16, "steps_per_check out of range"); t.spc = value; }
   else if (!strcmp(key, "pt_ctas")) {
 #ifdef VR_AB
     t.pt_ctas = value;
@@ -1143,6 +1165,28 @@ extern "C" int vr_renderer_quiet_download(const vr_renderer* r, uint8_t* out) {
     if (e != cudaSuccess) { vr_set_error("vr_renderer_quiet_download: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
   }
   pool_free(ctx, dev);
+  return st;
+}
+
+extern "C" int vr_debug_linear_fetch(const vr_renderer* r, const float* xyz, int n, int32_t* out) {
+  VR_REQUIRE(r && xyz && out && n > 0, "vr_debug_linear_fetch: bad argument");
+  VR_REQUIRE(r->vol_tex, "vr_debug_linear_fetch: no volume texture (hw-linear sampling + flush)");
+  vr_ctx* ctx = r->ctx;
+  VR_CUDA(cudaSetDevice(ctx->device));
+  float* d_xyz = nullptr;
+  int32_t* d_out = nullptr;
+  VR_CUDA(pool_alloc(ctx, &d_xyz, (size_t)n * 12));
+  VR_CUDA(pool_alloc(ctx, &d_out, (size_t)n * 4));
+  int st = VR_OK;
+  cudaError_t e = cudaMemcpyAsync(d_xyz, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) { vr_set_error("vr_debug_linear_fetch: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  if (st == VR_OK) st = vrk_linear_fetch(ctx, r->vol_tex, d_xyz, n, d_out);
+  if (st == VR_OK) {
+    e = cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { vr_set_error("vr_debug_linear_fetch: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  }
+  pool_free(ctx, d_xyz); pool_free(ctx, d_out);
   return st;
 }
 

@@ -167,6 +167,7 @@ extern "C" int vr_cache_allreduce(vr_renderer* r, uint8_t* host_rgba) {
   }
   VR_TRY(vrk_xc_scatter_resolve(r, wide));
   if (!host_rgba) return VR_OK;
+  if (host_rgba == r->frame_host) r->host_epoch = 0;  // full pull outside read_frame: the next incremental pull starts over
   VR_CUDA(cudaMemcpyAsync(host_rgba, r->frame, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost, ctx->stream));
   VR_CUDA(cudaStreamSynchronize(ctx->stream));
   return VR_OK;
@@ -238,6 +239,7 @@ extern "C" int vr_frame_allgather(vr_renderer* r, uint8_t* host_rgba) {
     r->primary_valid = false;
   }
   if (!host_rgba) return VR_OK;
+  if (host_rgba == r->frame_host) r->host_epoch = 0;  // full pull outside read_frame: the next incremental pull starts over
   VR_CUDA(cudaMemcpyAsync(host_rgba, r->frame, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost, ctx->stream));
   VR_CUDA(cudaStreamSynchronize(ctx->stream));
   return VR_OK;

@@ -143,7 +143,8 @@ struct vr_renderer {
   struct Tuning {
     int pixel_major = 1;               // k_trace_pt<.., REUSE> item order: groups of this many pixels x all frames (0: frame-major)
     int rule[2] = {5, 1};              // k_trace_pt leaves its march region when marching lanes * rule[0] < waiting lanes * rule[1]
-    int lin_rule[4] = {2, 1, 2, 1};    // hw-linear: the same for the quiet-step loop and the event-test loop
+    int lin_w[3] = {4, 2, 1};          // hw-linear scheduler: weights of quiet steps / event tests / event processing
+    int spc = 2;                       // steps per scheduling decision of k_trace_pt
     int pt_ctas = 0;                   // -DVR_AB builds only: register budget variant of k_trace_pt
   } tune;
   // Which cache entries can be non-zero: 0 none (just reset), 1 only cache[hit[pix]] of the current `hit` buffer (every trace
@@ -162,6 +163,13 @@ struct vr_renderer {
   bool primary_across_calls = false;  // vr_renderer_set_primary_reuse(r, 2)
   float primary_pos[3] = {0, 0, 0}, primary_dir[3] = {0, 0, 0};
   int primary_rows[2] = {0, 0};
+  // Incremental pull of the renderer-owned host frame (vr_renderer_host_frame): while the primary records stay valid the
+  // environment pixels of the frame cannot change, so a pull copies only the bounding box of the shaded pixels (k_primary
+  // reduces it, bbox_pin receives it) instead of the whole frame.  primary_epoch counts k_primary runs; host_epoch is the epoch
+  // whose complete frame the host buffer holds (0: none).
+  uint64_t primary_epoch = 0, host_epoch = 0;
+  int* bbox_dev = nullptr;   // {min x, min y, max x, max y} of the shaded pixels
+  int* bbox_pin = nullptr;
   uint4* queue = nullptr;  // hybrid schedule: admitted primary hits (3 x uint4 each)
   size_t queue_cap = 0;
   uint2* xchg = nullptr;  // W*H compact cache entries for the spp-split exchange (allocated on first use)
@@ -229,6 +237,7 @@ int vrk_lin_field_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz,
                         cudaSurfaceObject_t out);
 int vrk_lin_field_masks(vr_ctx* ctx, cudaSurfaceObject_t field, int nx, int ny, int nz, uint8_t* masks_dev);
 // device RNG known-answer dump (tests): hemisphere integer triples and directions over a (seed, gid) grid (vr_render.cu)
+int vrk_linear_fetch(vr_ctx* ctx, cudaTextureObject_t tex, const float* xyz_dev, int n, int32_t* out_dev);
 int vrk_rng_dump(vr_ctx* ctx, const int32_t* seeds_dev, const uint32_t* gid_dev, int n, const float* normal_rough_dev, int32_t* ra_dev,
                  int32_t* comp_dev, float* dir_dev);
 // the volume kernels under VR_SAMPLING_HW_LINEAR: box = the box-averaged volume, px its padded row length (vr_volume_ops.cu)

@@ -30,7 +30,8 @@ struct RenderParams {
   // VR_SAMPLING_HW_LINEAR: the step field (vr_quiet.cu) — per voxel cell the SDF byte and one "quiet" bit per octant, 16 bits behind
   // a surface object
   cudaSurfaceObject_t lin_surf;
-  int lin_fa, lin_fb, lin_sa, lin_sb;  // k_trace_pt<.., LINEAR>: leave rules of the quiet-step loop and of the event-test loop
+  int lin_wf, lin_ws, lin_we;  // k_trace_pt<.., LINEAR>: weights of quiet steps / event tests / event processing in its scheduler
+  int spc;                     // k_trace_pt: steps per scheduling decision
   const uchar4* __restrict__ env;
   int env_w, env_h;
   uint32_t* __restrict__ cache;
@@ -46,6 +47,7 @@ struct RenderParams {
   int rule_a, rule_b;   // k_trace_pt leaves its step loop when marching lanes * rule_a < waiting lanes * rule_b (VR_PT_RULE=a,b)
   int seeds[VR_MAX_BATCH];
   unsigned long long* counters;
+  int* bbox;  // k_primary: bounding box of the shaded pixels {min x, min y, max x, max y} (may be null)
   // hybrid schedule: k_trace<QUEUE> appends admitted primary hits here, k_trace_pt runs their secondary paths.
   // primary-reuse schedule: k_primary appends ONE record per shaded pixel, k_trace_pt<.., true> runs token admission and the
   // secondary paths for every (record, frame) pair.
@@ -127,8 +129,19 @@ __device__ __forceinline__ bool cut_box(const VolView& v, Ray shot, f3* cut_poin
 // volume (undefined by OpenCL 1.2): the texture unit interpolates the texels (centres at +0.5, 8-bit weights,
 // border 0) and the result is rounded to an integer.  The same unit through a normalised-float read gives value / 32767;
 // rint(t * 32767) in double equals the OpenCL value on all 48 196 probe samples (profiles/r1b_cuda_texture_vs_opencl_linear.txt).
+// The filter works with 8 fraction bits, so value * 256 is an integer k, and the hardware's result is floor(k / 256 + 1/2)
+// (oracle.cpp hw_round).  For |value| < 8192 one fused multiply-add into the binade of 2^23 recovers k exactly from the float
+// (t * 32767 * 256 = k (1 + e), |k e| <= 2^21 * 2^-24; the single rounding of the fma is to an integer) and the rounding is an
+// add and a shift — no conversion instructions, no fp64.  Larger values take the double-precision route.
+__device__ __forceinline__ int tex_value(float t) {
+  if (fabsf(t) < 0.25f) {
+    const int k = __float_as_int(__fmaf_rn(t, 8388352.0f, 12582912.0f)) - 0x4B400000;  // 32767 * 256; 1.5 * 2^23
+    return (k + 128) >> 8;
+  }
+  return __double2int_rn((double)t * 32767.0);
+}
 __device__ __forceinline__ int vol_linear(const RenderParams& p, float x, float y, float z) {
-  return __double2int_rn((double)tex3D<float>(p.vol_tex, x, y, z) * 32767.0);
+  return tex_value(tex3D<float>(p.vol_tex, x, y, z));
 }
 // gradient_prewitt_nn at a float position with that sampler, utility_filter.cl:2-35: taps at p +- 1 on each axis
 __device__ __forceinline__ f3 gradient_linear(const RenderParams& p, f3 o) {
@@ -153,11 +166,25 @@ __device__ __forceinline__ unsigned lin_cell(const RenderParams& p, int x, int y
 }
 __device__ __forceinline__ int lin_sdf(unsigned cell) { return (int)(signed char)(cell & 0xFFu); }
 // o - floor(o) is exact in fp32 for o >= 0 (Sterbenz), so the comparison equals the oracle's double evaluation of the fixed-point cell
-__device__ __forceinline__ bool lin_quiet(unsigned cell, f3 o, int vx, int vy, int vz) {
+__device__ __forceinline__ bool lin_quiet(unsigned cell, float frac_x, float frac_y, float frac_z) {
   const float h = 0.498046875f;  // 127.5 / 256
-  const unsigned oct = (o.x - (float)vx >= h ? 1u : 0u) | (o.y - (float)vy >= h ? 2u : 0u) | (o.z - (float)vz >= h ? 4u : 0u);
+  const unsigned oct = (frac_x >= h ? 1u : 0u) | (frac_y >= h ? 2u : 0u) | (frac_z >= h ? 4u : 0u);
   return ((cell >> (8u + oct)) & 1u) != 0u;
 }
+__device__ __forceinline__ bool lin_quiet(unsigned cell, f3 o, int vx, int vy, int vz) {
+  return lin_quiet(cell, o.x - (float)vx, o.y - (float)vy, o.z - (float)vz);
+}
+// The step loops of k_trace_pt without the conversion pipe (ncu: XU 42 % busy with float<->int conversions of the step):
+//  * floor of a coordinate: for 0 <= x < 2^23, x + 2^23 rounded DOWN is exactly 2^23 + floor(x) (ulp 1 there), so the integer is
+//    a subtraction on the bit pattern and the float floor a subtraction of 2^23 — FADD.RM + IADD + FADD.  A negative x yields a
+//    negative integer that is not its floor: the step loops only test its sign and feed it to the surface read (0 out of range).
+//  * the SDF byte as a float: 1.5 * 2^23 + d is exact in the mantissa for |d| < 2^22.
+__device__ __forceinline__ int floor_pair(float x, float* fl) {
+  const float t = __fadd_rd(x, 8388608.0f);
+  *fl = __fsub_rn(t, 8388608.0f);
+  return __float_as_int(t) - 0x4B000000;
+}
+__device__ __forceinline__ float small_int_to_float(int d) { return __fsub_rn(__int_as_float(0x4B400000 + d), 12582912.0f); }
 
 // sample_environment_map, utility_environment_map.cl:3-13: normalised coords, clamp to edge; nearest texel, or (LINEAR) the
 // texture unit's bilinear interpolation of the RGBA8 texels rounded to integers
@@ -453,6 +480,12 @@ __global__ void __launch_bounds__(128, LINEAR ? 8 : 12) k_primary(const RenderPa
       h.base = cur.o + cur.d;
       h.normal = -normalize3_shared_rcp(grad);
       store_record(p.queue, slot, h);
+      if (p.bbox) {  // the incremental frame pull copies this box only (vr_api.cu read_frame)
+        const int x0 = __reduce_min_sync(m, x), y0 = __reduce_min_sync(m, y), x1 = __reduce_max_sync(m, x), y1 = __reduce_max_sync(m, y);
+        if (lane == (unsigned)(__ffs(m) - 1)) {
+          atomicMin(p.bbox + 0, x0); atomicMin(p.bbox + 1, y0); atomicMax(p.bbox + 2, x1); atomicMax(p.bbox + 3, y1);
+        }
+      }
     }
   }
   if (COUNT) {  // per-sample counters: the n samples of the pixel each own this primary segment
@@ -672,14 +705,15 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
     if (LINEAR) {
       // one march() + the gather that classifies the new position (utility_ray.cl:148-154, :112-117)
       auto advance = [&]() {
-        const float step_size = max_cl((float)d, 0.5f);
+        const float step_size = max_cl(small_int_to_float(d), 0.5f);
         o = o + step_size * dv;
         if (COUNT) c_steps++;
         steps_left--;
-        const int vx = ifloor(o.x), vy = ifloor(o.y), vz = ifloor(o.z);
+        float fx, fy, fz;
+        const int vx = floor_pair(o.x, &fx), vy = floor_pair(o.y, &fy), vz = floor_pair(o.z, &fz);
         const unsigned cell = lin_cell(p, vx, vy, vz);
         d = lin_sdf(cell);
-        if (lin_quiet(cell, o, vx, vy, vz)) {  // no event possible here: get_event_and_value returns None
+        if (lin_quiet(cell, o.x - fx, o.y - fy, o.z - fz)) {  // no event possible here: get_event_and_value returns None
           pending = false;
           marching = steps_left != 0;
           if (!marching) ev = EVP_NONE;
@@ -690,18 +724,21 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
           if (exited) ev = EVP_EXIT;
         }
       };
+      // Three kinds of work wait in a warp: quiet steps (cheap: ~25 instructions), event tests (seven filtered fetches + the
+      // transfer function: ~5x) and event processing / refills outside this region (normalisations, RNG bounce, environment
+      // lookup: ~10x).  Every round the warp does the kind whose lane count, weighted by how cheap the kind is, is largest: cheap
+      // work may run with few lanes, expensive work waits until enough lanes want it (ncu on the first version, which ran the
+      // event tests whenever the quiet-step loop paused: 2.8 of 32 lanes active in the test code).
       for (;;) {
-        // ---- quiet-step loop ----
-        for (;;) {
-          if (marching) advance();
-          const unsigned act = __ballot_sync(0xffffffffu, marching);
-          if (!act) break;
-          const unsigned others = __ballot_sync(0xffffffffu, !marching && (pending || mode != M_IDLE || !exhausted));
-          if (__popc(act) * p.lin_fa < __popc(others) * p.lin_fb) break;
-        }
-        // ---- event-test loop: get_event_and_value (utility_ray.cl:126-138) where an event is possible ----
-        for (;;) {
-          if (!__ballot_sync(0xffffffffu, pending)) break;
+        const unsigned mF = __ballot_sync(0xffffffffu, marching), mS = __ballot_sync(0xffffffffu, pending);
+        if (!(mF | mS)) break;
+        const unsigned mE = __ballot_sync(0xffffffffu, !marching && !pending && (mode != M_IDLE || !exhausted));
+        const int F = __popc(mF) * p.lin_wf, S = __popc(mS) * p.lin_ws, E = __popc(mE) * p.lin_we;
+        if (F >= S && F >= E) {
+          for (int u = 0; u < p.spc; ++u)
+            if (marching) advance();
+        } else if (S >= E) {
+          // get_event_and_value (utility_ray.cl:126-138) where an event is possible
           if (pending) {
             const f3 grad = gradient_linear(p, o);
             const int value = vol_linear(p, o.x, o.y, o.z);
@@ -718,29 +755,26 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
               advance();
             }
           }
-          const unsigned pend = __ballot_sync(0xffffffffu, pending);
-          if (!pend) break;
-          const unsigned others = __ballot_sync(0xffffffffu, !pending && (marching || mode != M_IDLE || !exhausted));
-          if (__popc(pend) * p.lin_sa < __popc(others) * p.lin_sb) break;
+        } else {
+          break;
         }
-        const unsigned go = __ballot_sync(0xffffffffu, marching || pending);
-        if (!go) break;
-        const unsigned waiting = __ballot_sync(0xffffffffu, !marching && !pending && (mode != M_IDLE || !exhausted));
-        if (__popc(go) * p.rule_a < __popc(waiting) * p.rule_b) break;
       }
       continue;
     }
 
     // ---- step loop: march (second half) + get_event_and_value with the SDF-sign shortcut -------------------------------------------
     for (;;) {
-      if (marching) {
-        const float step_size = max_cl((float)d, 0.5f);
-        o = o + step_size * dv;
-        if (COUNT) c_steps++;
-        steps_left--;
-        const int vx = ifloor(o.x), vy = ifloor(o.y), vz = ifloor(o.z);
+      for (int u = 0; u < p.spc; ++u) {
+        if (!marching) continue;
         if (SURF) {
-          // the surface returns 0 outside the field (and real voxels are never 0): bounds only matter when the step ends
+          // conversion-free step (floor_pair): the surface returns 0 outside the field (and real voxels are never 0), so bounds
+          // only matter when the step ends, and then only the sign of the floored coordinates is used
+          const float step_size = max_cl(small_int_to_float(d), 0.5f);
+          o = o + step_size * dv;
+          if (COUNT) c_steps++;
+          steps_left--;
+          float fx, fy, fz;
+          const int vx = floor_pair(o.x, &fx), vy = floor_pair(o.y, &fy), vz = floor_pair(o.z, &fz);
           d = surf3Dread<signed char>(p.sdf_surf, vx, vy, vz, cudaBoundaryModeZero);
           if (d <= 0) {
             const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
@@ -748,6 +782,11 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
             ev = exited ? EVP_EXIT : (d < 0 ? EVP_SDF_NEG : EVP_FARFACE);
           } else if (steps_left == 0) { marching = false; ev = EVP_NONE; }
         } else {
+          const float step_size = max_cl((float)d, 0.5f);
+          o = o + step_size * dv;
+          if (COUNT) c_steps++;
+          steps_left--;
+          const int vx = ifloor(o.x), vy = ifloor(o.y), vz = ifloor(o.z);
           const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
           if (exited) { marching = false; ev = EVP_EXIT; }
           else {
@@ -910,9 +949,14 @@ static int launch_trace(vr_renderer* r, RenderParams& p, const float pos[3], con
                     r->primary_rows[0] == r->row0 && r->primary_rows[1] == r->row1;
   if (!same || COUNT || (first_of_call && !r->primary_across_calls)) {
     VR_CUDA(cudaMemsetAsync(p.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
+    VR_CUDA(cudaMemsetAsync(r->bbox_dev, 0x7F, 2 * sizeof(int), ctx->stream));      // min fields: large
+    VR_CUDA(cudaMemsetAsync(r->bbox_dev + 2, 0xFF, 2 * sizeof(int), ctx->stream));  // max fields: -1
+    p.bbox = r->bbox_dev;
     dim3 g1(div_up(r->W, 8), div_up(rows, 16), 1);
     k_primary<COUNT, LINEAR><<<g1, 128, 0, ctx->stream>>>(p);
     ctx->launches++;
+    VR_CUDA(cudaMemcpyAsync(r->bbox_pin, r->bbox_dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    r->primary_epoch++;
     memcpy(r->primary_pos, pos, 12); memcpy(r->primary_dir, dir, 12);
     r->primary_rows[0] = r->row0; r->primary_rows[1] = r->row1;
     r->primary_valid = true;
@@ -974,11 +1018,13 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     p.nframes = nframes;
     p.pixel_major = r->tune.pixel_major;
     p.rule_a = r->tune.rule[0]; p.rule_b = r->tune.rule[1];
-    p.lin_fa = r->tune.lin_rule[0]; p.lin_fb = r->tune.lin_rule[1]; p.lin_sa = r->tune.lin_rule[2]; p.lin_sb = r->tune.lin_rule[3];
+    p.lin_wf = r->tune.lin_w[0]; p.lin_ws = r->tune.lin_w[1]; p.lin_we = r->tune.lin_w[2];
+    p.spc = r->tune.spc;
     for (int k = 0; k < nframes; ++k) p.seeds[k] = seeds[k];
     p.token_cap = r->token_cap;
     p.counters = r->counters;
     p.queue = nullptr; p.qcount = nullptr; p.qcap = 0;
+    p.bbox = nullptr;
     p.tf = r->tf_active;
     int st;
     if (lin) st = r->count ? launch_trace<true, true>(r, p, pos, dir, rows, nframes, first_of_call)
@@ -1148,6 +1194,18 @@ __global__ void __launch_bounds__(128) k_rng_dump(const int32_t* __restrict__ se
   const f3 nrm = {normal_rough[4 * i], normal_rough[4 * i + 1], normal_rough[4 * i + 2]};
   const f3 d = hemisphere_reflective_p(nrm, seeds[i], normal_rough[4 * i + 3], xyp);
   dir_out[3 * i] = d.x; dir_out[3 * i + 1] = d.y; dir_out[3 * i + 2] = d.z;
+}
+
+// hw-linear fetch known answers (tests): the value get_event_and_value sees at n float positions, through the renderer's texture
+__global__ void __launch_bounds__(128) k_linear_fetch(cudaTextureObject_t tex, const float* __restrict__ xyz, int n, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = tex_value(tex3D<float>(tex, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+}
+int vrk_linear_fetch(vr_ctx* ctx, cudaTextureObject_t tex, const float* xyz_dev, int n, int32_t* out_dev) {
+  k_linear_fetch<<<div_up((size_t)n, 128), 128, 0, ctx->stream>>>(tex, xyz_dev, n, out_dev);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  return VR_OK;
 }
 
 int vrk_rng_dump(vr_ctx* ctx, const int32_t* seeds_dev, const uint32_t* gid_dev, int n, const float* normal_rough_dev, int32_t* ra_dev,

@@ -309,11 +309,15 @@ int vr_renderer_set_primary_reuse(vr_renderer* r, int level);
 int vr_renderer_enable_timing(vr_renderer* r, int enable);
 int vr_renderer_kernel_times(vr_renderer* r, double out_ms[2], int* n_frames, int reset);
 /* Schedule tuning of the persistent-warp tracer; never changes a result.  Keys: "pixel_major" (items per pixel group, 0 =
- * frame-major), "rule_a"/"rule_b" (leave the march region when marching*a < waiting*b), "lin_fast_a/b", "lin_slow_a/b" (the
- * same for the two loops of the hw-linear path), "pt_ctas" (register budget; only in the A/B build, tools/ab). */
+ * frame-major), "rule_a"/"rule_b" (leave the march region when marching*a < waiting*b), "steps_per_check", "lin_w_fast" /
+ * "lin_w_slow" / "lin_w_event" (weights of the three kinds of work in the hw-linear scheduler), "pt_ctas" (register budget;
+ * only in the A/B build, tools/ab). */
 int vr_renderer_set_tuning(vr_renderer* r, const char* key, int value);
 /* hw-linear step field: the quiet-octant byte of every voxel cell, x fastest (tests: equals the oracle's orc_quiet_cells) */
 int vr_renderer_quiet_download(const vr_renderer* r, uint8_t* out);
+/* hw-linear fetch known answers: the value get_event_and_value reads at n float positions (x, y, z triples) through the
+ * renderer's volume texture (tests: equals the oracle's model of the hardware filter, itself pinned on 874 545 OpenCL samples) */
+int vr_debug_linear_fetch(const vr_renderer* r, const float* xyz, int n, int32_t* out);
 /* Device RNG known answers (utility_sampling.cl:13-21,40-50): runs the device functions of the trace kernels on n items
  * (seed, gid0, gid1, normal.xyz + roughness) and returns the three hashes `ra`, the components `(ra % 2048) - 1024`, and the
  * sampled direction. */

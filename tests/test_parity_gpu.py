@@ -782,3 +782,63 @@ def test_array_cache_stays_bounded_over_many_clip_boxes(vr_ctx):
         r.flush_changes()
         assert vr_ctx.array_count <= base + 4   # + the 16-bit step field
     r.close(); env.close(); vol.close()
+
+
+def test_incremental_host_frame_pull_equals_full_pull(vr_ctx):
+    """Pulls into the renderer-owned host frame copy only the bounding box of the shaded pixels while the primary records stay valid
+    (vr_renderer_set_primary_reuse(r, 2)); the buffer must equal a full pull after every call — across camera changes, a frame
+    filter into the same buffer, a flush and a cache reset."""
+    n, W, H = 48, 200, 120
+    v, envimg, tf = synth.synth_ct(n), synth.synth_env(128, 64), synth.default_tf()
+    vol, env = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
+    r = api.Renderer(vr_ctx, W, H)
+    r.image_set(vol, env); r.set_tf(tf); r.set_primary_reuse(2); r.flush_changes()
+    hf = r.host_frame()
+    cams = [synth.default_camera(n), synth.closeup_camera(n), ((500.0, 500.0, 500.0), (0.577, 0.577, 0.577))]  # the last one sees no voxel
+    seeds = synth.glibc_rand(12)
+    k = 0
+    for rep in range(2):
+        for pos, d in cams:
+            for j in range(3):
+                r.render_frame(pos, d, seeds[k % 12], out=hf); k += 1
+                full = r.resolve()                       # full pull into a separate buffer
+                assert np.array_equal(hf, full), (rep, j)
+            if rep == 0:
+                r.filter_frame(2, 2.0, api.VR_FILTER2D_BILATERAL, readback=False)
+                api._check(api.lib().vr_renderer_filter_frame(r.h, 2, api.C.c_float(2.0), api.VR_FILTER2D_BILATERAL, api._vp(hf)))
+                r.render_frame(pos, d, seeds[k % 12], out=hf); k += 1   # after a filter into the host frame: a full pull again
+                assert np.array_equal(hf, r.resolve())
+        r.reset_cache()
+        r.flush_changes()
+    r.close(); env.close(); vol.close()
+
+
+def test_hw_linear_fetch_equals_oracle_model_incl_ties_and_large_values(vr_ctx):
+    """The value the hw-linear path reads at a float position (texture unit + tex_value) against the oracle's model of the hardware
+    filter (hw_linear_fetch, pinned bit for bit on 874 545 samples of NVIDIA's OpenCL runtime): random positions, positions on the
+    1/256 grid (where the rounding ties live), positions outside the volume (border 0), and a volume with values up to +-32767
+    (the fp64 route of tex_value)."""
+    rng = np.random.default_rng(11)
+    envimg = synth.synth_env(64, 32)
+    env = api.EnvMap(vr_ctx, envimg)
+    for which in ("ct", "extreme"):
+        if which == "ct":
+            v = synth.synth_ct(0, dims=(45, 37, 29))
+        else:
+            v = rng.integers(-32768, 32768, size=(19, 23, 31)).astype(np.int16)
+        nz, ny, nx = v.shape
+        vol = api.Volume(vr_ctx, v)
+        r = api.Renderer(vr_ctx, 32, 32)
+        r.set_sampling(api.VR_SAMPLING_HW_LINEAR)
+        r.image_set(vol, env); r.set_tf(synth.default_tf()); r.flush_changes()
+        n = 200000
+        dims = np.array([nx, ny, nz], np.float32)
+        a = (rng.random((n, 3), dtype=np.float32) * (dims + 4.0) - 2.0).astype(np.float32)          # anywhere, incl. outside
+        b = (rng.integers(-256, (dims.max() + 1) * 256, size=(n, 3)) / 256.0).astype(np.float32)     # on the fixed-point grid
+        c = (rng.integers(0, dims.max() * 2, size=(n, 3)) / 2.0).astype(np.float32)                  # integer and half positions
+        pts = np.concatenate([a, b, c])
+        got = r.linear_fetch(pts)
+        want = o.hw_linear_fetch(v, pts)
+        assert np.array_equal(got, want), (which, int((got != want).sum()))
+        r.close(); vol.close()
+    env.close()

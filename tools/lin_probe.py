@@ -10,7 +10,7 @@ import torch  # noqa: E402
 from cl_volume_renderer_b200 import api, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-quick = len(sys.argv) > 2
+quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
 W, H = 1920, 1080
 ctx = api.Context(0)
 s = torch.cuda.ExternalStream(ctx.stream)
@@ -48,14 +48,15 @@ for sampling, name in ((api.VR_SAMPLING_NEAREST, "nearest"), (api.VR_SAMPLING_HW
     r.set_trace_mode(2)
     if sampling == api.VR_SAMPLING_HW_LINEAR and not quick:
         settings = []
-        for fa, fb in ((1, 1), (2, 1), (4, 1), (8, 1), (1, 2), (0, 1)):
-            for sa, sb in ((1, 1), (2, 1), (4, 1), (8, 1), (1, 2), (0, 1)):
-                settings.append({"lin_fast_a": fa, "lin_fast_b": fb, "lin_slow_a": sa, "lin_slow_b": sb})
-        for ra in (2, 5, 10):
-            settings.append({"rule_a": ra, "rule_b": 1})
+        for w in ((4, 2, 1), (8, 2, 1), (4, 1, 1), (8, 4, 1), (2, 1, 1), (6, 3, 1), (4, 3, 1), (8, 3, 2), (16, 4, 1), (3, 2, 1), (2, 2, 1), (16, 8, 1),
+                  (8, 1, 1), (12, 3, 1)):
+            settings.append({"lin_w_fast": w[0], "lin_w_slow": w[1], "lin_w_event": w[2]})
+        for spc in (1, 3, 4):
+            settings.append({"steps_per_check": spc})
         if ab:
             for c in (6, 10, 12):
                 settings.append({"pt_ctas": c})
+        base = {"lin_w_fast": 4, "lin_w_slow": 2, "lin_w_event": 1, "steps_per_check": 2}
         for st in settings:
             for k, v in st.items():
                 r.set_tuning(k, v)
@@ -63,8 +64,17 @@ for sampling, name in ((api.VR_SAMPLING_NEAREST, "nearest"), (api.VR_SAMPLING_HW
             for cam, (pos, d) in cams.items():
                 row[cam + "_ms"] = measure(r, pos, d, 2)
             print(json.dumps(row), flush=True)
-            for k, v in (("lin_fast_a", 2), ("lin_fast_b", 1), ("lin_slow_a", 2), ("lin_slow_b", 1), ("rule_a", 5), ("rule_b", 1)):
+            for k, v in base.items():
                 r.set_tuning(k, v)
             if ab:
                 r.set_tuning("pt_ctas", 0)
+    if sampling == api.VR_SAMPLING_NEAREST and not quick:
+        for st in ({"steps_per_check": 1}, {"steps_per_check": 3}, {"steps_per_check": 4}, {"rule_a": 3}, {"rule_a": 8}):
+            for k, v in st.items():
+                r.set_tuning(k, v)
+            row = dict(st, sampling="nearest")
+            for cam, (pos, d) in cams.items():
+                row[cam + "_ms"] = measure(r, pos, d, 2)
+            print(json.dumps(row), flush=True)
+            r.set_tuning("steps_per_check", 2); r.set_tuning("rule_a", 5)
     r.close()
