@@ -30,7 +30,8 @@ struct RenderParams {
   // VR_SAMPLING_HW_LINEAR: the step field (vr_quiet.cu) — per voxel cell the SDF byte and one "quiet" bit per octant, 16 bits behind
   // a surface object
   cudaSurfaceObject_t lin_surf;
-  int lin_wf, lin_ws, lin_we;  // k_trace_pt<.., LINEAR>: weights of quiet steps / event tests / event processing in its scheduler
+  int lin_sched;               // k_trace_pt<.., LINEAR>: 0 two loops with leave rules, 1 weighted choice
+  int lin_wf, lin_ws, lin_we;  // its parameters: weights of quiet steps / event tests / event processing
   int spc;                     // k_trace_pt: steps per scheduling decision
   const uchar4* __restrict__ env;
   int env_w, env_h;
@@ -48,7 +49,7 @@ struct RenderParams {
   int seeds[VR_MAX_BATCH];
   unsigned long long* counters;
   int* bbox;  // k_primary: bounding box of the shaded pixels {min x, min y, max x, max y} (may be null)
-  // hybrid schedule: k_trace<QUEUE> appends admitted primary hits here, k_trace_pt runs their secondary paths.
+  // hybrid schedule: k_primary<.., PERFRAME> appends admitted primary hits here, k_trace_pt runs their secondary paths.
   // primary-reuse schedule: k_primary appends ONE record per shaded pixel, k_trace_pt<.., true> runs token admission and the
   // secondary paths for every (record, frame) pair.
   uint4* queue;       // 3 x uint4 per record (HitRecord)
@@ -197,9 +198,13 @@ __device__ __forceinline__ uchar4 env_sample(const RenderParams& p, f3 d) {
   u = u + 0.5f;
   v = v + 0.5f;
   if (LINEAR) {
+    // bilinear with 8 fraction bits: channel * 256 is an integer k <= 65280, recovered exactly by one fma (see tex_value); the
+    // hardware's integer result is floor(k / 256 + 1/2)
     const float4 t = tex2D<float4>(p.env_tex, u, v);
-    return make_uchar4((unsigned char)__double2int_rn((double)t.x * 255.0), (unsigned char)__double2int_rn((double)t.y * 255.0),
-                       (unsigned char)__double2int_rn((double)t.z * 255.0), (unsigned char)__double2int_rn((double)t.w * 255.0));
+    const int kx = __float_as_int(__fmaf_rn(t.x, 65280.0f, 12582912.0f)) - 0x4B400000, ky = __float_as_int(__fmaf_rn(t.y, 65280.0f, 12582912.0f)) - 0x4B400000;
+    const int kz = __float_as_int(__fmaf_rn(t.z, 65280.0f, 12582912.0f)) - 0x4B400000, kw = __float_as_int(__fmaf_rn(t.w, 65280.0f, 12582912.0f)) - 0x4B400000;
+    return make_uchar4((unsigned char)((kx + 128) >> 8), (unsigned char)((ky + 128) >> 8), (unsigned char)((kz + 128) >> 8),
+                       (unsigned char)((kw + 128) >> 8));
   }
   int ix = f2i(floorf(u * (float)p.env_w));
   int iy = f2i(floorf(v * (float)p.env_h));
@@ -252,8 +257,11 @@ __device__ __forceinline__ int march_to_next_event(const RenderParams& p, Ray& r
       if (lin_quiet(cell, r.o, x, y, z)) continue;
       const bool exited = ((x | y | z) < 0) | ((float)nx < r.o.x) | ((float)ny < r.o.y) | ((float)nz < r.o.z);
       if (exited) return EV_EXIT;
-      grad = gradient_linear(p, r.o);                              // get_event_and_value, utility_ray.cl:126-138
+      // get_event_and_value, utility_ray.cl:126-138.  The value first: when no clause can match it, the gradient (six more
+      // fetches) cannot change the verdict
       const int value = vol_linear(p, r.o.x, r.o.y, r.o.z);
+      if (!tf_value_may_match(p.tf, (int)(short)value)) continue;
+      grad = gradient_linear(p, r.o);
       const int clause = tf_match(p.tf, (int)(short)value, f2s(length3(grad)));
       if (clause == 0) continue;
       const vr_tf_rect& q = p.tf.r[clause - 1];
@@ -301,7 +309,7 @@ __device__ __forceinline__ int march_to_next_event(const RenderParams& p, Ray& r
   return EV_NONE;
 }
 
-template <bool COUNT, bool QUEUE, bool LINEAR = false>
+template <bool COUNT, bool LINEAR = false>
 __global__ void __launch_bounds__(128, LINEAR ? 6 : 12) k_trace(const RenderParams p) {
   // one warp = an 8x4 pixel tile: neighbouring primary rays walk neighbouring voxels
   const int x = blockIdx.x * 8 + (threadIdx.x & 7);
@@ -350,25 +358,6 @@ __global__ void __launch_bounds__(128, LINEAR ? 6 : 12) k_trace(const RenderPara
           const int t = (int)atomicAdd(hi, 0x00010000u);
           if ((unsigned)(t >> 16) < (unsigned)p.token_cap) admitted = true;
           else atomicSub(hi, 0x00010000u);
-        }
-      }
-      // hybrid schedule: hand the secondary paths to k_trace_pt; when the queue is full they run inline below
-      if (QUEUE && admitted) {
-        const unsigned m = __activemask();
-        unsigned first = 0;
-        const unsigned lane = threadIdx.x & 31;
-        if (lane == (unsigned)(__ffs(m) - 1)) first = atomicAdd(p.qcount, (unsigned)__popc(m));
-        first = __shfl_sync(m, first, __ffs(m) - 1);
-        const unsigned slot = first + (unsigned)__popc(m & ((1u << lane) - 1u));
-        if (slot < p.qcap) {
-          HitRecord h;
-          h.xy = x | (y << 16); h.seed = seed; h.voxel = (unsigned)voxel; h.clause = colour_clause;
-          h.base = cur.o + cur.d;
-          h.normal = -normalize3_shared_rcp(grad);
-          store_record(p.queue, slot, h);
-          c_adm++;
-          c_normals++;
-          admitted = false;
         }
       }
       if (admitted) {
@@ -436,11 +425,15 @@ __global__ void __launch_bounds__(128, LINEAR ? 6 : 12) k_trace(const RenderPara
 // the shading normal (:42) — depends on the camera only.  A progressive batch (vr_render_frames: n seeds, one camera)
 // therefore evaluates it ONCE per pixel; the n samples of the pixel differ from the token admission (:39) onwards, which
 // k_trace_pt<.., true> runs per (pixel, frame).  Same values as n executions of the reference kernel, 1/n of the work.
-template <bool COUNT, bool LINEAR = false>
+//
+// PERFRAME (hybrid schedule, vr_renderer_set_trace_mode(r, 1)): the same kernel once per pixel AND frame (blockIdx.z = frame), as
+// when the camera moves between frames — nothing is shared between the samples of a pixel.  It then also runs the token
+// admission of its sample (ray_marching.cl:39) and queues admitted hits only; k_trace_pt<.., false> runs their secondary paths.
+template <bool COUNT, bool LINEAR = false, bool PERFRAME = false>
 __global__ void __launch_bounds__(128, LINEAR ? 8 : 12) k_primary(const RenderParams p) {
   const int x = blockIdx.x * 8 + (threadIdx.x & 7);
   const int y = p.row0 + blockIdx.y * 16 + (threadIdx.x >> 3);
-  unsigned c_steps = 0, c_env = 0, c_hits = 0, c_samples = 0;
+  unsigned c_steps = 0, c_env = 0, c_hits = 0, c_samples = 0, c_adm = 0;
   if (x < p.W && y < p.row1 && row_owned(p, y)) {
     c_samples = 1;
     const size_t pix = (size_t)y * p.W + x;
@@ -469,28 +462,42 @@ __global__ void __launch_bounds__(128, LINEAR ? 8 : 12) k_primary(const RenderPa
       const size_t voxel = (size_t)p.vol.nx * p.vol.nz * vy + (size_t)p.vol.nx * vz + vx;
       p.hit[pix] = (uint32_t)voxel;
       c_hits++;
+      bool queue_it = true;
+      if (PERFRAME) {  // atomic_allow_write_max, utility.cl:20-31
+        uint32_t* hi = p.cache + 2 * voxel + 1;
+        queue_it = false;
+        const int w = (int)(short)(__ldcv(hi) >> 16);
+        if (!((unsigned)w > (unsigned)p.token_cap)) {
+          const int t = (int)atomicAdd(hi, 0x00010000u);
+          if ((unsigned)(t >> 16) < (unsigned)p.token_cap) queue_it = true;
+          else atomicSub(hi, 0x00010000u);
+        }
+        if (queue_it) c_adm++;
+      }
+      if (queue_it) {
       const unsigned m = __activemask();
       unsigned first = 0;
       const unsigned lane = threadIdx.x & 31;
       if (lane == (unsigned)(__ffs(m) - 1)) first = atomicAdd(p.qcount, (unsigned)__popc(m));
       first = __shfl_sync(m, first, __ffs(m) - 1);
-      const unsigned slot = first + (unsigned)__popc(m & ((1u << lane) - 1u));  // < W*rows <= qcap
+      const unsigned slot = first + (unsigned)__popc(m & ((1u << lane) - 1u));  // < W*rows(*frames of the launch) <= qcap
       HitRecord h;
-      h.xy = x | (y << 16); h.seed = 0; h.voxel = (unsigned)voxel; h.clause = colour_clause;
+      h.xy = x | (y << 16); h.seed = PERFRAME ? p.seeds[blockIdx.z] : 0; h.voxel = (unsigned)voxel; h.clause = colour_clause;
       h.base = cur.o + cur.d;
       h.normal = -normalize3_shared_rcp(grad);
       store_record(p.queue, slot, h);
-      if (p.bbox) {  // the incremental frame pull copies this box only (vr_api.cu read_frame)
+      if (!PERFRAME && p.bbox) {  // the incremental frame pull copies this box only (vr_api.cu read_frame)
         const int x0 = __reduce_min_sync(m, x), y0 = __reduce_min_sync(m, y), x1 = __reduce_max_sync(m, x), y1 = __reduce_max_sync(m, y);
         if (lane == (unsigned)(__ffs(m) - 1)) {
           atomicMin(p.bbox + 0, x0); atomicMin(p.bbox + 1, y0); atomicMax(p.bbox + 2, x1); atomicMax(p.bbox + 3, y1);
         }
       }
+      }
     }
   }
-  if (COUNT) {  // per-sample counters: the n samples of the pixel each own this primary segment
-    const unsigned n = (unsigned)p.nframes;
-    unsigned v[6] = {c_steps * n, 0u, c_env * n, c_hits * n, 0u, c_samples * n};
+  if (COUNT) {  // per-sample counters: the n samples of the pixel each own this primary segment (PERFRAME: one sample per thread)
+    const unsigned n = PERFRAME ? 1u : (unsigned)p.nframes;
+    unsigned v[6] = {c_steps * n, c_adm, c_env * n, c_hits * n, c_adm, c_samples * n};
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       unsigned s = v[k];
@@ -503,7 +510,7 @@ __global__ void __launch_bounds__(128, LINEAR ? 8 : 12) k_primary(const RenderPa
 // ---- k_trace_pt: the secondary paths (ray_marching.cl:47-76) of the queued primary hits, on persistent warps ------------
 // k_trace gives every pixel a thread for its whole life; with the secondary paths inline a warp runs until its LAST lane
 // is done and ncu shows 12-17 of 32 lanes active per instruction (only the lanes whose primary ray hit do secondary work,
-// 1..3 segments of 1..70 steps each, twice).  In the hybrid schedule k_trace<QUEUE> stops at the admitted primary hit and
+// 1..3 segments of 1..70 steps each, twice).  In the hybrid schedule k_primary<.., PERFRAME> stops at the admitted primary hit and
 // appends a HitRecord; here a lane is a SLOT: warps pull records from the queue, all lanes with a segment in flight step
 // together, and finished segments are processed in batches.  Event processing costs more than stepping (normalisations,
 // the RNG bounce, the env lookup), so (a) the warp leaves the step loop only when the marching lanes are outnumbered 5 : 1, and
@@ -724,11 +731,58 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
           if (exited) ev = EVP_EXIT;
         }
       };
-      // Three kinds of work wait in a warp: quiet steps (cheap: ~25 instructions), event tests (seven filtered fetches + the
-      // transfer function: ~5x) and event processing / refills outside this region (normalisations, RNG bounce, environment
-      // lookup: ~10x).  Every round the warp does the kind whose lane count, weighted by how cheap the kind is, is largest: cheap
-      // work may run with few lanes, expensive work waits until enough lanes want it (ncu on the first version, which ran the
-      // event tests whenever the quiet-step loop paused: 2.8 of 32 lanes active in the test code).
+      // get_event_and_value (utility_ray.cl:126-138) where an event is possible.  The value first: when no clause can match
+      // it, the gradient (six more fetches) cannot change the verdict.
+      auto event_test = [&]() {
+        const int value = vol_linear(p, o.x, o.y, o.z);
+        int clause = 0;
+        if (tf_value_may_match(p.tf, (int)(short)value)) {
+          const f3 grad = gradient_linear(p, o);
+          clause = tf_match(p.tf, (int)(short)value, f2s(length3(grad)));
+          if (clause != 0) hgrad = grad;
+        }
+        if (clause != 0) {
+          if (!(p.tf.r[clause - 1].flags & VR_TF_THRESHOLD)) clause_col = clause;
+          ev = EVP_HIT;
+          pending = false;
+        } else if (steps_left == 0) {
+          ev = EVP_NONE;
+          pending = false;
+        } else {
+          advance();
+        }
+      };
+      if (p.lin_sched == 0) {
+        // Two loops: quiet steps until the lanes that still step are outnumbered (lin_wf : 1), then event tests until the
+        // pending lanes are (lin_ws : 1); the region is left when the lanes waiting outside outnumber the rest (rule_a : rule_b).
+        for (;;) {
+          for (;;) {
+            for (int u = 0; u < p.spc; ++u)
+              if (marching) advance();
+            const unsigned act = __ballot_sync(0xffffffffu, marching);
+            if (!act) break;
+            const unsigned others = __ballot_sync(0xffffffffu, !marching && (pending || mode != M_IDLE || !exhausted));
+            if (__popc(act) * p.lin_wf < __popc(others)) break;
+          }
+          for (;;) {
+            if (!__ballot_sync(0xffffffffu, pending)) break;
+            if (pending) event_test();
+            const unsigned pend = __ballot_sync(0xffffffffu, pending);
+            if (!pend) break;
+            const unsigned others = __ballot_sync(0xffffffffu, !pending && (marching || mode != M_IDLE || !exhausted));
+            if (__popc(pend) * p.lin_ws < __popc(others)) break;
+          }
+          const unsigned go = __ballot_sync(0xffffffffu, marching || pending);
+          if (!go) break;
+          const unsigned waiting = __ballot_sync(0xffffffffu, !marching && !pending && (mode != M_IDLE || !exhausted));
+          if (__popc(go) * p.lin_we < __popc(waiting)) break;
+        }
+        continue;
+      }
+      // Weighted choice (lin_sched 1).  Three kinds of work wait in a warp: quiet steps (cheap), event tests (1 to 7 filtered
+      // fetches + the transfer function) and event processing / refills outside this region (normalisations, RNG bounce,
+      // environment lookup).  Every round the warp does the kind whose lane count times its weight is largest: cheap work may
+      // run with few lanes, expensive work waits until enough lanes want it.
       for (;;) {
         const unsigned mF = __ballot_sync(0xffffffffu, marching), mS = __ballot_sync(0xffffffffu, pending);
         if (!(mF | mS)) break;
@@ -738,23 +792,7 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
           for (int u = 0; u < p.spc; ++u)
             if (marching) advance();
         } else if (S >= E) {
-          // get_event_and_value (utility_ray.cl:126-138) where an event is possible
-          if (pending) {
-            const f3 grad = gradient_linear(p, o);
-            const int value = vol_linear(p, o.x, o.y, o.z);
-            const int clause = tf_match(p.tf, (int)(short)value, f2s(length3(grad)));
-            if (clause != 0) {
-              if (!(p.tf.r[clause - 1].flags & VR_TF_THRESHOLD)) clause_col = clause;
-              hgrad = grad;
-              ev = EVP_HIT;
-              pending = false;
-            } else if (steps_left == 0) {
-              ev = EVP_NONE;
-              pending = false;
-            } else {
-              advance();
-            }
-          }
+          if (pending) event_test();
         } else {
           break;
         }
@@ -917,14 +955,15 @@ static int launch_trace(vr_renderer* r, RenderParams& p, const float pos[3], con
   dim3 grid(div_up(r->W, 8), div_up(rows, 16), nframes);
   if (r->trace_mode == 0) {  // one thread per pixel and frame for its whole life
     r->primary_valid = false;
-    k_trace<COUNT, false, LINEAR><<<grid, 128, 0, ctx->stream>>>(p);
+    k_trace<COUNT, LINEAR><<<grid, 128, 0, ctx->stream>>>(p);
     ctx->launches++;
     return VR_OK;
   }
-  // mode 1 (hybrid): dense thread-per-pixel k_trace per frame queues admitted hits, persistent warps run their secondary paths
+  // mode 1 (hybrid): k_primary per pixel and frame (primary march + token admission) queues the admitted hits, persistent warps
+  //                  run their secondary paths
   // mode 2 (primary reuse, default): k_primary once per pixel, persistent warps run admission + secondary paths per (pixel, frame)
   const bool reuse = r->trace_mode == 2;
-  const size_t cap = reuse ? (size_t)r->W * rows : std::min<size_t>(pixels, (size_t)32 << 20);
+  const size_t cap = reuse ? (size_t)r->W * rows : std::max<size_t>((size_t)r->W * rows, std::min<size_t>(pixels, (size_t)32 << 20));
   if (r->queue_cap < cap) {
     if (r->queue) VR_CUDA(cudaFreeAsync(r->queue, ctx->stream));
     r->queue = nullptr; r->queue_cap = 0;
@@ -936,11 +975,21 @@ static int launch_trace(vr_renderer* r, RenderParams& p, const float pos[3], con
   p.qcap = (unsigned)r->queue_cap;
   p.qcount = reinterpret_cast<unsigned*>(r->counters + 6);
   if (!reuse) {
+    // as many frames per launch pair as the queue can hold if every pixel were shaded: the queue never overflows
     r->primary_valid = false;
-    VR_CUDA(cudaMemsetAsync(p.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
-    k_trace<COUNT, true, LINEAR><<<grid, 128, 0, ctx->stream>>>(p);
-    ctx->launches++;
-    return launch_pt_select<COUNT, false, LINEAR>(r, p, p.qcount + 1);
+    const int fps = (int)std::max<size_t>(1, r->queue_cap / ((size_t)r->W * rows));
+    RenderParams q = p;
+    for (int f0 = 0; f0 < nframes; f0 += fps) {
+      const int nb = std::min(fps, nframes - f0);
+      q.nframes = nb;
+      for (int k = 0; k < nb; ++k) q.seeds[k] = p.seeds[f0 + k];
+      VR_CUDA(cudaMemsetAsync(q.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
+      dim3 gq(div_up(r->W, 8), div_up(rows, 16), nb);
+      k_primary<COUNT, LINEAR, true><<<gq, 128, 0, ctx->stream>>>(q);
+      ctx->launches++;
+      VR_TRY((launch_pt_select<COUNT, false, LINEAR>(r, q, q.qcount + 1)));
+    }
+    return VR_OK;
   }
   // The records stay valid while camera, rows and scene are unchanged.  Within one call they are always reused; across
   // calls only on request (vr_renderer_set_primary_reuse(r, 2): the frame_emitter loop calls render_frame once per
@@ -1018,6 +1067,7 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     p.nframes = nframes;
     p.pixel_major = r->tune.pixel_major;
     p.rule_a = r->tune.rule[0]; p.rule_b = r->tune.rule[1];
+    p.lin_sched = r->tune.lin_sched;
     p.lin_wf = r->tune.lin_w[0]; p.lin_ws = r->tune.lin_w[1]; p.lin_we = r->tune.lin_w[2];
     p.spc = r->tune.spc;
     for (int k = 0; k < nframes; ++k) p.seeds[k] = seeds[k];

@@ -309,8 +309,8 @@ int vr_renderer_set_primary_reuse(vr_renderer* r, int level);
 int vr_renderer_enable_timing(vr_renderer* r, int enable);
 int vr_renderer_kernel_times(vr_renderer* r, double out_ms[2], int* n_frames, int reset);
 /* Schedule tuning of the persistent-warp tracer; never changes a result.  Keys: "pixel_major" (items per pixel group, 0 =
- * frame-major), "rule_a"/"rule_b" (leave the march region when marching*a < waiting*b), "steps_per_check", "lin_w_fast" /
- * "lin_w_slow" / "lin_w_event" (weights of the three kinds of work in the hw-linear scheduler), "pt_ctas" (register budget;
+ * frame-major), "rule_a"/"rule_b" (leave the march region when marching*a < waiting*b), "steps_per_check", "lin_sched" (hw-linear
+ * march region: 0 two loops with leave rules, 1 weighted choice per round) with "lin_w_fast" / "lin_w_slow" / "lin_w_event", "pt_ctas" (register budget;
  * only in the A/B build, tools/ab). */
 int vr_renderer_set_tuning(vr_renderer* r, const char* key, int value);
 /* hw-linear step field: the quiet-octant byte of every voxel cell, x fastest (tests: equals the oracle's orc_quiet_cells) */

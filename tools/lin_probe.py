@@ -48,15 +48,16 @@ for sampling, name in ((api.VR_SAMPLING_NEAREST, "nearest"), (api.VR_SAMPLING_HW
     r.set_trace_mode(2)
     if sampling == api.VR_SAMPLING_HW_LINEAR and not quick:
         settings = []
-        for w in ((4, 2, 1), (8, 2, 1), (4, 1, 1), (8, 4, 1), (2, 1, 1), (6, 3, 1), (4, 3, 1), (8, 3, 2), (16, 4, 1), (3, 2, 1), (2, 2, 1), (16, 8, 1),
-                  (8, 1, 1), (12, 3, 1)):
-            settings.append({"lin_w_fast": w[0], "lin_w_slow": w[1], "lin_w_event": w[2]})
+        for w in ((4, 2, 2), (4, 1, 2), (8, 2, 2), (2, 2, 2), (4, 2, 1), (4, 2, 3), (4, 4, 2), (6, 2, 2), (3, 2, 2), (4, 2, 5)):
+            settings.append({"lin_sched": 0, "lin_w_fast": w[0], "lin_w_slow": w[1], "lin_w_event": w[2]})
+        for w in ((4, 3, 1), (2, 2, 1), (4, 2, 1), (3, 2, 1), (3, 3, 1), (4, 4, 1), (2, 3, 1), (6, 4, 1)):
+            settings.append({"lin_sched": 1, "lin_w_fast": w[0], "lin_w_slow": w[1], "lin_w_event": w[2]})
         for spc in (1, 3, 4):
             settings.append({"steps_per_check": spc})
         if ab:
             for c in (6, 10, 12):
                 settings.append({"pt_ctas": c})
-        base = {"lin_w_fast": 4, "lin_w_slow": 2, "lin_w_event": 1, "steps_per_check": 2}
+        base = {"lin_sched": 0, "lin_w_fast": 4, "lin_w_slow": 2, "lin_w_event": 2, "steps_per_check": 2}
         for st in settings:
             for k, v in st.items():
                 r.set_tuning(k, v)
