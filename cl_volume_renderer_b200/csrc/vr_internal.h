@@ -144,8 +144,8 @@ struct vr_renderer {
     int pixel_major = 1;               // k_trace_pt<.., REUSE> item order: groups of this many pixels x all frames (0: frame-major)
     int rule[2] = {5, 1};              // k_trace_pt leaves its march region when marching lanes * rule[0] < waiting lanes * rule[1]
     int lin_sched = 0;                 // hw-linear: 0 quiet-step loop + event-test loop with leave rules, 1 weighted choice per round
-    int lin_w[3] = {4, 2, 2};          // their parameters (quiet steps / event tests / event processing)
-    int spc = 2;                       // steps per scheduling decision of k_trace_pt
+    int lin_w[3] = {3, 2, 2};          // their parameters (quiet steps / event tests / event processing)
+    int spc = 4;                       // steps per scheduling decision of k_trace_pt
     int pt_ctas = 0;                   // -DVR_AB builds only: register budget variant of k_trace_pt
   } tune;
   // Which cache entries can be non-zero: 0 none (just reset), 1 only cache[hit[pix]] of the current `hit` buffer (every trace

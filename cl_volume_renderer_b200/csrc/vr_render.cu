@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(128, LINEAR ? 6 : 12) k_trace(const RenderPara
 // when the camera moves between frames — nothing is shared between the samples of a pixel.  It then also runs the token
 // admission of its sample (ray_marching.cl:39) and queues admitted hits only; k_trace_pt<.., false> runs their secondary paths.
 template <bool COUNT, bool LINEAR = false, bool PERFRAME = false>
-__global__ void __launch_bounds__(128, LINEAR ? 8 : 12) k_primary(const RenderParams p) {
+__global__ void __launch_bounds__(128, 12) k_primary(const RenderParams p) {
   const int x = blockIdx.x * 8 + (threadIdx.x & 7);
   const int y = p.row0 + blockIdx.y * 16 + (threadIdx.x >> 3);
   unsigned c_steps = 0, c_env = 0, c_hits = 0, c_samples = 0, c_adm = 0;
@@ -464,6 +464,10 @@ __global__ void __launch_bounds__(128, LINEAR ? 8 : 12) k_primary(const RenderPa
       c_hits++;
       bool queue_it = true;
       if (PERFRAME) {  // atomic_allow_write_max, utility.cl:20-31
+        if (blockIdx.z == 0) {  // hits of one frame: sizes the launches of the call's other frames (launch_trace)
+          const unsigned mh = __activemask();
+          if ((threadIdx.x & 31) == (unsigned)(__ffs(mh) - 1)) atomicAdd(p.qcount + 2, (unsigned)__popc(mh));
+        }
         uint32_t* hi = p.cache + 2 * voxel + 1;
         queue_it = false;
         const int w = (int)(short)(__ldcv(hi) >> 16);
@@ -975,18 +979,26 @@ static int launch_trace(vr_renderer* r, RenderParams& p, const float pos[3], con
   p.qcap = (unsigned)r->queue_cap;
   p.qcount = reinterpret_cast<unsigned*>(r->counters + 6);
   if (!reuse) {
-    // as many frames per launch pair as the queue can hold if every pixel were shaded: the queue never overflows
+    // The queue never overflows: the primary hits of a call's frames are the same pixels (one camera), so the first frame runs
+    // alone, its hit count h is read back (one 4-byte transfer per call), and the other frames go h-sized per launch pair.
     r->primary_valid = false;
-    const int fps = (int)std::max<size_t>(1, r->queue_cap / ((size_t)r->W * rows));
     RenderParams q = p;
+    unsigned* hits = p.qcount + 2;  // word [2] of the renderer's spare counter pair
+    int fps = 1;
     for (int f0 = 0; f0 < nframes; f0 += fps) {
       const int nb = std::min(fps, nframes - f0);
       q.nframes = nb;
       for (int k = 0; k < nb; ++k) q.seeds[k] = p.seeds[f0 + k];
-      VR_CUDA(cudaMemsetAsync(q.qcount, 0, 2 * sizeof(unsigned), ctx->stream));
+      VR_CUDA(cudaMemsetAsync(q.qcount, 0, 3 * sizeof(unsigned), ctx->stream));
       dim3 gq(div_up(r->W, 8), div_up(rows, 16), nb);
       k_primary<COUNT, LINEAR, true><<<gq, 128, 0, ctx->stream>>>(q);
       ctx->launches++;
+      if (f0 == 0 && nframes > 1) {
+        unsigned* pin = reinterpret_cast<unsigned*>(ctx->scratch_host) + 16;
+        VR_CUDA(cudaMemcpyAsync(pin, hits, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        VR_CUDA(cudaStreamSynchronize(ctx->stream));
+        fps = (int)std::min<size_t>(VR_MAX_BATCH, std::max<size_t>(1, r->queue_cap / std::max<size_t>(*pin, 1)));
+      }
       VR_TRY((launch_pt_select<COUNT, false, LINEAR>(r, q, q.qcount + 1)));
     }
     return VR_OK;

@@ -23,6 +23,14 @@ def run(n):
     vol.clip((8, 8, 8), (n - 8, n - 8, n - 8))                     # k_clip
     vol2 = api.Volume(ctx, synth.synth_ct(n))
     vol2.filter()                                                  # k_bilateral
+    vol2.set_sampling(api.VR_SAMPLING_HW_LINEAR)                   # k_boxavg, k_fetch_stats_v8<LINEAR>
+    vol2.set_value_clip(-2000, 3000); vol2.set_gradient_clip(0, 4000)
+    r2 = api.Renderer(ctx, W, H); r2.set_sampling(api.VR_SAMPLING_HW_LINEAR); r2.image_set(vol2, env); r2.set_tf(synth.default_tf())
+    r2.flush_changes()                                             # k_lin_field
+    r2.render_tf(500, 500)                                         # k_histogram_v8<LINEAR>
+    r2.render_frames(pos, d, synth.glibc_rand(16), readback=False) # LINEAR k_primary / k_trace_pt
+    r2.close()
+    vol2.filter()                                                  # k_bilateral on the box-averaged volume
     ctx.synchronize()
     print("done")
 
@@ -33,12 +41,13 @@ def report(path, n):
     agg = collections.OrderedDict()
     for r in rows[hi + 1:]:
         if len(r) <= vi: continue
-        k = r[ki].split('(')[0].replace('void ', ''); v = float(r[vi].replace(',', ''))
+        k = r[ki].split('(')[0].replace('void ', '').split('<')[0]; v = float(r[vi].replace(',', ''))
         v = v / 1e3 if r[ui] == 'ns' else (v * 1e3 if r[ui] == 'ms' else v)
         a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v
     N = n ** 3; Nc = (n - 16) ** 3
     alg = {'k_fetch_stats_v8': 2 * N, 'k_fetch_stats': 2 * N, 'k_cache_reset': 8 * N, 'k_sdf_base': 3 * N, 'k_histogram_v8': 2 * N + 4 * 250000,
-           'k_histogram': 2 * N + 4 * 250000, 'k_sdf_unbrick': 2 * N, 'k_clip': 4 * Nc, 'k_bilateral': 4 * N, 'k_tf_color_frame_ranked': 8 * 250000}
+           'k_histogram': 2 * N + 4 * 250000, 'k_sdf_unbrick': 2 * N, 'k_clip': 4 * Nc, 'k_bilateral': 4 * N, 'k_tf_color_frame_ranked': 8 * 250000,
+           'k_boxavg': 4 * N, 'k_lin_field': 5 * N, 'k_sdf_events_v8': 2 * N + N // 8, 'k_sdf_assemble': N + N, 'k_sdf_band_bits': 3 * N // 8}
     out = {}
     for k, (cnt, us) in agg.items():
         b = alg.get(k)
