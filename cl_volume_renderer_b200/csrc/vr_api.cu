@@ -1135,6 +1135,7 @@ extern "C" int vr_renderer_set_tuning(vr_renderer* r, const char* key, int value
   if (!strcmp(key, "pixel_major")) { VR_REQUIRE(value >= 0 && value <= 4096, "pixel_major out of range"); t.pixel_major = value; }
   else if (!strcmp(key, "rule_a")) { VR_REQUIRE(value >= 1 && value <= 1024, "rule_a out of range"); t.rule[0] = value; }
   else if (!strcmp(key, "rule_b")) { VR_REQUIRE(value >= 1 && value <= 1024, "rule_b out of range"); t.rule[1] = value; }
+  else if (!strcmp(key, "surf")) { VR_REQUIRE(value == 0 || value == 1, "surf must be 0 or 1"); t.surf = value; }
   else if (!strcmp(key, "lin_sched")) { VR_REQUIRE(value == 0 || value == 1, "lin_sched must be 0 or 1"); t.lin_sched = value; }
   else if (!strcmp(key, "lin_w_fast")) { VR_REQUIRE(value >= 1 && value <= 1024, "lin_w_fast out of range"); t.lin_w[0] = value; }
   else if (!strcmp(key, "lin_w_slow")) { VR_REQUIRE(value >= 1 && value <= 1024, "lin_w_slow out of range"); t.lin_w[1] = value; }

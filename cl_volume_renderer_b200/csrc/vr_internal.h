@@ -146,6 +146,7 @@ struct vr_renderer {
     int lin_sched = 0;                 // hw-linear: 0 quiet-step loop + event-test loop with leave rules, 1 weighted choice per round
     int lin_w[3] = {3, 2, 2};          // their parameters (quiet steps / event tests / event processing)
     int spc = 4;                       // steps per scheduling decision of k_trace_pt
+    int surf = 1;                      // NEAREST k_trace_pt gathers the SDF through the surface object (0: bricked field, __ldg)
     int pt_ctas = 0;                   // -DVR_AB builds only: register budget variant of k_trace_pt
   } tune;
   // Which cache entries can be non-zero: 0 none (just reset), 1 only cache[hit[pix]] of the current `hit` buffer (every trace

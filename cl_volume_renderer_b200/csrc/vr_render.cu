@@ -936,7 +936,7 @@ static int launch_pt_select(vr_renderer* r, const RenderParams& p, unsigned* wc)
 #endif
     return launch_pt<COUNT, REUSE, 8, true, true>(ctx, p, wc);
   }
-  const bool surf = REUSE && !COUNT && r->sdf->surf != 0;  // the surface-object gather serves the production schedule
+  const bool surf = REUSE && !COUNT && r->sdf->surf != 0 && r->tune.surf;  // the surface-object gather serves the production schedule
 #ifdef VR_AB
   if (REUSE && !COUNT) {
     const int c = r->tune.pt_ctas;
@@ -985,8 +985,8 @@ static int launch_trace(vr_renderer* r, RenderParams& p, const float pos[3], con
     RenderParams q = p;
     unsigned* hits = p.qcount + 2;  // word [2] of the renderer's spare counter pair
     int fps = 1;
-    for (int f0 = 0; f0 < nframes; f0 += fps) {
-      const int nb = std::min(fps, nframes - f0);
+    for (int f0 = 0, nb = 0; f0 < nframes; f0 += nb) {
+      nb = std::min(fps, nframes - f0);
       q.nframes = nb;
       for (int k = 0; k < nb; ++k) q.seeds[k] = p.seeds[f0 + k];
       VR_CUDA(cudaMemsetAsync(q.qcount, 0, 3 * sizeof(unsigned), ctx->stream));

@@ -15,10 +15,10 @@ W, H = 1920, 1080
 ctx = api.Context(0)
 vol = api.Volume(ctx, synth.synth_ct(n)); env = api.EnvMap(ctx, synth.synth_env(2048, 1024))
 seeds = synth.glibc_rand(64 * 3)
-for sampling, name in ((api.VR_SAMPLING_NEAREST, "nearest"), (api.VR_SAMPLING_HW_LINEAR, "hw_linear")):
+for sampling, name, surf in ((api.VR_SAMPLING_NEAREST, "nearest", 1), (api.VR_SAMPLING_NEAREST, "nearest_bricked_ldg", 0), (api.VR_SAMPLING_HW_LINEAR, "hw_linear", 1)):
     for cam, (pos, d) in (("default", synth.default_camera(n)), ("closeup", synth.closeup_camera(n))):
         r = api.Renderer(ctx, W, H)
-        r.set_sampling(sampling); r.set_primary_reuse(2)
+        r.set_sampling(sampling); r.set_primary_reuse(2); r.set_tuning("surf", surf)
         r.image_set(vol, env); r.set_tf(synth.default_tf()); r.flush_changes()
         hf = r.host_frame()
         other = np.empty((H, W, 4), np.uint8)
