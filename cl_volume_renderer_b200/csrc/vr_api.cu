@@ -40,18 +40,20 @@ static void pinned_release(vr_ctx* ctx, void* p) {
     if (b.p == p) b.in_use = false;
 }
 
-// 3-D CUDA arrays behind surface objects, recycled by (size, bits).  Releasing keeps at most two unused arrays (the flush
-// builds the fresh SDF before it lets go of the old one, so two of a size are the steady state); older ones are freed, so a
-// session that walks through many clip boxes does not accumulate an array per size.
+// 3-D CUDA arrays (SDF surface, hw-linear step field and volume texture), recycled by (size, kind).  Releasing keeps at most four
+// unused arrays (the flush builds the fresh SDF before it lets go of the old one; a hw-linear renderer holds three kinds);
+// older ones are freed, so a session that walks through many clip boxes does not accumulate an array per size.
 int array3d_acquire(vr_ctx* ctx, int nx, int ny, int nz, int bits, cudaArray_t* arr, cudaSurfaceObject_t* surf) {
   for (auto& a : ctx->arrays3d)
     if (!a.in_use && a.nx == nx && a.ny == ny && a.nz == nz && a.bits == bits) { a.in_use = true; *arr = a.arr; *surf = a.surf; return VR_OK; }
+  // bits: 8 = int8 + surface (SDF), 16 = uint16 + surface (hw-linear step field), 17 = int16, texture only (hw-linear volume copy)
   cudaChannelFormatDesc desc = bits == 8 ? cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindSigned)
-                                         : cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
+                               : (bits == 16 ? cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned)
+                                             : cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindSigned));
   cudaArray_t a = nullptr;
   cudaSurfaceObject_t so = 0;
-  cudaError_t e = cudaMalloc3DArray(&a, &desc, make_cudaExtent(nx, ny, nz), cudaArraySurfaceLoadStore);
-  if (e == cudaSuccess) {
+  cudaError_t e = cudaMalloc3DArray(&a, &desc, make_cudaExtent(nx, ny, nz), bits == 17 ? cudaArrayDefault : cudaArraySurfaceLoadStore);
+  if (e == cudaSuccess && bits != 17) {
     cudaResourceDesc rd{};
     rd.resType = cudaResourceTypeArray;
     rd.res.array.array = a;
@@ -77,9 +79,9 @@ void array3d_release(vr_ctx* ctx, cudaArray_t arr) {
         ++unused;
         if (oldest < 0 || ctx->arrays3d[i].released < ctx->arrays3d[oldest].released) oldest = (int)i;
       }
-    if (unused <= 2) break;
+    if (unused <= 4) break;
     cudaStreamSynchronize(ctx->stream);
-    cudaDestroySurfaceObject(ctx->arrays3d[oldest].surf);
+    if (ctx->arrays3d[oldest].surf) cudaDestroySurfaceObject(ctx->arrays3d[oldest].surf);
     cudaFreeArray(ctx->arrays3d[oldest].arr);
     ctx->arrays3d.erase(ctx->arrays3d.begin() + oldest);
   }
@@ -136,7 +138,7 @@ extern "C" void vr_ctx_destroy(vr_ctx* c) {
   if (c->scratch) cudaFree(c->scratch);
   if (c->scratch_host) cudaFreeHost(c->scratch_host);
   for (auto& b : c->pinned) cudaFreeHost(b.p);
-  for (auto& a : c->arrays3d) { cudaDestroySurfaceObject(a.surf); cudaFreeArray(a.arr); }
+  for (auto& a : c->arrays3d) { if (a.surf) cudaDestroySurfaceObject(a.surf); cudaFreeArray(a.arr); }
   vr_comm_release(c);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -615,7 +617,7 @@ static void release_textures(vr_renderer* r) {
   r->lin_arr = nullptr; r->lin_surf = 0;
   if (r->vol_tex) cudaDestroyTextureObject(r->vol_tex);
   if (r->env_tex) cudaDestroyTextureObject(r->env_tex);
-  if (r->vol_arr) cudaFreeArray(r->vol_arr);
+  array3d_release(r->ctx, r->vol_arr);  // back to the context's cache: a renderer created for the next job of the same size reuses it
   if (r->env_arr) cudaFreeArray(r->env_arr);
   r->vol_tex = r->env_tex = 0;
   r->vol_arr = r->env_arr = nullptr;
@@ -634,8 +636,8 @@ static int build_textures(vr_renderer* r) {
   int st = VR_OK;
   cudaError_t e = cudaSuccess;
   if (!same) {
-    cudaChannelFormatDesc d16 = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindSigned);
-    e = cudaMalloc3DArray(&r->vol_arr, &d16, make_cudaExtent(v->nx, v->ny, v->nz));
+    cudaSurfaceObject_t none = 0;
+    if (array3d_acquire(ctx, v->nx, v->ny, v->nz, 17, &r->vol_arr, &none) != VR_OK) { release_textures(r); return VR_ERR_CUDA; }
   }
   if (e == cudaSuccess) {
     cudaMemcpy3DParms p{};
@@ -836,7 +838,7 @@ static int read_frame(vr_renderer* r, uint8_t* host_rgba) {
   }
   VR_CUDA(cudaMemcpyAsync(host_rgba, r->frame, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost, ctx->stream));
   VR_CUDA(cudaStreamSynchronize(ctx->stream));  // also completes the bounding-box transfer of the k_primary before it
-  if (own) r->host_epoch = (r->primary_valid && r->trace_mode == 2 && r->row0 == 0 && r->row1 == r->H) ? r->primary_epoch : 0;
+  if (own) r->host_epoch = (r->primary_valid && r->trace_mode >= 2 && r->row0 == 0 && r->row1 == r->H) ? r->primary_epoch : 0;
   return VR_OK;
 }
 
@@ -980,7 +982,11 @@ extern "C" int vr_renderer_set_token_cap(vr_renderer* r, int cap) {
 }
 
 extern "C" int vr_renderer_set_trace_mode(vr_renderer* r, int mode) {
+#ifdef VR_AB
+  VR_REQUIRE(r && mode >= 0 && mode <= 3, "vr_renderer_set_trace_mode: mode must be 0, 1, 2 (or 3 in this A/B build)");
+#else
   VR_REQUIRE(r && mode >= 0 && mode <= 2, "vr_renderer_set_trace_mode: mode must be 0, 1 or 2");
+#endif
   r->trace_mode = mode;
   r->primary_valid = false;
   return VR_OK;
@@ -1135,6 +1141,8 @@ extern "C" int vr_renderer_set_tuning(vr_renderer* r, const char* key, int value
   if (!strcmp(key, "pixel_major")) { VR_REQUIRE(value >= 0 && value <= 4096, "pixel_major out of range"); t.pixel_major = value; }
   else if (!strcmp(key, "rule_a")) { VR_REQUIRE(value >= 1 && value <= 1024, "rule_a out of range"); t.rule[0] = value; }
   else if (!strcmp(key, "rule_b")) { VR_REQUIRE(value >= 1 && value <= 1024, "rule_b out of range"); t.rule[1] = value; }
+  else if (!strcmp(key, "sm_k")) { VR_REQUIRE(value >= 1 && value <= 70, "sm_k out of range"); t.sm_k = value; }
+  else if (!strcmp(key, "sm_leave")) { VR_REQUIRE(value >= 0 && value <= 32, "sm_leave out of range"); t.sm_leave = value; }
   else if (!strcmp(key, "surf")) { VR_REQUIRE(value == 0 || value == 1, "surf must be 0 or 1"); t.surf = value; }
   else if (!strcmp(key, "lin_sched")) { VR_REQUIRE(value == 0 || value == 1, "lin_sched must be 0 or 1"); t.lin_sched = value; }
   else if (!strcmp(key, "lin_w_fast")) { VR_REQUIRE(value >= 1 && value <= 1024, "lin_w_fast out of range"); t.lin_w[0] = value; }

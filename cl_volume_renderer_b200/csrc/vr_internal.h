@@ -46,7 +46,7 @@ struct vr_ctx {
   struct PinnedBuf { void* p; size_t bytes; bool in_use; };
   std::vector<PinnedBuf> pinned;
   // 3-D arrays (+ surface objects) of the SDF (8 bits per voxel) and of the hw-linear step field (16 bits) are recycled by size
-  // as well: cudaMalloc3DArray / cudaFreeArray synchronise.  At most two unused arrays are kept (array3d_release).
+  // as well: cudaMalloc3DArray / cudaFreeArray synchronise.  At most four unused arrays are kept (array3d_release).
   struct Array3D { cudaArray_t arr; cudaSurfaceObject_t surf; int nx, ny, nz, bits; bool in_use; uint64_t released; };
   std::vector<Array3D> arrays3d;
   uint64_t array_clock = 0;
@@ -146,6 +146,7 @@ struct vr_renderer {
     int lin_sched = 0;                 // hw-linear: 0 quiet-step loop + event-test loop with leave rules, 1 weighted choice per round
     int lin_w[3] = {3, 2, 2};          // their parameters (quiet steps / event tests / event processing)
     int spc = 4;                       // steps per scheduling decision of k_trace_pt
+    int sm_k = 16, sm_leave = 16;      // k_trace_sm (trace mode 3): steps per visit of a marching batch, early-stop threshold
     int surf = 1;                      // NEAREST k_trace_pt gathers the SDF through the surface object (0: bricked field, __ldg)
     int pt_ctas = 0;                   // -DVR_AB builds only: register budget variant of k_trace_pt
   } tune;
@@ -159,7 +160,8 @@ struct vr_renderer {
   bool count = false;
   unsigned long long* counters = nullptr;  // 6 x u64 on device (+ 2 spare words: [6] is k_trace_pt's work counter)
   // 0: k_trace alone (a thread per pixel for its whole life), 1: hybrid k_trace + k_trace_pt per frame,
-  // 2 (default): k_primary once per pixel and call + k_trace_pt per (pixel, frame)
+  // 2 (default): k_primary once per pixel and call + k_trace_pt per (pixel, frame); 3: the same with k_trace_sm (slots in
+  // shared memory, packed batches)
   int trace_mode = 2;
   bool primary_valid = false;         // r->queue holds the primary records of (primary_pos, primary_dir, primary_rows)
   bool primary_across_calls = false;  // vr_renderer_set_primary_reuse(r, 2)

@@ -33,6 +33,7 @@ struct RenderParams {
   int lin_sched;               // k_trace_pt<.., LINEAR>: 0 two loops with leave rules, 1 weighted choice
   int lin_wf, lin_ws, lin_we;  // its parameters: weights of quiet steps / event tests / event processing
   int spc;                     // k_trace_pt: steps per scheduling decision
+  int sm_k, sm_leave;          // k_trace_sm: steps per visit of a marching batch; a batch stops early below this many marching lanes
   const uchar4* __restrict__ env;
   int env_w, env_h;
   uint32_t* __restrict__ cache;
@@ -857,6 +858,379 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
   }
 }
 
+#ifdef VR_AB
+// ---- k_trace_sm: the same secondary paths with the slots in SHARED memory and every kind of work packed -------------------------
+// k_trace_pt keeps a sample in one lane for its whole life, so a lane whose segment ended is dead weight in the step loop until
+// the warp leaves it, and event processing runs with whatever lanes happen to wait (ncu: 15-20 of 32 lanes active in the step
+// loop, the kernel issue-bound).  Here a CTA owns SM_SLOTS sample slots in shared memory and three lists of slot numbers —
+// slots whose segment ended or that are free (E), slots that march (M), and, under hw-linear sampling, slots that stand at a
+// position where the event test must be evaluated (P).  A round processes every list of the current generation in batches of 32
+// CONSECUTIVE list entries per warp — a batch is all events, all marching or all tests, so its lanes do the same thing — and
+// appends each slot to the list of the next generation it now belongs to: marching lanes that end their segment go to E, the
+// others back to M after at most sm_k steps (a batch stops early when fewer than sm_leave of its lanes still march), events
+// that started a segment go to M, free slots that found no admitted sample return to E.  Two __syncthreads per round; what
+// a sample computes is unchanged.
+// MEASURED AND NOT ADOPTED (profiles/r2e_trace_sm_probe.jsonl): parity-green in every test, but 4.1-4.5 ms per 64-frame step
+// against k_trace_pt's 2.02 (hw-linear 5.4-5.7 against 3.3).  The premise was wrong: the SDF makes segments so short (about 6
+// steps) that marching is ~10 % of k_trace_pt's instructions; the rest is event processing, which k_trace_pt already runs in
+// batches of ~24 lanes, and here pays a round trip of the slot state through shared memory plus two barriers per round.
+// Compiled into the A/B build only (-DVR_AB, vr_renderer_set_trace_mode(r, 3)).
+#define SM_SLOTS 512
+#define SM_THREADS 256
+enum { SMW_OX = 0, SMW_OY, SMW_OZ, SMW_DX, SMW_DY, SMW_DZ, SMW_PK, SMW_ATT, SMW_ER, SMW_EG, SMW_EB, SMW_BVP, SMW_REC, SMW_SEED, SMW_XYP,
+       SMW_WORDS_NEAREST, SMW_GX = SMW_WORDS_NEAREST, SMW_GY, SMW_GZ, SMW_WORDS_LINEAR };
+enum { SML_E = 0, SML_M = 1, SML_P = 2 };
+static size_t sm_trace_smem_bytes(bool linear) {
+  return (size_t)(linear ? SMW_WORDS_LINEAR : SMW_WORDS_NEAREST) * SM_SLOTS * 4 + (size_t)2 * 3 * SM_SLOTS * 2;
+}
+
+template <bool COUNT, bool REUSE, bool LINEAR>
+__global__ void __launch_bounds__(SM_THREADS, LINEAR ? 4 : 6) k_trace_sm(const RenderParams p, unsigned* __restrict__ work_counter) {
+  extern __shared__ uint32_t sm_dyn[];
+  constexpr int NW = LINEAR ? SMW_WORDS_LINEAR : SMW_WORDS_NEAREST;
+  uint32_t* st = sm_dyn;                                                          // [NW][SM_SLOTS]
+  unsigned short* lists = reinterpret_cast<unsigned short*>(sm_dyn + NW * SM_SLOTS);  // [generation][kind][SM_SLOTS]
+  __shared__ unsigned cnt[2][3];
+  __shared__ unsigned cursor;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int nx = p.vol.nx, ny = p.vol.ny, nz = p.vol.nz;
+  const unsigned records = min(__ldcv(p.qcount), p.qcap);
+  const unsigned total = REUSE ? (p.pixel_major ? (records + p.pixel_major - 1) / p.pixel_major * p.pixel_major : records) * (unsigned)p.nframes
+                               : records;
+  // every slot starts free: the first round's E list is all of them
+  for (unsigned i = threadIdx.x; i < SM_SLOTS; i += SM_THREADS) {
+    lists[(0 * 3 + SML_E) * SM_SLOTS + i] = (unsigned short)i;
+    st[SMW_PK * SM_SLOTS + i] = 0u;
+  }
+  if (threadIdx.x == 0) {
+    cnt[0][SML_E] = SM_SLOTS; cnt[0][SML_M] = 0; cnt[0][SML_P] = 0;
+    cnt[1][SML_E] = 0; cnt[1][SML_M] = 0; cnt[1][SML_P] = 0;
+    cursor = 0;
+  }
+  unsigned c_steps = 0, c_normals = 0, c_env = 0, c_adm = 0;
+  bool exhausted = false;  // per warp: this warp has seen the end of the work queue
+  int cur = 0;
+
+  // append the slots of the lanes with `pred` to list `kind` of generation `gen` (all lanes of the warp call this together)
+  auto push = [&](int gen, int kind, bool pred, unsigned id) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (!m) return;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&cnt[gen][kind], (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pred) lists[(gen * 3 + kind) * SM_SLOTS + base + (unsigned)__popc(m & lt_mask)] = (unsigned short)id;
+  };
+  // pk: d (int8) | steps_left << 8 | po << 16 | pi << 18 | ev << 22 | clause_col << 25 | busy << 30
+  auto pack = [](int d, int steps_left, int po, int pi, int ev, int clause_col, int busy) -> uint32_t {
+    return ((unsigned)d & 0xFFu) | ((unsigned)steps_left << 8) | ((unsigned)po << 16) | ((unsigned)pi << 18) | ((unsigned)ev << 22) |
+           ((unsigned)clause_col << 25) | ((unsigned)busy << 30);
+  };
+
+  for (;;) {
+    __syncthreads();  // the lists of generation `cur` are complete, `cursor` is 0
+    const unsigned nE = cnt[cur][SML_E], nM = cnt[cur][SML_M], nP = LINEAR ? cnt[cur][SML_P] : 0u;
+    if (nE + nM + nP == 0) break;
+    const unsigned bM = (nM + 31) >> 5, bP = (nP + 31) >> 5, bE = (nE + 31) >> 5;
+    const int nxt = cur ^ 1;
+    for (;;) {
+      unsigned b = 0;
+      if (lane == 0) b = atomicAdd(&cursor, 1u);
+      b = __shfl_sync(0xffffffffu, b, 0);
+      if (b >= bM + bP + bE) break;
+      if (b < bM) {
+        // ---- a batch of marching slots: up to sm_k steps ----------------------------------------------------------------------
+        const unsigned e = b * 32 + lane;
+        const bool valid = e < nM;
+        const unsigned id = valid ? lists[(cur * 3 + SML_M) * SM_SLOTS + e] : 0u;
+        f3 o = {0, 0, 0}, dv = {0, 0, 0};
+        uint32_t pk = 0;
+        if (valid) {
+          o = {__uint_as_float(st[SMW_OX * SM_SLOTS + id]), __uint_as_float(st[SMW_OY * SM_SLOTS + id]), __uint_as_float(st[SMW_OZ * SM_SLOTS + id])};
+          dv = {__uint_as_float(st[SMW_DX * SM_SLOTS + id]), __uint_as_float(st[SMW_DY * SM_SLOTS + id]), __uint_as_float(st[SMW_DZ * SM_SLOTS + id])};
+          pk = st[SMW_PK * SM_SLOTS + id];
+        }
+        int d = (int)(signed char)(pk & 0xFFu), steps_left = (int)((pk >> 8) & 0xFFu);
+        int ev = EVP_NONE;
+        bool marching = valid, pending = false;
+        for (int k = 0; k < p.sm_k; ++k) {
+          if (marching) {
+            const float step_size = max_cl(small_int_to_float(d), 0.5f);
+            o = o + step_size * dv;
+            if (COUNT) c_steps++;
+            steps_left--;
+            float fx, fy, fz;
+            const int vx = floor_pair(o.x, &fx), vy = floor_pair(o.y, &fy), vz = floor_pair(o.z, &fz);
+            if (LINEAR) {
+              const unsigned cell = lin_cell(p, vx, vy, vz);
+              d = lin_sdf(cell);
+              if (lin_quiet(cell, o.x - fx, o.y - fy, o.z - fz)) {
+                if (steps_left == 0) { marching = false; ev = EVP_NONE; }
+              } else {
+                const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
+                marching = false;
+                pending = !exited;
+                if (exited) ev = EVP_EXIT;
+              }
+            } else {
+              d = surf3Dread<signed char>(p.sdf_surf, vx, vy, vz, cudaBoundaryModeZero);
+              if (d <= 0) {
+                const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
+                marching = false;
+                ev = exited ? EVP_EXIT : (d < 0 ? EVP_SDF_NEG : EVP_FARFACE);
+              } else if (steps_left == 0) { marching = false; ev = EVP_NONE; }
+            }
+          }
+          if (__popc(__ballot_sync(0xffffffffu, marching)) < p.sm_leave) break;
+        }
+        if (valid) {
+          st[SMW_OX * SM_SLOTS + id] = __float_as_uint(o.x); st[SMW_OY * SM_SLOTS + id] = __float_as_uint(o.y); st[SMW_OZ * SM_SLOTS + id] = __float_as_uint(o.z);
+          st[SMW_PK * SM_SLOTS + id] = (pk & 0x7E3F0000u) | ((unsigned)d & 0xFFu) | ((unsigned)steps_left << 8) | ((unsigned)ev << 22);
+        }
+        push(nxt, SML_M, valid && marching, id);
+        if (LINEAR) push(nxt, SML_P, valid && pending, id);
+        push(nxt, SML_E, valid && !marching && !pending, id);
+      } else if (LINEAR && b < bM + bP) {
+        // ---- a batch of slots that need get_event_and_value at their position (utility_ray.cl:126-138) --------------------------
+        const unsigned e = (b - bM) * 32 + lane;
+        const bool valid = e < nP;
+        const unsigned id = valid ? lists[(cur * 3 + SML_P) * SM_SLOTS + e] : 0u;
+        bool marching = false, pending = false;
+        if (valid) {
+          f3 o = {__uint_as_float(st[SMW_OX * SM_SLOTS + id]), __uint_as_float(st[SMW_OY * SM_SLOTS + id]), __uint_as_float(st[SMW_OZ * SM_SLOTS + id])};
+          uint32_t pk = st[SMW_PK * SM_SLOTS + id];
+          int d = (int)(signed char)(pk & 0xFFu), steps_left = (int)((pk >> 8) & 0xFFu);
+          int clause_col = (int)((pk >> 25) & 31u);
+          int ev = EVP_NONE;
+          const int value = vol_linear(p, o.x, o.y, o.z);
+          int clause = 0;
+          if (tf_value_may_match(p.tf, (int)(short)value)) {
+            const f3 grad = gradient_linear(p, o);
+            clause = tf_match(p.tf, (int)(short)value, f2s(length3(grad)));
+            if (clause != 0) {
+              st[SMW_GX * SM_SLOTS + id] = __float_as_uint(grad.x); st[SMW_GY * SM_SLOTS + id] = __float_as_uint(grad.y);
+              st[SMW_GZ * SM_SLOTS + id] = __float_as_uint(grad.z);
+            }
+          }
+          if (clause != 0) {
+            if (!(p.tf.r[clause - 1].flags & VR_TF_THRESHOLD)) clause_col = clause;
+            ev = EVP_HIT;
+          } else if (steps_left == 0) {
+            ev = EVP_NONE;
+          } else {  // no event here: the next march() and the gather that classifies the new position
+            const f3 dv = {__uint_as_float(st[SMW_DX * SM_SLOTS + id]), __uint_as_float(st[SMW_DY * SM_SLOTS + id]), __uint_as_float(st[SMW_DZ * SM_SLOTS + id])};
+            const float step_size = max_cl(small_int_to_float(d), 0.5f);
+            o = o + step_size * dv;
+            if (COUNT) c_steps++;
+            steps_left--;
+            float fx, fy, fz;
+            const int vx = floor_pair(o.x, &fx), vy = floor_pair(o.y, &fy), vz = floor_pair(o.z, &fz);
+            const unsigned cell = lin_cell(p, vx, vy, vz);
+            d = lin_sdf(cell);
+            if (lin_quiet(cell, o.x - fx, o.y - fy, o.z - fz)) {
+              marching = steps_left != 0;
+              if (!marching) ev = EVP_NONE;
+            } else {
+              const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
+              pending = !exited;
+              if (exited) ev = EVP_EXIT;
+            }
+            st[SMW_OX * SM_SLOTS + id] = __float_as_uint(o.x); st[SMW_OY * SM_SLOTS + id] = __float_as_uint(o.y); st[SMW_OZ * SM_SLOTS + id] = __float_as_uint(o.z);
+          }
+          st[SMW_PK * SM_SLOTS + id] = (pk & 0x403F0000u) | ((unsigned)d & 0xFFu) | ((unsigned)steps_left << 8) | ((unsigned)ev << 22) | ((unsigned)clause_col << 25);
+        }
+        push(nxt, SML_M, valid && marching, id);
+        push(nxt, SML_P, valid && pending, id);
+        push(nxt, SML_E, valid && !marching && !pending, id);
+      } else {
+        // ---- a batch of slots whose segment ended, or that are free: ray_marching.cl:53-76, refill, bounce, start --------------
+        const unsigned e = (b - bM - bP) * 32 + lane;
+        const bool valid = e < nE;
+        const unsigned id = valid ? lists[(cur * 3 + SML_E) * SM_SLOTS + e] : 0u;
+        uint32_t pk = valid ? st[SMW_PK * SM_SLOTS + id] : 0u;
+        int d = (int)(signed char)(pk & 0xFFu), steps_left = (int)((pk >> 8) & 0xFFu);
+        int po = (int)((pk >> 16) & 3u), pi = (int)((pk >> 18) & 15u), ev = (int)((pk >> 22) & 7u), clause_col = (int)((pk >> 25) & 31u);
+        bool busy = ((pk >> 30) & 1u) != 0u;
+        f3 o = {0, 0, 0}, dv = {0, 0, 0};
+        float atten = 0, er = 0, eg = 0, eb = 0;
+        unsigned bvp = 0, rec = 0, xyp = 0;
+        int seed = 0;
+        if (busy) {
+          o = {__uint_as_float(st[SMW_OX * SM_SLOTS + id]), __uint_as_float(st[SMW_OY * SM_SLOTS + id]), __uint_as_float(st[SMW_OZ * SM_SLOTS + id])};
+          dv = {__uint_as_float(st[SMW_DX * SM_SLOTS + id]), __uint_as_float(st[SMW_DY * SM_SLOTS + id]), __uint_as_float(st[SMW_DZ * SM_SLOTS + id])};
+          atten = __uint_as_float(st[SMW_ATT * SM_SLOTS + id]);
+          er = __uint_as_float(st[SMW_ER * SM_SLOTS + id]); eg = __uint_as_float(st[SMW_EG * SM_SLOTS + id]); eb = __uint_as_float(st[SMW_EB * SM_SLOTS + id]);
+          bvp = st[SMW_BVP * SM_SLOTS + id]; rec = st[SMW_REC * SM_SLOTS + id]; seed = (int)st[SMW_SEED * SM_SLOTS + id]; xyp = st[SMW_XYP * SM_SLOTS + id];
+        }
+        auto energy = [&](int k) -> float { return clause_col ? p.tf.e[clause_col - 1][k] : 0.0f; };
+        bool need_bounce = false, reset_atten = false, need_start = false, resume = false;
+        f3 bn = {0, 0, 0};
+        int bseed = 0;
+        if (busy) {
+          f3 grad = {0.0f, 0.0f, 0.0f};
+          if (LINEAR) {
+            if (ev == EVP_HIT)
+              grad = {__uint_as_float(st[SMW_GX * SM_SLOTS + id]), __uint_as_float(st[SMW_GY * SM_SLOTS + id]), __uint_as_float(st[SMW_GZ * SM_SLOTS + id])};
+          } else if (ev == EVP_SDF_NEG || ev == EVP_FARFACE) {
+            const int vx = ifloor(o.x), vy = ifloor(o.y), vz = ifloor(o.z);
+            grad = gradient_voxel(p.vol, vx, vy, vz);
+            const int value = ev == EVP_SDF_NEG ? p.vol.at(vx, vy, vz) : 0;
+            const int clause = tf_match(p.tf, value, f2s(length3(grad)));
+            if (ev == EVP_FARFACE && clause == 0) {
+              ev = EVP_NONE;                     // no event on the far face: `continue` in march_to_next_event
+              if (steps_left > 0) resume = true;
+            } else {
+              if (clause > 0 && !(p.tf.r[clause - 1].flags & VR_TF_THRESHOLD)) clause_col = clause;
+              ev = EVP_HIT;
+            }
+          }
+          if (!resume) {  // body of the i-loop, ray_marching.cl:53-72
+            bool next_o = false;
+            if (ev == EVP_EXIT) {
+              const float factor = pi == 8 ? 8.0f / 8.0f : (pi == 9 ? 8.0f / 9.0f : 8.0f / 10.0f);
+              const uchar4 lm = env_sample<LINEAR>(p, dv);
+              if (COUNT) c_env++;
+              const unsigned bv0 = f2u((float)(bvp & 1023u) + atten * er * (float)lm.x * factor / 1.0f);
+              const unsigned bv1 = f2u((float)((bvp >> 10) & 1023u) + atten * eg * (float)lm.y * factor / 1.0f);
+              const unsigned bv2 = f2u((float)(bvp >> 20) + atten * eb * (float)lm.z * factor / 1.0f);
+              bvp = bv0 | (bv1 << 10) | (bv2 << 20);
+              next_o = true;
+            } else {
+              const bool more = pi < 10;
+              if (ev == EVP_HIT) {
+                if (COUNT) c_normals++;
+                er *= energy(0); eg *= energy(1); eb *= energy(2);
+                if (more) {
+                  bn = -normalize3_shared_rcp(grad);
+                  o = o + dv;
+                  bseed = seed + po + pi;
+                  need_bounce = true;
+                }
+              }
+              ++pi;
+              if (more) need_start = true;
+              else next_o = true;
+            }
+            if (next_o) {
+              if (po == 1) {
+                po = 2; pi = 8;
+                const HitRecord h2 = load_record(p.queue, rec);
+                o = h2.base;
+                bn = h2.normal; bseed = seed + po;
+                need_bounce = true; reset_atten = true; need_start = true;
+              } else {
+                const unsigned bv0 = (bvp & 1023u) / 2u, bv1 = ((bvp >> 10) & 1023u) / 2u, bv2 = (bvp >> 20) / 2u;
+                const uint32_t low = bv0 + (bv1 << 16);
+                const uint32_t high = bv2;
+                const size_t voxel = p.queue[3 * (size_t)rec].z;
+                if (low) atomicAdd(p.cache + 2 * voxel, low);
+                if (high) atomicAdd(p.cache + 2 * voxel + 1, high);
+                busy = false;
+              }
+            }
+          }
+        }
+        // refill: free slots draw the next work items
+        bool retry = false;
+        {
+          const unsigned idle = __ballot_sync(0xffffffffu, valid && !busy);
+          if (idle && !exhausted) {
+            unsigned first = 0;
+            if (lane == 0) first = atomicAdd(work_counter, (unsigned)__popc(idle));
+            first = __shfl_sync(0xffffffffu, first, 0);
+            exhausted = first + (unsigned)__popc(idle) >= total;
+            const unsigned idx = first + (unsigned)__popc(idle & lt_mask);
+            bool take = valid && !busy && idx < total;
+            retry = take;  // a drawn item that is rejected (voxel at its token cap, padding item) frees the slot for the next draw
+            HitRecord h;
+            if (take) {
+              if (REUSE) {
+                unsigned f;
+                if (p.pixel_major) {
+                  const unsigned pb = (unsigned)p.pixel_major, gsz = pb * (unsigned)p.nframes;
+                  const unsigned grp = idx / gsz, within = idx - grp * gsz;
+                  f = within / pb;
+                  rec = grp * pb + (within - f * pb);
+                } else { f = idx / records; rec = idx - f * records; }
+                if (rec >= records) take = false;
+                else {
+                  h = load_record(p.queue, rec);
+                  h.seed = p.seeds[f];
+                  uint32_t* hi = p.cache + 2 * (size_t)h.voxel + 1;  // atomic_allow_write_max, utility.cl:20-31
+                  const int w = (int)(short)(__ldcv(hi) >> 16);
+                  take = false;
+                  if (!((unsigned)w > (unsigned)p.token_cap)) {
+                    const int t = (int)atomicAdd(hi, 0x00010000u);
+                    if ((unsigned)(t >> 16) < (unsigned)p.token_cap) take = true;
+                    else atomicSub(hi, 0x00010000u);
+                  }
+                  if (COUNT && take) { c_adm++; c_normals++; }
+                }
+              } else {
+                rec = idx;
+                h = load_record(p.queue, idx);
+              }
+            }
+            if (take) {  // ray_marching.cl:42-50 for o = 1
+              xyp = (unsigned)((h.xy & 0xFFFF) + 1) * (unsigned)((h.xy >> 16) + 1);
+              seed = h.seed; clause_col = h.clause;
+              er = energy(0); eg = energy(1); eb = energy(2);
+              bvp = 0;
+              po = 1; pi = 8;
+              o = h.base;
+              bn = h.normal; bseed = seed + po;
+              need_bounce = true; reset_atten = true; need_start = true;
+              busy = true;
+              retry = false;
+            }
+          }
+        }
+        if (need_bounce) {
+          dv = hemisphere_reflective_p(bn, bseed, energy(3), xyp);
+          o = o + bn * 2.0f;
+          const float a = fabsf(dot3(dv, bn));
+          atten = reset_atten ? a : atten * a;
+        }
+        if (need_start) {  // first half of march(), utility_ray.cl:148-150
+          if (LINEAR) d = lin_sdf(lin_cell(p, f2i(o.x), f2i(o.y), f2i(o.z)));
+          else d = surf3Dread<signed char>(p.sdf_surf, f2i(o.x), f2i(o.y), f2i(o.z), cudaBoundaryModeZero);
+          steps_left = 70;
+          ev = EVP_NONE;
+        }
+        if (valid) {
+          if (busy) {
+            st[SMW_OX * SM_SLOTS + id] = __float_as_uint(o.x); st[SMW_OY * SM_SLOTS + id] = __float_as_uint(o.y); st[SMW_OZ * SM_SLOTS + id] = __float_as_uint(o.z);
+            st[SMW_DX * SM_SLOTS + id] = __float_as_uint(dv.x); st[SMW_DY * SM_SLOTS + id] = __float_as_uint(dv.y); st[SMW_DZ * SM_SLOTS + id] = __float_as_uint(dv.z);
+            st[SMW_ATT * SM_SLOTS + id] = __float_as_uint(atten);
+            st[SMW_ER * SM_SLOTS + id] = __float_as_uint(er); st[SMW_EG * SM_SLOTS + id] = __float_as_uint(eg); st[SMW_EB * SM_SLOTS + id] = __float_as_uint(eb);
+            st[SMW_BVP * SM_SLOTS + id] = bvp; st[SMW_REC * SM_SLOTS + id] = rec; st[SMW_SEED * SM_SLOTS + id] = (uint32_t)seed; st[SMW_XYP * SM_SLOTS + id] = xyp;
+          }
+          st[SMW_PK * SM_SLOTS + id] = pack(d, steps_left, po, pi, ev, clause_col, busy ? 1 : 0);
+        }
+        push(nxt, SML_M, valid && busy, id);           // a started (or resumed) segment marches next round
+        push(nxt, SML_E, valid && !busy && retry, id);  // rejected draw: try the next item; exhausted queue: the slot retires
+      }
+    }
+    __syncthreads();  // every warp is done with generation `cur`
+    if (threadIdx.x == 0) {
+      cnt[cur][SML_E] = 0; cnt[cur][SML_M] = 0; cnt[cur][SML_P] = 0;
+      cursor = 0;
+    }
+    cur = nxt;
+  }
+  if (COUNT) {
+    unsigned v[5] = {c_steps, c_normals, c_env, 0u, c_adm};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      unsigned sum = v[k];
+      for (int q = 16; q > 0; q >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, q);
+      if (lane == 0 && sum) atomicAdd(p.counters + k, (unsigned long long)sum);
+    }
+  }
+}
+
+#endif  // VR_AB
+
 // phase 2: ray_marching.cl:82-99
 __device__ __forceinline__ uchar4 resolve_rgbw(uint32_t r, uint32_t g, uint32_t b, uint32_t w);
 __device__ __forceinline__ uchar4 resolve_entry(const uint2 c) {
@@ -966,7 +1340,7 @@ static int launch_trace(vr_renderer* r, RenderParams& p, const float pos[3], con
   // mode 1 (hybrid): k_primary per pixel and frame (primary march + token admission) queues the admitted hits, persistent warps
   //                  run their secondary paths
   // mode 2 (primary reuse, default): k_primary once per pixel, persistent warps run admission + secondary paths per (pixel, frame)
-  const bool reuse = r->trace_mode == 2;
+  const bool reuse = r->trace_mode >= 2;
   const size_t cap = reuse ? (size_t)r->W * rows : std::max<size_t>((size_t)r->W * rows, std::min<size_t>(pixels, (size_t)32 << 20));
   if (r->queue_cap < cap) {
     if (r->queue) VR_CUDA(cudaFreeAsync(r->queue, ctx->stream));
@@ -1023,6 +1397,21 @@ static int launch_trace(vr_renderer* r, RenderParams& p, const float pos[3], con
     r->primary_valid = true;
   }
   VR_CUDA(cudaMemsetAsync(p.qcount + 1, 0, sizeof(unsigned), ctx->stream));
+#ifdef VR_AB
+  if (r->trace_mode == 3 && (LINEAR || r->sdf->surf)) {  // slots in shared memory, packed batches (k_trace_sm)
+    static int per_sm = 0;
+    const size_t smem = sm_trace_smem_bytes(LINEAR);
+    if (!per_sm) {
+      VR_CUDA(cudaFuncSetAttribute(k_trace_sm<COUNT, true, LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VR_CUDA(cudaFuncSetAttribute(k_trace_sm<COUNT, true, LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_sm<COUNT, true, LINEAR>, SM_THREADS, smem));
+    }
+    const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)std::max(1, per_sm);
+    k_trace_sm<COUNT, true, LINEAR><<<blocks, SM_THREADS, smem, ctx->stream>>>(p, p.qcount + 1);
+    ctx->launches++;
+    return VR_OK;
+  }
+#endif
   return launch_pt_select<COUNT, true, LINEAR>(r, p, p.qcount + 1);
 }
 
@@ -1082,6 +1471,7 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     p.lin_sched = r->tune.lin_sched;
     p.lin_wf = r->tune.lin_w[0]; p.lin_ws = r->tune.lin_w[1]; p.lin_we = r->tune.lin_w[2];
     p.spc = r->tune.spc;
+    p.sm_k = r->tune.sm_k; p.sm_leave = r->tune.sm_leave;
     for (int k = 0; k < nframes; ++k) p.seeds[k] = seeds[k];
     p.token_cap = r->token_cap;
     p.counters = r->counters;

@@ -348,6 +348,36 @@ def test_sdf_alternative_builds_bit_exact(mode):
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 
 
+def test_ab_build_trace_sm_equals_default_schedule():
+    """The A/B build's trace mode 3 (k_trace_sm: sample slots in shared memory, packed batches — measured and not adopted, see
+    vr_render.cu) computes the same samples: voxel cache and counters identical to the default schedule, under both samplings."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env["VR_LIB"] = os.path.join(root, "tools", "ab", "libvr_ab.so")
+    assert os.path.exists(env["VR_LIB"]), "build the A/B library: make ab"
+    code = (
+        "import numpy as np\n"
+        "from cl_volume_renderer_b200 import api, synth\n"
+        "ctx = api.Context(0)\n"
+        "n, W, H = 64, 160, 120\n"
+        "vol = api.Volume(ctx, synth.synth_ct(n)); env = api.EnvMap(ctx, synth.synth_env(128, 64))\n"
+        "seeds = synth.glibc_rand(16)\n"
+        "for sampling in (api.VR_SAMPLING_NEAREST, api.VR_SAMPLING_HW_LINEAR):\n"
+        "    res = []\n"
+        "    for mode in (2, 3):\n"
+        "        r = api.Renderer(ctx, W, H); r.set_sampling(sampling); r.set_trace_mode(mode)\n"
+        "        r.image_set(vol, env); r.set_tf(synth.default_tf()); r.flush_changes(); r.enable_counters(True)\n"
+        "        for cam in (synth.default_camera(n), synth.closeup_camera(n)):\n"
+        "            f = r.render_frames(cam[0], cam[1], seeds)\n"
+        "        res.append((r.cache_download(), r.counters(), f)); r.close()\n"
+        "    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1] and np.array_equal(res[0][2], res[1][2])\n"
+        "    assert res[0][0].any()\n"
+        "print('OK')\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_render_odd_shapes_and_empty_tf(vr_ctx, both):
     """Edge cases the reference leaves to luck: a frame that is not a multiple of its 8x8 work-groups (render has no bounds guard,
     clw_function.hpp:235-237 asserts instead), a volume whose dims are not multiples of the brick / word sizes, an empty transfer
@@ -766,7 +796,7 @@ def test_tf_colours_outside_0_255_are_rejected(vr_ctx):
 
 
 def test_array_cache_stays_bounded_over_many_clip_boxes(vr_ctx):
-    """the context recycles the SDF's 3-D arrays by size and keeps at most two unused ones"""
+    """the context recycles the 3-D arrays (SDF surface, hw-linear step field and volume texture) by size and keeps at most four unused"""
     v, envimg, tf = synth.synth_ct(48), synth.synth_env(64, 32), synth.default_tf()
     vol, env = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
     r = api.Renderer(vr_ctx, 32, 32)
@@ -775,12 +805,12 @@ def test_array_cache_stays_bounded_over_many_clip_boxes(vr_ctx):
     for k in range(12):
         vol.clip((0, 0, 0), (24 + 2 * k, 40, 40))
         r.flush_changes()
-        assert vr_ctx.array_count <= base + 3   # the renderer's current SDF + at most two cached
+        assert vr_ctx.array_count <= base + 5   # the renderer's current SDF + at most four cached
     r.set_sampling(api.VR_SAMPLING_HW_LINEAR)
     for k in range(6):
         vol.clip((0, 0, 0), (24 + 2 * k, 40, 40))
         r.flush_changes()
-        assert vr_ctx.array_count <= base + 4   # + the 16-bit step field
+        assert vr_ctx.array_count <= base + 7   # + the 16-bit step field and the volume texture array
     r.close(); env.close(); vol.close()
 
 

@@ -38,13 +38,22 @@ for sampling, name in ((api.VR_SAMPLING_NEAREST, "nearest"), (api.VR_SAMPLING_HW
     import time
     t0 = time.perf_counter(); r.flush_changes(); ctx.synchronize(); flush1 = 1e3 * (time.perf_counter() - t0)
     t0 = time.perf_counter(); r.flush_changes(); ctx.synchronize(); flush2 = 1e3 * (time.perf_counter() - t0)
-    for mode in (2, 1, 0):
+    for mode in ((2, 3, 1, 0) if ab else (2, 1, 0)):
         r.set_trace_mode(mode)
         row = {"sampling": name, "mode": mode, "flush_ms_first": flush1, "flush_ms_again": flush2}
         for cam, (pos, d) in cams.items():
             row[cam + "_ms"] = measure(r, pos, d)
             row[cam + "_gsamples"] = W * H * 64 / row[cam + "_ms"] / 1e6
         print(json.dumps(row), flush=True)
+    if ab:
+        r.set_trace_mode(3)
+    for k, lv in (((8, 16), (16, 8), (16, 24), (32, 16), (70, 16), (16, 1), (8, 24), (24, 20)) if ab else ()):
+        r.set_tuning("sm_k", k); r.set_tuning("sm_leave", lv)
+        row = {"sampling": name, "mode": 3, "sm_k": k, "sm_leave": lv}
+        for cam, (pos, d) in cams.items():
+            row[cam + "_ms"] = measure(r, pos, d, 2)
+        print(json.dumps(row), flush=True)
+    r.set_tuning("sm_k", 16); r.set_tuning("sm_leave", 16)
     r.set_trace_mode(2)
     if sampling == api.VR_SAMPLING_HW_LINEAR and not quick:
         settings = []
