@@ -39,6 +39,7 @@ struct RenderParams {
   uint32_t* __restrict__ cache;
   uint32_t* __restrict__ hit;
   uchar4* __restrict__ frame;
+  float fnx, fny, fnz;  // the volume's dims as floats (exit test of the step loops)
   int W, H, row0, row1;
   int blk_rows, blk_rank, blk_n;  // image-tile split: row block b = y / blk_rows is traced by rank b % blk_n (blk_n <= 1: every row)
   f3 cam_pos, cam_dir;
@@ -46,6 +47,7 @@ struct RenderParams {
   int token_cap;
   int nframes;          // frames in this launch: blockIdx.z selects the seed
   int pixel_major;      // k_trace_pt<.., REUSE> item order (see there)
+  int nframes_shift;    // log2(nframes) when pixel_major == 1 and nframes is a power of two, else -1
   int rule_a, rule_b;   // k_trace_pt leaves its step loop when marching lanes * rule_a < waiting lanes * rule_b (VR_PT_RULE=a,b)
   int seeds[VR_MAX_BATCH];
   unsigned long long* counters;
@@ -544,6 +546,8 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
   // slot state
   int mode = M_IDLE;
   bool marching = false;
+  bool unclassified = false;          // the segment ended inside the step loop; `ev` is decided after the loop
+  bool lastq = false;                 // LINEAR: verdict of the step field at the position where the lane stopped
   bool pending = false;               // LINEAR: the event test at the current position is still to be done
   f3 hgrad = {0.0f, 0.0f, 0.0f};      // LINEAR: gradient of that test when it found a hit
   int ev = EVP_NONE;
@@ -654,7 +658,10 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
             // step on the bench scene; groups of 2..32 pixels measure the same, so it is temporal, not intra-warp, locality).
             // VR_PT_ORDER=0: frame-major, consecutive items are neighbouring pixels of one frame.
             unsigned f;
-            if (p.pixel_major) {  // groups of pixel_major pixels x nframes frames, the pixels of a group fastest
+            if (p.nframes_shift >= 0) {  // the default order (pixel_major 1) with a power-of-two batch: no divisions
+              rec = idx >> p.nframes_shift;
+              f = idx & ((1u << p.nframes_shift) - 1u);
+            } else if (p.pixel_major) {  // groups of pixel_major pixels x nframes frames, the pixels of a group fastest
               const unsigned pb = (unsigned)p.pixel_major, gsz = pb * (unsigned)p.nframes;
               const unsigned grp = idx / gsz, within = idx - grp * gsz;
               f = within / pb;
@@ -730,7 +737,7 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
           marching = steps_left != 0;
           if (!marching) ev = EVP_NONE;
         } else {
-          const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
+          const bool exited = ((vx | vy | vz) < 0) | (p.fnx < o.x) | (p.fny < o.y) | (p.fnz < o.z);
           marching = false;
           pending = !exited;
           if (exited) ev = EVP_EXIT;
@@ -738,6 +745,32 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
       };
       // get_event_and_value (utility_ray.cl:126-138) where an event is possible.  The value first: when no clause can match
       // it, the gradient (six more fetches) cannot change the verdict.
+      // the same step inside the quiet-step loops: only "keeps marching or not" is decided there; classify() sorts the lanes that
+      // stopped into step budget used up / left the volume / event test pending, once per loop exit
+      auto advance_quiet = [&]() {
+        const float step_size = max_cl(small_int_to_float(d), 0.5f);
+        o = o + step_size * dv;
+        if (COUNT) c_steps++;
+        steps_left--;
+        float fx, fy, fz;
+        const int vx = floor_pair(o.x, &fx), vy = floor_pair(o.y, &fy), vz = floor_pair(o.z, &fz);
+        const unsigned cell = lin_cell(p, vx, vy, vz);
+        d = lin_sdf(cell);
+        lastq = lin_quiet(cell, o.x - fx, o.y - fy, o.z - fz);
+        marching = lastq & (steps_left != 0);
+        unclassified = true;
+      };
+      auto classify = [&]() {
+        if (unclassified && !marching) {
+          if (lastq) ev = EVP_NONE;
+          else {
+            const bool exited = (o.x < 0.0f) | (o.y < 0.0f) | (o.z < 0.0f) | (p.fnx < o.x) | (p.fny < o.y) | (p.fnz < o.z);
+            pending = !exited;
+            if (exited) ev = EVP_EXIT;
+          }
+        }
+        unclassified = false;
+      };
       auto event_test = [&]() {
         const int value = vol_linear(p, o.x, o.y, o.z);
         int clause = 0;
@@ -763,12 +796,13 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
         for (;;) {
           for (;;) {
             for (int u = 0; u < p.spc; ++u)
-              if (marching) advance();
+              if (marching) advance_quiet();
             const unsigned act = __ballot_sync(0xffffffffu, marching);
             if (!act) break;
-            const unsigned others = __ballot_sync(0xffffffffu, !marching && (pending || mode != M_IDLE || !exhausted));
+            const unsigned others = __ballot_sync(0xffffffffu, !marching && (mode != M_IDLE || !exhausted));
             if (__popc(act) * p.lin_wf < __popc(others)) break;
           }
+          classify();
           for (;;) {
             if (!__ballot_sync(0xffffffffu, pending)) break;
             if (pending) event_test();
@@ -795,7 +829,8 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
         const int F = __popc(mF) * p.lin_wf, S = __popc(mS) * p.lin_ws, E = __popc(mE) * p.lin_we;
         if (F >= S && F >= E) {
           for (int u = 0; u < p.spc; ++u)
-            if (marching) advance();
+            if (marching) advance_quiet();
+          classify();
         } else if (S >= E) {
           if (pending) event_test();
         } else {
@@ -810,8 +845,11 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
       for (int u = 0; u < p.spc; ++u) {
         if (!marching) continue;
         if (SURF) {
-          // conversion-free step (floor_pair): the surface returns 0 outside the field (and real voxels are never 0), so bounds
-          // only matter when the step ends, and then only the sign of the floored coordinates is used
+          // conversion-free step (floor_pair): the surface returns 0 outside the field (and real voxels are never 0), so a step
+          // ends exactly when the gather is <= 0 or the 70 steps are used up.  WHY it ended (exit, event voxel, far face, step
+          // budget) is decided once, after the loop (`unclassified` below): segments are only ~6 steps long, so with ~20 lanes
+          // marching some lane ends in almost every iteration, and a divergent tail inside the loop ran nearly every time
+          // (ncu: 10 % of the kernel's instructions at 2-9 active lanes).
           const float step_size = max_cl(small_int_to_float(d), 0.5f);
           o = o + step_size * dv;
           if (COUNT) c_steps++;
@@ -819,11 +857,8 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
           float fx, fy, fz;
           const int vx = floor_pair(o.x, &fx), vy = floor_pair(o.y, &fy), vz = floor_pair(o.z, &fz);
           d = surf3Dread<signed char>(p.sdf_surf, vx, vy, vz, cudaBoundaryModeZero);
-          if (d <= 0) {
-            const bool exited = ((vx | vy | vz) < 0) | ((float)nx < o.x) | ((float)ny < o.y) | ((float)nz < o.z);
-            marching = false;
-            ev = exited ? EVP_EXIT : (d < 0 ? EVP_SDF_NEG : EVP_FARFACE);
-          } else if (steps_left == 0) { marching = false; ev = EVP_NONE; }
+          marching = (d > 0) & (steps_left != 0);
+          unclassified = true;
         } else {
           const float step_size = max_cl((float)d, 0.5f);
           o = o + step_size * dv;
@@ -845,6 +880,11 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
       // stepping until the lanes that still march are outnumbered 5 : 1 by the lanes that wait for an event or a refill
       const unsigned waiting = __ballot_sync(0xffffffffu, !marching && (mode != M_IDLE || !exhausted));
       if (__popc(act) * p.rule_a < __popc(waiting) * p.rule_b) break;
+    }
+    if (SURF && unclassified && !marching) {  // exited_volume (utility_ray.cl:112-117) and the SDF-sign event test, once per segment
+      const bool exited = (o.x < 0.0f) | (o.y < 0.0f) | (o.z < 0.0f) | (p.fnx < o.x) | (p.fny < o.y) | (p.fnz < o.z);
+      ev = d > 0 ? EVP_NONE : (exited ? EVP_EXIT : (d < 0 ? EVP_SDF_NEG : EVP_FARFACE));
+      unclassified = false;
     }
   }
   if (COUNT) {
@@ -1452,6 +1492,7 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     p.vol = VolView{r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz};
     p.sdf = SdfView{r->sdf->field, r->sdf->nx, r->sdf->ny, r->sdf->nz, r->sdf->nx / 8 + 1, r->sdf->ny / 8 + 1};
     p.sdf_surf = r->sdf->surf;
+    p.fnx = (float)r->vol->nx; p.fny = (float)r->vol->ny; p.fnz = (float)r->vol->nz;
     p.vol_tex = r->vol_tex; p.env_tex = r->env_tex;
     p.lin_surf = r->lin_surf;
     p.env = r->env->texels;
@@ -1467,6 +1508,10 @@ int vrk_render(vr_renderer* r, const float pos[3], const float dir[3], const int
     camera_basis(dir, &p.cam_side, &p.cam_up);
     p.nframes = nframes;
     p.pixel_major = r->tune.pixel_major;
+    p.nframes_shift = -1;
+    if (p.pixel_major == 1 && (nframes & (nframes - 1)) == 0)
+      for (int b = 0; b < 8; ++b)
+        if ((1 << b) == nframes) p.nframes_shift = b;
     p.rule_a = r->tune.rule[0]; p.rule_b = r->tune.rule[1];
     p.lin_sched = r->tune.lin_sched;
     p.lin_wf = r->tune.lin_w[0]; p.lin_ws = r->tune.lin_w[1]; p.lin_we = r->tune.lin_w[2];

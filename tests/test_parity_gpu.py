@@ -362,17 +362,23 @@ def test_ab_build_trace_sm_equals_default_schedule():
         "ctx = api.Context(0)\n"
         "n, W, H = 64, 160, 120\n"
         "vol = api.Volume(ctx, synth.synth_ct(n)); env = api.EnvMap(ctx, synth.synth_env(128, 64))\n"
-        "seeds = synth.glibc_rand(16)\n"
+        "seeds = synth.glibc_rand(4)\n"
         "for sampling in (api.VR_SAMPLING_NEAREST, api.VR_SAMPLING_HW_LINEAR):\n"
         "    res = []\n"
         "    for mode in (2, 3):\n"
         "        r = api.Renderer(ctx, W, H); r.set_sampling(sampling); r.set_trace_mode(mode)\n"
         "        r.image_set(vol, env); r.set_tf(synth.default_tf()); r.flush_changes(); r.enable_counters(True)\n"
+        "        out = []\n"
         "        for cam in (synth.default_camera(n), synth.closeup_camera(n)):\n"
+        "            r.reset_cache()\n"
         "            f = r.render_frames(cam[0], cam[1], seeds)\n"
-        "        res.append((r.cache_download(), r.counters(), f)); r.close()\n"
-        "    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1] and np.array_equal(res[0][2], res[1][2])\n"
-        "    assert res[0][0].any()\n"
+        "            out.append((r.cache_download(), f))\n"
+        "        c = r.counters(); r.close()\n"
+        "        assert c['admitted'] == c['primary_hits'] > 0   # the token cap is never reached: admissions do not depend on the order\n"
+        "        res.append((out, c))\n"
+        "    assert res[0][1] == res[1][1]\n"
+        "    for k in range(2):\n"
+        "        assert np.array_equal(res[0][0][k][0], res[1][0][k][0]) and np.array_equal(res[0][0][k][1], res[1][0][k][1])\n"
         "print('OK')\n")
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
