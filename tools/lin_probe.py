@@ -61,12 +61,12 @@ for sampling, name in ((api.VR_SAMPLING_NEAREST, "nearest"), (api.VR_SAMPLING_HW
             settings.append({"lin_sched": 0, "lin_w_fast": w[0], "lin_w_slow": w[1], "lin_w_event": w[2]})
         for w in ((4, 3, 1), (2, 2, 1), (4, 2, 1), (3, 2, 1), (3, 3, 1), (4, 4, 1), (2, 3, 1), (6, 4, 1)):
             settings.append({"lin_sched": 1, "lin_w_fast": w[0], "lin_w_slow": w[1], "lin_w_event": w[2]})
-        for spc in (1, 3, 4):
+        for spc in (2, 3, 6, 8):
             settings.append({"steps_per_check": spc})
         if ab:
-            for c in (6, 10, 12):
+            for c in (6, 8, 10):
                 settings.append({"pt_ctas": c})
-        base = {"lin_sched": 0, "lin_w_fast": 4, "lin_w_slow": 2, "lin_w_event": 2, "steps_per_check": 2}
+        base = {"lin_sched": 0, "lin_w_fast": 3, "lin_w_slow": 2, "lin_w_event": 2, "steps_per_check": 4}
         for st in settings:
             for k, v in st.items():
                 r.set_tuning(k, v)
@@ -79,12 +79,13 @@ for sampling, name in ((api.VR_SAMPLING_NEAREST, "nearest"), (api.VR_SAMPLING_HW
             if ab:
                 r.set_tuning("pt_ctas", 0)
     if sampling == api.VR_SAMPLING_NEAREST and not quick:
-        for st in ({"steps_per_check": 1}, {"steps_per_check": 3}, {"steps_per_check": 4}, {"rule_a": 3}, {"rule_a": 8}):
+        for st in ({"steps_per_check": 2}, {"steps_per_check": 3}, {"steps_per_check": 6}, {"steps_per_check": 8}, {"rule_a": 3}, {"rule_a": 8},
+                   {"rule_a": 3, "steps_per_check": 8}, {"pixel_major": 2}, {"pixel_major": 8}):
             for k, v in st.items():
                 r.set_tuning(k, v)
             row = dict(st, sampling="nearest")
             for cam, (pos, d) in cams.items():
                 row[cam + "_ms"] = measure(r, pos, d, 2)
             print(json.dumps(row), flush=True)
-            r.set_tuning("steps_per_check", 2); r.set_tuning("rule_a", 5)
+            r.set_tuning("steps_per_check", 4); r.set_tuning("rule_a", 5); r.set_tuning("pixel_major", 1)
     r.close()
