@@ -618,6 +618,14 @@ def run_ours(args, rank, world, local_rank):
                 chk = s5.checksum()
                 s5.close()
             row["sdf_build_ms"] = min(ts)
+            ts = []
+            for rep in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                s5 = api.Sdf(ctx, v5, tf, sharded="slab")
+                ts.append(rank_max(1e3 * (time.perf_counter() - t0)))
+                s5.close()
+            row["sdf_build_ms_without_gather"] = min(ts)
             if world > 1:
                 s1 = api.Sdf(ctx, v5, tf)      # the single-GPU build of the same volume on this rank
                 row["sdf_identical_to_single_gpu_build"] = bool(rank_min_int(int(s1.checksum() == chk)))
@@ -656,7 +664,8 @@ def run_ours(args, rank, world, local_rank):
             if own:
                 v5.close()
         return {"rows": rows, "what": "BASELINE config 5: vr_sdf_build_sharded (z-slabs + 16 halo planes, bit-volume halo swaps every 14 "
-                                      "levels with ncclSend/ncclRecv, gather of the field), vr_histogram_sharded (slab counts + all-reduce), "
+                                      "levels with ncclSend/ncclRecv, gather of the field so that every rank can render; "
+                                      "`sdf_build_ms_without_gather` = vr_sdf_build_slab_only, the build itself), vr_histogram_sharded (slab counts + all-reduce), "
                                       "vr_volume_filter_sharded (slab + 2 halo planes, gather) — wall time per call incl. its "
                                       "synchronisation, min of 2-3 repetitions after the first, max over ranks; results compared with the "
                                       "single-GPU calls on every rank through device-side checksums"}

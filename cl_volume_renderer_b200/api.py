@@ -134,6 +134,7 @@ SYMBOLS = {
     "vr_volume_upload_sharded": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "vr_sdf_build_sharded": (C.c_int, [_P, _P, C.POINTER(TfRect), C.c_int, C.POINTER(_P)]),
     "vr_renderer_set_sharded_build": (C.c_int, [_P, C.c_int]),
+    "vr_sdf_build_slab_only": (C.c_int, [_P, _P, C.POINTER(TfRect), C.c_int, C.POINTER(_P)]),
     "vr_histogram_sharded": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), _P]),
     "vr_volume_filter_sharded": (C.c_int, [_P]),
 }
@@ -399,10 +400,11 @@ class Sdf:
     """signed_distance_field (app/signed_distance_field.hpp:5-12)"""
 
     def __init__(self, ctx, volume, tf_specs, sharded=False):
+        """sharded: False single GPU; True z-slab build + gather; "slab" z-slab build only (own planes valid)"""
         arr, n = make_rects(tf_specs)
         self.h = _P()
         self.dims = volume.dims()
-        fn = lib().vr_sdf_build_sharded if sharded else lib().vr_sdf_build
+        fn = lib().vr_sdf_build_slab_only if sharded == "slab" else (lib().vr_sdf_build_sharded if sharded else lib().vr_sdf_build)
         _check(fn(ctx.h, volume.h, arr, n, C.byref(self.h)))
 
     def close(self):

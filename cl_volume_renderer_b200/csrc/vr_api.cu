@@ -454,7 +454,7 @@ extern "C" void vr_envmap_destroy(vr_envmap* e) {
 }
 
 // ---- SDF -----------------------------------------------------------------------------------------------------
-int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, vr_sdf** out, bool sharded) {
+int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, vr_sdf** out, int sharded) {
   VR_CUDA(cudaSetDevice(ctx->device));
   vr_sdf* s = new (std::nothrow) vr_sdf();
   if (!s) return VR_ERR_NOMEM;
@@ -467,7 +467,7 @@ int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, vr_sdf*
     delete s;
     return VR_ERR_CUDA;
   }
-  int st = sharded ? vrk_sdf_build_sharded(ctx, vol->current(), vol->nx, vol->ny, vol->nz, tf, s->field, &s->levels, &s->max_it, s->surf)
+  int st = sharded ? vrk_sdf_build_sharded(ctx, vol->current(), vol->nx, vol->ny, vol->nz, tf, s->field, &s->levels, &s->max_it, s->surf, sharded == 1)
                    : vrk_sdf_build(ctx, vol->current(), vol->nx, vol->ny, vol->nz, tf, s->field, &s->levels, &s->max_it, s->surf);
   if (st != VR_OK) { vr_sdf_destroy(s); return st; }
   *out = s;
@@ -490,7 +490,7 @@ extern "C" int vr_sdf_build(vr_ctx* ctx, const vr_volume* vol, const vr_tf_rect*
   VR_TRY(volume_finish(vol));
   VR_REQUIRE(n_rects >= 0 && n_rects <= VR_TF_MAX_RECTS, "vr_sdf_build: too many TF clauses");
   VR_TRY(tf_check_colours(rects, n_rects, "vr_sdf_build"));
-  return sdf_build_impl(ctx, vol, vr_make_tf_table(rects, n_rects), out, false);
+  return sdf_build_impl(ctx, vol, vr_make_tf_table(rects, n_rects), out, 0);
 }
 
 extern "C" void vr_sdf_destroy(vr_sdf* s) {
@@ -796,7 +796,7 @@ extern "C" int vr_renderer_flush(vr_renderer* r) {
   r->cache_dirty = 0;
   r->tf_active = r->tf_pending;                                  // renderer.cpp:39
   vr_sdf* fresh = nullptr;                                       // renderer.cpp:42
-  int st = sdf_build_impl(ctx, r->vol, r->tf_active, &fresh, r->sharded_build);
+  int st = sdf_build_impl(ctx, r->vol, r->tf_active, &fresh, r->sharded_build ? 1 : 0);
   if (forked) VR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // later work on the compute stream sees the reset cache
   VR_TRY(st);
   vr_sdf_destroy(r->sdf);
@@ -805,6 +805,7 @@ extern "C" int vr_renderer_flush(vr_renderer* r) {
   r->flushed_vol = nullptr;
   if (r->sampling == VR_SAMPLING_HW_LINEAR) VR_TRY(build_textures(r));
   r->flushed_vol = r->vol; r->flushed_env = r->env; r->flushed_generation = r->vol->generation;
+  r->flush_count++;
   return VR_OK;
 }
 

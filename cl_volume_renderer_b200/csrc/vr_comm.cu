@@ -159,10 +159,21 @@ extern "C" int vr_cache_allreduce(vr_renderer* r, uint8_t* host_rgba) {
   unsigned* count_dev = nullptr;
   VR_TRY(vrk_xc_gather(r, &count_dev, wide));
   if (ctx->comm && ctx->comm_size > 1) {
-    unsigned* pin = reinterpret_cast<unsigned*>(ctx->scratch_host);
-    VR_CUDA(cudaMemcpyAsync(pin, count_dev, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-    VR_CUDA(cudaStreamSynchronize(ctx->stream));
-    const size_t words = (size_t)pin[0] * (wide ? 4 : 2);  // identical on all ranks: same camera, same hit buffer
+    // the NCCL count = shaded pixels, identical on all ranks (same camera, same hit buffer).  The hit buffer is a function of
+    // camera, rows and flushed scene, so the count is read back (4 bytes + a stream synchronisation) once per such signature
+    // and a progressive loop enqueues its exchanges without ever waiting for the device.
+    const bool same = r->xc_sig_valid && r->xc_flush == r->flush_count && !memcmp(r->xc_pos, r->dirty_pos, 12) &&
+                      !memcmp(r->xc_dir, r->dirty_dir, 12) && r->cache_dirty == 1;
+    if (!same) {
+      unsigned* pin = reinterpret_cast<unsigned*>(ctx->scratch_host);
+      VR_CUDA(cudaMemcpyAsync(pin, count_dev, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+      VR_CUDA(cudaStreamSynchronize(ctx->stream));
+      r->xc_count_host = pin[0];
+      r->xc_sig_valid = r->cache_dirty == 1;  // one camera since the last reset: dirty_pos / dirty_dir describe the hit buffer
+      r->xc_flush = r->flush_count;
+      memcpy(r->xc_pos, r->dirty_pos, 12); memcpy(r->xc_dir, r->dirty_dir, 12);
+    }
+    const size_t words = (size_t)r->xc_count_host * (wide ? 4 : 2);
     if (words) VR_NCCL(ncclAllReduce(r->xchg, r->xchg, words, ncclUint32, ncclSum, comm_of(ctx), ctx->stream));
   }
   VR_TRY(vrk_xc_scatter_resolve(r, wide));
@@ -287,7 +298,19 @@ extern "C" int vr_volume_upload_sharded(vr_ctx* ctx, const int16_t* own_planes, 
     if (e != cudaSuccess) { vr_set_error("vr_volume_upload_sharded: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
   }
   if (st == VR_OK && ctx->comm && n > 1) st = gather_ranges(ctx, v->original, off, len);
-  if (st == VR_OK) st = vrk_fetch_stats(ctx, v->original, nx, ny, nz, v->stats, 0, nz);  // reference_volume.cpp:22-41 (synchronises)
+  // fetch_stats (reference_volume.cpp:22-41): every rank reduces its own planes (their gradient taps reach the gathered
+  // neighbours), one MIN all-reduce of {min v, -max v, min g, -max g} combines them
+  if (st == VR_OK) {
+    int z0 = 0, z1 = nz;
+    if (ctx->comm && n > 1) st = vr_comm_slab(ctx, nz, ctx->comm_rank, &z0, &z1);
+    if (st == VR_OK && z1 > z0) st = vrk_fetch_stats(ctx, v->original, nx, ny, nz, v->stats, z0, z1);
+    else if (st == VR_OK) { v->stats[0] = v->stats[2] = INT32_MAX; v->stats[1] = v->stats[3] = INT32_MIN; }
+    if (st == VR_OK && ctx->comm && n > 1) {
+      int32_t t[4] = {v->stats[0], v->stats[1] == INT32_MIN ? INT32_MAX : -v->stats[1], v->stats[2], v->stats[3] == INT32_MIN ? INT32_MAX : -v->stats[3]};
+      st = vr_comm_allreduce_host(ctx, t, 4, 0, 1);
+      v->stats[0] = t[0]; v->stats[1] = -t[1]; v->stats[2] = t[2]; v->stats[3] = -t[3];
+    }
+  }
   if (st != VR_OK) {
     cudaStreamSynchronize(ctx->stream);
     cudaFreeAsync(v->original, ctx->stream);
@@ -308,7 +331,7 @@ extern "C" int vr_volume_upload_sharded(vr_ctx* ctx, const int16_t* own_planes, 
 #define VR_SDF_HALO (VR_SDF_K + 2)
 
 int vrk_sdf_build_sharded(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field, int* levels_out,
-                          int* max_it_out, cudaSurfaceObject_t surf) {
+                          int* max_it_out, cudaSurfaceObject_t surf, bool gather) {
   const int n = ctx->comm_size, rank = ctx->comm_rank;
   const int max_it = std::min(std::max(nx, std::max(ny, nz)) / 2, 127);  // signed_distance_field.cpp:11 on the GLOBAL volume
   int z0s[64], z1s[64];
@@ -362,8 +385,8 @@ int vrk_sdf_build_sharded(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int n
     cudaError_t e = cudaMemcpyAsync(field + off[rank], slab_field + layer * (lo / BR), len[rank], cudaMemcpyDeviceToDevice, ctx->stream);
     if (e != cudaSuccess) { vr_set_error("vr_sdf_build_sharded: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
   }
-  if (st == VR_OK) st = gather_ranges(ctx, field, off, len);
-  if (st == VR_OK && surf) st = vrk_sdf_to_surface(ctx, field, nx, ny, nz, surf);
+  if (st == VR_OK && gather) st = gather_ranges(ctx, field, off, len);
+  if (st == VR_OK && gather && surf) st = vrk_sdf_to_surface(ctx, field, nx, ny, nz, surf);
   if (slab_field) cudaFreeAsync(slab_field, ctx->stream);
   vrk_sdf_slab_destroy(s);  // synchronises the stream
   *levels_out = 0;          // diagnostics only: the sharded build does not collect the per-level change flags
@@ -375,7 +398,13 @@ extern "C" int vr_sdf_build_sharded(vr_ctx* ctx, const vr_volume* vol, const vr_
   VR_REQUIRE(ctx && vol && out && (rects || n_rects == 0), "vr_sdf_build_sharded: null argument");
   VR_TRY(volume_finish(vol));
   VR_REQUIRE(n_rects >= 0 && n_rects <= VR_TF_MAX_RECTS, "vr_sdf_build_sharded: too many TF clauses");
-  return sdf_build_impl(ctx, vol, vr_make_tf_table(rects, n_rects), out, true);
+  return sdf_build_impl(ctx, vol, vr_make_tf_table(rects, n_rects), out, 1);
+}
+extern "C" int vr_sdf_build_slab_only(vr_ctx* ctx, const vr_volume* vol, const vr_tf_rect* rects, int n_rects, vr_sdf** out) {
+  VR_REQUIRE(ctx && vol && out && (rects || n_rects == 0), "vr_sdf_build_slab_only: null argument");
+  VR_TRY(volume_finish(vol));
+  VR_REQUIRE(n_rects >= 0 && n_rects <= VR_TF_MAX_RECTS, "vr_sdf_build_slab_only: too many TF clauses");
+  return sdf_build_impl(ctx, vol, vr_make_tf_table(rects, n_rects), out, 2);
 }
 
 extern "C" int vr_renderer_set_sharded_build(vr_renderer* r, int enable) {

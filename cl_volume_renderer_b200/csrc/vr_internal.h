@@ -177,6 +177,12 @@ struct vr_renderer {
   uint4* queue = nullptr;  // hybrid schedule: admitted primary hits (3 x uint4 each)
   size_t queue_cap = 0;
   uint2* xchg = nullptr;  // W*H compact cache entries for the spp-split exchange (allocated on first use)
+  // vr_cache_allreduce needs the number of shaded pixels on the host (the NCCL count).  It is a function of the hit buffer,
+  // i.e. of camera, rows and flushed scene: remembered per such signature, so a progressive loop reads it back once
+  bool xc_sig_valid = false;
+  unsigned xc_count_host = 0;
+  float xc_pos[3] = {0, 0, 0}, xc_dir[3] = {0, 0, 0};
+  uint64_t xc_flush = 0, flush_count = 0;
   uint32_t* xc_idx = nullptr;    // per shaded pixel: its entry in the dense exchange array (vr_cache_allreduce)
   unsigned* xc_counts = nullptr; // per 256-pixel block: shaded pixels before it; [blocks] = total
   // image-tile split: rows are dealt out in blocks of blk_rows, block b belongs to rank b % blk_n (vr_renderer_set_row_blocks)
@@ -217,7 +223,7 @@ int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const
                   int* levels_out, int* max_it_out, cudaSurfaceObject_t surf = 0);
 // the same field built z-slab-sharded over the context's communicator (vr_comm.cu); falls back to vrk_sdf_build without one
 int vrk_sdf_build_sharded(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field, int* levels_out,
-                          int* max_it_out, cudaSurfaceObject_t surf);
+                          int* max_it_out, cudaSurfaceObject_t surf, bool gather);
 size_t vrk_sdf_field_bytes(int nx, int ny, int nz);
 int vrk_sdf_unbrick(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, int8_t* linear);
 int vrk_sdf_to_surface(vr_ctx* ctx, const int8_t* field, int nx, int ny, int nz, cudaSurfaceObject_t surf);
@@ -234,7 +240,8 @@ int vrk_xc_scatter_resolve(vr_renderer* r, bool wide);
 int vrk_checksum(vr_ctx* ctx, const void* dev, size_t bytes, uint64_t* out);
 int vrk_cache_gather(vr_ctx* ctx, const uint32_t* cache, const uint32_t* idx_dev, size_t n, uint2* out_dev);
 void vr_comm_release(vr_ctx* ctx);
-int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, vr_sdf** out, bool sharded);
+// sharded: 0 single-GPU build, 1 z-slab build + gather of the field, 2 z-slab build only (the rank's own planes are valid)
+int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, vr_sdf** out, int sharded);
 int volume_finish(const vr_volume* cv);
 // hw-linear step field: per voxel cell the SDF byte + 8 quiet-octant bits, written into a 16-bit 3-D surface (vr_quiet.cu)
 int vrk_lin_field_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const int8_t* sdf_bricked, const TfTable& tf,

@@ -71,8 +71,13 @@ class SlabSdf:
 
     def __init__(self, slab, tf_specs):
         self.slab = slab
-        self.sdf = api.SdfSlab(slab.ctx, slab.vol, tf_specs, global_max_it(slab.dims_global))
         self.n_own = slab.z1 - slab.z0
+        # a rank forwards its `halo` lowest / highest OWN planes: with fewer own planes than that it would forward planes of its
+        # other halo, which are stale after K levels, and the sharded field would be silently wrong
+        if (slab.lo and self.n_own < slab.lo) or (slab.hi and self.n_own < slab.hi):
+            raise ValueError(f"z-slab of {self.n_own} planes is thinner than the halo ({max(slab.lo, slab.hi)}): use fewer ranks "
+                             f"(nz >= {SDF_HALO} * world) or the unsharded build")
+        self.sdf = api.SdfSlab(slab.ctx, slab.vol, tf_specs, global_max_it(slab.dims_global))
 
     def boundary_planes(self):
         """(send_down, recv_down, send_up, recv_up) as (first plane, plane count) in slab coordinates; None at a face"""
@@ -85,7 +90,11 @@ class SlabSdf:
         return down, up
 
     def run(self, exchange):
-        """exchange(self): overwrite the halo planes of the current bit volume with the neighbours' boundary planes"""
+        """exchange(self): overwrite the halo planes of the current bit volume with the neighbours' boundary planes.
+        STREAM CONTRACT: vr_sdf_slab_advance enqueues on the context's stream (api.Context.stream) and does not synchronise, so
+        `exchange` must either run its copies / collectives on that same stream (torch.cuda.ExternalStream(ctx.stream), as
+        tools/c5_sweep.py does) or call ctx.synchronize() first (as tests/test_sharding.py does); on any other stream the
+        transfer races the wave kernels.  The C-ABI's vr_sdf_build_sharded does all of this inside the library."""
         while not self.sdf.finished:
             self.sdf.advance(SDF_EXCHANGE_LEVELS)
             if self.sdf.finished:

@@ -259,6 +259,10 @@ int vr_volume_upload_sharded(vr_ctx* ctx, const int16_t* own_planes, int nx, int
  * whole volume (replicated).  vr_renderer_set_sharded_build makes vr_renderer_flush build its SDF this way. */
 int vr_sdf_build_sharded(vr_ctx* ctx, const vr_volume* vol, const vr_tf_rect* rects, int n_rects, vr_sdf** out);
 int vr_renderer_set_sharded_build(vr_renderer* r, int enable);
+/* the same build without the final gather: only the planes vr_comm_slab assigns to this rank are valid in the result (a consumer
+ * that works slab by slab, or writes its slab out, does not need the other ranks' planes; vr_sdf_download returns the whole
+ * array, meaningful in those planes only).  Not for rendering. */
+int vr_sdf_build_slab_only(vr_ctx* ctx, const vr_volume* vol, const vr_tf_rect* rects, int n_rects, vr_sdf** out);
 /* tf_sort_values / bilateral_filter over the rank's planes of the replicated volume + all-reduce of the bins / gather of the
  * filtered planes: same results as vr_histogram / vr_volume_filter on every rank */
 int vr_histogram_sharded(const vr_volume* vol, int width, int height, const float range[4], uint32_t* bins_out);
