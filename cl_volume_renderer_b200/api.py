@@ -86,6 +86,7 @@ SYMBOLS = {
     "vr_renderer_set_tf": (C.c_int, [_P, C.POINTER(TfRect), C.c_int]),
     "vr_renderer_set_tf_code": (C.c_int, [_P, C.c_char_p]),
     "vr_renderer_flush": (C.c_int, [_P]),
+    "vr_renderer_last_flush_kept_fields": (C.c_int, [_P]),
     "vr_renderer_reset_cache": (C.c_int, [_P]),
     "vr_render_frame": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, _P]),
     "vr_render_frames": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int, _P]),
@@ -499,6 +500,10 @@ class Renderer:
 
     def flush_changes(self):
         _check(lib().vr_renderer_flush(self.h))
+
+    @property
+    def last_flush_kept_fields(self):
+        return bool(lib().vr_renderer_last_flush_kept_fields(self.h))
 
     def reset_cache(self):
         _check(lib().vr_renderer_reset_cache(self.h))

@@ -762,6 +762,17 @@ extern "C" int vr_renderer_reset_cache(vr_renderer* r) {
   return st;
 }
 
+// same event predicate: clause count, kinds, value and gradient ranges in order — everything of is_event_gen except the colours
+static bool tf_same_predicate(const TfTable& a, const TfTable& b) {
+  if (a.n != b.n) return false;
+  for (int i = 0; i < a.n; ++i) {
+    const vr_tf_rect &x = a.r[i], &y = b.r[i];
+    if (x.flags != y.flags || memcmp(&x.min_v, &y.min_v, sizeof(float)) || memcmp(&x.max_v, &y.max_v, sizeof(float))) return false;
+    if ((x.flags & VR_TF_USE_GRADIENT) && (memcmp(&x.min_g, &y.min_g, sizeof(float)) || memcmp(&x.max_g, &y.max_g, sizeof(float)))) return false;
+  }
+  return true;
+}
+
 extern "C" int vr_renderer_flush(vr_renderer* r) {
   VR_REQUIRE(r && r->vol && r->env, "vr_renderer_flush: no scene bound (vr_renderer_set_scene)");
   VR_TRY(volume_finish(r->vol));
@@ -794,16 +805,30 @@ extern "C" int vr_renderer_flush(vr_renderer* r) {
     forked = true;
   }
   r->cache_dirty = 0;
+  // Incremental rebuild: the SDF and the step field depend on the transfer function only through its event
+  // PREDICATE (value / gradient ranges, clause order and kind), not through the colours.  A flush after a colour edit — the
+  // common edit in the reference's UI, which re-JITs three kernels and rebuilds the field for it (renderer.cpp:39-42) — keeps
+  // both when volume, environment map and sampling are those of the last flush.
+  const bool keep_field = r->sdf && r->flushed_vol == r->vol && r->flushed_env == r->env && r->flushed_generation == r->vol->generation &&
+                          r->flushed_sampling == r->sampling && r->flushed_sharded == r->sharded_build &&
+                          tf_same_predicate(r->tf_active, r->tf_pending) &&
+                          (r->sampling != VR_SAMPLING_HW_LINEAR || (r->vol_tex && r->env_tex && r->lin_surf));
   r->tf_active = r->tf_pending;                                  // renderer.cpp:39
-  vr_sdf* fresh = nullptr;                                       // renderer.cpp:42
-  int st = sdf_build_impl(ctx, r->vol, r->tf_active, &fresh, r->sharded_build ? 1 : 0);
-  if (forked) VR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // later work on the compute stream sees the reset cache
-  VR_TRY(st);
-  vr_sdf_destroy(r->sdf);
-  r->sdf = fresh;
+  if (!keep_field) {
+    vr_sdf* fresh = nullptr;                                     // renderer.cpp:42
+    int st = sdf_build_impl(ctx, r->vol, r->tf_active, &fresh, r->sharded_build ? 1 : 0);
+    if (forked) VR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // later work on the compute stream sees the reset cache
+    forked = false;
+    VR_TRY(st);
+    vr_sdf_destroy(r->sdf);
+    r->sdf = fresh;
+  }
+  if (forked) VR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  r->fields_kept = keep_field;
   VR_CUDA(cudaMemsetAsync(r->hit, 0xFF, (size_t)r->W * r->H * 4, r->ctx->stream));
   r->flushed_vol = nullptr;
-  if (r->sampling == VR_SAMPLING_HW_LINEAR) VR_TRY(build_textures(r));
+  if (r->sampling == VR_SAMPLING_HW_LINEAR && !keep_field) VR_TRY(build_textures(r));
+  r->flushed_sampling = r->sampling; r->flushed_sharded = r->sharded_build;
   r->flushed_vol = r->vol; r->flushed_env = r->env; r->flushed_generation = r->vol->generation;
   r->flush_count++;
   return VR_OK;
@@ -975,6 +1000,7 @@ extern "C" int vr_cache_download_at(const vr_renderer* r, const uint32_t* voxels
 }
 
 extern "C" const vr_sdf* vr_renderer_sdf(const vr_renderer* r) { return r ? r->sdf : nullptr; }
+extern "C" int vr_renderer_last_flush_kept_fields(const vr_renderer* r) { return r && r->fields_kept ? 1 : 0; }
 
 extern "C" int vr_renderer_set_token_cap(vr_renderer* r, int cap) {
   VR_REQUIRE(r && cap >= 1 && cap <= 256, "vr_renderer_set_token_cap: cap must be in [1,256]");

@@ -138,6 +138,9 @@ struct vr_renderer {
   const vr_volume* flushed_vol = nullptr;
   const vr_envmap* flushed_env = nullptr;
   uint64_t flushed_generation = 0;
+  int flushed_sampling = -1;
+  bool flushed_sharded = false;
+  bool fields_kept = false;           // the last flush kept SDF and step field (same event predicate: only colours changed)
   uchar4* filtered = nullptr;         // vr_renderer_filter_frame writes here: the traced frame stays as it is
   // schedule tuning (vr_renderer_set_tuning): never changes a result
   struct Tuning {

@@ -136,8 +136,11 @@ int vr_renderer_set_scene(vr_renderer* r, const vr_volume* vol, const vr_envmap*
 int vr_renderer_set_tf(vr_renderer* r, const vr_tf_rect* rects, int n_rects);
 int vr_renderer_set_tf_code(vr_renderer* r, const char* is_event_gen_src);
 /* flush_changes, renderer.cpp:25-43: (re)allocate + zero the voxel cache (buffer_reset.cl:3-13),
- * adopt the pending TF, rebuild the SDF. */
+ * adopt the pending TF, rebuild the SDF.  Incremental: when only the COLOURS of the transfer function changed since the last
+ * flush (same clauses, same value / gradient ranges; same volume, environment map and sampling), the SDF — and the hw-linear
+ * step field and textures — are kept, since they depend on the event predicate only; vr_renderer_last_flush_kept_fields tells. */
 int vr_renderer_flush(vr_renderer* r);
+int vr_renderer_last_flush_kept_fields(const vr_renderer* r);
 /* buffer_reset only (renderer.cpp:32-35) */
 int vr_renderer_reset_cache(vr_renderer* r);
 /* render_frame, renderer.cpp:131-158 + ray_marching.cl:152-199: one sample per pixel accumulated into the

@@ -878,3 +878,41 @@ def test_hw_linear_fetch_equals_oracle_model_incl_ties_and_large_values(vr_ctx):
         assert np.array_equal(got, want), (which, int((got != want).sum()))
         r.close(); vol.close()
     env.close()
+
+
+@pytest.mark.parametrize("sampling", [api.VR_SAMPLING_NEAREST, api.VR_SAMPLING_HW_LINEAR], ids=["nearest", "hw_linear"])
+def test_flush_after_a_colour_edit_keeps_the_fields_and_renders_the_new_colours(vr_ctx, sampling):
+    """Incremental rebuild: a flush whose transfer function differs from the last one in colours only keeps the SDF
+    (and the hw-linear step field); a threshold edit, a new volume generation or a sampling switch rebuilds.  Either way the
+    frames are those of a fresh renderer with that transfer function."""
+    n, W, H = 48, 96, 64
+    v, envimg = synth.synth_ct(n), synth.synth_env(128, 64)
+    pos, d = synth.default_camera(n)
+    seeds = synth.glibc_rand(3)
+
+    def tf(lo, col):
+        return [{"min_v": lo, "max_v": 1200.0, "min_g": 0.0, "max_g": 4000.0, "flags": 0, "rgba": col}]
+
+    def fresh(t):
+        vol2, env2 = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
+        r2 = api.Renderer(vr_ctx, W, H); r2.set_sampling(sampling); r2.image_set(vol2, env2); r2.set_tf(t); r2.flush_changes()
+        f = r2.render_frames(pos, d, seeds); c = r2.cache_download()
+        r2.close(); env2.close(); vol2.close()
+        return f, c
+
+    vol, env = api.Volume(vr_ctx, v), api.EnvMap(vr_ctx, envimg)
+    r = api.Renderer(vr_ctx, W, H); r.set_sampling(sampling); r.image_set(vol, env)
+    r.set_tf(tf(500.0, (255, 255, 255, 255))); r.flush_changes()
+    assert not r.last_flush_kept_fields
+    r.render_frames(pos, d, seeds)
+    for t, kept in ((tf(500.0, (255, 64, 32, 128)), True), (tf(500.0, (10, 200, 255, 255)), True), (tf(650.0, (10, 200, 255, 255)), False),
+                    (tf(650.0, (255, 255, 255, 40)), True)):
+        r.set_tf(t); r.flush_changes()
+        assert r.last_flush_kept_fields == kept
+        f = r.render_frames(pos, d, seeds)
+        wf, wc = fresh(t)
+        assert np.array_equal(r.cache_download(), wc) and np.array_equal(f, wf)
+    vol.filter()                      # new volume generation: rebuild
+    r.flush_changes()
+    assert not r.last_flush_kept_fields
+    r.close(); env.close(); vol.close()
