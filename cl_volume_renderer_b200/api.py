@@ -133,6 +133,7 @@ SYMBOLS = {
     "vr_renderer_set_row_blocks": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "vr_frame_allgather": (C.c_int, [_P, _P]),
     "vr_volume_upload_sharded": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vr_volume_upload_sharded_async": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "vr_sdf_build_sharded": (C.c_int, [_P, _P, C.POINTER(TfRect), C.c_int, C.POINTER(_P)]),
     "vr_renderer_set_sharded_build": (C.c_int, [_P, C.c_int]),
     "vr_sdf_build_slab_only": (C.c_int, [_P, _P, C.POINTER(TfRect), C.c_int, C.POINTER(_P)]),
@@ -308,7 +309,8 @@ class Volume:
             gx, gy, gz = sharded_dims
             z0, z1 = ctx.comm_slab(gz)
             assert (nx, ny, nz) == (gx, gy, z1 - z0), "sharded upload: pass exactly this rank's planes"
-            _check(lib().vr_volume_upload_sharded(ctx.h, _vp(voxels), gx, gy, gz, C.byref(self.h)))
+            fn = lib().vr_volume_upload_sharded_async if async_upload else lib().vr_volume_upload_sharded
+            _check(fn(ctx.h, _vp(voxels), gx, gy, gz, C.byref(self.h)))
         elif async_upload:
             assert interior is None
             _check(lib().vr_volume_upload_async(ctx.h, _vp(voxels), nx, ny, nz, C.byref(self.h)))

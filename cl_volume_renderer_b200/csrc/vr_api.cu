@@ -28,14 +28,14 @@ static void pool_free(vr_ctx* ctx, void* p) {
   if (p) cudaFreeAsync(p, ctx->stream);
 }
 
-static cudaError_t pinned_acquire(vr_ctx* ctx, void** p, size_t bytes) {
+cudaError_t pinned_acquire(vr_ctx* ctx, void** p, size_t bytes) {
   for (auto& b : ctx->pinned)
     if (!b.in_use && b.bytes == bytes) { b.in_use = true; *p = b.p; return cudaSuccess; }
   cudaError_t e = cudaMallocHost(p, bytes);
   if (e == cudaSuccess) ctx->pinned.push_back({*p, bytes, true});
   return e;
 }
-static void pinned_release(vr_ctx* ctx, void* p) {
+void pinned_release(vr_ctx* ctx, void* p) {
   for (auto& b : ctx->pinned)
     if (b.p == p) b.in_use = false;
 }

@@ -30,6 +30,7 @@ struct NcclApi {
   decltype(&::ncclGroupStart) GroupStart = nullptr;
   decltype(&::ncclGroupEnd) GroupEnd = nullptr;
   decltype(&::ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&::ncclCommSplit) CommSplit = nullptr;  // optional (NCCL >= 2.18): the copy-stream communicator
   bool ok = false;
 } g_nccl;
 
@@ -46,6 +47,7 @@ int nccl_bind() {
   VR_BIND(GetUniqueId); VR_BIND(CommInitRank); VR_BIND(CommDestroy); VR_BIND(AllReduce); VR_BIND(AllGather); VR_BIND(Broadcast);
   VR_BIND(Send); VR_BIND(Recv); VR_BIND(GroupStart); VR_BIND(GroupEnd); VR_BIND(GetErrorString);
 #undef VR_BIND
+  g_nccl.CommSplit = reinterpret_cast<decltype(g_nccl.CommSplit)>(dlsym(h, "ncclCommSplit"));
   if (!all) { vr_set_error("vr_comm: libnccl.so.2 lacks an expected symbol"); return VR_ERR_INVALID; }
   g_nccl.ok = true;
   return VR_OK;
@@ -94,6 +96,12 @@ extern "C" int vr_comm_init(vr_ctx* ctx, int rank, int nranks, const uint8_t id[
   ncclComm_t c = nullptr;
   VR_NCCL(ncclCommInitRank(&c, nranks, u, rank));
   ctx->comm = c; ctx->comm_rank = rank; ctx->comm_size = nranks;
+  // collectives of the asynchronous sharded ingest run on the copy stream beside the compute stream's: they need a communicator
+  // of their own (operations of ONE communicator must be issued in one order on all ranks)
+  if (nranks > 1 && g_nccl.CommSplit) {
+    ncclComm_t c2 = nullptr;
+    if (g_nccl.CommSplit(c, 0, rank, &c2, nullptr) == ncclSuccess) ctx->comm_copy = c2;
+  }
   return VR_OK;
 }
 
@@ -101,6 +109,9 @@ void vr_comm_release(vr_ctx* ctx) {
   if (!ctx || !ctx->comm) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->comm_copy) ncclCommDestroy((ncclComm_t)ctx->comm_copy);
+  ctx->comm_copy = nullptr;
   ncclCommDestroy(comm_of(ctx));
   ctx->comm = nullptr; ctx->comm_rank = 0; ctx->comm_size = 1;
 }
@@ -258,12 +269,14 @@ extern "C" int vr_frame_allgather(vr_renderer* r, uint8_t* host_rgba) {
 
 // ---- sharded ingest -----------------------------------------------------------------------------------------------------------
 // in-place gather of per-rank byte ranges of one buffer: a group of broadcasts, one per rank (ranges may differ in size)
-static int gather_ranges(vr_ctx* ctx, void* base, const size_t* off, const size_t* len) {
+static int gather_ranges(vr_ctx* ctx, void* base, const size_t* off, const size_t* len, bool on_copy_stream = false) {
+  ncclComm_t comm = on_copy_stream ? (ncclComm_t)ctx->comm_copy : comm_of(ctx);
+  cudaStream_t stream = on_copy_stream ? ctx->copy_stream : ctx->stream;
   VR_NCCL(ncclGroupStart());
   for (int k = 0; k < ctx->comm_size; ++k)
     if (len[k]) {
       char* p = reinterpret_cast<char*>(base) + off[k];
-      ncclResult_t e = ncclBroadcast(p, p, len[k], ncclUint8, k, comm_of(ctx), ctx->stream);
+      ncclResult_t e = ncclBroadcast(p, p, len[k], ncclUint8, k, comm, stream);
       if (e != ncclSuccess) { ncclGroupEnd(); vr_set_error("ncclBroadcast: %s", ncclGetErrorString(e)); return VR_ERR_CUDA; }
     }
   VR_NCCL(ncclGroupEnd());
@@ -317,6 +330,60 @@ extern "C" int vr_volume_upload_sharded(vr_ctx* ctx, const int16_t* own_planes, 
     delete v;
     return st;
   }
+  *out = v;
+  return VR_OK;
+}
+
+// The same ingest without blocking: copy, gather and fetch_stats run on the context's copy stream (the gather on the copy-stream
+// communicator) beside whatever the compute stream is doing — job k+1 arrives while job k builds its SDF and renders.  Like
+// vr_volume_upload_async, every call that uses the volume waits for it; `own_planes` must stay valid until then.
+extern "C" int vr_volume_upload_sharded_async(vr_ctx* ctx, const int16_t* own_planes, int nx, int ny, int nz, vr_volume** out) {
+  VR_REQUIRE(ctx && own_planes && out, "vr_volume_upload_sharded_async: null argument");
+  if (!ctx->comm || ctx->comm_size == 1) return vr_volume_upload_async(ctx, own_planes, nx, ny, nz, out);
+  if (!ctx->comm_copy) return vr_volume_upload_sharded(ctx, own_planes, nx, ny, nz, out);  // NCCL without ncclCommSplit: blocking form
+  VR_REQUIRE(nx > 0 && ny > 0 && nz > 0, "vr_volume_upload_sharded_async: dimensions must be positive");
+  VR_REQUIRE((size_t)nx * ny * nz < ((size_t)1 << 32) - 1, "vr_volume_upload_sharded_async: more than 2^32-2 voxels");
+  const int n = ctx->comm_size;
+  VR_REQUIRE(n <= 64, "vr_volume_upload_sharded_async: more than 64 ranks");
+  VR_CUDA(cudaSetDevice(ctx->device));
+  vr_volume* v = new (std::nothrow) vr_volume();
+  if (!v) return VR_ERR_NOMEM;
+  v->ctx = ctx;
+  v->onx = v->nx = nx; v->ony = v->ny = ny; v->onz = v->nz = nz;
+  v->zlo = 0; v->zhi = nz;
+  const size_t plane = (size_t)nx * ny * sizeof(int16_t);
+  size_t off[64], len[64];
+  int st = VR_OK;
+  for (int k = 0; k < n && st == VR_OK; ++k) {
+    int z0, z1;
+    st = vr_comm_slab(ctx, nz, k, &z0, &z1);
+    off[k] = plane * z0; len[k] = plane * (z1 - z0);
+  }
+  cudaError_t e = cudaSuccess;
+  if (st == VR_OK) e = cudaMallocAsync(reinterpret_cast<void**>(&v->original), plane * nz, ctx->copy_stream);
+  if (st == VR_OK && e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&v->stats_dev), 4 * sizeof(int32_t), ctx->copy_stream);
+  if (st == VR_OK && e == cudaSuccess) e = pinned_acquire(ctx, reinterpret_cast<void**>(&v->stats_pin), 64);
+  if (st == VR_OK && e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ready, cudaEventDisableTiming);
+  if (st == VR_OK && e == cudaSuccess && len[ctx->comm_rank])
+    e = cudaMemcpyAsync(reinterpret_cast<char*>(v->original) + off[ctx->comm_rank], own_planes, len[ctx->comm_rank], cudaMemcpyHostToDevice,
+                        ctx->copy_stream);
+  if (st == VR_OK && e != cudaSuccess) { vr_set_error("vr_volume_upload_sharded_async: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+  if (st == VR_OK) st = gather_ranges(ctx, v->original, off, len, true);
+  if (st == VR_OK) st = vrk_fetch_stats_enqueue(ctx, ctx->copy_stream, v->original, nx, ny, nz, 0, nz, v->stats_dev, v->stats_pin);
+  if (st == VR_OK && (e = cudaEventRecord(v->ready, ctx->copy_stream)) != cudaSuccess) {
+    vr_set_error("vr_volume_upload_sharded_async: %s", cudaGetErrorString(e));
+    st = VR_ERR_CUDA;
+  }
+  if (st != VR_OK) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    if (v->original) cudaFreeAsync(v->original, ctx->copy_stream);
+    if (v->stats_dev) cudaFreeAsync(v->stats_dev, ctx->copy_stream);
+    if (v->stats_pin) pinned_release(ctx, v->stats_pin);
+    if (v->ready) cudaEventDestroy(v->ready);
+    delete v;
+    return st;
+  }
+  v->pending = true;
   *out = v;
   return VR_OK;
 }

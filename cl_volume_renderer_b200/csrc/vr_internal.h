@@ -51,6 +51,7 @@ struct vr_ctx {
   std::vector<Array3D> arrays3d;
   uint64_t array_clock = 0;
   void* comm = nullptr;  // ncclComm_t once vr_comm_init was called (vr_comm.cu)
+  void* comm_copy = nullptr;  // a second communicator over the same ranks for collectives on the copy stream (sharded async ingest)
   int comm_rank = 0, comm_size = 1;
 };
 int array3d_acquire(vr_ctx* ctx, int nx, int ny, int nz, int bits, cudaArray_t* arr, cudaSurfaceObject_t* surf);
@@ -246,6 +247,8 @@ void vr_comm_release(vr_ctx* ctx);
 // sharded: 0 single-GPU build, 1 z-slab build + gather of the field, 2 z-slab build only (the rank's own planes are valid)
 int sdf_build_impl(vr_ctx* ctx, const vr_volume* vol, const TfTable& tf, vr_sdf** out, int sharded);
 int volume_finish(const vr_volume* cv);
+cudaError_t pinned_acquire(vr_ctx* ctx, void** p, size_t bytes);
+void pinned_release(vr_ctx* ctx, void* p);
 // hw-linear step field: per voxel cell the SDF byte + 8 quiet-octant bits, written into a 16-bit 3-D surface (vr_quiet.cu)
 int vrk_lin_field_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const int8_t* sdf_bricked, const TfTable& tf,
                         cudaSurfaceObject_t out);

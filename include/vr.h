@@ -257,6 +257,9 @@ int vr_frame_allgather(vr_renderer* r, uint8_t* host_rgba);
  * planes arrive from the other ranks over NVLink instead of N copies of the whole volume over PCIe.  Result: the whole volume
  * on every rank, as after vr_volume_upload. */
 int vr_volume_upload_sharded(vr_ctx* ctx, const int16_t* own_planes, int nx, int ny, int nz, vr_volume** out);
+/* the same without blocking (cf. vr_volume_upload_async): copy, gather (on a second communicator, so that it can run beside the
+ * compute stream's collectives) and fetch_stats go to the copy stream; every call that uses the volume waits for it */
+int vr_volume_upload_sharded_async(vr_ctx* ctx, const int16_t* own_planes, int nx, int ny, int nz, vr_volume** out);
 /* z-slab SDF build (BASELINE config 5): every rank runs the wavefront on its slab + 16 halo planes, swaps the boundary planes
  * of the bit volume with its z-neighbours every 14 levels and gathers the field; bit-identical to vr_sdf_build.  `vol` is the
  * whole volume (replicated).  vr_renderer_set_sharded_build makes vr_renderer_flush build its SDF this way. */

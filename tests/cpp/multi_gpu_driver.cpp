@@ -123,7 +123,22 @@ int main(int argc, char** argv) {
       CHECK(vr_sdf_download(sdf2, sd.data()));
       dump(out + "/sdf_thr_filtered.bin", sd.data(), sd.size());
     }
+    // asynchronous sharded ingest (copy stream + its own communicator) while the compute stream is busy with a collective
+    vr_volume* vol_b = nullptr;
+    CHECK(vr_volume_upload_sharded_async(ctx, vox + (size_t)nx * ny * z0, nx, ny, nz, &vol_b));
+    CHECK(vr_histogram_sharded(vol, 100, 80, range, bins.data()));
+    if (rank == 0) {
+      std::vector<int16_t> back((size_t)nx * ny * nz);
+      int32_t st2[4];
+      CHECK(vr_volume_stats(vol_b, st2));
+      CHECK(vr_volume_download(vol_b, back.data()));
+      dump(out + "/volume_gathered_async.bin", back.data(), back.size() * 2);
+      printf("stats_async %d %d %d %d\n", st2[0], st2[1], st2[2], st2[3]);
+    } else {
+      CHECK(vr_volume_wait(vol_b));
+    }
     CHECK(vr_comm_barrier(ctx));
+    vr_volume_destroy(vol_b);
     vr_sdf_destroy(sdf2);
     vr_renderer_destroy(r);
     vr_envmap_destroy(env);

@@ -151,6 +151,7 @@ def _check_cpp_driver_outputs(tmp_path, vol, env, pos, d, seeds, stdout, n=64, W
     tf = synth.default_tf()
     # sharded ingest: the gathered volume is the volume
     assert np.array_equal(np.fromfile(tmp_path / "volume_gathered.bin", dtype=np.int16).reshape(vol.shape), vol)
+    assert np.array_equal(np.fromfile(tmp_path / "volume_gathered_async.bin", dtype=np.int16).reshape(vol.shape), vol)
     # z-slab SDF build inside the flush: bit-identical to the oracle
     ref = o.Renderer(vol, env, tf, Wd, Hd)
     assert np.array_equal(np.fromfile(tmp_path / "sdf.bin", dtype=np.int8).reshape(vol.shape), ref.sdf)
@@ -171,7 +172,7 @@ def _check_cpp_driver_outputs(tmp_path, vol, env, pos, d, seeds, stdout, n=64, W
     assert (tiles == want).all(axis=-1).mean() > 0.9
     # z-slab histogram and bilateral filter
     st = o.fetch_stats(vol)
-    assert f"stats {st[0]} {st[1]} {st[2]} {st[3]}" in stdout
+    assert f"stats {st[0]} {st[1]} {st[2]} {st[3]}" in stdout and f"stats_async {st[0]} {st[1]} {st[2]} {st[3]}" in stdout
     rng = [float(x) for x in st]
     assert np.array_equal(np.fromfile(tmp_path / "bins.bin", dtype=np.uint32), o.histogram(vol, 100, 80, rng))
     filt = np.fromfile(tmp_path / "filtered.bin", dtype=np.int16).reshape(vol.shape)
