@@ -164,8 +164,8 @@ int volume_finish(const vr_volume* cv) {
   vr_volume* v = const_cast<vr_volume*>(cv);
   if (!v || !v->pending) return VR_OK;
   VR_CUDA(cudaEventSynchronize(v->ready));
-  memcpy(v->stats, v->stats_pin, sizeof(v->stats));
   v->pending = false;
+  VR_TRY(vrk_fetch_stats_finalize(v->ctx, v->original, v->nx, v->ny, v->nz, v->zlo, v->zhi, v->stats_pin, v->stats));
   pinned_release(v->ctx, v->stats_pin);
   v->stats_pin = nullptr;
   pool_free(v->ctx, v->stats_dev);

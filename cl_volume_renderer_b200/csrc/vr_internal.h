@@ -206,6 +206,8 @@ int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int
 // the same on any stream, without waiting: dev4 / pin4 = 4 ints of device scratch / pinned host memory that receive the result
 int vrk_fetch_stats_enqueue(vr_ctx* ctx, cudaStream_t stream, const int16_t* vol, int nx, int ny, int nz, int zlo, int zhi,
                             int32_t* dev4, int32_t* pin4);
+// completes an enqueued fetch_stats once its transfer into pin4 has finished (accepts the integer kernel's result or reruns in fp32)
+int vrk_fetch_stats_finalize(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int zlo, int zhi, const int32_t* pin4, int32_t out[4]);
 int vrk_clip(vr_ctx* ctx, const int16_t* src, int snx, int sny, int snz, const uint32_t start[3], int16_t* dst, int nx,
              int ny, int nz);
 int vrk_bilateral(vr_ctx* ctx, const int16_t* src, int16_t* dst, int nx, int ny, int nz);

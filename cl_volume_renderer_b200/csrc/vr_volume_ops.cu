@@ -180,15 +180,77 @@ __global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8(VolView vol, VolV
   }
 }
 
+// fetch_stats in integer arithmetic (speculative; ncu on k_fetch_stats_v8: DRAM traffic exactly 2·N, issue active 80 % — the
+// int->float conversions and fp32 products of 24 differences per octet, not the memory system, were the bound).
+// (float)dx*(float)dx + ... in fp32 equals the integer dx*dx + dy*dy + dz*dz EXACTLY while every |d| < 4096 and the sum stays
+// below 2^24 (all products and partial sums are then representable).  The kernel returns {min v, max v, min S, max S} with the
+// integer S; the host accepts them when max(max v, 0) - min(min v, 0) < 4096 (every difference, border zeros included, is
+// then below 4096, so S cannot have wrapped either) and max S < 2^24, and takes the square roots itself (IEEE sqrtf on both
+// sides); anything else — volumes with neighbouring voxels more than 4095 apart — reruns the fp32 kernel.
+__global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8i(VolView vol, int32_t* __restrict__ stats, int zlo, int zhi) {
+  const int x0 = (blockIdx.x * VX + threadIdx.x) * 8;
+  const int y = blockIdx.y * VY + threadIdx.y;
+  const int z = blockIdx.z * VZ + threadIdx.z;
+  int mnv = INT32_MAX, mxv = INT32_MIN;
+  unsigned mns = 0xFFFFFFFFu, mxs = 0u;
+  if (x0 < vol.nx && y < vol.ny && z >= zlo && z < zhi) {
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    const size_t row = ((size_t)z * vol.ny + y) * vol.nx + x0;
+    const size_t sy = vol.nx, sz = (size_t)vol.nx * vol.ny;
+    const uint4 qc = __ldg(reinterpret_cast<const uint4*>(vol.v + row));
+    const uint4 qym = y > 0 ? __ldg(reinterpret_cast<const uint4*>(vol.v + row - sy)) : zero;
+    const uint4 qyp = y + 1 < vol.ny ? __ldg(reinterpret_cast<const uint4*>(vol.v + row + sy)) : zero;
+    const uint4 qzm = z > 0 ? __ldg(reinterpret_cast<const uint4*>(vol.v + row - sz)) : zero;
+    const uint4 qzp = z + 1 < vol.nz ? __ldg(reinterpret_cast<const uint4*>(vol.v + row + sz)) : zero;
+    int c[10];
+    c[0] = x0 > 0 ? (int)__ldg(vol.v + row - 1) : 0;
+    c[9] = x0 + 8 < vol.nx ? (int)__ldg(vol.v + row + 8) : 0;
+    unpack8(qc, c + 1);
+    const unsigned wym[4] = {qym.x, qym.y, qym.z, qym.w}, wyp[4] = {qyp.x, qyp.y, qyp.z, qyp.w};
+    const unsigned wzm[4] = {qzm.x, qzm.y, qzm.z, qzm.w}, wzp[4] = {qzp.x, qzp.y, qzp.z, qzp.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int sh = 16 * (k & 1);
+      const int dx = c[k + 2] - c[k];
+      const int dy = (int)(short)(wyp[k >> 1] >> sh) - (int)(short)(wym[k >> 1] >> sh);
+      const int dz = (int)(short)(wzp[k >> 1] >> sh) - (int)(short)(wzm[k >> 1] >> sh);
+      const unsigned S = (unsigned)(dx * dx) + (unsigned)(dy * dy) + (unsigned)(dz * dz);
+      mns = min(mns, S); mxs = max(mxs, S);
+      mnv = min(mnv, c[k + 1]); mxv = max(mxv, c[k + 1]);
+    }
+  }
+  for (int q = 16; q > 0; q >>= 1) {
+    mnv = min(mnv, __shfl_xor_sync(0xffffffffu, mnv, q));
+    mxv = max(mxv, __shfl_xor_sync(0xffffffffu, mxv, q));
+    mns = min(mns, __shfl_xor_sync(0xffffffffu, mns, q));
+    mxs = max(mxs, __shfl_xor_sync(0xffffffffu, mxs, q));
+  }
+  __shared__ unsigned s4[4][VX * VY * VZ / 32];
+  const int tid = threadIdx.x + VX * (threadIdx.y + VY * threadIdx.z);
+  if ((tid & 31) == 0) { s4[0][tid >> 5] = (unsigned)mnv; s4[1][tid >> 5] = (unsigned)mxv; s4[2][tid >> 5] = mns; s4[3][tid >> 5] = mxs; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < VX * VY * VZ / 32; ++w) {
+      mnv = min(mnv, (int)s4[0][w]); mxv = max(mxv, (int)s4[1][w]); mns = min(mns, s4[2][w]); mxs = max(mxs, s4[3][w]);
+    }
+    atomicMin(stats + 0, mnv); atomicMax(stats + 1, mxv);
+    atomicMin(reinterpret_cast<unsigned*>(stats) + 2, mns); atomicMax(reinterpret_cast<unsigned*>(stats) + 3, mxs);
+  }
+}
+
+// pin4[8] tells vrk_fetch_stats_finalize what pin4[0..3] will hold: 0 = the final stats, 1 = {min v, max v, min S, max S} of the
+// integer kernel (to be checked and converted)
 int vrk_fetch_stats_enqueue(vr_ctx* ctx, cudaStream_t stream, const int16_t* vol, int nx, int ny, int nz, int zlo, int zhi,
                             int32_t* dev4, int32_t* pin4) {
-  const int32_t init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};  // reference_volume.cpp:22-28
+  const bool fast = nx % 8 == 0;
+  const int32_t init[4] = {INT32_MAX, INT32_MIN, fast ? -1 : INT32_MAX, fast ? 0 : INT32_MIN};  // reference_volume.cpp:22-28 (S: unsigned)
   memcpy(pin4, init, sizeof(init));
+  pin4[8] = fast ? 1 : 0;
   VR_CUDA(cudaMemcpyAsync(dev4, pin4, sizeof(init), cudaMemcpyHostToDevice, stream));
   VolView v{vol, nx, ny, nz};
-  if (nx % 8 == 0) {
+  if (fast) {
     dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
-    k_fetch_stats_v8<false><<<grid, block, 0, stream>>>(v, v, nx, ny, dev4, zlo, zhi);
+    k_fetch_stats_v8i<<<grid, block, 0, stream>>>(v, dev4, zlo, zhi);
   } else {
     dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
     k_fetch_stats<<<grid, block, 0, stream>>>(v, dev4, zlo, zhi);
@@ -196,6 +258,34 @@ int vrk_fetch_stats_enqueue(vr_ctx* ctx, cudaStream_t stream, const int16_t* vol
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
   VR_CUDA(cudaMemcpyAsync(pin4, dev4, sizeof(init), cudaMemcpyDeviceToHost, stream));
+  return VR_OK;
+}
+
+// after the transfer into pin4 has completed: accept the integer kernel's result or rerun in fp32 (on the context's stream, blocking)
+int vrk_fetch_stats_finalize(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int zlo, int zhi, const int32_t* pin4, int32_t out[4]) {
+  if (pin4[8] == 0) { memcpy(out, pin4, 4 * sizeof(int32_t)); return VR_OK; }
+  const int mnv = pin4[0], mxv = pin4[1];
+  const unsigned mns = (unsigned)pin4[2], mxs = (unsigned)pin4[3];
+  const bool empty = mnv > mxv;  // no voxel in [zlo, zhi)
+  if (empty) { out[0] = out[2] = INT32_MAX; out[1] = out[3] = INT32_MIN; return VR_OK; }
+  if ((long long)std::max(mxv, 0) - (long long)std::min(mnv, 0) < 4096 && mxs < (1u << 24)) {
+    out[0] = mnv; out[1] = mxv;
+    out[2] = (int)sqrtf((float)mns); out[3] = (int)sqrtf((float)mxs);   // implicit float->int of atomic_min/max(int*, float)
+    return VR_OK;
+  }
+  const int32_t init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
+  int32_t* pin = ctx->scratch_host + 32;  // bytes 128.. of the pinned scratch
+  int32_t* dev = ctx->scratch + 32;
+  memcpy(pin, init, sizeof(init));
+  VR_CUDA(cudaMemcpyAsync(dev, pin, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  VolView v{vol, nx, ny, nz};
+  dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
+  k_fetch_stats_v8<false><<<grid, block, 0, ctx->stream>>>(v, v, nx, ny, dev, zlo, zhi);
+  ctx->launches++;
+  VR_CUDA(cudaGetLastError());
+  VR_CUDA(cudaMemcpyAsync(pin, dev, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, pin, sizeof(init));
   return VR_OK;
 }
 
@@ -219,8 +309,7 @@ int vrk_fetch_stats_linear(vr_ctx* ctx, const int16_t* box, int px, const int16_
 int vrk_fetch_stats(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int32_t out[4], int zlo, int zhi) {
   VR_TRY(vrk_fetch_stats_enqueue(ctx, ctx->stream, vol, nx, ny, nz, zlo, zhi, ctx->scratch, ctx->scratch_host));
   VR_CUDA(cudaStreamSynchronize(ctx->stream));
-  memcpy(out, ctx->scratch_host, 4 * sizeof(int32_t));
-  return VR_OK;
+  return vrk_fetch_stats_finalize(ctx, vol, nx, ny, nz, zlo, zhi, ctx->scratch_host, out);
 }
 
 // ---- apply_clip: reference_volume_clip.cl:4-15 ---------------------------------------------------------------

@@ -62,6 +62,28 @@ def test_fetch_stats_bit_exact(vr_ctx):
         vol.close()
 
 
+def test_fetch_stats_integer_path_and_its_fp32_fallback(vr_ctx):
+    """nx % 8 == 0 takes the speculative integer kernel: exact while neighbouring voxels are less than 4096 apart and the squared
+    gradient stays below 2^24; volumes beyond that (full-range noise, a single 5000 step, values straddling zero by 4096) must come
+    out of the fp32 rerun — all bit-exact against the oracle, blocking and asynchronous upload alike."""
+    rng = np.random.default_rng(7)
+    vols = [synth.synth_ct(64),
+            rng.integers(-32768, 32768, size=(24, 16, 40)).astype(np.int16),            # every difference huge: fallback
+            rng.integers(0, 4095, size=(16, 24, 32)).astype(np.int16),                  # range 4094 but sums up to 3*4094^2 > 2^24: fallback
+            rng.integers(-100, 100, size=(16, 16, 16)).astype(np.int16),                 # small: integer path
+            np.full((8, 8, 8), 4095, np.int16), np.full((8, 8, 16), -4096, np.int16)]   # border zeros 4095 / 4096 away
+    step = np.zeros((16, 16, 24), np.int16); step[:, :, 12:] = 5000
+    vols.append(step)
+    for v in vols:
+        want = o.fetch_stats(v)
+        vol = api.Volume(vr_ctx, v)
+        assert vol.stats() == want
+        vol.close()
+        vol = api.Volume(vr_ctx, v, async_upload=True)
+        assert vol.stats() == want
+        vol.close()
+
+
 @pytest.mark.parametrize("which", ["ragged", "x8"])  # nx % 8 == 0 takes the vectorised kernels
 def test_histogram_bit_exact(vr_ctx, which):
     v = _ragged() if which == "ragged" else synth.synth_ct(0, dims=(72, 37, 29))
