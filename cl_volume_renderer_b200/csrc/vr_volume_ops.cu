@@ -142,24 +142,28 @@ int vrk_boxavg(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int16_t*
 template <bool LINEAR>
 __global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8(VolView vol, VolView orig, int lim_x, int lim_y, int32_t* __restrict__ stats,
                                                                int zlo, int zhi) {
-  const int x0 = (blockIdx.x * VX + threadIdx.x) * 8;
-  const int y = blockIdx.y * VY + threadIdx.y;
-  const int z = blockIdx.z * VZ + threadIdx.z;
   int mnv = INT32_MAX, mxv = INT32_MIN, mng = INT32_MAX, mxg = INT32_MIN;
-  if (x0 < lim_x && y < lim_y && z >= zlo && z < zhi) {
-    const Octet o = load_octet(vol, x0, y, z);
-    float smin = grad_sq(o, 0), smax = smin;
-    const bool face = LINEAR && (y == 0 || z == 0);
-    mnv = mxv = (LINEAR && (face || x0 == 0)) ? box_edge(orig, x0, y, z) : o.c[0];
+  const unsigned tx = div_up_dev(lim_x, VX * 8), ty = div_up_dev(lim_y, VY), tz = div_up_dev(zhi, VZ);
+  for (unsigned t = blockIdx.x; t < tx * ty * tz; t += gridDim.x) {  // persistent CTAs: one set of atomics per CTA at the end
+    const int x0 = (int)(((t % tx) * VX + threadIdx.x) * 8);
+    const int y = (int)(((t / tx) % ty) * VY + threadIdx.y);
+    const int z = (int)((t / (tx * ty)) * VZ + threadIdx.z);
+    if (x0 < lim_x && y < lim_y && z >= zlo && z < zhi) {
+      const Octet o = load_octet(vol, x0, y, z);
+      float smin = grad_sq(o, 0), smax = smin;
+      const bool face = LINEAR && (y == 0 || z == 0);
+      const int v0 = (LINEAR && (face || x0 == 0)) ? box_edge(orig, x0, y, z) : o.c[0];
+      mnv = min(mnv, v0); mxv = max(mxv, v0);
 #pragma unroll
-    for (int k = 1; k < 8; ++k) {
-      if (x0 + k >= lim_x) break;
-      const float s = grad_sq(o, k);
-      smin = fminf(smin, s); smax = fmaxf(smax, s);
-      const int v = face ? box_edge(orig, x0 + k, y, z) : o.c[k];
-      mnv = min(mnv, v); mxv = max(mxv, v);
+      for (int k = 1; k < 8; ++k) {
+        if (x0 + k >= lim_x) break;
+        const float s = grad_sq(o, k);
+        smin = fminf(smin, s); smax = fmaxf(smax, s);
+        const int v = face ? box_edge(orig, x0 + k, y, z) : o.c[k];
+        mnv = min(mnv, v); mxv = max(mxv, v);
+      }
+      mng = min(mng, f2i(sqrtf(smin))); mxg = max(mxg, f2i(sqrtf(smax)));
     }
-    mng = f2i(sqrtf(smin)); mxg = f2i(sqrtf(smax));
   }
   for (int q = 16; q > 0; q >>= 1) {
     mnv = min(mnv, __shfl_xor_sync(0xffffffffu, mnv, q));
@@ -187,36 +191,60 @@ __global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8(VolView vol, VolV
 // integer S; the host accepts them when max(max v, 0) - min(min v, 0) < 4096 (every difference, border zeros included, is
 // then below 4096, so S cannot have wrapped either) and max S < 2^24, and takes the square roots itself (IEEE sqrtf on both
 // sides); anything else — volumes with neighbouring voxels more than 4095 apart — reruns the fp32 kernel.
-__global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8i(VolView vol, int32_t* __restrict__ stats, int zlo, int zhi) {
-  const int x0 = (blockIdx.x * VX + threadIdx.x) * 8;
-  const int y = blockIdx.y * VY + threadIdx.y;
-  const int z = blockIdx.z * VZ + threadIdx.z;
+// Persistent CTAs of 16 x-octets x 16 rows walk z: a thread keeps the unpacked planes z-1 and z of its octet in registers and
+// loads plane z+1 plus the rows y-1 / y+1 of plane z — three 16-byte loads per octet instead of five, and every plane of the
+// volume comes from DRAM once (the two earlier versions: one CTA per tile, whose 4 atomics per CTA on the same four words
+// serialised in L2 — 0.21 ms whatever the arithmetic cost; then persistent CTAs over scattered tiles, 0.15 ms with the z
+// neighbours re-read from DRAM, 390 MB instead of 268).  The x neighbours beyond the octet come from the neighbouring lanes.
+#define SX 16
+#define SY 16
+#define SZC 32  // planes per work item
+__global__ void __launch_bounds__(SX* SY) k_fetch_stats_v8i(VolView vol, int32_t* __restrict__ stats, int zlo, int zhi) {
   int mnv = INT32_MAX, mxv = INT32_MIN;
   unsigned mns = 0xFFFFFFFFu, mxs = 0u;
-  if (x0 < vol.nx && y < vol.ny && z >= zlo && z < zhi) {
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-    const size_t row = ((size_t)z * vol.ny + y) * vol.nx + x0;
-    const size_t sy = vol.nx, sz = (size_t)vol.nx * vol.ny;
-    const uint4 qc = __ldg(reinterpret_cast<const uint4*>(vol.v + row));
-    const uint4 qym = y > 0 ? __ldg(reinterpret_cast<const uint4*>(vol.v + row - sy)) : zero;
-    const uint4 qyp = y + 1 < vol.ny ? __ldg(reinterpret_cast<const uint4*>(vol.v + row + sy)) : zero;
-    const uint4 qzm = z > 0 ? __ldg(reinterpret_cast<const uint4*>(vol.v + row - sz)) : zero;
-    const uint4 qzp = z + 1 < vol.nz ? __ldg(reinterpret_cast<const uint4*>(vol.v + row + sz)) : zero;
-    int c[10];
-    c[0] = x0 > 0 ? (int)__ldg(vol.v + row - 1) : 0;
-    c[9] = x0 + 8 < vol.nx ? (int)__ldg(vol.v + row + 8) : 0;
-    unpack8(qc, c + 1);
-    const unsigned wym[4] = {qym.x, qym.y, qym.z, qym.w}, wyp[4] = {qyp.x, qyp.y, qyp.z, qyp.w};
-    const unsigned wzm[4] = {qzm.x, qzm.y, qzm.z, qzm.w}, wzp[4] = {qzp.x, qzp.y, qzp.z, qzp.w};
+  const unsigned tx = div_up_dev(vol.nx, SX * 8), ty = div_up_dev(vol.ny, SY), tz = div_up_dev(zhi - zlo, SZC);
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const size_t sy = vol.nx, sz = (size_t)vol.nx * vol.ny;
+  const unsigned lane = (threadIdx.x + SX * threadIdx.y) & 31;  // a warp = 16 octets of row y and 16 of row y+1
+  for (unsigned t = blockIdx.x; t < tx * ty * tz; t += gridDim.x) {
+    const int x0 = (int)(((t % tx) * SX + threadIdx.x) * 8);
+    const int y = (int)(((t / tx) % ty) * SY + threadIdx.y);
+    const int z0 = zlo + (int)(t / (tx * ty)) * SZC, z1 = min(z0 + SZC, zhi);
+    const bool in = x0 < vol.nx && y < vol.ny;
+    const size_t col = (size_t)y * vol.nx + x0;
+    int pm[8], pc[8];  // planes z-1 and z of this octet, unpacked
+    {
+      const uint4 a = (in && z0 > 0) ? __ldg(reinterpret_cast<const uint4*>(vol.v + col + sz * (size_t)(z0 - 1))) : zero;
+      const uint4 b = in ? __ldg(reinterpret_cast<const uint4*>(vol.v + col + sz * (size_t)z0)) : zero;
+      unpack8(a, pm); unpack8(b, pc);
+    }
+    for (int z = z0; z < z1; ++z) {
+      const size_t row = col + sz * (size_t)z;
+      const uint4 qzp = (in && z + 1 < vol.nz) ? __ldg(reinterpret_cast<const uint4*>(vol.v + row + sz)) : zero;
+      const uint4 qym = (in && y > 0) ? __ldg(reinterpret_cast<const uint4*>(vol.v + row - sy)) : zero;
+      const uint4 qyp = (in && y + 1 < vol.ny) ? __ldg(reinterpret_cast<const uint4*>(vol.v + row + sy)) : zero;
+      // x neighbours beyond the octet: the neighbouring lanes' edge voxels; the lanes at the ends of the CTA's row segment load theirs
+      int xl = __shfl_up_sync(0xffffffffu, pc[7], 1), xr = __shfl_down_sync(0xffffffffu, pc[0], 1);
+      if ((lane & 15) == 0) xl = (in && x0 > 0) ? (int)__ldg(vol.v + row - 1) : 0;
+      if ((lane & 15) == 15) xr = (in && x0 + 8 < vol.nx) ? (int)__ldg(vol.v + row + 8) : 0;
+      if (x0 + 8 >= vol.nx) xr = 0;  // the lane to the right, if any, is outside the volume
+      int pp[8];
+      unpack8(qzp, pp);
+      if (in) {
+        const unsigned wym[4] = {qym.x, qym.y, qym.z, qym.w}, wyp[4] = {qyp.x, qyp.y, qyp.z, qyp.w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int sh = 16 * (k & 1);
-      const int dx = c[k + 2] - c[k];
-      const int dy = (int)(short)(wyp[k >> 1] >> sh) - (int)(short)(wym[k >> 1] >> sh);
-      const int dz = (int)(short)(wzp[k >> 1] >> sh) - (int)(short)(wzm[k >> 1] >> sh);
-      const unsigned S = (unsigned)(dx * dx) + (unsigned)(dy * dy) + (unsigned)(dz * dz);
-      mns = min(mns, S); mxs = max(mxs, S);
-      mnv = min(mnv, c[k + 1]); mxv = max(mxv, c[k + 1]);
+        for (int k = 0; k < 8; ++k) {
+          const int sh = 16 * (k & 1);
+          const int dx = (k == 7 ? xr : pc[k + 1]) - (k == 0 ? xl : pc[k - 1]);
+          const int dy = (int)(short)(wyp[k >> 1] >> sh) - (int)(short)(wym[k >> 1] >> sh);
+          const int dz = pp[k] - pm[k];
+          const unsigned S = (unsigned)(dx * dx) + (unsigned)(dy * dy) + (unsigned)(dz * dz);
+          mns = min(mns, S); mxs = max(mxs, S);
+          mnv = min(mnv, pc[k]); mxv = max(mxv, pc[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { pm[k] = pc[k]; pc[k] = pp[k]; }
     }
   }
   for (int q = 16; q > 0; q >>= 1) {
@@ -225,12 +253,12 @@ __global__ void __launch_bounds__(VX* VY* VZ) k_fetch_stats_v8i(VolView vol, int
     mns = min(mns, __shfl_xor_sync(0xffffffffu, mns, q));
     mxs = max(mxs, __shfl_xor_sync(0xffffffffu, mxs, q));
   }
-  __shared__ unsigned s4[4][VX * VY * VZ / 32];
-  const int tid = threadIdx.x + VX * (threadIdx.y + VY * threadIdx.z);
+  __shared__ unsigned s4[4][SX * SY / 32];
+  const int tid = threadIdx.x + SX * threadIdx.y;
   if ((tid & 31) == 0) { s4[0][tid >> 5] = (unsigned)mnv; s4[1][tid >> 5] = (unsigned)mxv; s4[2][tid >> 5] = mns; s4[3][tid >> 5] = mxs; }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < VX * VY * VZ / 32; ++w) {
+    for (int w = 1; w < SX * SY / 32; ++w) {
       mnv = min(mnv, (int)s4[0][w]); mxv = max(mxv, (int)s4[1][w]); mns = min(mns, s4[2][w]); mxs = max(mxs, s4[3][w]);
     }
     atomicMin(stats + 0, mnv); atomicMax(stats + 1, mxv);
@@ -249,7 +277,8 @@ int vrk_fetch_stats_enqueue(vr_ctx* ctx, cudaStream_t stream, const int16_t* vol
   VR_CUDA(cudaMemcpyAsync(dev4, pin4, sizeof(init), cudaMemcpyHostToDevice, stream));
   VolView v{vol, nx, ny, nz};
   if (fast) {
-    dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
+    const size_t items = (size_t)div_up(nx, SX * 8) * div_up(ny, SY) * div_up(zhi - zlo, SZC);
+    dim3 grid((unsigned)std::min<size_t>(items, (size_t)ctx->sm_count * 8)), block(SX, SY, 1);
     k_fetch_stats_v8i<<<grid, block, 0, stream>>>(v, dev4, zlo, zhi);
   } else {
     dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
@@ -279,7 +308,8 @@ int vrk_fetch_stats_finalize(vr_ctx* ctx, const int16_t* vol, int nx, int ny, in
   memcpy(pin, init, sizeof(init));
   VR_CUDA(cudaMemcpyAsync(dev, pin, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   VolView v{vol, nx, ny, nz};
-  dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
+  const size_t tiles = (size_t)div_up(nx, VX * 8) * div_up(ny, VY) * div_up(zhi, VZ);
+  dim3 grid((unsigned)std::min<size_t>(tiles, (size_t)ctx->sm_count * 8)), block(VX, VY, VZ);
   k_fetch_stats_v8<false><<<grid, block, 0, ctx->stream>>>(v, v, nx, ny, dev, zlo, zhi);
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
@@ -296,8 +326,10 @@ int vrk_fetch_stats_linear(vr_ctx* ctx, const int16_t* box, int px, const int16_
   memcpy(ctx->scratch_host, init, sizeof(init));
   VR_CUDA(cudaMemcpyAsync(ctx->scratch, ctx->scratch_host, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   VolView b{box, px, ny + 1, nz + 1}, v{vol, nx, ny, nz};
-  dim3 grid(div_up(nx, VX * 8), div_up(ny, VY), div_up(nz, VZ)), block(VX, VY, VZ);
-  k_fetch_stats_v8<true><<<grid, block, 0, ctx->stream>>>(b, v, nx, ny, ctx->scratch, zlo, std::min(zhi, nz));
+  const int zh = std::min(zhi, nz);
+  const size_t tiles = (size_t)div_up(nx, VX * 8) * div_up(ny, VY) * div_up(zh, VZ);
+  dim3 grid((unsigned)std::min<size_t>(tiles, (size_t)ctx->sm_count * 8)), block(VX, VY, VZ);
+  k_fetch_stats_v8<true><<<grid, block, 0, ctx->stream>>>(b, v, nx, ny, ctx->scratch, zlo, zh);
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
   VR_CUDA(cudaMemcpyAsync(ctx->scratch_host, ctx->scratch, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
