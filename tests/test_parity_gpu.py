@@ -30,7 +30,11 @@ def test_sdf_reference_golden_vector(vr_ctx):
 
 @pytest.mark.parametrize("dims,tf", [((45, 37, 29), "default"), ((64, 64, 64), "default"), ((96, 80, 72), "thr"),
                                      ((8, 8, 8), "default"), ((2, 2, 2), "thr"), ((1, 5, 3), "thr"),
-                                     ((130, 20, 20), "grad")])
+                                     ((130, 20, 20), "grad"),
+                                     # rows of a multiple of 4 words run the 128-voxels-per-thread level kernel (k_sdf_wave8): one quad,
+                                     # lanes beyond the row, 8 lanes along x, rows wider than a warp tile (edge loads), ragged y / z
+                                     ((128, 40, 36), "default"), ((256, 23, 21), "thr"), ((640, 19, 18), "default"),
+                                     ((1152, 13, 11), "thr"), ((384, 70, 9), "grad")])
 def test_sdf_matches_oracle(vr_ctx, dims, tf):
     v = synth.synth_ct(0, dims=dims)
     tfs = {"default": synth.default_tf(), "thr": synth.threshold_tf(300),
