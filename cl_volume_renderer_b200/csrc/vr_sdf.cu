@@ -16,25 +16,26 @@
 // B200 formulation — a bit-parallel wavefront:
 //   A voxel's level is the first k at which it belongs to R_k, where R_0 = band and R_k = R_{k-1} | dilate(R_{k-1}); dilate takes
 //   the union over the 8 clamped corner offsets and is separable per axis.  With one BIT per voxel (32 voxels along x per
-//   word) a level is a handful of shifts and ORs per word and the working set (two 16 MiB bit volumes at 512^3) lives in L2.
-//     k_sdf_events   : E = event bit of every voxel (is_event_gen once per voxel; the reference evaluates it 9x)
-//     k_sdf_band_bits: R_0 = voxels with a clamped corner of the other event state (signed_distance_field.cl:22-48)
-//     k_sdf_wave5    : one launch per level; warp tiles of 128 x 8 x 8 voxels whose 3x3x3 tile neighbourhood did not change in
-//                      the previous level are skipped (both bit volumes already agree there).  The level at which a voxel's bit
-//                      appears is recorded in 7 bit planes (RED.OR of the new bits into plane j for every set bit j of level+1):
-//                      the wave never writes a field byte (ncu on the variants that did: that is where their time went)
-//     k_sdf_assemble : planes + event bits -> the bricked int8 field (8x8x8 bricks of 512 bytes, apron of zeros at
-//                      x == nx / y == ny / z == nz — what the ray marcher gathers from), written exactly once, coalesced
+//   word) a level is a handful of shifts and ORs per word on a 16 MiB bit volume (512^3) that the previous level left in L2.
+//     k_sdf_events    : E = event bit of every voxel (is_event_gen once per voxel; the reference evaluates it 9x)
+//     k_sdf_band_bits9: R_0 = voxels with a clamped corner of the other event state (signed_distance_field.cl:22-48)
+//     k_sdf_wave9     : one launch per level (programmatic dependent launch), R_{k-1} -> R_k, every R_k KEPT; a thread owns 128
+//                       voxels of YR rows and walks TZ planes, nothing is recorded per voxel
+//     k_sdf_count     : level of a voxel = 1 + the number of kept bit volumes in which its bit is still clear (bit-sliced counting)
+//     k_sdf_assemble8 : counts + event bits -> the bricked int8 field (8x8x8 bricks of 512 bytes, apron of zeros at
+//                       x == nx / y == ny / z == nz) and the 3-D array the ray marcher gathers from, written exactly once
+//   Rows that are not a multiple of 4 words (and volumes too large to keep max_it - 1 bit volumes) use k_sdf_wave6: two bit
+//   volumes, tile skipping, the level recorded at the moment a bit appears (RED.OR into 7 interleaved level planes).
 //   The build is an object that advances level by level (vr_sdf_slab): the single-GPU build runs it to the end, the z-slab
-//   sharded build (parallel.py) swaps halo planes of the bit volume between its ranks every K levels.
-// Alternative schedules, all bit-exact, live in vr_sdf_variants.cu and are linked into the A/B build only (`make ab` ->
-// libvr_ab.so, selected there with VR_SDF_MODE; DESIGN.md §4.2 has the table).
+//   sharded build (vr_comm.cu) swaps halo planes of the current bit volume between its ranks every K levels.
+// Alternative schedules, all bit-exact, live in tools/ab/vr_sdf_variants.cu (and k_sdf_wave5 below) and are linked into the A/B
+// build only (`make ab` -> libvr_ab.so, selected there with VR_SDF_MODE / VR_SDF_WAVE; DESIGN.md §4.2 has the table).
 #include <cstring>
 #include "vr_sdf_common.cuh"
 
 // ---- one level: R_out = R_in | dilate(R_in) -------------------------------------------------------------------------------
-// Same level semantics, one WARP per tile (4 words x 8 rows x 8 planes): lane = lx + 4*ly, the warp walks the planes.  The
-// y- and x-dilated rows yd(z') are computed once per plane (10 per tile) and reused by the planes z'-1 and z'+1, and all the
+// k_sdf_wave5 (round 1's level kernel, A/B build only): one WARP per tile (4 words x 8 rows x 8 planes), lane = lx + 4*ly, the
+// warp walks the planes.  The y- and x-dilated rows yd(z') are computed once per plane (10 per tile) and reused by the planes z'-1 and z'+1, and all the
 // per-word index arithmetic of k_sdf_wave3 (ncu: ~250 instructions per word, issue-bound) is shared by the 8 words of a
 // thread's column: ~40 instructions per word.  No block-level synchronisation.
 template <int XW, int TZ>  // words per tile row: lane = lx + XW*ly, tile = XW words x (32/XW) rows x TZ planes
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) k_sdf_wave5(WaveDims g, int tx, int ty, i
   }
 }
 
-// ---- the default level kernel --------------------------------------------------------------------------------------------------
+// ---- the level kernel for any row width (two bit volumes + level planes) -------------------------------------------------------
 // k_sdf_wave5 above spends ~105 thread instructions per word and level (ncu: 13.9 M warp instructions per level at 512^3), most
 // of them on per-lane halo handling: every lane loads the rows y-1 and y+1 itself and x-dilates both.  Here a THREAD owns a
 // column of YR rows of one word and walks TZ planes: per plane it loads YR+2 words, x-dilates each once (the neighbouring words'
@@ -624,28 +625,40 @@ int vrk_sdf_slab_create(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz,
   static const int pdl_env = getenv("VR_SDF_PDL") ? atoi(getenv("VR_SDF_PDL")) : 1;
   s->pdl = pdl_env != 0;
 #endif
-  if (s->wave == 9) {
-    if (s->variant >= W9_VARIANTS) s->variant = 0;
-    int yr, tz;
-    w9_shape(s->variant, &yr, &tz);
-    s->xl = (w.nxw / 4 > 4) ? 8 : 4;
-    w.tx = div_up(w.nxw / 4, s->xl); w.ty = div_up(ny, (32 / s->xl) * yr); w.tz = div_up(nz, tz);
-    s->nsnaps = std::max(max_it - 1, 1);
-  } else if (s->wave == 6) {
-    if (s->variant >= W6_VARIANTS) s->variant = 0;
-    int xw, gy, yr, tz;
-    w6_shape(s->variant, &xw, &gy, &yr, &tz);
-    w.tx = div_up(w.nxw, xw); w.ty = div_up(ny, gy * yr); w.tz = div_up(nz, (32 / (xw * gy)) * tz);
-  } else {
-    w.tx = (w.nxw + WT_XW - 1) / WT_XW; w.ty = (ny + WT_Y - 1) / WT_Y; w.tz = (nz + s->tile_z - 1) / s->tile_z;
-  }
   w.lastbit = (unsigned)((nx - 1) & 31);
   s->nwords = (size_t)w.nxw * ny * nz;
-  s->ntiles = (size_t)w.tx * w.ty * w.tz;
   const size_t nwords = s->nwords;
-  cudaError_t e = cudaMallocAsync(&s->scratch, ((size_t)(1 + s->nsnaps) * nwords + 2 * s->ntiles + 2 * SDF_FLAGS) * 4, ctx->stream);
-  if (e == cudaSuccess) e = cudaMallocAsync(&s->planes, (s->wave == 5 ? 7 * nwords : 16 * ((nwords + 1) / 2)) * 4, ctx->stream);
-  if (e != cudaSuccess) { vr_set_error("vr_sdf_slab_create: %s", cudaGetErrorString(e)); delete s; return VR_ERR_CUDA; }
+  for (;;) {
+    if (s->wave == 9) {
+      if (s->variant >= W9_VARIANTS) s->variant = 0;
+      int yr, tz;
+      w9_shape(s->variant, &yr, &tz);
+      s->xl = (w.nxw / 4 > 4) ? 8 : 4;
+      w.tx = div_up(w.nxw / 4, s->xl); w.ty = div_up(ny, (32 / s->xl) * yr); w.tz = div_up(nz, tz);
+      s->nsnaps = std::max(max_it - 1, 1);
+    } else if (s->wave == 6) {
+      if (s->variant >= W6_VARIANTS) s->variant = 0;
+      int xw, gy, yr, tz;
+      w6_shape(s->variant, &xw, &gy, &yr, &tz);
+      w.tx = div_up(w.nxw, xw); w.ty = div_up(ny, gy * yr); w.tz = div_up(nz, (32 / (xw * gy)) * tz);
+      s->nsnaps = 2;
+    } else {
+      w.tx = (w.nxw + WT_XW - 1) / WT_XW; w.ty = (ny + WT_Y - 1) / WT_Y; w.tz = (nz + s->tile_z - 1) / s->tile_z;
+      s->nsnaps = 2;
+    }
+    s->ntiles = (size_t)w.tx * w.ty * w.tz;
+    cudaError_t e = cudaMallocAsync(&s->scratch, ((size_t)(1 + s->nsnaps) * nwords + 2 * s->ntiles + 2 * SDF_FLAGS) * 4, ctx->stream);
+    if (e == cudaSuccess) {
+      e = cudaMallocAsync(&s->planes, (s->wave == 5 ? 7 * nwords : 16 * ((nwords + 1) / 2)) * 4, ctx->stream);
+      if (e != cudaSuccess) { cudaFreeAsync(s->scratch, ctx->stream); s->scratch = nullptr; }
+    }
+    if (e == cudaSuccess) break;
+    cudaGetLastError();
+    if (s->wave == 9) { s->wave = 6; s->variant = 0; continue; }  // no room for max_it - 1 bit volumes: two of them + level planes
+    vr_set_error("vr_sdf_slab_create: %s", cudaGetErrorString(e));
+    delete s;
+    return VR_ERR_CUDA;
+  }
   VR_CUDA(cudaMemsetAsync(s->stamps(0), 0, (2 * s->ntiles + 2 * SDF_FLAGS) * 4, ctx->stream));
   if (s->wave == 5) VR_CUDA(cudaMemsetAsync(s->planes + nwords, 0, 6 * nwords * 4, ctx->stream));
   VolView v{vol, nx, ny, nz};
