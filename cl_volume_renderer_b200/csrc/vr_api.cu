@@ -413,7 +413,7 @@ extern "C" int vr_histogram(const vr_volume* v, int width, int height, const flo
   int s = v->sampling == VR_SAMPLING_HW_LINEAR
               ? vrk_histogram_linear(v->ctx, v->box, v->box_px, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi,
                                      v->stats[0])
-              : vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi, v->stats[0]);
+              : vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi, v->stats[0], v->stats[1]);
   if (s == VR_OK) {
     cudaError_t e = cudaMemcpyAsync(bins_out, bins, bytes, cudaMemcpyDeviceToHost, v->ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(v->ctx->stream);
@@ -1147,7 +1147,7 @@ extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba
                  ? vrk_histogram_linear(ctx, r->vol->box, r->vol->box_px, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height,
                                         range, bins, r->vol->zlo, r->vol->zhi, r->vol->stats[0])
                  : vrk_histogram(ctx, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height, range, bins, r->vol->zlo,
-                                 r->vol->zhi, r->vol->stats[0]);
+                                 r->vol->zhi, r->vol->stats[0], r->vol->stats[1]);
   // renderer.cpp:65-96 without the host round trip: rounding, distinct-value ranking and colouring stay on the device
   if (status == VR_OK) status = vrk_tf_image(ctx, reinterpret_cast<int32_t*>(bins), scratch, width, height, img);
   if (status == VR_OK) {

@@ -494,7 +494,7 @@ extern "C" int vr_histogram_sharded(const vr_volume* v, int width, int height, c
   const size_t nb = (size_t)width * height;
   VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&bins), nb * 4, ctx->stream));
   int st = VR_OK;
-  if (z1 > z0) st = vrk_histogram(ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, z0, z1, v->stats[0]);
+  if (z1 > z0) st = vrk_histogram(ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, z0, z1, v->stats[0], v->stats[1]);
   else if (cudaMemsetAsync(bins, 0, nb * 4, ctx->stream) != cudaSuccess) st = VR_ERR_CUDA;
   if (st == VR_OK && ctx->comm && ctx->comm_size > 1) {
     ncclResult_t e = ncclAllReduce(bins, bins, nb, ncclUint32, ncclSum, comm_of(ctx), ctx->stream);

@@ -212,7 +212,7 @@ int vrk_clip(vr_ctx* ctx, const int16_t* src, int snx, int sny, int snz, const u
              int ny, int nz);
 int vrk_bilateral(vr_ctx* ctx, const int16_t* src, int16_t* dst, int nx, int ny, int nz);
 int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4],
-                  uint32_t* bins_dev, int zlo, int zhi, int vol_min_value = 0);
+                  uint32_t* bins_dev, int zlo, int zhi, int vol_min_value = 0, int vol_max_value = -0x7fffffff);  // max < min: range unknown
 struct vr_sdf_slab;
 int vrk_sdf_slab_create(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int max_it, vr_sdf_slab** out);
 int vrk_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* done);

@@ -558,18 +558,189 @@ __global__ void __launch_bounds__(VX* VY* VZ) k_histogram_v8(VolView vol, VolVie
   }
 }
 
+// tf_sort_values through tables.  ncu on k_histogram_v8 (r2c): 71 % issue active, ~90 instructions per voxel — IEEE sqrt, two IEEE
+// divisions and two roundf per voxel, which bit-exactness fixes.  But a voxel's column px is a function of its VALUE alone and its
+// row py of its squared gradient S alone, and both arguments are small integers for real data: when every difference of
+// neighbouring voxels (border zeros included) is below 4096 and max_g < 4096, S = dx^2 + dy^2 + dz^2 is the same number in int32
+// and in the fp32 evaluation order of length() (every product and partial sum below 2^24 is exact; a sum that is not exact is
+// above max_g^2 in both), so k_hist_tables evaluates the reference's expressions ONCE per distinct value (<= 4096) and per
+// S < HPY, and the volume pass looks them up in shared memory: ~25 instructions per voxel.  S >= HPY (steep edges) takes the
+// expressions directly.  Volumes outside the guard use k_histogram_v8.  The pass itself is k_fetch_stats_v8i's: persistent CTAs
+// walk z with the unpacked planes z-1 and z in registers, three 16-byte loads per octet.
+#define HPX 4096   // value table entries
+#define HP1 8192   // squared-gradient table, one entry per S < HP1 (gradient < 90.5)
+#define HP2 8192   // one entry per block of 128 S values up to S < 2^20 (gradient < 1024): the row if the whole block shares it
+#define HSKIP (-32768)   // the voxel is not counted (value > max_v / gradient > max_g)
+#define HNONUNI (-32767) // the block of S values spans two rows (or the skip threshold): evaluate the expression
+struct HistArgs {
+  int width, height;
+  float min_v, max_v, min_g, max_g;
+  int vmin, nval;  // table covers values vmin .. vmin + nval - 1
+};
+// the reference's expressions (histogram.cl:17-27); the host has checked that every result fits 16 bits with room for the markers
+__device__ __forceinline__ int hist_px(const HistArgs& a, int value) {
+  if ((float)value > a.max_v) return HSKIP;
+  return f2i(roundf((((float)value - a.min_v) / (a.max_v - a.min_v)) * (float)a.width));
+}
+__device__ __forceinline__ int hist_py(const HistArgs& a, unsigned S) {
+  const float g = sqrtf((float)S);
+  if (g > a.max_g) return HSKIP;
+  return f2i(roundf(((g - a.min_g) / (a.max_g - a.min_g)) * (float)a.height));
+}
+__global__ void __launch_bounds__(256) k_hist_tables(HistArgs a, short* __restrict__ pxl, short* __restrict__ pyl1, short* __restrict__ pyl2) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HPX + HP1 + HP2; i += gridDim.x * blockDim.x) {
+    if (i < HPX) pxl[i] = (short)(i < a.nval ? hist_px(a, a.vmin + i) : HSKIP);
+    else if (i < HPX + HP1) pyl1[i - HPX] = (short)hist_py(a, (unsigned)(i - HPX));
+    else {
+      const unsigned b = (unsigned)(i - HPX - HP1);
+      const int p0 = hist_py(a, b << 7), p1 = hist_py(a, (b << 7) + 127u);  // monotone in S: equal ends = one row for the block
+      pyl2[b] = (short)(p0 == p1 ? p0 : HNONUNI);
+    }
+  }
+}
+// One CTA of 16 x HBY threads per SM with (almost) all of its shared memory: the tables and a window of wc columns x wr rows of
+// the bin grid (HWBINS bins) placed at (column of the smallest value, row of gradient 0) and shaped by the host to span the
+// data's columns — 500 x 90 bins for the bench volume's 500 x 500 grid, 93 % of its voxels (the 64 x 128 window of
+// k_histogram_v8 caught a fraction of them; the rest went to global atomics one warp-merged bin at a time, and THAT was its
+// time, not the arithmetic: the table look-ups alone changed nothing, 1.06 ms both).
+#define HBY 64
+#define HZC 16       // planes per work item
+#define HWBINS 45056 // window bins (176 KiB)
+__global__ void __launch_bounds__(SX* HBY, 1) k_histogram_lut(VolView vol, uint32_t* __restrict__ bins, HistArgs a, int zlo, int zhi, int wx0,
+                                                              int wy0, int wc, int wr, const short* __restrict__ g_tables) {
+  extern __shared__ unsigned hsm[];
+  unsigned* win = hsm;                                     // wc x wr window of the bin grid
+  short* pxl = reinterpret_cast<short*>(hsm + HWBINS);     // HPX | HP1 | HP2, as k_hist_tables wrote them
+  const short* pyl1 = pxl + HPX;
+  const short* pyl2 = pyl1 + HP1;
+  const int tid = threadIdx.x + SX * threadIdx.y;
+  const int wbins = wc * wr;
+  for (int i = tid; i < wbins; i += SX * HBY) win[i] = 0;
+  for (int i = tid; i < (HPX + HP1 + HP2) / 2; i += SX * HBY) reinterpret_cast<unsigned*>(pxl)[i] = reinterpret_cast<const unsigned*>(g_tables)[i];
+  __syncthreads();
+  const unsigned tx = div_up_dev(vol.nx, SX * 8), ty = div_up_dev(vol.ny, HBY), tz = div_up_dev(zhi - zlo, HZC);
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const size_t sy = vol.nx, sz = (size_t)vol.nx * vol.ny;
+  const unsigned lane = tid & 31;  // a warp = 16 octets of row y and 16 of row y+1
+  const long long nbins = (long long)a.width * a.height;
+  for (unsigned t = blockIdx.x; t < tx * ty * tz; t += gridDim.x) {
+    const int x0 = (int)(((t % tx) * SX + threadIdx.x) * 8);
+    const int y = (int)(((t / tx) % ty) * HBY + threadIdx.y);
+    const int z0 = zlo + (int)(t / (tx * ty)) * HZC, z1 = min(z0 + HZC, zhi);
+    const bool in = x0 < vol.nx && y < vol.ny;
+    const size_t col = (size_t)y * vol.nx + x0;
+    int pm[8], pc[8];  // planes z-1 and z of this octet, unpacked
+    {
+      const uint4 qa = (in && z0 > 0) ? __ldg(reinterpret_cast<const uint4*>(vol.v + col + sz * (size_t)(z0 - 1))) : zero;
+      const uint4 qb = in ? __ldg(reinterpret_cast<const uint4*>(vol.v + col + sz * (size_t)z0)) : zero;
+      unpack8(qa, pm); unpack8(qb, pc);
+    }
+    for (int z = z0; z < z1; ++z) {
+      const size_t row = col + sz * (size_t)z;
+      const uint4 qzp = (in && z + 1 < vol.nz) ? __ldg(reinterpret_cast<const uint4*>(vol.v + row + sz)) : zero;
+      const uint4 qym = (in && y > 0) ? __ldg(reinterpret_cast<const uint4*>(vol.v + row - sy)) : zero;
+      const uint4 qyp = (in && y + 1 < vol.ny) ? __ldg(reinterpret_cast<const uint4*>(vol.v + row + sy)) : zero;
+      int xl = __shfl_up_sync(0xffffffffu, pc[7], 1), xr = __shfl_down_sync(0xffffffffu, pc[0], 1);
+      if ((lane & 15) == 0) xl = (in && x0 > 0) ? (int)__ldg(vol.v + row - 1) : 0;
+      if ((lane & 15) == 15) xr = (in && x0 + 8 < vol.nx) ? (int)__ldg(vol.v + row + 8) : 0;
+      if (x0 + 8 >= vol.nx) xr = 0;  // the lane to the right, if any, is outside the volume
+      int pp[8];
+      unpack8(qzp, pp);
+      // one shared-memory add per voxel inside the window (one per warp where all 32 lanes hit the same bin: air, the inside of
+      // a homogeneous object), one RED.ADD to the grid outside it — no warp-wide matching: steep-edge voxels are few per bin but
+      // present in almost every warp, and a match per voxel is what k_histogram_v8 spent its time on
+      const unsigned wym[4] = {qym.x, qym.y, qym.z, qym.w}, wyp[4] = {qyp.x, qyp.y, qyp.z, qyp.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int sh = 16 * (k & 1);
+        const int dx = (k == 7 ? xr : pc[k + 1]) - (k == 0 ? xl : pc[k - 1]);
+        const int dy = (int)(short)(wyp[k >> 1] >> sh) - (int)(short)(wym[k >> 1] >> sh);
+        const int dz = pp[k] - pm[k];
+        const unsigned S = (unsigned)(dx * dx) + (unsigned)(dy * dy) + (unsigned)(dz * dz);
+        const unsigned vi = (unsigned)(pc[k] - a.vmin);
+        const int px = vi < (unsigned)a.nval ? (int)pxl[vi] : hist_px(a, pc[k]);
+        int py;
+        if (S < HP1) py = pyl1[S];
+        else {
+          py = (S >> 7) < HP2 ? (int)pyl2[S >> 7] : HNONUNI;
+          if (py == HNONUNI) py = hist_py(a, S);
+        }
+        long long flat = -1;
+        int w = -1;
+        if (in && px != HSKIP && py != HSKIP) {
+          flat = (long long)px * a.height + py;
+          if (flat < 0 || flat >= nbins) flat = -1;
+          const unsigned wx = (unsigned)(px - wx0), wy = (unsigned)(py - wy0);
+          if (flat >= 0 && wx < (unsigned)wc && wy < (unsigned)wr && py < a.height) w = (int)(wx * (unsigned)wr + wy);
+        }
+        int same;
+        __match_all_sync(0xffffffffu, w, &same);
+        if (same && w >= 0) {
+          if (lane == 0) atomicAdd(&win[w], 32u);
+        } else if (w >= 0) {
+          atomicAdd(&win[w], 1u);
+        } else if (flat >= 0) {
+          atomicAdd(bins + flat, 1u);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { pm[k] = pc[k]; pc[k] = pp[k]; }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < wbins; i += SX * HBY) {
+    const unsigned c = win[i];
+    if (c) atomicAdd(bins + (long long)(wx0 + i / wr) * a.height + (wy0 + i % wr), c);  // non-zero only for bins inside the grid
+  }
+}
+
 int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4],
-                  uint32_t* bins_dev, int zlo, int zhi, int vol_min_value) {
+                  uint32_t* bins_dev, int zlo, int zhi, int vol_min_value, int vol_max_value) {
   VR_CUDA(cudaMemsetAsync(bins_dev, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
   VolView v{vol, nx, ny, nz};
   if (nx % 8 == 0) {
-    const size_t tiles = (size_t)div_up(nx, VX * 8) * div_up(ny, VY) * div_up(nz, VZ);
-    dim3 grid((unsigned)std::min<size_t>(tiles, (size_t)ctx->sm_count * 6)), block(VX, VY, VZ);
     // window origin: the bin of the smallest value at gradient 0 (same arithmetic as the kernel), clamped into the grid
     const float vr = range[1] - range[0], gr = range[3] - range[2];
     int wx0 = 0, wy0 = 0;
     if (vr > 0.0f) wx0 = std::max(0, std::min(width - 1, (int)roundf(((float)vol_min_value - range[0]) / vr * (float)width)));
     if (gr > 0.0f) wy0 = std::max(0, std::min(height - 1, (int)roundf((0.0f - range[2]) / gr * (float)height)));
+    // table path: every difference of two voxels (or a voxel and a border zero) below 4096, no counted gradient above 4095, and
+    // every column / row number the expressions can produce within 16 bits
+    const long long span = (long long)std::max(vol_max_value, 0) - (long long)std::min(vol_min_value, 0);
+    bool tables_ok = vol_max_value >= vol_min_value && span < 4096 && range[3] < 4096.0f && zhi > zlo && vr > 0.0f && gr > 0.0f;
+    if (tables_ok) {
+      const float px_lo = ((float)vol_min_value - range[0]) / vr * (float)width, px_hi = ((float)vol_max_value - range[0]) / vr * (float)width;
+      const float py_lo = (0.0f - range[2]) / gr * (float)height, py_hi = (range[3] - range[2]) / gr * (float)height;
+      tables_ok = fabsf(px_lo) < 32000.0f && fabsf(px_hi) < 32000.0f && fabsf(py_lo) < 32000.0f && fabsf(py_hi) < 32000.0f;
+    }
+    if (tables_ok) {
+      HistArgs a{width, height, range[0], range[1], range[2], range[3], vol_min_value, std::min(vol_max_value - vol_min_value + 1, HPX)};
+      short* tables = nullptr;
+      VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tables), (HPX + HP1 + HP2) * sizeof(short), ctx->stream));
+      k_hist_tables<<<(HPX + HP1 + HP2) / 256, 256, 0, ctx->stream>>>(a, tables, tables + HPX, tables + HPX + HP1);
+      const size_t smem = (size_t)HWBINS * 4 + (size_t)(HPX + HP1 + HP2) * 2;
+      static bool attr_set = false;
+      if (!attr_set) {
+        VR_CUDA(cudaFuncSetAttribute(k_histogram_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      // window: the columns the data's values span (as many as leave 16 rows), then as many rows as fit
+      const float top_v = std::min((float)vol_max_value, range[1]);
+      const int c_hi = std::max(0, std::min(width - 1, (int)roundf((top_v - range[0]) / vr * (float)width)));
+      const int ncols = std::max(1, c_hi - wx0 + 1);
+      const int wr = std::max(16, std::min(height - wy0, HWBINS / ncols));
+      const int wc = std::max(1, std::min(ncols, HWBINS / wr));
+      const int zh = std::min(zhi, nz);
+      const size_t items = (size_t)div_up(nx, SX * 8) * div_up(ny, HBY) * div_up(zh - zlo, HZC);
+      k_histogram_lut<<<(unsigned)std::min<size_t>(items, (size_t)ctx->sm_count), dim3(SX, HBY, 1), smem, ctx->stream>>>(
+          v, bins_dev, a, zlo, zh, wx0, wy0, wc, wr, tables);
+      ctx->launches += 2;
+      VR_CUDA(cudaGetLastError());
+      VR_CUDA(cudaFreeAsync(tables, ctx->stream));
+      return VR_OK;
+    }
+    const size_t tiles = (size_t)div_up(nx, VX * 8) * div_up(ny, VY) * div_up(nz, VZ);
+    dim3 grid((unsigned)std::min<size_t>(tiles, (size_t)ctx->sm_count * 6)), block(VX, VY, VZ);
     k_histogram_v8<false><<<grid, block, 0, ctx->stream>>>(v, v, nx, ny, bins_dev, width, height, range[0], range[1], range[2], range[3], zlo,
                                                           std::min(zhi, nz), wx0, wy0);
   } else {

@@ -100,6 +100,28 @@ def test_histogram_bit_exact(vr_ctx, which):
     vol.close()
 
 
+def test_histogram_table_path_bit_exact(vr_ctx):
+    """nx % 8 == 0 and every voxel difference below 4096: k_histogram_lut (columns / rows from tables of the reference's expressions,
+    steep gradients through the per-block table or the expression itself).  Noise of the full admissible span makes squared
+    gradients up to 3 * 3999^2 (beyond fp32's exact integers: those voxels are above any admissible max_g in both arithmetics)."""
+    rng = np.random.default_rng(5)
+    v = rng.integers(-2000, 2000, size=(24, 40, 64)).astype(np.int16)
+    v[8:16, 10:30, 16:48] = 1500                                        # a homogeneous block: runs, window hits
+    st = o.fetch_stats(v)
+    vol = api.Volume(vr_ctx, v)
+    for (w, h, r) in [(256, 256, st), (64, 64, [-2000, 3000, 0, 4000]), (100, 300, [-500, 1200, 20, 2500]), (31, 17, [0, 100, 5, 50])]:
+        got = vol.histogram(w, h, [float(x) for x in r])
+        want = o.histogram(v, w, h, [float(x) for x in r])
+        assert np.array_equal(got, want), (w, h, r)
+    vol.close()
+    v2 = synth.synth_ct(0, dims=(128, 48, 40))
+    st2 = o.fetch_stats(v2)
+    vol = api.Volume(vr_ctx, v2)
+    for (w, h, r) in [(500, 500, st2), (256, 128, [-2000, 3000, 0, 4000])]:
+        assert np.array_equal(vol.histogram(w, h, [float(x) for x in r]), o.histogram(v2, w, h, [float(x) for x in r]))
+    vol.close()
+
+
 def test_clip_bit_exact(vr_ctx):
     v = _ragged()
     vol = api.Volume(vr_ctx, v)

@@ -47,7 +47,8 @@ def report(path, n):
     N = n ** 3; Nc = (n - 16) ** 3
     alg = {'k_fetch_stats_v8': 2 * N, 'k_fetch_stats': 2 * N, 'k_cache_reset': 8 * N, 'k_sdf_base': 3 * N, 'k_histogram_v8': 2 * N + 4 * 250000,
            'k_histogram': 2 * N + 4 * 250000, 'k_sdf_unbrick': 2 * N, 'k_clip': 4 * Nc, 'k_bilateral': 4 * N, 'k_tf_color_frame_ranked': 8 * 250000,
-           'k_boxavg': 4 * N, 'k_lin_field': 5 * N, 'k_sdf_events_v8': 2 * N + N // 8, 'k_sdf_assemble': N + N, 'k_sdf_band_bits': 3 * N // 8}
+           'k_histogram_lut': 2 * N + 4 * 250000, 'k_sdf_count': N // 8 * 126, 'k_sdf_assemble8': N + N, 'k_sdf_band_bits9': 3 * N // 8,
+           'k_sdf_wave9': 2 * N // 8, 'k_fetch_stats_v8i': 2 * N, 'k_boxavg': 4 * N, 'k_lin_field': 5 * N, 'k_sdf_events_v8': 2 * N + N // 8, 'k_sdf_assemble': N + N, 'k_sdf_band_bits': 3 * N // 8}
     out = {}
     for k, (cnt, us) in agg.items():
         b = alg.get(k)
@@ -58,7 +59,7 @@ def report(path, n):
                   "frac_of_6461.5": round(gbs / 6461.5, 3) if gbs else None}
         print(f"{k:28s} n={cnt:4d} total={us:10.1f} us  alg={'%.0f MB' % (b/1e6) if b else '-':>10s}  {('%.0f GB/s' % gbs) if gbs else '':>10s} {('%.1f%%' % (100*gbs/6461.5)) if gbs else ''}")
     sdf = sum(v["total_us"] for k, v in out.items() if k.startswith("k_sdf_") and not k.startswith("k_sdf_unbrick"))
-    print(f"SDF build (base + levels): {sdf:.0f} us -> 3N/t = {3*N/(sdf*1e-6)/1e9:.0f} GB/s")
+    if sdf: print(f"SDF build (base + levels): {sdf:.0f} us -> 3N/t = {3*N/(sdf*1e-6)/1e9:.0f} GB/s")
     return out
 
 if __name__ == "__main__":
