@@ -455,7 +455,8 @@ int vrk_sdf_build_sharded(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int n
   if (st == VR_OK && gather) st = gather_ranges(ctx, field, off, len);
   if (st == VR_OK && gather && surf) st = vrk_sdf_to_surface(ctx, field, nx, ny, nz, surf);
   if (slab_field) cudaFreeAsync(slab_field, ctx->stream);
-  vrk_sdf_slab_destroy(s);  // synchronises the stream
+  if (st == VR_OK) st = vrk_sdf_slab_status(s);  // synchronises the stream (the destroy below would anyway)
+  vrk_sdf_slab_destroy(s);
   *levels_out = 0;          // diagnostics only: the sharded build does not collect the per-level change flags
   *max_it_out = max_it;
   return st;

@@ -279,25 +279,17 @@ __device__ __forceinline__ Quad x_dilate4(const Quad& a, const XEdge& e, const u
 }
 
 #define SDF_FLAGS 130  // flags: changed[SDF_FLAGS] | ran[SDF_FLAGS]
-template <int XL, int YR, int TZ, bool EDGE, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_sdf_wave9(WaveDims g, int tx, int ty, int tz, int level, const uint32_t* Rin, uint32_t* Rout,
-                                                         unsigned* flags, int force) {
+// one warp tile of one level: R_out = R_in | dilate(R_in) on XL*4 words x (32/XL)*YR rows x TZ planes; returns "a bit was set"
+template <int XL, int YR, int TZ, bool EDGE>
+__device__ __forceinline__ bool wave9_tile(const WaveDims& g, int tx, int ty, int tile, const uint32_t* Rin, uint32_t* Rout) {
   constexpr int GYL = 32 / XL;
   static_assert(GYL >= 2 && XL * GYL == 32, "row groups");
-  // programmatic dependent launch: the next level's CTAs may be scheduled as soon as this grid leaves room and do their index
-  // arithmetic; they wait below until this grid has completed and its bit volume is visible
-  cudaTriggerProgrammaticLaunchCompletion();
-  const int ntiles = tx * ty * tz;
   const unsigned lane = threadIdx.x & 31;
   const int lx = lane % XL, gy = lane / XL;
   const int nq = g.nxw >> 2;  // quads per row
   const unsigned plane_stride = (unsigned)g.ny * (unsigned)g.nxw;
-  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
   bool changed = false;
-  cudaGridDependencySynchronize();
-  if (level > 1 && !force && __ldcg(flags + level - 1) == 0u) return;  // grid-uniform: the previous level set nothing
-  if (blockIdx.x == 0 && threadIdx.x == 0) flags[SDF_FLAGS + level] = 1u;
-  for (int tile = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); tile < ntiles; tile += nwarps) {
+  {
     const int ttx = tile % tx, tq = tile / tx;
     const int tty = tq % ty, ttz = tq / ty;
     const int xq = ttx * XL + lx, y0 = (tty * GYL + gy) * YR, z0 = ttz * TZ;
@@ -322,21 +314,33 @@ __global__ void __launch_bounds__(128, MINB) k_sdf_wave9(WaveDims g, int tx, int
 #pragma unroll
     for (int j = 0; j < YR; ++j) { ydA[j] = Quad{0u, 0u, 0u, 0u}; ydB[j] = ydA[j]; cprev[j] = ydA[j]; }
     unsigned wout = (unsigned)z0 * plane_stride + (unsigned)y0 * (unsigned)g.nxw + (unsigned)xq * 4u;  // (row y0, plane z0 + k - 2)
-    Quad c[YR], ch;  // the plane being processed; the next plane's words are requested before this one's are used
+    // The plane being processed and a queue of PF planes already requested: an iteration is ~350 cycles of dependent work, an L2
+    // round trip more than twice that, so a plane is requested PF + 1 iterations before it is used (with one plane ahead the
+    // loop waited for every load: a lone warp took ~7 us for the 10 planes of a tile)
+    constexpr int PF = 2;
+    Quad c[YR], ch, q[PF][YR], qh[PF];
+    auto plane_offset = [&](int k) { return (unsigned)min(max(z0 - 1 + k, 0), g.nz - 1) * plane_stride; };  // 32-bit word indices: nwords <= 2^27
     {
-      const unsigned zo = (unsigned)min(max(z0 - 1, 0), g.nz - 1) * plane_stride;  // 32-bit word indices: nwords <= 2^27
+      const unsigned zo = plane_offset(0);
 #pragma unroll
       for (int j = 0; j < YR; ++j) c[j] = q_load(Rin + (zo + ro[j]), xin);
       ch = q_load(Rin + (zo + rh), hin);
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        const unsigned zi = plane_offset(1 + i);
+#pragma unroll
+        for (int j = 0; j < YR; ++j) q[i][j] = q_load(Rin + (zi + ro[j]), xin && 1 + i < TZ + 2);
+        qh[i] = q_load(Rin + (zi + rh), hin && 1 + i < TZ + 2);
+      }
     }
 #pragma unroll 1
     for (int k = 0; k < TZ + 2; ++k) {
-      const unsigned zo = (unsigned)min(max(z0 - 1 + k, 0), g.nz - 1) * plane_stride;
-      const unsigned zn = (unsigned)min(max(z0 + k, 0), g.nz - 1) * plane_stride;
+      const unsigned zo = plane_offset(k);
+      const unsigned zn = plane_offset(k + PF + 1);
       Quad cn[YR], cnh, xd[YR];
 #pragma unroll
-      for (int j = 0; j < YR; ++j) cn[j] = q_load(Rin + (zn + ro[j]), xin && k < TZ + 1);
-      cnh = q_load(Rin + (zn + rh), hin && k < TZ + 1);
+      for (int j = 0; j < YR; ++j) cn[j] = q_load(Rin + (zn + ro[j]), xin && k + PF + 1 < TZ + 2);
+      cnh = q_load(Rin + (zn + rh), hin && k + PF + 1 < TZ + 2);
 #pragma unroll
       for (int j = 0; j < YR; ++j) xd[j] = x_dilate4<EDGE>(c[j], e, Rin, zo + ro[j]);
       const Quad xh = x_dilate4<EDGE>(ch, e, Rin, zo + rh);
@@ -361,11 +365,96 @@ __global__ void __launch_bounds__(128, MINB) k_sdf_wave9(WaveDims g, int tx, int
       }
       if (k >= 2) wout += plane_stride;
 #pragma unroll
-      for (int j = 0; j < YR; ++j) { ydA[j] = ydB[j]; ydB[j] = yd[j]; cprev[j] = c[j]; c[j] = cn[j]; }
-      ch = cnh;
+      for (int j = 0; j < YR; ++j) {
+        ydA[j] = ydB[j]; ydB[j] = yd[j]; cprev[j] = c[j]; c[j] = q[0][j];
+#pragma unroll
+        for (int i = 0; i + 1 < PF; ++i) q[i][j] = q[i + 1][j];
+        q[PF - 1][j] = cn[j];
+      }
+      ch = qh[0];
+#pragma unroll
+      for (int i = 0; i + 1 < PF; ++i) qh[i] = qh[i + 1];
+      qh[PF - 1] = cnh;
     }
-  }
+    }
+  return changed;
+}
+
+template <int XL, int YR, int TZ, bool EDGE, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_sdf_wave9(WaveDims g, int tx, int ty, int tz, int level, const uint32_t* Rin, uint32_t* Rout,
+                                                         unsigned* flags, int force) {
+  // programmatic dependent launch: the next level's CTAs may be scheduled as soon as this grid leaves room and do their index
+  // arithmetic; they wait below until this grid has completed and its bit volume is visible
+  cudaTriggerProgrammaticLaunchCompletion();
+  const int ntiles = tx * ty * tz;
+  const unsigned lane = threadIdx.x & 31;
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  bool changed = false;
+  cudaGridDependencySynchronize();
+  if (level > 1 && !force && __ldcg(flags + level - 1) == 0u) return;  // grid-uniform: the previous level set nothing
+  if (blockIdx.x == 0 && threadIdx.x == 0) flags[SDF_FLAGS + level] = 1u;
+  for (int tile = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); tile < ntiles; tile += nwarps)
+    changed |= wave9_tile<XL, YR, TZ, EDGE>(g, tx, ty, tile, Rin, Rout);
   if (__any_sync(0xffffffffu, changed) && lane == 0) flags[level] = 1u;
+}
+
+// ---- all levels of a call in ONE launch, tiles synchronised point to point -----------------------------------------------------------
+// A level per launch costs ~5.5 us of launch, ramp and drain whatever the volume's size (512^3: 11.3 us per level, a volume a fifth
+// of it: 6.8 us), and a grid barrier costs no less.  But a tile of level k needs only the 3x3x3 tile neighbourhood of level k-1,
+// and because every level writes its OWN bit volume there are no write-after-read hazards at all: a warp may run ahead of the
+// rest of the grid as far as its neighbours allow.  So the grid is launched once (cooperatively: all CTAs resident, a warp per
+// tile when they fit), every tile publishes the last level it completed (fence + release store), and a warp acquires its 27
+// neighbours' counters before it starts a tile of the next level.  Stalled neighbours skew the wave locally instead of stopping it.
+// flags[2 * SDF_FLAGS] = 1 if a wait timed out (the host reports it; nothing then waits any longer).
+// Polling load: relaxed at gpu scope (served by L2).  An acquire would add an invalidation of the whole L1 (ncu: CCTL.IVALL, 16 % of
+// the kernel's stall samples) that nothing here needs — every read of a bit volume is an ld.cg, which does not look at L1 — and
+// the bit-volume loads of a tile are issued only after the counters it depends on have been seen (they are behind the branch).
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+template <int XL, int YR, int TZ, bool EDGE>
+__global__ void __launch_bounds__(128) k_sdf_flow(WaveDims g, int tx, int ty, int tz, int level0, int nlevels, uint32_t* snaps, size_t nwords,
+                                                  int* done, unsigned* flags) {
+  const int ntiles = tx * ty * tz;
+  const unsigned lane = threadIdx.x & 31;
+  const int warp0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  unsigned* const err = flags + 2 * SDF_FLAGS;
+  for (int it = level0; it < level0 + nlevels; ++it) {
+    const uint32_t* Rin = snaps + (size_t)(it - 1) * nwords;
+    uint32_t* Rout = snaps + (size_t)it * nwords;
+    bool changed = false;
+    if (warp0 == 0 && lane == 0) flags[SDF_FLAGS + it] = 1u;  // the level ran (k_sdf_count)
+    for (int tile = warp0; tile < ntiles; tile += nwarps) {
+      {  // acquire: the 3x3x3 tile neighbourhood has completed level it - 1
+        const int ttx = tile % tx, tq = tile / tx;
+        const int tty = tq % ty, ttz = tq / ty;
+        const int ox = (int)lane % 3 - 1, oy = ((int)lane / 3) % 3 - 1, oz = (int)lane / 9 - 1;
+        const int ax = ttx + ox, ay = tty + oy, az = ttz + oz;
+        const bool need = lane < 27 && (unsigned)ax < (unsigned)tx && (unsigned)ay < (unsigned)ty && (unsigned)az < (unsigned)tz;
+        const int* f = done + ((az * ty + ay) * tx + ax);
+        long long t0 = 0;
+        bool ok = !need || ld_acquire(f) >= it - 1;
+        while (!__all_sync(0xffffffffu, ok)) {
+          if (!t0) t0 = clock64();
+          __nanosleep(64);
+          if (!ok) ok = ld_acquire(f) >= it - 1;
+          int bail = 0;
+          if (lane == 0) {
+            if (clock64() - t0 > 4000000000ll) *reinterpret_cast<volatile unsigned*>(err) = 1u;  // ~2 s: a neighbour is not coming
+            bail = *reinterpret_cast<volatile unsigned*>(err) != 0u;
+          }
+          if (__shfl_sync(0xffffffffu, bail, 0)) return;  // a wait timed out somewhere: every warp gives up
+        }
+      }
+      changed |= wave9_tile<XL, YR, TZ, EDGE>(g, tx, ty, tile, Rin, Rout);
+      __syncwarp();                                // the lanes' stores happen before lane 0's release (one fence per warp:
+      if (lane == 0) st_release(done + tile, it);  // with a __threadfence() per lane in front, ncu showed two ERRBARs, 24 % of the stalls)
+    }
+    if (__any_sync(0xffffffffu, changed) && lane == 0) flags[it] = 1u;
+  }
 }
 
 // level of every voxel from the kept bit volumes R_0 .. R_{n-1}: z = the number of them in which its bit is still clear (a voxel
@@ -575,14 +664,15 @@ struct vr_sdf_slab {
   int level = 1;       // next level to run
   size_t nwords = 0, ntiles = 0;
   int wave = 9;        // level kernel
-  int variant = 0;     // tile geometry of the kernel (A/B build: VR_SDF_VARIANT)
+  int variant = -1;    // tile geometry of the kernel (-1: the kernel's default; A/B build: VR_SDF_VARIANT)
   int xl = 4;          // k_sdf_wave9: lanes along x
   int tile_z = WT_Z;   // planes per warp tile of k_sdf_wave5
   int nsnaps = 2;      // bit volumes behind E: max_it - 1 for k_sdf_wave9 (R_0 .. R_{max_it-2}), else the ping-pong pair
   uint32_t* scratch = nullptr;  // E | R[nsnaps] | stamps[2][ntiles] | flags: changed[130], ran[130]
   uint32_t* planes = nullptr;   // level planes (interleaved; planar for k_sdf_wave5)
   bool all_active = false;
-  bool pdl = true;          // k_sdf_wave9 launched with programmatic stream serialization
+  bool flow = true;         // k_sdf_wave9's tiles in one cooperative launch per call, synchronised point to point (k_sdf_flow)
+  bool pdl = true;          // else: a launch per level with programmatic stream serialization
   bool early_exit = false;  // k_sdf_wave9: levels after one that set nothing return at once (single-GPU build only: a sharded build
                             // exchanges the current bit volume, which must then have been written)
   uint32_t* E() const { return scratch; }
@@ -594,7 +684,8 @@ struct vr_sdf_slab {
   uint32_t* Rout(int it) const { return wave == 9 ? R(it) : R(it & 1); }
 };
 
-// k_sdf_wave9 instantiations: {YR, TZ, min CTAs per SM}; variant 0 is the product's
+// k_sdf_wave9 / k_sdf_flow tile shapes: {YR, TZ}.  The product uses 0 (k_sdf_flow) and 3 (k_sdf_wave9); measured at 512^3 and in a
+// size sweep
 static void w9_shape(int variant, int* yr, int* tz) {
   static const int t[W9_VARIANTS][2] = {{2, 8}, {2, 4}, {4, 4}, {4, 8}, {1, 8}, {2, 16}};
   *yr = t[variant][0]; *tz = t[variant][1];
@@ -620,9 +711,10 @@ int vrk_sdf_slab_create(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz,
   static const int var_env = getenv("VR_SDF_VARIANT") ? atoi(getenv("VR_SDF_VARIANT")) : 0;
   static const int tile_z_env = getenv("VR_SDF_TZ") ? atoi(getenv("VR_SDF_TZ")) : WT_Z;
   if (wave_env == 5 || wave_env == 6) s->wave = wave_env;
-  s->variant = std::max(var_env, 0);
+  s->variant = getenv("VR_SDF_VARIANT") ? std::max(var_env, 0) : -1;
   s->tile_z = (tile_z_env == 2 || tile_z_env == 4 || tile_z_env == 16) ? tile_z_env : WT_Z;
   static const int pdl_env = getenv("VR_SDF_PDL") ? atoi(getenv("VR_SDF_PDL")) : 1;
+  static const int flow_env = getenv("VR_SDF_FLOW") ? atoi(getenv("VR_SDF_FLOW")) : -1;
   s->pdl = pdl_env != 0;
 #endif
   w.lastbit = (unsigned)((nx - 1) & 31);
@@ -630,14 +722,23 @@ int vrk_sdf_slab_create(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz,
   const size_t nwords = s->nwords;
   for (;;) {
     if (s->wave == 9) {
-      if (s->variant >= W9_VARIANTS) s->variant = 0;
+      // One launch per level (tiles of 4 rows x 8 planes per thread, programmatic dependent launch) while a level is a single
+      // wave of CTAs at that kernel's 2 CTAs per SM; beyond that (640^3 and up on 148 SMs) the levels of a call run in one
+      // cooperative launch whose tiles synchronise point to point (k_sdf_flow, 2 rows x 8 planes).  Measured, ms per build:
+      // 256^3 0.95 / 1.06, 384^3 1.35 / 1.67, 512^3 1.79 / 2.12, 640^3 7.4 / 4.5, 768^3 11.2 / 7.1, 1024^3 34 / 15.0.
+      s->xl = (w.nxw / 4 > 4) ? 8 : 4;
+      const size_t tiles48 = (size_t)div_up(w.nxw / 4, s->xl) * div_up(ny, (32 / s->xl) * 4) * div_up(nz, 8);
+      s->flow = tiles48 > (size_t)ctx->sm_count * 8;
+#ifdef VR_AB
+      if (flow_env >= 0) s->flow = flow_env != 0;
+#endif
+      if (s->variant < 0 || s->variant >= W9_VARIANTS) s->variant = s->flow ? 0 : 3;
       int yr, tz;
       w9_shape(s->variant, &yr, &tz);
-      s->xl = (w.nxw / 4 > 4) ? 8 : 4;
       w.tx = div_up(w.nxw / 4, s->xl); w.ty = div_up(ny, (32 / s->xl) * yr); w.tz = div_up(nz, tz);
       s->nsnaps = std::max(max_it - 1, 1);
     } else if (s->wave == 6) {
-      if (s->variant >= W6_VARIANTS) s->variant = 0;
+      if (s->variant < 0 || s->variant >= W6_VARIANTS) s->variant = 0;
       int xw, gy, yr, tz;
       w6_shape(s->variant, &xw, &gy, &yr, &tz);
       w.tx = div_up(w.nxw, xw); w.ty = div_up(ny, gy * yr); w.tz = div_up(nz, (32 / (xw * gy)) * tz);
@@ -647,19 +748,19 @@ int vrk_sdf_slab_create(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz,
       s->nsnaps = 2;
     }
     s->ntiles = (size_t)w.tx * w.ty * w.tz;
-    cudaError_t e = cudaMallocAsync(&s->scratch, ((size_t)(1 + s->nsnaps) * nwords + 2 * s->ntiles + 2 * SDF_FLAGS) * 4, ctx->stream);
+    cudaError_t e = cudaMallocAsync(&s->scratch, ((size_t)(1 + s->nsnaps) * nwords + 2 * s->ntiles + 2 * SDF_FLAGS + 2) * 4, ctx->stream);
     if (e == cudaSuccess) {
       e = cudaMallocAsync(&s->planes, (s->wave == 5 ? 7 * nwords : 16 * ((nwords + 1) / 2)) * 4, ctx->stream);
       if (e != cudaSuccess) { cudaFreeAsync(s->scratch, ctx->stream); s->scratch = nullptr; }
     }
     if (e == cudaSuccess) break;
     cudaGetLastError();
-    if (s->wave == 9) { s->wave = 6; s->variant = 0; continue; }  // no room for max_it - 1 bit volumes: two of them + level planes
+    if (s->wave == 9) { s->wave = 6; s->variant = -1; continue; }  // no room for max_it - 1 bit volumes: two of them + level planes
     vr_set_error("vr_sdf_slab_create: %s", cudaGetErrorString(e));
     delete s;
     return VR_ERR_CUDA;
   }
-  VR_CUDA(cudaMemsetAsync(s->stamps(0), 0, (2 * s->ntiles + 2 * SDF_FLAGS) * 4, ctx->stream));
+  VR_CUDA(cudaMemsetAsync(s->stamps(0), 0, (2 * s->ntiles + 2 * SDF_FLAGS + 2) * 4, ctx->stream));
   if (s->wave == 5) VR_CUDA(cudaMemsetAsync(s->planes + nwords, 0, 6 * nwords * 4, ctx->stream));
   VolView v{vol, nx, ny, nz};
   if (!tf.needs_gradient && nx % 8 == 0) {
@@ -696,6 +797,30 @@ static void launch_wave9(vr_sdf_slab* s, int it, unsigned grid) {
   if (w.nxw / 4 > XL) cudaLaunchKernelEx(&cfg, k_sdf_wave9<XL, YR, TZ, true, MINB>, w, w.tx, w.ty, w.tz, it, rin, s->Rout(it), s->changed(), force);
   else cudaLaunchKernelEx(&cfg, k_sdf_wave9<XL, YR, TZ, false, MINB>, w, w.tx, w.ty, w.tz, it, rin, s->Rout(it), s->changed(), force);
 }
+// cooperative launch of k_sdf_flow: the grid must be resident (occupancy x SMs, queried once per instantiation)
+template <int XL, int YR, int TZ>
+static int launch_flow(vr_sdf_slab* s, int level0, int nlevels) {
+  vr_ctx* ctx = s->ctx;
+  WaveDims w = s->w;
+  const bool edge = w.nxw / 4 > XL;
+  void (*kern)(WaveDims, int, int, int, int, int, uint32_t*, size_t, int*, unsigned*) =
+      edge ? k_sdf_flow<XL, YR, TZ, true> : k_sdf_flow<XL, YR, TZ, false>;
+  static int occ[2] = {0, 0};
+  if (!occ[edge]) {
+    VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[edge], kern, 128, 0));
+    if (occ[edge] < 1) { vr_set_error("k_sdf_flow: no resident block"); return VR_ERR_CUDA; }
+  }
+  const unsigned grid = (unsigned)std::min<size_t>(div_up(s->ntiles, 4), (size_t)ctx->sm_count * occ[edge]);
+  int tx = w.tx, ty = w.ty, tz = w.tz;
+  uint32_t* snaps = s->R(0);
+  size_t nwords = s->nwords;
+  int* done = s->stamps(0);
+  unsigned* flags = s->changed();
+  void* args[] = {&w, &tx, &ty, &tz, &level0, &nlevels, &snaps, &nwords, &done, &flags};
+  VR_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(128), args, 0, ctx->stream));
+  return VR_OK;
+}
+
 template <int XW, int GY, int YR, int TZ>
 static void launch_wave6(vr_sdf_slab* s, int it, unsigned grid) {
   const WaveDims& w = s->w;
@@ -713,19 +838,43 @@ int vrk_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* done) {
   vr_ctx* ctx = s->ctx;
   const unsigned grid = (unsigned)std::min<size_t>(div_up(s->ntiles, 4), (size_t)ctx->sm_count * 64);  // a warp per tile, CTAs of 4 warps
   int n = 0;
+  if (s->wave == 9 && s->flow) {
+    n = std::max(0, std::min(nlevels, s->max_it - 1 - s->level));
+    if (n > 0) {
+      int st;
+#define VR_FLOW(YR, TZ) st = s->xl == 8 ? launch_flow<8, YR, TZ>(s, s->level, n) : launch_flow<4, YR, TZ>(s, s->level, n)
+      switch (s->variant) {
+#ifdef VR_AB
+        case 1: VR_FLOW(2, 4); break;
+        case 2: VR_FLOW(4, 4); break;
+        case 3: VR_FLOW(4, 8); break;
+        case 4: VR_FLOW(1, 8); break;
+        case 5: VR_FLOW(2, 16); break;
+#endif
+        default: VR_FLOW(2, 8); break;  // variant 0
+      }
+#undef VR_FLOW
+      if (st != VR_OK) return st;
+      s->level += n;
+      s->all_active = false;
+      ctx->launches++;
+    }
+    if (done) *done = n;
+    return VR_OK;
+  }
   for (; n < nlevels && s->level + 1 < s->max_it; ++n, ++s->level) {
     const int it = s->level;
     if (s->wave == 9) {
 #define VR_W9(YR, TZ, MINB) do { if (s->xl == 8) launch_wave9<8, YR, TZ, MINB>(s, it, grid); else launch_wave9<4, YR, TZ, MINB>(s, it, grid); } while (0)
       switch (s->variant) {
 #ifdef VR_AB
-        case 1: VR_W9(2, 4, 7); break;
-        case 2: VR_W9(4, 4, 4); break;
-        case 3: VR_W9(4, 8, 3); break;
-        case 4: VR_W9(1, 8, 8); break;
-        case 5: VR_W9(2, 16, 5); break;
+        case 0: VR_W9(2, 8, 4); break;
+        case 1: VR_W9(2, 4, 4); break;
+        case 2: VR_W9(4, 4, 2); break;
+        case 4: VR_W9(1, 8, 6); break;
+        case 5: VR_W9(2, 16, 4); break;
 #endif
-        default: VR_W9(2, 8, 5); break;
+        default: VR_W9(4, 8, 2); break;  // variant 3
       }
 #undef VR_W9
     } else if (s->wave == 6) {
@@ -794,6 +943,16 @@ int vrk_sdf_slab_assemble(vr_sdf_slab* s, int8_t* field, cudaSurfaceObject_t sur
   return VR_OK;
 }
 
+// blocking: has a tile of k_sdf_flow given up waiting for a neighbour?  (never observed; the field would be incomplete)
+int vrk_sdf_slab_status(vr_sdf_slab* s) {
+  if (!(s->wave == 9 && s->flow)) return VR_OK;
+  unsigned* pin = reinterpret_cast<unsigned*>(s->ctx->scratch_host);
+  VR_CUDA(cudaMemcpyAsync(pin, s->changed() + 2 * SDF_FLAGS, sizeof(unsigned), cudaMemcpyDeviceToHost, s->ctx->stream));
+  VR_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  if (pin[0] != 0u) { vr_set_error("vr_sdf: a tile of the level wave waited in vain for a neighbour"); return VR_ERR_CUDA; }
+  return VR_OK;
+}
+
 void vrk_sdf_slab_destroy(vr_sdf_slab* s) {
   if (!s) return;
   cudaFreeAsync(s->scratch, s->ctx->stream);
@@ -852,9 +1011,10 @@ int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const
   int levels = 0;
   if (st == VR_OK) {
     unsigned* hc = reinterpret_cast<unsigned*>(ctx->scratch_host);
-    cudaError_t e = cudaMemcpyAsync(hc, s->changed(), sizeof(unsigned) * 130, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(hc, s->changed(), sizeof(unsigned) * (2 * SDF_FLAGS + 1), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { vr_set_error("vrk_sdf_build: %s", cudaGetErrorString(e)); st = VR_ERR_CUDA; }
+    if (st == VR_OK && hc[2 * SDF_FLAGS] != 0) { vr_set_error("vrk_sdf_build: a tile of the level wave waited in vain for a neighbour"); st = VR_ERR_CUDA; }
     for (int it = 1; st == VR_OK && it + 1 < max_it; ++it)
       if (hc[it] != 0) levels = it;
   }

@@ -1,11 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 : > gpurun_out/s_probe2.txt
-python tools/sdf_probe.py 512 >> gpurun_out/s_probe2.txt 2>&1
-export VR_LIB=tools/ab/libvr_ab.so
-VR_SDF_WAVE=6 python tools/sdf_probe.py 512 >> gpurun_out/s_probe2.txt 2>&1
-for v in 0 1 2 3; do
-  VR_SDF_W6=$v python tools/sdf_probe.py 512 >> gpurun_out/s_probe2.txt 2>&1
-  VR_SDF_W6=$v python tools/sdf_probe.py 1000,200,136 >> gpurun_out/s_probe2.txt 2>&1
-done
+timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_sharding.py tests/test_big_gpu.py -m gpu -q -x -k "sdf or slab or 1024" --timeout=300 -p no:cacheprovider 2>&1 | tail -3
+for n in 256 512 640 1024; do timeout 120 python tools/sdf_probe.py $n >> gpurun_out/s_probe2.txt 2>&1; done
 cat gpurun_out/s_probe2.txt

@@ -14,5 +14,5 @@ for _ in range(5):
     ctx.synchronize(); t0 = time.perf_counter()
     s = api.Sdf(ctx, vol, synth.default_tf())
     ts.append(1e3 * (time.perf_counter() - t0)); lv = s.levels; ck = s.checksum(); s.close()
-env = {k: os.environ[k] for k in ("VR_SDF_MODE", "VR_SDF_WAVE", "VR_SDF_VARIANT", "VR_SDF_TZ") if k in os.environ}
+env = {k: os.environ[k] for k in ("VR_SDF_MODE", "VR_SDF_WAVE", "VR_SDF_VARIANT", "VR_SDF_TZ", "VR_SDF_FLOW", "VR_SDF_PDL") if k in os.environ}
 print(f"dims={dims} {env} sdf_build_ms min {min(ts):.3f} median {np.median(ts):.3f} levels {lv} checksum {ck:#x}")
