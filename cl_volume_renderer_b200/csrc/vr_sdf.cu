@@ -466,6 +466,22 @@ __device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uin
   s = a ^ b ^ c;
   cy = (a & b) | (c & (a | b));
 }
+// add the number of set inputs among z[0..6] (bit-sliced) into the 7-bit counters cnt
+__device__ __forceinline__ void count_add7(const uint32_t z[7], uint32_t cnt[7]) {
+  uint32_t s0, c0, s1, c1, s2, c2, s3, c3;
+  full_add(z[0], z[1], z[2], s0, c0);
+  full_add(z[3], z[4], z[5], s1, c1);
+  full_add(s0, s1, z[6], s2, c2);    // weight 1: s2
+  full_add(c0, c1, c2, s3, c3);      // weight 2: s3, weight 4: c3
+  uint32_t cy, t;
+  t = cnt[0] & s2; cnt[0] ^= s2; cy = t;                                   // + s2
+  full_add(cnt[1], s3, cy, t, cy); cnt[1] = t;                             // + 2 s3
+  full_add(cnt[2], c3, cy, t, cy); cnt[2] = t;                             // + 4 c3
+#pragma unroll
+  for (int b = 3; b < 7; ++b) { t = cnt[b] & cy; cnt[b] ^= cy; cy = t; }
+}
+// A thread owns FOUR consecutive words (rows are a multiple of 4 words here): seven 16-byte loads in flight per thread — with one
+// word per thread the pass reached 3.9 TB/s of the 2 GiB it streams.
 static __global__ void __launch_bounds__(256) k_sdf_count(WaveDims g, const uint32_t* __restrict__ snaps, unsigned nwords, int nsnaps,
                                                          const unsigned* __restrict__ flags, uint32_t* __restrict__ planes8) {
   // the levels that ran are a prefix (a level returns early only when its predecessor set nothing, and so do all after it)
@@ -477,38 +493,53 @@ static __global__ void __launch_bounds__(256) k_sdf_count(WaveDims g, const uint
   }
   __syncthreads();
   const int n = nrun;
-  for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
-    const uint32_t vm = valid_mask(g, (int)(w % (unsigned)g.nxw));
-    uint32_t cnt[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    uint32_t cur = 0u;
-    const uint32_t* p = snaps + w;
-    for (int k0 = 0; k0 < n; k0 += 7, p += (size_t)7 * nwords) {
-      uint32_t z[7];
+  const unsigned nquads = nwords >> 2;
+  const unsigned qrow = (unsigned)g.nxw >> 2;
+  for (unsigned qi = blockIdx.x * blockDim.x + threadIdx.x; qi < nquads; qi += gridDim.x * blockDim.x) {
+    const unsigned w = qi * 4u;
+    const uint32_t vm3 = (qi % qrow == qrow - 1) ? valid_mask(g, g.nxw - 1) : 0xFFFFFFFFu;  // only a row's last word can be partial
+    uint32_t cnt[4][7];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int b = 0; b < 7; ++b) cnt[c][b] = 0u;
+    uint4 cur = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* p = reinterpret_cast<const uint4*>(snaps + w);
+    const size_t stride = (size_t)nwords >> 2;  // uint4 per bit volume
+    for (int k0 = 0; k0 < n; k0 += 7, p += 7 * stride) {
+      uint4 v[7];
       const int m = n - k0;  // volumes left (this group: min(m, 7)); beyond the end nothing is clear
 #pragma unroll
-      for (int i = 0; i < 7; ++i) z[i] = (i < m) ? __ldcs(p + (size_t)i * nwords) : 0xFFFFFFFFu;
+      for (int i = 0; i < 7; ++i) v[i] = (i < m) ? __ldcs(p + (size_t)i * stride) : make_uint4(~0u, ~0u, ~0u, ~0u);
 #pragma unroll
-      for (int i = 0; i < 7; ++i) if (i < m) cur = z[i];
+      for (int i = 0; i < 7; ++i) if (i < m) cur = v[i];
+      const bool full_first = (v[0].x & v[0].y & v[0].z & (v[0].w | ~vm3)) == 0xFFFFFFFFu;
+      if (full_first) break;  // full already in the group's first volume: nothing more to count
+      uint32_t z[7];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) z[i] = ~z[i] & vm;
-      if (z[0] == 0u) break;  // full already in the group's first volume: nothing more to count
-      uint32_t s0, c0, s1, c1, s2, c2, s3, c3;
-      full_add(z[0], z[1], z[2], s0, c0);
-      full_add(z[3], z[4], z[5], s1, c1);
-      full_add(s0, s1, z[6], s2, c2);    // weight 1: s2
-      full_add(c0, c1, c2, s3, c3);      // weight 2: s3, weight 4: c3
-      uint32_t cy, t;
-      t = cnt[0] & s2; cnt[0] ^= s2; cy = t;                                   // + s2
-      full_add(cnt[1], s3, cy, t, cy); cnt[1] = t;                             // + 2 s3
-      full_add(cnt[2], c3, cy, t, cy); cnt[2] = t;                             // + 4 c3
+      for (int i = 0; i < 7; ++i) z[i] = ~v[i].x;
+      count_add7(z, cnt[0]);
 #pragma unroll
-      for (int b = 3; b < 7; ++b) { t = cnt[b] & cy; cnt[b] ^= cy; cy = t; }
-      if (z[6] == 0u) break;
+      for (int i = 0; i < 7; ++i) z[i] = ~v[i].y;
+      count_add7(z, cnt[1]);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) z[i] = ~v[i].z;
+      count_add7(z, cnt[2]);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) z[i] = ~v[i].w & vm3;
+      count_add7(z, cnt[3]);
+      if ((v[6].x & v[6].y & v[6].z & (v[6].w | ~vm3)) == 0xFFFFFFFFu) break;
     }
-    uint32_t* q = planes8 + plane_word(w);
-#pragma unroll
-    for (int b = 0; b < 7; ++b) q[2 * b] = cnt[b];
-    q[14] = cur & vm;
+    // the words w, w+1 share a 64-byte line of the interleaved planes, w+2, w+3 the next: {plane b of w, plane b of w+1} pairs
+    uint4* q = reinterpret_cast<uint4*>(planes8 + plane_word(w));
+    q[0] = make_uint4(cnt[0][0], cnt[1][0], cnt[0][1], cnt[1][1]);
+    q[1] = make_uint4(cnt[0][2], cnt[1][2], cnt[0][3], cnt[1][3]);
+    q[2] = make_uint4(cnt[0][4], cnt[1][4], cnt[0][5], cnt[1][5]);
+    q[3] = make_uint4(cnt[0][6], cnt[1][6], cur.x, cur.y);
+    q[4] = make_uint4(cnt[2][0], cnt[3][0], cnt[2][1], cnt[3][1]);
+    q[5] = make_uint4(cnt[2][2], cnt[3][2], cnt[2][3], cnt[3][3]);
+    q[6] = make_uint4(cnt[2][4], cnt[3][4], cnt[2][5], cnt[3][5]);
+    q[7] = make_uint4(cnt[2][6], cnt[3][6], cur.z, cur.w & vm3);
   }
 }
 
@@ -929,7 +960,7 @@ int vrk_sdf_slab_assemble(vr_sdf_slab* s, int8_t* field, cudaSurfaceObject_t sur
   const unsigned bg = (unsigned)std::min<size_t>(div_up(items, 8), (size_t)s->ctx->sm_count * 16);
   if (s->wave == 9) {
     // the levels run so far: R_0 .. R_{level-1}
-    const unsigned cg = (unsigned)std::min<size_t>(div_up(s->nwords, 256), (size_t)s->ctx->sm_count * 16);
+    const unsigned cg = (unsigned)std::min<size_t>(div_up(s->nwords / 4, 256), (size_t)s->ctx->sm_count * 16);
     k_sdf_count<<<cg, 256, 0, s->ctx->stream>>>(w, s->R(0), (unsigned)s->nwords, std::min(s->level, s->nsnaps), s->changed(), s->planes);
     s->ctx->launches++;
     k_sdf_assemble8<true><<<bg, 256, 0, s->ctx->stream>>>(w, s->max_it, s->E(), s->planes, field, nxwf, items, surf);
