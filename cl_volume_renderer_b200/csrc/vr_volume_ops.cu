@@ -719,11 +719,8 @@ int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int w
       VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tables), (HPX + HP1 + HP2) * sizeof(short), ctx->stream));
       k_hist_tables<<<(HPX + HP1 + HP2) / 256, 256, 0, ctx->stream>>>(a, tables, tables + HPX, tables + HPX + HP1);
       const size_t smem = (size_t)HWBINS * 4 + (size_t)(HPX + HP1 + HP2) * 2;
-      static bool attr_set = false;
-      if (!attr_set) {
-        VR_CUDA(cudaFuncSetAttribute(k_histogram_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-      }
+      // per device (a host may drive several GPUs from one process): set on every call, it is cheap
+      VR_CUDA(cudaFuncSetAttribute(k_histogram_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       // window: the columns the data's values span (as many as leave 16 rows), then as many rows as fit
       const float top_v = std::min((float)vol_max_value, range[1]);
       const int c_hi = std::max(0, std::min(width - 1, (int)roundf((top_v - range[0]) / vr * (float)width)));

@@ -142,7 +142,7 @@ def _run_cpp_driver(tmp_path, nranks, n=64, Wd=160, Hd=120, nseeds=8, block_rows
     np.asarray(d, dtype=np.float32).tofile(tmp_path / "dir.bin")
     out = subprocess.run([drv, str(tmp_path / "vol.raw"), str(n), str(n), str(n), str(tmp_path / "env.raw"), "128", "64", str(Wd), str(Hd),
                           str(tmp_path / "seeds.bin"), str(nseeds), str(nranks), str(block_rows), str(tmp_path)],
-                         capture_output=True, text=True, timeout=300)
+                         capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "EVERYTHING FINE" in out.stdout, out.stderr + out.stdout
     return vol, env, pos, d, seeds, out.stdout
 
