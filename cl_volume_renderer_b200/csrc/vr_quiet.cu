@@ -8,12 +8,9 @@
 // transfer function — `value >= min_v && value <= max_v`, or `value > K` (tf_part.cpp:60-77) — no event can occur at p, whatever
 // the gradient clause says.  c is floor(p) - 1 or floor(p), so every voxel cell floor(p) has 8 octants with one verdict each.
 //
-// k_lin_field writes, per voxel cell, 16 bits into a 3-D surface: low byte = the SDF value (what march() reads at trunc(origin),
-// utility_ray.cl:148-150), high byte = the 8 verdicts (bit ux + 2 uy + 4 uz set = quiet).  A thread owns an (x, y) column of ZC
-// cells and walks z with a three-plane window of per-plane quadrant intervals; a warp is 32 consecutive x of one row, so per
-// plane a lane loads 3 texels and gets its x neighbours by shuffle.  One test of the whole neighbourhood's interval settles all
-// eight octants of most cells.  (First version, 9 loads per plane and float compares per octant: 351 instructions per cell,
-// 1.47 ms at 512^3, issue-bound.)  Algorithmic bytes: 2 N (volume) + N (SDF) read, 2 N written.
+// The step field holds, per voxel cell, 16 bits in a 3-D surface: low byte = the SDF value (what march() reads at trunc(origin),
+// utility_ray.cl:148-150), high byte = the 8 verdicts (bit ux + 2 uy + 4 uz set = quiet).  Algorithmic bytes: 2 N (volume) + N (SDF)
+// read, 2 N written.
 #include "vr_device.cuh"
 
 // The clauses as integer intervals: voxel values are integers, so `(float)v >= min_v` is `v >= ceil(min_v)`, `(float)v <= max_v` is
@@ -43,89 +40,98 @@ __device__ __forceinline__ bool tf_interval_quiet(const TfIntervals& s, int n, i
   return true;
 }
 
-struct Quad {
-  int lo[4], hi[4];  // [ux + 2*uy]: interval of the texels {x-1+ux, x+ux} x {y-1+uy, y+uy} of one plane
-};
-
-// A warp owns 32 consecutive x of one row: a lane loads its own texel of the rows y-1, y, y+1, the x neighbours come from the
-// neighbouring lanes (lanes 0 and 1 also load the two texels beyond the ends of the warp's segment).
-__device__ __forceinline__ Quad plane_quadrants(const VolView& vol, int x0, unsigned lane, int y, int z) {
-  int t[3][3];
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int yy = y - 1 + dy;
-    const int v = vol.at(x0 + (int)lane, yy, z);  // outside the volume: border colour 0
-    const int h = lane < 2 ? vol.at(lane == 0 ? x0 - 1 : x0 + 32, yy, z) : 0;
-    int l = __shfl_up_sync(0xffffffffu, v, 1), r = __shfl_down_sync(0xffffffffu, v, 1);
-    const int h0 = __shfl_sync(0xffffffffu, h, 0), h1 = __shfl_sync(0xffffffffu, h, 1);
-    if (lane == 0) l = h0;
-    if (lane == 31) r = h1;
-    t[dy][0] = l; t[dy][1] = v; t[dy][2] = r;
-  }
-  int alo[3][2], ahi[3][2];
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    alo[dy][0] = min(t[dy][0], t[dy][1]); ahi[dy][0] = max(t[dy][0], t[dy][1]);
-    alo[dy][1] = min(t[dy][1], t[dy][2]); ahi[dy][1] = max(t[dy][1], t[dy][2]);
-  }
-  Quad q;
-#pragma unroll
-  for (int uy = 0; uy < 2; ++uy)
-#pragma unroll
-    for (int ux = 0; ux < 2; ++ux) {
-      q.lo[ux + 2 * uy] = min(alo[uy][ux], alo[uy + 1][ux]);
-      q.hi[ux + 2 * uy] = max(ahi[uy][ux], ahi[uy + 1][ux]);
-    }
-  return q;
-}
-
-template <int ZC>
-__global__ void __launch_bounds__(256) k_lin_field(VolView vol, SdfView sdf, TfTable tf, cudaSurfaceObject_t out) {
+// Round 2's first kernel computed, per voxel cell, the eight octant intervals from a three-plane window (one thread per cell
+// column, ~120 instructions per cell, 0.96 ms at 512^3).  But the interval of octant (ux, uy, uz) of cell (x, y, z) is the min / max
+// of the 2x2x2 texel block whose upper corner is c = (x + ux, y + uy, z + uz) — it belongs to the LATTICE CORNER c, and eight cells
+// share it.  So:
+//   k_lin_corners: Q(c) = 1 iff [min, max] of the texels {cx-1, cx} x {cy-1, cy} x {cz-1, cz} (0 outside the volume) meets no
+//                  clause — one test per corner, one BIT per corner (a warp = 32 consecutive cx of a corner row, ballot = word),
+//                  walking cz with the previous plane's 2x2 min / max in registers: two 2-byte loads per corner
+//   k_lin_cells  : a thread assembles four cells of a row: 5 bits of each of the four corner rows (y, y+1) x (z, z+1) give the
+//                  four verdict bytes (bit ux + 2 uy + 4 uz of cell i = Q(x + i + ux, y + uy, z + uz)), one 4-byte load the SDF
+//                  bytes, one 8-byte surface write the four 16-bit entries
+// spread the low 4 bits of b to 4 bytes 0x00/0x01
+__device__ __forceinline__ uint32_t bits4_to_bytes4(uint32_t b) { return ((b & 0xFu) * 0x00204081u) & 0x01010101u; }
+#define QC_Z 32  // corner planes per warp item
+__global__ void __launch_bounds__(256) k_lin_corners(VolView vol, TfTable tf, uint32_t* __restrict__ Q, int qw, unsigned items, unsigned rows,
+                                                     unsigned zchunks) {
   __shared__ TfIntervals iv;
   tf_intervals_init(tf, &iv, (int)threadIdx.x);
   __syncthreads();
   const unsigned lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * 32, x = x0 + (int)lane;
-  const int y = blockIdx.y * 8 + (int)(threadIdx.x >> 5);  // one row per warp
-  const int z0 = blockIdx.z * ZC;
-  if (y >= vol.ny) return;
-  Quad m = plane_quadrants(vol, x0, lane, y, z0 - 1), c = plane_quadrants(vol, x0, lane, y, z0);
-  const int z1 = min(z0 + ZC, vol.nz);
-  for (int z = z0; z < z1; ++z) {
-    const Quad n = plane_quadrants(vol, x0, lane, y, z + 1);
-    unsigned mask = 0xFFu;
-    // most cells are far from any surface: one test of the whole 3x3x3 neighbourhood settles all eight octants
-    int ulo = min(min(m.lo[0], m.lo[1]), min(m.lo[2], m.lo[3])), uhi = max(max(m.hi[0], m.hi[1]), max(m.hi[2], m.hi[3]));
-    ulo = min(ulo, min(min(c.lo[0], c.lo[1]), min(c.lo[2], c.lo[3]))); uhi = max(uhi, max(max(c.hi[0], c.hi[1]), max(c.hi[2], c.hi[3])));
-    ulo = min(ulo, min(min(n.lo[0], n.lo[1]), min(n.lo[2], n.lo[3]))); uhi = max(uhi, max(max(n.hi[0], n.hi[1]), max(n.hi[2], n.hi[3])));
-    if (!tf_interval_quiet(iv, tf.n, ulo, uhi)) {
-      mask = 0;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < items; it += nwarps) {
+    const unsigned xb = it % (unsigned)qw, t = it / (unsigned)qw;
+    const int cy = (int)(t % rows), zc = (int)(t / rows);
+    const int cx = (int)(xb * 32u + lane);
+    const int z0 = zc * QC_Z, z1 = min(z0 + QC_Z, vol.nz + 1);
+    // 2x2 min / max of texel plane z at this corner's (x, y): texels (cx-1, cx) x (cy-1, cy)
+    auto plane = [&](int z, int* mn, int* mx) {
+      const int a = vol.at(cx, cy - 1, z), b = vol.at(cx, cy, z);
+      int al = __shfl_up_sync(0xffffffffu, a, 1), bl = __shfl_up_sync(0xffffffffu, b, 1);
+      if (lane == 0) { al = vol.at(cx - 1, cy - 1, z); bl = vol.at(cx - 1, cy, z); }
+      *mn = min(min(a, b), min(al, bl));
+      *mx = max(max(a, b), max(al, bl));
+    };
+    int pmn, pmx;
+    plane(z0 - 1, &pmn, &pmx);
+    for (int cz = z0; cz < z1; ++cz) {
+      int mn, mx;
+      plane(cz, &mn, &mx);
+      const bool quiet = tf_interval_quiet(iv, tf.n, min(pmn, mn), max(pmx, mx));
+      const unsigned word = __ballot_sync(0xffffffffu, quiet && cx <= vol.nx);
+      if (lane == 0) Q[((size_t)cz * rows + (unsigned)cy) * (unsigned)qw + xb] = word;
+      pmn = mn; pmx = mx;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_lin_cells(SdfView sdf, const uint32_t* __restrict__ Q, int qw, unsigned rows, cudaSurfaceObject_t out,
+                                                   unsigned groups_x, size_t ngroups) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ngroups; i += (size_t)gridDim.x * blockDim.x) {
+    const int x0 = (int)(i % groups_x) * 4;
+    const size_t t = i / groups_x;
+    const int y = (int)(t % (unsigned)sdf.ny), z = (int)(t / (unsigned)sdf.ny);
+    const unsigned wi = (unsigned)x0 >> 5, sh = (unsigned)x0 & 31u;
+    uint32_t m = 0;  // byte i = the eight verdicts of cell x0 + i
 #pragma unroll
-      for (int oct = 0; oct < 8; ++oct) {
-        const int q = oct & 3;
-        const int mn = (oct & 4) ? min(c.lo[q], n.lo[q]) : min(m.lo[q], c.lo[q]);
-        const int mx = (oct & 4) ? max(c.hi[q], n.hi[q]) : max(m.hi[q], c.hi[q]);
-        if (tf_interval_quiet(iv, tf.n, mn, mx)) mask |= 1u << oct;
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t* row = Q + ((size_t)(z + (r >> 1)) * rows + (unsigned)(y + (r & 1))) * (unsigned)qw + wi;
+      const uint32_t w0 = __ldg(row), w1 = (sh == 28u && (int)wi + 1 < qw) ? __ldg(row + 1) : 0u;
+      const uint32_t b = __funnelshift_r(w0, w1, sh) & 0x1Fu;  // corners x0 .. x0 + 4 of this corner row
+      m |= bits4_to_bytes4(b) << (2 * (r & 1) + 4 * (r >> 1));           // ux = 0
+      m |= bits4_to_bytes4(b >> 1) << (1 + 2 * (r & 1) + 4 * (r >> 1));  // ux = 1
+    }
+    if (x0 + 4 <= sdf.nx) {
+      const uint32_t d = __ldg(reinterpret_cast<const uint32_t*>(sdf.f + sdf.addr(x0, y, z)));  // four bytes of one brick row
+      surf3Dwrite(make_uint2(__byte_perm(d, m, 0x5140), __byte_perm(d, m, 0x7362)), out, x0 * 2, y, z);
+    } else {
+      for (int k = 0; x0 + k < sdf.nx; ++k) {
+        const unsigned d = (unsigned)(unsigned char)__ldg(sdf.f + sdf.addr(x0 + k, y, z));
+        surf3Dwrite((unsigned short)((((m >> (8 * k)) & 0xFFu) << 8) | d), out, (x0 + k) * 2, y, z);
       }
     }
-    if (x < vol.nx) {
-      const unsigned d = (unsigned)(unsigned char)__ldg(sdf.f + sdf.addr(x, y, z));
-      surf3Dwrite((unsigned short)((mask << 8) | d), out, x * 2, y, z);
-    }
-    m = c;
-    c = n;
   }
 }
 
 int vrk_lin_field_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const int8_t* sdf_bricked, const TfTable& tf,
                         cudaSurfaceObject_t out) {
-  constexpr int ZC = 16;
   VolView v{vol, nx, ny, nz};
   SdfView s{sdf_bricked, nx, ny, nz, nx / 8 + 1, ny / 8 + 1};
-  dim3 grid(div_up(nx, 32), div_up(ny, 8), div_up(nz, ZC));
-  k_lin_field<ZC><<<grid, 256, 0, ctx->stream>>>(v, s, tf, out);
-  ctx->launches++;
+  const int qw = (nx + 1 + 31) / 32;
+  const unsigned rows = (unsigned)ny + 1u, zchunks = (unsigned)div_up(nz + 1, QC_Z);
+  uint32_t* Q = nullptr;
+  VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&Q), (size_t)qw * rows * ((size_t)nz + 1) * sizeof(uint32_t), ctx->stream));
+  const unsigned items = (unsigned)qw * rows * zchunks;
+  k_lin_corners<<<(unsigned)std::min<size_t>(div_up(items, 8), (size_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(v, tf, Q, qw, items, rows,
+                                                                                                                   zchunks);
+  const unsigned groups_x = (unsigned)div_up(nx, 4);
+  const size_t ngroups = (size_t)groups_x * ny * nz;
+  k_lin_cells<<<(unsigned)std::min<size_t>(div_up(ngroups, 256), (size_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(s, Q, qw, rows, out, groups_x,
+                                                                                                                     ngroups);
+  ctx->launches += 2;
   VR_CUDA(cudaGetLastError());
+  VR_CUDA(cudaFreeAsync(Q, ctx->stream));
   return VR_OK;
 }
 
