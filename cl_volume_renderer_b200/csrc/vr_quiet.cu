@@ -53,35 +53,67 @@ __device__ __forceinline__ bool tf_interval_quiet(const TfIntervals& s, int n, i
 // spread the low 4 bits of b to 4 bytes 0x00/0x01
 __device__ __forceinline__ uint32_t bits4_to_bytes4(uint32_t b) { return ((b & 0xFu) * 0x00204081u) & 0x01010101u; }
 #define QC_Z 32  // corner planes per warp item
+template <int NCL>  // clauses of the transfer function kept in registers (1 or 2: what the UI and the tests generate); 0 = any number
 __global__ void __launch_bounds__(256) k_lin_corners(VolView vol, TfTable tf, uint32_t* __restrict__ Q, int qw, unsigned items, unsigned rows,
                                                      unsigned zchunks) {
   __shared__ TfIntervals iv;
   tf_intervals_init(tf, &iv, (int)threadIdx.x);
   __syncthreads();
+  const int lo0 = iv.lo[0], hi0 = iv.hi[0], lo1 = NCL == 2 ? iv.lo[1] : 0, hi1 = NCL == 2 ? iv.hi[1] : 0;
   const unsigned lane = threadIdx.x & 31;
   const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  const size_t nxy = (size_t)vol.nx * vol.ny;
+  const size_t qplane = (size_t)rows * (unsigned)qw;
   for (unsigned it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < items; it += nwarps) {
     const unsigned xb = it % (unsigned)qw, t = it / (unsigned)qw;
     const int cy = (int)(t % rows), zc = (int)(t / rows);
     const int cx = (int)(xb * 32u + lane);
     const int z0 = zc * QC_Z, z1 = min(z0 + QC_Z, vol.nz + 1);
-    // 2x2 min / max of texel plane z at this corner's (x, y): texels (cx-1, cx) x (cy-1, cy)
-    auto plane = [&](int z, int* mn, int* mx) {
-      const int a = vol.at(cx, cy - 1, z), b = vol.at(cx, cy, z);
-      int al = __shfl_up_sync(0xffffffffu, a, 1), bl = __shfl_up_sync(0xffffffffu, b, 1);
-      if (lane == 0) { al = vol.at(cx - 1, cy - 1, z); bl = vol.at(cx - 1, cy, z); }
-      *mn = min(min(a, b), min(al, bl));
-      *mx = max(max(a, b), max(al, bl));
+    // 2x2 min / max of texel plane z at this corner's (x, y): texels (cx-1, cx) x (cy-1, cy); texels outside the volume are 0.
+    // Which of a lane's four loads exist is decided once per item (rows cy-1 / cy inside the volume, texel cx inside, lane 0 also
+    // loads the texel left of the warp's segment; the other lanes get theirs by shuffle); pointers advance by a plane per step.
+    const bool xin = cx < vol.nx, lin = lane == 0 && cx >= 1 && cx - 1 < vol.nx;
+    const bool pa = cy >= 1 && xin, pb = cy < vol.ny && xin, pa0 = cy >= 1 && lin, pb0 = cy < vol.ny && lin;
+    struct Tex4 { int a, b, a0, b0; };
+    // texel (cx, cy - 1, z); the pointer may lie outside the allocation while no predicate lets it be used
+    const int16_t* p = vol.v + ((ptrdiff_t)(z0 - 1) * (ptrdiff_t)nxy + (ptrdiff_t)(cy - 1) * vol.nx + cx);
+    int zt = z0 - 1;  // texel plane p points into
+    auto fetch = [&]() {
+      const bool zv = (unsigned)zt < (unsigned)vol.nz;
+      Tex4 q;
+      q.a = (zv && pa) ? (int)__ldg(p) : 0;
+      q.b = (zv && pb) ? (int)__ldg(p + vol.nx) : 0;
+      q.a0 = (zv && pa0) ? (int)__ldg(p - 1) : 0;
+      q.b0 = (zv && pb0) ? (int)__ldg(p + vol.nx - 1) : 0;
+      p += nxy; ++zt;
+      return q;
+    };
+    auto plane = [&](const Tex4& q, int* mn, int* mx) {
+      int al = __shfl_up_sync(0xffffffffu, q.a, 1), bl = __shfl_up_sync(0xffffffffu, q.b, 1);
+      if (lane == 0) { al = q.a0; bl = q.b0; }
+      *mn = min(min(q.a, q.b), min(al, bl));
+      *mx = max(max(q.a, q.b), max(al, bl));
     };
     int pmn, pmx;
-    plane(z0 - 1, &pmn, &pmx);
-    for (int cz = z0; cz < z1; ++cz) {
+    plane(fetch(), &pmn, &pmx);
+    Tex4 cur = fetch(), nxt = fetch();  // two planes in flight: an iteration is far shorter than a load
+    uint32_t* qout = Q + ((size_t)z0 * qplane + (size_t)cy * (unsigned)qw + xb);
+    for (int cz = z0; cz < z1; ++cz, qout += qplane) {
+      const Tex4 nn = fetch();
       int mn, mx;
-      plane(cz, &mn, &mx);
-      const bool quiet = tf_interval_quiet(iv, tf.n, min(pmn, mn), max(pmx, mx));
-      const unsigned word = __ballot_sync(0xffffffffu, quiet && cx <= vol.nx);
-      if (lane == 0) Q[((size_t)cz * rows + (unsigned)cy) * (unsigned)qw + xb] = word;
+      plane(cur, &mn, &mx);
+      const int bmn = min(pmn, mn), bmx = max(pmx, mx);
+      bool hit;  // the interval meets a clause
+      if (NCL == 1) hit = (bmx >= lo0) & (bmn <= hi0);
+      else if (NCL == 2) hit = ((bmx >= lo0) & (bmn <= hi0)) | ((bmx >= lo1) & (bmn <= hi1));
+      else {
+        hit = false;  // a uniform loop, no early exit: lanes do not diverge
+        for (int i = 0; i < tf.n; ++i) hit |= (bmx >= iv.lo[i]) & (bmn <= iv.hi[i]);
+      }
+      const unsigned word = __ballot_sync(0xffffffffu, !hit && cx <= vol.nx);
+      if (lane == 0) *qout = word;
       pmn = mn; pmx = mx;
+      cur = nxt; nxt = nn;
     }
   }
 }
@@ -123,8 +155,10 @@ int vrk_lin_field_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz,
   uint32_t* Q = nullptr;
   VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&Q), (size_t)qw * rows * ((size_t)nz + 1) * sizeof(uint32_t), ctx->stream));
   const unsigned items = (unsigned)qw * rows * zchunks;
-  k_lin_corners<<<(unsigned)std::min<size_t>(div_up(items, 8), (size_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(v, tf, Q, qw, items, rows,
-                                                                                                                   zchunks);
+  const unsigned cgrid = (unsigned)std::min<size_t>(div_up(items, 8), (size_t)ctx->sm_count * 32);
+  if (tf.n == 1) k_lin_corners<1><<<cgrid, 256, 0, ctx->stream>>>(v, tf, Q, qw, items, rows, zchunks);
+  else if (tf.n == 2) k_lin_corners<2><<<cgrid, 256, 0, ctx->stream>>>(v, tf, Q, qw, items, rows, zchunks);
+  else k_lin_corners<0><<<cgrid, 256, 0, ctx->stream>>>(v, tf, Q, qw, items, rows, zchunks);
   const unsigned groups_x = (unsigned)div_up(nx, 4);
   const size_t ngroups = (size_t)groups_x * ny * nz;
   k_lin_cells<<<(unsigned)std::min<size_t>(div_up(ngroups, 256), (size_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(s, Q, qw, rows, out, groups_x,
