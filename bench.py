@@ -70,89 +70,123 @@ def peaks():
 
 class ClockSampler:
     """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region of the default run is
-    ~15 ms, shorter than one `nvidia-smi -lms` period, so the clocks are polled through NVML in a thread (every ~1 ms);
-    `nvidia-smi --query-gpu` is the fallback when pynvml is missing."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    ~10 ms, shorter than one `nvidia-smi -lms` period, so the clocks are polled through NVML every ~1 ms — in a separate PROCESS,
+    started before the warm-up: a polling thread inside the bench process competes with the launching thread for the interpreter
+    lock and the driver, which a single-GPU step hides behind its queue but which cost a multi-GPU step 25 % (every rank waits
+    for rank 0 in the exchange: 2.51 ms per step at 8 GPUs with the thread, 2.01 without).  `begin()` / `end()` bracket the timed
+    region; only samples taken inside it are reported.  `nvidia-smi --query-gpu` is the fallback when pynvml is missing."""
+    POLLER = r"""
+import sys, time
+import pynvml as n
+n.nvmlInit()
+bus = sys.argv[1]
+h = None
+for i in range(n.nvmlDeviceGetCount()):
+    hh = n.nvmlDeviceGetHandleByIndex(i)
+    b = n.nvmlDeviceGetPciInfo(hh).busId
+    b = b.decode() if isinstance(b, bytes) else b
+    if bus and bus.lower() in b.lower():
+        h = hh
+        break
+if h is None:
+    h = n.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))
+try:
+    mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+except Exception:
+    mx = -1
+print("ready", mx, flush=True)
+while True:
+    try:
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        print(repr(time.time()), sm, int(r), flush=True)
+    except Exception:
+        pass
+    time.sleep(0.001)
+"""
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
         self.proc = None
-        self.nvml = None
-        self.sm, self.reason_bits, self.stop_flag = [], 0, False
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            # CUDA_VISIBLE_DEVICES may renumber devices: resolve by the CUDA device's PCI bus id
-            import torch
-            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
-            self.h = None
-            if bus is not None:
-                for i in range(pynvml.nvmlDeviceGetCount()):
-                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
-                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
-                        self.h = h
-                        break
-            if self.h is None:
-                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.nvml = pynvml
-        except Exception as e:
-            log("NVML unavailable, falling back to nvidia-smi:", e)
-
-    def _poll(self):
-        n = self.nvml
-        while not self.stop_flag:
-            try:
-                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
-                self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-            except Exception:
-                try:
-                    self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                except Exception:
-                    pass
-            time.sleep(0.001)
+        self.lines = []
+        self.mx = None
+        self.t0 = self.t1 = None
+        self.mode = None
 
     def start(self):
-        if self.nvml:
-            self.stop_flag = False
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
-            return
+        """launch the poller and wait until it samples (call before the warm-up)"""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception as e:  # nvidia-smi missing: report it, do not fail the bench
-            log("clock sampler unavailable:", e)
+            import pynvml  # noqa: F401  (only to know the subprocess can import it)
+            import torch
+            bus = ""
+            try:
+                pr = torch.cuda.get_device_properties(self.index)
+                bus = ":%02x:%02x." % (pr.pci_bus_id, pr.pci_device_id) if hasattr(pr, "pci_bus_id") else ""
+            except Exception:
+                pass
+            self.proc = subprocess.Popen([sys.executable, "-c", self.POLLER, bus, str(self.index)], stdout=subprocess.PIPE, text=True)
+            first = self.proc.stdout.readline().split()
+            if not first or first[0] != "ready":
+                raise RuntimeError("poller did not start")
+            self.mx = float(first[1]) if float(first[1]) > 0 else None
+            self.mode = "nvml"
+        except Exception as e:
+            log("NVML poller unavailable, falling back to nvidia-smi:", e)
+            try:
+                Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                     "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                              "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                self.mode = "smi"
+            except Exception as e2:  # nvidia-smi missing: report it, do not fail the bench
+                log("clock sampler unavailable:", e2)
+                self.proc = None
+                return
+        self.t = threading.Thread(target=self._read, daemon=True)  # drains the pipe; idle while nothing arrives
+        self.t.start()
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.lines.append(line)
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        if self.nvml:
-            n = self.nvml
-            self.stop_flag = True
-            self.t.join(timeout=1.0)
-            try:
-                mx = float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM))
-            except Exception:
-                mx = None
-            names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-            reasons = sorted(k for k, bit in names.items() if self.reason_bits & bit)
-            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": mx, "reasons": reasons,
-                    "samples": len(self.sm), "source": "NVML polled every 1 ms during the timed region"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable"]}
+        time.sleep(0.15 if self.mode == "smi" else 0.01)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        if self.mode == "nvml":
+            sm, bits, n_in = [], 0, 0
+            every = []
+            for ln in list(self.lines):
+                f = ln.split()
+                if len(f) != 3:
+                    continue
+                try:
+                    t, c, r = float(f[0]), float(f[1]), int(f[2])
+                except ValueError:
+                    continue
+                every.append(c)
+                if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1:
+                    sm.append(c); bits |= r; n_in += 1
+            if not sm and every:  # a region shorter than one poll: the samples next to it
+                sm = every[-3:]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(k for k, b in names.items() if bits & b),
+                    "samples": n_in, "source": "NVML polled every ~1 ms by a separate process; samples inside the timed region"}
+        rows = [[c.strip() for c in ln.split(",")] for ln in self.lines]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) < 9:
                 continue
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
@@ -313,21 +347,23 @@ def run_ours(args, rank, world, local_rank):
         r.render_frames(pos, d, seeds, readback=False)
         counters = r.counters(reset=True)
         r.enable_counters(False)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()          # its own process, running before the warm-up
         for _ in range(warmup):
             step()
         barrier()
         launches0 = ctx.launches
         r.enable_timing(True)
         r.kernel_times(reset=True)
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.begin()
         e0.record(ext)
         for _ in range(steps):
             step()
         e1.record(ext)
         e1.synchronize()
+        sampler.end()
         barrier()
         clocks = sampler.stop() if rank == 0 else None
         ms_local = e0.elapsed_time(e1)

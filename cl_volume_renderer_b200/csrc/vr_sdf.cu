@@ -885,21 +885,30 @@ int vrk_sdf_slab_advance(vr_sdf_slab* s, int nlevels, int* done) {
         default: VR_FLOW(2, 8); break;  // variant 0
       }
 #undef VR_FLOW
-      if (st != VR_OK) return st;
-      s->level += n;
-      s->all_active = false;
-      ctx->launches++;
+      if (st == VR_OK) {
+        s->level += n;
+        s->all_active = false;
+        ctx->launches++;
+        if (done) *done = n;
+        return VR_OK;
+      }
+      // the cooperative launch was refused (no co-residency on this device / under this sharing mode): a launch per level with
+      // the same tiles from here on
+      cudaGetLastError();
+      s->flow = false;
+      n = 0;
+    } else {
+      if (done) *done = 0;
+      return VR_OK;
     }
-    if (done) *done = n;
-    return VR_OK;
   }
   for (; n < nlevels && s->level + 1 < s->max_it; ++n, ++s->level) {
     const int it = s->level;
     if (s->wave == 9) {
 #define VR_W9(YR, TZ, MINB) do { if (s->xl == 8) launch_wave9<8, YR, TZ, MINB>(s, it, grid); else launch_wave9<4, YR, TZ, MINB>(s, it, grid); } while (0)
       switch (s->variant) {
+        case 0: VR_W9(2, 8, 4); break;  // k_sdf_flow's tile shape: the fallback when a cooperative launch is refused
 #ifdef VR_AB
-        case 0: VR_W9(2, 8, 4); break;
         case 1: VR_W9(2, 4, 4); break;
         case 2: VR_W9(4, 4, 2); break;
         case 4: VR_W9(1, 8, 6); break;
