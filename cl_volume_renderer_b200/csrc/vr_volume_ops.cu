@@ -118,18 +118,49 @@ __device__ __forceinline__ int box_edge(const VolView& v, int x, int y, int z) {
     s += v.at(min(max(x - 1 + (c & 1), 0), v.nx - 1), min(max(y - 1 + ((c >> 1) & 1), 0), v.ny - 1), min(max(z - 1 + (c >> 2), 0), v.nz - 1));
   return (s + 4) >> 3;
 }
+// A thread writes 8 consecutive x of one (y, z): the four contributing rows come as 16-byte loads (plus the voxel left of the group),
+// summed per column first, then neighbouring columns — 4 vector loads and ~100 instructions per 8 outputs (first version: 8 scalar
+// loads per output, 0.69 ms at 512^3).
 __global__ void __launch_bounds__(256) k_boxavg(VolView v, int16_t* __restrict__ out, int px) {
-  const size_t n = (size_t)px * (v.ny + 1) * (v.nz + 1);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % px);
-    const size_t t = i / px;
+  const unsigned gx = (unsigned)px >> 3;  // px is a multiple of 8
+  const size_t ngroups = (size_t)gx * (v.ny + 1) * (v.nz + 1);
+  const bool vec = (v.nx & 7) == 0;  // rows of the volume 16-byte aligned
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ngroups; i += (size_t)gridDim.x * blockDim.x) {
+    const int x0 = (int)(i % gx) * 8;
+    const size_t t = i / gx;
     const int y = (int)(t % (v.ny + 1)), z = (int)(t / (v.ny + 1));
-    out[i] = x <= v.nx ? (int16_t)box_border(v, x, y, z) : (int16_t)0;
+    int col[9];  // sums over the 2 x 2 rows (y-1..y, z-1..z) of the voxels x0-1 .. x0+7; voxels outside the volume are 0
+#pragma unroll
+    for (int k = 0; k < 9; ++k) col[k] = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int yy = y - 1 + (c & 1), zz = z - 1 + (c >> 1);
+      if ((unsigned)yy >= (unsigned)v.ny || (unsigned)zz >= (unsigned)v.nz) continue;
+      const int16_t* row = v.v + ((size_t)zz * v.ny + yy) * v.nx;
+      if (x0 > 0 && x0 - 1 < v.nx) col[0] += (int)__ldg(row + x0 - 1);
+      if (vec && x0 + 8 <= v.nx) {
+        int w[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(row + x0)), w);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) col[1 + k] += w[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (x0 + k < v.nx) col[1 + k] += (int)__ldg(row + x0 + k);
+      }
+    }
+    unsigned o[4];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      const int a = x0 + k <= v.nx ? (col[k] + col[k + 1] + 4) >> 3 : 0, b = x0 + k + 1 <= v.nx ? (col[k + 1] + col[k + 2] + 4) >> 3 : 0;
+      o[k >> 1] = ((unsigned)a & 0xFFFFu) | ((unsigned)b << 16);
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 int vrk_boxavg(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int16_t* out, int px) {
   VolView v{vol, nx, ny, nz};
-  const size_t n = (size_t)px * (ny + 1) * (nz + 1);
+  const size_t n = (size_t)(px / 8) * (ny + 1) * (nz + 1);
   k_boxavg<<<(unsigned)std::min<size_t>(div_up(n, 256), (size_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(v, out, px);
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
