@@ -396,6 +396,40 @@ def test_sdf_alternative_builds_bit_exact(mode):
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 
 
+@pytest.mark.parametrize("knobs", [{"VR_SDF_FLOW": "1"}, {"VR_SDF_FLOW": "0"}, {"VR_SDF_FLOW": "0", "VR_SDF_PDL": "0", "VR_SDF_VARIANT": "0"},
+                                   {"VR_SDF_FLOW": "1", "VR_SDF_VARIANT": "4"}, {"VR_SDF_WAVE": "6"}, {"VR_SDF_WAVE": "5"}],
+                         ids=["flow", "per_level", "per_level_2x8_no_pdl", "flow_1x8", "wave6", "wave5"])
+def test_sdf_level_kernels_bit_exact(knobs):
+    """Every way the product can run the level wave — tiles synchronised point to point in one cooperative launch (k_sdf_flow, what
+    volumes above 512^3 take), a launch per level (k_sdf_wave9), the two-volume kernel for odd row widths (k_sdf_wave6) — and round 1's
+    k_sdf_wave5, forced through the A/B build's knobs at sizes the oracle finishes in seconds: rows of 1, 2, 5 and 9 quads (lanes beyond
+    the row, 8 lanes along x, edge loads), several tiles per axis, ragged y / z.  Own process: the knobs are read once per process."""
+    import subprocess, sys, os
+    env = dict(os.environ)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env["VR_LIB"] = os.path.join(root, "tools", "ab", "libvr_ab.so")
+    assert os.path.exists(env["VR_LIB"]), "build the A/B library: make ab"
+    env.update(knobs)
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, 'tests')\n"
+        "import oracle_lib as o\n"
+        "from cl_volume_renderer_b200 import api, synth\n"
+        "ctx = api.Context(0)\n"
+        "G = np.load('tests/golden/sdf_ref.npz')\n"
+        "vol = api.Volume(ctx, G['volume']); s = api.Sdf(ctx, vol, synth.threshold_tf(int(G['threshold'])))\n"
+        "assert np.array_equal(s.download(), G['sdf'])\n"
+        "for dims, tf in (((128, 70, 45), synth.default_tf()), ((256, 23, 21), synth.threshold_tf(300)), ((640, 19, 37), synth.default_tf()),\n"
+        "                 ((1152, 13, 11), synth.threshold_tf(700))):\n"
+        "    v = synth.synth_ct(0, dims=dims); vol2 = api.Volume(ctx, v)\n"
+        "    s2 = api.Sdf(ctx, vol2, tf)\n"
+        "    assert np.array_equal(s2.download(), o.sdf_build(v, tf)[0]), dims\n"
+        "    s2.close(); vol2.close()\n"
+        "print('OK')\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_ab_build_trace_sm_equals_default_schedule():
     """The A/B build's trace mode 3 (k_trace_sm: sample slots in shared memory, packed batches — measured and not adopted, see
     vr_render.cu) computes the same samples: voxel cache and counters identical to the default schedule, under both samplings."""
