@@ -696,22 +696,19 @@ __global__ void __launch_bounds__(SX* HBY, 1) k_histogram_lut(VolView vol, uint3
           py = (S >> 7) < HP2 ? (int)pyl2[S >> 7] : HNONUNI;
           if (py == HNONUNI) py = hist_py(a, S);
         }
-        long long flat = -1;
-        int w = -1;
-        if (in && px != HSKIP && py != HSKIP) {
-          flat = (long long)px * a.height + py;
-          if (flat < 0 || flat >= nbins) flat = -1;
-          const unsigned wx = (unsigned)(px - wx0), wy = (unsigned)(py - wy0);
-          if (flat >= 0 && wx < (unsigned)wc && wy < (unsigned)wr && py < a.height) w = (int)(wx * (unsigned)wr + wy);
-        }
+        // inside the window (columns wx0 .. wx0 + wc - 1 lie inside the grid, so with py < height the bin does too; the markers
+        // are large negative numbers and fail the unsigned tests): no 64-bit bin number needed
+        const unsigned wx = (unsigned)(px - wx0), wy = (unsigned)(py - wy0);
+        const int w = (in && wx < (unsigned)wc && wy < (unsigned)wr && py < a.height) ? (int)(wx * (unsigned)wr + wy) : -1;
         int same;
         __match_all_sync(0xffffffffu, w, &same);
         if (same && w >= 0) {
           if (lane == 0) atomicAdd(&win[w], 32u);
         } else if (w >= 0) {
           atomicAdd(&win[w], 1u);
-        } else if (flat >= 0) {
-          atomicAdd(bins + flat, 1u);
+        } else if (in && px != HSKIP && py != HSKIP) {
+          const long long flat = (long long)px * a.height + py;
+          if (flat >= 0 && flat < nbins) atomicAdd(bins + flat, 1u);
         }
       }
 #pragma unroll
