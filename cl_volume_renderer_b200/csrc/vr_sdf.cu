@@ -632,6 +632,69 @@ static __global__ void __launch_bounds__(256) k_sdf_assemble8(WaveDims g, int ma
   }
 }
 
+// k_sdf_count's counters -> the bricked field, a WORD per lane: a warp item is 4 words x 8 rows of one plane, lane = word * 8 + row,
+// so a lane reads its word's eight plane entries once (k_sdf_assemble8 reads them in each of the four lanes that share a word:
+// 28 instructions per voxel, issue-bound at 0.17 ms) and loops over the word's four 8-voxel pieces; the eight rows of a word
+// still write 64 contiguous bytes of a brick slice per piece.
+static __global__ void __launch_bounds__(256) k_sdf_assemble9(WaveDims g, int max_it, const uint32_t* __restrict__ E,
+                                                             const uint32_t* __restrict__ planes8, int8_t* __restrict__ field,
+                                                             unsigned nxg, unsigned items, cudaSurfaceObject_t surf) {
+  const unsigned lane = threadIdx.x & 31;
+  const int yr = lane & 7, wl = lane >> 3;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned it = warp; it < items; it += nwarps) {
+    const unsigned t = it / nxg;
+    const int xw = (int)(it - t * nxg) * 4 + wl;
+    const int z = (int)(t / (unsigned)g.by), yg = (int)(t - (unsigned)z * (unsigned)g.by);
+    const int y = yg * 8 + yr;
+    if (xw * 4 >= g.bx) continue;
+    const bool in = xw < g.nxw && y < g.ny && z < g.nz;
+    uint32_t pl[7], ev = 0u, vm = 0u, reached = 0u;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) pl[j] = 0u;
+    if (in) {
+      const unsigned w = ((unsigned)z * (unsigned)g.ny + (unsigned)y) * (unsigned)g.nxw + (unsigned)xw;
+      ev = __ldg(E + w); vm = valid_mask(g, xw);
+      const uint32_t* pp = planes8 + plane_word(w);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) pl[j] = __ldg(pp + 2 * j);
+      reached = __ldg(pp + 14);
+    }
+    const size_t slice = (((size_t)(z >> 3) * g.by + yg) * g.bx) * BRV + ((z & 7) << 6) + (yr << 3);
+#pragma unroll
+    for (int piece = 0; piece < 4; ++piece) {
+      const int brick_x = xw * 4 + piece;
+      if (brick_x >= g.bx) break;
+      const int sh = 8 * piece;
+      const uint32_t e8 = (ev >> sh) & 0xFFu, v8 = (vm >> sh) & 0xFFu, r8 = (reached >> sh) & 0xFFu;
+      uint32_t m0 = 0, m1 = 0;  // per byte: the 7-bit count of bit volumes in which the voxel is clear
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const uint32_t p8 = (pl[j] >> sh) & 0xFFu;
+        m0 |= bits4_to_bytes(p8) << j;
+        m1 |= bits4_to_bytes(p8 >> 4) << j;
+      }
+      uint32_t out[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        // level = count + 1 where the voxel was reached (count <= 125: no carry between the bytes), max_it elsewhere; sign by event
+        const uint32_t rb = bits4_to_bytes(r8 >> (4 * h)) * 0xFFu;
+        const uint32_t mag = (((h ? m1 : m0) + 0x01010101u) & rb) | (((uint32_t)max_it * 0x01010101u) & ~rb);
+        const uint32_t evb = bits4_to_bytes(e8 >> (4 * h)), vd = bits4_to_bytes(v8 >> (4 * h));
+        out[h] = ((mag ^ (evb * 0xFFu)) + evb) & (vd * 0xFFu);
+      }
+      *reinterpret_cast<uint2*>(field + slice + (size_t)brick_x * BRV) = make_uint2(out[0], out[1]);
+      if (surf && in) {  // the same 8 voxels into the 3-D array the marcher gathers from (no apron there)
+        const int x0 = brick_x * 8;
+        if (x0 + 8 <= g.nx) surf3Dwrite(make_uint2(out[0], out[1]), surf, x0, y, z);
+        else
+          for (int k = 0; x0 + k < g.nx; ++k) surf3Dwrite((signed char)((out[k >> 2] >> (8 * (k & 3))) & 0xFFu), surf, x0 + k, y, z);
+      }
+    }
+  }
+}
+
 // band bits only, into the first kept bit volume (k_sdf_wave9's scheme has no level planes to initialise)
 static __global__ void __launch_bounds__(256) k_sdf_band_bits9(WaveDims g, const uint32_t* __restrict__ E, uint32_t* __restrict__ R0,
                                                               unsigned nwords) {
@@ -972,7 +1035,9 @@ int vrk_sdf_slab_assemble(vr_sdf_slab* s, int8_t* field, cudaSurfaceObject_t sur
     const unsigned cg = (unsigned)std::min<size_t>(div_up(s->nwords / 4, 256), (size_t)s->ctx->sm_count * 16);
     k_sdf_count<<<cg, 256, 0, s->ctx->stream>>>(w, s->R(0), (unsigned)s->nwords, std::min(s->level, s->nsnaps), s->changed(), s->planes);
     s->ctx->launches++;
-    k_sdf_assemble8<true><<<bg, 256, 0, s->ctx->stream>>>(w, s->max_it, s->E(), s->planes, field, nxwf, items, surf);
+    const unsigned nxg = (nxwf + 3) / 4, items9 = nxg * (unsigned)w.by * (8u * (unsigned)w.bz);
+    k_sdf_assemble9<<<(unsigned)std::min<size_t>(div_up(items9, 8), (size_t)s->ctx->sm_count * 16), 256, 0, s->ctx->stream>>>(
+        w, s->max_it, s->E(), s->planes, field, nxg, items9, surf);
   } else if (s->wave == 6) {
     k_sdf_assemble8<false><<<bg, 256, 0, s->ctx->stream>>>(w, s->max_it, s->E(), s->planes, field, nxwf, items, surf);
   } else {
