@@ -427,11 +427,15 @@ int vrk_clip(vr_ctx* ctx, const int16_t* src, int snx, int sny, int snz, const u
 __device__ __forceinline__ int bil_class(int d2) {  // 0,1,2,3,4,5,6,8,9,12 -> 0..9
   return d2 <= 6 ? d2 : (d2 == 8 ? 7 : (d2 == 9 ? 8 : 9));
 }
+// A thread computes TWO outputs, z and z + 1: the tile value of a tap is loaded once for both (6 planes instead of 2 x 5), and
+// the index of the weight comes without a float -> int conversion (ncu on the first version: XU pipe 63 % busy with 125 F2I per
+// voxel, issue active 82 %): |mid - local| is an integer-valued float, fma(min(|d|, 16), 4, 1.5 * 2^23) has the byte offset 4 a in
+// its low mantissa bits.  Each output still accumulates its 125 taps in the reference's order (dz, dy, dx ascending).
 // dnx/dny/dnz: dims of the output (== the volume's; under VR_SAMPLING_HW_LINEAR `vol` is the box-averaged volume, one larger)
 __global__ void __launch_bounds__(TX* TY* TZ) k_bilateral(VolView vol, int16_t* __restrict__ dst, int dnx, int dny, int dnz) {
-  __shared__ float tile[TZ + 4][TY + 4][TX + 4];
+  __shared__ float tile[2 * TZ + 4][TY + 4][TX + 4];
   __shared__ float wtab[10 * BIL_A];
-  const int bx = blockIdx.x * TX, by = blockIdx.y * TY, bz = blockIdx.z * TZ;
+  const int bx = blockIdx.x * TX, by = blockIdx.y * TY, bz = blockIdx.z * (2 * TZ);
   const int tid = threadIdx.x + TX * (threadIdx.y + TY * threadIdx.z);
   const float sigmas = 0.6f, sigmar = 1.0f;
   if (tid < 10 * BIL_A) {
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_bilateral(VolView vol, int16_t* 
     const float cold = (diff * diff) / (2 * sigmar * sigmar);
     wtab[tid] = a == BIL_A - 1 ? 0.0f : expf(-posd - cold);  // a >= 16: expf(<= -128) == 0
   }
-  for (int i = tid; i < (TZ + 4) * (TY + 4) * (TX + 4); i += TX * TY * TZ) {
+  for (int i = tid; i < (2 * TZ + 4) * (TY + 4) * (TX + 4); i += TX * TY * TZ) {
     int lx = i % (TX + 4);
     int t = i / (TX + 4);
     int ly = t % (TY + 4);
@@ -450,28 +454,42 @@ __global__ void __launch_bounds__(TX* TY* TZ) k_bilateral(VolView vol, int16_t* 
     tile[lz][ly][lx] = (float)vol.at(bx + lx - 2, by + ly - 2, bz + lz - 2);
   }
   __syncthreads();
-  const int x = bx + threadIdx.x, y = by + threadIdx.y, z = bz + threadIdx.z;
+  const int x = bx + threadIdx.x, y = by + threadIdx.y, z = bz + 2 * threadIdx.z;
   if (x >= dnx || y >= dny || z >= dnz) return;
-  const float mid = tile[threadIdx.z + 2][threadIdx.y + 2][threadIdx.x + 2];
-  float out_colour = 0.0f, wp = 0.0f;
+  const int lz0 = 2 * threadIdx.z + 2;  // tile plane of output z
+  const float mid0 = tile[lz0][threadIdx.y + 2][threadIdx.x + 2], mid1 = tile[lz0 + 1][threadIdx.y + 2][threadIdx.x + 2];
+  float out0 = 0.0f, wp0 = 0.0f, out1 = 0.0f, wp1 = 0.0f;
+  const char* wbytes = reinterpret_cast<const char*>(wtab);
+  auto weight = [&](float mid, float local, int cls) {
+    const float t = __fmaf_rn(fminf(fabsf(mid - local), (float)(BIL_A - 1)), 4.0f, 12582912.0f);  // exact: both are integers of |value| < 2^15
+    return *reinterpret_cast<const float*>(wbytes + cls * (BIL_A * 4) + (__float_as_int(t) - 0x4B400000));
+  };
 #pragma unroll
-  for (int dz = -2; dz <= 2; ++dz)
+  for (int pz = -2; pz <= 3; ++pz)  // tile plane lz0 + pz: tap dz = pz of output z, tap dz = pz - 1 of output z + 1
 #pragma unroll
     for (int dy = -2; dy <= 2; ++dy)
 #pragma unroll
       for (int dx = -2; dx <= 2; ++dx) {
-        const float local = tile[threadIdx.z + 2 + dz][threadIdx.y + 2 + dy][threadIdx.x + 2 + dx];
-        const int a = min(__float2int_rn(fabsf(mid - local)), BIL_A - 1);  // exact: both are integers of |value| < 2^15
-        const float w = wtab[bil_class(dx * dx + dy * dy + dz * dz) * BIL_A + a];
-        wp += w;
-        out_colour += local * w;
+        const float local = tile[lz0 + pz][threadIdx.y + 2 + dy][threadIdx.x + 2 + dx];
+        if (pz <= 2) {
+          const float w = weight(mid0, local, bil_class(dx * dx + dy * dy + pz * pz));
+          wp0 += w;
+          out0 += local * w;
+        }
+        if (pz >= -1) {
+          const float w = weight(mid1, local, bil_class(dx * dx + dy * dy + (pz - 1) * (pz - 1)));
+          wp1 += w;
+          out1 += local * w;
+        }
       }
-  dst[(size_t)x + (size_t)dnx * ((size_t)y + (size_t)dny * (size_t)z)] = (int16_t)f2s(out_colour / wp);
+  const size_t o = (size_t)x + (size_t)dnx * ((size_t)y + (size_t)dny * (size_t)z);
+  dst[o] = (int16_t)f2s(out0 / wp0);
+  if (z + 1 < dnz) dst[o + (size_t)dnx * dny] = (int16_t)f2s(out1 / wp1);
 }
 
 int vrk_bilateral(vr_ctx* ctx, const int16_t* src, int16_t* dst, int nx, int ny, int nz) {
   VolView v{src, nx, ny, nz};
-  dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
+  dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, 2 * TZ)), block(TX, TY, TZ);
   k_bilateral<<<grid, block, 0, ctx->stream>>>(v, dst, nx, ny, nz);
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
@@ -480,7 +498,7 @@ int vrk_bilateral(vr_ctx* ctx, const int16_t* src, int16_t* dst, int nx, int ny,
 // centre and taps from the box-averaged volume (border addressing: utility_filter.cl:40), output for the volume's own voxels
 int vrk_bilateral_linear(vr_ctx* ctx, const int16_t* box, int px, int nx, int ny, int nz, int16_t* dst) {
   VolView b{box, px, ny + 1, nz + 1};
-  dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, TZ)), block(TX, TY, TZ);
+  dim3 grid(div_up(nx, TX), div_up(ny, TY), div_up(nz, 2 * TZ)), block(TX, TY, TZ);
   k_bilateral<<<grid, block, 0, ctx->stream>>>(b, dst, nx, ny, nz);
   ctx->launches++;
   VR_CUDA(cudaGetLastError());
