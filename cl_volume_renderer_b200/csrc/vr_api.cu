@@ -1176,11 +1176,13 @@ extern "C" int vr_renderer_set_tuning(vr_renderer* r, const char* key, int value
   else if (!strcmp(key, "lin_w_slow")) { VR_REQUIRE(value >= 1 && value <= 1024, "lin_w_slow out of range"); t.lin_w[1] = value; }
   else if (!strcmp(key, "lin_w_event")) { VR_REQUIRE(value >= 1 && value <= 1024, "lin_w_event out of range"); t.lin_w[2] = value; }
   else if (!strcmp(key, "steps_per_check")) { VR_REQUIRE(value >= 1 && value <= 16, "steps_per_check out of range"); t.spc = value; }
-  else if (!strcmp(key, "pt_ctas")) {
+  else if (!strcmp(key, "pt_ctas") || !strcmp(key, "pt_slots") || !strcmp(key, "pt2_ctas")) {
 #ifdef VR_AB
-    t.pt_ctas = value;
+    if (!strcmp(key, "pt_slots")) { VR_REQUIRE(value == 1 || value == 2, "pt_slots must be 1 or 2"); t.pt_slots = value; }
+    else if (!strcmp(key, "pt2_ctas")) { VR_REQUIRE(value == 6 || value == 7 || value == 8 || value == 10, "pt2_ctas must be 6, 7, 8 or 10"); t.pt2_ctas = value; }
+    else t.pt_ctas = value;
 #else
-    vr_set_error("vr_renderer_set_tuning: pt_ctas needs the A/B build of the library (make ab)");
+    vr_set_error("vr_renderer_set_tuning: %s needs the A/B build of the library (make ab)", key);
     return VR_ERR_INVALID;
 #endif
   } else { vr_set_error("vr_renderer_set_tuning: unknown key '%s'", key); return VR_ERR_INVALID; }

@@ -153,6 +153,8 @@ struct vr_renderer {
     int sm_k = 16, sm_leave = 16;      // k_trace_sm (trace mode 3): steps per visit of a marching batch, early-stop threshold
     int surf = 1;                      // NEAREST k_trace_pt gathers the SDF through the surface object (0: bricked field, __ldg)
     int pt_ctas = 0;                   // -DVR_AB builds only: register budget variant of k_trace_pt
+    int pt_slots = 1;                  // sample slots per lane of the NEAREST production trace: 1 = k_trace_pt, 2 = k_trace_pt2
+    int pt2_ctas = 8;                  // CTAs per SM (register budget) of k_trace_pt2: 6, 7, 8, 10
   } tune;
   // Which cache entries can be non-zero: 0 none (just reset), 1 only cache[hit[pix]] of the current `hit` buffer (every trace
   // since the last reset used the camera / rows in dirty_pos.. below), 2 unknown (full reset needed).  A frame reset then

@@ -899,6 +899,219 @@ __global__ void __launch_bounds__(128, CTAS) k_trace_pt(const RenderParams p, un
 }
 
 #ifdef VR_AB
+// ---- k_trace_pt2: two sample slots per lane (A/B build; measured and NOT adopted) ------------------------------------------------------
+// ncu on k_trace_pt (profiles/r2f_nearest_trace_phase_64frames_ncu_full_summary.txt): 69 % of the stall samples are the long
+// scoreboard — a step is ~25 instructions followed by a dependent gather of ~500 cycles, each lane has ONE gather in flight, and
+// with 12 warps per scheduler that is 12 x 25 instructions per 500 cycles = the 0.59 issue rate measured.  Registers, not warp
+// slots, cap the warps (40 registers at 48 warps per SM; 32 spill).  Here a lane carries TWO samples: every phase of the slot
+// machine runs over both (statically unrolled, the state stays in registers), and the step loop issues both slots' gathers back to
+// back — two independent chains per lane.  Same samples, same arithmetic; the production schedule only (batched primary reuse,
+// NEAREST, surface gather).
+// MEASURED (tools/slots_probe.py, bench scene, ms per 64-frame step, default / close-up view): k_trace_pt 1.93 / 5.58; two slots at
+// 10 / 8 / 7 / 6 CTAs per SM (48 / 64 / 72 / 79 registers) 2.34 / 2.41 / 2.50 / 2.79 and 6.57 / 6.83 / 7.10 / 7.89 — slower, and the
+// more warps the better even with spills: what hides the latency is warps in EVERY phase (event processing, refills, bounces run
+// per slot, one after the other, with the divergence they have), not gathers in flight in the step loop alone.
+template <int CTAS>
+__global__ void __launch_bounds__(128, CTAS) k_trace_pt2(const RenderParams p, unsigned* __restrict__ work_counter) {
+  constexpr int NS = 2;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned records = min(__ldcv(p.qcount), p.qcap);
+  const unsigned total = (p.pixel_major ? (records + p.pixel_major - 1) / p.pixel_major * p.pixel_major : records) * (unsigned)p.nframes;
+
+  int mode[NS], ev[NS], seed[NS], d[NS], steps_left[NS], clause_col[NS], po[NS], pi[NS];
+  bool marching[NS], unclassified[NS];
+  unsigned xyp[NS], rec[NS], bvp[NS];
+  f3 o[NS], dv[NS];
+  float atten[NS], er[NS], eg[NS], eb[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    mode[s] = M_IDLE; ev[s] = EVP_NONE; seed[s] = 0; d[s] = 0; steps_left[s] = 0; clause_col[s] = 0; po[s] = 0; pi[s] = 0;
+    marching[s] = false; unclassified[s] = false; xyp[s] = 0; rec[s] = 0; bvp[s] = 0;
+    o[s] = {0, 0, 0}; dv[s] = {0, 0, 0}; atten[s] = 0; er[s] = 0; eg[s] = 0; eb[s] = 0;
+  }
+  bool exhausted = false;
+
+  for (;;) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      bool need_bounce = false, reset_atten = false, need_start = false;
+      f3 bn = {0, 0, 0};
+      int bseed = 0;
+      auto energy = [&](int k) -> float { return clause_col[s] ? p.tf.e[clause_col[s] - 1][k] : 0.0f; };
+
+      // ---- events of the slots whose segment ended (k_trace_pt has the commentary) -----------------------------------------
+      if (mode[s] != M_IDLE && !marching[s]) {
+        f3 grad = {0.0f, 0.0f, 0.0f};
+        if (ev[s] == EVP_SDF_NEG || ev[s] == EVP_FARFACE) {
+          const int vx = ifloor(o[s].x), vy = ifloor(o[s].y), vz = ifloor(o[s].z);
+          grad = gradient_voxel(p.vol, vx, vy, vz);
+          const int value = ev[s] == EVP_SDF_NEG ? p.vol.at(vx, vy, vz) : 0;
+          const int clause = tf_match(p.tf, value, f2s(length3(grad)));
+          if (ev[s] == EVP_FARFACE && clause == 0) {
+            ev[s] = EVP_NONE;
+            if (steps_left[s] > 0) marching[s] = true;
+          } else {
+            if (clause > 0 && !(p.tf.r[clause - 1].flags & VR_TF_THRESHOLD)) clause_col[s] = clause;
+            ev[s] = EVP_HIT;
+          }
+        }
+        if (!marching[s]) {  // body of the i-loop, ray_marching.cl:53-72
+          bool next_o = false;
+          if (ev[s] == EVP_EXIT) {
+            const float factor = pi[s] == 8 ? 8.0f / 8.0f : (pi[s] == 9 ? 8.0f / 9.0f : 8.0f / 10.0f);
+            const uchar4 lm = env_sample<false>(p, dv[s]);
+            const unsigned bv0 = f2u((float)(bvp[s] & 1023u) + atten[s] * er[s] * (float)lm.x * factor / 1.0f);
+            const unsigned bv1 = f2u((float)((bvp[s] >> 10) & 1023u) + atten[s] * eg[s] * (float)lm.y * factor / 1.0f);
+            const unsigned bv2 = f2u((float)(bvp[s] >> 20) + atten[s] * eb[s] * (float)lm.z * factor / 1.0f);
+            bvp[s] = bv0 | (bv1 << 10) | (bv2 << 20);
+            next_o = true;
+          } else {
+            const bool more = pi[s] < 10;
+            if (ev[s] == EVP_HIT) {
+              er[s] *= energy(0); eg[s] *= energy(1); eb[s] *= energy(2);
+              if (more) {
+                bn = -normalize3_shared_rcp(grad);
+                o[s] = o[s] + dv[s];
+                bseed = seed[s] + po[s] + pi[s];
+                need_bounce = true;
+              }
+            }
+            ++pi[s];
+            if (more) need_start = true;
+            else next_o = true;
+          }
+          if (next_o) {
+            if (po[s] == 1) {
+              po[s] = 2; pi[s] = 8;
+              const HitRecord h2 = load_record(p.queue, rec[s]);
+              o[s] = h2.base;
+              bn = h2.normal; bseed = seed[s] + po[s];
+              need_bounce = true; reset_atten = true; need_start = true;
+            } else {
+              const unsigned bv0 = (bvp[s] & 1023u) / 2u, bv1 = ((bvp[s] >> 10) & 1023u) / 2u, bv2 = (bvp[s] >> 20) / 2u;
+              const uint32_t low = bv0 + (bv1 << 16);
+              const uint32_t high = bv2;
+              const size_t voxel = p.queue[3 * (size_t)rec[s]].z;
+              if (low) atomicAdd(p.cache + 2 * voxel, low);
+              if (high) atomicAdd(p.cache + 2 * voxel + 1, high);
+              mode[s] = M_IDLE;
+            }
+          }
+        }
+      }
+
+      // ---- refill free slots from the queue ------------------------------------------------------------------------------
+      for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, mode[s] == M_IDLE);
+        if (!idle || exhausted) break;
+        {
+          unsigned first = 0;
+          if (lane == 0) first = atomicAdd(work_counter, (unsigned)__popc(idle));
+          first = __shfl_sync(0xffffffffu, first, 0);
+          exhausted = first + (unsigned)__popc(idle) >= total;
+          const unsigned idx = first + (unsigned)__popc(idle & lt_mask);
+          bool take = mode[s] == M_IDLE && idx < total;
+          HitRecord h;
+          if (take) {
+            unsigned f;
+            if (p.nframes_shift >= 0) {
+              rec[s] = idx >> p.nframes_shift;
+              f = idx & ((1u << p.nframes_shift) - 1u);
+            } else if (p.pixel_major) {
+              const unsigned pb = (unsigned)p.pixel_major, gsz = pb * (unsigned)p.nframes;
+              const unsigned grp = idx / gsz, within = idx - grp * gsz;
+              f = within / pb;
+              rec[s] = grp * pb + (within - f * pb);
+            } else { f = idx / records; rec[s] = idx - f * records; }
+            if (rec[s] >= records) take = false;
+            else {
+              h = load_record(p.queue, rec[s]);
+              h.seed = p.seeds[f];
+              uint32_t* hi = p.cache + 2 * (size_t)h.voxel + 1;
+              const int w = (int)(short)(__ldcv(hi) >> 16);
+              take = false;
+              if (!((unsigned)w > (unsigned)p.token_cap)) {
+                const int t = (int)atomicAdd(hi, 0x00010000u);
+                if ((unsigned)(t >> 16) < (unsigned)p.token_cap) take = true;
+                else atomicSub(hi, 0x00010000u);
+              }
+            }
+          }
+          if (take) {
+            xyp[s] = (unsigned)((h.xy & 0xFFFF) + 1) * (unsigned)((h.xy >> 16) + 1);
+            seed[s] = h.seed; clause_col[s] = h.clause;
+            er[s] = energy(0); eg[s] = energy(1); eb[s] = energy(2);
+            bvp[s] = 0;
+            po[s] = 1; pi[s] = 8;
+            o[s] = h.base;
+            bn = h.normal; bseed = seed[s] + po[s];
+            need_bounce = true; reset_atten = true; need_start = true;
+            mode[s] = M_SECOND;
+          }
+        }
+        if (__popc(__ballot_sync(0xffffffffu, mode[s] == M_IDLE)) < 16) break;
+      }
+
+      // ---- the one bounce site + first half of march() -------------------------------------------------------------------------
+      if (need_bounce) {
+        dv[s] = hemisphere_reflective_p(bn, bseed, energy(3), xyp[s]);
+        o[s] = o[s] + bn * 2.0f;
+        const float a = fabsf(dot3(dv[s], bn));
+        atten[s] = reset_atten ? a : atten[s] * a;
+      }
+      if (need_start) {
+        d[s] = surf3Dread<signed char>(p.sdf_surf, f2i(o[s].x), f2i(o[s].y), f2i(o[s].z), cudaBoundaryModeZero);
+        steps_left[s] = 70;
+        marching[s] = true;
+        ev[s] = EVP_NONE;
+      }
+    }
+    if (!__ballot_sync(0xffffffffu, mode[0] != M_IDLE || mode[1] != M_IDLE)) break;  // queue empty and every slot free
+
+    // ---- step loop: both slots' gathers are issued back to back ------------------------------------------------------------------
+    for (;;) {
+      for (int u = 0; u < p.spc; ++u) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          if (!marching[s]) continue;
+          const float step_size = max_cl(small_int_to_float(d[s]), 0.5f);
+          o[s] = o[s] + step_size * dv[s];
+          steps_left[s]--;
+          float fx, fy, fz;
+          const int vx = floor_pair(o[s].x, &fx), vy = floor_pair(o[s].y, &fy), vz = floor_pair(o[s].z, &fz);
+          d[s] = surf3Dread<signed char>(p.sdf_surf, vx, vy, vz, cudaBoundaryModeZero);
+          marching[s] = (d[s] > 0) & (steps_left[s] != 0);
+          unclassified[s] = true;
+        }
+      }
+      const int act = __popc(__ballot_sync(0xffffffffu, marching[0])) + __popc(__ballot_sync(0xffffffffu, marching[1]));
+      if (!act) break;
+      const int waiting = __popc(__ballot_sync(0xffffffffu, !marching[0] && (mode[0] != M_IDLE || !exhausted))) +
+                          __popc(__ballot_sync(0xffffffffu, !marching[1] && (mode[1] != M_IDLE || !exhausted)));
+      if (act * p.rule_a < waiting * p.rule_b) break;
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (unclassified[s] && !marching[s]) {  // exited_volume and the SDF-sign event test, once per segment
+        const bool exited = (o[s].x < 0.0f) | (o[s].y < 0.0f) | (o[s].z < 0.0f) | (p.fnx < o[s].x) | (p.fny < o[s].y) | (p.fnz < o[s].z);
+        ev[s] = d[s] > 0 ? EVP_NONE : (exited ? EVP_EXIT : (d[s] < 0 ? EVP_SDF_NEG : EVP_FARFACE));
+        unclassified[s] = false;
+      }
+  }
+}
+template <int CTAS>
+static int launch_pt2(vr_ctx* ctx, const RenderParams& p, unsigned* work_counter) {
+  static int per_sm = 0;
+  if (!per_sm) VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_pt2<CTAS>, 128, 0));
+  const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)std::max(1, per_sm);
+  k_trace_pt2<CTAS><<<blocks, 128, 0, ctx->stream>>>(p, work_counter);
+  ctx->launches++;
+  return VR_OK;
+}
+#endif
+
+#ifdef VR_AB
 // ---- k_trace_sm: the same secondary paths with the slots in SHARED memory and every kind of work packed -------------------------
 // k_trace_pt keeps a sample in one lane for its whole life, so a lane whose segment ended is dead weight in the step loop until
 // the warp leaves it, and event processing runs with whatever lanes happen to wait (ncu: 15-20 of 32 lanes active in the step
@@ -1351,6 +1564,16 @@ static int launch_pt_select(vr_renderer* r, const RenderParams& p, unsigned* wc)
     return launch_pt<COUNT, REUSE, 12, true, true>(ctx, p, wc);  // measured 8 / 10 / 12 CTAs per SM: 3.15 / 3.10 / 2.91 ms per step
   }
   const bool surf = REUSE && !COUNT && r->sdf->surf != 0 && r->tune.surf;  // the surface-object gather serves the production schedule
+#ifdef VR_AB
+  if (surf && r->tune.pt_slots == 2) {
+    switch (r->tune.pt2_ctas) {
+      case 6: return launch_pt2<6>(ctx, p, wc);
+      case 7: return launch_pt2<7>(ctx, p, wc);
+      case 10: return launch_pt2<10>(ctx, p, wc);
+      default: return launch_pt2<8>(ctx, p, wc);
+    }
+  }
+#endif
 #ifdef VR_AB
   if (REUSE && !COUNT) {
     const int c = r->tune.pt_ctas;
