@@ -114,6 +114,8 @@ int vr_envmap_bind(vr_ctx* ctx, const uint8_t* rgba8, int w, int h, vr_envmap** 
 void vr_envmap_destroy(vr_envmap* env);
 
 /* ---- signed_distance_field (app/signed_distance_field.cpp:7-35 + signed_distance_field.cl) ---------- */
+/* Scratch during the build: one bit per voxel and level, (max_it - 1) * nx*ny*nz / 8 bytes (2 GiB at 512^3), from the context's
+ * stream-ordered pool and returned to it; if that allocation fails the build uses two bit volumes + level planes instead. */
 int vr_sdf_build(vr_ctx* ctx, const vr_volume* vol, const vr_tf_rect* rects, int n_rects, vr_sdf** out);
 void vr_sdf_destroy(vr_sdf* sdf);
 /* x-fastest int8, same order as clw_image<char>::pull() (tests/sdf/sdf_test.cpp:24-31) */
