@@ -295,6 +295,7 @@ extern "C" int vr_volume_set_sampling(vr_volume* v, int mode) {
   if (mode == v->sampling) return VR_OK;
   VR_CUDA(cudaSetDevice(v->ctx->device));
   if (mode == VR_SAMPLING_HW_LINEAR) {
+    v->raw_range[0] = v->stats[0]; v->raw_range[1] = v->stats[1];  // the NEAREST extremes: clip and filter can only narrow them
     VR_TRY(volume_build_textures(v));
     int st = vrk_fetch_stats_linear(v->ctx, v->box, v->box_px, v->current(), v->nx, v->ny, v->nz, v->stats, v->zlo, v->zhi);
     if (st != VR_OK) { volume_release_textures(v); return st; }
@@ -412,7 +413,7 @@ extern "C" int vr_histogram(const vr_volume* v, int width, int height, const flo
   VR_CUDA(pool_alloc(v->ctx, &bins, bytes));
   int s = v->sampling == VR_SAMPLING_HW_LINEAR
               ? vrk_histogram_linear(v->ctx, v->box, v->box_px, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi,
-                                     v->stats[0])
+                                     v->stats[0], v->raw_range[0], v->raw_range[1])
               : vrk_histogram(v->ctx, v->current(), v->nx, v->ny, v->nz, width, height, range, bins, v->zlo, v->zhi, v->stats[0], v->stats[1]);
   if (s == VR_OK) {
     cudaError_t e = cudaMemcpyAsync(bins_out, bins, bytes, cudaMemcpyDeviceToHost, v->ctx->stream);
@@ -1145,7 +1146,7 @@ extern "C" int vr_render_tf(vr_renderer* r, int width, int height, uint8_t* rgba
   if (status == VR_OK)
     status = r->vol->sampling == VR_SAMPLING_HW_LINEAR
                  ? vrk_histogram_linear(ctx, r->vol->box, r->vol->box_px, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height,
-                                        range, bins, r->vol->zlo, r->vol->zhi, r->vol->stats[0])
+                                        range, bins, r->vol->zlo, r->vol->zhi, r->vol->stats[0], r->vol->raw_range[0], r->vol->raw_range[1])
                  : vrk_histogram(ctx, r->vol->current(), r->vol->nx, r->vol->ny, r->vol->nz, width, height, range, bins, r->vol->zlo,
                                  r->vol->zhi, r->vol->stats[0], r->vol->stats[1]);
   // renderer.cpp:65-96 without the host round trip: rounding, distinct-value ranking and colouring stay on the device

@@ -72,6 +72,7 @@ struct vr_volume {
   int16_t* cropped = nullptr;  // device, non-null once clipped (reference_volume.hpp:31-33)
   int nx = 0, ny = 0, nz = 0;  // dims of the current volume
   int32_t stats[4] = {0, 0, 0, 0};
+  int32_t raw_range[2] = {0, -1};  // min / max of the voxel values as last measured under NEAREST (bounds the box-averaged copy); max < min: unknown
   // vr_volume_upload_async: copy + stats are in flight on ctx->copy_stream until `ready`; every API call that uses the
   // volume finishes the upload first (volume_finish in vr_api.cu)
   cudaEvent_t ready = nullptr;
@@ -267,7 +268,7 @@ int vrk_boxavg(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int16_t*
 int vrk_fetch_stats_linear(vr_ctx* ctx, const int16_t* box, int px, const int16_t* vol, int nx, int ny, int nz, int32_t out[4], int zlo,
                            int zhi);
 int vrk_histogram_linear(vr_ctx* ctx, const int16_t* box, int px, const int16_t* vol, int nx, int ny, int nz, int width, int height,
-                         const float range[4], uint32_t* bins_dev, int zlo, int zhi, int vol_min_value);
+                         const float range[4], uint32_t* bins_dev, int zlo, int zhi, int vol_min_value, int raw_min = 0, int raw_max = -1);
 int vrk_bilateral_linear(vr_ctx* ctx, const int16_t* box, int px, int nx, int ny, int nz, int16_t* dst);
 // 2d_image_filter.cl: src != dst, both w*h RGBA8 on the device
 int vrk_filter2d(vr_ctx* ctx, const uchar4* src, uchar4* dst, int w, int h, int kernel_size, float sigma, int mode);

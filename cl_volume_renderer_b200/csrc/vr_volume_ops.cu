@@ -655,8 +655,12 @@ __global__ void __launch_bounds__(256) k_hist_tables(HistArgs a, short* __restri
 #define HBY 64
 #define HZC 16       // planes per work item
 #define HWBINS 45056 // window bins (176 KiB)
-__global__ void __launch_bounds__(SX* HBY, 1) k_histogram_lut(VolView vol, uint32_t* __restrict__ bins, HistArgs a, int zlo, int zhi, int wx0,
-                                                              int wy0, int wc, int wr, const short* __restrict__ g_tables) {
+// LINEAR: `vol` is the box-averaged volume (its apron rows / columns / planes are gradient neighbours only), `orig` the volume
+// itself: voxels x < lim_x, y < lim_y count, and the value read on the three low faces is box_edge's (see k_boxavg).
+template <bool LINEAR>
+__global__ void __launch_bounds__(SX* HBY, 1) k_histogram_lut(VolView vol, VolView orig, int lim_x, int lim_y, uint32_t* __restrict__ bins,
+                                                              HistArgs a, int zlo, int zhi, int wx0, int wy0, int wc, int wr,
+                                                              const short* __restrict__ g_tables) {
   extern __shared__ unsigned hsm[];
   unsigned* win = hsm;                                     // wc x wr window of the bin grid
   short* pxl = reinterpret_cast<short*>(hsm + HWBINS);     // HPX | HP1 | HP2, as k_hist_tables wrote them
@@ -667,7 +671,7 @@ __global__ void __launch_bounds__(SX* HBY, 1) k_histogram_lut(VolView vol, uint3
   for (int i = tid; i < wbins; i += SX * HBY) win[i] = 0;
   for (int i = tid; i < (HPX + HP1 + HP2) / 2; i += SX * HBY) reinterpret_cast<unsigned*>(pxl)[i] = reinterpret_cast<const unsigned*>(g_tables)[i];
   __syncthreads();
-  const unsigned tx = div_up_dev(vol.nx, SX * 8), ty = div_up_dev(vol.ny, HBY), tz = div_up_dev(zhi - zlo, HZC);
+  const unsigned tx = div_up_dev(lim_x, SX * 8), ty = div_up_dev(lim_y, HBY), tz = div_up_dev(zhi - zlo, HZC);
   const uint4 zero = make_uint4(0, 0, 0, 0);
   const size_t sy = vol.nx, sz = (size_t)vol.nx * vol.ny;
   const unsigned lane = tid & 31;  // a warp = 16 octets of row y and 16 of row y+1
@@ -676,7 +680,8 @@ __global__ void __launch_bounds__(SX* HBY, 1) k_histogram_lut(VolView vol, uint3
     const int x0 = (int)(((t % tx) * SX + threadIdx.x) * 8);
     const int y = (int)(((t / tx) % ty) * HBY + threadIdx.y);
     const int z0 = zlo + (int)(t / (tx * ty)) * HZC, z1 = min(z0 + HZC, zhi);
-    const bool in = x0 < vol.nx && y < vol.ny;
+    const bool in = x0 < vol.nx && y < vol.ny;     // the octet exists (is loaded: its edge voxels are other lanes' neighbours)
+    const bool cnt = x0 < lim_x && y < lim_y;      // ... and (some of) its voxels are counted
     const size_t col = (size_t)y * vol.nx + x0;
     int pm[8], pc[8];  // planes z-1 and z of this octet, unpacked
     {
@@ -706,8 +711,10 @@ __global__ void __launch_bounds__(SX* HBY, 1) k_histogram_lut(VolView vol, uint3
         const int dy = (int)(short)(wyp[k >> 1] >> sh) - (int)(short)(wym[k >> 1] >> sh);
         const int dz = pp[k] - pm[k];
         const unsigned S = (unsigned)(dx * dx) + (unsigned)(dy * dy) + (unsigned)(dz * dz);
-        const unsigned vi = (unsigned)(pc[k] - a.vmin);
-        const int px = vi < (unsigned)a.nval ? (int)pxl[vi] : hist_px(a, pc[k]);
+        int value = pc[k];
+        if (LINEAR && (y == 0 || z == 0 || x0 + k == 0) && cnt && x0 + k < lim_x) value = box_edge(orig, x0 + k, y, z);
+        const unsigned vi = (unsigned)(value - a.vmin);
+        const int px = vi < (unsigned)a.nval ? (int)pxl[vi] : hist_px(a, value);
         int py;
         if (S < HP1) py = pyl1[S];
         else {
@@ -717,14 +724,15 @@ __global__ void __launch_bounds__(SX* HBY, 1) k_histogram_lut(VolView vol, uint3
         // inside the window (columns wx0 .. wx0 + wc - 1 lie inside the grid, so with py < height the bin does too; the markers
         // are large negative numbers and fail the unsigned tests): no 64-bit bin number needed
         const unsigned wx = (unsigned)(px - wx0), wy = (unsigned)(py - wy0);
-        const int w = (in && wx < (unsigned)wc && wy < (unsigned)wr && py < a.height) ? (int)(wx * (unsigned)wr + wy) : -1;
+        const bool counted = cnt && (!LINEAR || x0 + k < lim_x);
+        const int w = (counted && wx < (unsigned)wc && wy < (unsigned)wr && py < a.height) ? (int)(wx * (unsigned)wr + wy) : -1;
         int same;
         __match_all_sync(0xffffffffu, w, &same);
         if (same && w >= 0) {
           if (lane == 0) atomicAdd(&win[w], 32u);
         } else if (w >= 0) {
           atomicAdd(&win[w], 1u);
-        } else if (in && px != HSKIP && py != HSKIP) {
+        } else if (counted && px != HSKIP && py != HSKIP) {
           const long long flat = (long long)px * a.height + py;
           if (flat >= 0 && flat < nbins) atomicAdd(bins + flat, 1u);
         }
@@ -740,6 +748,43 @@ __global__ void __launch_bounds__(SX* HBY, 1) k_histogram_lut(VolView vol, uint3
   }
 }
 
+// the table path of tf_sort_values, if its guards hold: every difference of two voxels (or a voxel and a border zero) below 4096,
+// no counted gradient above 4095, and every column / row number the expressions can produce within 16 bits.  [vmin, vmax] must
+// bound every value `vol` holds.  Returns false when the caller has to use k_histogram_v8.
+template <bool LINEAR>
+static bool hist_tables_launch(vr_ctx* ctx, const VolView& vol, const VolView& orig, int nx, int ny, int nz, int width, int height,
+                               const float range[4], uint32_t* bins_dev, int zlo, int zhi, int vmin, int vmax, int wx0, int wy0) {
+  const float vr = range[1] - range[0], gr = range[3] - range[2];
+  const long long span = (long long)std::max(vmax, 0) - (long long)std::min(vmin, 0);
+  if (!(vmax >= vmin && span < 4096 && range[3] < 4096.0f && zhi > zlo && vr > 0.0f && gr > 0.0f)) return false;
+  const float px_lo = ((float)vmin - range[0]) / vr * (float)width, px_hi = ((float)vmax - range[0]) / vr * (float)width;
+  const float py_lo = (0.0f - range[2]) / gr * (float)height, py_hi = (range[3] - range[2]) / gr * (float)height;
+  if (!(fabsf(px_lo) < 32000.0f && fabsf(px_hi) < 32000.0f && fabsf(py_lo) < 32000.0f && fabsf(py_hi) < 32000.0f)) return false;
+  HistArgs a{width, height, range[0], range[1], range[2], range[3], vmin, std::min(vmax - vmin + 1, HPX)};
+  short* tables = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&tables), (HPX + HP1 + HP2) * sizeof(short), ctx->stream) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  k_hist_tables<<<(HPX + HP1 + HP2) / 256, 256, 0, ctx->stream>>>(a, tables, tables + HPX, tables + HPX + HP1);
+  const size_t smem = (size_t)HWBINS * 4 + (size_t)(HPX + HP1 + HP2) * 2;
+  // per device (a host may drive several GPUs from one process): set on every call, it is cheap
+  cudaFuncSetAttribute(k_histogram_lut<LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // window: the columns the data's values span (as many as leave 16 rows), then as many rows as fit
+  const float top_v = std::min((float)vmax, range[1]);
+  const int c_hi = std::max(0, std::min(width - 1, (int)roundf((top_v - range[0]) / vr * (float)width)));
+  const int ncols = std::max(1, c_hi - wx0 + 1);
+  const int wr = std::max(16, std::min(height - wy0, HWBINS / ncols));
+  const int wc = std::max(1, std::min(ncols, HWBINS / wr));
+  const int zh = std::min(zhi, nz);
+  const size_t items = (size_t)div_up(nx, SX * 8) * div_up(ny, HBY) * div_up(zh - zlo, HZC);
+  k_histogram_lut<LINEAR><<<(unsigned)std::min<size_t>(items, (size_t)ctx->sm_count), dim3(SX, HBY, 1), smem, ctx->stream>>>(
+      vol, orig, nx, ny, bins_dev, a, zlo, zh, wx0, wy0, wc, wr, tables);
+  ctx->launches += 2;
+  cudaFreeAsync(tables, ctx->stream);
+  return true;
+}
+
 int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int width, int height, const float range[4],
                   uint32_t* bins_dev, int zlo, int zhi, int vol_min_value, int vol_max_value) {
   VR_CUDA(cudaMemsetAsync(bins_dev, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
@@ -750,36 +795,9 @@ int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int w
     int wx0 = 0, wy0 = 0;
     if (vr > 0.0f) wx0 = std::max(0, std::min(width - 1, (int)roundf(((float)vol_min_value - range[0]) / vr * (float)width)));
     if (gr > 0.0f) wy0 = std::max(0, std::min(height - 1, (int)roundf((0.0f - range[2]) / gr * (float)height)));
-    // table path: every difference of two voxels (or a voxel and a border zero) below 4096, no counted gradient above 4095, and
-    // every column / row number the expressions can produce within 16 bits
-    const long long span = (long long)std::max(vol_max_value, 0) - (long long)std::min(vol_min_value, 0);
-    bool tables_ok = vol_max_value >= vol_min_value && span < 4096 && range[3] < 4096.0f && zhi > zlo && vr > 0.0f && gr > 0.0f;
-    if (tables_ok) {
-      const float px_lo = ((float)vol_min_value - range[0]) / vr * (float)width, px_hi = ((float)vol_max_value - range[0]) / vr * (float)width;
-      const float py_lo = (0.0f - range[2]) / gr * (float)height, py_hi = (range[3] - range[2]) / gr * (float)height;
-      tables_ok = fabsf(px_lo) < 32000.0f && fabsf(px_hi) < 32000.0f && fabsf(py_lo) < 32000.0f && fabsf(py_hi) < 32000.0f;
-    }
-    if (tables_ok) {
-      HistArgs a{width, height, range[0], range[1], range[2], range[3], vol_min_value, std::min(vol_max_value - vol_min_value + 1, HPX)};
-      short* tables = nullptr;
-      VR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tables), (HPX + HP1 + HP2) * sizeof(short), ctx->stream));
-      k_hist_tables<<<(HPX + HP1 + HP2) / 256, 256, 0, ctx->stream>>>(a, tables, tables + HPX, tables + HPX + HP1);
-      const size_t smem = (size_t)HWBINS * 4 + (size_t)(HPX + HP1 + HP2) * 2;
-      // per device (a host may drive several GPUs from one process): set on every call, it is cheap
-      VR_CUDA(cudaFuncSetAttribute(k_histogram_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      // window: the columns the data's values span (as many as leave 16 rows), then as many rows as fit
-      const float top_v = std::min((float)vol_max_value, range[1]);
-      const int c_hi = std::max(0, std::min(width - 1, (int)roundf((top_v - range[0]) / vr * (float)width)));
-      const int ncols = std::max(1, c_hi - wx0 + 1);
-      const int wr = std::max(16, std::min(height - wy0, HWBINS / ncols));
-      const int wc = std::max(1, std::min(ncols, HWBINS / wr));
-      const int zh = std::min(zhi, nz);
-      const size_t items = (size_t)div_up(nx, SX * 8) * div_up(ny, HBY) * div_up(zh - zlo, HZC);
-      k_histogram_lut<<<(unsigned)std::min<size_t>(items, (size_t)ctx->sm_count), dim3(SX, HBY, 1), smem, ctx->stream>>>(
-          v, bins_dev, a, zlo, zh, wx0, wy0, wc, wr, tables);
-      ctx->launches += 2;
+    if (hist_tables_launch<false>(ctx, v, v, nx, ny, nz, width, height, range, bins_dev, zlo, zhi, vol_min_value, vol_max_value, wx0, wy0))
+    {
       VR_CUDA(cudaGetLastError());
-      VR_CUDA(cudaFreeAsync(tables, ctx->stream));
       return VR_OK;
     }
     const size_t tiles = (size_t)div_up(nx, VX * 8) * div_up(ny, VY) * div_up(nz, VZ);
@@ -795,8 +813,10 @@ int vrk_histogram(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, int w
   return VR_OK;
 }
 
+// raw_min / raw_max: bounds of the values of the volume the box average was built from (every box value, apron included, is a
+// rounded mean of such values and border zeros, hence inside [min(raw_min, 0), max(raw_max, 0)]); raw_max < raw_min: unknown
 int vrk_histogram_linear(vr_ctx* ctx, const int16_t* box, int px, const int16_t* vol, int nx, int ny, int nz, int width, int height,
-                         const float range[4], uint32_t* bins_dev, int zlo, int zhi, int vol_min_value) {
+                         const float range[4], uint32_t* bins_dev, int zlo, int zhi, int vol_min_value, int raw_min, int raw_max) {
   VR_CUDA(cudaMemsetAsync(bins_dev, 0, sizeof(uint32_t) * (size_t)width * height, ctx->stream));
   VolView b{box, px, ny + 1, nz + 1}, v{vol, nx, ny, nz};
   const size_t tiles = (size_t)div_up(nx, VX * 8) * div_up(ny, VY) * div_up(nz, VZ);
@@ -805,6 +825,12 @@ int vrk_histogram_linear(vr_ctx* ctx, const int16_t* box, int px, const int16_t*
   int wx0 = 0, wy0 = 0;
   if (vr > 0.0f) wx0 = std::max(0, std::min(width - 1, (int)roundf(((float)vol_min_value - range[0]) / vr * (float)width)));
   if (gr > 0.0f) wy0 = std::max(0, std::min(height - 1, (int)roundf((0.0f - range[2]) / gr * (float)height)));
+  if (raw_max >= raw_min &&
+      hist_tables_launch<true>(ctx, b, v, nx, ny, nz, width, height, range, bins_dev, zlo, zhi, std::min(raw_min, 0), std::max(raw_max, 0), wx0, wy0))
+  {
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+  }
   k_histogram_v8<true><<<grid, block, 0, ctx->stream>>>(b, v, nx, ny, bins_dev, width, height, range[0], range[1], range[2], range[3], zlo,
                                                         std::min(zhi, nz), wx0, wy0);
   ctx->launches++;

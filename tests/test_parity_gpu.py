@@ -710,6 +710,15 @@ def test_volume_kernels_hw_linear_match_oracle_model(vr_ctx):
     assert vol.stats() != near_stats
     rng = [float(x) for x in near_stats]
     assert np.array_equal(vol.histogram(500, 500, rng), o.histogram_shipped(v, 1, 500, 500, rng))
+    # the table path under this reading (k_histogram_lut<LINEAR>): clipped ranges, a coarse grid, rows below gradient 0
+    for (w, h, r2) in [(64, 64, [-2000.0, 3000.0, 0.0, 4000.0]), (31, 17, [0.0, 100.0, 5.0, 50.0]), (100, 300, [200.0, 1200.0, 20.0, 900.0])]:
+        assert np.array_equal(vol.histogram(w, h, r2), o.histogram_shipped(v, 1, w, h, r2)), (w, h, r2)
+    v8 = synth.synth_ct(3, dims=(64, 24, 20))   # rows of whole octets: the last octet of a row ends at the volume's face
+    vol8 = api.Volume(vr_ctx, v8)
+    st8 = [float(x) for x in vol8.stats()]
+    vol8.set_sampling(api.VR_SAMPLING_HW_LINEAR)
+    assert np.array_equal(vol8.histogram(256, 128, st8), o.histogram_shipped(v8, 1, 256, 128, st8))
+    vol8.close()
     vol.filter()
     got, want = vol.download(), o.bilateral_shipped(v)
     dd = np.abs(got.astype(np.int32) - want.astype(np.int32))
