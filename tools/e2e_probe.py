@@ -10,8 +10,9 @@ vp=torch.empty(v.shape,dtype=torch.int16,pin_memory=True); vp.numpy()[...]=v
 ep=torch.empty(e.shape,dtype=torch.uint8,pin_memory=True); ep.numpy()[...]=e
 pos,d=synth.default_camera(n); seeds=synth.glibc_rand(64); tf=api.tf_format(synth.default_tf())
 r=api.Renderer(ctx,W,H); hf=r.host_frame()
+if len(sys.argv) > 1 and sys.argv[1] == "linear": r.set_sampling(api.VR_SAMPLING_HW_LINEAR)
 cur=api.Volume(ctx,vp.numpy(),async_upload=True)
-for it in range(5):
+for it in range(6):
     T=[time.perf_counter()]
     def m(): T.append(time.perf_counter())
     en=api.EnvMap(ctx,ep.numpy()); m()
