@@ -459,7 +459,7 @@ def run_ours(args, rank, world, local_rank):
                 nxt = api.Volume(ctx, own, sharded_dims=(VOL_N, VOL_N, VOL_N), async_upload=True) if start_next else None
                 r2.image_set(v_ready, en2)
                 r2.next_event_code_set(tf_code)
-                r2.flush_changes()                                              # z-slab SDF build + gather of the field
+                r2.flush_changes()                                              # SDF build (z-slab sharded above 512^3)
                 r2.render_frames(pos, d, seeds, readback=False)
                 r2.cache_allreduce(readback=True, out=hf)
                 chk = int(hf[::97, ::89].sum())
@@ -480,7 +480,8 @@ def run_ours(args, rank, world, local_rank):
             res["what"] = ("per step (one headless job on N ranks): every rank uploads ITS z-slab of the volume from pinned host memory "
                            "(vr_volume_upload_sharded_async: the other planes arrive over NVLink; copy, gather and fetch_stats on the copy "
                            "stream and its own communicator while the previous job computes) and the env map, vr_renderer_flush builds the "
-                           "SDF z-slab-sharded (halo swaps + gather, NCCL behind the C-ABI), every rank traces its own 64 seeds, "
+                           "SDF (on every rank: at 512^3 a level is one wave of thread blocks and z-slabs would only add halo swaps and a "
+                           "gather — the library shards the build above that size, as the c4 / c5 legs do), every rank traces its own 64 seeds, "
                            "vr_cache_allreduce sums the touched cache entries and every rank reads the resolved frame back; every job's "
                            "H2D and D2H are inside the timed region")
         res.update({"unit": "Msamples/s", "d2h_bytes_per_step": int(W * H * 4), "steps": nsteps})

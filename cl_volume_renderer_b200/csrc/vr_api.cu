@@ -817,7 +817,9 @@ extern "C" int vr_renderer_flush(vr_renderer* r) {
   r->tf_active = r->tf_pending;                                  // renderer.cpp:39
   if (!keep_field) {
     vr_sdf* fresh = nullptr;                                     // renderer.cpp:42
-    int st = sdf_build_impl(ctx, r->vol, r->tf_active, &fresh, r->sharded_build ? 1 : 0);
+    // z-slab sharded only where slabs pay: a volume whose levels are a single wave of CTAs is built on every rank (no collectives)
+    const bool slabs = r->sharded_build && !vrk_sdf_single_wave(ctx, r->vol->nx, r->vol->ny, r->vol->nz);
+    int st = sdf_build_impl(ctx, r->vol, r->tf_active, &fresh, slabs ? 1 : 0);
     if (forked) VR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // later work on the compute stream sees the reset cache
     forked = false;
     VR_TRY(st);

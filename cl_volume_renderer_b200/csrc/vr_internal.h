@@ -226,6 +226,7 @@ int vrk_sdf_slab_level(const vr_sdf_slab* s);
 bool vrk_sdf_slab_finished(const vr_sdf_slab* s);
 int vrk_sdf_slab_assemble(vr_sdf_slab* s, int8_t* field, cudaSurfaceObject_t surf = 0);
 int vrk_sdf_slab_status(vr_sdf_slab* s);
+bool vrk_sdf_single_wave(const vr_ctx* ctx, int nx, int ny, int nz);
 void vrk_sdf_slab_destroy(vr_sdf_slab* s);
 int vrk_tf_image(vr_ctx* ctx, int32_t* bins_dev, int* scratch_dev, int width, int height, uchar4* out_dev);
 // surf != 0: the field is also written into that surface (the production schedule does it in its assembly pass)

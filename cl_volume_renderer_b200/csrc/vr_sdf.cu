@@ -1097,6 +1097,17 @@ int vrk_sdf_build_variant(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int n
                           int* max_it_out);  // vr_sdf_variants.cu: the schedules tried on the way, linked into the A/B build only
 #endif
 
+// Is a build of this size in the regime where a level is a single wave of CTAs (vrk_sdf_slab_create's criterion)?  There a level
+// costs the serial chain of one warp through its tile whatever the number of planes, so z-slabs on several GPUs buy nothing
+// (512^3: 1.61 ms on one GPU, 1.73 ms on 8) and only add the halo swaps and the gather; above it they pay (1024^3: 13.6 -> 5.7 ms).
+bool vrk_sdf_single_wave(const vr_ctx* ctx, int nx, int ny, int nz) {
+  const int nxw = (nx + 31) / 32;
+  if (nxw % 4 != 0) return (size_t)nx * ny * nz <= ((size_t)1 << 27);  // the two-volume kernel: same order of magnitude
+  const int xl = (nxw / 4 > 4) ? 8 : 4;
+  const size_t tiles48 = (size_t)div_up(nxw / 4, xl) * div_up(ny, (32 / xl) * 4) * div_up(nz, 8);
+  return tiles48 <= (size_t)ctx->sm_count * 8;
+}
+
 int vrk_sdf_build(vr_ctx* ctx, const int16_t* vol, int nx, int ny, int nz, const TfTable& tf, int8_t* field, int* levels_out,
                   int* max_it_out, cudaSurfaceObject_t surf) {
 #ifdef VR_AB

@@ -264,7 +264,9 @@ int vr_volume_upload_sharded(vr_ctx* ctx, const int16_t* own_planes, int nx, int
 int vr_volume_upload_sharded_async(vr_ctx* ctx, const int16_t* own_planes, int nx, int ny, int nz, vr_volume** out);
 /* z-slab SDF build (BASELINE config 5): every rank runs the wavefront on its slab + 16 halo planes, swaps the boundary planes
  * of the bit volume with its z-neighbours every 14 levels and gathers the field; bit-identical to vr_sdf_build.  `vol` is the
- * whole volume (replicated).  vr_renderer_set_sharded_build makes vr_renderer_flush build its SDF this way. */
+ * whole volume (replicated).  vr_renderer_set_sharded_build lets vr_renderer_flush build its SDF this way where slabs pay: a
+ * volume whose levels are a single wave of thread blocks (up to 512^3 on a B200) costs the same per level however thin the slab,
+ * so it is built on every rank without any collective; larger volumes are built in slabs (1024^3: 13.6 -> 5.7 ms on 8 GPUs). */
 int vr_sdf_build_sharded(vr_ctx* ctx, const vr_volume* vol, const vr_tf_rect* rects, int n_rects, vr_sdf** out);
 int vr_renderer_set_sharded_build(vr_renderer* r, int enable);
 /* the same build without the final gather: only the planes vr_comm_slab assigns to this rank are valid in the result (a consumer
